@@ -1,0 +1,309 @@
+"""ctypes front-ends for the two CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+* ``oracle.port``  -- oracle/plm_oracle.c, the plain-C restatement (``_ref/libploracle.so``)
+* ``oracle.ref``   -- the reference itself, /root/reference/stvo-pl/src/{matching,gridStructure,
+  lineIterator}.cpp compiled unmodified (``_ref/libplref.so``; see oracle/Makefile)
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU arms may import this package; the
+product (pl_inertial_slam_b200) never does.  Nothing here reads /root/reference at run time: the
+GPU box only has the prebuilt ``_ref/*.so`` files.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_DIR = os.path.join(_HERE, "_ref")
+REFERENCE_ROOT = "/root/reference"
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+def build(verbose: bool = False) -> None:
+    """Compile the C restatement and, when /root/reference is present, the reference itself."""
+    targets = ["oracle"]
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "stvo-pl", "src")):
+        targets.append("ref")
+    out = subprocess.run(["make", "-C", _HERE] + targets, capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def _load(name: str):
+    path = os.path.join(_REF_DIR, name)
+    if not os.path.exists(path):
+        build()
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    return C.CDLL(path)
+
+
+def _desc(a: np.ndarray):
+    """(pointer, rows, step) for an n x 32 uint8 matrix whose rows are contiguous."""
+    assert a.dtype == np.uint8 and a.ndim == 2 and a.shape[1] == 32, (a.dtype, a.shape)
+    assert a.strides[1] == 1
+    return a.ctypes.data_as(_u8p), int(a.shape[0]), C.c_size_t(a.strides[0] if a.shape[0] > 1 else 32)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_i32p)
+
+
+class _Port:
+    """oracle/plm_oracle.c"""
+
+    def __init__(self):
+        self._lib = None
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            L = _load("libploracle.so")
+            L.plo_hamming256.restype = C.c_int
+            L.plo_hamming256.argtypes = [_u8p, _u8p]
+            L.plo_knn2.restype = None
+            L.plo_knn2.argtypes = [_u8p, C.c_int, C.c_size_t, _u8p, C.c_int, C.c_size_t, _i32p, _i32p]
+            L.plo_match_nnr.restype = C.c_int
+            L.plo_match_nnr.argtypes = [_u8p, C.c_int, C.c_size_t, _u8p, C.c_int, C.c_size_t, C.c_float, _i32p]
+            L.plo_match.restype = C.c_int
+            L.plo_match.argtypes = [_u8p, C.c_int, C.c_size_t, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_int, _i32p]
+            L.plo_line_coords.restype = C.c_int
+            L.plo_line_coords.argtypes = [C.c_double] * 4 + [_i32p, C.c_int]
+            L.plo_match_grid_points.restype = C.c_int
+            L.plo_match_grid_points.argtypes = [_i32p, _u8p, C.c_int, C.c_size_t, _i32p, _i32p, C.c_int, C.c_int,
+                                                _u8p, C.c_int, C.c_size_t, _i32p, C.c_double, C.c_int, _i32p]
+            L.plo_match_grid_lines.restype = C.c_int
+            L.plo_match_grid_lines.argtypes = [_i32p, _u8p, C.c_int, C.c_size_t, _i32p, _i32p, C.c_int, C.c_int,
+                                               _u8p, C.c_int, C.c_size_t, _f64p, C.c_double, _i32p, C.c_double,
+                                               C.c_int, _i32p]
+            L.plo_stereo_filter_points.restype = C.c_int
+            L.plo_stereo_filter_points.argtypes = [_f32p, _f32p, _i32p, C.c_int, C.c_double, C.c_double, _u8p, _f64p]
+            L.plo_stereo_filter_lines.restype = C.c_int
+            L.plo_stereo_filter_lines.argtypes = [_f32p, _f32p, _i32p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                                  C.c_double, _u8p, _f64p]
+            L.plo_line_overlap_stereo.restype = C.c_double
+            L.plo_line_overlap_stereo.argtypes = [C.c_double] * 5
+            self._lib = L
+        return self._lib
+
+    def distance(self, a, b) -> int:
+        a = np.ascontiguousarray(a, np.uint8).reshape(32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(32)
+        return self.lib.plo_hamming256(a.ctypes.data_as(_u8p), b.ctypes.data_as(_u8p))
+
+    def knn2(self, d1, d2):
+        """-> (idx n1x2 int32, dist n1x2 int32); absent slots are (-1, INT_MAX)."""
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        idx = np.empty((n1, 2), np.int32)
+        dist = np.empty((n1, 2), np.int32)
+        self.lib.plo_knn2(p1, n1, s1, p2, n2, s2, idx.ctypes.data_as(_i32p), dist.ctypes.data_as(_i32p))
+        return idx, dist
+
+    def knn2_packed(self, d1, d2, idx_base: int = 0) -> np.ndarray:
+        """Packed (dist << 32 | idx) uint64 keys, n1 x 2, UINT64_MAX where absent."""
+        idx, dist = self.knn2(d1, d2)
+        key = (dist.astype(np.uint64) << np.uint64(32)) | (idx.astype(np.int64) + idx_base).astype(np.uint64)
+        key[idx < 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        return key
+
+    def match_nnr(self, d1, d2, nnr, m12=None):
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        m12 = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = self.lib.plo_match_nnr(p1, n1, s1, p2, n2, s2, C.c_float(nnr), m12.ctypes.data_as(_i32p))
+        return n, m12
+
+    def match(self, d1, d2, nnr, best_lr=True, m12=None):
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        m12 = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = self.lib.plo_match(p1, n1, s1, p2, n2, s2, C.c_float(nnr), int(bool(best_lr)),
+                               m12.ctypes.data_as(_i32p))
+        return n, m12
+
+    def line_coords(self, x1, y1, x2, y2, max_cells=4096) -> np.ndarray:
+        cells = np.empty((max_cells, 2), np.int32)
+        n = self.lib.plo_line_coords(x1, y1, x2, y2, cells.ctypes.data_as(_i32p), max_cells)
+        assert n <= max_cells
+        return cells[:n].copy()
+
+    def match_grid_points(self, xy, d1, cell_start, cell_items, rows, cols, d2, win, ratio, best_lr=True, m12=None):
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        xy, xyp = _i32(xy)
+        cs, csp = _i32(cell_start)
+        ci, cip = _i32(cell_items if len(cell_items) else np.zeros(1, np.int32))
+        w, wp = _i32(win)
+        m12 = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = self.lib.plo_match_grid_points(xyp, p1, n1, s1, csp, cip, rows, cols, p2, n2, s2, wp,
+                                           float(ratio), int(bool(best_lr)), m12.ctypes.data_as(_i32p))
+        return n, m12
+
+    def match_grid_lines(self, xyxy, d1, cell_start, cell_items, rows, cols, d2, dirs2, line_sim_th, win, ratio,
+                         best_lr=True, m12=None):
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        xy, xyp = _i32(xyxy)
+        cs, csp = _i32(cell_start)
+        ci, cip = _i32(cell_items if len(cell_items) else np.zeros(1, np.int32))
+        w, wp = _i32(win)
+        dirs2 = np.ascontiguousarray(dirs2, np.float64)
+        m12 = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = self.lib.plo_match_grid_lines(xyp, p1, n1, s1, csp, cip, rows, cols, p2, n2, s2,
+                                          dirs2.ctypes.data_as(_f64p), float(line_sim_th), wp, float(ratio),
+                                          int(bool(best_lr)), m12.ctypes.data_as(_i32p))
+        return n, m12
+
+    def stereo_filter_points(self, kp_l, kp_r, m12, max_dist_epip=1.0, min_disp=1.0):
+        kp_l = np.ascontiguousarray(kp_l, np.float32)
+        kp_r = np.ascontiguousarray(kp_r, np.float32)
+        m, mp = _i32(m12)
+        n1 = len(m)
+        keep = np.zeros(n1, np.uint8)
+        disp = np.zeros(n1, np.float64)
+        n = self.lib.plo_stereo_filter_points(kp_l.ctypes.data_as(_f32p), kp_r.ctypes.data_as(_f32p), mp, n1,
+                                              max_dist_epip, min_disp, keep.ctypes.data_as(_u8p),
+                                              disp.ctypes.data_as(_f64p))
+        return n, keep, disp
+
+    def stereo_filter_lines(self, ln_l, ln_r, m12, min_disp=1.0, line_horiz_th=0.1, stereo_overlap_th=0.75,
+                            ls_min_disp_ratio=0.7):
+        ln_l = np.ascontiguousarray(ln_l, np.float32)
+        ln_r = np.ascontiguousarray(ln_r, np.float32)
+        m, mp = _i32(m12)
+        n1 = len(m)
+        keep = np.zeros(n1, np.uint8)
+        disp = np.zeros((n1, 2), np.float64)
+        n = self.lib.plo_stereo_filter_lines(ln_l.ctypes.data_as(_f32p), ln_r.ctypes.data_as(_f32p), mp, n1,
+                                             min_disp, line_horiz_th, stereo_overlap_th, ls_min_disp_ratio,
+                                             keep.ctypes.data_as(_u8p), disp.ctypes.data_as(_f64p))
+        return n, keep, disp
+
+
+class _Ref:
+    """The reference's own matching.cpp / gridStructure.cpp / lineIterator.cpp (compiled unmodified)."""
+
+    def __init__(self):
+        self._lib = None
+
+    def available(self) -> bool:
+        try:
+            return self.lib is not None
+        except (FileNotFoundError, OSError, RuntimeError):
+            return False
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            L = _load("libplref.so")
+            L.plref_set_threads.argtypes = [C.c_int]
+            L.plref_get_threads.restype = C.c_int
+            L.plref_set_config.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+            L.plref_distance.restype = C.c_int
+            L.plref_distance.argtypes = [_u8p, _u8p]
+            sig = [_u8p, C.c_int, C.c_size_t, _u8p, C.c_int, C.c_size_t, C.c_float, _i32p, C.POINTER(C.c_int)]
+            L.plref_match_nnr.restype = C.c_int
+            L.plref_match_nnr.argtypes = sig
+            L.plref_match.restype = C.c_int
+            L.plref_match.argtypes = sig
+            L.plref_match_grid_points.restype = C.c_int
+            L.plref_match_grid_points.argtypes = [_i32p, _u8p, C.c_int, C.c_size_t, _i32p, _i32p, C.c_int, C.c_int,
+                                                  _u8p, C.c_int, C.c_size_t, _i32p, _i32p, C.POINTER(C.c_int)]
+            L.plref_match_grid_lines.restype = C.c_int
+            L.plref_match_grid_lines.argtypes = [_i32p, _u8p, C.c_int, C.c_size_t, _i32p, _i32p, C.c_int, C.c_int,
+                                                 _u8p, C.c_int, C.c_size_t, _f64p, _i32p, _i32p, C.POINTER(C.c_int)]
+            L.plref_line_coords.restype = C.c_int
+            L.plref_line_coords.argtypes = [C.c_double] * 4 + [_i32p, C.c_int]
+            L.plref_normalize.argtypes = [_f64p]
+            self._lib = L
+        return self._lib
+
+    def set_threads(self, n: int):
+        self.lib.plref_set_threads(int(n))
+
+    def set_config(self, best_lr=True, lr_parallel=True, min_ratio_12p=0.9, line_sim_th=0.75):
+        self.lib.plref_set_config(int(bool(best_lr)), int(bool(lr_parallel)), float(min_ratio_12p),
+                                  float(line_sim_th))
+
+    def distance(self, a, b) -> int:
+        a = np.ascontiguousarray(a, np.uint8).reshape(32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(32)
+        return self.lib.plref_distance(a.ctypes.data_as(_u8p), b.ctypes.data_as(_u8p))
+
+    def _nnr_like(self, fn, d1, d2, nnr, m12):
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        m12 = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = C.c_int(0)
+        st = fn(p1, n1, s1, p2, n2, s2, C.c_float(nnr), m12.ctypes.data_as(_i32p), C.byref(n))
+        if st != 0:
+            raise RuntimeError("reference threw std::runtime_error")
+        return n.value, m12
+
+    def match_nnr(self, d1, d2, nnr, m12=None):
+        return self._nnr_like(self.lib.plref_match_nnr, d1, d2, nnr, m12)
+
+    def match(self, d1, d2, nnr, best_lr=True, lr_parallel=True, m12=None):
+        self.set_config(best_lr=best_lr, lr_parallel=lr_parallel)
+        return self._nnr_like(self.lib.plref_match, d1, d2, nnr, m12)
+
+    def match_grid_points(self, xy, d1, cell_start, cell_items, rows, cols, d2, win, ratio, best_lr=True, m12=None):
+        self.set_config(best_lr=best_lr, min_ratio_12p=ratio)
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        xy, xyp = _i32(xy)
+        cs, csp = _i32(cell_start)
+        ci, cip = _i32(cell_items if len(cell_items) else np.zeros(1, np.int32))
+        w, wp = _i32(win)
+        m12 = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = C.c_int(0)
+        st = self.lib.plref_match_grid_points(xyp, p1, n1, s1, csp, cip, rows, cols, p2, n2, s2, wp,
+                                              m12.ctypes.data_as(_i32p), C.byref(n))
+        if st != 0:
+            raise RuntimeError("reference threw std::runtime_error")
+        return n.value, m12
+
+    def match_grid_lines(self, xyxy, d1, cell_start, cell_items, rows, cols, d2, dirs2, line_sim_th, win, ratio,
+                         best_lr=True, m12=None):
+        self.set_config(best_lr=best_lr, min_ratio_12p=ratio, line_sim_th=line_sim_th)
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        xy, xyp = _i32(xyxy)
+        cs, csp = _i32(cell_start)
+        ci, cip = _i32(cell_items if len(cell_items) else np.zeros(1, np.int32))
+        w, wp = _i32(win)
+        dirs2 = np.ascontiguousarray(dirs2, np.float64)
+        m12 = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = C.c_int(0)
+        st = self.lib.plref_match_grid_lines(xyp, p1, n1, s1, csp, cip, rows, cols, p2, n2, s2,
+                                             dirs2.ctypes.data_as(_f64p), wp, m12.ctypes.data_as(_i32p),
+                                             C.byref(n))
+        if st != 0:
+            raise RuntimeError("reference threw std::runtime_error")
+        return n.value, m12
+
+    def line_coords(self, x1, y1, x2, y2, max_cells=4096) -> np.ndarray:
+        cells = np.empty((max_cells, 2), np.int32)
+        n = self.lib.plref_line_coords(x1, y1, x2, y2, cells.ctypes.data_as(_i32p), max_cells)
+        assert n <= max_cells
+        return cells[:n].copy()
+
+    def normalize(self, v) -> np.ndarray:
+        v = np.array(v, np.float64)
+        self.lib.plref_normalize(v.ctypes.data_as(_f64p))
+        return v
+
+
+port = _Port()
+ref = _Ref()

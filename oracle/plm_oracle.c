@@ -1,0 +1,458 @@
+/*
+ * plm_oracle.c -- CPU restatement of the PL-inertial-slam descriptor-matching path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
+ * and there only as the checker (or the CPU arm), never as the thing shipped.
+ *
+ * Parity status: the reference holds no golden vectors / known-answer tests for this path
+ * (SURVEY.md section 4).  This restatement is therefore pinned against the reference ITSELF:
+ * oracle/_ref/libplref.so is /root/reference/stvo-pl/src/{matching,gridStructure,lineIterator}.cpp
+ * compiled unmodified (oracle/Makefile) and tests/test_oracle_vs_ref.py compares the two on
+ * random + tie-stress inputs; tests/golden/ holds vectors generated from that build
+ * (tools/make_golden.py).  The one third-party piece absent from /root/reference is
+ * cv::BFMatcher::knnMatch (OpenCV 3.3, features2d; call site matching.cpp:47-48): its K=2
+ * batchDistance insertion rule is restated in plo_knn2() and cross-checked against the
+ * in-container cv2 4.13 wheel (tests/test_oracle_vs_ref.py::test_knn2_vs_cv2).
+ *
+ * Every function cites the reference lines it follows (paths relative to /root/reference).
+ */
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PLO_API __attribute__((visibility("default")))
+
+/* Built with -ffp-contract=off: the reference is compiled for baseline x86-64 (no FMA,
+ * CMakeLists.txt:41), so every product that feeds a comparison is rounded separately. */
+
+/* std::min / std::max semantics (NaN behaviour differs from fmin/fmax). */
+static inline double plo_min(double a, double b) { return (b < a) ? b : a; }
+static inline double plo_max(double a, double b) { return (a < b) ? b : a; }
+
+/* stvo-pl/src/matching.cpp:93-109  StVO::distance -- 8 x int32 xor + SWAR popcount. */
+PLO_API int plo_hamming256(const uint8_t *a, const uint8_t *b)
+{
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t wa, wb;
+        memcpy(&wa, a + 4 * i, 4);
+        memcpy(&wb, b + 4 * i, 4);
+        uint32_t v = wa ^ wb;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+/*
+ * cv::BFMatcher::knnMatch(k=2) as called at stvo-pl/src/matching.cpp:47-48.  OpenCV's
+ * batchDistance (K>0 branch) keeps, per query row, K (dist, idx) slots initialised to
+ * (INT_MAX, -1); train row j with distance d enters iff d < dist[K-1] and is shifted up while
+ * dist[k] > d  ==> lexicographic (distance, train index) ordering, lowest index first on ties.
+ * idx/dist are n1 x 2; absent slots stay (-1, INT_MAX).
+ */
+PLO_API void plo_knn2(const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
+                      size_t step2, int32_t *idx, int32_t *dist)
+{
+    for (int i = 0; i < n1; i++) {
+        int32_t bd[2] = {INT_MAX, INT_MAX};
+        int32_t bi[2] = {-1, -1};
+        const uint8_t *q = d1 + (size_t)i * step1;
+        for (int j = 0; j < n2; j++) {
+            int d = plo_hamming256(q, d2 + (size_t)j * step2);
+            if (d < bd[1]) {
+                int k = 0;
+                if (bd[0] > d) { bd[1] = bd[0]; bi[1] = bi[0]; k = -1; }
+                bd[k + 1] = d;
+                bi[k + 1] = j;
+            }
+        }
+        idx[2 * i] = bi[0]; idx[2 * i + 1] = bi[1];
+        dist[2 * i] = bd[0]; dist[2 * i + 1] = bd[1];
+    }
+}
+
+/*
+ * stvo-pl/src/matching.cpp:41-61  StVO::matchNNR.
+ * m12 is IN/OUT: the reference does matches_12.resize(n1,-1), which only initialises slots the
+ * caller's vector did not already have; here the caller passes the already-resized buffer.
+ * Acceptance test is evaluated in float (DMatch::distance is float, nnr is float) -- :54.
+ * Returns the number of accepted rows, or -1 for the n2 < 2 case (UB in the reference).
+ */
+PLO_API int plo_match_nnr(const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
+                          size_t step2, float nnr, int32_t *m12)
+{
+    if (n2 < 2) return -1;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(n1 > 0 ? n1 : 1));
+    int32_t *dist = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(n1 > 0 ? n1 : 1));
+    plo_knn2(d1, n1, step1, d2, n2, step2, idx, dist);
+    int matches = 0;
+    for (int i = 0; i < n1; i++) {
+        const float lhs = (float)dist[2 * i];
+        const float rhs = (float)dist[2 * i + 1] * nnr;
+        if (lhs < rhs) {
+            m12[i] = idx[2 * i];
+            matches++;
+        }
+    }
+    free(idx);
+    free(dist);
+    return matches;
+}
+
+/*
+ * stvo-pl/src/matching.cpp:63-91  StVO::match.  best_lr = Config::bestLRMatches().
+ * The mutual check walks EVERY entry >= 0 of m12, stale ones included (:80-86), so the
+ * returned count can undershoot (even go negative) on the stale-fallback call sites
+ * (src/mapHandler.cpp:325-329).  Stale entries must be < n2 (the reference indexes
+ * matches_21[i2] unchecked).
+ */
+PLO_API int plo_match(const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
+                      size_t step2, float nnr, int best_lr, int32_t *m12)
+{
+    if (!best_lr) return plo_match_nnr(d1, n1, step1, d2, n2, step2, nnr, m12);
+    if (n2 < 2 || n1 < 2) return INT_MIN;
+    int matches = plo_match_nnr(d1, n1, step1, d2, n2, step2, nnr, m12);
+    int32_t *m21 = (int32_t *)malloc(sizeof(int32_t) * (size_t)n2);
+    for (int j = 0; j < n2; j++) m21[j] = -1;
+    plo_match_nnr(d2, n2, step2, d1, n1, step1, nnr, m21);
+    for (int i1 = 0; i1 < n1; i1++) {
+        int i2 = m12[i1];
+        if (i2 >= 0 && m21[i2] != i1) {
+            m12[i1] = -1;
+            matches--;
+        }
+    }
+    free(m21);
+    return matches;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * Grid (CSR form of StVO::GridStructure).  Cell (x, y), 0 <= x < cols, 0 <= y < rows, has
+ * linear id  x*rows + y  -- the reference stores grid[x][y] with x outermost
+ * (stvo-pl/src/gridStructure.cpp:49).  cell_start has cols*rows+1 entries.
+ * ------------------------------------------------------------------------------------- */
+
+/*
+ * stvo-pl/src/lineIterator.cpp:34-77 + stvo-pl/src/gridStructure.cpp:33-41 getLineCoords:
+ * Bresenham from double endpoints.  NOTE the reference never initialises y/x/maxX from the
+ * *rounded* endpoints: y = static_cast<int>(y1), x = static_cast<int>(x1),
+ * maxX = static_cast<int>(x2) after the steep / order swaps (:50-55).
+ * Writes up to max_cells (x, y) pairs, returns the number of cells of the full walk.
+ */
+PLO_API int plo_line_coords(double x1, double y1, double x2, double y2, int32_t *cells,
+                            int max_cells)
+{
+    const int steep = fabs(y2 - y1) > fabs(x2 - x1);
+    double t;
+    if (steep) { t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
+    if (x1 > x2) { t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    const double dx = x2 - x1;
+    const double dy = fabs(y2 - y1);
+    double error = dx / 2.0;
+    const int ystep = (y1 < y2) ? 1 : -1;
+    int y = (int)y1;
+    int x = (int)x1;
+    const int maxX = (int)x2;
+    int n = 0;
+    while (x <= maxX) {
+        if (n < max_cells) {
+            cells[2 * n] = steep ? y : x;
+            cells[2 * n + 1] = steep ? x : y;
+        }
+        n++;
+        error -= dy;
+        if (error < 0) { y += ystep; error += dx; }
+        x++;
+    }
+    return n;
+}
+
+/* GridStructure::get (stvo-pl/src/gridStructure.cpp:65-76): clamp the window to the grid. */
+static void plo_window(int x, int y, const int32_t win[4], int rows, int cols, int *min_x,
+                       int *max_x, int *min_y, int *max_y)
+{
+    int a = x - win[0]; *min_x = a > 0 ? a : 0;
+    int b = x + win[1] + 1; *max_x = b < cols ? b : cols;
+    int c = y - win[2]; *min_y = c > 0 ? c : 0;
+    int d = y + win[3] + 1; *max_y = d < rows ? d : rows;
+}
+
+typedef struct {
+    int32_t *list;  /* de-duplicated candidate ids (the unordered_set)            */
+    int32_t *stamp; /* stamp[id - lo] == tag  <=> id already in the set           */
+    int32_t lo, hi; /* id range covered by stamp                                   */
+    int n;
+} plo_set;
+
+static void plo_set_add_window(plo_set *s, int tag, int x, int y, const int32_t win[4],
+                               const int32_t *cell_start, const int32_t *cell_items, int rows,
+                               int cols)
+{
+    int min_x, max_x, min_y, max_y;
+    plo_window(x, y, win, rows, cols, &min_x, &max_x, &min_y, &max_y);
+    for (int x_ = min_x; x_ < max_x; ++x_)
+        for (int y_ = min_y; y_ < max_y; ++y_) {
+            int c = x_ * rows + y_;
+            for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
+                int id = cell_items[k];
+                if (id < s->lo || id >= s->hi) { /* out-of-range ids: keep once each is moot,
+                                                    the matcher skips them (:141) */
+                    continue;
+                }
+                if (s->stamp[id - s->lo] != tag) {
+                    s->stamp[id - s->lo] = tag;
+                    s->list[s->n++] = id;
+                }
+            }
+        }
+}
+
+/*
+ * Shared body of both StVO::matchGrid overloads (stvo-pl/src/matching.cpp:111-177 points,
+ * :179-258 lines).  is_lines selects the two-window candidate union (:213-215) and the
+ * direction filter (:221-222, NaN passes because !(NaN < th)).
+ * ratio = Config::minRatio12P() for BOTH overloads (:160, :241), evaluated in double.
+ * The unordered_set iteration order of the reference is unspecified; for ratio <= 1 an accepted
+ * row has a strict unique minimum so the order cannot change any output (SURVEY 8a note 1).
+ */
+static int plo_match_grid(int is_lines, const int32_t *coords, const uint8_t *d1, int n1,
+                          size_t step1, const int32_t *cell_start, const int32_t *cell_items,
+                          int rows, int cols, const uint8_t *d2, int n2, size_t step2,
+                          const double *dirs2, double line_sim_th, const int32_t win[4],
+                          double ratio, int best_lr, int32_t *m12)
+{
+    int matches = 0;
+    int32_t *m21 = NULL, *distances = NULL;
+    if (best_lr) {
+        m21 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
+        distances = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
+        for (int j = 0; j < n2; j++) { m21[j] = -1; distances[j] = INT_MAX; }
+    }
+    const int n_items = cell_start[rows * cols];
+    plo_set set;
+    set.lo = 0;
+    set.hi = n2;
+    set.list = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
+    set.stamp = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
+    for (int j = 0; j < n2; j++) set.stamp[j] = -1;
+    (void)n_items;
+
+    for (int i1 = 0; i1 < n1; ++i1) {
+        int best_d = INT_MAX, best_d2 = INT_MAX, best_idx = -1;
+        const uint8_t *desc = d1 + (size_t)i1 * step1;
+        double vx = 0.0, vy = 0.0;
+        set.n = 0;
+        if (!is_lines) {
+            plo_set_add_window(&set, i1, coords[2 * i1], coords[2 * i1 + 1], win, cell_start,
+                               cell_items, rows, cols);
+        } else {
+            const int32_t *c = coords + 4 * i1;
+            vx = (double)(c[2] - c[0]);
+            vy = (double)(c[3] - c[1]);
+            /* matching.h:43-48 normalize: magnitude = sqrt(x*x + y*y), no FMA contraction */
+            const double xx = vx * vx, yy = vy * vy;
+            double mag = sqrt(xx + yy);
+            vx /= mag;
+            vy /= mag;
+            plo_set_add_window(&set, i1, c[0], c[1], win, cell_start, cell_items, rows, cols);
+            plo_set_add_window(&set, i1, c[2], c[3], win, cell_start, cell_items, rows, cols);
+        }
+        /* `if (candidates.empty()) continue;` (:139/:217): ids outside [0,n2) would make the
+         * set non-empty but are skipped below, and an all-skipped row is never accepted for
+         * ratio <= 1, so dropping them from the set is equivalent. */
+        if (set.n == 0) continue;
+        for (int k = 0; k < set.n; k++) {
+            const int i2 = set.list[k];
+            if (is_lines) {
+                const double p0 = vx * dirs2[2 * i2], p1 = vy * dirs2[2 * i2 + 1];
+                double dp = p0 + p1;
+                if (fabs(dp) < line_sim_th) continue;
+            }
+            const int d = plo_hamming256(desc, d2 + (size_t)i2 * step2);
+            if (best_lr) {
+                if (d < distances[i2]) {
+                    distances[i2] = d;
+                    m21[i2] = i1;
+                } else
+                    continue;
+            }
+            if (d < best_d) {
+                best_d2 = best_d;
+                best_d = d;
+                best_idx = i2;
+            } else if (d < best_d2)
+                best_d2 = d;
+        }
+        if ((double)best_d < (double)best_d2 * ratio) {
+            m12[i1] = best_idx;
+            matches++;
+        }
+    }
+    if (best_lr) {
+        for (int i1 = 0; i1 < n1; ++i1) {
+            int i2 = m12[i1];
+            if (i2 >= 0 && m21[i2] != i1) {
+                m12[i1] = -1;
+                matches--;
+            }
+        }
+    }
+    free(m21);
+    free(distances);
+    free(set.list);
+    free(set.stamp);
+    return matches;
+}
+
+/* stvo-pl/src/matching.cpp:111-177.  xy = n1 x (x, y) grid-cell coords; win = {width.first,
+ * width.second, height.first, height.second} of GridWindow (gridStructure.h:35-37). */
+PLO_API int plo_match_grid_points(const int32_t *xy, const uint8_t *d1, int n1, size_t step1,
+                                  const int32_t *cell_start, const int32_t *cell_items,
+                                  int rows, int cols, const uint8_t *d2, int n2, size_t step2,
+                                  const int32_t win[4], double ratio, int best_lr,
+                                  int32_t *m12)
+{
+    return plo_match_grid(0, xy, d1, n1, step1, cell_start, cell_items, rows, cols, d2, n2,
+                          step2, NULL, 0.0, win, ratio, best_lr, m12);
+}
+
+/* stvo-pl/src/matching.cpp:179-258.  xyxy = n1 x (sx, sy, ex, ey); dirs2 = n2 x (dx, dy). */
+PLO_API int plo_match_grid_lines(const int32_t *xyxy, const uint8_t *d1, int n1, size_t step1,
+                                 const int32_t *cell_start, const int32_t *cell_items,
+                                 int rows, int cols, const uint8_t *d2, int n2, size_t step2,
+                                 const double *dirs2, double line_sim_th,
+                                 const int32_t win[4], double ratio, int best_lr,
+                                 int32_t *m12)
+{
+    return plo_match_grid(1, xyxy, d1, n1, step1, cell_start, cell_items, rows, cols, d2, n2,
+                          step2, dirs2, line_sim_th, win, ratio, best_lr, m12);
+}
+
+/* ---------------------------------------------------------------------------------------
+ * Stereo post-filters (the drivers' per-match geometry gates).
+ * ------------------------------------------------------------------------------------- */
+
+/*
+ * stvo-pl/src/stereoFrame.cpp:162-171 (matchStereoPoints): a match (i1 -> i2) survives iff
+ * |y_l - y_r| <= maxDistEpip (float subtraction, std::abs(float) promoted to double for the
+ * compare) and disp = x_l - x_r (float subtraction widened to double) >= minDisp.
+ * kp_* are n x (x, y) float32 pixel coordinates (cv::KeyPoint::pt).
+ * keep[i1] = 1/0, disp[i1] = disparity of kept rows (else 0).  Returns the number kept.
+ */
+PLO_API int plo_stereo_filter_points(const float *kp_l, const float *kp_r, const int32_t *m12,
+                                     int n1, double max_dist_epip, double min_disp,
+                                     uint8_t *keep, double *disp)
+{
+    int kept = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        keep[i1] = 0;
+        disp[i1] = 0.0;
+        const int i2 = m12[i1];
+        if (i2 < 0) continue;
+        const float dyf = kp_l[2 * i1 + 1] - kp_r[2 * i2 + 1];
+        if ((double)fabsf(dyf) <= max_dist_epip) {
+            const float dxf = kp_l[2 * i1] - kp_r[2 * i2];
+            double disp_ = (double)dxf;
+            if (disp_ >= min_disp) {
+                keep[i1] = 1;
+                disp[i1] = disp_;
+                kept++;
+            }
+        }
+    }
+    return kept;
+}
+
+/* stvo-pl/src/stereoFrame.cpp:484-519  lineSegmentOverlapStereo (all double). */
+PLO_API double plo_line_overlap_stereo(double spl_obs, double epl_obs, double spl_proj,
+                                       double epl_proj, double line_horiz_th)
+{
+    double overlap = 1.f;
+    if (fabs(epl_obs - spl_obs) > line_horiz_th) {
+        double sln = plo_min(spl_obs, epl_obs);
+        double eln = plo_max(spl_obs, epl_obs);
+        double spn = plo_min(spl_proj, epl_proj);
+        double epn = plo_max(spl_proj, epl_proj);
+        double length = eln - spn;
+        if ((epn < sln) || (spn > eln))
+            overlap = 0.f;
+        else {
+            if ((epn > eln) && (spn < sln))
+                overlap = eln - sln;
+            else
+                overlap = plo_min(eln, epn) - plo_max(sln, spn);
+        }
+        if (length > 0.01f)
+            overlap = overlap / length;
+        else
+            overlap = 0.f;
+        if (overlap > 1.f) overlap = 1.f;
+    }
+    return overlap;
+}
+
+/*
+ * stvo-pl/src/stereoFrame.cpp:359-385 (matchStereoLines) + :416-426 filterLineSegmentDisparity.
+ * ln_* are n x (sx, sy, ex, ey) float32 (cv::line_descriptor::KeyLine start/endPoint), widened
+ * to double on entry exactly like the Vector3d initialisation at :366-370.
+ * Quirk kept: sp_r is overwritten (x interpolated at y = sp_l.y, :377) BEFORE ep_r is
+ * interpolated (:378), so the second interpolation and the |sp_r.y - ep_r.y| gate (:384) see
+ * the updated values.
+ * keep[i1] = 1/0; disp_se[2*i1 .. +1] = (disp_s, disp_e) as computed (including the -1/-1
+ * rejection marker) for rows with a match, else (0,0).  Returns the number kept.
+ */
+PLO_API int plo_stereo_filter_lines(const float *ln_l, const float *ln_r, const int32_t *m12,
+                                    int n1, double min_disp, double line_horiz_th,
+                                    double stereo_overlap_th, double ls_min_disp_ratio,
+                                    uint8_t *keep, double *disp_se)
+{
+    int kept = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        keep[i1] = 0;
+        disp_se[2 * i1] = disp_se[2 * i1 + 1] = 0.0;
+        const int i2 = m12[i1];
+        if (i2 < 0) continue;
+        double sp_l[2] = {ln_l[4 * i1 + 0], ln_l[4 * i1 + 1]};
+        double ep_l[2] = {ln_l[4 * i1 + 2], ln_l[4 * i1 + 3]};
+        double sp_r[2] = {ln_r[4 * i2 + 0], ln_r[4 * i2 + 1]};
+        double ep_r[2] = {ln_r[4 * i2 + 2], ln_r[4 * i2 + 3]};
+
+        double overlap =
+            plo_line_overlap_stereo(sp_l[1], ep_l[1], sp_r[1], ep_r[1], line_horiz_th);
+
+        {
+            const double a = sp_r[0] * (sp_l[1] - ep_r[1]);
+            const double b = ep_r[0] * (sp_r[1] - sp_l[1]);
+            double nx = (a + b) / (sp_r[1] - ep_r[1]);
+            sp_r[0] = nx;
+            sp_r[1] = sp_l[1];
+        }
+        {
+            const double a = sp_r[0] * (ep_l[1] - ep_r[1]);
+            const double b = ep_r[0] * (sp_r[1] - ep_l[1]);
+            double nx = (a + b) / (sp_r[1] - ep_r[1]);
+            ep_r[0] = nx;
+            ep_r[1] = ep_l[1];
+        }
+        double disp_s = sp_l[0] - sp_r[0];
+        double disp_e = ep_l[0] - ep_r[0];
+        if (plo_min(disp_s, disp_e) / plo_max(disp_s, disp_e) < ls_min_disp_ratio) {
+            disp_s = -1.0;
+            disp_e = -1.0;
+        }
+        disp_se[2 * i1] = disp_s;
+        disp_se[2 * i1 + 1] = disp_e;
+        if (disp_s >= min_disp && disp_e >= min_disp &&
+            fabs(sp_l[1] - ep_l[1]) > line_horiz_th &&
+            fabs(sp_r[1] - ep_r[1]) > line_horiz_th && overlap > stereo_overlap_th) {
+            keep[i1] = 1;
+            kept++;
+        }
+    }
+    return kept;
+}
