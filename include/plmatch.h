@@ -1,0 +1,227 @@
+/*
+ * plmatch.h -- C ABI of the B200-native descriptor-matching path of PL-inertial-slam.
+ *
+ * This is the drop-in boundary: every entry point below replaces one
+ * function of the reference's matching layer (paths relative to the reference checkout):
+ *
+ *   plm_hamming256          StVO::distance                 stvo-pl/src/matching.cpp:93-109
+ *   plm_knn2                cv::BFMatcher::knnMatch(k=2)   call site stvo-pl/src/matching.cpp:47-48
+ *   plm_match_nnr           StVO::matchNNR                 stvo-pl/src/matching.cpp:41-61
+ *   plm_match               StVO::match                    stvo-pl/src/matching.cpp:63-91
+ *   plm_match_grid_points   StVO::matchGrid (points)       stvo-pl/src/matching.cpp:111-177
+ *   plm_match_grid_lines    StVO::matchGrid (lines)        stvo-pl/src/matching.cpp:179-258
+ *   plm_stereo_filter_points  gates of matchStereoPoints   stvo-pl/src/stereoFrame.cpp:162-171
+ *   plm_stereo_filter_lines   gates of matchStereoLines    stvo-pl/src/stereoFrame.cpp:359-385,
+ *                             filterLineSegmentDisparity :416-426, lineSegmentOverlapStereo :484-519
+ *   plm_batch_*             the per-frame loop             app/plslam_dataset.cpp:114-172
+ *   plm_db_* / plm_dev_*    keyframe / local-map database  src/mapHandler.cpp:583-803, 3301-3409
+ *
+ * The C++ replacement of stvo-pl/src/matching.cpp that keeps the StVO:: signatures and calls this
+ * ABI is pl_inertial_slam_b200/csrc/stvo_matching_gpu.cpp.
+ *
+ * Conventions
+ *  - Descriptors are 256-bit (32-byte) rows, `step` bytes apart (cv::Mat::step); step >= 32.
+ *  - m12_inout is IN/OUT like the reference's std::vector<int>& matches_12 after
+ *    resize(n1, -1): the library writes accepted rows and cross-check culls only, never resets.
+ *    Entries >= 0 on input ("stale" matches of the fallback call sites, mapHandler.cpp:325-329)
+ *    must be < n2.
+ *  - Every function returns a status (PLM_OK or < 0); the reference's int return value (match
+ *    count; may be off or negative in the stale-fallback quirk) comes back through n_matches.
+ *  - No exception crosses this boundary and there is NO CPU fallback: without a usable CUDA device
+ *    every compute entry point returns PLM_E_CUDA.
+ *  - A plm_ctx owns one CUDA stream, device scratch and pinned staging.  It may be used by one
+ *    host thread at a time; pass NULL to use a lazily created per-thread default context
+ *    (re-entrant from any number of host threads).
+ *  - Packed top-2 keys: key = (uint64)distance << 32 | train_index, UINT64_MAX when absent;
+ *    unsigned min over keys == the reference's lowest-index tie-breaking.
+ */
+#ifndef PLMATCH_H_
+#define PLMATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLM_VERSION 100
+
+#define PLM_OK             0
+#define PLM_E_INVALID     -1 /* null pointer, negative size, step < 32, misaligned device pointer  */
+#define PLM_E_SIZE        -2 /* size mismatch: "[matchNNR] Different size for matches and descriptors!",
+                                "[matchGrid] Each point/line needs a corresponding descriptor!"      */
+#define PLM_E_TRAIN       -3 /* fewer than 2 train rows for an NNR test (UB in the reference)        */
+#define PLM_E_GRID        -4 /* "[GridStructure] invalid dimension" or malformed CSR                  */
+#define PLM_E_RATIO       -5 /* matchGrid ratio > 1: the reference's result then depends on
+                                unordered_set iteration order                                        */
+#define PLM_E_CUDA        -6 /* CUDA runtime failure (see plm_last_error)                            */
+#define PLM_E_NOMEM       -7
+#define PLM_E_UNSUPPORTED -8 /* size outside what the kernels support (documented per function)      */
+
+typedef struct plm_ctx plm_ctx;
+typedef struct plm_db plm_db;
+
+#define PLM_KEY_ABSENT UINT64_MAX
+
+int plm_version(void);
+const char *plm_status_string(int status);
+/* Message of the last failing call on this thread (CUDA error string included). */
+const char *plm_last_error(void);
+int plm_device_count(int *count);
+
+int plm_ctx_create(int device, plm_ctx **out);
+int plm_ctx_destroy(plm_ctx *ctx);
+/* cudaStream_t the context launches on. */
+void *plm_ctx_stream(plm_ctx *ctx);
+/* Borrow an external stream (e.g. torch's current stream); pass NULL to return to the own stream. */
+int plm_ctx_set_stream(plm_ctx *ctx, void *cuda_stream);
+int plm_ctx_synchronize(plm_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t plm_ctx_launch_count(plm_ctx *ctx);
+
+/* ---- host-buffer entry points (what the StVO:: wrappers call) -------------------------------- */
+
+/* dist[i] = Hamming(a row i, b row i), i < n.  StVO::distance is the n == 1 case. */
+int plm_hamming256(plm_ctx *ctx, const uint8_t *a, size_t step_a, const uint8_t *b, size_t step_b,
+                   int n, int32_t *dist);
+
+/* Two nearest train rows per query row as packed keys, top2 = n1 x 2 uint64 (best, second).
+ * idx_base is added to the train index (database shards).  n2 >= 0 (absent slots = PLM_KEY_ABSENT). */
+int plm_knn2(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
+             size_t step2, uint64_t idx_base, uint64_t *top2);
+
+/* StVO::matchNNR.  Accept row i iff (float)d0 < (float)d1 * nnr (float arithmetic, as :54). */
+int plm_match_nnr(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
+                  size_t step2, float nnr, int32_t *m12_inout, int *n_matches);
+
+/* StVO::match.  best_lr = Config::bestLRMatches(): both directions + mutual check. */
+int plm_match(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
+              size_t step2, float nnr, int best_lr, int32_t *m12_inout, int *n_matches);
+
+/* StVO::matchGrid, points.  xy = n1 x (x, y) grid-cell coordinates of the queries.
+ * Grid = CSR of GridStructure over the train features: cell (x, y) has id x * grid_rows + y,
+ * cell_start has grid_rows * grid_cols + 1 entries, cell_items the bucket contents.
+ * win = { width.first, width.second, height.first, height.second } of GridWindow.
+ * ratio = Config::minRatio12P() (double arithmetic, :160); must be <= 1.
+ * Supported: n2 <= 32768. */
+int plm_match_grid_points(plm_ctx *ctx, const int32_t *xy, const uint8_t *d1, int n1, size_t step1,
+                          const int32_t *cell_start, const int32_t *cell_items, int grid_rows,
+                          int grid_cols, const uint8_t *d2, int n2, size_t step2,
+                          const int32_t win[4], double ratio, int best_lr, int32_t *m12_inout,
+                          int *n_matches);
+
+/* StVO::matchGrid, lines.  xyxy = n1 x (start x, start y, end x, end y) cell coordinates;
+ * dirs2 = n2 x (dx, dy) unit directions of the train lines; a candidate is skipped when
+ * fabs(dot(normalize(end - start), dirs2[i2])) < line_sim_th (NaN passes, :221).
+ * ratio = Config::minRatio12P() -- the reference uses the POINT ratio here too (:241). */
+int plm_match_grid_lines(plm_ctx *ctx, const int32_t *xyxy, const uint8_t *d1, int n1, size_t step1,
+                         const int32_t *cell_start, const int32_t *cell_items, int grid_rows,
+                         int grid_cols, const uint8_t *d2, int n2, size_t step2, const double *dirs2,
+                         double line_sim_th, const int32_t win[4], double ratio, int best_lr,
+                         int32_t *m12_inout, int *n_matches);
+
+/* Epipolar / minimum-disparity gate of matchStereoPoints.  kp_l = n1 x (x, y) float32 pixels,
+ * kp_r = n2 x 2.  keep[i1] = 1 iff m12[i1] >= 0 passes; disp[i1] = x_l - x_r of kept rows. */
+int plm_stereo_filter_points(plm_ctx *ctx, const float *kp_l, int n1, const float *kp_r, int n2,
+                             const int32_t *m12, double max_dist_epip, double min_disp,
+                             uint8_t *keep, double *disp, int *n_kept);
+
+/* Overlap / disparity-ratio / horizontal-line gate of matchStereoLines.  ln_* = n x (sx, sy, ex,
+ * ey) float32 pixels.  disp_se = n1 x (disp_s, disp_e). */
+int plm_stereo_filter_lines(plm_ctx *ctx, const float *ln_l, int n1, const float *ln_r, int n2,
+                            const int32_t *m12, double min_disp, double line_horiz_th,
+                            double stereo_overlap_th, double ls_min_disp_ratio, uint8_t *keep,
+                            double *disp_se, int *n_kept);
+
+/* ---- batched replay (one launch per stage over a frame arena) -------------------------------- */
+
+/* One brute-force job: rows [off1, off1+n1) x rows [off2, off2+n2) of the descriptor arena;
+ * results land at m12_arena[off_m .. off_m + n1). */
+typedef struct plm_pair_job {
+    int64_t off1, off2, off_m;
+    int32_t n1, n2;
+} plm_pair_job;
+
+/* One grid job (points when is_lines == 0).  Offsets index the arenas passed to
+ * plm_batch_set_match_grid: coords (int32 elements), descriptor rows, CSR arenas, dirs2 (doubles).
+ * Every job must be frame-sized: n1 <= 4096 and n2 <= 32768. */
+typedef struct plm_grid_job {
+    int64_t off_coords; /* into coords arena, int32 units (2 or 4 per query)        */
+    int64_t off1, off2; /* descriptor arena rows                                     */
+    int64_t off_cell_start, off_cell_items;
+    int64_t off_dirs2;  /* into dirs2 arena, double units (lines only)               */
+    int64_t off_m;
+    int32_t n1, n2, is_lines, pad_;
+    int32_t win[4];
+} plm_grid_job;
+
+/* A batch owns the device copy of its arenas and job tables, so a replay can be prepared once
+ * (set_*), run many times (run: kernels only, enqueued on the context's stream, no host sync) and
+ * read back (fetch: device -> host + sync).  run() first restores the uploaded m12 arena, so every
+ * run sees the same IN values. */
+typedef struct plm_batch plm_batch;
+int plm_batch_create(plm_ctx *ctx, plm_batch **out);
+int plm_batch_destroy(plm_batch *b);
+
+/* StVO::match for every job; counts[j] = the reference's return value for job j.
+ * arena = n_rows x 32 bytes, contiguous.  Jobs with n2 < 2 (or n1 < 2 with best_lr) get
+ * counts[j] = INT32_MIN and are skipped (the reference would be UB / throw).
+ * m12_arena (n_m entries) is the IN value of every job's match vector. */
+int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_rows, const plm_pair_job *jobs,
+                        int n_jobs, float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m);
+
+/* StVO::matchGrid (points or lines per job) for every job, one CTA per job. */
+int plm_batch_set_match_grid(plm_batch *b, const uint8_t *arena, int64_t n_rows, const int32_t *coords,
+                             int64_t n_coords, const int32_t *cell_start, int64_t n_cell_start,
+                             const int32_t *cell_items, int64_t n_cell_items, const double *dirs2,
+                             int64_t n_dirs2, int grid_rows, int grid_cols, const plm_grid_job *jobs,
+                             int n_jobs, double ratio, double line_sim_th, int best_lr,
+                             const int32_t *m12_arena, int64_t n_m);
+
+int plm_batch_run(plm_batch *b);
+int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts);
+/* Bytes the last set_* call copied host -> device / fetch copies device -> host. */
+int64_t plm_batch_h2d_bytes(const plm_batch *b);
+int64_t plm_batch_d2h_bytes(const plm_batch *b);
+
+/* ---- device-resident entry points (descriptor database shards, multi-GPU merge) -------------- */
+/* All *_dev pointers are device pointers on the context's device; descriptor rows are contiguous
+ * (32-byte step) and 16-byte aligned.  Work is enqueued on the context's stream, no host sync. */
+
+int plm_dev_knn2(plm_ctx *ctx, const void *d1_dev, int n1, const void *d2_dev, int64_t n2,
+                 uint64_t idx_base, uint64_t *top2_dev);
+/* top2_out[q] = two smallest keys among parts[p][q][0..1], p < n_parts (parts = n_parts x n1 x 2). */
+int plm_dev_top2_merge(plm_ctx *ctx, const uint64_t *parts_dev, int n_parts, int n1,
+                       uint64_t *top2_out_dev);
+/* matchNNR acceptance from packed top-2: m12[q] = idx0 and ++*count where the ratio test passes. */
+int plm_dev_nnr_accept(plm_ctx *ctx, const uint64_t *top2_dev, int n1, float nnr,
+                       int32_t *m12_dev_inout, int32_t *count_dev);
+/* Mutual check (matching.cpp:80-86): cull m12[i1] >= 0 with m21[m12[i1]] != i1, --*count each. */
+int plm_dev_cross_check(plm_ctx *ctx, int32_t *m12_dev_inout, int n1, int64_t i1_base,
+                        const int32_t *m21_dev, int64_t n2, int32_t *count_dev);
+
+/* A device-resident descriptor database shard (keyframe DB / local map). */
+int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out);
+int plm_db_destroy(plm_db *db);
+/* Copy n rows from host (step bytes apart) to rows [at_row, at_row + n); grows size to cover them. */
+int plm_db_upload(plm_db *db, const uint8_t *rows, int64_t n, size_t step, int64_t at_row);
+int64_t plm_db_size(const plm_db *db);
+void *plm_db_device_ptr(const plm_db *db);
+/* knn2 of host queries against the resident shard (H2D queries, D2H packed top-2). */
+int plm_db_knn2(plm_db *db, const uint8_t *q, int nq, size_t step, uint64_t idx_base, uint64_t *top2);
+
+/* Tuning knobs (measurement only; results never depend on them):
+ *   "knn_variant"  1 = carry-save 5-POPC Hamming (default), 0 = plain 8-POPC. */
+int plm_set_option(const char *key, int value);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+
+/* Issue-rate micro-benchmark of the integer pipe on the context's device: giga-instructions/s of
+ * independent POPC.32 (*popc_gops) and LOP3.32 (*lop3_gops) per GPU. */
+int plm_measure_int_peaks(plm_ctx *ctx, double *popc_gops, double *lop3_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLMATCH_H_ */

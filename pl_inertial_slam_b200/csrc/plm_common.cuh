@@ -1,0 +1,77 @@
+// Shared device helpers: 256-bit Hamming distance on the integer pipe, packed top-2 keys.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace plm {
+
+constexpr uint32_t KEY32_ABSENT = 0xFFFFFFFFu;
+constexpr unsigned long long KEY64_ABSENT = 0xFFFFFFFFFFFFFFFFull;
+
+// A 256-bit descriptor held in registers as two 128-bit halves.
+struct Desc {
+    uint4 lo, hi;
+};
+
+__device__ __forceinline__ Desc load_desc(const uint4 *__restrict__ base, long long row) {
+    Desc d;
+    d.lo = __ldg(base + 2 * row);
+    d.hi = __ldg(base + 2 * row + 1);
+    return d;
+}
+
+// StVO::distance (stvo-pl/src/matching.cpp:93-109): 8 x (xor, popcount).  LOP3 + POPC + IADD3.
+__device__ __forceinline__ int hamming256(const Desc &a, const uint4 &blo, const uint4 &bhi) {
+    int s0 = __popc(a.lo.x ^ blo.x) + __popc(a.lo.y ^ blo.y) + __popc(a.lo.z ^ blo.z);
+    int s1 = __popc(a.lo.w ^ blo.w) + __popc(a.hi.x ^ bhi.x) + __popc(a.hi.y ^ bhi.y);
+    int s2 = __popc(a.hi.z ^ bhi.z) + __popc(a.hi.w ^ bhi.w);
+    return s0 + s1 + s2;
+}
+
+__device__ __forceinline__ int hamming256(const Desc &a, const Desc &b) {
+    return hamming256(a, b.lo, b.hi);
+}
+
+// Carry-save variant: two LOP3 full adders (sum = a^b^c, carry = maj(a,b,c)) compress six of the
+// eight xor words into 2 "ones" + 2 "twos" words, then a third compresses the ones again:
+// 5 POPC instead of 8 at the price of 6 LOP3 -- POPC issues at a quarter of the LOP3 rate, so this
+// moves work from the saturated pipe to the idle one.  Exactly the same integer result.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+__device__ __forceinline__ int hamming256_csa(const Desc &a, const uint4 &blo, const uint4 &bhi) {
+    const uint32_t x0 = a.lo.x ^ blo.x, x1 = a.lo.y ^ blo.y, x2 = a.lo.z ^ blo.z, x3 = a.lo.w ^ blo.w;
+    const uint32_t x4 = a.hi.x ^ bhi.x, x5 = a.hi.y ^ bhi.y, x6 = a.hi.z ^ bhi.z, x7 = a.hi.w ^ bhi.w;
+    const uint32_t sa = lop3_xor3(x0, x1, x2), ca = lop3_maj(x0, x1, x2);
+    const uint32_t sb = lop3_xor3(x3, x4, x5), cb = lop3_maj(x3, x4, x5);
+    const uint32_t sc = lop3_xor3(sa, sb, x6), cc = lop3_maj(sa, sb, x6);
+    const int ones = __popc(sc) + __popc(x7);
+    const int twos = __popc(ca) + __popc(cb) + __popc(cc);
+    return ones + 2 * twos;
+}
+
+// Packed 64-bit key: (distance << 32) | global train index.  Unsigned min == (dist, idx) lexicographic.
+__device__ __forceinline__ unsigned long long make_key64(uint32_t dist, uint32_t idx) {
+    return (static_cast<unsigned long long>(dist) << 32) | idx;
+}
+
+// Insert key k into the sorted pair (b0 <= b1).
+__device__ __forceinline__ void top2_insert(uint32_t &b0, uint32_t &b1, uint32_t k) {
+    b1 = min(b1, max(b0, k));
+    b0 = min(b0, k);
+}
+__device__ __forceinline__ void top2_insert(unsigned long long &b0, unsigned long long &b1,
+                                            unsigned long long k) {
+    b1 = min(b1, max(b0, k));
+    b0 = min(b0, k);
+}
+
+} // namespace plm

@@ -1,0 +1,362 @@
+// Grid-windowed matching: StVO::matchGrid for points (stvo-pl/src/matching.cpp:111-177) and lines
+// (:179-258) over a CSR copy of StVO::GridStructure (stvo-pl/src/gridStructure.cpp:43-83).
+//
+// The reference walks the query rows i1 in order and keeps distances[i2] = running minimum per
+// train feature; a pair only counts for row i1 when it strictly improves that minimum.  Stated
+// without the loop-carried dependence (SURVEY 8a note 1):
+//     live(i1,i2)  <=>  D(i1,i2) < min{ D(i1',i2) : i1' < i1, i2 in cand(i1') }
+//     m21[i2]       =   the live pair of column i2 with the smallest D  (= lowest i1 at the minimum)
+//     row result    =   two smallest D over the live pairs of the row, fp64 ratio test, mutual check
+// Parallel form used here: consecutive rows are split into chunks, one warp per chunk.
+//   phase A  every warp computes the column minima of its own chunk          (wmin[w][i2], u16)
+//   scan     exclusive prefix-min over the chunks in row order  -> wmin[w][i2] becomes the
+//            threshold a pair of chunk w must beat before the chunk starts
+//   phase C  every warp replays its rows IN ORDER against its private threshold array, which
+//            reproduces the sequential semantics inside the chunk exactly; lanes own candidates.
+// A frame-sized job (n1 <= ~1-2k rows) is one CTA and one launch including the mutual check; a
+// map-sized job (200k rows) uses one CTA per 32*W rows with the scan done by a second kernel.
+// Distances are recomputed in phase C instead of being stored: a pair list would need a dynamic
+// allocation, and 8 POPC are cheaper than the round trip.
+#pragma once
+#include "plm_common.cuh"
+
+namespace plm {
+
+struct GridJob {
+    const int32_t *coords;     // n1 x 2 (points) or n1 x 4 (lines), grid-cell coordinates
+    const uint4 *d1;           // n1 query descriptors
+    const int32_t *cell_start; // grid_rows*grid_cols + 1
+    const int32_t *cell_items;
+    const uint4 *d2;           // n2 train descriptors
+    const double *dirs2;       // n2 x 2 (lines only)
+    int32_t *m12;              // in/out, n1
+    int32_t *count;            // accepted - culled
+    int32_t n1, n2, is_lines, pad_;
+    int32_t win[4];
+    long long i1_base;         // global row index of local row 0 (row-sharded map; 0 otherwise)
+};
+
+struct GridParams {
+    int grid_rows, grid_cols;
+    int best_lr;
+    int rows_per_warp;          // chunked launch only; the fused kernel derives it from n1
+    double ratio, line_sim_th;
+    // chunked (multi-CTA) launch only:
+    uint16_t *cta_min;          // [n_cta][n2] per-CTA column minima, turned into thresholds in place
+    unsigned long long *m21key; // [n2] (D << 32 | i1) of the best live pair per column
+};
+
+constexpr uint16_t D_INF = 0xFFFFu;
+constexpr int GRID_KEY_BITS = 22;
+
+struct RowWindows {
+    int n_win;
+    int min_x[2], nx[2], min_y[2], max_y[2];
+    int n_ranges;
+};
+
+// GridStructure::get window clamp (gridStructure.cpp:67-71).  One window per point, two per line
+// (start and end cell, matching.cpp:213-215).
+__device__ __forceinline__ void clamp_window(RowWindows &rw, int k, int x, int y, const int32_t win[4],
+                                             int grid_rows, int grid_cols) {
+    const long long ax = static_cast<long long>(x) - win[0], bx = static_cast<long long>(x) + win[1] + 1;
+    const long long ay = static_cast<long long>(y) - win[2], by = static_cast<long long>(y) + win[3] + 1;
+    const int min_x = static_cast<int>(max(0ll, ax)), max_x = static_cast<int>(min(static_cast<long long>(grid_cols), bx));
+    const int min_y = static_cast<int>(max(0ll, ay)), max_y = static_cast<int>(min(static_cast<long long>(grid_rows), by));
+    const bool any = max_x > min_x && max_y > min_y;
+    rw.min_x[k] = min_x;
+    rw.nx[k] = any ? max_x - min_x : 0;
+    rw.min_y[k] = min_y;
+    rw.max_y[k] = max_y;
+}
+
+// Calls body(i2) once per candidate slot of the row's window(s), 32 slots at a time with lane ==
+// slot; lanes without a slot get i2 = -1.  All 32 lanes call body together (it may use warp
+// collectives).  Because cell ids are x-major, one window column is one contiguous item range:
+// lanes first fetch the <= 32 range bounds, scan their lengths, then map flat slots to items with
+// a shuffle binary search -- no per-range serial loop.
+template <class Body>
+__device__ __forceinline__ void for_each_candidate(const RowWindows &rw, const GridJob &job, int grid_rows,
+                                                   int lane, Body &&body) {
+    for (int rg0 = 0; rg0 < rw.n_ranges; rg0 += 32) {
+        const int t = rg0 + lane;
+        int lo = 0, hi = 0;
+        if (t < rw.n_ranges) {
+            const int k = (t < rw.nx[0]) ? 0 : 1;
+            const int x = rw.min_x[k] + (k ? t - rw.nx[0] : t);
+            lo = __ldg(job.cell_start + x * grid_rows + rw.min_y[k]);
+            hi = __ldg(job.cell_start + x * grid_rows + rw.max_y[k]);
+        }
+        const int cnt = max(hi - lo, 0);
+        int incl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+            if (lane >= s) incl += v;
+        }
+        const int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const int excl = incl - cnt;
+        for (int c0 = 0; c0 < tot; c0 += 32) {
+            const int p = c0 + lane;
+            int r = 0;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const int v = __shfl_sync(0xFFFFFFFFu, incl, r + s - 1);
+                if (v <= p) r += s;
+            }
+            const int lo_r = __shfl_sync(0xFFFFFFFFu, lo, r);
+            const int ex_r = __shfl_sync(0xFFFFFFFFu, excl, r);
+            int i2 = -1;
+            if (p < tot) i2 = __ldg(job.cell_items + lo_r + (p - ex_r));
+            body(i2);
+        }
+    }
+}
+
+struct RowQuery {
+    RowWindows rw;
+    Desc q;
+    double vx, vy; // normalised query direction (lines)
+};
+
+__device__ __forceinline__ RowQuery load_row(const GridJob &job, const GridParams &gp, int i1) {
+    RowQuery r;
+    r.q = load_desc(job.d1, i1);
+    r.vx = r.vy = 0.0;
+    if (!job.is_lines) {
+        const int2 c = make_int2(__ldg(job.coords + 2 * static_cast<long long>(i1)), __ldg(job.coords + 2 * static_cast<long long>(i1) + 1));
+        r.rw.n_win = 1;
+        clamp_window(r.rw, 0, c.x, c.y, job.win, gp.grid_rows, gp.grid_cols);
+        r.rw.nx[1] = 0;
+        r.rw.min_x[1] = r.rw.min_y[1] = r.rw.max_y[1] = 0;
+    } else {
+        const int32_t *cp = job.coords + 4 * static_cast<long long>(i1);
+        const int4 c = make_int4(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3));
+        r.rw.n_win = 2;
+        clamp_window(r.rw, 0, c.x, c.y, job.win, gp.grid_rows, gp.grid_cols);
+        clamp_window(r.rw, 1, c.z, c.w, job.win, gp.grid_rows, gp.grid_cols);
+        // matching.cpp:210-211 + matching.h:43-48: v = (ep - sp) as ints -> double, divided by
+        // sqrt(x*x + y*y).  Separate roundings (the reference has no FMA); 0/0 = NaN is kept.
+        const double dx = static_cast<double>(c.z - c.x), dy = static_cast<double>(c.w - c.y);
+        const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        r.vx = __ddiv_rn(dx, mag);
+        r.vy = __ddiv_rn(dy, mag);
+    }
+    r.rw.n_ranges = r.rw.nx[0] + r.rw.nx[1];
+    return r;
+}
+
+// matching.cpp:141 (range check) and :221 (direction filter; `fabs(NaN) < th` is false -> kept).
+__device__ __forceinline__ bool candidate_ok(const GridJob &job, const GridParams &gp, const RowQuery &r, int i2) {
+    if (i2 < 0 || i2 >= job.n2) return false;
+    if (job.is_lines) {
+        const double2 d = make_double2(__ldg(job.dirs2 + 2 * static_cast<long long>(i2)), __ldg(job.dirs2 + 2 * static_cast<long long>(i2) + 1));
+        const double dp = __dadd_rn(__dmul_rn(r.vx, d.x), __dmul_rn(r.vy, d.y));
+        if (fabs(dp) < gp.line_sim_th) return false;
+    }
+    return true;
+}
+
+// Phase A for the rows [row0, row1) of one warp: wmin[i2] = min D over the chunk's pairs.
+__device__ __forceinline__ void chunk_minima(const GridJob &job, const GridParams &gp, int row0, int row1,
+                                             uint16_t *wmin, int lane) {
+    for (int i1 = row0; i1 < row1; ++i1) {
+        const RowQuery r = load_row(job, gp, i1);
+        for_each_candidate(r.rw, job, gp.grid_rows, lane, [&](int i2) {
+            if (candidate_ok(job, gp, r, i2)) {
+                const int d = hamming256(r.q, load_desc(job.d2, i2));
+                // lanes holding the same i2 (a line listed in several cells) write the same value
+                if (d < wmin[i2]) wmin[i2] = static_cast<uint16_t>(d);
+            }
+            __syncwarp();
+        });
+    }
+}
+
+// Phase C for the rows [row0, row1) of one warp.  wthr is the warp's private threshold array
+// (best_lr) or duplicate-stamp array (!best_lr).  M21 receives (D, i1) of live pairs.
+// Returns the number of accepted rows (valid in lane 0).
+template <class M21>
+__device__ __forceinline__ int chunk_match(const GridJob &job, const GridParams &gp, int row0, int row1,
+                                           uint16_t *wthr, int lane, M21 &&m21_update) {
+    int accepted = 0;
+    for (int i1 = row0; i1 < row1; ++i1) {
+        const RowQuery r = load_row(job, gp, i1);
+        uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT;
+        const uint16_t stamp = static_cast<uint16_t>(i1 - row0);
+        for_each_candidate(r.rw, job, gp.grid_rows, lane, [&](int i2) {
+            bool ok = candidate_ok(job, gp, r, i2);
+            // the candidate set is a set (std::unordered_set, matching.cpp:136/213): drop repeats
+            // inside this batch of 32 ...
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, ok ? i2 : -1 - lane);
+            ok = ok && (lane == __ffs(peers) - 1);
+            if (ok) {
+                const int d = hamming256(r.q, load_desc(job.d2, i2));
+                bool live;
+                if (gp.best_lr) {
+                    // ... and across batches: a repeat no longer beats the threshold it set itself
+                    live = d < wthr[i2];
+                    if (live) {
+                        wthr[i2] = static_cast<uint16_t>(d);
+                        m21_update(i2, d, i1);
+                    }
+                } else {
+                    live = wthr[i2] != stamp;
+                    wthr[i2] = stamp;
+                }
+                if (live) top2_insert(b0, b1, (static_cast<uint32_t>(d) << GRID_KEY_BITS) | static_cast<uint32_t>(i2));
+            }
+            __syncwarp();
+        });
+        // warp top-2: keys are distinct (one per train index) except the ABSENT sentinel
+        const uint32_t m0 = __reduce_min_sync(0xFFFFFFFFu, b0);
+        const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, (b0 == m0) ? b1 : b0);
+        if (lane == 0 && r.rw.n_ranges > 0) {
+            // matching.cpp:160 / :241 -- int -> double, one double multiply, strict compare
+            const int best_d = (m0 == KEY32_ABSENT) ? 0x7FFFFFFF : static_cast<int>(m0 >> GRID_KEY_BITS);
+            const int best_d2 = (m1 == KEY32_ABSENT) ? 0x7FFFFFFF : static_cast<int>(m1 >> GRID_KEY_BITS);
+            if (m0 != KEY32_ABSENT &&
+                static_cast<double>(best_d) < __dmul_rn(static_cast<double>(best_d2), gp.ratio)) {
+                job.m12[i1] = static_cast<int32_t>(m0 & ((1u << GRID_KEY_BITS) - 1));
+                ++accepted;
+            }
+        }
+    }
+    return accepted;
+}
+
+// ---- fused single-CTA kernel: one job per CTA (blockIdx.x), everything in one launch --------------
+// dynamic smem: uint16 wmin[W][n2_max] | uint32 m21key[n2_max]
+__global__ void __launch_bounds__(1024)
+grid_match_fused_kernel(const GridJob *__restrict__ jobs, GridParams gp, int n2_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_count;
+    const GridJob job = jobs[blockIdx.x];
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint16_t *wmin = reinterpret_cast<uint16_t *>(smem_raw);
+    uint32_t *m21key = reinterpret_cast<uint32_t *>(smem_raw + ((static_cast<size_t>(W) * n2_max * 2 + 15) & ~size_t(15)));
+    const int n1 = job.n1, n2 = job.n2;
+    if (threadIdx.x == 0) s_count = 0;
+    for (int i = threadIdx.x; i < W * n2_max; i += blockDim.x) wmin[i] = D_INF;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) m21key[i] = KEY32_ABSENT;
+    __syncthreads();
+
+    const int rpw = (n1 + W - 1) / W;
+    const int row0 = min(n1, warp * rpw), row1 = min(n1, row0 + rpw);
+    uint16_t *mine = wmin + static_cast<size_t>(warp) * n2_max;
+
+    if (gp.best_lr) {
+        chunk_minima(job, gp, row0, row1, mine, lane);
+        __syncthreads();
+        // exclusive prefix-min over the chunks, per column
+        for (int i2 = threadIdx.x; i2 < n2; i2 += blockDim.x) {
+            uint16_t run = D_INF;
+            for (int w = 0; w < W; ++w) {
+                const uint16_t t = wmin[static_cast<size_t>(w) * n2_max + i2];
+                wmin[static_cast<size_t>(w) * n2_max + i2] = run;
+                run = min(run, t);
+            }
+        }
+        __syncthreads();
+    }
+
+    const int acc = chunk_match(job, gp, row0, row1, mine, lane, [&](int i2, int d, int i1) {
+        atomicMin(&m21key[i2], (static_cast<uint32_t>(d) << GRID_KEY_BITS) | static_cast<uint32_t>(i1));
+    });
+    if (lane == 0 && acc) atomicAdd(&s_count, acc);
+    __syncthreads();
+
+    if (gp.best_lr) {
+        // mutual check (matching.cpp:166-174) over every entry >= 0, stale ones included
+        int culled = 0;
+        for (int i1 = threadIdx.x; i1 < n1; i1 += blockDim.x) {
+            const int32_t i2 = job.m12[i1];
+            if (i2 >= 0) {
+                const uint32_t k = (i2 < n2) ? m21key[i2] : KEY32_ABSENT;
+                const int back = (k == KEY32_ABSENT) ? -1 : static_cast<int>(k & ((1u << GRID_KEY_BITS) - 1));
+                if (back != i1) {
+                    job.m12[i1] = -1;
+                    ++culled;
+                }
+            }
+        }
+        if (culled) atomicSub(&s_count, culled);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *job.count = s_count;
+}
+
+// ---- chunked launch for map-sized jobs: CTA c owns rows [c*W*rpw, (c+1)*W*rpw) --------------------
+// pass 0: per-CTA column minima -> gp.cta_min[c][:]
+// (then grid_scan_kernel turns cta_min into exclusive thresholds)
+// pass 1: phase A again in shared memory, seeded prefix over the warps, phase C, accepts counted
+// dynamic smem: uint16 wmin[W][n2]
+template <int PASS>
+__global__ void __launch_bounds__(1024)
+grid_match_chunked_kernel(GridJob job, GridParams gp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n1 = job.n1, n2 = job.n2;
+    uint16_t *wmin = reinterpret_cast<uint16_t *>(smem_raw);
+    for (int i = threadIdx.x; i < W * n2; i += blockDim.x) wmin[i] = D_INF;
+    __syncthreads();
+    const long long cta_row0 = static_cast<long long>(blockIdx.x) * W * gp.rows_per_warp;
+    const int row0 = static_cast<int>(min(static_cast<long long>(n1), cta_row0 + static_cast<long long>(warp) * gp.rows_per_warp));
+    const int row1 = min(n1, row0 + gp.rows_per_warp);
+    uint16_t *mine = wmin + static_cast<size_t>(warp) * n2;
+    uint16_t *cta_min = gp.cta_min + static_cast<size_t>(blockIdx.x) * n2;
+
+    if (gp.best_lr) {
+        chunk_minima(job, gp, row0, row1, mine, lane);
+        __syncthreads();
+        if (PASS == 0) {
+            for (int i2 = threadIdx.x; i2 < n2; i2 += blockDim.x) {
+                uint16_t run = D_INF;
+                for (int w = 0; w < W; ++w) run = min(run, wmin[static_cast<size_t>(w) * n2 + i2]);
+                cta_min[i2] = run;
+            }
+            return;
+        }
+        for (int i2 = threadIdx.x; i2 < n2; i2 += blockDim.x) {
+            uint16_t run = cta_min[i2]; // threshold inherited from all earlier CTAs (and lower shards)
+            for (int w = 0; w < W; ++w) {
+                const uint16_t t = wmin[static_cast<size_t>(w) * n2 + i2];
+                wmin[static_cast<size_t>(w) * n2 + i2] = run;
+                run = min(run, t);
+            }
+        }
+        __syncthreads();
+    }
+    if (PASS == 1) {
+        const int acc = chunk_match(job, gp, row0, row1, mine, lane, [&](int i2, int d, int i1) {
+            atomicMin(&gp.m21key[i2], make_key64(static_cast<uint32_t>(d), static_cast<uint32_t>(job.i1_base + i1)));
+        });
+        if (lane == 0 && acc) atomicAdd(job.count, acc);
+    }
+}
+
+// cta_min[c][i2] <- min(seed[i2], min over c' < c of cta_min[c'][i2]); col_min[i2] = overall minimum.
+// seed (may be null) carries the minima of lower-ranked database shards (multi-GPU).
+__global__ void grid_scan_kernel(uint16_t *__restrict__ cta_min, int n_cta, int n2,
+                                 const uint16_t *__restrict__ seed, uint16_t *__restrict__ col_min) {
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i2 >= n2) return;
+    uint16_t run = seed ? seed[i2] : D_INF;
+    for (int c = 0; c < n_cta; ++c) {
+        const uint16_t t = cta_min[static_cast<size_t>(c) * n2 + i2];
+        cta_min[static_cast<size_t>(c) * n2 + i2] = run;
+        run = min(run, t);
+    }
+    if (col_min) col_min[i2] = run;
+}
+
+// m21[i2] = row of the best live pair (or -1), from the 64-bit keys of the chunked launch.
+__global__ void m21_from_keys_kernel(const unsigned long long *__restrict__ m21key, int n2,
+                                     int32_t *__restrict__ m21) {
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i2 >= n2) return;
+    const unsigned long long k = m21key[i2];
+    m21[i2] = (k == KEY64_ABSENT) ? -1 : static_cast<int32_t>(k & 0xFFFFFFFFull);
+}
+
+} // namespace plm

@@ -1,0 +1,252 @@
+// Brute-force Hamming top-2 (replaces cv::BFMatcher::knnMatch(k=2) behind StVO::matchNNR,
+// call site stvo-pl/src/matching.cpp:47-48) and the small epilogues of matchNNR / match.
+//
+// Layout: one thread owns one query descriptor in 8 registers; the CTA streams its slice of the
+// train set ("database") through shared memory in 8 KB stages (cp.async, double buffered); all
+// lanes read the same train row, so each row costs two broadcast LDS.128 per warp.  Per pair:
+// 8 LOP3(xor) + 8 POPC + IADD3 tree (or the 5-POPC carry-save form), then a 32-bit packed key
+// (dist << 22 | slice-local row) goes through a 3-instruction min/max top-2 update.  Slices are
+// merged lexicographically afterwards, so ties always resolve to the lowest train index.
+#pragma once
+#include "plm_common.cuh"
+
+namespace plm {
+
+constexpr int KNN_STAGE_ROWS = 256;               // train rows per shared-memory stage (8 KB)
+constexpr int KNN_IDX_BITS = 22;                  // slice-local row index bits in the 32-bit key
+constexpr int KNN_MAX_SLICE_ROWS = 1 << KNN_IDX_BITS;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long expand_key(uint32_t k, unsigned long long row_base) {
+    if (k == KEY32_ABSENT) return KEY64_ABSENT;
+    return make_key64(k >> KNN_IDX_BITS, 0u) + row_base + (k & (KNN_MAX_SLICE_ROWS - 1));
+}
+
+// One brute-force direction: queries q[0..n1) against train rows db[0..n2), split into n_slices
+// slices of slice_rows rows.  part[slice][query] = (best, second) packed 64-bit keys.
+struct KnnTask {
+    const uint4 *q;
+    const uint4 *db;
+    ulonglong2 *part;   // [n_slices][n1]
+    ulonglong2 *top2;   // [n1] merged result (may be null when only the acceptance is wanted)
+    int32_t *m;         // in/out match vector written by the NNR acceptance (may be null)
+    int32_t *count;     // accepted-row counter (may be null)
+    unsigned long long idx_base;
+    long long n2;
+    int n1, slice_rows, n_slices, pad_;
+};
+struct KnnTaskPair {
+    KnnTask t[2];
+};
+
+template <int THREADS, bool CSA>
+__device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, int slice, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
+    const int tid = threadIdx.x;
+    const int n1 = t.n1;
+    const int qi = qblock * THREADS + tid;
+    Desc a;
+    if (qi < n1) {
+        a = load_desc(t.q, qi);
+    } else {
+        a.lo = make_uint4(0, 0, 0, 0);
+        a.hi = a.lo;
+    }
+    const long long r0 = static_cast<long long>(slice) * t.slice_rows;
+    const long long r1 = min(t.n2, r0 + t.slice_rows);
+    const int n_rows = static_cast<int>(max(r1 - r0, 0ll));
+    const int n_stage = (n_rows + KNN_STAGE_ROWS - 1) / KNN_STAGE_ROWS;
+    const uint4 *db = t.db;
+
+    auto issue = [&](int st) {
+        const int rows = min(KNN_STAGE_ROWS, n_rows - st * KNN_STAGE_ROWS);
+        const uint4 *src = db + 2 * (r0 + static_cast<long long>(st) * KNN_STAGE_ROWS);
+        uint4 *dst = stage[st & 1];
+        for (int i = tid; i < rows * 2; i += THREADS) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+
+    uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT;
+    if (n_stage > 0) issue(0);
+    for (int st = 0; st < n_stage; ++st) {
+        if (st + 1 < n_stage) {
+            issue(st + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int rows = min(KNN_STAGE_ROWS, n_rows - st * KNN_STAGE_ROWS);
+        const uint4 *buf = stage[st & 1];
+        const uint32_t key_base = static_cast<uint32_t>(st * KNN_STAGE_ROWS);
+#pragma unroll 8
+        for (int j = 0; j < rows; ++j) {
+            const uint4 blo = buf[2 * j], bhi = buf[2 * j + 1];
+            const int d = CSA ? hamming256_csa(a, blo, bhi) : hamming256(a, blo, bhi);
+            const uint32_t k = (static_cast<uint32_t>(d) << KNN_IDX_BITS) + (key_base + j);
+            top2_insert(b0, b1, k);
+        }
+        __syncthreads();
+    }
+    if (qi < n1) {
+        const unsigned long long base = t.idx_base + static_cast<unsigned long long>(r0);
+        t.part[static_cast<size_t>(slice) * n1 + qi] = make_ulonglong2(expand_key(b0, base), expand_key(b1, base));
+    }
+}
+
+// grid = (max qblocks, max slices, n_tasks <= 2): both directions of StVO::match in one launch.
+template <int THREADS, bool CSA>
+__global__ void __launch_bounds__(THREADS) knn2_slice_kernel(const KnnTaskPair tasks) {
+    __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
+    const KnnTask &t = tasks.t[blockIdx.z];
+    if (static_cast<int>(blockIdx.x) * THREADS >= t.n1 || static_cast<int>(blockIdx.y) >= t.n_slices) return;
+    knn2_slice_body<THREADS, CSA>(t, blockIdx.x, blockIdx.y, stage);
+}
+
+// Batched form: cta_map[cta] = (task, qblock, slice); tasks live in device memory.
+template <int THREADS, bool CSA>
+__global__ void __launch_bounds__(THREADS) knn2_slice_list_kernel(const KnnTask *__restrict__ tasks, const int4 *__restrict__ cta_map) {
+    __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
+    const int4 m = __ldg(cta_map + blockIdx.x);
+    const KnnTask t = tasks[m.x];
+    knn2_slice_body<THREADS, CSA>(t, m.y, m.z, stage);
+}
+
+// Slice merge + (optionally) the matchNNR acceptance (stvo-pl/src/matching.cpp:53-58).
+// top2[q] = two smallest of part[p][q].{x,y}, p < n_slices.  Keys with different train indices are
+// distinct, so a plain lexicographic min-2 reproduces lowest-index tie-breaking across slices,
+// database shards and GPUs alike.  Acceptance is a float compare of a float product (no FMA); only
+// accepted rows are written because m is the reference's in/out matches_12.
+__device__ __forceinline__ void knn2_merge_body(const KnnTask &t, int q, float nnr, bool do_accept) {
+    bool acc = false;
+    if (q < t.n1) {
+        unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
+        for (int p = 0; p < t.n_slices; ++p) {
+            const ulonglong2 v = t.part[static_cast<size_t>(p) * t.n1 + q];
+            top2_insert(b0, b1, v.x);
+            top2_insert(b0, b1, v.y);
+        }
+        if (t.top2) t.top2[q] = make_ulonglong2(b0, b1);
+        if (do_accept && b1 != KEY64_ABSENT) {
+            const float d0 = static_cast<float>(static_cast<int>(b0 >> 32));
+            const float d1 = static_cast<float>(static_cast<int>(b1 >> 32));
+            if (d0 < __fmul_rn(d1, nnr)) {
+                t.m[q] = static_cast<int32_t>(b0 & 0xFFFFFFFFull);
+                acc = true;
+            }
+        }
+    }
+    if (do_accept) {
+        const unsigned msk = __ballot_sync(0xFFFFFFFFu, acc);
+        if ((threadIdx.x & 31) == 0 && msk && t.count) atomicAdd(t.count, __popc(msk));
+    }
+}
+
+__global__ void knn2_merge_kernel(const KnnTaskPair tasks, float nnr, int do_accept) {
+    const KnnTask &t = tasks.t[blockIdx.y];
+    knn2_merge_body(t, blockIdx.x * blockDim.x + threadIdx.x, nnr, do_accept != 0);
+}
+
+// Batched form: merge_map[cta] = (task, first query of this CTA).
+__global__ void knn2_merge_list_kernel(const KnnTask *__restrict__ tasks, const int2 *__restrict__ merge_map, float nnr, int do_accept) {
+    const int2 m = __ldg(merge_map + blockIdx.x);
+    const KnnTask t = tasks[m.x];
+    knn2_merge_body(t, m.y + threadIdx.x, nnr, do_accept != 0);
+}
+
+// Stand-alone merge of n_parts x n1 x 2 keys (database shards gathered from other GPUs).
+__global__ void top2_merge_kernel(const ulonglong2 *__restrict__ parts, int n_parts, int n1,
+                                  ulonglong2 *__restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n1) return;
+    unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
+    for (int p = 0; p < n_parts; ++p) {
+        const ulonglong2 v = parts[static_cast<size_t>(p) * n1 + q];
+        top2_insert(b0, b1, v.x);
+        top2_insert(b0, b1, v.y);
+    }
+    out[q] = make_ulonglong2(b0, b1);
+}
+
+// matchNNR acceptance from already merged keys (multi-GPU path).
+__global__ void nnr_accept_kernel(const ulonglong2 *__restrict__ top2, int n1, float nnr,
+                                  int32_t *__restrict__ m12, int32_t *__restrict__ count) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    bool acc = false;
+    if (q < n1) {
+        const ulonglong2 v = top2[q];
+        if (v.y != KEY64_ABSENT) {
+            const float d0 = static_cast<float>(static_cast<int>(v.x >> 32));
+            const float d1 = static_cast<float>(static_cast<int>(v.y >> 32));
+            if (d0 < __fmul_rn(d1, nnr)) {
+                m12[q] = static_cast<int32_t>(v.x & 0xFFFFFFFFull);
+                acc = true;
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, acc);
+    if ((threadIdx.x & 31) == 0 && m && count) atomicAdd(count, __popc(m));
+}
+
+// Mutual check (matching.cpp:80-86 / :166-174): every m12 entry >= 0 -- stale ones included --
+// whose reverse match is not i1 is culled and decrements the count.
+__global__ void cross_check_kernel(int32_t *__restrict__ m12, int n1, long long i1_base,
+                                   const int32_t *__restrict__ m21, long long n2,
+                                   int32_t *__restrict__ count) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    bool cull = false;
+    if (i1 < n1) {
+        const int32_t i2 = m12[i1];
+        if (i2 >= 0 && (i2 >= n2 || static_cast<long long>(m21[i2]) != i1_base + i1)) {
+            m12[i1] = -1;
+            cull = true;
+        }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, cull);
+    if ((threadIdx.x & 31) == 0 && m) atomicSub(count, __popc(m));
+}
+
+// StVO::distance for n independent pairs.
+__global__ void hamming_pairs_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, int n,
+                                     int32_t *__restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dist[i] = hamming256(load_desc(a, i), load_desc(b, i));
+}
+
+} // namespace plm
+
+namespace plm {
+
+// Batched mutual check: xmap[cta] = (job, first row of this CTA).
+struct XJob {
+    int32_t *m12;
+    const int32_t *m21;
+    int32_t *count;
+    int32_t n1, n2;
+};
+
+__global__ void cross_check_list_kernel(const XJob *__restrict__ jobs, const int2 *__restrict__ xmap) {
+    const int2 m = __ldg(xmap + blockIdx.x);
+    const XJob j = jobs[m.x];
+    const int i1 = m.y + threadIdx.x;
+    bool cull = false;
+    if (i1 < j.n1) {
+        const int32_t i2 = j.m12[i1];
+        if (i2 >= 0 && (i2 >= j.n2 || j.m21[i2] != i1)) {
+            j.m12[i1] = -1;
+            cull = true;
+        }
+    }
+    const unsigned msk = __ballot_sync(0xFFFFFFFFu, cull);
+    if ((threadIdx.x & 31) == 0 && msk) atomicSub(j.count, __popc(msk));
+}
+
+} // namespace plm

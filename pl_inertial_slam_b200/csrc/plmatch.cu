@@ -1,0 +1,1343 @@
+// C ABI of the B200 descriptor-matching path (include/plmatch.h): contexts, staging, launches.
+// Built for sm_100a only; there is no CPU code path behind any compute entry point.
+#include "../../include/plmatch.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "plm_common.cuh"
+#include "plm_grid.cuh"
+#include "plm_knn2.cuh"
+#include "plm_micro.cuh"
+#include "plm_stereo.cuh"
+
+#define PLM_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string &msg) {
+    g_last_error = msg;
+    return status;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            return fail(e_ == cudaErrorMemoryAllocation ? PLM_E_NOMEM : PLM_E_CUDA,               \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+        }                                                                                         \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Accumulates a block layout (offsets first, pointers once the block exists).
+struct Layout {
+    size_t total = 0;
+    size_t add(size_t bytes) {
+        const size_t off = total;
+        total = align_up(total + bytes);
+        return off;
+    }
+};
+
+} // namespace
+
+struct plm_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    char *d_buf = nullptr;
+    size_t d_cap = 0;
+    char *h_buf = nullptr; // pinned
+    size_t h_cap = 0;
+    uint64_t launches = 0;
+    bool fused_attr_set = false;
+    size_t chunked_attr[2] = {0, 0};
+
+    int ensure_device(size_t bytes) {
+        if (bytes <= d_cap) return PLM_OK;
+        CU_TRY(cudaStreamSynchronize(stream));
+        if (d_buf) CU_TRY(cudaFree(d_buf));
+        d_buf = nullptr;
+        d_cap = 0;
+        const size_t cap = align_up(bytes + bytes / 4, 1 << 20);
+        CU_TRY(cudaMalloc(reinterpret_cast<void **>(&d_buf), cap));
+        d_cap = cap;
+        return PLM_OK;
+    }
+    int ensure_pinned(size_t bytes) {
+        if (bytes <= h_cap) return PLM_OK;
+        CU_TRY(cudaStreamSynchronize(stream));
+        if (h_buf) CU_TRY(cudaFreeHost(h_buf));
+        h_buf = nullptr;
+        h_cap = 0;
+        const size_t cap = align_up(bytes + bytes / 4, 1 << 16);
+        CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_buf), cap, cudaHostAllocDefault));
+        h_cap = cap;
+        return PLM_OK;
+    }
+};
+
+struct plm_db {
+    plm_ctx *ctx = nullptr;
+    uint4 *rows = nullptr;
+    int64_t capacity = 0;
+    int64_t size = 0;
+};
+
+namespace {
+
+struct TlsCtx {
+    plm_ctx *ctx = nullptr;
+    ~TlsCtx() {
+        if (ctx) plm_ctx_destroy(ctx);
+    }
+};
+thread_local TlsCtx g_tls;
+
+int resolve_ctx(plm_ctx *&ctx) {
+    if (ctx) {
+        CU_TRY(cudaSetDevice(ctx->device));
+        return PLM_OK;
+    }
+    if (!g_tls.ctx) {
+        int dev = 0;
+        CU_TRY(cudaGetDevice(&dev));
+        const int st = plm_ctx_create(dev, &g_tls.ctx);
+        if (st != PLM_OK) return st;
+    }
+    ctx = g_tls.ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    return PLM_OK;
+}
+
+// Packs n rows of 32 bytes, `step` bytes apart, into a contiguous block.
+void pack_rows(void *dst, const uint8_t *src, int64_t n, size_t step) {
+    if (n <= 0) return;
+    if (step == 32) {
+        std::memcpy(dst, src, static_cast<size_t>(n) * 32);
+    } else {
+        uint8_t *d = static_cast<uint8_t *>(dst);
+        for (int64_t i = 0; i < n; ++i) std::memcpy(d + i * 32, src + static_cast<size_t>(i) * step, 32);
+    }
+}
+
+struct KnnPlan {
+    int threads = 128;
+    int n_slices = 1;
+    int slice_rows = plm::KNN_STAGE_ROWS;
+};
+
+// Splits the train set so that the launch has several waves of CTAs on 148 SMs; small problems get
+// narrow CTAs so that a frame-sized call still spreads over the whole chip.
+KnnPlan plan_knn(int n1, long long n2, int sm_count) {
+    KnnPlan p;
+    p.threads = (n1 >= 4096) ? 128 : 64;
+    const long long qblocks = std::max<long long>(1, (n1 + p.threads - 1) / p.threads);
+    const long long target = static_cast<long long>(sm_count) * 16;
+    long long slices = std::max<long long>(1, (target + qblocks - 1) / qblocks);
+    const long long max_slices = std::max<long long>(1, (n2 + 63) / 64);
+    slices = std::min(slices, max_slices);
+    long long rows = (n2 + slices - 1) / slices;
+    rows = std::max<long long>(64, (rows + 63) / 64 * 64);
+    rows = std::min<long long>(rows, plm::KNN_MAX_SLICE_ROWS);
+    p.slice_rows = static_cast<int>(rows);
+    p.n_slices = static_cast<int>(std::max<long long>(1, (n2 + rows - 1) / rows));
+    return p;
+}
+
+int g_use_csa = -1;
+bool use_csa() {
+    if (g_use_csa < 0) {
+        const char *e = std::getenv("PLM_KNN_VARIANT");
+        g_use_csa = (e && std::strcmp(e, "popc8") == 0) ? 0 : 1;
+    }
+    return g_use_csa != 0;
+}
+
+int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int threads) {
+    int qb = 0, sl = 0;
+    for (int i = 0; i < n_tasks; ++i) {
+        qb = std::max(qb, (tp.t[i].n1 + threads - 1) / threads);
+        sl = std::max(sl, tp.t[i].n_slices);
+    }
+    if (qb == 0 || sl == 0) return PLM_OK;
+    const dim3 grid(qb, sl, n_tasks);
+    const bool csa = use_csa();
+    if (threads == 128) {
+        if (csa) plm::knn2_slice_kernel<128, true><<<grid, 128, 0, ctx->stream>>>(tp);
+        else plm::knn2_slice_kernel<128, false><<<grid, 128, 0, ctx->stream>>>(tp);
+    } else {
+        if (csa) plm::knn2_slice_kernel<64, true><<<grid, 64, 0, ctx->stream>>>(tp);
+        else plm::knn2_slice_kernel<64, false><<<grid, 64, 0, ctx->stream>>>(tp);
+    }
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+int launch_knn_merge(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, float nnr, int do_accept) {
+    int n = 0;
+    for (int i = 0; i < n_tasks; ++i) n = std::max(n, tp.t[i].n1);
+    if (n == 0) return PLM_OK;
+    const dim3 grid((n + 127) / 128, n_tasks);
+    plm::knn2_merge_kernel<<<grid, 128, 0, ctx->stream>>>(tp, nnr, do_accept);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+int check_desc(const uint8_t *d, int n, size_t step) {
+    if (n < 0) return fail(PLM_E_INVALID, "negative row count");
+    if (n > 0 && !d) return fail(PLM_E_INVALID, "null descriptor pointer");
+    if (n > 0 && step < 32) return fail(PLM_E_INVALID, "descriptor step < 32 bytes");
+    return PLM_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+PLM_API int plm_set_option(const char *key, int value) {
+    if (!key) return fail(PLM_E_INVALID, "null key");
+    if (std::strcmp(key, "knn_variant") == 0) {
+        g_use_csa = value ? 1 : 0;
+        return PLM_OK;
+    }
+    return fail(PLM_E_INVALID, std::string("unknown option ") + key);
+}
+
+PLM_API int plm_version(void) { return PLM_VERSION; }
+
+PLM_API const char *plm_status_string(int status) {
+    switch (status) {
+    case PLM_OK: return "ok";
+    case PLM_E_INVALID: return "invalid argument";
+    case PLM_E_SIZE: return "size mismatch between features and descriptors";
+    case PLM_E_TRAIN: return "fewer than two train descriptors";
+    case PLM_E_GRID: return "[GridStructure] invalid dimension";
+    case PLM_E_RATIO: return "matchGrid ratio must be <= 1";
+    case PLM_E_CUDA: return "CUDA failure";
+    case PLM_E_NOMEM: return "out of memory";
+    case PLM_E_UNSUPPORTED: return "unsupported size";
+    default: return "unknown status";
+    }
+}
+
+PLM_API const char *plm_last_error(void) { return g_last_error.c_str(); }
+
+PLM_API int plm_device_count(int *count) {
+    if (!count) return fail(PLM_E_INVALID, "null count");
+    *count = 0;
+    CU_TRY(cudaGetDeviceCount(count));
+    return PLM_OK;
+}
+
+PLM_API int plm_ctx_create(int device, plm_ctx **out) {
+    if (!out) return fail(PLM_E_INVALID, "null out");
+    *out = nullptr;
+    int n = 0;
+    CU_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(PLM_E_CUDA, "no such CUDA device");
+    CU_TRY(cudaSetDevice(device));
+    plm_ctx *c = new (std::nothrow) plm_ctx();
+    if (!c) return fail(PLM_E_NOMEM, "host allocation failed");
+    c->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(PLM_E_CUDA, cudaGetErrorString(e));
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(PLM_E_CUDA, cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return PLM_OK;
+}
+
+PLM_API int plm_ctx_destroy(plm_ctx *ctx) {
+    if (!ctx) return PLM_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->own_stream);
+        cudaStreamDestroy(ctx->own_stream);
+    }
+    if (ctx->d_buf) cudaFree(ctx->d_buf);
+    if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
+    if (g_tls.ctx == ctx) g_tls.ctx = nullptr;
+    delete ctx;
+    return PLM_OK;
+}
+
+PLM_API void *plm_ctx_stream(plm_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+PLM_API int plm_ctx_set_stream(plm_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(PLM_E_INVALID, "null ctx");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return PLM_OK;
+}
+
+PLM_API int plm_ctx_synchronize(plm_ctx *ctx) {
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return PLM_OK;
+}
+
+PLM_API uint64_t plm_ctx_launch_count(plm_ctx *ctx) {
+    if (!ctx) ctx = g_tls.ctx;
+    return ctx ? ctx->launches : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+PLM_API int plm_hamming256(plm_ctx *ctx, const uint8_t *a, size_t step_a, const uint8_t *b, size_t step_b,
+                           int n, int32_t *dist) {
+    int st = check_desc(a, n, step_a);
+    if (st == PLM_OK) st = check_desc(b, n, step_b);
+    if (st != PLM_OK) return st;
+    if (n > 0 && !dist) return fail(PLM_E_INVALID, "null dist");
+    if (n == 0) return PLM_OK;
+    if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+    Layout L;
+    const size_t o_a = L.add(size_t(n) * 32), o_b = L.add(size_t(n) * 32);
+    const size_t in_bytes = L.total;
+    const size_t o_d = L.add(size_t(n) * 4);
+    if ((st = ctx->ensure_pinned(L.total)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    pack_rows(ctx->h_buf + o_a, a, n, step_a);
+    pack_rows(ctx->h_buf + o_b, b, n, step_b);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    plm::hamming_pairs_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(
+        reinterpret_cast<const uint4 *>(ctx->d_buf + o_a), reinterpret_cast<const uint4 *>(ctx->d_buf + o_b), n,
+        reinterpret_cast<int32_t *>(ctx->d_buf + o_d));
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_d, ctx->d_buf + o_d, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(dist, ctx->h_buf + o_d, size_t(n) * 4);
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Brute force on device-resident rows; partial buffers come from the context scratch AFTER
+// `reserved` bytes (which the caller is using for its own staged data).
+namespace {
+
+struct KnnScratch {
+    size_t part_off[2] = {0, 0};
+};
+
+int build_knn_task(plm_ctx *ctx, Layout &L, plm::KnnTask &t, KnnPlan &plan, const uint4 *q, int n1, const uint4 *db,
+                   long long n2, unsigned long long idx_base, size_t &part_off) {
+    plan = plan_knn(n1, n2, ctx->sm_count);
+    t.q = q;
+    t.db = db;
+    t.n1 = n1;
+    t.n2 = n2;
+    t.idx_base = idx_base;
+    t.slice_rows = plan.slice_rows;
+    t.n_slices = plan.n_slices;
+    t.part = nullptr;
+    t.top2 = nullptr;
+    t.m = nullptr;
+    t.count = nullptr;
+    t.pad_ = 0;
+    part_off = L.add(size_t(plan.n_slices) * size_t(std::max(n1, 1)) * sizeof(ulonglong2));
+    return PLM_OK;
+}
+
+} // namespace
+
+PLM_API int plm_dev_knn2(plm_ctx *ctx, const void *d1_dev, int n1, const void *d2_dev, int64_t n2, uint64_t idx_base,
+                         uint64_t *top2_dev) {
+    if (n1 < 0 || n2 < 0) return fail(PLM_E_INVALID, "negative row count");
+    if ((n1 > 0 && !d1_dev) || (n2 > 0 && !d2_dev) || (n1 > 0 && !top2_dev)) return fail(PLM_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(d1_dev) | reinterpret_cast<uintptr_t>(d2_dev) | reinterpret_cast<uintptr_t>(top2_dev)) & 15)
+        return fail(PLM_E_INVALID, "device pointers must be 16-byte aligned");
+    if (idx_base + static_cast<uint64_t>(n2) > (1ull << 32)) return fail(PLM_E_UNSUPPORTED, "train index does not fit 32 bits");
+    if (n1 == 0) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout L;
+    plm::KnnTaskPair tp;
+    std::memset(&tp, 0, sizeof(tp));
+    KnnPlan plan;
+    size_t part_off = 0;
+    build_knn_task(ctx, L, tp.t[0], plan, static_cast<const uint4 *>(d1_dev), n1, static_cast<const uint4 *>(d2_dev), n2,
+                   idx_base, part_off);
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    tp.t[0].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off);
+    tp.t[0].top2 = reinterpret_cast<ulonglong2 *>(top2_dev);
+    if ((st = launch_knn_slices(ctx, tp, 1, plan.threads)) != PLM_OK) return st;
+    return launch_knn_merge(ctx, tp, 1, 0.f, 0);
+}
+
+PLM_API int plm_dev_top2_merge(plm_ctx *ctx, const uint64_t *parts_dev, int n_parts, int n1, uint64_t *top2_out_dev) {
+    if (n_parts < 0 || n1 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n1 > 0 && (!parts_dev || !top2_out_dev)) return fail(PLM_E_INVALID, "null pointer");
+    if (n1 == 0) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::top2_merge_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const ulonglong2 *>(parts_dev), n_parts, n1,
+                                                                     reinterpret_cast<ulonglong2 *>(top2_out_dev));
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_nnr_accept(plm_ctx *ctx, const uint64_t *top2_dev, int n1, float nnr, int32_t *m12_dev_inout,
+                               int32_t *count_dev) {
+    if (n1 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n1 > 0 && (!top2_dev || !m12_dev_inout)) return fail(PLM_E_INVALID, "null pointer");
+    if (n1 == 0) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::nnr_accept_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const ulonglong2 *>(top2_dev), n1, nnr,
+                                                                     m12_dev_inout, count_dev);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_cross_check(plm_ctx *ctx, int32_t *m12_dev_inout, int n1, int64_t i1_base, const int32_t *m21_dev,
+                                int64_t n2, int32_t *count_dev) {
+    if (n1 < 0 || n2 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n1 > 0 && (!m12_dev_inout || !count_dev || (n2 > 0 && !m21_dev))) return fail(PLM_E_INVALID, "null pointer");
+    if (n1 == 0) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::cross_check_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(m12_dev_inout, n1, i1_base, m21_dev, n2, count_dev);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+PLM_API int plm_knn2(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2, size_t step2,
+                     uint64_t idx_base, uint64_t *top2) {
+    int st = check_desc(d1, n1, step1);
+    if (st == PLM_OK) st = check_desc(d2, n2, step2);
+    if (st != PLM_OK) return st;
+    if (n1 > 0 && !top2) return fail(PLM_E_INVALID, "null top2");
+    if (idx_base + static_cast<uint64_t>(n2) > (1ull << 32)) return fail(PLM_E_UNSUPPORTED, "train index does not fit 32 bits");
+    if (n1 == 0) return PLM_OK;
+    if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+
+    Layout L;
+    const size_t o_d1 = L.add(size_t(n1) * 32), o_d2 = L.add(size_t(n2) * 32);
+    const size_t in_bytes = L.total;
+    const size_t o_top2 = L.add(size_t(n1) * 16);
+    const size_t staged = L.total;
+    plm::KnnTaskPair tp;
+    std::memset(&tp, 0, sizeof(tp));
+    KnnPlan plan;
+    size_t part_off = 0;
+    build_knn_task(ctx, L, tp.t[0], plan, nullptr, n1, nullptr, n2, idx_base, part_off);
+    if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    pack_rows(ctx->h_buf + o_d1, d1, n1, step1);
+    pack_rows(ctx->h_buf + o_d2, d2, n2, step2);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    tp.t[0].q = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d1);
+    tp.t[0].db = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d2);
+    tp.t[0].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off);
+    tp.t[0].top2 = reinterpret_cast<ulonglong2 *>(ctx->d_buf + o_top2);
+    if ((st = launch_knn_slices(ctx, tp, 1, plan.threads)) != PLM_OK) return st;
+    if ((st = launch_knn_merge(ctx, tp, 1, 0.f, 0)) != PLM_OK) return st;
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_top2, ctx->d_buf + o_top2, size_t(n1) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(top2, ctx->h_buf + o_top2, size_t(n1) * 16);
+    return PLM_OK;
+}
+
+// StVO::matchNNR / StVO::match share one implementation: direction 21 + mutual check are added
+// when best_lr is set.
+static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2, size_t step2,
+                      float nnr, int best_lr, int32_t *m12_inout, int *n_matches) {
+    int st = check_desc(d1, n1, step1);
+    if (st == PLM_OK) st = check_desc(d2, n2, step2);
+    if (st != PLM_OK) return st;
+    if (!n_matches) return fail(PLM_E_INVALID, "null n_matches");
+    if (n1 > 0 && !m12_inout) return fail(PLM_E_INVALID, "null m12");
+    *n_matches = 0;
+    // matches_[idx][1] is read unconditionally (matching.cpp:54): fewer than 2 train rows is UB /
+    // a throw in the reference.  With best_lr the roles swap, so both sides need >= 2 rows.
+    if (n2 < 2) return fail(PLM_E_TRAIN, "matchNNR needs at least 2 train descriptors");
+    if (best_lr && n1 < 2) return fail(PLM_E_TRAIN, "match (bestLRMatches) needs at least 2 descriptors on both sides");
+    if (n1 == 0) return PLM_OK;
+    if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+
+    Layout L;
+    const size_t o_d1 = L.add(size_t(n1) * 32), o_d2 = L.add(size_t(n2) * 32);
+    const size_t o_m12 = L.add(size_t(n1) * 4 + 4); // m12 followed by the counter
+    const size_t in_bytes = L.total;
+    const size_t o_m21 = L.add(size_t(n2) * 4);
+    const size_t staged = L.total;
+    plm::KnnTaskPair tp;
+    std::memset(&tp, 0, sizeof(tp));
+    KnnPlan plan[2];
+    size_t part_off[2] = {0, 0};
+    build_knn_task(ctx, L, tp.t[0], plan[0], nullptr, n1, nullptr, n2, 0, part_off[0]);
+    if (best_lr) build_knn_task(ctx, L, tp.t[1], plan[1], nullptr, n2, nullptr, n1, 0, part_off[1]);
+    if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+
+    pack_rows(ctx->h_buf + o_d1, d1, n1, step1);
+    pack_rows(ctx->h_buf + o_d2, d2, n2, step2);
+    std::memcpy(ctx->h_buf + o_m12, m12_inout, size_t(n1) * 4);
+    std::memset(ctx->h_buf + o_m12 + size_t(n1) * 4, 0, 4);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    const uint4 *dd1 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d1);
+    const uint4 *dd2 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d2);
+    int32_t *dm12 = reinterpret_cast<int32_t *>(ctx->d_buf + o_m12);
+    int32_t *dcount = dm12 + n1;
+    int32_t *dm21 = reinterpret_cast<int32_t *>(ctx->d_buf + o_m21);
+    tp.t[0].q = dd1;
+    tp.t[0].db = dd2;
+    tp.t[0].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off[0]);
+    tp.t[0].m = dm12;
+    tp.t[0].count = dcount;
+    int n_tasks = 1;
+    if (best_lr) {
+        CU_TRY(cudaMemsetAsync(dm21, 0xFF, size_t(n2) * 4, ctx->stream));
+        tp.t[1].q = dd2;
+        tp.t[1].db = dd1;
+        tp.t[1].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off[1]);
+        tp.t[1].m = dm21;
+        tp.t[1].count = nullptr; // the reference ignores the 21 count (matching.cpp:72,77)
+        n_tasks = 2;
+    }
+    const int threads = std::max(plan[0].threads, best_lr ? plan[1].threads : 0);
+    // both directions share one launch and therefore one CTA width; the slice plans stay valid
+    if ((st = launch_knn_slices(ctx, tp, n_tasks, threads)) != PLM_OK) return st;
+    if ((st = launch_knn_merge(ctx, tp, n_tasks, nnr, 1)) != PLM_OK) return st;
+    if (best_lr) {
+        plm::cross_check_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(dm12, n1, 0, dm21, n2, dcount);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_m12, ctx->d_buf + o_m12, size_t(n1) * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(m12_inout, ctx->h_buf + o_m12, size_t(n1) * 4);
+    int32_t cnt;
+    std::memcpy(&cnt, ctx->h_buf + o_m12 + size_t(n1) * 4, 4);
+    *n_matches = cnt;
+    return PLM_OK;
+}
+
+PLM_API int plm_match_nnr(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2, size_t step2,
+                          float nnr, int32_t *m12_inout, int *n_matches) {
+    return match_impl(ctx, d1, n1, step1, d2, n2, step2, nnr, 0, m12_inout, n_matches);
+}
+
+PLM_API int plm_match(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2, size_t step2,
+                      float nnr, int best_lr, int32_t *m12_inout, int *n_matches) {
+    return match_impl(ctx, d1, n1, step1, d2, n2, step2, nnr, best_lr ? 1 : 0, m12_inout, n_matches);
+}
+
+// ---------------------------------------------------------------------------------------------
+// matchGrid
+namespace {
+
+constexpr int GRID_N2_MAX = 32768;
+constexpr int GRID_CHUNK_ROWS_PER_WARP = 32;
+constexpr int GRID_FUSED_MAX_ROWS = 4096;
+
+struct FusedShape {
+    int warps;
+    size_t smem;
+};
+
+size_t fused_smem(int warps, int n2_max) { return align_up(size_t(warps) * n2_max * 2, 16) + size_t(n2_max) * 4; }
+
+// Number of warps of the fused kernel: as many chunks as shared memory allows, at least ~4 rows each.
+FusedShape fused_shape(const plm_ctx *ctx, int n1_max, int n2_max) {
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+    int w = std::min(32, std::max(1, (n1_max + 3) / 4));
+    while (w > 1 && fused_smem(w, n2_max) > budget) --w;
+    return {w, fused_smem(w, n2_max)};
+}
+
+int validate_grid(const int32_t *cell_start, const int32_t *cell_items, int grid_rows, int grid_cols, int *n_items) {
+    if (grid_rows <= 0 || grid_cols <= 0) return fail(PLM_E_GRID, "[GridStructure] invalid dimension");
+    if (static_cast<long long>(grid_rows) * grid_cols > (1 << 24)) return fail(PLM_E_UNSUPPORTED, "grid too large");
+    if (!cell_start) return fail(PLM_E_INVALID, "null cell_start");
+    const int n_cells = grid_rows * grid_cols;
+    if (cell_start[0] != 0) return fail(PLM_E_GRID, "cell_start[0] must be 0");
+    for (int c = 0; c < n_cells; ++c)
+        if (cell_start[c + 1] < cell_start[c]) return fail(PLM_E_GRID, "cell_start must be non-decreasing");
+    *n_items = cell_start[n_cells];
+    if (*n_items > 0 && !cell_items) return fail(PLM_E_INVALID, "null cell_items");
+    return PLM_OK;
+}
+
+int launch_grid_fused(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, const plm::GridParams &gp, int n1_max,
+                      int n2_max) {
+    const FusedShape fs = fused_shape(ctx, n1_max, n2_max);
+    if (fs.smem > ctx->smem_optin) return fail(PLM_E_UNSUPPORTED, "matchGrid: train set too large for shared memory");
+    if (!ctx->fused_attr_set) {
+        CU_TRY(cudaFuncSetAttribute(plm::grid_match_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(std::min<size_t>(ctx->smem_optin, 227 * 1024))));
+        ctx->fused_attr_set = true;
+    }
+    plm::grid_match_fused_kernel<<<n_jobs, fs.warps * 32, fs.smem, ctx->stream>>>(jobs_dev, gp, n2_max);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// Map-sized job: pass 0 (per-CTA minima) -> scan -> pass 1 (match) -> mutual check.
+// scratch: cta_min [n_cta][n2] u16, m21key [n2] u64, m21 [n2] i32 -- offsets into ctx->d_buf.
+int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams gp, size_t off_cta_min, size_t off_m21key,
+                        size_t off_m21, int warps, int n_cta) {
+    const size_t smem = size_t(warps) * job.n2 * 2;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (ctx->chunked_attr[pass] < smem) {
+            if (pass == 0)
+                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(std::min<size_t>(ctx->smem_optin, 227 * 1024))));
+            else
+                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(std::min<size_t>(ctx->smem_optin, 227 * 1024))));
+            ctx->chunked_attr[pass] = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+        }
+    }
+    gp.rows_per_warp = GRID_CHUNK_ROWS_PER_WARP;
+    gp.cta_min = reinterpret_cast<uint16_t *>(ctx->d_buf + off_cta_min);
+    gp.m21key = reinterpret_cast<unsigned long long *>(ctx->d_buf + off_m21key);
+    int32_t *m21 = reinterpret_cast<int32_t *>(ctx->d_buf + off_m21);
+    if (gp.best_lr) {
+        CU_TRY(cudaMemsetAsync(gp.m21key, 0xFF, size_t(job.n2) * 8, ctx->stream));
+        plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        plm::grid_scan_kernel<<<(job.n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, job.n2, nullptr, nullptr);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    plm::grid_match_chunked_kernel<1><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    if (gp.best_lr) {
+        plm::m21_from_keys_kernel<<<(job.n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.m21key, job.n2, m21);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        plm::cross_check_kernel<<<(job.n1 + 127) / 128, 128, 0, ctx->stream>>>(job.m12, job.n1, job.i1_base, m21, job.n2,
+                                                                              job.count);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    return PLM_OK;
+}
+
+int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uint8_t *d1, int n1, size_t step1,
+                    const int32_t *cell_start, const int32_t *cell_items, int grid_rows, int grid_cols, const uint8_t *d2,
+                    int n2, size_t step2, const double *dirs2, double line_sim_th, const int32_t win[4], double ratio,
+                    int best_lr, int32_t *m12_inout, int *n_matches) {
+    int st = check_desc(d1, n1, step1);
+    if (st == PLM_OK) st = check_desc(d2, n2, step2);
+    if (st != PLM_OK) return st;
+    if (!n_matches || !win) return fail(PLM_E_INVALID, "null n_matches / win");
+    if (n1 > 0 && (!coords || !m12_inout)) return fail(PLM_E_INVALID, "null coords / m12");
+    if (is_lines && n2 > 0 && !dirs2) return fail(PLM_E_INVALID, "null dirs2");
+    *n_matches = 0;
+    if (ratio > 1.0) return fail(PLM_E_RATIO, plm_status_string(PLM_E_RATIO));
+    int n_items = 0;
+    if ((st = validate_grid(cell_start, cell_items, grid_rows, grid_cols, &n_items)) != PLM_OK) return st;
+    if (n2 > GRID_N2_MAX) return fail(PLM_E_UNSUPPORTED, "matchGrid supports at most 32768 train features");
+    if (n1 == 0) return PLM_OK;
+    if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+
+    const int n_cells = grid_rows * grid_cols;
+    const int cpq = is_lines ? 4 : 2;
+    Layout L;
+    const size_t o_d1 = L.add(size_t(n1) * 32), o_d2 = L.add(size_t(std::max(n2, 1)) * 32);
+    const size_t o_xy = L.add(size_t(n1) * cpq * 4);
+    const size_t o_cs = L.add(size_t(n_cells + 1) * 4), o_ci = L.add(size_t(std::max(n_items, 1)) * 4);
+    const size_t o_dir = L.add(is_lines ? size_t(std::max(n2, 1)) * 16 : 0);
+    const size_t o_job = L.add(sizeof(plm::GridJob));
+    const size_t o_m12 = L.add(size_t(n1) * 4 + 4);
+    const size_t in_bytes = L.total;
+    const size_t staged = L.total;
+
+    const bool fused = n1 <= GRID_FUSED_MAX_ROWS && n1 < (1 << plm::GRID_KEY_BITS);
+    int warps = 0, n_cta = 0;
+    size_t o_cta_min = 0, o_m21key = 0, o_m21 = 0;
+    if (!fused) {
+        const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+        warps = 16;
+        while (warps > 1 && size_t(warps) * std::max(n2, 1) * 2 > budget) warps >>= 1;
+        const long long rows_per_cta = static_cast<long long>(warps) * GRID_CHUNK_ROWS_PER_WARP;
+        n_cta = static_cast<int>((n1 + rows_per_cta - 1) / rows_per_cta);
+        o_cta_min = L.add(size_t(n_cta) * std::max(n2, 1) * 2);
+        o_m21key = L.add(size_t(std::max(n2, 1)) * 8);
+        o_m21 = L.add(size_t(std::max(n2, 1)) * 4);
+    }
+    if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+
+    pack_rows(ctx->h_buf + o_d1, d1, n1, step1);
+    pack_rows(ctx->h_buf + o_d2, d2, n2, step2);
+    std::memcpy(ctx->h_buf + o_xy, coords, size_t(n1) * cpq * 4);
+    std::memcpy(ctx->h_buf + o_cs, cell_start, size_t(n_cells + 1) * 4);
+    if (n_items > 0) std::memcpy(ctx->h_buf + o_ci, cell_items, size_t(n_items) * 4);
+    if (is_lines && n2 > 0) std::memcpy(ctx->h_buf + o_dir, dirs2, size_t(n2) * 16);
+    std::memcpy(ctx->h_buf + o_m12, m12_inout, size_t(n1) * 4);
+    std::memset(ctx->h_buf + o_m12 + size_t(n1) * 4, 0, 4);
+
+    plm::GridJob job;
+    std::memset(&job, 0, sizeof(job));
+    job.coords = reinterpret_cast<const int32_t *>(ctx->d_buf + o_xy);
+    job.d1 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d1);
+    job.cell_start = reinterpret_cast<const int32_t *>(ctx->d_buf + o_cs);
+    job.cell_items = reinterpret_cast<const int32_t *>(ctx->d_buf + o_ci);
+    job.d2 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d2);
+    job.dirs2 = reinterpret_cast<const double *>(ctx->d_buf + o_dir);
+    job.m12 = reinterpret_cast<int32_t *>(ctx->d_buf + o_m12);
+    job.count = job.m12 + n1;
+    job.n1 = n1;
+    job.n2 = n2;
+    job.is_lines = is_lines;
+    for (int i = 0; i < 4; ++i) job.win[i] = win[i];
+    job.i1_base = 0;
+    std::memcpy(ctx->h_buf + o_job, &job, sizeof(job));
+
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    plm::GridParams gp;
+    std::memset(&gp, 0, sizeof(gp));
+    gp.grid_rows = grid_rows;
+    gp.grid_cols = grid_cols;
+    gp.best_lr = best_lr ? 1 : 0;
+    gp.ratio = ratio;
+    gp.line_sim_th = line_sim_th;
+    if (fused) {
+        st = launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(ctx->d_buf + o_job), 1, gp, n1, std::max(n2, 1));
+    } else {
+        st = launch_grid_chunked(ctx, job, gp, o_cta_min, o_m21key, o_m21, warps, n_cta);
+    }
+    if (st != PLM_OK) return st;
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_m12, ctx->d_buf + o_m12, size_t(n1) * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(m12_inout, ctx->h_buf + o_m12, size_t(n1) * 4);
+    int32_t cnt;
+    std::memcpy(&cnt, ctx->h_buf + o_m12 + size_t(n1) * 4, 4);
+    *n_matches = cnt;
+    return PLM_OK;
+}
+
+} // namespace
+
+PLM_API int plm_match_grid_points(plm_ctx *ctx, const int32_t *xy, const uint8_t *d1, int n1, size_t step1,
+                                  const int32_t *cell_start, const int32_t *cell_items, int grid_rows, int grid_cols,
+                                  const uint8_t *d2, int n2, size_t step2, const int32_t win[4], double ratio, int best_lr,
+                                  int32_t *m12_inout, int *n_matches) {
+    return match_grid_impl(ctx, 0, xy, d1, n1, step1, cell_start, cell_items, grid_rows, grid_cols, d2, n2, step2, nullptr,
+                           0.0, win, ratio, best_lr, m12_inout, n_matches);
+}
+
+PLM_API int plm_match_grid_lines(plm_ctx *ctx, const int32_t *xyxy, const uint8_t *d1, int n1, size_t step1,
+                                 const int32_t *cell_start, const int32_t *cell_items, int grid_rows, int grid_cols,
+                                 const uint8_t *d2, int n2, size_t step2, const double *dirs2, double line_sim_th,
+                                 const int32_t win[4], double ratio, int best_lr, int32_t *m12_inout, int *n_matches) {
+    return match_grid_impl(ctx, 1, xyxy, d1, n1, step1, cell_start, cell_items, grid_rows, grid_cols, d2, n2, step2, dirs2,
+                           line_sim_th, win, ratio, best_lr, m12_inout, n_matches);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stereo post-filters
+PLM_API int plm_stereo_filter_points(plm_ctx *ctx, const float *kp_l, int n1, const float *kp_r, int n2, const int32_t *m12,
+                                     double max_dist_epip, double min_disp, uint8_t *keep, double *disp, int *n_kept) {
+    if (n1 < 0 || n2 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (!n_kept) return fail(PLM_E_INVALID, "null n_kept");
+    *n_kept = 0;
+    if (n1 == 0) return PLM_OK;
+    if (!kp_l || !m12 || !keep || !disp || (n2 > 0 && !kp_r)) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout L;
+    const size_t o_l = L.add(size_t(n1) * 8), o_r = L.add(size_t(std::max(n2, 1)) * 8), o_m = L.add(size_t(n1) * 4);
+    const size_t in_bytes = L.total;
+    const size_t o_out = L.add(size_t(n1) * 8 + size_t(n1) + 8); // disp | keep | count
+    if ((st = ctx->ensure_pinned(L.total)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    std::memcpy(ctx->h_buf + o_l, kp_l, size_t(n1) * 8);
+    if (n2 > 0) std::memcpy(ctx->h_buf + o_r, kp_r, size_t(n2) * 8);
+    std::memcpy(ctx->h_buf + o_m, m12, size_t(n1) * 4);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    double *d_disp = reinterpret_cast<double *>(ctx->d_buf + o_out);
+    uint8_t *d_keep = reinterpret_cast<uint8_t *>(ctx->d_buf + o_out + size_t(n1) * 8);
+    const size_t cnt_off = align_up(size_t(n1) * 8 + size_t(n1), 4);
+    int32_t *d_cnt = reinterpret_cast<int32_t *>(ctx->d_buf + o_out + cnt_off);
+    CU_TRY(cudaMemsetAsync(d_cnt, 0, 4, ctx->stream));
+    plm::stereo_filter_points_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(
+        reinterpret_cast<const float2 *>(ctx->d_buf + o_l), reinterpret_cast<const float2 *>(ctx->d_buf + o_r), n2,
+        reinterpret_cast<const int32_t *>(ctx->d_buf + o_m), n1, max_dist_epip, min_disp, d_keep, d_disp, d_cnt);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_out, ctx->d_buf + o_out, cnt_off + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(disp, ctx->h_buf + o_out, size_t(n1) * 8);
+    std::memcpy(keep, ctx->h_buf + o_out + size_t(n1) * 8, size_t(n1));
+    int32_t cnt;
+    std::memcpy(&cnt, ctx->h_buf + o_out + cnt_off, 4);
+    *n_kept = cnt;
+    return PLM_OK;
+}
+
+PLM_API int plm_stereo_filter_lines(plm_ctx *ctx, const float *ln_l, int n1, const float *ln_r, int n2, const int32_t *m12,
+                                    double min_disp, double line_horiz_th, double stereo_overlap_th,
+                                    double ls_min_disp_ratio, uint8_t *keep, double *disp_se, int *n_kept) {
+    if (n1 < 0 || n2 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (!n_kept) return fail(PLM_E_INVALID, "null n_kept");
+    *n_kept = 0;
+    if (n1 == 0) return PLM_OK;
+    if (!ln_l || !m12 || !keep || !disp_se || (n2 > 0 && !ln_r)) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout L;
+    const size_t o_l = L.add(size_t(n1) * 16), o_r = L.add(size_t(std::max(n2, 1)) * 16), o_m = L.add(size_t(n1) * 4);
+    const size_t in_bytes = L.total;
+    const size_t o_out = L.add(size_t(n1) * 16 + size_t(n1) + 8);
+    if ((st = ctx->ensure_pinned(L.total)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    std::memcpy(ctx->h_buf + o_l, ln_l, size_t(n1) * 16);
+    if (n2 > 0) std::memcpy(ctx->h_buf + o_r, ln_r, size_t(n2) * 16);
+    std::memcpy(ctx->h_buf + o_m, m12, size_t(n1) * 4);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    double *d_disp = reinterpret_cast<double *>(ctx->d_buf + o_out);
+    uint8_t *d_keep = reinterpret_cast<uint8_t *>(ctx->d_buf + o_out + size_t(n1) * 16);
+    const size_t cnt_off = align_up(size_t(n1) * 16 + size_t(n1), 4);
+    int32_t *d_cnt = reinterpret_cast<int32_t *>(ctx->d_buf + o_out + cnt_off);
+    CU_TRY(cudaMemsetAsync(d_cnt, 0, 4, ctx->stream));
+    plm::stereo_filter_lines_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(
+        reinterpret_cast<const float4 *>(ctx->d_buf + o_l), reinterpret_cast<const float4 *>(ctx->d_buf + o_r), n2,
+        reinterpret_cast<const int32_t *>(ctx->d_buf + o_m), n1, min_disp, line_horiz_th, stereo_overlap_th,
+        ls_min_disp_ratio, d_keep, d_disp, d_cnt);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_out, ctx->d_buf + o_out, cnt_off + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(disp_se, ctx->h_buf + o_out, size_t(n1) * 16);
+    std::memcpy(keep, ctx->h_buf + o_out + size_t(n1) * 16, size_t(n1));
+    int32_t cnt;
+    std::memcpy(&cnt, ctx->h_buf + o_out + cnt_off, 4);
+    *n_kept = cnt;
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Database shard
+PLM_API int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out) {
+    if (!out) return fail(PLM_E_INVALID, "null out");
+    *out = nullptr;
+    if (capacity_rows < 0) return fail(PLM_E_INVALID, "negative capacity");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm_db *db = new (std::nothrow) plm_db();
+    if (!db) return fail(PLM_E_NOMEM, "host allocation failed");
+    db->ctx = ctx;
+    db->capacity = capacity_rows;
+    if (capacity_rows > 0) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&db->rows), size_t(capacity_rows) * 32);
+        if (e != cudaSuccess) {
+            delete db;
+            return fail(e == cudaErrorMemoryAllocation ? PLM_E_NOMEM : PLM_E_CUDA, cudaGetErrorString(e));
+        }
+    }
+    *out = db;
+    return PLM_OK;
+}
+
+PLM_API int plm_db_destroy(plm_db *db) {
+    if (!db) return PLM_OK;
+    if (db->ctx) cudaSetDevice(db->ctx->device);
+    if (db->rows) cudaFree(db->rows);
+    delete db;
+    return PLM_OK;
+}
+
+PLM_API int plm_db_upload(plm_db *db, const uint8_t *rows, int64_t n, size_t step, int64_t at_row) {
+    if (!db) return fail(PLM_E_INVALID, "null db");
+    if (n < 0 || at_row < 0 || at_row + n > db->capacity) return fail(PLM_E_INVALID, "rows outside the database capacity");
+    if (n == 0) return PLM_OK;
+    if (!rows || step < 32) return fail(PLM_E_INVALID, "null rows / step < 32");
+    plm_ctx *ctx = db->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    // staged through pinned memory in 32 MB pieces
+    const int64_t piece = (32 << 20) / 32;
+    if ((st = ctx->ensure_pinned(size_t(std::min(n, piece)) * 32)) != PLM_OK) return st;
+    for (int64_t r = 0; r < n; r += piece) {
+        const int64_t m = std::min(piece, n - r);
+        pack_rows(ctx->h_buf, rows + size_t(r) * step, m, step);
+        CU_TRY(cudaMemcpyAsync(db->rows + 2 * (at_row + r), ctx->h_buf, size_t(m) * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    db->size = std::max(db->size, at_row + n);
+    return PLM_OK;
+}
+
+PLM_API int64_t plm_db_size(const plm_db *db) { return db ? db->size : 0; }
+PLM_API void *plm_db_device_ptr(const plm_db *db) { return db ? static_cast<void *>(db->rows) : nullptr; }
+
+PLM_API int plm_db_knn2(plm_db *db, const uint8_t *q, int nq, size_t step, uint64_t idx_base, uint64_t *top2) {
+    if (!db) return fail(PLM_E_INVALID, "null db");
+    int st = check_desc(q, nq, step);
+    if (st != PLM_OK) return st;
+    if (nq > 0 && !top2) return fail(PLM_E_INVALID, "null top2");
+    if (idx_base + static_cast<uint64_t>(db->size) > (1ull << 32)) return fail(PLM_E_UNSUPPORTED, "train index does not fit 32 bits");
+    if (nq == 0) return PLM_OK;
+    plm_ctx *ctx = db->ctx;
+    if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+    Layout L;
+    const size_t o_q = L.add(size_t(nq) * 32);
+    const size_t o_top2 = L.add(size_t(nq) * 16);
+    const size_t staged = L.total;
+    plm::KnnTaskPair tp;
+    std::memset(&tp, 0, sizeof(tp));
+    KnnPlan plan;
+    size_t part_off = 0;
+    build_knn_task(ctx, L, tp.t[0], plan, nullptr, nq, db->rows, db->size, idx_base, part_off);
+    if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    pack_rows(ctx->h_buf + o_q, q, nq, step);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf + o_q, ctx->h_buf + o_q, size_t(nq) * 32, cudaMemcpyHostToDevice, ctx->stream));
+    tp.t[0].q = reinterpret_cast<const uint4 *>(ctx->d_buf + o_q);
+    tp.t[0].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off);
+    tp.t[0].top2 = reinterpret_cast<ulonglong2 *>(ctx->d_buf + o_top2);
+    if ((st = launch_knn_slices(ctx, tp, 1, plan.threads)) != PLM_OK) return st;
+    if ((st = launch_knn_merge(ctx, tp, 1, 0.f, 0)) != PLM_OK) return st;
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_top2, ctx->d_buf + o_top2, size_t(nq) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(top2, ctx->h_buf + o_top2, size_t(nq) * 16);
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+PLM_API int plm_measure_int_peaks(plm_ctx *ctx, double *popc_gops, double *lop3_gops) {
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    if ((st = ctx->ensure_device(1 << 20)) != PLM_OK) return st;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    double out[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        float best_ms = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU_TRY(cudaEventRecord(e0, ctx->stream));
+            if (which == 0) plm::popc_rate_kernel<<<blocks, threads, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(ctx->d_buf), iters);
+            else plm::lop3_rate_kernel<<<blocks, threads, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(ctx->d_buf), iters);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaEventRecord(e1, ctx->stream));
+            CU_TRY(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0) best_ms = std::min(best_ms, ms);
+        }
+        const double ops = double(blocks) * threads * double(iters) * plm::MICRO_OPS_PER_ITER;
+        out[which] = ops / (best_ms * 1e-3) * 1e-9;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (popc_gops) *popc_gops = out[0];
+    if (lop3_gops) *lop3_gops = out[1];
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched replay
+struct plm_batch {
+    plm_ctx *ctx = nullptr;
+    int kind = 0; // 0 unset, 1 match, 2 grid
+    char *d_buf = nullptr;
+    size_t d_cap = 0;
+    int n_jobs = 0;
+    int64_t n_m = 0;
+    size_t o_work = 0, o_init = 0, work_bytes = 0; // [m12 | counts] working copy and pristine copy
+    // match
+    size_t o_tasks = 0, o_cta_map = 0, o_merge_map = 0, o_xjobs = 0, o_xmap = 0, o_m21 = 0, m21_bytes = 0;
+    int n_slice_ctas = 0, n_merge_ctas = 0, n_x_ctas = 0;
+    float nnr = 0.f;
+    int best_lr = 0;
+    // grid
+    size_t o_gjobs = 0;
+    plm::GridParams gp;
+    int n1_max = 0, n2_max = 0;
+    int64_t h2d = 0, d2h = 0;
+
+    int ensure(size_t bytes) {
+        if (bytes <= d_cap) return PLM_OK;
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        if (d_buf) CU_TRY(cudaFree(d_buf));
+        d_buf = nullptr;
+        d_cap = 0;
+        CU_TRY(cudaMalloc(reinterpret_cast<void **>(&d_buf), align_up(bytes, 1 << 20)));
+        d_cap = align_up(bytes, 1 << 20);
+        return PLM_OK;
+    }
+};
+
+PLM_API int plm_batch_create(plm_ctx *ctx, plm_batch **out) {
+    if (!out) return fail(PLM_E_INVALID, "null out");
+    *out = nullptr;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm_batch *b = new (std::nothrow) plm_batch();
+    if (!b) return fail(PLM_E_NOMEM, "host allocation failed");
+    b->ctx = ctx;
+    *out = b;
+    return PLM_OK;
+}
+
+PLM_API int plm_batch_destroy(plm_batch *b) {
+    if (!b) return PLM_OK;
+    if (b->ctx) {
+        cudaSetDevice(b->ctx->device);
+        cudaStreamSynchronize(b->ctx->stream);
+    }
+    if (b->d_buf) cudaFree(b->d_buf);
+    delete b;
+    return PLM_OK;
+}
+
+PLM_API int64_t plm_batch_h2d_bytes(const plm_batch *b) { return b ? b->h2d : 0; }
+PLM_API int64_t plm_batch_d2h_bytes(const plm_batch *b) { return b ? b->d2h : 0; }
+
+namespace {
+constexpr int BATCH_THREADS = 64;
+}
+
+PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_rows, const plm_pair_job *jobs, int n_jobs,
+                                float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m) {
+    if (!b) return fail(PLM_E_INVALID, "null batch");
+    if (n_rows < 0 || n_jobs < 0 || n_m < 0) return fail(PLM_E_INVALID, "negative size");
+    if ((n_rows > 0 && !arena) || (n_jobs > 0 && !jobs) || (n_m > 0 && !m12_arena)) return fail(PLM_E_INVALID, "null pointer");
+    plm_ctx *ctx = b->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    best_lr = best_lr ? 1 : 0;
+
+    // host-side tables
+    std::vector<plm::KnnTask> tasks;
+    std::vector<int4> cta_map;
+    std::vector<int2> merge_map, xmap;
+    std::vector<plm::XJob> xjobs;
+    std::vector<int32_t> counts_init(static_cast<size_t>(n_jobs), 0);
+    std::vector<size_t> part_off; // per task, relative to the part arena
+    std::vector<int64_t> m21_off(static_cast<size_t>(n_jobs), 0);
+    int64_t m21_rows = 0;
+    size_t part_bytes = 0;
+    long long total_qblocks = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const plm_pair_job &jb = jobs[j];
+        if (jb.n1 < 0 || jb.n2 < 0 || jb.off1 < 0 || jb.off2 < 0 || jb.off_m < 0 || jb.off1 + jb.n1 > n_rows ||
+            jb.off2 + jb.n2 > n_rows || jb.off_m + jb.n1 > n_m)
+            return fail(PLM_E_INVALID, "batch job outside its arena");
+        if (jb.n2 < 2 || (best_lr && jb.n1 < 2)) continue;
+        total_qblocks += (jb.n1 + BATCH_THREADS - 1) / BATCH_THREADS;
+        if (best_lr) total_qblocks += (jb.n2 + BATCH_THREADS - 1) / BATCH_THREADS;
+    }
+    // slices per direction: enough CTAs for a few waves when the batch is small, 1 when it is large
+    const long long target = static_cast<long long>(ctx->sm_count) * 16;
+    const int want_slices = static_cast<int>(std::max<long long>(1, target / std::max<long long>(1, total_qblocks)));
+    for (int j = 0; j < n_jobs; ++j) {
+        const plm_pair_job &jb = jobs[j];
+        if (jb.n2 < 2 || (best_lr && jb.n1 < 2)) {
+            counts_init[j] = INT32_MIN;
+            continue;
+        }
+        m21_off[j] = m21_rows;
+        if (best_lr) m21_rows += jb.n2;
+        for (int dir = 0; dir <= best_lr; ++dir) {
+            plm::KnnTask t;
+            std::memset(&t, 0, sizeof(t));
+            const int nq = dir ? jb.n2 : jb.n1, nt = dir ? jb.n1 : jb.n2;
+            int slices = std::min(want_slices, std::max(1, (nt + 63) / 64));
+            int rows = ((nt + slices - 1) / slices + 63) / 64 * 64;
+            slices = std::max(1, (nt + rows - 1) / rows);
+            t.n1 = nq;
+            t.n2 = nt;
+            t.slice_rows = rows;
+            t.n_slices = slices;
+            t.idx_base = 0;
+            // pointers are patched once the device block exists; stash offsets in the fields
+            t.q = reinterpret_cast<const uint4 *>(static_cast<uintptr_t>(dir ? jb.off2 : jb.off1));
+            t.db = reinterpret_cast<const uint4 *>(static_cast<uintptr_t>(dir ? jb.off1 : jb.off2));
+            t.m = reinterpret_cast<int32_t *>(static_cast<uintptr_t>(dir ? m21_off[j] : jb.off_m));
+            t.count = dir ? nullptr : reinterpret_cast<int32_t *>(static_cast<uintptr_t>(j) + 1); // +1: non-null marker
+            t.pad_ = dir;
+            part_off.push_back(part_bytes);
+            part_bytes += align_up(size_t(slices) * nq * sizeof(ulonglong2));
+            const int task_id = static_cast<int>(tasks.size());
+            for (int qb = 0; qb * BATCH_THREADS < nq; ++qb) {
+                for (int s = 0; s < slices; ++s) cta_map.push_back(make_int4(task_id, qb, s, 0));
+                merge_map.push_back(make_int2(task_id, qb * BATCH_THREADS));
+            }
+            tasks.push_back(t);
+        }
+        if (best_lr) {
+            plm::XJob x;
+            x.m12 = reinterpret_cast<int32_t *>(static_cast<uintptr_t>(jb.off_m));
+            x.m21 = reinterpret_cast<const int32_t *>(static_cast<uintptr_t>(m21_off[j]));
+            x.count = reinterpret_cast<int32_t *>(static_cast<uintptr_t>(j));
+            x.n1 = jb.n1;
+            x.n2 = jb.n2;
+            const int xid = static_cast<int>(xjobs.size());
+            xjobs.push_back(x);
+            for (int r = 0; r < jb.n1; r += 128) xmap.push_back(make_int2(xid, r));
+        }
+    }
+
+    Layout L;
+    const size_t o_arena = L.add(size_t(n_rows) * 32);
+    b->work_bytes = align_up(size_t(n_m) * 4, 16) + size_t(n_jobs) * 4;
+    b->o_work = L.add(b->work_bytes);
+    b->o_init = L.add(b->work_bytes);
+    b->o_tasks = L.add(tasks.size() * sizeof(plm::KnnTask));
+    b->o_cta_map = L.add(cta_map.size() * sizeof(int4));
+    b->o_merge_map = L.add(merge_map.size() * sizeof(int2));
+    b->o_xjobs = L.add(xjobs.size() * sizeof(plm::XJob));
+    b->o_xmap = L.add(xmap.size() * sizeof(int2));
+    b->m21_bytes = size_t(m21_rows) * 4;
+    b->o_m21 = L.add(b->m21_bytes);
+    const size_t o_part = L.add(part_bytes);
+    if ((st = b->ensure(L.total)) != PLM_OK) return st;
+
+    char *D = b->d_buf;
+    int32_t *d_m12 = reinterpret_cast<int32_t *>(D + b->o_work);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(D + b->o_work + align_up(size_t(n_m) * 4, 16));
+    int32_t *d_m21 = reinterpret_cast<int32_t *>(D + b->o_m21);
+    const uint4 *d_arena = reinterpret_cast<const uint4 *>(D + o_arena);
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        plm::KnnTask &t = tasks[i];
+        const bool dir = t.pad_ != 0;
+        t.q = d_arena + 2 * reinterpret_cast<uintptr_t>(t.q);
+        t.db = d_arena + 2 * reinterpret_cast<uintptr_t>(t.db);
+        t.m = (dir ? d_m21 : d_m12) + reinterpret_cast<uintptr_t>(t.m);
+        t.count = t.count ? d_counts + (reinterpret_cast<uintptr_t>(t.count) - 1) : nullptr;
+        t.part = reinterpret_cast<ulonglong2 *>(D + o_part + part_off[i]);
+        t.top2 = nullptr;
+        t.pad_ = 0;
+    }
+    for (plm::XJob &x : xjobs) {
+        x.m12 = d_m12 + reinterpret_cast<uintptr_t>(x.m12);
+        x.m21 = d_m21 + reinterpret_cast<uintptr_t>(x.m21);
+        x.count = d_counts + reinterpret_cast<uintptr_t>(x.count);
+    }
+
+    // uploads: arenas straight from the caller's memory, tables through the pinned staging block
+    const size_t tbl_bytes = L.total - b->o_tasks; // generous upper bound of the table region
+    (void)tbl_bytes;
+    Layout S;
+    const size_t s_init = S.add(b->work_bytes);
+    const size_t s_tasks = S.add(tasks.size() * sizeof(plm::KnnTask));
+    const size_t s_cta = S.add(cta_map.size() * sizeof(int4));
+    const size_t s_merge = S.add(merge_map.size() * sizeof(int2));
+    const size_t s_xjobs = S.add(xjobs.size() * sizeof(plm::XJob));
+    const size_t s_xmap = S.add(xmap.size() * sizeof(int2));
+    if ((st = ctx->ensure_pinned(S.total)) != PLM_OK) return st;
+    char *H = ctx->h_buf;
+    if (n_m > 0) std::memcpy(H + s_init, m12_arena, size_t(n_m) * 4);
+    if (n_jobs > 0) std::memcpy(H + s_init + align_up(size_t(n_m) * 4, 16), counts_init.data(), size_t(n_jobs) * 4);
+    if (!tasks.empty()) std::memcpy(H + s_tasks, tasks.data(), tasks.size() * sizeof(plm::KnnTask));
+    if (!cta_map.empty()) std::memcpy(H + s_cta, cta_map.data(), cta_map.size() * sizeof(int4));
+    if (!merge_map.empty()) std::memcpy(H + s_merge, merge_map.data(), merge_map.size() * sizeof(int2));
+    if (!xjobs.empty()) std::memcpy(H + s_xjobs, xjobs.data(), xjobs.size() * sizeof(plm::XJob));
+    if (!xmap.empty()) std::memcpy(H + s_xmap, xmap.data(), xmap.size() * sizeof(int2));
+    cudaStream_t s = ctx->stream;
+    if (n_rows > 0) CU_TRY(cudaMemcpyAsync(D + o_arena, arena, size_t(n_rows) * 32, cudaMemcpyHostToDevice, s));
+    if (b->work_bytes) CU_TRY(cudaMemcpyAsync(D + b->o_init, H + s_init, b->work_bytes, cudaMemcpyHostToDevice, s));
+    if (!tasks.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_tasks, H + s_tasks, tasks.size() * sizeof(plm::KnnTask), cudaMemcpyHostToDevice, s));
+    if (!cta_map.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_cta_map, H + s_cta, cta_map.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+    if (!merge_map.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_merge_map, H + s_merge, merge_map.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    if (!xjobs.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_xjobs, H + s_xjobs, xjobs.size() * sizeof(plm::XJob), cudaMemcpyHostToDevice, s));
+    if (!xmap.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_xmap, H + s_xmap, xmap.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s)); // the pinned block is reused by the next call
+
+    b->kind = 1;
+    b->n_jobs = n_jobs;
+    b->n_m = n_m;
+    b->nnr = nnr;
+    b->best_lr = best_lr;
+    b->n_slice_ctas = static_cast<int>(cta_map.size());
+    b->n_merge_ctas = static_cast<int>(merge_map.size());
+    b->n_x_ctas = static_cast<int>(xmap.size());
+    b->h2d = static_cast<int64_t>(size_t(n_rows) * 32 + S.total);
+    b->d2h = static_cast<int64_t>(size_t(n_m) * 4 + size_t(n_jobs) * 4);
+    return PLM_OK;
+}
+
+PLM_API int plm_batch_set_match_grid(plm_batch *b, const uint8_t *arena, int64_t n_rows, const int32_t *coords,
+                                     int64_t n_coords, const int32_t *cell_start, int64_t n_cell_start,
+                                     const int32_t *cell_items, int64_t n_cell_items, const double *dirs2, int64_t n_dirs2,
+                                     int grid_rows, int grid_cols, const plm_grid_job *jobs, int n_jobs, double ratio,
+                                     double line_sim_th, int best_lr, const int32_t *m12_arena, int64_t n_m) {
+    if (!b) return fail(PLM_E_INVALID, "null batch");
+    if (n_rows < 0 || n_jobs < 0 || n_m < 0 || n_coords < 0 || n_cell_start < 0 || n_cell_items < 0 || n_dirs2 < 0)
+        return fail(PLM_E_INVALID, "negative size");
+    if ((n_rows > 0 && !arena) || (n_jobs > 0 && !jobs) || (n_m > 0 && !m12_arena) || (n_coords > 0 && !coords) ||
+        (n_cell_start > 0 && !cell_start) || (n_cell_items > 0 && !cell_items) || (n_dirs2 > 0 && !dirs2))
+        return fail(PLM_E_INVALID, "null pointer");
+    if (grid_rows <= 0 || grid_cols <= 0) return fail(PLM_E_GRID, "[GridStructure] invalid dimension");
+    if (ratio > 1.0) return fail(PLM_E_RATIO, plm_status_string(PLM_E_RATIO));
+    plm_ctx *ctx = b->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    const int64_t n_cells = static_cast<int64_t>(grid_rows) * grid_cols;
+
+    Layout L;
+    const size_t o_arena = L.add(size_t(n_rows) * 32);
+    const size_t o_coords = L.add(size_t(n_coords) * 4);
+    const size_t o_cs = L.add(size_t(n_cell_start) * 4);
+    const size_t o_ci = L.add(size_t(n_cell_items) * 4);
+    const size_t o_dirs = L.add(size_t(n_dirs2) * 8);
+    b->work_bytes = align_up(size_t(n_m) * 4, 16) + size_t(n_jobs) * 4;
+    b->o_work = L.add(b->work_bytes);
+    b->o_init = L.add(b->work_bytes);
+    b->o_gjobs = L.add(size_t(std::max(n_jobs, 1)) * sizeof(plm::GridJob));
+    if ((st = b->ensure(L.total)) != PLM_OK) return st;
+    char *D = b->d_buf;
+    int32_t *d_m12 = reinterpret_cast<int32_t *>(D + b->o_work);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(D + b->o_work + align_up(size_t(n_m) * 4, 16));
+
+    std::vector<plm::GridJob> gj(static_cast<size_t>(n_jobs));
+    int n1_max = 1, n2_max = 1;
+    for (int j = 0; j < n_jobs; ++j) {
+        const plm_grid_job &jb = jobs[j];
+        const int cpq = jb.is_lines ? 4 : 2;
+        if (jb.n1 < 0 || jb.n2 < 0 || jb.off1 < 0 || jb.off2 < 0 || jb.off_m < 0 || jb.off_coords < 0 ||
+            jb.off_cell_start < 0 || jb.off_cell_items < 0 || jb.off_dirs2 < 0 || jb.off1 + jb.n1 > n_rows ||
+            jb.off2 + jb.n2 > n_rows || jb.off_m + jb.n1 > n_m || jb.off_coords + int64_t(jb.n1) * cpq > n_coords ||
+            jb.off_cell_start + n_cells + 1 > n_cell_start || (jb.is_lines && jb.off_dirs2 + int64_t(jb.n2) * 2 > n_dirs2))
+            return fail(PLM_E_INVALID, "grid job outside its arena");
+        const int32_t *cs = cell_start + jb.off_cell_start;
+        if (cs[0] != 0) return fail(PLM_E_GRID, "cell_start[0] must be 0");
+        for (int64_t c = 0; c < n_cells; ++c)
+            if (cs[c + 1] < cs[c]) return fail(PLM_E_GRID, "cell_start must be non-decreasing");
+        if (jb.off_cell_items + cs[n_cells] > n_cell_items) return fail(PLM_E_INVALID, "grid job outside its item arena");
+        if (jb.n1 > GRID_FUSED_MAX_ROWS || jb.n2 > GRID_N2_MAX)
+            return fail(PLM_E_UNSUPPORTED, "batched matchGrid jobs must be frame-sized");
+        plm::GridJob &g = gj[j];
+        std::memset(&g, 0, sizeof(g));
+        g.coords = reinterpret_cast<const int32_t *>(D + o_coords) + jb.off_coords;
+        g.d1 = reinterpret_cast<const uint4 *>(D + o_arena) + 2 * jb.off1;
+        g.d2 = reinterpret_cast<const uint4 *>(D + o_arena) + 2 * jb.off2;
+        g.cell_start = reinterpret_cast<const int32_t *>(D + o_cs) + jb.off_cell_start;
+        g.cell_items = reinterpret_cast<const int32_t *>(D + o_ci) + jb.off_cell_items;
+        g.dirs2 = reinterpret_cast<const double *>(D + o_dirs) + jb.off_dirs2;
+        g.m12 = d_m12 + jb.off_m;
+        g.count = d_counts + j;
+        g.n1 = jb.n1;
+        g.n2 = jb.n2;
+        g.is_lines = jb.is_lines ? 1 : 0;
+        for (int i = 0; i < 4; ++i) g.win[i] = jb.win[i];
+        n1_max = std::max(n1_max, jb.n1);
+        n2_max = std::max(n2_max, jb.n2);
+    }
+    const FusedShape fs = fused_shape(ctx, n1_max, n2_max);
+    if (fs.smem > ctx->smem_optin) return fail(PLM_E_UNSUPPORTED, "matchGrid: train set too large for shared memory");
+
+    Layout S;
+    const size_t s_init = S.add(b->work_bytes);
+    const size_t s_jobs = S.add(gj.size() * sizeof(plm::GridJob));
+    if ((st = ctx->ensure_pinned(S.total)) != PLM_OK) return st;
+    char *H = ctx->h_buf;
+    if (n_m > 0) std::memcpy(H + s_init, m12_arena, size_t(n_m) * 4);
+    std::memset(H + s_init + align_up(size_t(n_m) * 4, 16), 0, size_t(n_jobs) * 4);
+    if (!gj.empty()) std::memcpy(H + s_jobs, gj.data(), gj.size() * sizeof(plm::GridJob));
+    cudaStream_t s = ctx->stream;
+    if (n_rows > 0) CU_TRY(cudaMemcpyAsync(D + o_arena, arena, size_t(n_rows) * 32, cudaMemcpyHostToDevice, s));
+    if (n_coords > 0) CU_TRY(cudaMemcpyAsync(D + o_coords, coords, size_t(n_coords) * 4, cudaMemcpyHostToDevice, s));
+    if (n_cell_start > 0) CU_TRY(cudaMemcpyAsync(D + o_cs, cell_start, size_t(n_cell_start) * 4, cudaMemcpyHostToDevice, s));
+    if (n_cell_items > 0) CU_TRY(cudaMemcpyAsync(D + o_ci, cell_items, size_t(n_cell_items) * 4, cudaMemcpyHostToDevice, s));
+    if (n_dirs2 > 0) CU_TRY(cudaMemcpyAsync(D + o_dirs, dirs2, size_t(n_dirs2) * 8, cudaMemcpyHostToDevice, s));
+    if (b->work_bytes) CU_TRY(cudaMemcpyAsync(D + b->o_init, H + s_init, b->work_bytes, cudaMemcpyHostToDevice, s));
+    if (!gj.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_gjobs, H + s_jobs, gj.size() * sizeof(plm::GridJob), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
+
+    b->kind = 2;
+    b->n_jobs = n_jobs;
+    b->n_m = n_m;
+    b->best_lr = best_lr ? 1 : 0;
+    std::memset(&b->gp, 0, sizeof(b->gp));
+    b->gp.grid_rows = grid_rows;
+    b->gp.grid_cols = grid_cols;
+    b->gp.best_lr = b->best_lr;
+    b->gp.ratio = ratio;
+    b->gp.line_sim_th = line_sim_th;
+    b->n1_max = n1_max;
+    b->n2_max = n2_max;
+    b->h2d = static_cast<int64_t>(size_t(n_rows) * 32 + size_t(n_coords) * 4 + size_t(n_cell_start) * 4 +
+                                  size_t(n_cell_items) * 4 + size_t(n_dirs2) * 8 + S.total);
+    b->d2h = static_cast<int64_t>(size_t(n_m) * 4 + size_t(n_jobs) * 4);
+    return PLM_OK;
+}
+
+PLM_API int plm_batch_run(plm_batch *b) {
+    if (!b || b->kind == 0) return fail(PLM_E_INVALID, "batch not prepared");
+    plm_ctx *ctx = b->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    cudaStream_t s = ctx->stream;
+    char *D = b->d_buf;
+    if (b->work_bytes) CU_TRY(cudaMemcpyAsync(D + b->o_work, D + b->o_init, b->work_bytes, cudaMemcpyDeviceToDevice, s));
+    if (b->n_jobs == 0) return PLM_OK;
+    if (b->kind == 1) {
+        if (b->n_slice_ctas == 0) return PLM_OK;
+        const plm::KnnTask *tasks = reinterpret_cast<const plm::KnnTask *>(D + b->o_tasks);
+        if (b->best_lr && b->m21_bytes) CU_TRY(cudaMemsetAsync(D + b->o_m21, 0xFF, b->m21_bytes, s));
+        if (use_csa())
+            plm::knn2_slice_list_kernel<BATCH_THREADS, true><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
+        else
+            plm::knn2_slice_list_kernel<BATCH_THREADS, false><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        plm::knn2_merge_list_kernel<<<b->n_merge_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int2 *>(D + b->o_merge_map), b->nnr, 1);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        if (b->best_lr && b->n_x_ctas) {
+            plm::cross_check_list_kernel<<<b->n_x_ctas, 128, 0, s>>>(reinterpret_cast<const plm::XJob *>(D + b->o_xjobs), reinterpret_cast<const int2 *>(D + b->o_xmap));
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+        return PLM_OK;
+    }
+    return launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(D + b->o_gjobs), b->n_jobs, b->gp, b->n1_max, b->n2_max);
+}
+
+PLM_API int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts) {
+    if (!b || b->kind == 0) return fail(PLM_E_INVALID, "batch not prepared");
+    plm_ctx *ctx = b->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    cudaStream_t s = ctx->stream;
+    char *D = b->d_buf;
+    if (m12_arena && b->n_m > 0) CU_TRY(cudaMemcpyAsync(m12_arena, D + b->o_work, size_t(b->n_m) * 4, cudaMemcpyDeviceToHost, s));
+    if (counts && b->n_jobs > 0)
+        CU_TRY(cudaMemcpyAsync(counts, D + b->o_work + align_up(size_t(b->n_m) * 4, 16), size_t(b->n_jobs) * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return PLM_OK;
+}

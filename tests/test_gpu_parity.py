@@ -1,0 +1,243 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on identical seeded inputs.
+
+Bar: bit-exact match index vectors, counts and packed top-2 keys (integer work); the two ratio tests
+are evaluated in the reference's precisions (fp32 for matchNNR, fp64 for matchGrid) and therefore
+also compare exactly.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import gpu_grid, oracle_grid, random_grid_case
+from pl_inertial_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+port = oracle.port
+
+
+@pytest.fixture(scope="module")
+def M(plm_lib):
+    from pl_inertial_slam_b200 import matching
+    return matching
+
+
+def test_distance(M):
+    rng = np.random.default_rng(11)
+    a, b = synth.rand_desc(rng, 300), synth.rand_desc(rng, 300)
+    got = M.distances(a, b)
+    want = np.array([port.distance(a[i], b[i]) for i in range(300)])
+    assert (got == want).all()
+    assert M.distance(a[0], a[0]) == 0
+    assert M.distance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+@pytest.mark.parametrize("n1,n2,tie", [(1, 2, True), (50, 2, True), (70, 3, True), (100, 33, True), (64, 1025, True),
+                                        (600, 600, False), (200, 200, False), (813, 1291, False),
+                                        (300, 5000, True), (4100, 700, False)])
+def test_knn2_packed_keys(M, n1, n2, tie):
+    rng = np.random.default_rng(1000 + n1 + n2)
+    d1 = synth.tie_stress_desc(rng, n1) if tie else synth.rand_desc(rng, n1)
+    d2 = synth.tie_stress_desc(rng, n2) if tie else synth.rand_desc(rng, n2)
+    got = M.knn2(d1, d2, idx_base=17)
+    want = port.knn2_packed(d1, d2, idx_base=17)
+    assert (got == want).all()
+
+
+def test_knn2_empty_and_single_train(M):
+    rng = np.random.default_rng(5)
+    d1 = synth.rand_desc(rng, 10)
+    got = M.knn2(d1, np.zeros((0, 32), np.uint8))
+    assert (got == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    got = M.knn2(d1, d1[:1])
+    want = port.knn2_packed(d1, d1[:1])
+    assert (got == want).all() and (got[:, 1] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    assert M.knn2(np.zeros((0, 32), np.uint8), d1).shape == (0, 2)
+
+
+@pytest.mark.parametrize("n1,n2,tie", [(2, 2, True), (50, 3, True), (33, 1025, True), (600, 600, False),
+                                        (200, 200, False), (640, 577, False), (5000, 300, False)])
+@pytest.mark.parametrize("nnr", [0.75, 0.9])
+@pytest.mark.parametrize("best_lr", [0, 1])
+def test_match_and_match_nnr(M, n1, n2, tie, nnr, best_lr):
+    rng = np.random.default_rng(7 * n1 + n2)
+    d2 = synth.tie_stress_desc(rng, n2) if tie else synth.rand_desc(rng, n2)
+    if tie:
+        d1 = synth.tie_stress_desc(rng, n1)
+    else:
+        d1 = synth.rand_desc(rng, n1)
+        k = min(n1, n2) * 2 // 3
+        d1[rng.choice(n1, k, replace=False)] = synth.flip_bits(rng, d2[rng.choice(n2, k, replace=False)], 0.08)
+    n_o, m_o = port.match(d1, d2, nnr, best_lr)
+    M.Config.bestLRMatches = bool(best_lr)
+    try:
+        m_g = []
+        n_g = M.match(d1, d2, nnr, m_g)
+    finally:
+        M.Config.bestLRMatches = True
+    assert n_g == n_o
+    assert (np.array(m_g) == m_o).all()
+    if not best_lr:
+        m_n = np.full(n1, -1, np.int32)
+        assert M.matchNNR(d1, d2, nnr, m_n) == n_o and (m_n == m_o).all()
+
+
+def test_match_stale_inout_fallback(M):
+    """mapHandler.cpp:325-329: match() is handed the vector matchGrid just filled; stale entries are
+    kept, cross-checked and can drive the returned count negative."""
+    rng = np.random.default_rng(99)
+    n1, n2 = 300, 280
+    d1, d2 = synth.rand_desc(rng, n1), synth.rand_desc(rng, n2)
+    d1[:100] = synth.flip_bits(rng, d2[:100], 0.05)
+    stale = np.full(n1, -1, np.int32)
+    stale[100:250] = rng.integers(0, n2, 150)
+    for best_lr in (0, 1):
+        n_o, m_o = port.match(d1, d2, 0.75, best_lr, m12=stale)
+        M.Config.bestLRMatches = bool(best_lr)
+        try:
+            m_g = stale.copy()
+            n_g = M.match(d1, d2, 0.75, m_g)
+        finally:
+            M.Config.bestLRMatches = True
+        assert n_g == n_o and (m_g == m_o).all()
+    assert port.match(d1, d2, 0.75, 1, m12=stale)[0] < 100  # culls of stale entries are subtracted
+
+
+def test_strided_descriptors(M):
+    """cv::Mat::step != 32 (a column range of a wider matrix)."""
+    rng = np.random.default_rng(3)
+    wide1 = rng.integers(0, 256, (200, 48), dtype=np.uint8)
+    wide2 = rng.integers(0, 256, (180, 64), dtype=np.uint8)
+    d1, d2 = wide1[:, 8:40], wide2[:, :32]
+    n_o, m_o = port.match(np.ascontiguousarray(d1), np.ascontiguousarray(d2), 0.9, 1)
+    m_g = []
+    assert M.match(d1, d2, 0.9, m_g) == n_o and (np.array(m_g) == m_o).all()
+
+
+GRID_CASES = [
+    # n1, n2, is_lines, tie, win, bad_items, zero_len
+    (600, 600, False, False, (10, 0, 0, 0), 0, 0),
+    (600, 600, False, False, (3, 3, 3, 3), 0, 0),
+    (500, 400, False, True, (3, 3, 3, 3), 0, 0),
+    (300, 900, False, True, (6, 2, 1, 4), 12, 0),
+    (37, 5, False, True, (70, 70, 50, 50), 0, 0),
+    (1, 1, False, False, (1, 1, 1, 1), 0, 0),
+    (900, 30, False, True, (64, 64, 48, 48), 0, 0),
+    (2500, 1500, False, False, (3, 3, 3, 3), 0, 0),
+    (200, 200, True, False, (10, 0, 0, 0), 0, 0),
+    (200, 200, True, False, (3, 3, 3, 3), 0, 4),
+    (150, 260, True, True, (3, 3, 3, 3), 0, 6),
+    (80, 40, True, True, (64, 64, 48, 48), 0, 3),
+    (1300, 700, True, False, (2, 2, 2, 2), 0, 0),
+]
+
+
+@pytest.mark.parametrize("n1,n2,is_lines,tie,win,bad_items,zero_len", GRID_CASES)
+@pytest.mark.parametrize("best_lr", [1, 0])
+@pytest.mark.parametrize("ratio", [0.75, 0.9, 1.0])
+def test_match_grid(M, n1, n2, is_lines, tie, win, bad_items, zero_len, best_lr, ratio):
+    rng = np.random.default_rng(n1 * 31 + n2 * 7 + int(is_lines))
+    case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=tie, win=win, bad_items=bad_items, zero_len=zero_len)
+    n_o, m_o = oracle_grid(port, case, ratio, best_lr)
+    n_g, m_g = gpu_grid(case, ratio, best_lr)
+    assert n_g == n_o
+    assert (m_g == m_o).all(), np.flatnonzero(m_g != m_o)[:10]
+
+
+def test_match_grid_small_grids_and_empty(M):
+    rng = np.random.default_rng(4)
+    for rows, cols in [(1, 1), (2, 5), (7, 3)]:
+        case = random_grid_case(rng, 120, 90, rows=rows, cols=cols, tie=True, win=(1, 1, 1, 1))
+        n_o, m_o = oracle_grid(port, case, 0.9, 1)
+        n_g, m_g = gpu_grid(case, 0.9, 1)
+        assert n_g == n_o and (m_g == m_o).all()
+    # empty grid (no train feature inside the image): nothing matches, stale entries are culled
+    case = random_grid_case(rng, 50, 40, win=(3, 3, 3, 3))
+    case["cell_start"] = np.zeros_like(case["cell_start"])
+    case["cell_items"] = np.zeros(0, np.int32)
+    stale = np.full(50, -1, np.int32)
+    stale[:10] = np.arange(10)
+    n_o, m_o = oracle_grid(port, case, 0.9, 1, m12=stale)
+    n_g, m_g = gpu_grid(case, 0.9, 1, m12=stale)
+    assert n_g == n_o == -10 and (m_g == m_o).all() and (m_g == -1).all()
+
+
+def test_match_grid_stereo_configs(M):
+    """Config 1 of BASELINE.json: the stereo point / line matchGrid calls of StereoFrame."""
+    sp = synth.make_stereo_pair(synth.SEED0 + 1)
+    for ratio in (0.75, 0.9):
+        a = synth.stereo_points_grid_args(sp)
+        case = dict(coords=a["xy"], d1=a["d1"], cell_start=a["cell_start"], cell_items=a["cell_items"],
+                    rows=a["rows"], cols=a["cols"], d2=a["d2"], win=a["win"], dirs2=None)
+        n_o, m_o = oracle_grid(port, case, ratio, 1)
+        n_g, m_g = gpu_grid(case, ratio, 1)
+        assert n_g == n_o and (m_g == m_o).all() and n_o > 300
+        b = synth.stereo_lines_grid_args(sp)
+        case = dict(coords=b["xyxy"], d1=b["d1"], cell_start=b["cell_start"], cell_items=b["cell_items"],
+                    rows=b["rows"], cols=b["cols"], d2=b["d2"], win=b["win"], dirs2=b["dirs2"])
+        n_o, m_o = oracle_grid(port, case, ratio, 1)
+        n_g, m_g = gpu_grid(case, ratio, 1)
+        assert n_g == n_o and (m_g == m_o).all() and n_o > 80
+
+
+@pytest.mark.parametrize("is_lines", [False, True])
+def test_match_grid_map_scale_chunked(M, is_lines):
+    """Config 4 shape (scaled so the oracle finishes in seconds): tens of thousands of map rows
+    against a frame-sized grid -> the multi-CTA chunked path."""
+    rng = np.random.default_rng(2024 + int(is_lines))
+    n1, n2 = (30000, 600) if not is_lines else (12000, 200)
+    case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=False, win=(3, 3, 3, 3), zero_len=5 if is_lines else 0)
+    for best_lr in (1, 0):
+        n_o, m_o = oracle_grid(port, case, 0.9, best_lr)
+        n_g, m_g = gpu_grid(case, 0.9, best_lr)
+        assert n_g == n_o and (m_g == m_o).all()
+
+
+def test_match_grid_map_scale_ties(M):
+    rng = np.random.default_rng(77)
+    case = random_grid_case(rng, 9000, 300, tie=True, win=(5, 5, 5, 5))
+    n_o, m_o = oracle_grid(port, case, 0.9, 1)
+    n_g, m_g = gpu_grid(case, 0.9, 1)
+    assert n_g == n_o and (m_g == m_o).all()
+
+
+def test_stereo_filters(M):
+    sp = synth.make_stereo_pair(synth.SEED0 + 1)
+    rng = np.random.default_rng(8)
+    m = rng.integers(-1, 600, 600).astype(np.int32)
+    m[:300] = np.arange(300)  # plausible and implausible pairings
+    n_o, k_o, d_o = port.stereo_filter_points(sp.kp_l, sp.kp_r, m)
+    n_g, k_g, d_g = M.stereo_filter_points(sp.kp_l, sp.kp_r, m)
+    assert n_g == n_o and (k_g == k_o).all() and (d_g == d_o).all()
+    ml = rng.integers(-1, 200, 200).astype(np.int32)
+    ln_r = sp.ln_r.copy()
+    ln_r[::17, 3] = ln_r[::17, 1]  # horizontal right lines: division by zero -> inf / NaN paths
+    n_o, k_o, d_o = port.stereo_filter_lines(sp.ln_l, ln_r, ml)
+    n_g, k_g, d_g = M.stereo_filter_lines(sp.ln_l, ln_r, ml)
+    assert n_g == n_o and (k_g == k_o).all()
+    assert np.array_equal(d_g, d_o, equal_nan=True)
+
+
+def test_threads_are_reentrant(M):
+    """up to ~6 host threads are inside the matching layer at once."""
+    import threading
+    rng = np.random.default_rng(21)
+    cases = []
+    for t in range(6):
+        d1, d2 = synth.rand_desc(rng, 300 + 10 * t), synth.rand_desc(rng, 280)
+        d1[:150] = synth.flip_bits(rng, d2[:150], 0.08)
+        cases.append((d1, d2, port.match(d1, d2, 0.9, 1)))
+    errors = []
+
+    def work(d1, d2, want):
+        try:
+            for _ in range(20):
+                m = []
+                n = M.match(d1, d2, 0.9, m)
+                assert n == want[0] and (np.array(m) == want[1]).all()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ths = [threading.Thread(target=work, args=c) for c in cases]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errors, errors
