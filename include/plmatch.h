@@ -74,11 +74,17 @@ int plm_ctx_create(int device, plm_ctx **out);
 int plm_ctx_destroy(plm_ctx *ctx);
 /* cudaStream_t the context launches on. */
 void *plm_ctx_stream(plm_ctx *ctx);
-/* Borrow an external stream (e.g. torch's current stream); pass NULL to return to the own stream. */
-int plm_ctx_set_stream(plm_ctx *ctx, void *cuda_stream);
+/* external != 0: launch on the caller's stream (e.g. torch's current stream; a NULL handle is the
+ * legacy default stream); external == 0: return to the context's own stream. */
+int plm_ctx_set_stream(plm_ctx *ctx, void *cuda_stream, int external);
 int plm_ctx_synchronize(plm_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t plm_ctx_launch_count(plm_ctx *ctx);
+
+/* Per-launch CUDA-event timing of the brute-force slice kernel (the roofline kernel): switch it on,
+ * run, then read the summed device time and the number of launches since the last read. */
+int plm_ctx_set_profiling(plm_ctx *ctx, int on);
+int plm_ctx_read_profile(plm_ctx *ctx, double *knn2_slice_ms, int *n_launches);
 
 /* ---- host-buffer entry points (what the StVO:: wrappers call) -------------------------------- */
 

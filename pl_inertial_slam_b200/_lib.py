@@ -53,8 +53,10 @@ SIGNATURES = {
     "plm_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "plm_ctx_destroy": (C.c_int, [vp]),
     "plm_ctx_stream": (vp, [vp]),
-    "plm_ctx_set_stream": (C.c_int, [vp, vp]),
+    "plm_ctx_set_stream": (C.c_int, [vp, vp, C.c_int]),
     "plm_ctx_synchronize": (C.c_int, [vp]),
+    "plm_ctx_set_profiling": (C.c_int, [vp, C.c_int]),
+    "plm_ctx_read_profile": (C.c_int, [vp, f64p, intp]),
     "plm_ctx_launch_count": (C.c_uint64, [vp]),
     "plm_hamming256": (C.c_int, [vp, u8p, C.c_size_t, u8p, C.c_size_t, C.c_int, i32p]),
     "plm_knn2": (C.c_int, [vp] + _DESC + _DESC + [C.c_uint64, u64p]),

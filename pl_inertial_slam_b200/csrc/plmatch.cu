@@ -66,6 +66,10 @@ struct plm_ctx {
     uint64_t launches = 0;
     bool fused_attr_set = false;
     size_t chunked_attr[2] = {0, 0};
+    // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
 
     int ensure_device(size_t bytes) {
         if (bytes <= d_cap) return PLM_OK;
@@ -177,6 +181,17 @@ int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int
     if (qb == 0 || sl == 0) return PLM_OK;
     const dim3 grid(qb, sl, n_tasks);
     const bool csa = use_csa();
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (ctx->profiling) {
+        if (!ctx->prof_free.empty()) {
+            ev = ctx->prof_free.back();
+            ctx->prof_free.pop_back();
+        } else {
+            CU_TRY(cudaEventCreate(&ev.first));
+            CU_TRY(cudaEventCreate(&ev.second));
+        }
+        CU_TRY(cudaEventRecord(ev.first, ctx->stream));
+    }
     if (threads == 128) {
         if (csa) plm::knn2_slice_kernel<128, true><<<grid, 128, 0, ctx->stream>>>(tp);
         else plm::knn2_slice_kernel<128, false><<<grid, 128, 0, ctx->stream>>>(tp);
@@ -186,6 +201,10 @@ int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int
     }
     ctx->launches++;
     CU_TRY(cudaGetLastError());
+    if (ctx->profiling) {
+        CU_TRY(cudaEventRecord(ev.second, ctx->stream));
+        ctx->prof_events.push_back(ev);
+    }
     return PLM_OK;
 }
 
@@ -289,9 +308,9 @@ PLM_API int plm_ctx_destroy(plm_ctx *ctx) {
 
 PLM_API void *plm_ctx_stream(plm_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
 
-PLM_API int plm_ctx_set_stream(plm_ctx *ctx, void *cuda_stream) {
+PLM_API int plm_ctx_set_stream(plm_ctx *ctx, void *cuda_stream, int external) {
     if (!ctx) return fail(PLM_E_INVALID, "null ctx");
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = external ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return PLM_OK;
 }
 
@@ -299,6 +318,31 @@ PLM_API int plm_ctx_synchronize(plm_ctx *ctx) {
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return PLM_OK;
+}
+
+PLM_API int plm_ctx_set_profiling(plm_ctx *ctx, int on) {
+    if (!ctx) return fail(PLM_E_INVALID, "null ctx");
+    ctx->profiling = on != 0;
+    return PLM_OK;
+}
+
+PLM_API int plm_ctx_read_profile(plm_ctx *ctx, double *knn2_slice_ms, int *n_launches) {
+    if (!ctx) return fail(PLM_E_INVALID, "null ctx");
+    CU_TRY(cudaSetDevice(ctx->device));
+    double total = 0.0;
+    int n = 0;
+    for (auto &ev : ctx->prof_events) {
+        CU_TRY(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        total += ms;
+        ++n;
+        ctx->prof_free.push_back(ev);
+    }
+    ctx->prof_events.clear();
+    if (knn2_slice_ms) *knn2_slice_ms = total;
+    if (n_launches) *n_launches = n;
     return PLM_OK;
 }
 
@@ -571,7 +615,7 @@ size_t fused_smem(int warps, int n2_max) { return align_up(size_t(warps) * n2_ma
 
 // Number of warps of the fused kernel: as many chunks as shared memory allows, at least ~4 rows each.
 FusedShape fused_shape(const plm_ctx *ctx, int n1_max, int n2_max) {
-    const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+    const size_t budget = std::min<size_t>(ctx->smem_optin - 2048, 200 * 1024);
     int w = std::min(32, std::max(1, (n1_max + 3) / 4));
     while (w > 1 && fused_smem(w, n2_max) > budget) --w;
     return {w, fused_smem(w, n2_max)};
@@ -593,10 +637,10 @@ int validate_grid(const int32_t *cell_start, const int32_t *cell_items, int grid
 int launch_grid_fused(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, const plm::GridParams &gp, int n1_max,
                       int n2_max) {
     const FusedShape fs = fused_shape(ctx, n1_max, n2_max);
-    if (fs.smem > ctx->smem_optin) return fail(PLM_E_UNSUPPORTED, "matchGrid: train set too large for shared memory");
+    if (fs.smem > ctx->smem_optin - 2048) return fail(PLM_E_UNSUPPORTED, "matchGrid: train set too large for shared memory");
     if (!ctx->fused_attr_set) {
         CU_TRY(cudaFuncSetAttribute(plm::grid_match_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(std::min<size_t>(ctx->smem_optin, 227 * 1024))));
+                                    static_cast<int>(ctx->smem_optin - 2048)));
         ctx->fused_attr_set = true;
     }
     plm::grid_match_fused_kernel<<<n_jobs, fs.warps * 32, fs.smem, ctx->stream>>>(jobs_dev, gp, n2_max);
@@ -614,11 +658,11 @@ int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams g
         if (ctx->chunked_attr[pass] < smem) {
             if (pass == 0)
                 CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(std::min<size_t>(ctx->smem_optin, 227 * 1024))));
+                                            static_cast<int>(ctx->smem_optin - 2048)));
             else
                 CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(std::min<size_t>(ctx->smem_optin, 227 * 1024))));
-            ctx->chunked_attr[pass] = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+                                            static_cast<int>(ctx->smem_optin - 2048)));
+            ctx->chunked_attr[pass] = ctx->smem_optin - 2048;
         }
     }
     gp.rows_per_warp = GRID_CHUNK_ROWS_PER_WARP;
@@ -683,7 +727,7 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     int warps = 0, n_cta = 0;
     size_t o_cta_min = 0, o_m21key = 0, o_m21 = 0;
     if (!fused) {
-        const size_t budget = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+        const size_t budget = std::min<size_t>(ctx->smem_optin - 2048, 200 * 1024);
         warps = 16;
         while (warps > 1 && size_t(warps) * std::max(n2, 1) * 2 > budget) warps >>= 1;
         const long long rows_per_cta = static_cast<long long>(warps) * GRID_CHUNK_ROWS_PER_WARP;

@@ -54,7 +54,9 @@ class Context:
         return self._h
 
     def set_stream(self, cuda_stream: Optional[int]):
-        L.check(self._lib.plm_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "plm_ctx_set_stream")
+        """Launch on an external stream handle (0 = the legacy default stream); None = own stream."""
+        ext = cuda_stream is not None
+        L.check(self._lib.plm_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0), int(ext)), "plm_ctx_set_stream")
 
     def synchronize(self):
         L.check(self._lib.plm_ctx_synchronize(self._h), "plm_ctx_synchronize")
@@ -62,6 +64,15 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._lib.plm_ctx_launch_count(self._h))
+
+    def set_profiling(self, on: bool):
+        L.check(self._lib.plm_ctx_set_profiling(self._h, int(bool(on))), "plm_ctx_set_profiling")
+
+    def read_profile(self) -> Tuple[float, int]:
+        """(summed device ms of the brute-force slice kernel, launches) since the last read."""
+        ms, n = C.c_double(0), C.c_int(0)
+        L.check(self._lib.plm_ctx_read_profile(self._h, C.byref(ms), C.byref(n)), "plm_ctx_read_profile")
+        return ms.value, n.value
 
     def measure_int_peaks(self) -> Tuple[float, float]:
         p, l = C.c_double(0), C.c_double(0)

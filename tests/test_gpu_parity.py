@@ -241,3 +241,36 @@ def test_threads_are_reentrant(M):
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert not errors, errors
+
+
+def test_gpu_vs_golden(M):
+    """The committed fixtures were produced by the reference's own matching.cpp (tools/make_golden.py)."""
+    import glob
+    import os
+    from conftest import ROOT
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+    assert len(files) >= 10
+    for path in files:
+        z = np.load(path)
+        name = os.path.basename(path)
+        if name.startswith("brute"):
+            for nnr in (0.75, 0.9):
+                for blr in (0, 1):
+                    M.Config.bestLRMatches = bool(blr)
+                    try:
+                        m = []
+                        n = M.match(z["d1"], z["d2"], nnr, m)
+                        ms = z["stale"].copy()
+                        ns = M.match(z["d1"], z["d2"], nnr, ms)
+                    finally:
+                        M.Config.bestLRMatches = True
+                    assert n == int(z[f"n_{nnr}_{blr}"]) and (np.array(m) == z[f"m_{nnr}_{blr}"]).all(), name
+                    assert ns == int(z[f"ns_{nnr}_{blr}"]) and (ms == z[f"ms_{nnr}_{blr}"]).all(), name
+        elif name.startswith("grid"):
+            case = dict(coords=z["coords"], d1=z["d1"], cell_start=z["cell_start"], cell_items=z["cell_items"],
+                        rows=int(z["rows"]), cols=int(z["cols"]), d2=z["d2"], win=z["win"],
+                        dirs2=z["dirs2"] if int(z["is_lines"]) else None)
+            for ratio in (0.75, 0.9, 1.0):
+                for blr in (0, 1):
+                    n, m = gpu_grid(case, ratio, blr)
+                    assert n == int(z[f"n_{ratio}_{blr}"]) and (m == z[f"m_{ratio}_{blr}"]).all(), name

@@ -1,0 +1,177 @@
+"""CPU tests: the oracle restatement against (1) golden vectors generated from the reference itself
+(tools/make_golden.py), (2) the compiled reference when oracle/_ref/libplref.so exists, (3) OpenCV's
+own BFMatcher (cv2 wheel) for the one un-vendored dependency, and the host-side grid logic."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT
+from helpers import oracle_grid, random_grid_case
+from pl_inertial_slam_b200 import grid as G
+from pl_inertial_slam_b200 import synth
+
+port, ref = oracle.port, oracle.ref
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libplref.so not built")
+
+
+def _golden(prefix):
+    files = sorted(glob.glob(os.path.join(GOLDEN, prefix + "_*.npz")))
+    assert files, "golden fixtures missing"
+    return files
+
+
+@pytest.mark.parametrize("path", _golden("brute"))
+def test_port_vs_golden_brute(path):
+    z = np.load(path)
+    for nnr in (0.75, 0.9):
+        for blr in (0, 1):
+            n, m = port.match(z["d1"], z["d2"], nnr, blr)
+            assert n == int(z[f"n_{nnr}_{blr}"]) and (m == z[f"m_{nnr}_{blr}"]).all()
+            n, m = port.match(z["d1"], z["d2"], nnr, blr, m12=z["stale"])
+            assert n == int(z[f"ns_{nnr}_{blr}"]) and (m == z[f"ms_{nnr}_{blr}"]).all()
+
+
+def _case_from_npz(z):
+    return dict(coords=z["coords"], d1=z["d1"], cell_start=z["cell_start"], cell_items=z["cell_items"],
+                rows=int(z["rows"]), cols=int(z["cols"]), d2=z["d2"], win=z["win"],
+                dirs2=z["dirs2"] if int(z["is_lines"]) else None)
+
+
+@pytest.mark.parametrize("path", _golden("grid"))
+def test_port_vs_golden_grid(path):
+    z = np.load(path)
+    case = _case_from_npz(z)
+    for ratio in (0.75, 0.9, 1.0):
+        for blr in (0, 1):
+            n, m = oracle_grid(port, case, ratio, blr)
+            assert n == int(z[f"n_{ratio}_{blr}"]) and (m == z[f"m_{ratio}_{blr}"]).all()
+
+
+def test_line_coords_vs_golden():
+    z = np.load(os.path.join(GOLDEN, "line_coords.npz"))
+    seg, cells, offs = z["seg"], z["cells"], z["offs"]
+    for i, s in enumerate(seg):
+        want = cells[offs[i]:offs[i + 1]]
+        assert (port.line_coords(*s) == want).all()
+        assert (np.array(G.getLineCoords(*s), np.int32).reshape(-1, 2) == want).all()
+    ids, cx, cy = G.line_cells(seg[:, 0], seg[:, 1], seg[:, 2], seg[:, 3])
+    assert (np.stack([cx, cy], 1) == cells).all()
+    assert (np.bincount(ids, minlength=len(seg)) == np.diff(offs)).all()
+
+
+def test_distance_known_answers():
+    z = np.zeros(32, np.uint8)
+    f = np.full(32, 255, np.uint8)
+    assert port.distance(z, z) == 0 and port.distance(z, f) == 256
+    one = z.copy(); one[17] = 0x10
+    assert port.distance(z, one) == 1
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a, b = synth.rand_desc(rng, 2)
+        assert port.distance(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+def test_knn2_vs_cv2():
+    """cv::BFMatcher is the one dependency not under /root/reference (OpenCV 3.3 there, 4.13 here)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    for n1, n2, tie in [(50, 2, 1), (70, 3, 1), (100, 33, 1), (64, 1025, 1), (300, 300, 0)]:
+        d1 = synth.tie_stress_desc(rng, n1) if tie else synth.rand_desc(rng, n1)
+        d2 = synth.tie_stress_desc(rng, n2) if tie else synth.rand_desc(rng, n2)
+        idx, dist = port.knn2(d1, d2)
+        m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d1, d2, k=2)
+        assert (np.array([[x.trainIdx for x in r] for r in m]) == idx).all()
+        assert (np.array([[int(x.distance) for x in r] for r in m]) == dist).all()
+
+
+@needs_ref
+def test_port_vs_reference_random():
+    rng = np.random.default_rng(2)
+    for _ in range(30):
+        n1, n2 = int(rng.integers(2, 200)), int(rng.integers(2, 200))
+        tie = bool(rng.integers(0, 2))
+        d1 = synth.tie_stress_desc(rng, n1) if tie else synth.rand_desc(rng, n1)
+        d2 = synth.tie_stress_desc(rng, n2) if tie else synth.rand_desc(rng, n2)
+        for blr in (0, 1):
+            for lr_par in (0, 1):
+                assert_same(port.match(d1, d2, 0.9, blr), ref.match(d1, d2, 0.9, best_lr=blr, lr_parallel=lr_par))
+        a, b = d1[0], d2[0]
+        assert port.distance(a, b) == ref.distance(a, b)
+
+
+def assert_same(x, y):
+    assert x[0] == y[0] and (x[1] == y[1]).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("is_lines", [False, True])
+def test_port_vs_reference_grid_random(is_lines):
+    """The reference iterates an unordered_set; the port iterates cells in order -- 200 random
+    cases with heavy ties show the outputs agree for ratio <= 1 (SURVEY 8a note 1)."""
+    rng = np.random.default_rng(3 + int(is_lines))
+    for it in range(100):
+        n1, n2 = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        w = tuple(int(v) for v in rng.integers(0, 6, 4))
+        case = random_grid_case(rng, n1, n2, rows=int(rng.integers(1, 20)), cols=int(rng.integers(1, 20)),
+                                is_lines=is_lines, tie=bool(it % 2), win=w, bad_items=int(rng.integers(0, 3)),
+                                zero_len=int(rng.integers(0, 3)))
+        for ratio in (0.75, 1.0):
+            for blr in (0, 1):
+                got = oracle_grid(port, case, ratio, blr)
+                if is_lines:
+                    want = ref.match_grid_lines(case["coords"], case["d1"], case["cell_start"], case["cell_items"],
+                                                case["rows"], case["cols"], case["d2"], case["dirs2"], 0.75,
+                                                case["win"], ratio, blr)
+                else:
+                    want = ref.match_grid_points(case["coords"], case["d1"], case["cell_start"], case["cell_items"],
+                                                 case["rows"], case["cols"], case["d2"], case["win"], ratio, blr)
+                assert_same(got, want)
+
+
+def test_grid_mirror_matches_csr_builders():
+    """GridStructure.at/get/to_csr (host mirror) against the vectorised CSR builders."""
+    rng = np.random.default_rng(5)
+    px, py = rng.uniform(-2, 66, 400), rng.uniform(-2, 50, 400)
+    g = G.GridStructure(G.GRID_ROWS, G.GRID_COLS)
+    for i in range(400):
+        g.at(px[i], py[i]).append(i)
+    cs, ci = g.to_csr()
+    cs2, ci2 = G.csr_from_points(px, py)
+    assert (cs == cs2).all() and (ci == ci2).all()
+    w = G.GridWindow((3, 1), (0, 2))
+    for (x, y) in [(0, 0), (63, 47), (10, 20), (-1, 5), (70, 50)]:
+        s = set()
+        g.get(x, y, w, s)
+        want = set()
+        for x_ in range(max(0, x - 3), min(64, x + 2)):
+            for y_ in range(max(0, y), min(48, y + 3)):
+                c = x_ * 48 + y_
+                want.update(ci[cs[c]:cs[c + 1]].tolist())
+        assert s == want
+    seg = rng.uniform(0, 60, (50, 4))
+    g2 = G.GridStructure(48, 64)
+    for i, s in enumerate(seg):
+        for (x, y) in G.getLineCoords(*s):
+            g2.at(x, y).append(i)
+    a, b = g2.to_csr()
+    a2, b2 = G.csr_from_lines(seg[:, 0], seg[:, 1], seg[:, 2], seg[:, 3])
+    assert (a == a2).all() and (b == b2).all()
+    with pytest.raises(RuntimeError):
+        G.GridStructure(48, 0)
+
+
+def test_stereo_filter_port_properties():
+    sp = synth.make_stereo_pair(synth.SEED0 + 1)
+    m = np.arange(600, dtype=np.int32)
+    n, keep, disp = port.stereo_filter_points(sp.kp_l, sp.kp_r, m)
+    dy = np.abs(sp.kp_l[:, 1] - sp.kp_r[:, 1])
+    dx = (sp.kp_l[:, 0] - sp.kp_r[:, 0]).astype(np.float64)
+    want = (dy.astype(np.float64) <= 1.0) & (dx >= 1.0)
+    assert (keep.astype(bool) == want).all() and n == want.sum()
+    assert port.lib.plo_line_overlap_stereo(0.0, 10.0, 0.0, 10.0, 0.1) == 1.0
+    assert port.lib.plo_line_overlap_stereo(0.0, 10.0, 20.0, 30.0, 0.1) == 0.0
+    assert port.lib.plo_line_overlap_stereo(5.0, 5.05, 20.0, 30.0, 0.1) == 1.0  # horizontal: untouched

@@ -1,0 +1,105 @@
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF (oracle/_ref/libplref.so = the reference's
+matching.cpp / gridStructure.cpp / lineIterator.cpp compiled unmodified, see oracle/Makefile).
+
+Run in the build container (needs /root/reference to build libplref.so):
+    python tools/make_golden.py
+The fixtures are small (a few hundred KB) and committed; tests compare the oracle port and the CUDA
+path against them, so parity stays pinned on machines where the reference cannot be built.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from helpers import random_grid_case  # noqa: E402
+from pl_inertial_slam_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+ref = oracle.ref
+assert ref.available(), "build oracle/_ref/libplref.so first (make -C oracle ref)"
+
+
+def save(name, **arrays):
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+    print("wrote", name, {k: getattr(v, "shape", v) for k, v in arrays.items()})
+
+
+def brute_cases():
+    rng = np.random.default_rng(synth.SEED0 + 9)
+    shapes = [(2, 2, 1), (50, 2, 1), (70, 3, 1), (100, 33, 1), (64, 1025, 1), (200, 200, 0), (301, 277, 0)]
+    for ci, (n1, n2, tie) in enumerate(shapes):
+        d2 = synth.tie_stress_desc(rng, n2) if tie else synth.rand_desc(rng, n2)
+        if tie:
+            d1 = synth.tie_stress_desc(rng, n1)
+        else:
+            d1 = synth.rand_desc(rng, n1)
+            k = min(n1, n2) * 2 // 3
+            d1[rng.choice(n1, k, replace=False)] = synth.flip_bits(rng, d2[rng.choice(n2, k, replace=False)], 0.08)
+        stale = np.full(n1, -1, np.int32)
+        if n1 > 10:
+            pos = rng.choice(n1, n1 // 4, replace=False)
+            stale[pos] = rng.integers(0, n2, len(pos))
+        out = dict(d1=d1, d2=d2, stale=stale)
+        for nnr in (0.75, 0.9):
+            for blr in (0, 1):
+                n, m = ref.match(d1, d2, nnr, best_lr=blr)
+                out[f"m_{nnr}_{blr}"] = m
+                out[f"n_{nnr}_{blr}"] = np.int32(n)
+                n, m = ref.match(d1, d2, nnr, best_lr=blr, m12=stale)
+                out[f"ms_{nnr}_{blr}"] = m
+                out[f"ns_{nnr}_{blr}"] = np.int32(n)
+        save(f"brute_{ci}", **out)
+
+
+def grid_cases():
+    specs = [
+        (300, 300, False, False, (10, 0, 0, 0), 0, 0),
+        (250, 200, False, True, (3, 3, 3, 3), 6, 0),
+        (40, 6, False, True, (70, 70, 50, 50), 0, 0),
+        (120, 120, True, False, (10, 0, 0, 0), 0, 3),
+        (150, 90, True, True, (3, 3, 3, 3), 0, 5),
+        (1500, 200, False, False, (3, 3, 3, 3), 0, 0),
+    ]
+    for ci, (n1, n2, is_lines, tie, win, bad, zl) in enumerate(specs):
+        rng = np.random.default_rng(synth.SEED0 + 100 + ci)
+        case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=tie, win=win, bad_items=bad, zero_len=zl)
+        out = {k: v for k, v in case.items() if v is not None}
+        out["is_lines"] = np.int32(is_lines)
+        for ratio in (0.75, 0.9, 1.0):
+            for blr in (0, 1):
+                if is_lines:
+                    n, m = ref.match_grid_lines(case["coords"], case["d1"], case["cell_start"], case["cell_items"],
+                                                case["rows"], case["cols"], case["d2"], case["dirs2"], 0.75,
+                                                case["win"], ratio, blr)
+                else:
+                    n, m = ref.match_grid_points(case["coords"], case["d1"], case["cell_start"], case["cell_items"],
+                                                 case["rows"], case["cols"], case["d2"], case["win"], ratio, blr)
+                out[f"m_{ratio}_{blr}"] = m
+                out[f"n_{ratio}_{blr}"] = np.int32(n)
+        save(f"grid_{ci}", **out)
+
+
+def line_coord_cases():
+    rng = np.random.default_rng(synth.SEED0 + 200)
+    seg = rng.uniform(-4, 70, (200, 4))
+    seg[:10, 2:] = seg[:10, :2]            # zero-length
+    seg[10:20, 1] = seg[10:20, 3]          # horizontal
+    seg[20:30, 0] = seg[20:30, 2]          # vertical
+    flat, offs = [], [0]
+    for s in seg:
+        c = ref.line_coords(*s)
+        flat.append(c)
+        offs.append(offs[-1] + len(c))
+    save("line_coords", seg=seg, cells=np.concatenate(flat), offs=np.array(offs, np.int64))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    brute_cases()
+    grid_cases()
+    line_coord_cases()
