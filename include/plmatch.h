@@ -207,6 +207,36 @@ int plm_dev_nnr_accept(plm_ctx *ctx, const uint64_t *top2_dev, int n1, float nnr
 int plm_dev_cross_check(plm_ctx *ctx, int32_t *m12_dev_inout, int n1, int64_t i1_base,
                         const int32_t *m21_dev, int64_t n2, int32_t *count_dev);
 
+/* Row-sharded matchGrid (config 4: the local map is desc1, sharded over GPUs).  All
+ * pointers are device pointers.  The running per-column minimum of the reference spans shards, so
+ * the call is split around ONE exchange:
+ *   1. plm_dev_grid_colmin   col_min[i2] = min Hamming distance of this shard's candidate pairs
+ *                            (uint16, 0xFFFF = none)
+ *   -- caller all-gathers col_min and takes, per column, the min over LOWER-ranked shards = seed --
+ *   2. plm_dev_grid_match    matches this shard's rows against thresholds that start at seed
+ *                            (NULL = none); accepted rows go to m12_inout, *count += accepts and
+ *                            m21key[i2] = min over live pairs of (distance << 32 | i1_base + i1)
+ *                            (UINT64_MAX = none)
+ *   -- caller min-reduces m21key over shards --
+ *   3. plm_dev_m21_from_keys + plm_dev_cross_check finish the mutual check on every shard. */
+typedef struct plm_dev_grid_args {
+    const int32_t *coords;     /* n1 x 2 (points) or n1 x 4 (lines) */
+    const void *d1;            /* n1 x 32 bytes */
+    const int32_t *cell_start; /* grid_rows * grid_cols + 1 */
+    const int32_t *cell_items;
+    const void *d2;            /* n2 x 32 bytes */
+    const double *dirs2;       /* n2 x 2, lines only */
+    int32_t *m12_inout;        /* n1 */
+    int32_t *count;            /* 1 */
+    int64_t i1_base;           /* global index of this shard's row 0 */
+    double ratio, line_sim_th;
+    int32_t n1, n2, grid_rows, grid_cols, is_lines, best_lr;
+    int32_t win[4];
+} plm_dev_grid_args;
+int plm_dev_grid_colmin(plm_ctx *ctx, const plm_dev_grid_args *a, uint16_t *col_min_dev);
+int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const uint16_t *seed_dev, uint64_t *m21key_dev);
+int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int n2, int32_t *m21_dev);
+
 /* A device-resident descriptor database shard (keyframe DB / local map). */
 int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out);
 int plm_db_destroy(plm_db *db);

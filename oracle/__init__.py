@@ -31,6 +31,8 @@ def build(verbose: bool = False) -> None:
     targets = ["oracle"]
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "stvo-pl", "src")):
         targets.append("ref")
+        if os.path.exists(os.path.join(_HERE, "..", "pl_inertial_slam_b200", "lib", "libplmatch.so")):
+            targets.append("stvo_gpu")  # the C++ drop-in over the CUDA library, same harness
     out = subprocess.run(["make", "-C", _HERE] + targets, capture_output=True, text=True)
     if verbose or out.returncode != 0:
         print(out.stdout, out.stderr)
@@ -86,6 +88,10 @@ class _Port:
             L.plo_match_grid_lines.argtypes = [_i32p, _u8p, C.c_int, C.c_size_t, _i32p, _i32p, C.c_int, C.c_int,
                                                _u8p, C.c_int, C.c_size_t, _f64p, C.c_double, _i32p, C.c_double,
                                                C.c_int, _i32p]
+            L.plo_match_grid_shard.restype = C.c_int
+            L.plo_match_grid_shard.argtypes = [C.c_int, _i32p, _u8p, C.c_int, C.c_size_t, C.c_int64, _i32p, _i32p,
+                                               C.c_int, C.c_int, _u8p, C.c_int, C.c_size_t, _f64p, C.c_double, _i32p,
+                                               C.c_double, C.c_int, _i32p, C.c_void_p, C.c_void_p, C.c_void_p]
             L.plo_stereo_filter_points.restype = C.c_int
             L.plo_stereo_filter_points.argtypes = [_f32p, _f32p, _i32p, C.c_int, C.c_double, C.c_double, _u8p, _f64p]
             L.plo_stereo_filter_lines.restype = C.c_int
@@ -165,6 +171,29 @@ class _Port:
                                           int(bool(best_lr)), m12.ctypes.data_as(_i32p))
         return n, m12
 
+    def match_grid_shard(self, is_lines, coords, d1, i1_base, cell_start, cell_items, rows, cols, d2, dirs2,
+                         line_sim_th, win, ratio, best_lr, m12, seed=None):
+        """Row-shard form: (accepts, m12, colmin uint16[n2], m21key uint64[n2]); no mutual check."""
+        p1, n1, s1 = _desc(d1)
+        p2, n2, s2 = _desc(d2)
+        xy, xyp = _i32(coords)
+        cs, csp = _i32(cell_start)
+        ci, cip = _i32(cell_items if len(cell_items) else np.zeros(1, np.int32))
+        w, wp = _i32(win)
+        dirs = np.ascontiguousarray(dirs2 if dirs2 is not None else np.zeros((max(n2, 1), 2)), np.float64)
+        m12 = np.array(m12, np.int32)
+        colmin = np.full(max(n2, 1), 0xFFFF, np.uint16)
+        key = np.full(max(n2, 1), 0xFFFFFFFFFFFFFFFF, np.uint64)
+        seed_p = None
+        if seed is not None:
+            seed = np.ascontiguousarray(seed, np.uint16)
+            seed_p = seed.ctypes.data_as(C.c_void_p)
+        n = self.lib.plo_match_grid_shard(int(bool(is_lines)), xyp, p1, n1, s1, int(i1_base), csp, cip, rows, cols, p2,
+                                          n2, s2, dirs.ctypes.data_as(_f64p), float(line_sim_th), wp, float(ratio),
+                                          int(bool(best_lr)), m12.ctypes.data_as(_i32p), seed_p,
+                                          colmin.ctypes.data_as(C.c_void_p), key.ctypes.data_as(C.c_void_p))
+        return n, m12, colmin[:n2], key[:n2]
+
     def stereo_filter_points(self, kp_l, kp_r, m12, max_dist_epip=1.0, min_disp=1.0):
         kp_l = np.ascontiguousarray(kp_l, np.float32)
         kp_r = np.ascontiguousarray(kp_r, np.float32)
@@ -192,10 +221,13 @@ class _Port:
 
 
 class _Ref:
-    """The reference's own matching.cpp / gridStructure.cpp / lineIterator.cpp (compiled unmodified)."""
+    """The reference's own matching.cpp / gridStructure.cpp / lineIterator.cpp (compiled unmodified),
+    or -- with libname="libstvo_gpu.so" -- the product's C++ drop-in for matching.cpp (StVO::
+    signatures over the CUDA library) behind the same extern "C" harness."""
 
-    def __init__(self):
+    def __init__(self, libname: str = "libplref.so"):
         self._lib = None
+        self._libname = libname
 
     def available(self) -> bool:
         try:
@@ -206,7 +238,7 @@ class _Ref:
     @property
     def lib(self):
         if self._lib is None:
-            L = _load("libplref.so")
+            L = _load(self._libname)
             L.plref_set_threads.argtypes = [C.c_int]
             L.plref_get_threads.restype = C.c_int
             L.plref_set_config.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
@@ -307,3 +339,4 @@ class _Ref:
 
 port = _Port()
 ref = _Ref()
+stvo_gpu = _Ref("libstvo_gpu.so")  # the thing under test in tests/test_cxx_dropin.py, not a checker

@@ -220,18 +220,51 @@ static void plo_set_add_window(plo_set *s, int tag, int x, int y, const int32_t 
  * The unordered_set iteration order of the reference is unspecified; for ratio <= 1 an accepted
  * row has a strict unique minimum so the order cannot change any output (SURVEY 8a note 1).
  */
+static int plo_match_grid_ex(int is_lines, const int32_t *coords, const uint8_t *d1, int n1,
+                             size_t step1, const int32_t *cell_start, const int32_t *cell_items,
+                             int rows, int cols, const uint8_t *d2, int n2, size_t step2,
+                             const double *dirs2, double line_sim_th, const int32_t win[4],
+                             double ratio, int best_lr, int32_t *m12, const uint16_t *seed,
+                             int do_cross, int64_t i1_base, uint16_t *colmin_out,
+                             uint64_t *m21key_out);
+
 static int plo_match_grid(int is_lines, const int32_t *coords, const uint8_t *d1, int n1,
                           size_t step1, const int32_t *cell_start, const int32_t *cell_items,
                           int rows, int cols, const uint8_t *d2, int n2, size_t step2,
                           const double *dirs2, double line_sim_th, const int32_t win[4],
                           double ratio, int best_lr, int32_t *m12)
 {
+    return plo_match_grid_ex(is_lines, coords, d1, n1, step1, cell_start, cell_items, rows, cols,
+                             d2, n2, step2, dirs2, line_sim_th, win, ratio, best_lr, m12, NULL, 1,
+                             0, NULL, NULL);
+}
+
+/*
+ * The loop above with three hooks for ROW-SHARDED execution: `seed` initialises
+ * distances[] (the running column minima left behind by the rows of lower-ranked shards; 0xFFFF =
+ * INT_MAX), do_cross = 0 defers the final mutual check (it needs every shard's m21), and the
+ * per-column state is exported: colmin_out = final distances[] (0xFFFF = INT_MAX), m21key_out =
+ * (distance << 32 | i1_base + i1) of the last live pair of this shard (UINT64_MAX = none).
+ * With seed == NULL, do_cross == 1 it is exactly the reference function.
+ */
+static int plo_match_grid_ex(int is_lines, const int32_t *coords, const uint8_t *d1, int n1,
+                             size_t step1, const int32_t *cell_start, const int32_t *cell_items,
+                             int rows, int cols, const uint8_t *d2, int n2, size_t step2,
+                             const double *dirs2, double line_sim_th, const int32_t win[4],
+                             double ratio, int best_lr, int32_t *m12, const uint16_t *seed,
+                             int do_cross, int64_t i1_base, uint16_t *colmin_out,
+                             uint64_t *m21key_out)
+{
     int matches = 0;
     int32_t *m21 = NULL, *distances = NULL;
     if (best_lr) {
         m21 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
         distances = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n2 > 0 ? n2 : 1));
-        for (int j = 0; j < n2; j++) { m21[j] = -1; distances[j] = INT_MAX; }
+        for (int j = 0; j < n2; j++) {
+            m21[j] = -1;
+            distances[j] = (seed && seed[j] != 0xFFFFu) ? (int)seed[j] : INT_MAX;
+            if (m21key_out) m21key_out[j] = UINT64_MAX;
+        }
     }
     const int n_items = cell_start[rows * cols];
     plo_set set;
@@ -278,6 +311,8 @@ static int plo_match_grid(int is_lines, const int32_t *coords, const uint8_t *d1
                 if (d < distances[i2]) {
                     distances[i2] = d;
                     m21[i2] = i1;
+                    if (m21key_out)
+                        m21key_out[i2] = ((uint64_t)d << 32) | (uint64_t)(i1_base + i1);
                 } else
                     continue;
             }
@@ -293,7 +328,10 @@ static int plo_match_grid(int is_lines, const int32_t *coords, const uint8_t *d1
             matches++;
         }
     }
-    if (best_lr) {
+    if (best_lr && colmin_out)
+        for (int j = 0; j < n2; j++)
+            colmin_out[j] = distances[j] == INT_MAX ? 0xFFFFu : (uint16_t)distances[j];
+    if (best_lr && do_cross) {
         for (int i1 = 0; i1 < n1; ++i1) {
             int i2 = m12[i1];
             if (i2 >= 0 && m21[i2] != i1) {
@@ -331,6 +369,19 @@ PLO_API int plo_match_grid_lines(const int32_t *xyxy, const uint8_t *d1, int n1,
 {
     return plo_match_grid(1, xyxy, d1, n1, step1, cell_start, cell_items, rows, cols, d2, n2,
                           step2, dirs2, line_sim_th, win, ratio, best_lr, m12);
+}
+
+/* Row-shard form of both matchGrid overloads (tests of the multi-GPU orchestration). */
+PLO_API int plo_match_grid_shard(int is_lines, const int32_t *coords, const uint8_t *d1, int n1,
+                                 size_t step1, int64_t i1_base, const int32_t *cell_start,
+                                 const int32_t *cell_items, int rows, int cols, const uint8_t *d2,
+                                 int n2, size_t step2, const double *dirs2, double line_sim_th,
+                                 const int32_t win[4], double ratio, int best_lr, int32_t *m12,
+                                 const uint16_t *seed, uint16_t *colmin_out, uint64_t *m21key_out)
+{
+    return plo_match_grid_ex(is_lines, coords, d1, n1, step1, cell_start, cell_items, rows, cols,
+                             d2, n2, step2, dirs2, line_sim_th, win, ratio, best_lr, m12, seed, 0,
+                             i1_base, colmin_out, m21key_out);
 }
 
 /* ---------------------------------------------------------------------------------------

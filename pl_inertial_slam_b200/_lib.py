@@ -36,6 +36,13 @@ class GridJob(C.Structure):
                 ("n2", C.c_int32), ("is_lines", C.c_int32), ("pad_", C.c_int32), ("win", C.c_int32 * 4)]
 
 
+class DevGridArgs(C.Structure):
+    _fields_ = [("coords", vp), ("d1", vp), ("cell_start", vp), ("cell_items", vp), ("d2", vp), ("dirs2", vp),
+                ("m12_inout", vp), ("count", vp), ("i1_base", C.c_int64), ("ratio", C.c_double),
+                ("line_sim_th", C.c_double), ("n1", C.c_int32), ("n2", C.c_int32), ("grid_rows", C.c_int32),
+                ("grid_cols", C.c_int32), ("is_lines", C.c_int32), ("best_lr", C.c_int32), ("win", C.c_int32 * 4)]
+
+
 PAIR_JOB_DTYPE = np.dtype([("off1", "<i8"), ("off2", "<i8"), ("off_m", "<i8"), ("n1", "<i4"), ("n2", "<i4")])
 GRID_JOB_DTYPE = np.dtype([("off_coords", "<i8"), ("off1", "<i8"), ("off2", "<i8"), ("off_cell_start", "<i8"),
                            ("off_cell_items", "<i8"), ("off_dirs2", "<i8"), ("off_m", "<i8"), ("n1", "<i4"),
@@ -84,6 +91,9 @@ SIGNATURES = {
     "plm_dev_top2_merge": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
     "plm_dev_nnr_accept": (C.c_int, [vp, vp, C.c_int, C.c_float, vp, vp]),
     "plm_dev_cross_check": (C.c_int, [vp, vp, C.c_int, C.c_int64, vp, C.c_int64, vp]),
+    "plm_dev_grid_colmin": (C.c_int, [vp, C.POINTER(DevGridArgs), vp]),
+    "plm_dev_grid_match": (C.c_int, [vp, C.POINTER(DevGridArgs), vp, vp]),
+    "plm_dev_m21_from_keys": (C.c_int, [vp, vp, C.c_int, vp]),
     "plm_db_create": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
     "plm_db_destroy": (C.c_int, [vp]),
     "plm_db_upload": (C.c_int, [vp, vp, C.c_int64, C.c_size_t, C.c_int64]),

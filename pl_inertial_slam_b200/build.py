@@ -14,7 +14,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libplmatch.so")
-REFERENCE_INC = "/root/reference/stvo-pl/include"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -54,37 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(res.stdout, res.stderr, file=sys.stderr)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed building libplmatch.so")
-    build_stvo_wrapper(force=force, verbose=verbose)
     return LIB
-
-
-STVO_LIB = os.path.join(LIBDIR, "libstvo_matching_gpu.so")
-
-
-def build_stvo_wrapper(force: bool = False, verbose: bool = False):
-    """The C++ drop-in for stvo-pl/src/matching.cpp needs the reference's own headers
-    (matching.h, gridStructure.h, config.h); it is built only where /root/reference exists and the
-    prebuilt .so travels to the GPU box."""
-    src = os.path.join(CSRC, "stvo_matching_gpu.cpp")
-    if not os.path.exists(src) or not os.path.isdir(REFERENCE_INC):
-        return None
-    shim = os.path.join(HERE, "..", "oracle", "shim")
-    harness = os.path.join(CSRC, "stvo_harness.cpp")
-    ref_src = "/root/reference/stvo-pl/src"
-    sources = [src, harness]
-    if not (force or _stale(STVO_LIB, sources + [LIB])):
-        return STVO_LIB
-    cmd = ["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-fvisibility=hidden",
-           "-I", shim, "-I", REFERENCE_INC, "-I", os.path.join(HERE, "..", "include"),
-           src, harness, os.path.join(ref_src, "gridStructure.cpp"), os.path.join(ref_src, "lineIterator.cpp"),
-           os.path.join(shim, "config_stub.cpp"),
-           "-o", STVO_LIB, "-L", LIBDIR, "-lplmatch", "-Wl,-rpath,$ORIGIN"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        print(res.stdout, res.stderr, file=sys.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("g++ failed building libstvo_matching_gpu.so")
-    return STVO_LIB
 
 
 if __name__ == "__main__":

@@ -808,6 +808,128 @@ PLM_API int plm_match_grid_lines(plm_ctx *ctx, const int32_t *xyxy, const uint8_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-sharded matchGrid on device-resident data
+namespace {
+
+int dev_grid_setup(plm_ctx *&ctx, const plm_dev_grid_args *a, plm::GridJob &job, plm::GridParams &gp, int &warps, int &n_cta,
+                   size_t &smem) {
+    if (!a) return fail(PLM_E_INVALID, "null args");
+    if (a->n1 < 0 || a->n2 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (a->grid_rows <= 0 || a->grid_cols <= 0) return fail(PLM_E_GRID, "[GridStructure] invalid dimension");
+    if (a->ratio > 1.0) return fail(PLM_E_RATIO, plm_status_string(PLM_E_RATIO));
+    if (a->n2 > GRID_N2_MAX) return fail(PLM_E_UNSUPPORTED, "matchGrid supports at most 32768 train features");
+    if (a->n1 > 0 && (!a->coords || !a->d1 || !a->m12_inout || !a->count)) return fail(PLM_E_INVALID, "null pointer");
+    if (!a->cell_start || (a->n2 > 0 && !a->d2) || (a->is_lines && a->n2 > 0 && !a->dirs2)) return fail(PLM_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(a->d1) | reinterpret_cast<uintptr_t>(a->d2)) & 15)
+        return fail(PLM_E_INVALID, "device descriptor pointers must be 16-byte aligned");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    std::memset(&job, 0, sizeof(job));
+    job.coords = a->coords;
+    job.d1 = static_cast<const uint4 *>(a->d1);
+    job.cell_start = a->cell_start;
+    job.cell_items = a->cell_items;
+    job.d2 = static_cast<const uint4 *>(a->d2);
+    job.dirs2 = a->dirs2;
+    job.m12 = a->m12_inout;
+    job.count = a->count;
+    job.n1 = a->n1;
+    job.n2 = a->n2;
+    job.is_lines = a->is_lines ? 1 : 0;
+    for (int i = 0; i < 4; ++i) job.win[i] = a->win[i];
+    job.i1_base = a->i1_base;
+    std::memset(&gp, 0, sizeof(gp));
+    gp.grid_rows = a->grid_rows;
+    gp.grid_cols = a->grid_cols;
+    gp.best_lr = a->best_lr ? 1 : 0;
+    gp.ratio = a->ratio;
+    gp.line_sim_th = a->line_sim_th;
+    gp.rows_per_warp = GRID_CHUNK_ROWS_PER_WARP;
+    const size_t budget = std::min<size_t>(ctx->smem_optin - 2048, 200 * 1024);
+    warps = 16;
+    while (warps > 1 && size_t(warps) * std::max(a->n2, 1) * 2 > budget) warps >>= 1;
+    const long long rows_per_cta = static_cast<long long>(warps) * GRID_CHUNK_ROWS_PER_WARP;
+    n_cta = static_cast<int>((a->n1 + rows_per_cta - 1) / rows_per_cta);
+    smem = size_t(warps) * std::max(a->n2, 1) * 2;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (ctx->chunked_attr[pass] < smem) {
+            if (pass == 0)
+                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(ctx->smem_optin - 2048)));
+            else
+                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(ctx->smem_optin - 2048)));
+            ctx->chunked_attr[pass] = ctx->smem_optin - 2048;
+        }
+    }
+    st = ctx->ensure_device(align_up(size_t(std::max(n_cta, 1)) * std::max(a->n2, 1) * 2));
+    if (st != PLM_OK) return st;
+    gp.cta_min = reinterpret_cast<uint16_t *>(ctx->d_buf);
+    return PLM_OK;
+}
+
+} // namespace
+
+PLM_API int plm_dev_grid_colmin(plm_ctx *ctx, const plm_dev_grid_args *a, uint16_t *col_min_dev) {
+    plm::GridJob job;
+    plm::GridParams gp;
+    int warps = 0, n_cta = 0;
+    size_t smem = 0;
+    int st = dev_grid_setup(ctx, a, job, gp, warps, n_cta, smem);
+    if (st != PLM_OK) return st;
+    if (a->n2 == 0) return PLM_OK;
+    if (!col_min_dev) return fail(PLM_E_INVALID, "null col_min");
+    if (!gp.best_lr || n_cta == 0) {
+        CU_TRY(cudaMemsetAsync(col_min_dev, 0xFF, size_t(a->n2) * 2, ctx->stream));
+        return PLM_OK;
+    }
+    plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    plm::grid_scan_kernel<<<(a->n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, nullptr, col_min_dev);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const uint16_t *seed_dev, uint64_t *m21key_dev) {
+    plm::GridJob job;
+    plm::GridParams gp;
+    int warps = 0, n_cta = 0;
+    size_t smem = 0;
+    int st = dev_grid_setup(ctx, a, job, gp, warps, n_cta, smem);
+    if (st != PLM_OK) return st;
+    if (gp.best_lr && a->n2 > 0 && !m21key_dev) return fail(PLM_E_INVALID, "null m21key");
+    gp.m21key = reinterpret_cast<unsigned long long *>(m21key_dev);
+    if (gp.best_lr && a->n2 > 0) CU_TRY(cudaMemsetAsync(m21key_dev, 0xFF, size_t(a->n2) * 8, ctx->stream));
+    if (n_cta == 0 || a->n2 == 0) return PLM_OK;
+    if (gp.best_lr) {
+        plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        plm::grid_scan_kernel<<<(a->n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, seed_dev, nullptr);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    plm::grid_match_chunked_kernel<1><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int n2, int32_t *m21_dev) {
+    if (n2 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n2 == 0) return PLM_OK;
+    if (!m21key_dev || !m21_dev) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::m21_from_keys_kernel<<<(n2 + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(m21key_dev), n2, m21_dev);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stereo post-filters
 PLM_API int plm_stereo_filter_points(plm_ctx *ctx, const float *kp_l, int n1, const float *kp_r, int n2, const int32_t *m12,
                                      double max_dist_epip, double min_disp, uint8_t *keep, double *disp, int *n_kept) {

@@ -1,17 +1,26 @@
-"""Device-resident descriptor database shards (keyframe database / local map) and the multi-GPU
-top-2 merge.
+"""Device-resident descriptor databases sharded over GPUs (one process per GPU, torch.distributed).
 
-The reference keeps every keyframe's descriptor Mats in host memory (include/keyFrame.h:69-96) and
-matches one candidate at a time (src/mapHandler.cpp:3301-3409).  Here the database rows live in HBM,
-row-sharded over the ranks of a torch.distributed job (one process per GPU); a query is matched
-against the local shard by the brute-force kernel, the per-query packed top-2 keys of all shards are
-all-gathered over NCCL/NVLink and merged lexicographically, so the G-GPU result is bit-identical to
-the single-GPU one (lowest global index wins ties).  torch is plumbing only: device memory, streams
-and the collective.
+The reference keeps every keyframe's descriptor Mats and the local map in host memory
+(include/keyFrame.h:69-96, src/mapHandler.cpp:583-803) and matches on one core.  Here the rows live in
+HBM, row-sharded contiguously over the ranks; torch is plumbing only (device memory,
+streams, the NCCL collective), all arithmetic is in the CUDA library:
+
+* ``ShardedDescriptorDB`` -- flat keyframe database (config 5): queries replicated, per-shard top-2
+  with GLOBAL row indices, all_gather of the packed keys, lexicographic merge.  Unsigned min over
+  (distance << 32 | global index) is the reference's lowest-index tie-breaking, so any number of
+  shards gives bit-identical results.
+* ``ShardedMap`` -- the local map is desc1 (the QUERY side) of matchMap2KF* (config 4): rows
+  sharded, the frame (desc2 + its grid) replicated.  ``match`` needs one exchange (the 21 direction's
+  top-2), ``match_grid`` needs the per-column running minima of lower-ranked shards before matching
+  and the per-column best pairs after it.
+
+The arithmetic backend is injected (``DeviceOps`` = the CUDA library) so the orchestration can be
+exercised on CPU tensors with gloo in the test-suite.
 """
 from __future__ import annotations
 
 import ctypes as C
+from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import numpy as np
@@ -20,9 +29,11 @@ import torch
 from . import _lib as L
 from .matching import Context
 
+INT64_MIN = -(1 << 63)
 
-def _ptr(t: torch.Tensor) -> C.c_void_p:
-    return C.c_void_p(t.data_ptr())
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)
 
 
 def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
@@ -32,8 +43,19 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_rows, lo + per)
 
 
+@dataclass
+class GridFrame:
+    """The replicated (train) side of a matchGrid call, resident on the device."""
+    d2: torch.Tensor                 # n2 x 32 uint8
+    cell_start: torch.Tensor         # rows*cols+1 int32
+    cell_items: torch.Tensor         # int32
+    rows: int
+    cols: int
+    dirs2: Optional[torch.Tensor] = None   # n2 x 2 float64 (lines)
+
+
 class DeviceOps:
-    """Thin wrappers of the plm_dev_* entry points on torch CUDA tensors (current torch stream)."""
+    """The plm_dev_* entry points on torch CUDA tensors, launched on torch's current stream."""
 
     def __init__(self, device: Optional[int] = None):
         self.device = torch.cuda.current_device() if device is None else device
@@ -44,7 +66,7 @@ class DeviceOps:
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def knn2(self, q: torch.Tensor, db: torch.Tensor, idx_base: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """q: nq x 32 uint8, db: n x 32 uint8 (both CUDA, contiguous) -> nq x 2 int64 packed keys."""
+        """q: nq x 32 uint8, db: n x 32 uint8 (contiguous) -> nq x 2 int64 packed keys."""
         assert q.is_cuda and db.is_cuda and q.dtype == torch.uint8 and db.dtype == torch.uint8
         assert q.is_contiguous() and db.is_contiguous() and q.shape[-1] == 32 and db.shape[-1] == 32
         nq, n = q.shape[0], db.shape[0]
@@ -56,7 +78,7 @@ class DeviceOps:
 
     def top2_merge(self, parts: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """parts: P x nq x 2 int64 packed keys -> nq x 2 (two smallest keys per query)."""
-        assert parts.is_cuda and parts.dtype == torch.int64 and parts.is_contiguous() and parts.dim() == 3
+        assert parts.dtype == torch.int64 and parts.is_contiguous() and parts.dim() == 3
         p, nq = parts.shape[0], parts.shape[1]
         if out is None:
             out = torch.empty((nq, 2), dtype=torch.int64, device=parts.device)
@@ -64,8 +86,8 @@ class DeviceOps:
         L.check(self.lib.plm_dev_top2_merge(self.ctx.handle, _ptr(parts), p, nq, _ptr(out)), "plm_dev_top2_merge")
         return out
 
-    def nnr_accept(self, top2: torch.Tensor, nnr: float, m12: torch.Tensor, count: torch.Tensor) -> None:
-        assert m12.dtype == torch.int32 and count.dtype == torch.int32
+    def nnr_accept(self, top2: torch.Tensor, nnr: float, m12: torch.Tensor, count: Optional[torch.Tensor]) -> None:
+        assert m12.dtype == torch.int32
         self._bind_stream()
         L.check(self.lib.plm_dev_nnr_accept(self.ctx.handle, _ptr(top2), top2.shape[0], C.c_float(nnr), _ptr(m12),
                                             _ptr(count)), "plm_dev_nnr_accept")
@@ -75,49 +97,108 @@ class DeviceOps:
         L.check(self.lib.plm_dev_cross_check(self.ctx.handle, _ptr(m12), m12.shape[0], i1_base, _ptr(m21),
                                              m21.shape[0], _ptr(count)), "plm_dev_cross_check")
 
+    def _grid_args(self, coords, d1, i1_base, frame: GridFrame, win, ratio, line_sim_th, best_lr, m12, count):
+        a = L.DevGridArgs()
+        a.coords, a.d1 = _ptr(coords), _ptr(d1)
+        a.cell_start, a.cell_items = _ptr(frame.cell_start), _ptr(frame.cell_items)
+        a.d2, a.dirs2 = _ptr(frame.d2), _ptr(frame.dirs2)
+        a.m12_inout, a.count = _ptr(m12), _ptr(count)
+        a.i1_base, a.ratio, a.line_sim_th = int(i1_base), float(ratio), float(line_sim_th)
+        a.n1, a.n2 = int(d1.shape[0]), int(frame.d2.shape[0])
+        a.grid_rows, a.grid_cols = frame.rows, frame.cols
+        a.is_lines, a.best_lr = int(frame.dirs2 is not None), int(bool(best_lr))
+        for i in range(4):
+            a.win[i] = int(win[i])
+        return a
 
-class ShardedDescriptorDB:
-    """Row-sharded descriptor database over the ranks of the default process group.
+    def grid_colmin(self, coords, d1, i1_base, frame, win, ratio, line_sim_th, best_lr) -> torch.Tensor:
+        """Per-column minimum distance over this shard's candidate pairs: int16 bits of uint16, n2."""
+        n2 = frame.d2.shape[0]
+        out = torch.empty(n2, dtype=torch.int16, device=d1.device)
+        a = self._grid_args(coords, d1, i1_base, frame, win, ratio, line_sim_th, best_lr, None, None)
+        # setup validates m12/count pointers only when n1 > 0; colmin never writes them
+        dummy = torch.zeros(max(1, d1.shape[0]) + 1, dtype=torch.int32, device=d1.device)
+        a.m12_inout, a.count = _ptr(dummy), C.c_void_p(dummy.data_ptr() + 4 * max(1, d1.shape[0]))
+        self._bind_stream()
+        L.check(self.lib.plm_dev_grid_colmin(self.ctx.handle, C.byref(a), _ptr(out)), "plm_dev_grid_colmin")
+        return out
 
-    ``rows`` (host, n x 32 uint8) is the WHOLE database on every rank for construction convenience;
-    each rank uploads only its contiguous shard.  With world == 1 no collective is issued.
-    """
+    def grid_match(self, coords, d1, i1_base, frame, win, ratio, line_sim_th, best_lr, m12, count,
+                   seed: Optional[torch.Tensor]) -> torch.Tensor:
+        """Match this shard's rows; returns m21key int64 bits of uint64, n2."""
+        n2 = frame.d2.shape[0]
+        key = torch.empty(n2, dtype=torch.int64, device=d1.device)
+        a = self._grid_args(coords, d1, i1_base, frame, win, ratio, line_sim_th, best_lr, m12, count)
+        self._bind_stream()
+        L.check(self.lib.plm_dev_grid_match(self.ctx.handle, C.byref(a), _ptr(seed), _ptr(key)), "plm_dev_grid_match")
+        return key
 
-    def __init__(self, rows: Optional[np.ndarray] = None, n_rows: Optional[int] = None, device: Optional[int] = None,
-                 group=None, shard: Optional[torch.Tensor] = None):
+    def m21_from_keys(self, key: torch.Tensor) -> torch.Tensor:
+        m21 = torch.empty(key.shape[0], dtype=torch.int32, device=key.device)
+        self._bind_stream()
+        L.check(self.lib.plm_dev_m21_from_keys(self.ctx.handle, _ptr(key), key.shape[0], _ptr(m21)), "plm_dev_m21_from_keys")
+        return m21
+
+
+class _Group:
+    """The collectives the sharded paths need, on the default (or a given) process group."""
+
+    def __init__(self, group=None):
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = group
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0
-        self.ops = DeviceOps(device)
-        dev = torch.device("cuda", self.ops.device)
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """-> [world, *t.shape]"""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        t = t.contiguous()
+        flat = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(flat, t, group=self.group)   # concatenation along dim 0
+        return flat.view((self.world,) + tuple(t.shape))
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class ShardedDescriptorDB:
+    """Flat descriptor database (config 5), row-sharded over the ranks of a process group.
+
+    Pass ``rows`` (host, the WHOLE database; each rank uploads only its shard) or an already resident
+    ``shard`` tensor with the global row count ``n_rows``.
+    """
+
+    def __init__(self, rows: Optional[np.ndarray] = None, n_rows: Optional[int] = None, device: Optional[int] = None,
+                 group=None, shard: Optional[torch.Tensor] = None, ops=None):
+        self.g = _Group(group)
+        self.world, self.rank = self.g.world, self.g.rank
+        self.ops = ops if ops is not None else DeviceOps(device)
         if shard is not None:
             assert n_rows is not None
-            self.n_rows = n_rows
-            self.lo, self.hi = shard_bounds(n_rows, self.world, self.rank)
+            self.n_rows = int(n_rows)
+            self.lo, self.hi = shard_bounds(self.n_rows, self.world, self.rank)
             assert shard.shape[0] == self.hi - self.lo
             self.shard = shard
         else:
             self.n_rows = int(rows.shape[0])
             self.lo, self.hi = shard_bounds(self.n_rows, self.world, self.rank)
-            self.shard = torch.from_numpy(np.ascontiguousarray(rows[self.lo:self.hi])).to(dev)
-        self._gather = None
+            t = torch.from_numpy(np.ascontiguousarray(rows[self.lo:self.hi]))
+            self.shard = t.to(torch.device("cuda", self.ops.device)) if hasattr(self.ops, "device") else t
 
     def knn2_local(self, q: torch.Tensor) -> torch.Tensor:
         """Packed top-2 of the queries over THIS rank's shard, with global row indices."""
         return self.ops.knn2(q, self.shard, idx_base=self.lo)
 
     def knn2(self, q: torch.Tensor) -> torch.Tensor:
-        """Packed top-2 over the whole database: local kernel -> all_gather (NCCL) -> merge kernel."""
+        """Packed top-2 over the whole database: local kernel -> all_gather -> merge kernel."""
         local = self.knn2_local(q)
         if self.world == 1:
             return local
-        nq = q.shape[0]
-        if self._gather is None or self._gather.shape[1] != nq:
-            self._gather = torch.empty((self.world, nq, 2), dtype=torch.int64, device=q.device)
-        self.dist.all_gather_into_tensor(self._gather, local, group=self.group)
-        return self.ops.top2_merge(self._gather)
+        return self.ops.top2_merge(self.g.all_gather(local))
 
     def match_nnr(self, q: torch.Tensor, nnr: float):
         """StVO::matchNNR of the queries against the whole (sharded) database -> (count, m12)."""
@@ -126,3 +207,83 @@ class ShardedDescriptorDB:
         count = torch.zeros(1, dtype=torch.int32, device=q.device)
         self.ops.nnr_accept(top2, nnr, m12, count)
         return count, m12
+
+
+class ShardedMap:
+    """The local map as the row-sharded QUERY side (desc1) of matchMap2KF* (config 4).
+
+    ``d1_shard`` / ``coords_shard`` are this rank's rows [lo, hi) of the n_rows map features
+    (coords: n x 2 cell coordinates for points, n x 4 for lines).
+    """
+
+    def __init__(self, n_rows: int, d1_shard: torch.Tensor, coords_shard: Optional[torch.Tensor] = None, group=None,
+                 ops=None, device: Optional[int] = None):
+        self.g = _Group(group)
+        self.world, self.rank = self.g.world, self.g.rank
+        self.ops = ops if ops is not None else DeviceOps(device)
+        self.n_rows = int(n_rows)
+        self.lo, self.hi = shard_bounds(self.n_rows, self.world, self.rank)
+        assert d1_shard.shape[0] == self.hi - self.lo
+        self.d1 = d1_shard
+        self.coords = coords_shard
+        self.per = (self.n_rows + self.world - 1) // self.world
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _gather_rows(self, m12_local: torch.Tensor) -> torch.Tensor:
+        """Concatenate the per-shard match vectors into the global n_rows vector (on every rank)."""
+        if self.world == 1:
+            return m12_local
+        pad = torch.full((self.per,), -1, dtype=m12_local.dtype, device=m12_local.device)
+        pad[: m12_local.shape[0]] = m12_local
+        return self.g.all_gather(pad).reshape(-1)[: self.n_rows]
+
+    def _local_m12(self, m12_global: Optional[torch.Tensor], device) -> torch.Tensor:
+        if m12_global is None:
+            return torch.full((self.hi - self.lo,), -1, dtype=torch.int32, device=device)
+        return m12_global[self.lo:self.hi].clone()
+
+    # -- StVO::match (brute-force fallback, mapHandler.cpp:645-650) --------------------------------
+    def match(self, d2: torch.Tensor, nnr: float, best_lr: bool = True, m12_inout: Optional[torch.Tensor] = None):
+        """-> (count tensor [1], m12 global int32[n_rows]); m12_inout is the global in/out vector."""
+        dev = d2.device
+        m12 = self._local_m12(m12_inout, dev)
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        # direction 12: the shard's rows are final locally
+        top12 = self.ops.knn2(self.d1, d2, idx_base=0)
+        self.ops.nnr_accept(top12, nnr, m12, count)
+        if best_lr:
+            # direction 21: per-shard top-2 with global map indices -> gather -> merge -> ratio test
+            part = self.ops.knn2(d2, self.d1, idx_base=self.lo)
+            top21 = part if self.world == 1 else self.ops.top2_merge(self.g.all_gather(part))
+            m21 = torch.full((d2.shape[0],), -1, dtype=torch.int32, device=dev)
+            self.ops.nnr_accept(top21, nnr, m21, None)
+            self.ops.cross_check(m12, self.lo, m21, count)
+        self.g.all_reduce_sum(count)
+        return count, self._gather_rows(m12)
+
+    # -- StVO::matchGrid (mapHandler.cpp:637-642 / :752-757) --------------------------------------
+    def match_grid(self, frame: GridFrame, win, ratio: float, line_sim_th: float = 0.75, best_lr: bool = True,
+                   m12_inout: Optional[torch.Tensor] = None):
+        dev = frame.d2.device
+        n2 = frame.d2.shape[0]
+        m12 = self._local_m12(m12_inout, dev)
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        seed = None
+        if best_lr and self.world > 1:
+            # running column minima left behind by the rows of lower-ranked shards
+            cm = self.ops.grid_colmin(self.coords, self.d1, self.lo, frame, win, ratio, line_sim_th, best_lr)
+            # uint16 bits travel as int32 (neither NCCL nor gloo carries 16-bit integers)
+            allcm = self.g.all_gather(cm.to(torch.int32) & 0xFFFF)          # [world, n2], 0xFFFF = none
+            if self.rank > 0:
+                seed = allcm[: self.rank].min(dim=0).values.to(torch.int16).contiguous()
+        key = self.ops.grid_match(self.coords, self.d1, self.lo, frame, win, ratio, line_sim_th, best_lr, m12, count, seed)
+        if best_lr:
+            if self.world > 1:
+                # unsigned min over shards of (distance << 32 | global row): flip the sign bit so that
+                # signed min orders like unsigned
+                allk = self.g.all_gather(key) ^ INT64_MIN
+                key = (allk.min(dim=0).values ^ INT64_MIN).contiguous()
+            m21 = self.ops.m21_from_keys(key) if n2 else torch.empty(0, dtype=torch.int32, device=dev)
+            self.ops.cross_check(m12, self.lo, m21, count)
+        self.g.all_reduce_sum(count)
+        return count, self._gather_rows(m12)

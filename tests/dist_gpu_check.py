@@ -1,0 +1,63 @@
+"""torchrun target: the sharded database / map paths over NCCL on real GPUs, checked against the
+oracle on every rank.  `python -m torch.distributed.run --nproc-per-node N tests/dist_gpu_check.py`"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import oracle  # noqa: E402
+from helpers import oracle_grid, random_grid_case  # noqa: E402
+from pl_inertial_slam_b200 import synth  # noqa: E402
+from pl_inertial_slam_b200.database import GridFrame, ShardedDescriptorDB, ShardedMap, shard_bounds  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    port = oracle.port
+    rng = np.random.default_rng(2026)
+
+    # flat database (config 5 shape, small)
+    db = synth.tie_stress_desc(rng, 30011)
+    q = synth.tie_stress_desc(rng, 801)
+    lo, hi = shard_bounds(len(db), world, rank)
+    sdb = ShardedDescriptorDB(n_rows=len(db), shard=torch.from_numpy(db[lo:hi].copy()).to(dev), device=local)
+    got = sdb.knn2(torch.from_numpy(q).to(dev)).cpu().numpy().view(np.uint64)
+    assert (got == port.knn2_packed(q, db)).all(), "sharded knn2"
+    count, m12 = sdb.match_nnr(torch.from_numpy(q).to(dev), 0.9)
+    n_o, m_o = port.match_nnr(q, db, 0.9)
+    assert int(count.item()) == n_o and (m12.cpu().numpy() == m_o).all(), "sharded matchNNR"
+
+    # map -> frame (config 4 shape, scaled)
+    for is_lines in (False, True):
+        n1, n2 = (24000, 600) if not is_lines else (9000, 200)
+        case = random_grid_case(rng, n1, n2, is_lines=is_lines, win=(3, 3, 3, 3), zero_len=3 if is_lines else 0)
+        lo, hi = shard_bounds(n1, world, rank)
+        frame = GridFrame(torch.from_numpy(case["d2"]).to(dev), torch.from_numpy(case["cell_start"]).to(dev),
+                          torch.from_numpy(case["cell_items"]).to(dev), case["rows"], case["cols"],
+                          torch.from_numpy(case["dirs2"]).to(dev) if is_lines else None)
+        smap = ShardedMap(n1, torch.from_numpy(case["d1"][lo:hi].copy()).to(dev),
+                          torch.from_numpy(case["coords"][lo:hi].copy()).to(dev), ops=sdb.ops)
+        for best_lr in (True, False):
+            count, m12 = smap.match_grid(frame, case["win"], 0.9, 0.75, best_lr)
+            n_o, m_o = oracle_grid(port, case, 0.9, best_lr)
+            assert int(count.item()) == n_o and (m12.cpu().numpy() == m_o).all(), ("sharded matchGrid", is_lines, best_lr)
+            count2, m12b = smap.match(frame.d2, 0.9, best_lr, m12_inout=m12)
+            n_o2, m_o2 = port.match(case["d1"], case["d2"], 0.9, best_lr, m12=m_o)
+            assert int(count2.item()) == n_o2 and (m12b.cpu().numpy() == m_o2).all(), ("sharded match fallback", is_lines)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_GPU_CHECK_OK world", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""The C++ drop-in for stvo-pl/src/matching.cpp (pl_inertial_slam_b200/csrc/stvo_matching_gpu.cpp):
+StVO::matchNNR / match / distance / matchGrid x2 with the reference's exact signatures, built against
+the reference's own headers (oracle/Makefile target stvo_gpu) and driven through std::vector<int>& /
+cv::Mat / GridStructure arguments by the extern "C" harness.  Compared with the oracle port."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import oracle_grid, random_grid_case
+from pl_inertial_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+port = oracle.port
+HAVE = os.path.exists(os.path.join(os.path.dirname(oracle.__file__), "_ref", "libstvo_gpu.so"))
+needs_lib = pytest.mark.skipif(not HAVE, reason="oracle/_ref/libstvo_gpu.so not built (needs the reference headers)")
+
+
+@needs_lib
+def test_stvo_match_and_distance(plm_lib):
+    gpu = oracle.stvo_gpu
+    rng = np.random.default_rng(1)
+    for n1, n2, tie in [(2, 2, True), (300, 280, False), (64, 1025, True)]:
+        d1 = synth.tie_stress_desc(rng, n1) if tie else synth.rand_desc(rng, n1)
+        d2 = synth.tie_stress_desc(rng, n2) if tie else synth.rand_desc(rng, n2)
+        if not tie:
+            d1[:100] = synth.flip_bits(rng, d2[:100], 0.08)
+        for blr in (0, 1):
+            for nnr in (0.75, 0.9):
+                n_o, m_o = port.match(d1, d2, nnr, blr)
+                n_g, m_g = gpu.match(d1, d2, nnr, best_lr=blr)
+                assert n_g == n_o and (m_g == m_o).all()
+        n_o, m_o = port.match_nnr(d1, d2, 0.9)
+        n_g, m_g = gpu.match_nnr(d1, d2, 0.9)
+        assert n_g == n_o and (m_g == m_o).all()
+        assert gpu.distance(d1[0], d2[0]) == port.distance(d1[0], d2[0])
+
+
+@needs_lib
+def test_stvo_match_throws_like_the_reference(plm_lib):
+    gpu = oracle.stvo_gpu
+    d = np.zeros((4, 32), np.uint8)
+    with pytest.raises(RuntimeError):
+        gpu.match_nnr(d, d[:1], 0.9)  # "[matchNNR] Different size for matches and descriptors!"
+
+
+@needs_lib
+@pytest.mark.parametrize("is_lines", [False, True])
+def test_stvo_match_grid(plm_lib, is_lines):
+    gpu = oracle.stvo_gpu
+    rng = np.random.default_rng(2 + int(is_lines))
+    for n1, n2, tie, win in [(400, 350, False, (10, 0, 0, 0)), (200, 260, True, (3, 3, 3, 3)), (6000, 300, False, (3, 3, 3, 3))]:
+        case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=tie, win=win, zero_len=3 if is_lines else 0)
+        for ratio in (0.75, 0.9):
+            for blr in (0, 1):
+                n_o, m_o = oracle_grid(port, case, ratio, blr)
+                if is_lines:
+                    n_g, m_g = gpu.match_grid_lines(case["coords"], case["d1"], case["cell_start"], case["cell_items"],
+                                                    case["rows"], case["cols"], case["d2"], case["dirs2"], 0.75,
+                                                    case["win"], ratio, blr)
+                else:
+                    n_g, m_g = gpu.match_grid_points(case["coords"], case["d1"], case["cell_start"], case["cell_items"],
+                                                     case["rows"], case["cols"], case["d2"], case["win"], ratio, blr)
+                assert n_g == n_o and (m_g == m_o).all()

@@ -1,0 +1,111 @@
+"""CUDA kernels of the sharded paths: (a) G shards emulated one after another on ONE GPU through the
+same DeviceOps primitives the multi-rank code uses (seeded chunked matchGrid, global-index top-2,
+merge), (b) a real NCCL run of tests/dist_gpu_check.py under torchrun when >= 2 GPUs are visible."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import oracle_grid, random_grid_case
+from pl_inertial_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+port = oracle.port
+INT64_MIN = -(1 << 63)
+
+
+@pytest.fixture(scope="module")
+def ops(plm_lib):
+    from pl_inertial_slam_b200.database import DeviceOps
+    return DeviceOps(0)
+
+
+def test_knn2_shards_merge_to_global(ops):
+    from pl_inertial_slam_b200.database import shard_bounds
+    rng = np.random.default_rng(9)
+    db = synth.tie_stress_desc(rng, 5003)
+    q = synth.tie_stress_desc(rng, 333)
+    want = port.knn2_packed(q, db)
+    qd = torch.from_numpy(q).cuda()
+    for world in (1, 2, 5):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_bounds(len(db), world, r)
+            parts.append(ops.knn2(qd, torch.from_numpy(db[lo:hi].copy()).cuda(), idx_base=lo))
+        merged = ops.top2_merge(torch.stack(parts).contiguous())
+        assert (merged.cpu().numpy().view(np.uint64) == want).all()
+
+
+@pytest.mark.parametrize("is_lines", [False, True])
+@pytest.mark.parametrize("world", [2, 3])
+def test_grid_shards_emulated(ops, is_lines, world):
+    from pl_inertial_slam_b200.database import GridFrame, shard_bounds
+    rng = np.random.default_rng(400 + world + int(is_lines))
+    n1, n2 = 5000, 300
+    for tie in (False, True):
+        case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=tie, win=(3, 3, 3, 3), zero_len=4 if is_lines else 0)
+        frame = GridFrame(torch.from_numpy(case["d2"]).cuda(), torch.from_numpy(case["cell_start"]).cuda(),
+                          torch.from_numpy(case["cell_items"]).cuda(), case["rows"], case["cols"],
+                          torch.from_numpy(case["dirs2"]).cuda() if is_lines else None)
+        d1 = torch.from_numpy(case["d1"]).cuda()
+        co = torch.from_numpy(case["coords"]).cuda()
+        for best_lr in (True, False):
+            n_o, m_o = oracle_grid(port, case, 0.9, best_lr)
+            spans = [shard_bounds(n1, world, r) for r in range(world)]
+            m12 = [torch.full((hi - lo,), -1, dtype=torch.int32, device="cuda") for lo, hi in spans]
+            cnt = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in spans]
+            cms = [ops.grid_colmin(co[lo:hi].contiguous(), d1[lo:hi].contiguous(), lo, frame, case["win"], 0.9, 0.75, best_lr)
+                   for lo, hi in spans]
+            allcm = torch.stack(cms).to(torch.int32) & 0xFFFF
+            keys = []
+            for r, (lo, hi) in enumerate(spans):
+                seed = allcm[:r].min(dim=0).values.to(torch.int16).contiguous() if (r > 0 and best_lr) else None
+                keys.append(ops.grid_match(co[lo:hi].contiguous(), d1[lo:hi].contiguous(), lo, frame, case["win"], 0.9, 0.75,
+                                           best_lr, m12[r], cnt[r], seed))
+            if best_lr:
+                key = ((torch.stack(keys) ^ INT64_MIN).min(dim=0).values ^ INT64_MIN).contiguous()
+                m21 = ops.m21_from_keys(key)
+                for r, (lo, hi) in enumerate(spans):
+                    ops.cross_check(m12[r], lo, m21, cnt[r])
+            got = torch.cat(m12).cpu().numpy()
+            total = int(sum(int(c.item()) for c in cnt))
+            assert total == n_o and (got == m_o).all(), (is_lines, world, tie, best_lr)
+
+
+def test_sharded_classes_world1(ops):
+    """ShardedDescriptorDB / ShardedMap without a process group (world = 1) on the GPU."""
+    from pl_inertial_slam_b200.database import GridFrame, ShardedDescriptorDB, ShardedMap
+    rng = np.random.default_rng(31)
+    db = synth.rand_desc(rng, 40000)
+    q = synth.flip_bits(rng, db[rng.choice(40000, 500)], 0.08)
+    sdb = ShardedDescriptorDB(rows=db, ops=ops)
+    count, m12 = sdb.match_nnr(torch.from_numpy(q).cuda(), 0.9)
+    n_o, m_o = port.match_nnr(q, db, 0.9)
+    assert int(count.item()) == n_o and (m12.cpu().numpy() == m_o).all()
+
+    case = random_grid_case(rng, 20000, 600, win=(3, 3, 3, 3))
+    frame = GridFrame(torch.from_numpy(case["d2"]).cuda(), torch.from_numpy(case["cell_start"]).cuda(),
+                      torch.from_numpy(case["cell_items"]).cuda(), case["rows"], case["cols"])
+    smap = ShardedMap(20000, torch.from_numpy(case["d1"]).cuda(), torch.from_numpy(case["coords"]).cuda(), ops=ops)
+    count, m12 = smap.match_grid(frame, case["win"], 0.9)
+    n_o, m_o = oracle_grid(port, case, 0.9, 1)
+    assert int(count.item()) == n_o and (m12.cpu().numpy() == m_o).all()
+    # fallback: match() on the vector matchGrid just filled (mapHandler.cpp:645-650)
+    count2, m12b = smap.match(frame.d2, 0.9, True, m12_inout=m12)
+    n_o2, m_o2 = port.match(case["d1"], case["d2"], 0.9, True, m12=m_o)
+    assert int(count2.item()) == n_o2 and (m12b.cpu().numpy() == m_o2).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_nccl_two_ranks():
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_gpu_check.py")
+    n = min(torch.cuda.device_count(), 8)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", script],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "DIST_GPU_CHECK_OK" in res.stdout
