@@ -220,3 +220,173 @@ def make_keyframe_db(seed: int, n_kf: int, per_kf: int = 800, revisit_frac: floa
             src = int(rng.integers(0, k))
             db[k * per_kf:(k + 1) * per_kf] = flip_bits(rng, db[src * per_kf:(src + 1) * per_kf], flip_p)
     return db
+
+
+# ---- config 3: offline replay of many stereo frames (vectorised over frames) ---------------------
+
+@dataclass
+class Replay:
+    """Arenas + job tables of an n_frames replay: per frame one stereo matchGrid(points), one stereo
+    matchGrid(lines), one temporal match(points) and one temporal match(lines) against the previous
+    frame (app/plslam_dataset.cpp:114-172 -> stereoFrame.cpp:157,356 and stereoFrameHandler.cpp:168,191).
+    Descriptor arena row layout per frame: [left points | right points | left lines | right lines]."""
+    n_frames: int
+    arena: np.ndarray            # rows x 32 uint8
+    n_pts: np.ndarray            # per frame
+    n_lines: np.ndarray
+    off_pl: np.ndarray           # arena row offsets per frame
+    off_pr: np.ndarray
+    off_ll: np.ndarray
+    off_lr: np.ndarray
+    coords: np.ndarray           # int32 arena: per frame [xy of left points | xyxy of left lines]
+    off_cpts: np.ndarray
+    off_clines: np.ndarray
+    cell_start: np.ndarray       # int32 arena: per frame [points grid | lines grid], 3073 each
+    cell_items: np.ndarray
+    off_items_p: np.ndarray
+    off_items_l: np.ndarray
+    dirs2: np.ndarray            # float64 arena: per frame 2 * n_lines
+    off_dirs: np.ndarray
+    kp_l: np.ndarray             # float32 pixel coordinates (for the stereo gates), same order as arena
+    kp_r: np.ndarray
+    ln_l: np.ndarray
+    ln_r: np.ndarray
+    off_m_p: np.ndarray          # match-vector arena offsets
+    off_m_l: np.ndarray
+    n_m: int
+
+
+def make_replay(seed: int, n_frames: int, mean_pts: int = 600, sd_pts: int = 50, mean_lines: int = 200,
+                sd_lines: int = 25, flip_p: float = 0.08, outlier_frac: float = 0.25) -> Replay:
+    rng = np.random.default_rng(seed)
+    F = n_frames
+    n_pts = np.clip(np.rint(rng.normal(mean_pts, sd_pts, F)), 2, None).astype(np.int64)
+    n_lines = np.clip(np.rint(rng.normal(mean_lines, sd_lines, F)), 2, None).astype(np.int64)
+    per_frame = 2 * n_pts + 2 * n_lines
+    base = np.concatenate([[0], np.cumsum(per_frame)])
+    off_pl = base[:-1]
+    off_pr = off_pl + n_pts
+    off_ll = off_pr + n_pts
+    off_lr = off_ll + n_lines
+    arena = np.empty((int(base[-1]), 32), np.uint8)
+    P, Lm = int(n_pts.max()), int(n_lines.max())
+    b = 19.0
+
+    def evolve(prev, n, cap):
+        """Left descriptors of the next frame: noisy copies of the previous frame's, shuffled, with
+        outlier_frac replaced by fresh random rows (so the temporal matcher has true matches)."""
+        cur = rand_desc(rng, cap)
+        k = min(len(prev), n)
+        cur[:k] = flip_bits(rng, prev[:k], flip_p / 2)
+        out = rng.random(cap) < outlier_frac
+        cur[out] = rand_desc(rng, int(out.sum()))
+        return cur[rng.permutation(cap)][:n]
+
+    kp_l = np.empty((int(n_pts.sum()), 2), np.float32)
+    kp_r = np.empty_like(kp_l)
+    ln_l = np.empty((int(n_lines.sum()), 4), np.float32)
+    ln_r = np.empty_like(ln_l)
+    pbase = np.concatenate([[0], np.cumsum(n_pts)])
+    lbase = np.concatenate([[0], np.cumsum(n_lines)])
+    prev_p = rand_desc(rng, P)
+    prev_l = rand_desc(rng, Lm)
+    for f in range(F):
+        n, m = int(n_pts[f]), int(n_lines[f])
+        dl = evolve(prev_p, n, max(n, len(prev_p)))
+        prev_p = dl
+        dr = flip_bits(rng, dl, flip_p)
+        out = rng.random(n) < outlier_frac
+        dr[out] = rand_desc(rng, int(out.sum()))
+        perm = rng.permutation(n)
+        arena[off_pl[f]:off_pl[f] + n] = dl
+        arena[off_pr[f]:off_pr[f] + n] = dr[perm]
+        xl = rng.uniform(b, IMG_W - b, n); yl = rng.uniform(b, IMG_H - b, n)
+        xr = xl - rng.uniform(1.0, 100.0, n); yr = yl + rng.normal(0.0, 0.5, n)
+        xr[out] = rng.uniform(b, IMG_W - b, int(out.sum())); yr[out] = rng.uniform(b, IMG_H - b, int(out.sum()))
+        kp_l[pbase[f]:pbase[f + 1]] = np.stack([xl, yl], 1)
+        kp_r[pbase[f]:pbase[f + 1]] = np.stack([xr, yr], 1)[perm]
+
+        ll = evolve(prev_l, m, max(m, len(prev_l)))
+        prev_l = ll
+        lr = flip_bits(rng, ll, flip_p)
+        lout = rng.random(m) < outlier_frac
+        lr[lout] = rand_desc(rng, int(lout.sum()))
+        lperm = rng.permutation(m)
+        arena[off_ll[f]:off_ll[f] + m] = ll
+        arena[off_lr[f]:off_lr[f] + m] = lr[lperm]
+        sx = rng.uniform(b, IMG_W - b, m); sy = rng.uniform(b, IMG_H - b, m)
+        ang = rng.uniform(0, 2 * np.pi, m); length = rng.uniform(0.025 * IMG_H, 150.0, m)
+        ex = np.clip(sx + length * np.cos(ang), 1.0, IMG_W - 2.0); ey = np.clip(sy + length * np.sin(ang), 1.0, IMG_H - 2.0)
+        d = rng.uniform(1.0, 100.0, m)
+        r = np.stack([sx - d + rng.normal(0, 0.3, m), sy + rng.normal(0, 0.5, m),
+                      ex - d + rng.normal(0, 0.3, m), ey + rng.normal(0, 0.5, m)], 1)
+        no = int(lout.sum())
+        r[lout] = np.stack([rng.uniform(b, IMG_W - b, no), rng.uniform(b, IMG_H - b, no),
+                            rng.uniform(b, IMG_W - b, no), rng.uniform(b, IMG_H - b, no)], 1)
+        ln_l[lbase[f]:lbase[f + 1]] = np.stack([sx, sy, ex, ey], 1)
+        ln_r[lbase[f]:lbase[f + 1]] = r[lperm]
+
+    # query coordinates (stereoFrame.cpp:140-143 / :329-333): trunc(px * inv)
+    kl = kp_l.astype(np.float64)
+    xy = np.stack([np.trunc(kl[:, 0] * INV_W), np.trunc(kl[:, 1] * INV_H)], 1).astype(np.int32)
+    l64 = ln_l.astype(np.float64)
+    xyxy = np.stack([np.trunc(l64[:, 0] * INV_W), np.trunc(l64[:, 1] * INV_H),
+                     np.trunc(l64[:, 2] * INV_W), np.trunc(l64[:, 3] * INV_H)], 1).astype(np.int32)
+    ccount = 2 * n_pts + 4 * n_lines
+    cbase = np.concatenate([[0], np.cumsum(ccount)])
+    off_cpts = cbase[:-1]
+    off_clines = off_cpts + 2 * n_pts
+    coords = np.empty(int(cbase[-1]), np.int32)
+    for f in range(F):
+        coords[off_cpts[f]:off_cpts[f] + 2 * n_pts[f]] = xy[pbase[f]:pbase[f + 1]].ravel()
+        coords[off_clines[f]:off_clines[f] + 4 * n_lines[f]] = xyxy[lbase[f]:lbase[f + 1]].ravel()
+
+    # grids over the RIGHT features, all frames at once: key = frame * n_cells + x * rows + y
+    n_cells = G.GRID_ROWS * G.GRID_COLS
+    kr = kp_r.astype(np.float64)
+    cx = np.trunc(kr[:, 0] * INV_W).astype(np.int64); cy = np.trunc(kr[:, 1] * INV_H).astype(np.int64)
+    fid = np.repeat(np.arange(F), n_pts)
+    local = np.arange(len(kr)) - np.repeat(pbase[:-1], n_pts)
+    ok = (cx >= 0) & (cx < G.GRID_COLS) & (cy >= 0) & (cy < G.GRID_ROWS)
+    key_p = fid[ok] * n_cells + cx[ok] * G.GRID_ROWS + cy[ok]
+    order = np.argsort(key_p, kind="stable")
+    items_p = local[ok][order].astype(np.int32)
+    cnt_p = np.bincount(key_p, minlength=F * n_cells).reshape(F, n_cells)
+
+    r64 = ln_r.astype(np.float64)
+    ids, lcx, lcy = G.line_cells(r64[:, 0] * INV_W, r64[:, 1] * INV_H, r64[:, 2] * INV_W, r64[:, 3] * INV_H)
+    lfid = np.repeat(np.arange(F), n_lines)[ids]
+    llocal = ids - np.repeat(lbase[:-1], n_lines)[ids]
+    okl = (lcx >= 0) & (lcx < G.GRID_COLS) & (lcy >= 0) & (lcy < G.GRID_ROWS)
+    key_l = lfid[okl] * n_cells + lcx[okl] * G.GRID_ROWS + lcy[okl]
+    order_l = np.argsort(key_l, kind="stable")
+    items_l = llocal[okl][order_l].astype(np.int32)
+    cnt_l = np.bincount(key_l, minlength=F * n_cells).reshape(F, n_cells)
+
+    cell_start = np.zeros((F, 2, n_cells + 1), np.int32)
+    np.cumsum(cnt_p, axis=1, out=cell_start[:, 0, 1:])
+    np.cumsum(cnt_l, axis=1, out=cell_start[:, 1, 1:])
+    tot_p = cell_start[:, 0, -1].astype(np.int64); tot_l = cell_start[:, 1, -1].astype(np.int64)
+    ibase = np.concatenate([[0], np.cumsum(tot_p + tot_l)])
+    off_items_p = ibase[:-1]
+    off_items_l = off_items_p + tot_p
+    cell_items = np.empty(int(ibase[-1]), np.int32)
+    pstart = np.concatenate([[0], np.cumsum(tot_p)]); lstart = np.concatenate([[0], np.cumsum(tot_l)])
+    for f in range(F):
+        cell_items[off_items_p[f]:off_items_p[f] + tot_p[f]] = items_p[pstart[f]:pstart[f + 1]]
+        cell_items[off_items_l[f]:off_items_l[f] + tot_l[f]] = items_l[lstart[f]:lstart[f + 1]]
+
+    fr = ln_r
+    vx = (fr[:, 2] - fr[:, 0]).astype(np.float64) * INV_W
+    vy = (fr[:, 3] - fr[:, 1]).astype(np.float64) * INV_H
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mag = np.sqrt(vx * vx + vy * vy)
+        dirs2 = np.stack([vx / mag, vy / mag], 1).ravel()
+    off_dirs = 2 * lbase[:-1]
+
+    mbase = np.concatenate([[0], np.cumsum(n_pts + n_lines)])
+    off_m_p = mbase[:-1]
+    off_m_l = off_m_p + n_pts
+    return Replay(F, arena, n_pts, n_lines, off_pl, off_pr, off_ll, off_lr, coords, off_cpts, off_clines,
+                  cell_start.reshape(-1), cell_items, off_items_p, off_items_l, dirs2, off_dirs, kp_l, kp_r, ln_l, ln_r,
+                  off_m_p, off_m_l, int(mbase[-1]))
