@@ -39,8 +39,9 @@ METRIC = "descriptor_pairs_per_s"
 UNIT = "pairs/s"
 N_KF, PER_KF = 20000, 800
 POPC_PER_PAIR = 8                 # one pair = 8 POPC.32 + 8 LOP(xor) + 7 adds
-ALU_INSTR_PER_PAIR_CSA = 22.0     # counted from SASS of knn2_slice_kernel<128,true>
-ALU_INSTR_PER_PAIR_POPC8 = 16.0
+# ALU-pipe instructions per pair counted from the SASS main loop of knn2_slice_kernel<128, V>
+ALU_INSTR_PER_PAIR = {"csa4": 17.0, "csa5": 22.0, "popc8": 16.0}
+POPC_ISSUED_PER_PAIR = {"csa4": 4, "csa5": 5, "popc8": 8}
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -351,8 +352,10 @@ def run_b200(args):
         pairs_per_launch = float(n_q) * float(hi - lo)
         launch_ms = slice_ms / max(slice_n, 1)
         popc_equiv = pairs_per_launch * POPC_PER_PAIR / (launch_ms * 1e-3) * 1e-9  # Gop/s
-        variant_csa = os.environ.get("PLM_KNN_VARIANT", "csa5") != "popc8"
-        alu_per_pair = ALU_INSTR_PER_PAIR_CSA if variant_csa else ALU_INSTR_PER_PAIR_POPC8
+        variant = os.environ.get("PLM_KNN_VARIANT", "csa4")
+        variant = variant if variant in ALU_INSTR_PER_PAIR else "csa4"
+        variant_csa = variant != "popc8"
+        alu_per_pair = ALU_INSTR_PER_PAIR[variant]
         alu_rate = pairs_per_launch * alu_per_pair / (launch_ms * 1e-3) * 1e-9
         algo_bytes = 32.0 * (n_q + (hi - lo)) + 16.0 * n_q
         hbm_peak = 6535.4
@@ -373,7 +376,8 @@ def run_b200(args):
             "peak_source": "measured in this run (plm_measure_int_peaks, independent POPC chains)",
             "kernel_ms_per_launch": launch_ms, "launches_timed": slice_n,
             "share_of_step": slice_ms / dev_ms,
-            "note": ("the kernel uses a carry-save form (5 POPC + 14 LOP3 per pair), so it can exceed the 8-POPC "
+            "variant": variant, "popc_issued_per_pair": POPC_ISSUED_PER_PAIR[variant],
+            "note": ("the kernel uses a carry-save form (4 POPC + 16 LOP3 per pair), so it can exceed the 8-POPC "
                      "roofline; the pipe that actually binds is the ALU pipe below") if variant_csa else "plain 8-POPC form",
             "alu_pipe": {"unit": "Ginstr/s", "achieved": alu_rate, "peak": lop3_gops, "frac": alu_rate / lop3_gops,
                          "instr_per_pair": alu_per_pair},

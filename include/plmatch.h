@@ -248,7 +248,8 @@ void *plm_db_device_ptr(const plm_db *db);
 int plm_db_knn2(plm_db *db, const uint8_t *q, int nq, size_t step, uint64_t idx_base, uint64_t *top2);
 
 /* Tuning knobs (measurement only; results never depend on them):
- *   "knn_variant"  1 = carry-save 5-POPC Hamming (default), 0 = plain 8-POPC. */
+ *   "knn_variant"  -1 = automatic (default), 0 = plain 8-POPC Hamming, 1 = carry-save 5-POPC,
+ *                  2 = carry-save 4-POPC with blocked top-2 update. */
 int plm_set_option(const char *key, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

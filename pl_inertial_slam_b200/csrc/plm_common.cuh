@@ -47,6 +47,12 @@ __device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
     return r;
 }
 
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 __device__ __forceinline__ int hamming256_csa(const Desc &a, const uint4 &blo, const uint4 &bhi) {
     const uint32_t x0 = a.lo.x ^ blo.x, x1 = a.lo.y ^ blo.y, x2 = a.lo.z ^ blo.z, x3 = a.lo.w ^ blo.w;
     const uint32_t x4 = a.hi.x ^ bhi.x, x5 = a.hi.y ^ bhi.y, x6 = a.hi.z ^ bhi.z, x7 = a.hi.w ^ bhi.w;
@@ -56,6 +62,20 @@ __device__ __forceinline__ int hamming256_csa(const Desc &a, const uint4 &blo, c
     const int ones = __popc(sc) + __popc(x7);
     const int twos = __popc(ca) + __popc(cb) + __popc(cc);
     return ones + 2 * twos;
+}
+
+// Four-POPC carry-save form: a fourth full adder compresses the three "twos" words again, so the
+// distance is popc(ones0) + popc(ones1) + 2*popc(twos) + 4*popc(fours): 4 POPC + 16 LOP3 per pair.
+__device__ __forceinline__ int hamming256_csa4(const Desc &a, const uint4 &blo, const uint4 &bhi) {
+    const uint32_t x0 = a.lo.x ^ blo.x, x1 = a.lo.y ^ blo.y, x2 = a.lo.z ^ blo.z, x3 = a.lo.w ^ blo.w;
+    const uint32_t x4 = a.hi.x ^ bhi.x, x5 = a.hi.y ^ bhi.y, x6 = a.hi.z ^ bhi.z, x7 = a.hi.w ^ bhi.w;
+    const uint32_t sa = lop3_xor3(x0, x1, x2), ca = lop3_maj(x0, x1, x2);
+    const uint32_t sb = lop3_xor3(x3, x4, x5), cb = lop3_maj(x3, x4, x5);
+    const uint32_t sc = lop3_xor3(sa, sb, x6), cc = lop3_maj(sa, sb, x6);
+    const uint32_t se = lop3_xor3(ca, cb, cc), ce = lop3_maj(ca, cb, cc);
+    // weights folded with integer multiply-adds: IMAD issues on the FMA pipe, which is idle, while
+    // the ALU pipe (LOP3 / IADD3 / VIMNMX) is the one that binds
+    return static_cast<int>(imad(__popc(ce), 4u, imad(__popc(se), 2u, imad(__popc(sc), 1u, __popc(x7)))));
 }
 
 // Packed 64-bit key: (distance << 32) | global train index.  Unsigned min == (dist, idx) lexicographic.

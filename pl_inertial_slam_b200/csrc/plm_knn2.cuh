@@ -47,7 +47,14 @@ struct KnnTaskPair {
     KnnTask t[2];
 };
 
-template <int THREADS, bool CSA>
+// VARIANT 0: plain 8-POPC distance, per-pair top-2 update
+// VARIANT 1: 5-POPC carry-save distance, per-pair top-2 update (frame-sized train sets)
+// VARIANT 2: 4-POPC carry-save distance, rows handled 8 at a time: the eight distances only go
+//            through the packed-key top-2 update when their minimum beats the thread's current
+//            second-best distance.  Train rows are scanned in increasing index order, so a row that
+//            merely ties the second best can never displace it (its key is larger) and the strict
+//            test is exact.  For long slices the update path is almost never taken.
+template <int THREADS, int VARIANT>
 __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, int slice, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
     const int tid = threadIdx.x;
     const int n1 = t.n1;
@@ -86,12 +93,31 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
         const int rows = min(KNN_STAGE_ROWS, n_rows - st * KNN_STAGE_ROWS);
         const uint4 *buf = stage[st & 1];
         const uint32_t key_base = static_cast<uint32_t>(st * KNN_STAGE_ROWS);
+        if (VARIANT == 2) {
+            int j = 0;
+            for (; j + 8 <= rows; j += 8) {
+                int d[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d[u] = hamming256_csa4(a, buf[2 * (j + u)], buf[2 * (j + u) + 1]);
+                const int m = min(min(min(d[0], d[1]), min(d[2], d[3])), min(min(d[4], d[5]), min(d[6], d[7])));
+                if (m < static_cast<int>(b1 >> KNN_IDX_BITS)) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        top2_insert(b0, b1, (static_cast<uint32_t>(d[u]) << KNN_IDX_BITS) + (key_base + j + u));
+                }
+            }
+            for (; j < rows; ++j) {
+                const int d = hamming256_csa4(a, buf[2 * j], buf[2 * j + 1]);
+                top2_insert(b0, b1, (static_cast<uint32_t>(d) << KNN_IDX_BITS) + (key_base + j));
+            }
+        } else {
 #pragma unroll 8
-        for (int j = 0; j < rows; ++j) {
-            const uint4 blo = buf[2 * j], bhi = buf[2 * j + 1];
-            const int d = CSA ? hamming256_csa(a, blo, bhi) : hamming256(a, blo, bhi);
-            const uint32_t k = (static_cast<uint32_t>(d) << KNN_IDX_BITS) + (key_base + j);
-            top2_insert(b0, b1, k);
+            for (int j = 0; j < rows; ++j) {
+                const uint4 blo = buf[2 * j], bhi = buf[2 * j + 1];
+                const int d = (VARIANT == 1) ? hamming256_csa(a, blo, bhi) : hamming256(a, blo, bhi);
+                const uint32_t k = (static_cast<uint32_t>(d) << KNN_IDX_BITS) + (key_base + j);
+                top2_insert(b0, b1, k);
+            }
         }
         __syncthreads();
     }
@@ -102,21 +128,21 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
 }
 
 // grid = (max qblocks, max slices, n_tasks <= 2): both directions of StVO::match in one launch.
-template <int THREADS, bool CSA>
+template <int THREADS, int VARIANT>
 __global__ void __launch_bounds__(THREADS) knn2_slice_kernel(const KnnTaskPair tasks) {
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
     const KnnTask &t = tasks.t[blockIdx.z];
     if (static_cast<int>(blockIdx.x) * THREADS >= t.n1 || static_cast<int>(blockIdx.y) >= t.n_slices) return;
-    knn2_slice_body<THREADS, CSA>(t, blockIdx.x, blockIdx.y, stage);
+    knn2_slice_body<THREADS, VARIANT>(t, blockIdx.x, blockIdx.y, stage);
 }
 
 // Batched form: cta_map[cta] = (task, qblock, slice); tasks live in device memory.
-template <int THREADS, bool CSA>
+template <int THREADS, int VARIANT>
 __global__ void __launch_bounds__(THREADS) knn2_slice_list_kernel(const KnnTask *__restrict__ tasks, const int4 *__restrict__ cta_map) {
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
     const int4 m = __ldg(cta_map + blockIdx.x);
     const KnnTask t = tasks[m.x];
-    knn2_slice_body<THREADS, CSA>(t, m.y, m.z, stage);
+    knn2_slice_body<THREADS, VARIANT>(t, m.y, m.z, stage);
 }
 
 // Slice merge + (optionally) the matchNNR acceptance (stvo-pl/src/matching.cpp:53-58).

@@ -163,13 +163,18 @@ KnnPlan plan_knn(int n1, long long n2, int sm_count) {
     return p;
 }
 
-int g_use_csa = -1;
-bool use_csa() {
-    if (g_use_csa < 0) {
+// -1 = automatic (variant 2 for long slices, 1 otherwise); 0/1/2 force a variant (measurement only)
+int g_knn_variant = -2;
+int knn_variant_for(int slice_rows) {
+    if (g_knn_variant == -2) {
         const char *e = std::getenv("PLM_KNN_VARIANT");
-        g_use_csa = (e && std::strcmp(e, "popc8") == 0) ? 0 : 1;
+        g_knn_variant = -1;
+        if (e && std::strcmp(e, "popc8") == 0) g_knn_variant = 0;
+        if (e && std::strcmp(e, "csa5") == 0) g_knn_variant = 1;
+        if (e && std::strcmp(e, "csa4") == 0) g_knn_variant = 2;
     }
-    return g_use_csa != 0;
+    if (g_knn_variant >= 0) return g_knn_variant;
+    return slice_rows >= 2048 ? 2 : 1;
 }
 
 int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int threads) {
@@ -180,7 +185,9 @@ int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int
     }
     if (qb == 0 || sl == 0) return PLM_OK;
     const dim3 grid(qb, sl, n_tasks);
-    const bool csa = use_csa();
+    int min_rows = INT_MAX;
+    for (int i = 0; i < n_tasks; ++i) min_rows = std::min(min_rows, tp.t[i].slice_rows);
+    const int variant = knn_variant_for(min_rows);
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (ctx->profiling) {
         if (!ctx->prof_free.empty()) {
@@ -193,11 +200,13 @@ int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int
         CU_TRY(cudaEventRecord(ev.first, ctx->stream));
     }
     if (threads == 128) {
-        if (csa) plm::knn2_slice_kernel<128, true><<<grid, 128, 0, ctx->stream>>>(tp);
-        else plm::knn2_slice_kernel<128, false><<<grid, 128, 0, ctx->stream>>>(tp);
+        if (variant == 2) plm::knn2_slice_kernel<128, 2><<<grid, 128, 0, ctx->stream>>>(tp);
+        else if (variant == 1) plm::knn2_slice_kernel<128, 1><<<grid, 128, 0, ctx->stream>>>(tp);
+        else plm::knn2_slice_kernel<128, 0><<<grid, 128, 0, ctx->stream>>>(tp);
     } else {
-        if (csa) plm::knn2_slice_kernel<64, true><<<grid, 64, 0, ctx->stream>>>(tp);
-        else plm::knn2_slice_kernel<64, false><<<grid, 64, 0, ctx->stream>>>(tp);
+        if (variant == 2) plm::knn2_slice_kernel<64, 2><<<grid, 64, 0, ctx->stream>>>(tp);
+        else if (variant == 1) plm::knn2_slice_kernel<64, 1><<<grid, 64, 0, ctx->stream>>>(tp);
+        else plm::knn2_slice_kernel<64, 0><<<grid, 64, 0, ctx->stream>>>(tp);
     }
     ctx->launches++;
     CU_TRY(cudaGetLastError());
@@ -232,7 +241,7 @@ int check_desc(const uint8_t *d, int n, size_t step) {
 PLM_API int plm_set_option(const char *key, int value) {
     if (!key) return fail(PLM_E_INVALID, "null key");
     if (std::strcmp(key, "knn_variant") == 0) {
-        g_use_csa = value ? 1 : 0;
+        g_knn_variant = (value >= 0 && value <= 2) ? value : -1;
         return PLM_OK;
     }
     return fail(PLM_E_INVALID, std::string("unknown option ") + key);
@@ -1475,10 +1484,10 @@ PLM_API int plm_batch_run(plm_batch *b) {
         if (b->n_slice_ctas == 0) return PLM_OK;
         const plm::KnnTask *tasks = reinterpret_cast<const plm::KnnTask *>(D + b->o_tasks);
         if (b->best_lr && b->m21_bytes) CU_TRY(cudaMemsetAsync(D + b->o_m21, 0xFF, b->m21_bytes, s));
-        if (use_csa())
-            plm::knn2_slice_list_kernel<BATCH_THREADS, true><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
+        if (knn_variant_for(0) == 0)
+            plm::knn2_slice_list_kernel<BATCH_THREADS, 0><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
         else
-            plm::knn2_slice_list_kernel<BATCH_THREADS, false><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
+            plm::knn2_slice_list_kernel<BATCH_THREADS, 1><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
         ctx->launches++;
         CU_TRY(cudaGetLastError());
         plm::knn2_merge_list_kernel<<<b->n_merge_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int2 *>(D + b->o_merge_map), b->nnr, 1);
