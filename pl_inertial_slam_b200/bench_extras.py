@@ -170,8 +170,70 @@ def replay_cpu_baseline(n_frames: int, seconds: float = 8.0) -> dict:
                       "(popcount-SWAR distance, scalar), all stages of the replay"}
 
 
+def map_to_frame(ctx) -> dict:
+    """Config 4 on one GPU: a 200 000-point / 50 000-line local map (desc1, with projected cell
+    coordinates) against one frame (600 / 200 features): matchGrid with a +-3 window, then the forced
+    brute-force match() fallback on the same vector.  Device-resident timings (CUDA events) plus the
+    host-buffer call."""
+    import torch
+    from .database import GridFrame, ShardedMap
+    from . import grid as G
+    sp = synth.make_stereo_pair(synth.SEED0 + 4)
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for name, n_map, is_lines in (("points_200k_x_600", 200_000, False), ("lines_50k_x_200", 50_000, True)):
+        rng = np.random.default_rng(synth.SEED0 + 40 + int(is_lines))
+        if not is_lines:
+            d1, xy = synth.make_map_points(synth.SEED0 + 4, n_map, sp)
+            d2 = sp.pdesc_l
+            c = sp.kp_l.astype(np.float64)
+            cs, ci = G.csr_from_points(c[:, 0] * synth.INV_W, c[:, 1] * synth.INV_H)
+            dirs = None
+            coords = xy
+        else:
+            d1 = synth.rand_desc(rng, n_map)
+            s = np.stack([rng.integers(-2, 66, n_map), rng.integers(-2, 50, n_map)], 1)
+            coords = np.concatenate([s, s + rng.integers(-8, 9, (n_map, 2))], 1).astype(np.int32)
+            d2 = sp.ldesc_l
+            from .drivers import line_grid
+            cs, ci, dirs = line_grid(sp.ln_l, synth.INV_W, synth.INV_H)
+        frame = GridFrame(torch.from_numpy(d2).to(dev), torch.from_numpy(cs).to(dev), torch.from_numpy(ci).to(dev),
+                          G.GRID_ROWS, G.GRID_COLS, torch.from_numpy(dirs).to(dev) if dirs is not None else None)
+        from .database import DeviceOps
+        ops = DeviceOps(dev.index)
+        smap = ShardedMap(n_map, torch.from_numpy(d1).to(dev), torch.from_numpy(coords).to(dev), ops=ops)
+        win = np.array([3, 3, 3, 3], np.int32)
+
+        def timed(fn, reps=10):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                r = fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps, r
+
+        g_ms, (cnt, m12) = timed(lambda: smap.match_grid(frame, win, 0.9, 0.75, True))
+        f_ms, (cnt2, _) = timed(lambda: smap.match(frame.d2, 0.9, True, m12_inout=m12))
+        grid_arg = (cs, ci, G.GRID_ROWS, G.GRID_COLS)
+        M.Config.minRatio12P = 0.9
+        if dirs is None:
+            host_ms = _median_ms(lambda: M.matchGrid(coords, d1, grid_arg, d2, win, np.full(n_map, -1, np.int32), ctx=ctx), reps=8, warm=2)
+        else:
+            host_ms = _median_ms(lambda: M.matchGrid(coords, d1, grid_arg, d2, dirs, win, np.full(n_map, -1, np.int32), ctx=ctx), reps=8, warm=2)
+        pairs = float(n_map) * len(d2)
+        out[name] = {"matchGrid_device_ms": g_ms, "matchGrid_host_call_ms": host_ms, "matchGrid_matches": int(cnt.item()),
+                     "match_fallback_device_ms": f_ms, "match_fallback_unique_pairs_per_s": pairs / (f_ms * 1e-3),
+                     "match_fallback_count": int(cnt2.item())}
+    return out
+
+
 def run(ctx, args) -> dict:
     out = {"frame_latency": frame_latency(ctx)}
+    try:
+        out["map_to_frame"] = map_to_frame(ctx)
+    except Exception as e:  # noqa: BLE001
+        out["map_to_frame"] = {"error": repr(e)}
     n = int(os.environ.get("PLM_REPLAY_FRAMES", "10000"))
     out["replay"] = replay_throughput(ctx, n)
     if not args.no_cpu_baseline:
