@@ -249,7 +249,9 @@ int plm_db_knn2(plm_db *db, const uint8_t *q, int nq, size_t step, uint64_t idx_
 
 /* Tuning knobs (measurement only; results never depend on them):
  *   "knn_variant"  -1 = automatic (default), 0 = plain 8-POPC Hamming, 1 = carry-save 5-POPC,
- *                  2 = carry-save 4-POPC with blocked top-2 update. */
+ *                  2 = carry-save 4-POPC with blocked top-2 update.
+ *   "grid_cluster" 1 = single matchGrid calls run on an 8-CTA thread-block cluster (default),
+ *                  0 = on one CTA. */
 int plm_set_option(const char *key, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

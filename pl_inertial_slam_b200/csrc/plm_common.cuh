@@ -20,6 +20,14 @@ __device__ __forceinline__ Desc load_desc(const uint4 *__restrict__ base, long l
     return d;
 }
 
+// Same through a generic pointer (the row may live in shared memory).
+__device__ __forceinline__ Desc load_desc_any(const uint4 *base, long long row) {
+    Desc d;
+    d.lo = base[2 * row];
+    d.hi = base[2 * row + 1];
+    return d;
+}
+
 // StVO::distance (stvo-pl/src/matching.cpp:93-109): 8 x (xor, popcount).  LOP3 + POPC + IADD3.
 __device__ __forceinline__ int hamming256(const Desc &a, const uint4 &blo, const uint4 &bhi) {
     int s0 = __popc(a.lo.x ^ blo.x) + __popc(a.lo.y ^ blo.y) + __popc(a.lo.z ^ blo.z);

@@ -18,9 +18,13 @@
 // Distances are recomputed in phase C instead of being stored: a pair list would need a dynamic
 // allocation, and 8 POPC are cheaper than the round trip.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "plm_common.cuh"
 
 namespace plm {
+
+namespace cg = cooperative_groups;
 
 struct GridJob {
     const int32_t *coords;     // n1 x 2 (points) or n1 x 4 (lines), grid-cell coordinates
@@ -34,12 +38,17 @@ struct GridJob {
     int32_t n1, n2, is_lines, pad_;
     int32_t win[4];
     long long i1_base;         // global row index of local row 0 (row-sharded map; 0 otherwise)
+    int32_t q_row_base, pad2_; // d1 / coords point at row q_row_base (staged per-CTA row windows)
 };
 
 struct GridParams {
     int grid_rows, grid_cols;
     int best_lr;
     int rows_per_warp;          // chunked launch only; the fused kernel derives it from n1
+    // fused kernel: when staged != 0 every input of the job is first copied into shared memory with
+    // coalesced 128-bit loads (capacities below, in elements), so the per-row dependent accesses
+    // (coords -> cell_start -> cell_items -> descriptor / threshold) cost shared-memory latency
+    int staged, cap_n1, cap_items, cap_pad_;
     double ratio, line_sim_th;
     // chunked (multi-CTA) launch only:
     uint16_t *cta_min;          // [n_cta][n2] per-CTA column minima, turned into thresholds in place
@@ -84,8 +93,8 @@ __device__ __forceinline__ void for_each_candidate(const RowWindows &rw, const G
         if (t < rw.n_ranges) {
             const int k = (t < rw.nx[0]) ? 0 : 1;
             const int x = rw.min_x[k] + (k ? t - rw.nx[0] : t);
-            lo = __ldg(job.cell_start + x * grid_rows + rw.min_y[k]);
-            hi = __ldg(job.cell_start + x * grid_rows + rw.max_y[k]);
+            lo = job.cell_start[x * grid_rows + rw.min_y[k]];
+            hi = job.cell_start[x * grid_rows + rw.max_y[k]];
         }
         const int cnt = max(hi - lo, 0);
         int incl = cnt;
@@ -107,7 +116,7 @@ __device__ __forceinline__ void for_each_candidate(const RowWindows &rw, const G
             const int lo_r = __shfl_sync(0xFFFFFFFFu, lo, r);
             const int ex_r = __shfl_sync(0xFFFFFFFFu, excl, r);
             int i2 = -1;
-            if (p < tot) i2 = __ldg(job.cell_items + lo_r + (p - ex_r));
+            if (p < tot) i2 = job.cell_items[lo_r + (p - ex_r)];
             body(i2);
         }
     }
@@ -121,17 +130,18 @@ struct RowQuery {
 
 __device__ __forceinline__ RowQuery load_row(const GridJob &job, const GridParams &gp, int i1) {
     RowQuery r;
-    r.q = load_desc(job.d1, i1);
+    r.q = load_desc_any(job.d1, i1 - job.q_row_base);
     r.vx = r.vy = 0.0;
     if (!job.is_lines) {
-        const int2 c = make_int2(__ldg(job.coords + 2 * static_cast<long long>(i1)), __ldg(job.coords + 2 * static_cast<long long>(i1) + 1));
+        const long long ci = i1 - job.q_row_base;
+        const int2 c = make_int2(job.coords[2 * ci], job.coords[2 * ci + 1]);
         r.rw.n_win = 1;
         clamp_window(r.rw, 0, c.x, c.y, job.win, gp.grid_rows, gp.grid_cols);
         r.rw.nx[1] = 0;
         r.rw.min_x[1] = r.rw.min_y[1] = r.rw.max_y[1] = 0;
     } else {
-        const int32_t *cp = job.coords + 4 * static_cast<long long>(i1);
-        const int4 c = make_int4(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3));
+        const int32_t *cp = job.coords + 4 * static_cast<long long>(i1 - job.q_row_base);
+        const int4 c = make_int4(cp[0], cp[1], cp[2], cp[3]);
         r.rw.n_win = 2;
         clamp_window(r.rw, 0, c.x, c.y, job.win, gp.grid_rows, gp.grid_cols);
         clamp_window(r.rw, 1, c.z, c.w, job.win, gp.grid_rows, gp.grid_cols);
@@ -150,7 +160,7 @@ __device__ __forceinline__ RowQuery load_row(const GridJob &job, const GridParam
 __device__ __forceinline__ bool candidate_ok(const GridJob &job, const GridParams &gp, const RowQuery &r, int i2) {
     if (i2 < 0 || i2 >= job.n2) return false;
     if (job.is_lines) {
-        const double2 d = make_double2(__ldg(job.dirs2 + 2 * static_cast<long long>(i2)), __ldg(job.dirs2 + 2 * static_cast<long long>(i2) + 1));
+        const double2 d = make_double2(job.dirs2[2 * static_cast<long long>(i2)], job.dirs2[2 * static_cast<long long>(i2) + 1]);
         const double dp = __dadd_rn(__dmul_rn(r.vx, d.x), __dmul_rn(r.vy, d.y));
         if (fabs(dp) < gp.line_sim_th) return false;
     }
@@ -164,7 +174,7 @@ __device__ __forceinline__ void chunk_minima(const GridJob &job, const GridParam
         const RowQuery r = load_row(job, gp, i1);
         for_each_candidate(r.rw, job, gp.grid_rows, lane, [&](int i2) {
             if (candidate_ok(job, gp, r, i2)) {
-                const int d = hamming256(r.q, load_desc(job.d2, i2));
+                const int d = hamming256(r.q, load_desc_any(job.d2, i2));
                 // lanes holding the same i2 (a line listed in several cells) write the same value
                 if (d < wmin[i2]) wmin[i2] = static_cast<uint16_t>(d);
             }
@@ -191,7 +201,7 @@ __device__ __forceinline__ int chunk_match(const GridJob &job, const GridParams 
             const unsigned peers = __match_any_sync(0xFFFFFFFFu, ok ? i2 : -1 - lane);
             ok = ok && (lane == __ffs(peers) - 1);
             if (ok) {
-                const int d = hamming256(r.q, load_desc(job.d2, i2));
+                const int d = hamming256(r.q, load_desc_any(job.d2, i2));
                 bool live;
                 if (gp.best_lr) {
                     // ... and across batches: a repeat no longer beats the threshold it set itself
@@ -225,17 +235,72 @@ __device__ __forceinline__ int chunk_match(const GridJob &job, const GridParams 
     return accepted;
 }
 
+// Cooperative copy of n_bytes (any alignment of the byte count; src and dst 16-byte aligned when
+// n_bytes >= 16) into shared memory.
+__device__ __forceinline__ void stage_bytes(unsigned char *dst, const void *src, size_t n_bytes) {
+    const size_t n16 = n_bytes >> 4;
+    const uint4 *s4 = static_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    if ((reinterpret_cast<size_t>(src) & 15) == 0) {
+        for (size_t i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        const unsigned char *sb = static_cast<const unsigned char *>(src);
+        for (size_t i = (n16 << 4) + threadIdx.x; i < n_bytes; i += blockDim.x) dst[i] = sb[i];
+    } else {
+        const uint32_t *s1 = static_cast<const uint32_t *>(src); // every arena is at least 4-byte aligned
+        uint32_t *d1 = reinterpret_cast<uint32_t *>(dst);
+        for (size_t i = threadIdx.x; i < (n_bytes >> 2); i += blockDim.x) d1[i] = __ldg(s1 + i);
+    }
+}
+
+__host__ __device__ inline size_t grid_align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+// Shared-memory footprint of the fused kernel (also used by the host to decide whether to stage).
+__host__ __device__ inline size_t grid_fused_smem(int warps, int n2_max, int staged, int cap_n1, int cap_items,
+                                                  int n_cells, bool any_lines) {
+    size_t b = grid_align16(static_cast<size_t>(warps) * n2_max * 2) + grid_align16(static_cast<size_t>(n2_max) * 4);
+    if (staged) {
+        b += grid_align16(static_cast<size_t>(n_cells + 1) * 4) + grid_align16(static_cast<size_t>(cap_items) * 4);
+        b += static_cast<size_t>(n2_max) * 32 + static_cast<size_t>(cap_n1) * 32;
+        b += grid_align16(static_cast<size_t>(cap_n1) * 16);
+        if (any_lines) b += static_cast<size_t>(n2_max) * 16;
+    }
+    return b;
+}
+
 // ---- fused single-CTA kernel: one job per CTA (blockIdx.x), everything in one launch --------------
-// dynamic smem: uint16 wmin[W][n2_max] | uint32 m21key[n2_max]
+// dynamic smem: uint16 wmin[W][n2_max] | uint32 m21key[n2_max] | staged copies of the job's inputs
 __global__ void __launch_bounds__(1024)
 grid_match_fused_kernel(const GridJob *__restrict__ jobs, GridParams gp, int n2_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_count;
-    const GridJob job = jobs[blockIdx.x];
+    GridJob job = jobs[blockIdx.x];
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint16_t *wmin = reinterpret_cast<uint16_t *>(smem_raw);
-    uint32_t *m21key = reinterpret_cast<uint32_t *>(smem_raw + ((static_cast<size_t>(W) * n2_max * 2 + 15) & ~size_t(15)));
+    uint32_t *m21key = reinterpret_cast<uint32_t *>(smem_raw + grid_align16(static_cast<size_t>(W) * n2_max * 2));
     const int n1 = job.n1, n2 = job.n2;
+    if (gp.staged) {
+        const int n_cells = gp.grid_rows * gp.grid_cols;
+        unsigned char *p = reinterpret_cast<unsigned char *>(m21key) + grid_align16(static_cast<size_t>(n2_max) * 4);
+        const int n_items = job.cell_start[n_cells];
+        unsigned char *s_cs = p; p += grid_align16(static_cast<size_t>(n_cells + 1) * 4);
+        unsigned char *s_ci = p; p += grid_align16(static_cast<size_t>(gp.cap_items) * 4);
+        unsigned char *s_d2 = p; p += static_cast<size_t>(n2_max) * 32;
+        unsigned char *s_d1 = p; p += static_cast<size_t>(gp.cap_n1) * 32;
+        unsigned char *s_co = p; p += grid_align16(static_cast<size_t>(gp.cap_n1) * 16);
+        unsigned char *s_dir = p;
+        stage_bytes(s_cs, job.cell_start, static_cast<size_t>(n_cells + 1) * 4);
+        stage_bytes(s_ci, job.cell_items, static_cast<size_t>(n_items) * 4);
+        stage_bytes(s_d2, job.d2, static_cast<size_t>(n2) * 32);
+        stage_bytes(s_d1, job.d1, static_cast<size_t>(n1) * 32);
+        stage_bytes(s_co, job.coords, static_cast<size_t>(n1) * (job.is_lines ? 16 : 8));
+        if (job.is_lines) stage_bytes(s_dir, job.dirs2, static_cast<size_t>(n2) * 16);
+        job.cell_start = reinterpret_cast<const int32_t *>(s_cs);
+        job.cell_items = reinterpret_cast<const int32_t *>(s_ci);
+        job.d2 = reinterpret_cast<const uint4 *>(s_d2);
+        job.d1 = reinterpret_cast<const uint4 *>(s_d1);
+        job.coords = reinterpret_cast<const int32_t *>(s_co);
+        if (job.is_lines) job.dirs2 = reinterpret_cast<const double *>(s_dir);
+    }
     if (threadIdx.x == 0) s_count = 0;
     for (int i = threadIdx.x; i < W * n2_max; i += blockDim.x) wmin[i] = D_INF;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) m21key[i] = KEY32_ABSENT;
@@ -284,6 +349,132 @@ grid_match_fused_kernel(const GridJob *__restrict__ jobs, GridParams gp, int n2_
         __syncthreads();
     }
     if (threadIdx.x == 0) *job.count = s_count;
+}
+
+// ---- cluster kernel: ONE frame-sized job spread over a thread-block cluster of CLUSTER CTAs -----------
+// A single call must not sit on one SM of 148: the chunks (warps) of the job are dealt to the CTAs of a
+// cluster in row order, every CTA keeps its chunk arrays in its own shared memory, and the two places
+// where chunks talk to each other go through distributed shared memory:
+//   * threshold seeding: CTA r reads the per-CTA column minima of the CTAs r' < r (their rows come first);
+//   * mutual check: the best live pair of a column is the minimum over the CTAs' m21key arrays.
+// grid = CLUSTER * n_jobs CTAs; job = blockIdx.x / CLUSTER.  *job.count must be zero on entry.
+// dynamic smem per CTA: uint16 wmin[W][n2_max] | uint16 ctamin[n2_max] | uint32 m21key[n2_max] | staged
+__host__ __device__ inline size_t grid_cluster_smem(int warps, int n2_max, int staged, int rows_per_cta, int cap_items,
+                                                    int n_cells, bool any_lines) {
+    size_t b = grid_align16(static_cast<size_t>(warps) * n2_max * 2) + grid_align16(static_cast<size_t>(n2_max) * 2) +
+               grid_align16(static_cast<size_t>(n2_max) * 4);
+    if (staged) {
+        b += grid_align16(static_cast<size_t>(n_cells + 1) * 4) + grid_align16(static_cast<size_t>(cap_items) * 4);
+        b += static_cast<size_t>(n2_max) * 32 + static_cast<size_t>(rows_per_cta) * 32;
+        b += grid_align16(static_cast<size_t>(rows_per_cta) * 16);
+        if (any_lines) b += static_cast<size_t>(n2_max) * 16;
+    }
+    return b;
+}
+
+template <int CLUSTER>
+__global__ void __launch_bounds__(512)
+grid_match_cluster_kernel(const GridJob *__restrict__ jobs, GridParams gp, int n2_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(cluster.block_rank());
+    GridJob job = jobs[blockIdx.x / CLUSTER];
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n1 = job.n1, n2 = job.n2;
+    uint16_t *wmin = reinterpret_cast<uint16_t *>(smem_raw);
+    uint16_t *ctamin = reinterpret_cast<uint16_t *>(smem_raw + grid_align16(static_cast<size_t>(W) * n2_max * 2));
+    uint32_t *m21key = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(ctamin) + grid_align16(static_cast<size_t>(n2_max) * 2));
+
+    // chunk g = rank * W + warp owns rows [g * rpw, (g + 1) * rpw): CTA order == row order
+    const int rpw = (n1 + CLUSTER * W - 1) / (CLUSTER * W);
+    const int cta_row0 = min(n1, rank * W * rpw), cta_row1 = min(n1, cta_row0 + W * rpw);
+    const int row0 = min(n1, cta_row0 + warp * rpw), row1 = min(n1, row0 + rpw);
+
+    for (int i = threadIdx.x; i < W * n2_max; i += blockDim.x) wmin[i] = D_INF;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) m21key[i] = KEY32_ABSENT;
+    if (gp.staged) {
+        const int n_cells = gp.grid_rows * gp.grid_cols;
+        unsigned char *p = reinterpret_cast<unsigned char *>(m21key) + grid_align16(static_cast<size_t>(n2_max) * 4);
+        const int n_items = job.cell_start[n_cells];
+        unsigned char *s_cs = p; p += grid_align16(static_cast<size_t>(n_cells + 1) * 4);
+        unsigned char *s_ci = p; p += grid_align16(static_cast<size_t>(gp.cap_items) * 4);
+        unsigned char *s_d2 = p; p += static_cast<size_t>(n2_max) * 32;
+        unsigned char *s_d1 = p; p += static_cast<size_t>(gp.cap_n1) * 32;
+        unsigned char *s_co = p; p += grid_align16(static_cast<size_t>(gp.cap_n1) * 16);
+        unsigned char *s_dir = p;
+        const int cpq = job.is_lines ? 4 : 2;
+        stage_bytes(s_cs, job.cell_start, static_cast<size_t>(n_cells + 1) * 4);
+        stage_bytes(s_ci, job.cell_items, static_cast<size_t>(n_items) * 4);
+        stage_bytes(s_d2, job.d2, static_cast<size_t>(n2) * 32);
+        stage_bytes(s_d1, job.d1 + 2 * static_cast<size_t>(cta_row0), static_cast<size_t>(cta_row1 - cta_row0) * 32);
+        stage_bytes(s_co, job.coords + static_cast<size_t>(cta_row0) * cpq, static_cast<size_t>(cta_row1 - cta_row0) * cpq * 4);
+        if (job.is_lines) stage_bytes(s_dir, job.dirs2, static_cast<size_t>(n2) * 16);
+        job.cell_start = reinterpret_cast<const int32_t *>(s_cs);
+        job.cell_items = reinterpret_cast<const int32_t *>(s_ci);
+        job.d2 = reinterpret_cast<const uint4 *>(s_d2);
+        job.d1 = reinterpret_cast<const uint4 *>(s_d1);
+        job.coords = reinterpret_cast<const int32_t *>(s_co);
+        job.q_row_base = cta_row0;
+        if (job.is_lines) job.dirs2 = reinterpret_cast<const double *>(s_dir);
+    }
+    __syncthreads();
+
+    uint16_t *mine = wmin + static_cast<size_t>(warp) * n2_max;
+    if (gp.best_lr) {
+        chunk_minima(job, gp, row0, row1, mine, lane);
+        __syncthreads();
+        // exclusive prefix-min over this CTA's chunks; the CTA total goes to ctamin for the higher ranks
+        for (int i2 = threadIdx.x; i2 < n2; i2 += blockDim.x) {
+            uint16_t run = D_INF;
+            for (int w = 0; w < W; ++w) {
+                const uint16_t t = wmin[static_cast<size_t>(w) * n2_max + i2];
+                wmin[static_cast<size_t>(w) * n2_max + i2] = run;
+                run = min(run, t);
+            }
+            ctamin[i2] = run;
+        }
+        cluster.sync();
+        if (rank > 0) {
+            for (int i2 = threadIdx.x; i2 < n2; i2 += blockDim.x) {
+                uint16_t seed = D_INF;
+                for (int r = 0; r < rank; ++r) seed = min(seed, cluster.map_shared_rank(ctamin, r)[i2]);
+                if (seed != D_INF)
+                    for (int w = 0; w < W; ++w) {
+                        uint16_t &t = wmin[static_cast<size_t>(w) * n2_max + i2];
+                        t = min(t, seed);
+                    }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int acc = chunk_match(job, gp, row0, row1, mine, lane, [&](int i2, int d, int i1) {
+        atomicMin(&m21key[i2], (static_cast<uint32_t>(d) << GRID_KEY_BITS) | static_cast<uint32_t>(i1));
+    });
+    if (lane == 0 && acc) atomicAdd(job.count, acc);
+
+    if (gp.best_lr) {
+        cluster.sync();
+        // mutual check (matching.cpp:166-174) over this CTA's rows, stale entries included
+        int culled = 0;
+        for (int i1 = cta_row0 + threadIdx.x; i1 < cta_row1; i1 += blockDim.x) {
+            const int32_t i2 = job.m12[i1];
+            if (i2 >= 0) {
+                uint32_t k = KEY32_ABSENT;
+                if (i2 < n2)
+                    for (int r = 0; r < CLUSTER; ++r) k = min(k, cluster.map_shared_rank(m21key, r)[i2]);
+                const int back = (k == KEY32_ABSENT) ? -1 : static_cast<int>(k & ((1u << GRID_KEY_BITS) - 1));
+                if (back != i1) {
+                    job.m12[i1] = -1;
+                    ++culled;
+                }
+            }
+        }
+        const unsigned msk = __ballot_sync(0xFFFFFFFFu, culled != 0);
+        (void)msk;
+        if (culled) atomicSub(job.count, culled);
+    }
+    cluster.sync(); // nobody leaves while its shared memory may still be read
 }
 
 // ---- chunked launch for map-sized jobs: CTA c owns rows [c*W*rpw, (c+1)*W*rpw) --------------------

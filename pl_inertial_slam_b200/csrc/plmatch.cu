@@ -65,6 +65,7 @@ struct plm_ctx {
     size_t h_cap = 0;
     uint64_t launches = 0;
     bool fused_attr_set = false;
+    bool cluster_attr_set = false;
     size_t chunked_attr[2] = {0, 0};
     // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
     bool profiling = false;
@@ -163,6 +164,8 @@ KnnPlan plan_knn(int n1, long long n2, int sm_count) {
     return p;
 }
 
+int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
+
 // -1 = automatic (variant 2 for long slices, 1 otherwise); 0/1/2 force a variant (measurement only)
 int g_knn_variant = -2;
 int knn_variant_for(int slice_rows) {
@@ -242,6 +245,10 @@ PLM_API int plm_set_option(const char *key, int value) {
     if (!key) return fail(PLM_E_INVALID, "null key");
     if (std::strcmp(key, "knn_variant") == 0) {
         g_knn_variant = (value >= 0 && value <= 2) ? value : -1;
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "grid_cluster") == 0) {
+        g_grid_cluster = value ? 1 : 0;
         return PLM_OK;
     }
     return fail(PLM_E_INVALID, std::string("unknown option ") + key);
@@ -617,17 +624,22 @@ constexpr int GRID_FUSED_MAX_ROWS = 4096;
 
 struct FusedShape {
     int warps;
+    int staged;
     size_t smem;
 };
 
-size_t fused_smem(int warps, int n2_max) { return align_up(size_t(warps) * n2_max * 2, 16) + size_t(n2_max) * 4; }
-
-// Number of warps of the fused kernel: as many chunks as shared memory allows, at least ~4 rows each.
-FusedShape fused_shape(const plm_ctx *ctx, int n1_max, int n2_max) {
-    const size_t budget = std::min<size_t>(ctx->smem_optin - 2048, 200 * 1024);
-    int w = std::min(32, std::max(1, (n1_max + 3) / 4));
-    while (w > 1 && fused_smem(w, n2_max) > budget) --w;
-    return {w, fused_smem(w, n2_max)};
+// Shape of the fused kernel: stage the job's inputs in shared memory when they fit next to at least
+// 8 chunk arrays, then as many warps (chunks) as the remaining shared memory allows, >= ~4 rows each.
+FusedShape fused_shape(const plm_ctx *ctx, int n1_max, int n2_max, int items_max, int n_cells, bool any_lines) {
+    const size_t budget = ctx->smem_optin - 2048;
+    const int want = std::min(32, std::max(1, (n1_max + 3) / 4));
+    for (int staged = 1; staged >= 0; --staged) {
+        int w = want;
+        while (w > 1 && plm::grid_fused_smem(w, n2_max, staged, n1_max, items_max, n_cells, any_lines) > budget) --w;
+        const size_t need = plm::grid_fused_smem(w, n2_max, staged, n1_max, items_max, n_cells, any_lines);
+        if (need <= budget && (!staged || w >= std::min(want, 8))) return {w, staged, need};
+    }
+    return {1, 0, plm::grid_fused_smem(1, n2_max, 0, n1_max, items_max, n_cells, any_lines)};
 }
 
 int validate_grid(const int32_t *cell_start, const int32_t *cell_items, int grid_rows, int grid_cols, int *n_items) {
@@ -643,10 +655,13 @@ int validate_grid(const int32_t *cell_start, const int32_t *cell_items, int grid
     return PLM_OK;
 }
 
-int launch_grid_fused(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, const plm::GridParams &gp, int n1_max,
-                      int n2_max) {
-    const FusedShape fs = fused_shape(ctx, n1_max, n2_max);
+int launch_grid_fused(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, plm::GridParams gp, int n1_max,
+                      int n2_max, int items_max, bool any_lines) {
+    const FusedShape fs = fused_shape(ctx, n1_max, n2_max, items_max, gp.grid_rows * gp.grid_cols, any_lines);
     if (fs.smem > ctx->smem_optin - 2048) return fail(PLM_E_UNSUPPORTED, "matchGrid: train set too large for shared memory");
+    gp.staged = fs.staged;
+    gp.cap_n1 = n1_max;
+    gp.cap_items = items_max;
     if (!ctx->fused_attr_set) {
         CU_TRY(cudaFuncSetAttribute(plm::grid_match_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(ctx->smem_optin - 2048)));
@@ -655,6 +670,51 @@ int launch_grid_fused(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, co
     plm::grid_match_fused_kernel<<<n_jobs, fs.warps * 32, fs.smem, ctx->stream>>>(jobs_dev, gp, n2_max);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// One frame-sized job on a cluster of 8 CTAs (8 SMs) -- the single-call path.
+constexpr int GRID_CLUSTER = 8;
+
+int launch_grid_cluster(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, plm::GridParams gp, int n1_max, int n2_max,
+                        int items_max, bool any_lines) {
+    const size_t budget = ctx->smem_optin - 2048;
+    const int n_cells = gp.grid_rows * gp.grid_cols;
+    int warps = 16, staged = 1;
+    size_t smem = 0;
+    for (;;) {
+        const int rpw = (n1_max + GRID_CLUSTER * warps - 1) / (GRID_CLUSTER * warps);
+        smem = plm::grid_cluster_smem(warps, n2_max, staged, warps * rpw, items_max, n_cells, any_lines);
+        if (smem <= budget) {
+            gp.cap_n1 = warps * rpw;
+            break;
+        }
+        if (staged) staged = 0;
+        else if (warps > 1) warps >>= 1;
+        else return fail(PLM_E_UNSUPPORTED, "matchGrid: train set too large for shared memory");
+    }
+    gp.staged = staged;
+    gp.cap_items = items_max;
+    if (!ctx->cluster_attr_set) {
+        CU_TRY(cudaFuncSetAttribute(plm::grid_match_cluster_kernel<GRID_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(ctx->smem_optin - 2048)));
+        ctx->cluster_attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(GRID_CLUSTER * n_jobs, 1, 1);
+    cfg.blockDim = dim3(warps * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GRID_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU_TRY(cudaLaunchKernelEx(&cfg, plm::grid_match_cluster_kernel<GRID_CLUSTER>, jobs_dev, gp, n2_max));
+    ctx->launches++;
     return PLM_OK;
 }
 
@@ -783,8 +843,11 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     gp.best_lr = best_lr ? 1 : 0;
     gp.ratio = ratio;
     gp.line_sim_th = line_sim_th;
-    if (fused) {
-        st = launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(ctx->d_buf + o_job), 1, gp, n1, std::max(n2, 1));
+    if (fused && n1 >= 64 && g_grid_cluster) {
+        st = launch_grid_cluster(ctx, reinterpret_cast<const plm::GridJob *>(ctx->d_buf + o_job), 1, gp, n1, std::max(n2, 1),
+                                 std::max(n_items, 1), is_lines != 0);
+    } else if (fused) {
+        st = launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(ctx->d_buf + o_job), 1, gp, n1, std::max(n2, 1), std::max(n_items, 1), is_lines != 0);
     } else {
         st = launch_grid_chunked(ctx, job, gp, o_cta_min, o_m21key, o_m21, warps, n_cta);
     }
@@ -1160,7 +1223,8 @@ struct plm_batch {
     // grid
     size_t o_gjobs = 0;
     plm::GridParams gp;
-    int n1_max = 0, n2_max = 0;
+    int n1_max = 0, n2_max = 0, items_max = 1;
+    bool any_lines = false;
     int64_t h2d = 0, d2h = 0;
 
     int ensure(size_t bytes) {
@@ -1399,7 +1463,8 @@ PLM_API int plm_batch_set_match_grid(plm_batch *b, const uint8_t *arena, int64_t
     int32_t *d_counts = reinterpret_cast<int32_t *>(D + b->o_work + align_up(size_t(n_m) * 4, 16));
 
     std::vector<plm::GridJob> gj(static_cast<size_t>(n_jobs));
-    int n1_max = 1, n2_max = 1;
+    int n1_max = 1, n2_max = 1, items_max = 1;
+    bool any_lines = false;
     for (int j = 0; j < n_jobs; ++j) {
         const plm_grid_job &jb = jobs[j];
         const int cpq = jb.is_lines ? 4 : 2;
@@ -1431,9 +1496,11 @@ PLM_API int plm_batch_set_match_grid(plm_batch *b, const uint8_t *arena, int64_t
         for (int i = 0; i < 4; ++i) g.win[i] = jb.win[i];
         n1_max = std::max(n1_max, jb.n1);
         n2_max = std::max(n2_max, jb.n2);
+        items_max = std::max(items_max, cs[n_cells]);
+        any_lines = any_lines || jb.is_lines != 0;
     }
-    const FusedShape fs = fused_shape(ctx, n1_max, n2_max);
-    if (fs.smem > ctx->smem_optin) return fail(PLM_E_UNSUPPORTED, "matchGrid: train set too large for shared memory");
+    b->items_max = items_max;
+    b->any_lines = any_lines;
 
     Layout S;
     const size_t s_init = S.add(b->work_bytes);
@@ -1500,7 +1567,8 @@ PLM_API int plm_batch_run(plm_batch *b) {
         }
         return PLM_OK;
     }
-    return launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(D + b->o_gjobs), b->n_jobs, b->gp, b->n1_max, b->n2_max);
+    return launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(D + b->o_gjobs), b->n_jobs, b->gp, b->n1_max, b->n2_max,
+                             b->items_max, b->any_lines);
 }
 
 PLM_API int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts) {
