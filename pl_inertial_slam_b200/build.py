@@ -53,7 +53,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(res.stdout, res.stderr, file=sys.stderr)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed building libplmatch.so")
+    build_tools(force=force)
     return LIB
+
+
+def build_tools(force: bool = False):
+    """tools/latency_bench: C-level latency of the host-buffer entry points (no Python in the loop)."""
+    src = os.path.join(HERE, "..", "tools", "latency_bench.cpp")
+    out = os.path.join(HERE, "..", "tools", "latency_bench")
+    if not os.path.exists(src) or not (force or _stale(out, [src, LIB])):
+        return
+    cmd = ["g++", "-O2", "-std=c++17", src, "-I", os.path.join(HERE, "..", "include"), "-L", LIBDIR, "-lplmatch",
+           "-Wl,-rpath,$ORIGIN/../pl_inertial_slam_b200/lib", "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout, res.stderr, file=sys.stderr)
+        raise RuntimeError("g++ failed building tools/latency_bench")
 
 
 if __name__ == "__main__":
