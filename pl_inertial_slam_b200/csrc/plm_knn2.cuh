@@ -25,23 +25,29 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long expand_key(uint32_t k, unsigned long long row_base) {
+__device__ __forceinline__ unsigned long long expand_key(uint32_t k, uint32_t row_base) {
     if (k == KEY32_ABSENT) return KEY64_ABSENT;
-    return make_key64(k >> KNN_IDX_BITS, 0u) + row_base + (k & (KNN_MAX_SLICE_ROWS - 1));
+    return make_key64(k >> KNN_IDX_BITS, row_base + (k & (KNN_MAX_SLICE_ROWS - 1)));
 }
 
-// One brute-force direction: queries q[0..n1) against train rows db[0..n2), split into n_slices
-// slices of slice_rows rows.  part[slice][query] = (best, second) packed 64-bit keys.
+// One brute-force direction: queries q[0..n1) against train rows db[0..n2).  The train set is cut
+// into n_units units of unit_rows <= KNN_STAGE_ROWS rows (one shared-memory stage each); CTA (qblock,
+// worker) scans units worker, worker + n_workers, ... in increasing row order through a continuous
+// double-buffered cp.async pipeline and keeps a running top-2 of packed 64-bit keys in registers.  A
+// launch is therefore a single wave of co-resident CTAs whatever the database size, work is balanced
+// to one 256-row unit, and only n_workers partial results per query exist.
+// part[worker][query] = (best, second).
 struct KnnTask {
     const uint4 *q;
     const uint4 *db;
-    ulonglong2 *part;   // [n_slices][n1]
+    ulonglong2 *part;   // [n_workers][n1]
     ulonglong2 *top2;   // [n1] merged result (may be null when only the acceptance is wanted)
     int32_t *m;         // in/out match vector written by the NNR acceptance (may be null)
     int32_t *count;     // accepted-row counter (may be null)
     unsigned long long idx_base;
     long long n2;
-    int n1, slice_rows, n_slices, pad_;
+    int n1, unit_rows, n_workers, n_units;
+    int pad_, pad2_;
 };
 struct KnnTaskPair {
     KnnTask t[2];
@@ -53,9 +59,9 @@ struct KnnTaskPair {
 //            through the packed-key top-2 update when their minimum beats the thread's current
 //            second-best distance.  Train rows are scanned in increasing index order, so a row that
 //            merely ties the second best can never displace it (its key is larger) and the strict
-//            test is exact.  For long slices the update path is almost never taken.
+//            test is exact.  For long scans the update path is almost never taken.
 template <int THREADS, int VARIANT>
-__device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, int slice, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
+__device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, int worker, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
     const int tid = threadIdx.x;
     const int n1 = t.n1;
     const int qi = qblock * THREADS + tid;
@@ -66,77 +72,80 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
         a.lo = make_uint4(0, 0, 0, 0);
         a.hi = a.lo;
     }
-    const long long r0 = static_cast<long long>(slice) * t.slice_rows;
-    const long long r1 = min(t.n2, r0 + t.slice_rows);
-    const int n_rows = static_cast<int>(max(r1 - r0, 0ll));
-    const int n_stage = (n_rows + KNN_STAGE_ROWS - 1) / KNN_STAGE_ROWS;
     const uint4 *db = t.db;
+    const int unit_rows = t.unit_rows, n_units = t.n_units, step = t.n_workers;
+    const uint32_t idx_base = static_cast<uint32_t>(t.idx_base); // idx_base + n2 <= 2^32 (checked by the host)
+    unsigned long long B0 = KEY64_ABSENT, B1 = KEY64_ABSENT;     // running top-2 over all units of this worker
+    int thr = 1023;                                              // variant 2: distance a row must beat (> 256: none yet)
 
-    auto issue = [&](int st) {
-        const int rows = min(KNN_STAGE_ROWS, n_rows - st * KNN_STAGE_ROWS);
-        const uint4 *src = db + 2 * (r0 + static_cast<long long>(st) * KNN_STAGE_ROWS);
-        uint4 *dst = stage[st & 1];
+    auto rows_of = [&](int u) { return static_cast<int>(min(static_cast<long long>(unit_rows), t.n2 - static_cast<long long>(u) * unit_rows)); };
+    auto issue = [&](int u, int buf) {
+        const int rows = rows_of(u);
+        const uint4 *src = db + 2 * (static_cast<long long>(u) * unit_rows);
+        uint4 *dst = stage[buf];
         for (int i = tid; i < rows * 2; i += THREADS) cp_async16(dst + i, src + i);
         cp_async_commit();
     };
 
-    uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT;
-    if (n_stage > 0) issue(0);
-    for (int st = 0; st < n_stage; ++st) {
-        if (st + 1 < n_stage) {
-            issue(st + 1);
+    int buf = 0;
+    if (worker < n_units) issue(worker, 0);
+    for (int u = worker; u < n_units; u += step, buf ^= 1) {
+        if (u + step < n_units) {
+            issue(u + step, buf ^ 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
-        const int rows = min(KNN_STAGE_ROWS, n_rows - st * KNN_STAGE_ROWS);
-        const uint4 *buf = stage[st & 1];
-        const uint32_t key_base = static_cast<uint32_t>(st * KNN_STAGE_ROWS);
+        const int rows = rows_of(u);
+        const uint4 *sb = stage[buf];
+        const uint32_t gbase = idx_base + static_cast<uint32_t>(u) * static_cast<uint32_t>(unit_rows);
         if (VARIANT == 2) {
             int j = 0;
             for (; j + 8 <= rows; j += 8) {
                 int d[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) d[u] = hamming256_csa4(a, buf[2 * (j + u)], buf[2 * (j + u) + 1]);
+                for (int v = 0; v < 8; ++v) d[v] = hamming256_csa4(a, sb[2 * (j + v)], sb[2 * (j + v) + 1]);
                 const int m = min(min(min(d[0], d[1]), min(d[2], d[3])), min(min(d[4], d[5]), min(d[6], d[7])));
-                if (m < static_cast<int>(b1 >> KNN_IDX_BITS)) {
+                if (m < thr) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        top2_insert(b0, b1, (static_cast<uint32_t>(d[u]) << KNN_IDX_BITS) + (key_base + j + u));
+                    for (int v = 0; v < 8; ++v) top2_insert(B0, B1, make_key64(d[v], gbase + j + v));
+                    thr = (B1 == KEY64_ABSENT) ? 1023 : static_cast<int>(B1 >> 32);
                 }
             }
             for (; j < rows; ++j) {
-                const int d = hamming256_csa4(a, buf[2 * j], buf[2 * j + 1]);
-                top2_insert(b0, b1, (static_cast<uint32_t>(d) << KNN_IDX_BITS) + (key_base + j));
+                const int d = hamming256_csa4(a, sb[2 * j], sb[2 * j + 1]);
+                if (d < thr) {
+                    top2_insert(B0, B1, make_key64(d, gbase + j));
+                    thr = (B1 == KEY64_ABSENT) ? 1023 : static_cast<int>(B1 >> 32);
+                }
             }
         } else {
+            uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT; // unit-local keys (d << 22 | row in unit)
 #pragma unroll 8
             for (int j = 0; j < rows; ++j) {
-                const uint4 blo = buf[2 * j], bhi = buf[2 * j + 1];
+                const uint4 blo = sb[2 * j], bhi = sb[2 * j + 1];
                 const int d = (VARIANT == 1) ? hamming256_csa(a, blo, bhi) : hamming256(a, blo, bhi);
-                const uint32_t k = (static_cast<uint32_t>(d) << KNN_IDX_BITS) + (key_base + j);
-                top2_insert(b0, b1, k);
+                top2_insert(b0, b1, (static_cast<uint32_t>(d) << KNN_IDX_BITS) + static_cast<uint32_t>(j));
             }
+            top2_insert(B0, B1, expand_key(b0, gbase));
+            top2_insert(B0, B1, expand_key(b1, gbase));
         }
         __syncthreads();
     }
-    if (qi < n1) {
-        const unsigned long long base = t.idx_base + static_cast<unsigned long long>(r0);
-        t.part[static_cast<size_t>(slice) * n1 + qi] = make_ulonglong2(expand_key(b0, base), expand_key(b1, base));
-    }
+    if (qi < n1) t.part[static_cast<size_t>(worker) * n1 + qi] = make_ulonglong2(B0, B1);
 }
 
-// grid = (max qblocks, max slices, n_tasks <= 2): both directions of StVO::match in one launch.
+// grid = (max qblocks, max workers, n_tasks <= 2): both directions of StVO::match in one launch.
 template <int THREADS, int VARIANT>
-__global__ void __launch_bounds__(THREADS) knn2_slice_kernel(const KnnTaskPair tasks) {
+__global__ void __launch_bounds__(THREADS, (THREADS == 128) ? 9 : 12) knn2_slice_kernel(const KnnTaskPair tasks) {
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
     const KnnTask &t = tasks.t[blockIdx.z];
-    if (static_cast<int>(blockIdx.x) * THREADS >= t.n1 || static_cast<int>(blockIdx.y) >= t.n_slices) return;
+    if (static_cast<int>(blockIdx.x) * THREADS >= t.n1 || static_cast<int>(blockIdx.y) >= t.n_workers) return;
     knn2_slice_body<THREADS, VARIANT>(t, blockIdx.x, blockIdx.y, stage);
 }
 
-// Batched form: cta_map[cta] = (task, qblock, slice); tasks live in device memory.
+// Batched form: cta_map[cta] = (task, qblock, worker); tasks live in device memory.
 template <int THREADS, int VARIANT>
 __global__ void __launch_bounds__(THREADS) knn2_slice_list_kernel(const KnnTask *__restrict__ tasks, const int4 *__restrict__ cta_map) {
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(THREADS) knn2_slice_list_kernel(const KnnTask 
 }
 
 // Slice merge + (optionally) the matchNNR acceptance (stvo-pl/src/matching.cpp:53-58).
-// top2[q] = two smallest of part[p][q].{x,y}, p < n_slices.  Keys with different train indices are
+// top2[q] = two smallest of part[p][q].{x,y}, p < n_workers.  Keys with different train indices are
 // distinct, so a plain lexicographic min-2 reproduces lowest-index tie-breaking across slices,
 // database shards and GPUs alike.  Acceptance is a float compare of a float product (no FMA); only
 // accepted rows are written because m is the reference's in/out matches_12.
@@ -154,7 +163,7 @@ __device__ __forceinline__ void knn2_merge_body(const KnnTask &t, int q, float n
     bool acc = false;
     if (q < t.n1) {
         unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
-        for (int p = 0; p < t.n_slices; ++p) {
+        for (int p = 0; p < t.n_workers; ++p) {
             const ulonglong2 v = t.part[static_cast<size_t>(p) * t.n1 + q];
             top2_insert(b0, b1, v.x);
             top2_insert(b0, b1, v.y);

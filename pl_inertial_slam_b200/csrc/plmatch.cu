@@ -66,6 +66,7 @@ struct plm_ctx {
     uint64_t launches = 0;
     bool fused_attr_set = false;
     bool cluster_attr_set = false;
+    int knn_occ[2][3] = {{0, 0, 0}, {0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
     // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
     bool profiling = false;
@@ -142,27 +143,10 @@ void pack_rows(void *dst, const uint8_t *src, int64_t n, size_t step) {
 
 struct KnnPlan {
     int threads = 128;
-    int n_slices = 1;
-    int slice_rows = plm::KNN_STAGE_ROWS;
+    int unit_rows = plm::KNN_STAGE_ROWS;
+    int n_units = 1;
+    int n_workers = 1;
 };
-
-// Splits the train set so that the launch has several waves of CTAs on 148 SMs; small problems get
-// narrow CTAs so that a frame-sized call still spreads over the whole chip.
-KnnPlan plan_knn(int n1, long long n2, int sm_count) {
-    KnnPlan p;
-    p.threads = (n1 >= 4096) ? 128 : 64;
-    const long long qblocks = std::max<long long>(1, (n1 + p.threads - 1) / p.threads);
-    const long long target = static_cast<long long>(sm_count) * 16;
-    long long slices = std::max<long long>(1, (target + qblocks - 1) / qblocks);
-    const long long max_slices = std::max<long long>(1, (n2 + 63) / 64);
-    slices = std::min(slices, max_slices);
-    long long rows = (n2 + slices - 1) / slices;
-    rows = std::max<long long>(64, (rows + 63) / 64 * 64);
-    rows = std::min<long long>(rows, plm::KNN_MAX_SLICE_ROWS);
-    p.slice_rows = static_cast<int>(rows);
-    p.n_slices = static_cast<int>(std::max<long long>(1, (n2 + rows - 1) / rows));
-    return p;
-}
 
 int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
 
@@ -180,17 +164,55 @@ int knn_variant_for(int slice_rows) {
     return slice_rows >= 2048 ? 2 : 1;
 }
 
+// CTAs of the brute-force kernel that are resident on one SM (per CTA width and variant).
+int knn_ctas_per_sm(plm_ctx *ctx, int threads, int variant) {
+    int &cached = ctx->knn_occ[threads == 128 ? 1 : 0][variant];
+    if (cached > 0) return cached;
+    int nb = 0;
+    cudaError_t e = cudaErrorUnknown;
+    if (threads == 128) {
+        if (variant == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<128, 2>, 128, 0);
+        else if (variant == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<128, 1>, 128, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<128, 0>, 128, 0);
+    } else {
+        if (variant == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<64, 2>, 64, 0);
+        else if (variant == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<64, 1>, 64, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<64, 0>, 64, 0);
+    }
+    cached = (e == cudaSuccess && nb > 0) ? nb : 8;
+    return cached;
+}
+
+// The train set is cut into units of <= 256 rows (one shared-memory stage) dealt round-robin to as many
+// workers per query block as fit on the chip at once: one wave of co-resident CTAs, no last-wave tail,
+// W partials per query.  Frame-sized problems get narrow CTAs and small units so that a single call
+// still spreads over the whole chip.
+KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2) {
+    KnnPlan p;
+    p.threads = (n1 >= 4096) ? 128 : 64;
+    const long long qblocks = std::max<long long>(1, (n1 + p.threads - 1) / p.threads);
+    const int variant = knn_variant_for(n2 >= 65536 ? 4096 : 64);
+    const long long capacity = static_cast<long long>(ctx->sm_count) * knn_ctas_per_sm(ctx, p.threads, variant);
+    const long long want = std::max<long long>(1, capacity / qblocks); // workers per query block
+    long long rows = (n2 + want - 1) / want;
+    rows = std::min<long long>(plm::KNN_STAGE_ROWS, std::max<long long>(64, (rows + 63) / 64 * 64));
+    p.unit_rows = static_cast<int>(rows);
+    p.n_units = static_cast<int>(std::max<long long>(1, (n2 + rows - 1) / rows));
+    p.n_workers = static_cast<int>(std::min<long long>(p.n_units, want));
+    return p;
+}
+
 int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int threads) {
     int qb = 0, sl = 0;
     for (int i = 0; i < n_tasks; ++i) {
         qb = std::max(qb, (tp.t[i].n1 + threads - 1) / threads);
-        sl = std::max(sl, tp.t[i].n_slices);
+        sl = std::max(sl, tp.t[i].n_workers);
     }
     if (qb == 0 || sl == 0) return PLM_OK;
     const dim3 grid(qb, sl, n_tasks);
     int min_rows = INT_MAX;
-    for (int i = 0; i < n_tasks; ++i) min_rows = std::min(min_rows, tp.t[i].slice_rows);
-    const int variant = knn_variant_for(min_rows);
+    for (int i = 0; i < n_tasks; ++i) min_rows = std::min<long long>(min_rows, std::min<long long>(tp.t[i].n2, INT_MAX));
+    const int variant = knn_variant_for(min_rows >= 65536 ? 4096 : 64);
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (ctx->profiling) {
         if (!ctx->prof_free.empty()) {
@@ -407,20 +429,22 @@ struct KnnScratch {
 
 int build_knn_task(plm_ctx *ctx, Layout &L, plm::KnnTask &t, KnnPlan &plan, const uint4 *q, int n1, const uint4 *db,
                    long long n2, unsigned long long idx_base, size_t &part_off) {
-    plan = plan_knn(n1, n2, ctx->sm_count);
+    plan = plan_knn(ctx, n1, n2);
     t.q = q;
     t.db = db;
     t.n1 = n1;
     t.n2 = n2;
     t.idx_base = idx_base;
-    t.slice_rows = plan.slice_rows;
-    t.n_slices = plan.n_slices;
+    t.unit_rows = plan.unit_rows;
+    t.n_units = plan.n_units;
+    t.n_workers = plan.n_workers;
+    t.pad2_ = 0;
     t.part = nullptr;
     t.top2 = nullptr;
     t.m = nullptr;
     t.count = nullptr;
     t.pad_ = 0;
-    part_off = L.add(size_t(plan.n_slices) * size_t(std::max(n1, 1)) * sizeof(ulonglong2));
+    part_off = L.add(size_t(plan.n_workers) * size_t(std::max(n1, 1)) * sizeof(ulonglong2));
     return PLM_OK;
 }
 
@@ -1314,13 +1338,15 @@ PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_ro
             plm::KnnTask t;
             std::memset(&t, 0, sizeof(t));
             const int nq = dir ? jb.n2 : jb.n1, nt = dir ? jb.n1 : jb.n2;
-            int slices = std::min(want_slices, std::max(1, (nt + 63) / 64));
-            int rows = ((nt + slices - 1) / slices + 63) / 64 * 64;
-            slices = std::max(1, (nt + rows - 1) / rows);
+            int slices = std::min(want_slices, std::max(1, (nt + 63) / 64)); // workers of this task
+            const int rows = std::min(plm::KNN_STAGE_ROWS, ((nt + slices - 1) / slices + 63) / 64 * 64);
+            const int units = std::max(1, (nt + rows - 1) / rows);
+            slices = std::min(slices, units);
             t.n1 = nq;
             t.n2 = nt;
-            t.slice_rows = rows;
-            t.n_slices = slices;
+            t.unit_rows = rows;
+            t.n_units = units;
+            t.n_workers = slices;
             t.idx_base = 0;
             // pointers are patched once the device block exists; stash offsets in the fields
             t.q = reinterpret_cast<const uint4 *>(static_cast<uintptr_t>(dir ? jb.off2 : jb.off1));
