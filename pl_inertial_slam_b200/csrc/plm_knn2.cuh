@@ -51,6 +51,8 @@ struct KnnTask {
 };
 struct KnnTaskPair {
     KnnTask t[2];
+    int cta_split; // CTAs [0, cta_split) belong to t[0], the rest to t[1]
+    int pad_;
 };
 
 // VARIANT 0: plain 8-POPC distance, per-pair top-2 update
@@ -136,13 +138,14 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
     if (qi < n1) t.part[static_cast<size_t>(worker) * n1 + qi] = make_ulonglong2(B0, B1);
 }
 
-// grid = (max qblocks, max workers, n_tasks <= 2): both directions of StVO::match in one launch.
+// 1-D grid over (task, query block, worker): both directions of StVO::match in one launch.
 template <int THREADS, int VARIANT>
 __global__ void __launch_bounds__(THREADS, (THREADS == 128) ? 9 : 12) knn2_slice_kernel(const KnnTaskPair tasks) {
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
-    const KnnTask &t = tasks.t[blockIdx.z];
-    if (static_cast<int>(blockIdx.x) * THREADS >= t.n1 || static_cast<int>(blockIdx.y) >= t.n_workers) return;
-    knn2_slice_body<THREADS, VARIANT>(t, blockIdx.x, blockIdx.y, stage);
+    const int which = static_cast<int>(blockIdx.x) >= tasks.cta_split ? 1 : 0;
+    const KnnTask &t = tasks.t[which];
+    const int local = static_cast<int>(blockIdx.x) - (which ? tasks.cta_split : 0);
+    knn2_slice_body<THREADS, VARIANT>(t, local / t.n_workers, local % t.n_workers, stage);
 }
 
 // Batched form: cta_map[cta] = (task, qblock, worker); tasks live in device memory.

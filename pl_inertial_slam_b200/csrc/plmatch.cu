@@ -202,14 +202,17 @@ KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2) {
     return p;
 }
 
-int launch_knn_slices(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, int threads) {
-    int qb = 0, sl = 0;
+int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threads) {
+    long long total = 0;
     for (int i = 0; i < n_tasks; ++i) {
-        qb = std::max(qb, (tp.t[i].n1 + threads - 1) / threads);
-        sl = std::max(sl, tp.t[i].n_workers);
+        const long long c = static_cast<long long>((tp.t[i].n1 + threads - 1) / threads) * tp.t[i].n_workers;
+        if (i == 0) tp.cta_split = static_cast<int>(c);
+        total += c;
     }
-    if (qb == 0 || sl == 0) return PLM_OK;
-    const dim3 grid(qb, sl, n_tasks);
+    if (n_tasks == 1) tp.cta_split = static_cast<int>(total);
+    if (total == 0) return PLM_OK;
+    if (total > INT_MAX) return fail(PLM_E_UNSUPPORTED, "too many query blocks");
+    const dim3 grid(static_cast<unsigned>(total), 1, 1);
     int min_rows = INT_MAX;
     for (int i = 0; i < n_tasks; ++i) min_rows = std::min<long long>(min_rows, std::min<long long>(tp.t[i].n2, INT_MAX));
     const int variant = knn_variant_for(min_rows >= 65536 ? 4096 : 64);
