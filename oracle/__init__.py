@@ -99,6 +99,18 @@ class _Port:
                                                   C.c_double, _u8p, _f64p]
             L.plo_line_overlap_stereo.restype = C.c_double
             L.plo_line_overlap_stereo.argtypes = [C.c_double] * 5
+            L.plo_csr_from_points.restype = C.c_int
+            L.plo_csr_from_points.argtypes = [_f32p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _i32p, _i32p]
+            L.plo_csr_from_lines.restype = C.c_int
+            L.plo_csr_from_lines.argtypes = [_f32p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _i32p, _i32p, _f64p]
+            L.plo_stereo_points.restype = C.c_int
+            L.plo_stereo_points.argtypes = [_f32p, _u8p, C.c_int, _f32p, _u8p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                            C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _f64p, _i32p,
+                                            _i32p, _f64p, _f64p]
+            L.plo_stereo_lines.restype = C.c_int
+            L.plo_stereo_lines.argtypes = [_f32p, _u8p, C.c_int, _f32p, _u8p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                           C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                           C.c_double, C.c_double, _f64p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]
             self._lib = L
         return self._lib
 
@@ -218,6 +230,71 @@ class _Port:
                                              min_disp, line_horiz_th, stereo_overlap_th, ls_min_disp_ratio,
                                              keep.ctypes.data_as(_u8p), disp.ctypes.data_as(_f64p))
         return n, keep, disp
+
+
+    # ---- whole stereo drivers (stereoFrame.cpp:131-184, :320-409) ---------------------------------------
+    def csr_from_points(self, kp, inv_w, inv_h, rows=48, cols=64):
+        kp = np.ascontiguousarray(kp, np.float32).reshape(-1, 2)
+        cs = np.zeros(rows * cols + 1, np.int32)
+        ci = np.zeros(max(1, len(kp)), np.int32)
+        n = self.lib.plo_csr_from_points(kp.ctypes.data_as(_f32p), len(kp), inv_w, inv_h, rows, cols,
+                                         cs.ctypes.data_as(_i32p), ci.ctypes.data_as(_i32p))
+        return cs, ci[:n]
+
+    def csr_from_lines(self, ln, inv_w, inv_h, rows=48, cols=64):
+        ln = np.ascontiguousarray(ln, np.float32).reshape(-1, 4)
+        cs = np.zeros(rows * cols + 1, np.int32)
+        dirs = np.zeros((len(ln), 2), np.float64)
+        n = self.lib.plo_csr_from_lines(ln.ctypes.data_as(_f32p), len(ln), inv_w, inv_h, rows, cols,
+                                        cs.ctypes.data_as(_i32p), None, None)
+        ci = np.zeros(max(1, n), np.int32)
+        self.lib.plo_csr_from_lines(ln.ctypes.data_as(_f32p), len(ln), inv_w, inv_h, rows, cols,
+                                    cs.ctypes.data_as(_i32p), ci.ctypes.data_as(_i32p), dirs.ctypes.data_as(_f64p))
+        return cs, ci[:n], dirs
+
+    def stereo_points(self, kp_l, d_l, kp_r, d_r, inv_w, inv_h, cam, rows=48, cols=64, matching_s_ws=10, ratio=0.9,
+                      best_lr=True, max_dist_epip=1.0, min_disp=1.0):
+        """StereoFrame::matchStereoPoints -> dict(m12, kept_i1, disp, P)."""
+        kp_l = np.ascontiguousarray(kp_l, np.float32).reshape(-1, 2)
+        kp_r = np.ascontiguousarray(kp_r, np.float32).reshape(-1, 2)
+        d_l = np.ascontiguousarray(d_l, np.uint8).reshape(-1, 32)
+        d_r = np.ascontiguousarray(d_r, np.uint8).reshape(-1, 32)
+        n_l, n_r = len(kp_l), len(kp_r)
+        cam = np.ascontiguousarray(cam, np.float64)
+        m12 = np.full(n_l, -1, np.int32)
+        kept = np.zeros(max(1, n_l), np.int32)
+        disp = np.zeros(max(1, n_l), np.float64)
+        P = np.zeros((max(1, n_l), 3), np.float64)
+        n = self.lib.plo_stereo_points(kp_l.ctypes.data_as(_f32p), d_l.ctypes.data_as(_u8p), n_l,
+                                       kp_r.ctypes.data_as(_f32p), d_r.ctypes.data_as(_u8p), n_r, inv_w, inv_h, rows,
+                                       cols, matching_s_ws, ratio, int(best_lr), max_dist_epip, min_disp,
+                                       cam.ctypes.data_as(_f64p), m12.ctypes.data_as(_i32p), kept.ctypes.data_as(_i32p),
+                                       disp.ctypes.data_as(_f64p), P.ctypes.data_as(_f64p))
+        return dict(m12=m12, kept_i1=kept[:n].copy(), disp=disp[:n].copy(), P=P[:n].copy())
+
+    def stereo_lines(self, ln_l, d_l, ln_r, d_r, inv_w, inv_h, cam, rows=48, cols=64, matching_s_ws=10, ratio=0.9,
+                     line_sim_th=0.75, best_lr=True, min_disp=1.0, line_horiz_th=0.1, stereo_overlap_th=0.75,
+                     ls_min_disp_ratio=0.7):
+        """StereoFrame::matchStereoLines -> dict(m12, kept_i1, disp_se, sP, eP, le)."""
+        ln_l = np.ascontiguousarray(ln_l, np.float32).reshape(-1, 4)
+        ln_r = np.ascontiguousarray(ln_r, np.float32).reshape(-1, 4)
+        d_l = np.ascontiguousarray(d_l, np.uint8).reshape(-1, 32)
+        d_r = np.ascontiguousarray(d_r, np.uint8).reshape(-1, 32)
+        n_l, n_r = len(ln_l), len(ln_r)
+        cam = np.ascontiguousarray(cam, np.float64)
+        m12 = np.full(n_l, -1, np.int32)
+        cap = max(1, n_l)
+        kept = np.zeros(cap, np.int32)
+        dse = np.zeros((cap, 2), np.float64)
+        sP, eP, le = (np.zeros((cap, 3), np.float64) for _ in range(3))
+        n = self.lib.plo_stereo_lines(ln_l.ctypes.data_as(_f32p), d_l.ctypes.data_as(_u8p), n_l,
+                                      ln_r.ctypes.data_as(_f32p), d_r.ctypes.data_as(_u8p), n_r, inv_w, inv_h, rows,
+                                      cols, matching_s_ws, ratio, line_sim_th, int(best_lr), min_disp, line_horiz_th,
+                                      stereo_overlap_th, ls_min_disp_ratio, cam.ctypes.data_as(_f64p),
+                                      m12.ctypes.data_as(_i32p), kept.ctypes.data_as(_i32p), dse.ctypes.data_as(_f64p),
+                                      sP.ctypes.data_as(_f64p), eP.ctypes.data_as(_f64p), le.ctypes.data_as(_f64p))
+        return dict(m12=m12, kept_i1=kept[:n].copy(), disp_se=dse[:n].copy(), sP=sP[:n].copy(), eP=eP[:n].copy(),
+                    le=le[:n].copy())
 
 
 class _Ref:

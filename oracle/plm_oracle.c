@@ -507,3 +507,195 @@ PLO_API int plo_stereo_filter_lines(const float *ln_l, const float *ln_r, const 
     }
     return kept;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * Whole stereo drivers (StereoFrame::matchStereoPoints / matchStereoLines): grid fill,
+ * matchGrid, geometry gates, compaction of the kept rows and back-projection.  These follow
+ * stvo-pl/src/stereoFrame.cpp, which cannot be compiled here (OpenCV + Eigen + line_descriptor),
+ * so unlike the matching functions above they are pinned by restatement only.
+ * ------------------------------------------------------------------------------------- */
+
+/* C++ double -> int conversion (truncation toward zero) of an already scaled coordinate. */
+static inline int plo_trunc(double v) { return (int)v; }
+
+/* grid.at(kp.x * inv_width, kp.y * inv_height).push_back(idx), stereoFrame.cpp:146-150 with
+ * GridStructure::at (gridStructure.cpp:56-63: off-grid pushes go to a sink list).  kp = n x (x, y)
+ * float pixel coordinates; float * double is evaluated in double.  CSR out. */
+PLO_API int plo_csr_from_points(const float *kp, int n, double inv_w, double inv_h, int rows,
+                                int cols, int32_t *cell_start, int32_t *cell_items)
+{
+    const int n_cells = rows * cols;
+    int32_t *cnt = (int32_t *)calloc((size_t)n_cells + 1, sizeof(int32_t));
+    int32_t *cid = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        const int x = plo_trunc((double)kp[2 * i] * inv_w), y = plo_trunc((double)kp[2 * i + 1] * inv_h);
+        cid[i] = (x >= 0 && x < cols && y >= 0 && y < rows) ? x * rows + y : -1;
+        if (cid[i] >= 0) cnt[cid[i]]++;
+    }
+    cell_start[0] = 0;
+    for (int c = 0; c < n_cells; c++) cell_start[c + 1] = cell_start[c] + cnt[c];
+    memset(cnt, 0, sizeof(int32_t) * (size_t)n_cells);
+    for (int i = 0; i < n; i++)
+        if (cid[i] >= 0) cell_items[cell_start[cid[i]] + cnt[cid[i]]++] = i;
+    free(cnt);
+    free(cid);
+    return cell_start[n_cells];
+}
+
+/* stereoFrame.cpp:336-349: directions (:342-344, float subtraction, * double, matching.h:43-48
+ * normalize) and the Bresenham grid fill of every right line (getLineCoords, :346-348).
+ * ln = n x (sx, sy, ex, ey) float.  Returns the item count (cell_items needs that many slots;
+ * call with cell_items == NULL to size it). */
+PLO_API int plo_csr_from_lines(const float *ln, int n, double inv_w, double inv_h, int rows, int cols,
+                               int32_t *cell_start, int32_t *cell_items, double *dirs)
+{
+    const int n_cells = rows * cols;
+    int32_t *cnt = (int32_t *)calloc((size_t)n_cells + 1, sizeof(int32_t));
+    const int cap = rows + cols + 4;
+    int32_t *cells = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)cap * 4);
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            cell_start[0] = 0;
+            for (int c = 0; c < n_cells; c++) cell_start[c + 1] = cell_start[c] + cnt[c];
+            memset(cnt, 0, sizeof(int32_t) * (size_t)n_cells);
+            if (!cell_items) break;
+        }
+        for (int i = 0; i < n; i++) {
+            const float *l = ln + 4 * i;
+            if (pass == 0 && dirs) {
+                double vx = (double)(l[2] - l[0]) * inv_w, vy = (double)(l[3] - l[1]) * inv_h;
+                const double xx = vx * vx, yy = vy * vy;
+                const double mag = sqrt(xx + yy);
+                dirs[2 * i] = vx / mag;
+                dirs[2 * i + 1] = vy / mag;
+            }
+            int m = plo_line_coords((double)l[0] * inv_w, (double)l[1] * inv_h, (double)l[2] * inv_w,
+                                    (double)l[3] * inv_h, cells, cap * 4);
+            if (m > cap * 4) m = cap * 4; /* cannot happen for on-image lines */
+            for (int k = 0; k < m; k++) {
+                const int x = cells[2 * k], y = cells[2 * k + 1];
+                if (x < 0 || x >= cols || y < 0 || y >= rows) continue;
+                const int c = x * rows + y;
+                if (pass == 0) cnt[c]++;
+                else cell_items[cell_start[c] + cnt[c]++] = i;
+            }
+        }
+    }
+    const int total = cell_start[n_cells];
+    free(cnt);
+    free(cells);
+    return total;
+}
+
+/* PinholeStereoCamera::backProjection (stvo-pl/src/pinholeStereoCamera.cpp:229-237).
+ * cam = {b, fx, cx, cy}. */
+static void plo_back_projection(const double cam[4], double u, double v, double disp, double P[3])
+{
+    const double bd = cam[0] / disp;
+    P[0] = bd * (u - cam[2]);
+    P[1] = bd * (v - cam[3]);
+    P[2] = bd * cam[1];
+}
+
+/*
+ * StereoFrame::matchStereoPoints (stvo-pl/src/stereoFrame.cpp:131-184).  Outputs: m12 (n_l, the
+ * matchGrid vector, starts at -1), and for the kept rows in i1 order (= the order of stereo_pt and
+ * of the compacted pdesc_l, :172-178): kept_i1, disp, P (3 per row).  Returns the number kept, or
+ * 0 with m12 untouched when either side is empty (:137-138).
+ */
+PLO_API int plo_stereo_points(const float *kp_l, const uint8_t *d_l, int n_l, const float *kp_r,
+                              const uint8_t *d_r, int n_r, double inv_w, double inv_h, int rows, int cols,
+                              int matching_s_ws, double ratio, int best_lr, double max_dist_epip,
+                              double min_disp, const double cam[4], int32_t *m12, int32_t *kept_i1,
+                              double *disp, double *P)
+{
+    if (n_l <= 0 || n_r <= 0) return 0;
+    const int n_cells = rows * cols;
+    int32_t *xy = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)n_l);
+    int32_t *cs = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n_cells + 1));
+    int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_r);
+    for (int i = 0; i < n_l; i++) { /* :142-143, pair<double,double> -> pair<int,int> */
+        xy[2 * i] = plo_trunc((double)kp_l[2 * i] * inv_w);
+        xy[2 * i + 1] = plo_trunc((double)kp_l[2 * i + 1] * inv_h);
+        m12[i] = -1;
+    }
+    plo_csr_from_points(kp_r, n_r, inv_w, inv_h, rows, cols, cs, ci);
+    const int32_t win[4] = {matching_s_ws, 0, 0, 0}; /* :152-154 */
+    plo_match_grid(0, xy, d_l, n_l, 32, cs, ci, rows, cols, d_r, n_r, 32, NULL, 0.0, win, ratio, best_lr, m12);
+    int kept = 0;
+    for (int i1 = 0; i1 < n_l; i1++) {
+        const int i2 = m12[i1];
+        if (i2 < 0) continue;
+        const float dyf = kp_l[2 * i1 + 1] - kp_r[2 * i2 + 1];
+        if (!((double)fabsf(dyf) <= max_dist_epip)) continue;
+        const double disp_ = (double)(kp_l[2 * i1] - kp_r[2 * i2]);
+        if (!(disp_ >= min_disp)) continue;
+        kept_i1[kept] = i1;
+        disp[kept] = disp_;
+        plo_back_projection(cam, (double)kp_l[2 * i1], (double)kp_l[2 * i1 + 1], disp_, P + 3 * kept);
+        kept++;
+    }
+    free(xy);
+    free(cs);
+    free(ci);
+    return kept;
+}
+
+/*
+ * StereoFrame::matchStereoLines (stvo-pl/src/stereoFrame.cpp:320-409).  Per kept row: kept_i1,
+ * disp_se (2), sP / eP (3 each), le (3) = normalised left line equation (:368: cross product of the
+ * homogeneous endpoints divided by sqrt(le0^2 + le1^2)).
+ */
+PLO_API int plo_stereo_lines(const float *ln_l, const uint8_t *d_l, int n_l, const float *ln_r,
+                             const uint8_t *d_r, int n_r, double inv_w, double inv_h, int rows, int cols,
+                             int matching_s_ws, double ratio, double line_sim_th, int best_lr,
+                             double min_disp, double line_horiz_th, double stereo_overlap_th,
+                             double ls_min_disp_ratio, const double cam[4], int32_t *m12,
+                             int32_t *kept_i1, double *disp_se, double *sP, double *eP, double *le)
+{
+    if (n_l <= 0 || n_r <= 0) return 0;
+    const int n_cells = rows * cols;
+    int32_t *xyxy = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)n_l);
+    int32_t *cs = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n_cells + 1));
+    double *dirs = (double *)malloc(sizeof(double) * 2 * (size_t)n_r);
+    for (int i = 0; i < n_l; i++) { /* :330-333 */
+        xyxy[4 * i + 0] = plo_trunc((double)ln_l[4 * i + 0] * inv_w);
+        xyxy[4 * i + 1] = plo_trunc((double)ln_l[4 * i + 1] * inv_h);
+        xyxy[4 * i + 2] = plo_trunc((double)ln_l[4 * i + 2] * inv_w);
+        xyxy[4 * i + 3] = plo_trunc((double)ln_l[4 * i + 3] * inv_h);
+        m12[i] = -1;
+    }
+    const int n_items = plo_csr_from_lines(ln_r, n_r, inv_w, inv_h, rows, cols, cs, NULL, NULL);
+    int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_items > 0 ? n_items : 1));
+    plo_csr_from_lines(ln_r, n_r, inv_w, inv_h, rows, cols, cs, ci, dirs);
+    const int32_t win[4] = {matching_s_ws, 0, 0, 0}; /* :351-353 */
+    plo_match_grid(1, xyxy, d_l, n_l, 32, cs, ci, rows, cols, d_r, n_r, 32, dirs, line_sim_th, win, ratio,
+                   best_lr, m12);
+    uint8_t *keep = (uint8_t *)malloc((size_t)n_l);
+    double *dse = (double *)malloc(sizeof(double) * 2 * (size_t)n_l);
+    plo_stereo_filter_lines(ln_l, ln_r, m12, n_l, min_disp, line_horiz_th, stereo_overlap_th, ls_min_disp_ratio,
+                            keep, dse);
+    int kept = 0;
+    for (int i1 = 0; i1 < n_l; i1++) {
+        if (!keep[i1]) continue;
+        const double x1 = ln_l[4 * i1], y1 = ln_l[4 * i1 + 1], x2 = ln_l[4 * i1 + 2], y2 = ln_l[4 * i1 + 3];
+        /* Eigen cross of (x1, y1, 1) and (x2, y2, 1), each product rounded separately */
+        const double c0 = y1 * 1.0 - 1.0 * y2;
+        const double c1 = 1.0 * x2 - x1 * 1.0;
+        const double p0 = x1 * y2, p1 = y1 * x2;
+        const double c2 = p0 - p1;
+        const double q0 = c0 * c0, q1 = c1 * c1;
+        const double nrm = sqrt(q0 + q1);
+        kept_i1[kept] = i1;
+        disp_se[2 * kept] = dse[2 * i1];
+        disp_se[2 * kept + 1] = dse[2 * i1 + 1];
+        plo_back_projection(cam, x1, y1, dse[2 * i1], sP + 3 * kept);
+        plo_back_projection(cam, x2, y2, dse[2 * i1 + 1], eP + 3 * kept);
+        le[3 * kept] = c0 / nrm;
+        le[3 * kept + 1] = c1 / nrm;
+        le[3 * kept + 2] = c2 / nrm;
+        kept++;
+    }
+    free(xyxy); free(cs); free(ci); free(dirs); free(keep); free(dse);
+    return kept;
+}

@@ -1,0 +1,79 @@
+"""One pass over every kernel of the library on a representative shape, for ncu captures.
+
+    python tools/profile_kernels.py            # plain run (must exit 0 before the same line runs under ncu)
+    ncu --set full --clock-control none --import-source on -o gpurun_out/prof_all python tools/profile_kernels.py
+
+Shapes: frame-sized calls of configs 1-2 (600 ORB + 200 LBD), the map-sized matchGrid of config 4
+(200 000 x 600), a 300-frame replay batch (config 3) and one 6400 x 2 000 000 brute-force launch (config 5,
+shortened so the ~40 ncu replays stay short).  Every kernel is launched once after one warm-up call.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pl_inertial_slam_b200 import grid as G  # noqa: E402
+from pl_inertial_slam_b200 import matching as M  # noqa: E402
+from pl_inertial_slam_b200 import replay, synth  # noqa: E402
+from pl_inertial_slam_b200.database import DeviceOps, GridFrame, ShardedMap  # noqa: E402
+
+quick = "--quick" in sys.argv
+ctx = M.Context(0)
+M.Config.minRatio12P = 0.9
+prev, curr = synth.make_temporal_pair(synth.SEED0 + 2)
+a = synth.stereo_points_grid_args(prev)
+b = synth.stereo_lines_grid_args(prev)
+ga = (a["cell_start"], a["cell_items"], a["rows"], a["cols"])
+gb = (b["cell_start"], b["cell_items"], b["rows"], b["cols"])
+
+# frame-sized host-buffer calls: cluster matchGrid (points, lines), match (both directions + merge + cross-check),
+# stereo geometry gates, StVO::distance
+m_p, m_l = [], []
+M.matchGrid(a["xy"], a["d1"], ga, a["d2"], a["win"], m_p, ctx=ctx)
+M.matchGrid(b["xyxy"], b["d1"], gb, b["d2"], b["dirs2"], b["win"], m_l, ctx=ctx)
+M.match(prev.pdesc_l, curr.pdesc_l, 0.9, [], ctx=ctx)
+M.matchNNR(prev.ldesc_l, curr.ldesc_l, 0.9, [], ctx=ctx)
+M.stereo_filter_points(prev.kp_l, prev.kp_r, m_p, ctx=ctx)
+M.stereo_filter_lines(prev.ln_l, prev.ln_r, m_l, ctx=ctx)
+M.distances(prev.pdesc_l, prev.pdesc_r, ctx=ctx)
+
+# replay batch: fused matchGrid kernel (one CTA per job), list kernels of the brute-force path
+rp = synth.make_replay(synth.SEED0 + 3, 100 if quick else 300)
+gjobs, tjobs = replay.stereo_grid_jobs(rp), replay.temporal_match_jobs(rp)
+m_in = np.full(rp.n_m, -1, np.int32)
+gbatch, tbatch = replay.MatchBatch(ctx), replay.MatchBatch(ctx)
+gbatch.set_match_grid(rp.arena, rp.coords, rp.cell_start, rp.cell_items, rp.dirs2, 48, 64, gjobs, 0.9, 0.75, True, m_in)
+tbatch.set_match(rp.arena, tjobs, 0.9, True, m_in)
+gbatch.run(); tbatch.run()
+gbatch.fetch(); tbatch.fetch()
+
+# map-sized matchGrid (chunked two-pass kernels + scan + m21 + cross-check) and the brute-force fallback
+dev = torch.device("cuda", 0)
+ops = DeviceOps(0)
+sp = synth.make_stereo_pair(synth.SEED0 + 4)
+n_map = 50_000 if quick else 200_000
+d1, xy = synth.make_map_points(synth.SEED0 + 4, n_map, sp)
+c = sp.kp_l.astype(np.float64)
+cs, ci = G.csr_from_points(c[:, 0] * synth.INV_W, c[:, 1] * synth.INV_H)
+frame = GridFrame(torch.from_numpy(sp.pdesc_l).to(dev), torch.from_numpy(cs).to(dev), torch.from_numpy(ci).to(dev),
+                  G.GRID_ROWS, G.GRID_COLS)
+smap = ShardedMap(n_map, torch.from_numpy(d1).to(dev), torch.from_numpy(xy).to(dev), ops=ops)
+win = np.array([3, 3, 3, 3], np.int32)
+cnt, m12 = smap.match_grid(frame, win, 0.9, 0.75, True)
+smap.match(frame.d2, 0.9, True, m12_inout=m12)
+
+# config-5 shaped brute force (variant csa4) + slice merge + multi-GPU style top-2 merge + acceptance
+gen = torch.Generator(device="cuda").manual_seed(1)
+q = torch.randint(0, 256, (6400, 32), dtype=torch.uint8, device="cuda", generator=gen)
+db = torch.randint(0, 256, (200_000 if quick else 2_000_000, 32), dtype=torch.uint8, device="cuda", generator=gen)
+t2 = ops.knn2(q, db)
+parts = torch.stack([t2, t2 + 1])
+merged = ops.top2_merge(parts)
+m = torch.full((6400,), -1, dtype=torch.int32, device="cuda")
+cntt = torch.zeros(1, dtype=torch.int32, device="cuda")
+ops.nnr_accept(merged, 0.9, m, cntt)
+torch.cuda.synchronize()
+ctx.synchronize()
+print("profile_kernels ok: launches", ctx.launch_count + ops.ctx.launch_count)
