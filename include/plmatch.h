@@ -14,6 +14,8 @@
  *   plm_stereo_filter_lines   gates of matchStereoLines    stvo-pl/src/stereoFrame.cpp:359-385,
  *                             filterLineSegmentDisparity :416-426, lineSegmentOverlapStereo :484-519
  *   plm_batch_*             the per-frame loop             app/plslam_dataset.cpp:114-172
+ *   plm_frames_*            StereoFrame::matchStereoPoints/Lines + StereoFrameHandler::matchF2FPoints/Lines
+ *                           on the device (stereoFrame.cpp:131-184,320-409; stereoFrameHandler.cpp:158-207)
  *   plm_db_* / plm_dev_*    keyframe / local-map database  src/mapHandler.cpp:583-803, 3301-3409
  *
  * The C++ replacement of stvo-pl/src/matching.cpp that keeps the StVO:: signatures and calls this
@@ -190,6 +192,77 @@ int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts);
 /* Bytes the last set_* call copied host -> device / fetch copies device -> host. */
 int64_t plm_batch_h2d_bytes(const plm_batch *b);
 int64_t plm_batch_d2h_bytes(const plm_batch *b);
+
+/* ---- device-resident stereo-frame pipeline (config 3) --------------------- */
+/* The per-frame work of the reference's front end from raw features to tracked features, without a
+ * host round trip between the stages:
+ *   stereo stage    StereoFrame::matchStereoPoints / matchStereoLines   stvo-pl/src/stereoFrame.cpp:131-184,
+ *                   :320-409 -- bucket grid of the right features (GridStructure::at; getLineCoords /
+ *                   LineIterator for lines, stvo-pl/src/lineIterator.cpp:34-77), matchGrid with the window
+ *                   (matchingSWs, 0) x (0, 0), the geometry gates, compaction of pdesc_l / ldesc_l to the kept
+ *                   rows and PinholeStereoCamera::backProjection (pinholeStereoCamera.cpp:229-237)
+ *   temporal stage  StereoFrameHandler::matchF2FPoints / matchF2FLines   stvo-pl/src/stereoFrameHandler.cpp:
+ *                   158-207 -- StVO::match(prev, curr) on the COMPACTED left descriptors; frame f is matched
+ *                   against frame f - 1 of the same upload.
+ * Arenas: descriptors n_rows x 32 bytes; keypoints (x, y) float32 pixels (cv::KeyPoint::pt); line segments
+ * (startPointX, startPointY, endPointX, endPointY) float32 pixels (cv::line_descriptor::KeyLine). */
+typedef struct plm_frame_rec {
+    int64_t desc_pl, desc_pr, desc_ll, desc_lr; /* first descriptor-arena row of left/right points, left/right lines */
+    int64_t kp_l, kp_r;                         /* first keypoint of the left / right image in the keypoint arena      */
+    int64_t ln_l, ln_r;                         /* first segment of the left / right image in the line arena           */
+    int32_t n_pl, n_pr, n_ll, n_lr;
+} plm_frame_rec;
+
+typedef struct plm_frame_config {
+    double inv_width, inv_height; /* GRID_COLS / image cols, GRID_ROWS / image rows (stereoFrame.cpp:47-48)       */
+    int32_t grid_rows, grid_cols; /* GRID_ROWS 48, GRID_COLS 64 (stereoFrame.h:51-52)                              */
+    int32_t matching_s_ws;        /* Config::matchingSWs()                                                          */
+    int32_t best_lr;              /* Config::bestLRMatches()                                                        */
+    double min_ratio_12p;         /* matchGrid ratio (points AND lines, matching.cpp:160,241) and the f2f point nnr */
+    double min_ratio_12l;         /* f2f line nnr (narrowed to float like the reference's call)                     */
+    double line_sim_th, max_dist_epip, min_disp, line_horiz_th, stereo_overlap_th, ls_min_disp_ratio;
+    double cam_b, cam_fx, cam_cx, cam_cy; /* PinholeStereoCamera baseline / focal length / principal point         */
+} plm_frame_config;
+
+/* Host output buffers; any pointer may be NULL (not copied).  "Left point slots" are the left keypoints of
+ * all frames concatenated in frame order (frame f starts at sum of n_pl over earlier frames, NP slots in
+ * total); "left line slots" likewise (NL).  Per frame, the first kept rows of a slot range are valid.
+ *   stereo_m12_*  matchGrid vector of the stereo stage (index into the frame's right set or -1)
+ *   kept_*        kept slot k -> left feature index i1 (the order of stereo_pt / stereo_ls and of the
+ *                 compacted descriptors)
+ *   pt_disp, pt_P          PointFeature::disp and ::P per kept point (P = 3 doubles)
+ *   ls_disp, ls_sP, ls_eP, ls_le   LineFeature::sdisp/edisp (2 doubles), ::sP, ::eP, ::le (3 doubles each)
+ *   f2f_m12_*     slot range of frame f holds StVO::match(frame f, frame f + 1): kept index of frame f ->
+ *                 kept index of frame f + 1 or -1 (the last frame's range is not written)
+ *   counts        n_frames x 6: [0] stereo point matches (matchGrid return), [1] kept points, [2] stereo
+ *                 line matches, [3] kept lines, [4] / [5] return value of the f2f point / line match of
+ *                 (frame f - 1, frame f); 0 for frame 0 and when either side has no stereo features
+ *                 (stereoFrameHandler.cpp:164,187), INT32_MIN where StVO::match would be undefined
+ *                 (fewer than two descriptors on a train side). */
+typedef struct plm_frames_out {
+    int32_t *stereo_m12_p, *stereo_m12_l;
+    int32_t *kept_p, *kept_l;
+    double *pt_disp, *pt_P;
+    double *ls_disp, *ls_sP, *ls_eP, *ls_le;
+    int32_t *f2f_m12_p, *f2f_m12_l;
+    int32_t *counts;
+} plm_frames_out;
+
+typedef struct plm_frames plm_frames;
+int plm_frames_create(plm_ctx *ctx, plm_frames **out);
+int plm_frames_destroy(plm_frames *fr);
+/* Copies the arenas to the device and prepares the job tables (one host -> device copy per arena).
+ * Supported: per frame n_pl, n_pr <= 4096 and n_ll, n_lr <= 4096; line segments whose Bresenham walk is
+ * longer than grid_rows + grid_cols + 2 cells (far off-image coordinates) are rejected. */
+int plm_frames_upload(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows, const float *kp_arena,
+                      int64_t n_kp, const float *ln_arena, int64_t n_ln, const plm_frame_rec *frames,
+                      int n_frames, const plm_frame_config *cfg);
+/* Stereo stage then temporal stage for every uploaded frame, enqueued on the context's stream. */
+int plm_frames_run(plm_frames *fr);
+/* Device -> host copy of the requested outputs + stream sync. */
+int plm_frames_fetch(plm_frames *fr, const plm_frames_out *out);
+int64_t plm_frames_h2d_bytes(const plm_frames *fr);
+int64_t plm_frames_d2h_bytes(const plm_frames *fr);
 
 /* ---- device-resident entry points (descriptor database shards, multi-GPU merge) -------------- */
 /* All *_dev pointers are device pointers on the context's device; descriptor rows are contiguous

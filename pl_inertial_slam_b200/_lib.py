@@ -43,6 +43,31 @@ class DevGridArgs(C.Structure):
                 ("grid_cols", C.c_int32), ("is_lines", C.c_int32), ("best_lr", C.c_int32), ("win", C.c_int32 * 4)]
 
 
+class FrameRec(C.Structure):
+    _fields_ = [("desc_pl", C.c_int64), ("desc_pr", C.c_int64), ("desc_ll", C.c_int64), ("desc_lr", C.c_int64),
+                ("kp_l", C.c_int64), ("kp_r", C.c_int64), ("ln_l", C.c_int64), ("ln_r", C.c_int64),
+                ("n_pl", C.c_int32), ("n_pr", C.c_int32), ("n_ll", C.c_int32), ("n_lr", C.c_int32)]
+
+
+class FrameConfig(C.Structure):
+    _fields_ = [("inv_width", C.c_double), ("inv_height", C.c_double), ("grid_rows", C.c_int32),
+                ("grid_cols", C.c_int32), ("matching_s_ws", C.c_int32), ("best_lr", C.c_int32),
+                ("min_ratio_12p", C.c_double), ("min_ratio_12l", C.c_double), ("line_sim_th", C.c_double),
+                ("max_dist_epip", C.c_double), ("min_disp", C.c_double), ("line_horiz_th", C.c_double),
+                ("stereo_overlap_th", C.c_double), ("ls_min_disp_ratio", C.c_double), ("cam_b", C.c_double),
+                ("cam_fx", C.c_double), ("cam_cx", C.c_double), ("cam_cy", C.c_double)]
+
+
+class FramesOut(C.Structure):
+    _fields_ = [(n, vp) for n in ("stereo_m12_p", "stereo_m12_l", "kept_p", "kept_l", "pt_disp", "pt_P", "ls_disp",
+                                  "ls_sP", "ls_eP", "ls_le", "f2f_m12_p", "f2f_m12_l", "counts")]
+
+
+FRAME_REC_DTYPE = np.dtype([("desc_pl", "<i8"), ("desc_pr", "<i8"), ("desc_ll", "<i8"), ("desc_lr", "<i8"),
+                            ("kp_l", "<i8"), ("kp_r", "<i8"), ("ln_l", "<i8"), ("ln_r", "<i8"), ("n_pl", "<i4"),
+                            ("n_pr", "<i4"), ("n_ll", "<i4"), ("n_lr", "<i4")])
+assert FRAME_REC_DTYPE.itemsize == C.sizeof(FrameRec)
+
 PAIR_JOB_DTYPE = np.dtype([("off1", "<i8"), ("off2", "<i8"), ("off_m", "<i8"), ("n1", "<i4"), ("n2", "<i4")])
 GRID_JOB_DTYPE = np.dtype([("off_coords", "<i8"), ("off1", "<i8"), ("off2", "<i8"), ("off_cell_start", "<i8"),
                            ("off_cell_items", "<i8"), ("off_dirs2", "<i8"), ("off_m", "<i8"), ("n1", "<i4"),
@@ -87,6 +112,14 @@ SIGNATURES = {
     "plm_batch_fetch": (C.c_int, [vp, vp, vp]),
     "plm_batch_h2d_bytes": (C.c_int64, [vp]),
     "plm_batch_d2h_bytes": (C.c_int64, [vp]),
+    "plm_frames_create": (C.c_int, [vp, C.POINTER(vp)]),
+    "plm_frames_destroy": (C.c_int, [vp]),
+    "plm_frames_upload": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int,
+                                    C.POINTER(FrameConfig)]),
+    "plm_frames_run": (C.c_int, [vp]),
+    "plm_frames_fetch": (C.c_int, [vp, C.POINTER(FramesOut)]),
+    "plm_frames_h2d_bytes": (C.c_int64, [vp]),
+    "plm_frames_d2h_bytes": (C.c_int64, [vp]),
     "plm_dev_knn2": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_uint64, vp]),
     "plm_dev_top2_merge": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
     "plm_dev_nnr_accept": (C.c_int, [vp, vp, C.c_int, C.c_float, vp, vp]),

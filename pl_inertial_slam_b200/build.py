@@ -38,7 +38,7 @@ def _stale(target: str, sources) -> bool:
 
 
 def cuda_sources():
-    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".inl"))]
     out.append(os.path.join(HERE, "..", "include", "plmatch.h"))
     return out
 

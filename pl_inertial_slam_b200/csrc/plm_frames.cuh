@@ -385,6 +385,14 @@ __host__ __device__ inline size_t f2f_smem(int cap1, int cap2) {
            grid_align16(static_cast<size_t>(cap1) * 4);
 }
 
+// 128-bit shared-memory load the compiler may not hoist or cache (other warps update the words).
+__device__ __forceinline__ uint4 lds_volatile_v4(const uint32_t *p) {
+    uint4 v;
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ bool nnr_accept_f32(uint32_t k0, uint32_t k1, float nnr) {
     const float d0 = static_cast<float>(static_cast<int>(k0 >> F2F_KEY_BITS));
     const float d1 = static_cast<float>(static_cast<int>(k1 >> F2F_KEY_BITS));
@@ -451,8 +459,10 @@ f2f_match_kernel(const F2FJob *__restrict__ jobs, int best_lr) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) m0[v] = __reduce_min_sync(0xFFFFFFFFu, ck[v]);
                 // column top-2 (d << 22 | i1): only warps that beat the current second best take the slow path
-                const uint4 sec = *reinterpret_cast<const volatile uint4 *>(csecond + j);
-                if (m0[0] < sec.x || m0[1] < sec.y || m0[2] < sec.z || m0[3] < sec.w) {
+                // The vote makes the branch warp-uniform even if lanes happened to read different snapshots
+                // of the (concurrently shrinking) thresholds; a stale larger value only costs a slow path.
+                const uint4 sec = lds_volatile_v4(csecond + j);
+                if (__any_sync(0xFFFFFFFFu, m0[0] < sec.x || m0[1] < sec.y || m0[2] < sec.z || m0[3] < sec.w)) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, ck[v] == m0[v] ? KEY32_ABSENT : ck[v]);

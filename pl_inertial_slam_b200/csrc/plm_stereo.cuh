@@ -13,6 +13,18 @@ __device__ __forceinline__ double std_max(double a, double b) { return (a < b) ?
 
 // StereoFrame::matchStereoPoints gates (stvo-pl/src/stereoFrame.cpp:168-171): float subtraction,
 // |dy| <= maxDistEpip and disparity >= minDisp compared in double.
+__device__ __forceinline__ bool stereo_point_gate(float2 l, float2 r, double max_dist_epip, double min_disp, double &disp) {
+    const float dy = __fsub_rn(l.y, r.y);
+    if (static_cast<double>(fabsf(dy)) <= max_dist_epip) {
+        const double d = static_cast<double>(__fsub_rn(l.x, r.x));
+        if (d >= min_disp) {
+            disp = d;
+            return true;
+        }
+    }
+    return false;
+}
+
 __global__ void stereo_filter_points_kernel(const float2 *__restrict__ kp_l, const float2 *__restrict__ kp_r, int n2,
                                             const int32_t *__restrict__ m12, int n1, double max_dist_epip,
                                             double min_disp, uint8_t *__restrict__ keep, double *__restrict__ disp,
@@ -22,17 +34,7 @@ __global__ void stereo_filter_points_kernel(const float2 *__restrict__ kp_l, con
     if (i1 < n1) {
         double dsp = 0.0;
         const int i2 = m12[i1];
-        if (i2 >= 0 && i2 < n2) {
-            const float2 l = kp_l[i1], r = kp_r[i2];
-            const float dy = __fsub_rn(l.y, r.y);
-            if (static_cast<double>(fabsf(dy)) <= max_dist_epip) {
-                const double d = static_cast<double>(__fsub_rn(l.x, r.x));
-                if (d >= min_disp) {
-                    kept = true;
-                    dsp = d;
-                }
-            }
-        }
+        if (i2 >= 0 && i2 < n2) kept = stereo_point_gate(kp_l[i1], kp_r[i2], max_dist_epip, min_disp, dsp);
         keep[i1] = kept ? 1 : 0;
         disp[i1] = dsp;
     }
@@ -65,6 +67,35 @@ __device__ __forceinline__ double line_overlap_stereo(double spl_obs, double epl
 
 // StereoFrame::matchStereoLines gates (stereoFrame.cpp:366-385) with filterLineSegmentDisparity
 // (:416-426).  sp_r is overwritten before ep_r is interpolated, as in the reference (:377-378).
+// disp_s / disp_e come back as computed (including the -1 / -1 rejection marker).
+__device__ __forceinline__ bool stereo_line_gate(float4 l, float4 r, double min_disp, double line_horiz_th,
+                                                 double stereo_overlap_th, double ls_min_disp_ratio, double &disp_s,
+                                                 double &disp_e) {
+    const double sp_l0 = l.x, sp_l1 = l.y, ep_l0 = l.z, ep_l1 = l.w;
+    double sp_r0 = r.x, sp_r1 = r.y, ep_r0 = r.z, ep_r1 = r.w;
+    const double overlap = line_overlap_stereo(sp_l1, ep_l1, sp_r1, ep_r1, line_horiz_th);
+    {
+        const double a = __dmul_rn(sp_r0, __dsub_rn(sp_l1, ep_r1));
+        const double b = __dmul_rn(ep_r0, __dsub_rn(sp_r1, sp_l1));
+        sp_r0 = __ddiv_rn(__dadd_rn(a, b), __dsub_rn(sp_r1, ep_r1));
+        sp_r1 = sp_l1;
+    }
+    {
+        const double a = __dmul_rn(sp_r0, __dsub_rn(ep_l1, ep_r1));
+        const double b = __dmul_rn(ep_r0, __dsub_rn(sp_r1, ep_l1));
+        ep_r0 = __ddiv_rn(__dadd_rn(a, b), __dsub_rn(sp_r1, ep_r1));
+        ep_r1 = ep_l1;
+    }
+    disp_s = __dsub_rn(sp_l0, sp_r0);
+    disp_e = __dsub_rn(ep_l0, ep_r0);
+    if (__ddiv_rn(std_min(disp_s, disp_e), std_max(disp_s, disp_e)) < ls_min_disp_ratio) {
+        disp_s = -1.0;
+        disp_e = -1.0;
+    }
+    return disp_s >= min_disp && disp_e >= min_disp && fabs(__dsub_rn(sp_l1, ep_l1)) > line_horiz_th &&
+           fabs(__dsub_rn(sp_r1, ep_r1)) > line_horiz_th && overlap > stereo_overlap_th;
+}
+
 __global__ void stereo_filter_lines_kernel(const float4 *__restrict__ ln_l, const float4 *__restrict__ ln_r, int n2,
                                            const int32_t *__restrict__ m12, int n1, double min_disp,
                                            double line_horiz_th, double stereo_overlap_th, double ls_min_disp_ratio,
@@ -75,32 +106,9 @@ __global__ void stereo_filter_lines_kernel(const float4 *__restrict__ ln_l, cons
     if (i1 < n1) {
         double disp_s = 0.0, disp_e = 0.0;
         const int i2 = m12[i1];
-        if (i2 >= 0 && i2 < n2) {
-            const float4 l = ln_l[i1], r = ln_r[i2];
-            const double sp_l0 = l.x, sp_l1 = l.y, ep_l0 = l.z, ep_l1 = l.w;
-            double sp_r0 = r.x, sp_r1 = r.y, ep_r0 = r.z, ep_r1 = r.w;
-            const double overlap = line_overlap_stereo(sp_l1, ep_l1, sp_r1, ep_r1, line_horiz_th);
-            {
-                const double a = __dmul_rn(sp_r0, __dsub_rn(sp_l1, ep_r1));
-                const double b = __dmul_rn(ep_r0, __dsub_rn(sp_r1, sp_l1));
-                sp_r0 = __ddiv_rn(__dadd_rn(a, b), __dsub_rn(sp_r1, ep_r1));
-                sp_r1 = sp_l1;
-            }
-            {
-                const double a = __dmul_rn(sp_r0, __dsub_rn(ep_l1, ep_r1));
-                const double b = __dmul_rn(ep_r0, __dsub_rn(sp_r1, ep_l1));
-                ep_r0 = __ddiv_rn(__dadd_rn(a, b), __dsub_rn(sp_r1, ep_r1));
-                ep_r1 = ep_l1;
-            }
-            disp_s = __dsub_rn(sp_l0, sp_r0);
-            disp_e = __dsub_rn(ep_l0, ep_r0);
-            if (__ddiv_rn(std_min(disp_s, disp_e), std_max(disp_s, disp_e)) < ls_min_disp_ratio) {
-                disp_s = -1.0;
-                disp_e = -1.0;
-            }
-            kept = disp_s >= min_disp && disp_e >= min_disp && fabs(__dsub_rn(sp_l1, ep_l1)) > line_horiz_th &&
-                   fabs(__dsub_rn(sp_r1, ep_r1)) > line_horiz_th && overlap > stereo_overlap_th;
-        }
+        if (i2 >= 0 && i2 < n2)
+            kept = stereo_line_gate(ln_l[i1], ln_r[i2], min_disp, line_horiz_th, stereo_overlap_th, ls_min_disp_ratio,
+                                    disp_s, disp_e);
         keep[i1] = kept ? 1 : 0;
         disp_se[2 * i1] = disp_s;
         disp_se[2 * i1 + 1] = disp_e;

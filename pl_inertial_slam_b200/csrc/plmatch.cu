@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -14,6 +15,7 @@
 #include <vector>
 
 #include "plm_common.cuh"
+#include "plm_frames.cuh"
 #include "plm_grid.cuh"
 #include "plm_knn2.cuh"
 #include "plm_micro.cuh"
@@ -1613,3 +1615,6 @@ PLM_API int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts) {
     CU_TRY(cudaStreamSynchronize(s));
     return PLM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+#include "plm_frames_api.inl"
