@@ -70,12 +70,12 @@ def frame_latency(ctx) -> dict:
     return out
 
 
-def replay_throughput(ctx, n_frames: int) -> dict:
+def replay_throughput(ctx, n_frames: int, rp=None) -> dict:
     """Config 3: n_frames stereo frames, stereo matchGrid (points + lines) and temporal match (points +
     lines) per frame, one launch per stage."""
     import torch
     t0 = time.perf_counter()
-    rp = synth.make_replay(synth.SEED0 + 3, n_frames)
+    rp = synth.make_replay(synth.SEED0 + 3, n_frames) if rp is None else rp
     gen_s = time.perf_counter() - t0
     gjobs = replay.stereo_grid_jobs(rp)
     tjobs = replay.temporal_match_jobs(rp)
@@ -125,6 +125,97 @@ def replay_throughput(ctx, n_frames: int) -> dict:
         "stage_order": "stereo matchGrid(points, lines) batch, then temporal match(points, lines) batch; stages "
                        "use the full per-frame descriptor sets (no stereo-filter compaction in between)",
     }
+
+
+def replay_pipeline(ctx, n_frames: int, rp=None) -> dict:
+    """Config 3 through the device-resident frame pipeline (plm_frames_*): raw keypoints / segments /
+    descriptors in, per frame the stereo drivers (grid build, matchGrid, gates, compaction, back-projection)
+    and the frame-to-frame match on the compacted descriptors; two launches per feature type for the replay."""
+    import torch
+    from .frames import FrameConfig, FramePipeline, replay_frame_records
+    rp = synth.make_replay(synth.SEED0 + 3, n_frames) if rp is None else rp
+    kp, ln, rec = replay_frame_records(rp)
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    arena, kp_t, ln_t = pin(rp.arena), pin(kp), pin(ln)
+    cfg = FrameConfig()
+    pipe = FramePipeline(ctx)
+    pipe.upload(arena, kp_t, ln_t, rec, cfg)
+    out = pipe.alloc_outputs(pinned=True)
+    pipe.run(); pipe.fetch(out)  # warm (allocations, attribute sets)
+    launches0 = ctx.launch_count
+
+    def e2e():
+        pipe.upload(arena, kp_t, ln_t, rec, cfg)
+        pipe.run()
+        pipe.fetch(out)
+
+    e2e()
+    t = time.perf_counter(); e2e(); e2e_s = time.perf_counter() - t
+    per_run = ctx.launch_count - launches0
+    ctx.synchronize()
+    reps = 5
+    t = time.perf_counter()
+    for _ in range(reps):
+        pipe.run()
+    ctx.synchronize()
+    dev_s = (time.perf_counter() - t) / reps
+    counts = out["counts"].numpy()
+    res = {
+        "frames": n_frames,
+        "device_resident": {"frames_per_s": n_frames / dev_s, "ms_total": dev_s * 1e3},
+        "e2e": {"frames_per_s": n_frames / e2e_s, "ms_total": e2e_s * 1e3, "h2d_bytes": pipe.h2d_bytes,
+                "d2h_bytes": pipe.d2h_bytes,
+                "note": "pinned host arenas (descriptors, keypoints, segments) -> device, both stages, every output "
+                        "(match vectors, kept lists, disparities, 3-D points / lines, counts) back to pinned host"},
+        "mean_kept_points": float(counts[:, 1].mean()), "mean_kept_lines": float(counts[:, 3].mean()),
+        "mean_f2f_point_matches": float(counts[1:, 4].mean()) if n_frames > 1 else 0.0,
+        "frames_with_stereo_matches": int((counts[:, 0] > 0).sum()),
+        "gpu_launches": per_run // 2,
+        "stages": "stereo_frame_kernel (points), stereo_frame_kernel (lines), f2f_match_kernel (points), "
+                  "f2f_match_kernel (lines); temporal matching runs on the stereo-filtered descriptors as in "
+                  "stereoFrameHandler.cpp:158-207",
+    }
+    pipe.close()
+    return res
+
+
+def replay_pipeline_cpu_baseline(n_frames: int) -> dict:
+    """The same pipeline on the host cores: frame-parallel thread pool over the C restatement of the stereo
+    drivers, then of StVO::match on the compacted descriptors."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from .frames import FrameConfig, replay_frame_records
+    cores = len(os.sched_getaffinity(0))
+    rp = synth.make_replay(synth.SEED0 + 3, n_frames)
+    kp, ln, rec = replay_frame_records(rp)
+    cfg = FrameConfig()
+    port = oracle.port
+    port.lib  # load before the pool starts
+
+    def stereo(f):
+        r = rec[f]
+        sl = lambda off, n, a: a[int(off):int(off) + int(n)]  # noqa: E731
+        dpl = sl(r["desc_pl"], r["n_pl"], rp.arena); dll = sl(r["desc_ll"], r["n_ll"], rp.arena)
+        p = port.stereo_points(sl(r["kp_l"], r["n_pl"], kp), dpl, sl(r["kp_r"], r["n_pr"], kp),
+                               sl(r["desc_pr"], r["n_pr"], rp.arena), cfg.inv_width, cfg.inv_height, cfg.cam)
+        q = port.stereo_lines(sl(r["ln_l"], r["n_ll"], ln), dll, sl(r["ln_r"], r["n_lr"], ln),
+                              sl(r["desc_lr"], r["n_lr"], rp.arena), cfg.inv_width, cfg.inv_height, cfg.cam)
+        return np.ascontiguousarray(dpl[p["kept_i1"]]), np.ascontiguousarray(dll[q["kept_i1"]])
+
+    def f2f(f):
+        for k in (0, 1):
+            a, b = comp[f - 1][k], comp[f][k]
+            if len(a) >= 2 and len(b) >= 2:
+                port.match(a, b, 0.9, True)
+
+    t = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        comp = list(ex.map(stereo, range(n_frames)))
+        list(ex.map(f2f, range(1, n_frames)))
+    dt = time.perf_counter() - t
+    return {"frames_per_s": n_frames / dt, "frames": n_frames, "cores": cores, "kind": "port",
+            "sample": f"{n_frames} frames, frame-parallel thread pool over the C restatement of the stereo drivers "
+                      "and of StVO::match on the compacted descriptors (scalar SWAR popcount)"}
 
 
 def replay_cpu_baseline(n_frames: int, seconds: float = 8.0) -> dict:
@@ -235,7 +326,10 @@ def run(ctx, args) -> dict:
     except Exception as e:  # noqa: BLE001
         out["map_to_frame"] = {"error": repr(e)}
     n = int(os.environ.get("PLM_REPLAY_FRAMES", "10000"))
-    out["replay"] = replay_throughput(ctx, n)
+    rp = synth.make_replay(synth.SEED0 + 3, n)
+    out["replay"] = replay_pipeline(ctx, n, rp)
+    out["replay_stage_batches"] = replay_throughput(ctx, n, rp)
     if not args.no_cpu_baseline:
-        out["replay"]["cpu_baseline"] = replay_cpu_baseline(min(n, 200))
+        out["replay"]["cpu_baseline"] = replay_pipeline_cpu_baseline(min(n, 200))
+        out["replay_stage_batches"]["cpu_baseline"] = replay_cpu_baseline(min(n, 200))
     return out

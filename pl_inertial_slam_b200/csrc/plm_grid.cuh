@@ -528,17 +528,29 @@ grid_match_chunked_kernel(GridJob job, GridParams gp) {
 
 // cta_min[c][i2] <- min(seed[i2], min over c' < c of cta_min[c'][i2]); col_min[i2] = overall minimum.
 // seed (may be null) carries the minima of lower-ranked database shards (multi-GPU).
+// One WARP per column: lanes take 32 consecutive CTAs at a time and scan them with shuffles, so the
+// dependent chain is n_cta / 32 steps long instead of n_cta (the map-sized launch has ~400 CTAs).
 __global__ void grid_scan_kernel(uint16_t *__restrict__ cta_min, int n_cta, int n2,
                                  const uint16_t *__restrict__ seed, uint16_t *__restrict__ col_min) {
-    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int i2 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i2 >= n2) return;
-    uint16_t run = seed ? seed[i2] : D_INF;
-    for (int c = 0; c < n_cta; ++c) {
-        const uint16_t t = cta_min[static_cast<size_t>(c) * n2 + i2];
-        cta_min[static_cast<size_t>(c) * n2 + i2] = run;
-        run = min(run, t);
+    uint32_t run = seed ? seed[i2] : D_INF;
+    for (int c0 = 0; c0 < n_cta; c0 += 32) {
+        const int c = c0 + lane;
+        const uint32_t t = (c < n_cta) ? cta_min[static_cast<size_t>(c) * n2 + i2] : D_INF;
+        uint32_t incl = t;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+            if (lane >= s) incl = min(incl, v);
+        }
+        uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane == 0) excl = D_INF;
+        if (c < n_cta) cta_min[static_cast<size_t>(c) * n2 + i2] = static_cast<uint16_t>(min(run, excl));
+        run = min(run, __shfl_sync(0xFFFFFFFFu, incl, 31));
     }
-    if (col_min) col_min[i2] = run;
+    if (col_min && lane == 0) col_min[i2] = static_cast<uint16_t>(run);
 }
 
 // m21[i2] = row of the best live pair (or -1), from the 64-bit keys of the chunked launch.

@@ -187,9 +187,41 @@ __device__ __forceinline__ void knn2_merge_body(const KnnTask &t, int q, float n
     }
 }
 
-__global__ void knn2_merge_kernel(const KnnTaskPair tasks, float nnr, int do_accept) {
-    const KnnTask &t = tasks.t[blockIdx.y];
+__global__ void knn2_merge_kernel(const KnnTaskPair tasks, int task0, float nnr, int do_accept) {
+    const KnnTask &t = tasks.t[task0 + blockIdx.y];
     knn2_merge_body(t, blockIdx.x * blockDim.x + threadIdx.x, nnr, do_accept != 0);
+}
+
+// Wide form for many partials per query (a short query side against a long train side, e.g. the 21
+// direction of the map fallback: 600 queries x ~180 workers): one WARP per query, lanes stride over the
+// workers and finish with a shuffle butterfly.  Same lexicographic min-2, same acceptance.
+__global__ void knn2_merge_wide_kernel(const KnnTaskPair tasks, int task0, float nnr, int do_accept) {
+    const KnnTask &t = tasks.t[task0 + blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= t.n1) return;
+    unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
+    for (int p = lane; p < t.n_workers; p += 32) {
+        const ulonglong2 v = t.part[static_cast<size_t>(p) * t.n1 + q];
+        top2_insert(b0, b1, v.x);
+        top2_insert(b0, b1, v.y);
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const unsigned long long o0 = __shfl_xor_sync(0xFFFFFFFFu, b0, s), o1 = __shfl_xor_sync(0xFFFFFFFFu, b1, s);
+        top2_insert(b0, b1, o0);
+        top2_insert(b0, b1, o1);
+    }
+    if (lane != 0) return;
+    if (t.top2) t.top2[q] = make_ulonglong2(b0, b1);
+    if (do_accept && b1 != KEY64_ABSENT) {
+        const float d0 = static_cast<float>(static_cast<int>(b0 >> 32));
+        const float d1 = static_cast<float>(static_cast<int>(b1 >> 32));
+        if (d0 < __fmul_rn(d1, nnr)) {
+            t.m[q] = static_cast<int32_t>(b0 & 0xFFFFFFFFull);
+            if (t.count) atomicAdd(t.count, 1);
+        }
+    }
 }
 
 // Batched form: merge_map[cta] = (task, first query of this CTA).

@@ -248,13 +248,25 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
 }
 
 int launch_knn_merge(plm_ctx *ctx, const plm::KnnTaskPair &tp, int n_tasks, float nnr, int do_accept) {
-    int n = 0;
-    for (int i = 0; i < n_tasks; ++i) n = std::max(n, tp.t[i].n1);
-    if (n == 0) return PLM_OK;
-    const dim3 grid((n + 127) / 128, n_tasks);
-    plm::knn2_merge_kernel<<<grid, 128, 0, ctx->stream>>>(tp, nnr, do_accept);
-    ctx->launches++;
-    CU_TRY(cudaGetLastError());
+    // few queries with many partials each (a short query side against a long train side) get one warp per
+    // query; the two directions of match() can differ, so the choice is per task
+    auto wide = [&](int i) { return tp.t[i].n_workers >= 32 && tp.t[i].n1 <= 16384; };
+    const bool split = n_tasks == 2 && wide(0) != wide(1);
+    for (int first = 0; first < n_tasks; first += split ? 1 : n_tasks) {
+        const int cnt = split ? 1 : n_tasks;
+        int n = 0;
+        for (int i = first; i < first + cnt; ++i) n = std::max(n, tp.t[i].n1);
+        if (n == 0) continue;
+        if (wide(first)) {
+            const dim3 grid((n + 3) / 4, cnt);
+            plm::knn2_merge_wide_kernel<<<grid, 128, 0, ctx->stream>>>(tp, first, nnr, do_accept);
+        } else {
+            const dim3 grid((n + 127) / 128, cnt);
+            plm::knn2_merge_kernel<<<grid, 128, 0, ctx->stream>>>(tp, first, nnr, do_accept);
+        }
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
     return PLM_OK;
 }
 
@@ -772,7 +784,7 @@ int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams g
         plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
-        plm::grid_scan_kernel<<<(job.n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, job.n2, nullptr, nullptr);
+        plm::grid_scan_kernel<<<(job.n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, job.n2, nullptr, nullptr);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
     }
@@ -987,7 +999,7 @@ PLM_API int plm_dev_grid_colmin(plm_ctx *ctx, const plm_dev_grid_args *a, uint16
     plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
-    plm::grid_scan_kernel<<<(a->n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, nullptr, col_min_dev);
+    plm::grid_scan_kernel<<<(a->n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, nullptr, col_min_dev);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;
@@ -1008,7 +1020,7 @@ PLM_API int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const u
         plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
-        plm::grid_scan_kernel<<<(a->n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, seed_dev, nullptr);
+        plm::grid_scan_kernel<<<(a->n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, seed_dev, nullptr);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
     }
