@@ -261,6 +261,15 @@ int plm_frames_upload(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows,
 int plm_frames_run(plm_frames *fr);
 /* Device -> host copy of the requested outputs + stream sync. */
 int plm_frames_fetch(plm_frames *fr, const plm_frames_out *out);
+/* upload + run + fetch as ONE pipelined call: the frames are cut into chunks of chunk_frames consecutive
+ * frames (<= 0: 256) and the chunks flow through three streams -- host -> device copy of chunk k + 1, the
+ * four launches of chunk k and the device -> host copy of chunk k - 1 overlap (both copy engines and the SMs
+ * busy at once), and the host-side preparation of a chunk overlaps with the device work of the previous ones.
+ * Arenas and outputs should be pinned host memory (pageable memory still works, without the overlap).
+ * Returns when every requested output is in host memory. */
+int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows, const float *kp_arena,
+                       int64_t n_kp, const float *ln_arena, int64_t n_ln, const plm_frame_rec *frames,
+                       int n_frames, const plm_frame_config *cfg, const plm_frames_out *out, int chunk_frames);
 int64_t plm_frames_h2d_bytes(const plm_frames *fr);
 int64_t plm_frames_d2h_bytes(const plm_frames *fr);
 
@@ -324,7 +333,9 @@ int plm_db_knn2(plm_db *db, const uint8_t *q, int nq, size_t step, uint64_t idx_
  *   "knn_variant"  -1 = automatic (default), 0 = plain 8-POPC Hamming, 1 = carry-save 5-POPC,
  *                  2 = carry-save 4-POPC with blocked top-2 update.
  *   "grid_cluster" 1 = single matchGrid calls run on an 8-CTA thread-block cluster (default),
- *                  0 = on one CTA. */
+ *                  0 = on one CTA.
+ *   "frames_pairs_p" / "frames_pairs_l"  candidate slots per query row the frame pipeline's pair-list
+ *                  matcher is sized for (default 8 / 0; 0 = always use the chunk phases). */
 int plm_set_option(const char *key, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

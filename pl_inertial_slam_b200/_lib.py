@@ -116,6 +116,8 @@ SIGNATURES = {
     "plm_frames_destroy": (C.c_int, [vp]),
     "plm_frames_upload": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int,
                                     C.POINTER(FrameConfig)]),
+    "plm_frames_process": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int,
+                                     C.POINTER(FrameConfig), C.POINTER(FramesOut), C.c_int]),
     "plm_frames_run": (C.c_int, [vp]),
     "plm_frames_fetch": (C.c_int, [vp, C.POINTER(FramesOut)]),
     "plm_frames_h2d_bytes": (C.c_int64, [vp]),

@@ -44,11 +44,14 @@ struct StereoJob {
 
 struct StereoCaps {
     int cap_l, cap_r, cap_items, warps;
+    int cap_pairs, pad_; // candidate slots the pair-list form can hold (more -> chunk phases)
 };
 
 __host__ __device__ inline size_t stereo_frame_smem(const StereoCaps &c, int n_cells, bool lines) {
-    size_t b = grid_align16(static_cast<size_t>(c.warps) * c.cap_r * 2);   // wmin
-    b += grid_align16(static_cast<size_t>(c.cap_r) * 4);                   // m21key
+    // scratch of the matcher: pair-list arrays, or (fallback) wmin + m21key of the chunk phases
+    const size_t chunk = grid_align16(static_cast<size_t>(c.warps) * c.cap_r * 2) + grid_align16(static_cast<size_t>(c.cap_r) * 4);
+    const size_t pairs = pairlist_smem(c.cap_pairs, c.cap_l, c.cap_r);
+    size_t b = chunk > pairs ? chunk : pairs;
     b += grid_align16(static_cast<size_t>(n_cells + 1) * 4);               // cell ends -> cell starts
     b += grid_align16(static_cast<size_t>(c.cap_items) * 4);               // cell items
     b += static_cast<size_t>(c.cap_r) * 32;                                // right descriptors
@@ -95,41 +98,6 @@ __device__ __forceinline__ void back_projection(const FrameCfg &c, double u, dou
     P[2] = __dmul_rn(bd, c.cam_fx);
 }
 
-// Exclusive-to-inclusive block scan of v[0..n) in shared memory (n ~ 3k cells): thread t owns a
-// contiguous strip.  s_part needs blockDim.x / 32 + 1 ints.
-__device__ __forceinline__ void block_inclusive_scan(int32_t *v, int n, int32_t *s_part) {
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + T - 1) / T;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += v[i];
-    int incl = sum;
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, s);
-        if (lane >= s) incl += t;
-    }
-    if (lane == 31) s_part[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int nw = T >> 5;
-        int w = (lane < nw) ? s_part[lane] : 0;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, w, s);
-            if (lane >= s) w += t;
-        }
-        if (lane < nw) s_part[lane] = w; // inclusive over warps
-    }
-    __syncthreads();
-    int run = incl - sum + (warp ? s_part[warp - 1] : 0);
-    for (int i = lo; i < hi; ++i) {
-        run += v[i];
-        v[i] = run;
-    }
-    __syncthreads();
-}
-
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 stereo_frame_kernel(const StereoJob *__restrict__ jobs, const FrameCfg cfg, const StereoCaps caps) {
@@ -154,8 +122,14 @@ stereo_frame_kernel(const StereoJob *__restrict__ jobs, const FrameCfg cfg, cons
     }
 
     unsigned char *p = smem_raw;
-    uint16_t *wmin = reinterpret_cast<uint16_t *>(p); p += grid_align16(static_cast<size_t>(W) * caps.cap_r * 2);
-    uint32_t *m21key = reinterpret_cast<uint32_t *>(p); p += grid_align16(static_cast<size_t>(caps.cap_r) * 4);
+    unsigned char *scratch = p;
+    {
+        const size_t chunk = grid_align16(static_cast<size_t>(W) * caps.cap_r * 2) + grid_align16(static_cast<size_t>(caps.cap_r) * 4);
+        const size_t pairs = pairlist_smem(caps.cap_pairs, caps.cap_l, caps.cap_r);
+        p += chunk > pairs ? chunk : pairs;
+    }
+    uint16_t *wmin = reinterpret_cast<uint16_t *>(scratch);
+    uint32_t *m21key = reinterpret_cast<uint32_t *>(scratch + grid_align16(static_cast<size_t>(W) * caps.cap_r * 2));
     int32_t *cs = reinterpret_cast<int32_t *>(p); p += grid_align16(static_cast<size_t>(n_cells + 1) * 4);
     int32_t *ci = reinterpret_cast<int32_t *>(p); p += grid_align16(static_cast<size_t>(caps.cap_items) * 4);
     uint4 *sd_r = reinterpret_cast<uint4 *>(p); p += static_cast<size_t>(caps.cap_r) * 32;
@@ -166,8 +140,6 @@ stereo_frame_kernel(const StereoJob *__restrict__ jobs, const FrameCfg cfg, cons
     // ---- stage + initialise ----------------------------------------------------------------------------
     stage_bytes(reinterpret_cast<unsigned char *>(sd_r), sj.d_r, static_cast<size_t>(n_r) * 32);
     for (int i = tid; i <= n_cells; i += THREADS) cs[i] = 0;
-    for (int i = tid; i < W * caps.cap_r; i += THREADS) wmin[i] = D_INF;
-    for (int i = tid; i < n_r; i += THREADS) m21key[i] = KEY32_ABSENT;
     for (int i = tid; i < n_l; i += THREADS) m12s[i] = -1; // matches_12 is a fresh vector (:156, :355)
     if (tid == 0) {
         s_count = 0;
@@ -262,42 +234,50 @@ stereo_frame_kernel(const StereoJob *__restrict__ jobs, const FrameCfg cfg, cons
     gp.ratio = cfg.ratio;
     gp.line_sim_th = cfg.line_sim_th;
 
-    const int rpw = (n_l + W - 1) / W;
-    const int row0 = min(n_l, warp * rpw), row1 = min(n_l, row0 + rpw);
-    uint16_t *mine = wmin + static_cast<size_t>(warp) * caps.cap_r;
-    if (gp.best_lr) {
-        chunk_minima(job, gp, row0, row1, mine, lane);
+    const PairArrays pa = pairlist_carve(scratch, caps.cap_pairs, caps.cap_l, caps.cap_r);
+    if (!pairlist_match(job, gp, pa, s_part, &s_count)) {
+        // too many candidate slots for the pair list (features piled up in a few cells): chunk phases
         __syncthreads();
-        for (int i2 = tid; i2 < n_r; i2 += THREADS) {
-            uint16_t run = D_INF;
-            for (int w = 0; w < W; ++w) {
-                const uint16_t t = wmin[static_cast<size_t>(w) * caps.cap_r + i2];
-                wmin[static_cast<size_t>(w) * caps.cap_r + i2] = run;
-                run = min(run, t);
-            }
-        }
+        for (int i = tid; i < W * caps.cap_r; i += THREADS) wmin[i] = D_INF;
+        for (int i = tid; i < n_r; i += THREADS) m21key[i] = KEY32_ABSENT;
         __syncthreads();
-    }
-    const int acc = chunk_match(job, gp, row0, row1, mine, lane, [&](int i2, int d, int i1) {
-        atomicMin(&m21key[i2], (static_cast<uint32_t>(d) << GRID_KEY_BITS) | static_cast<uint32_t>(i1));
-    });
-    if (lane == 0 && acc) atomicAdd(&s_count, acc);
-    __syncthreads();
-    if (gp.best_lr) {
-        int culled = 0;
-        for (int i1 = tid; i1 < n_l; i1 += THREADS) {
-            const int32_t i2 = m12s[i1];
-            if (i2 >= 0) {
-                const uint32_t k = m21key[i2];
-                const int back = (k == KEY32_ABSENT) ? -1 : static_cast<int>(k & ((1u << GRID_KEY_BITS) - 1));
-                if (back != i1) {
-                    m12s[i1] = -1;
-                    ++culled;
+        const int rpw = (n_l + W - 1) / W;
+        const int row0 = min(n_l, warp * rpw), row1 = min(n_l, row0 + rpw);
+        uint16_t *mine = wmin + static_cast<size_t>(warp) * caps.cap_r;
+        if (gp.best_lr) {
+            chunk_minima(job, gp, row0, row1, mine, lane);
+            __syncthreads();
+            for (int i2 = tid; i2 < n_r; i2 += THREADS) {
+                uint16_t run = D_INF;
+                for (int w = 0; w < W; ++w) {
+                    const uint16_t t = wmin[static_cast<size_t>(w) * caps.cap_r + i2];
+                    wmin[static_cast<size_t>(w) * caps.cap_r + i2] = run;
+                    run = min(run, t);
                 }
             }
+            __syncthreads();
         }
-        if (culled) atomicSub(&s_count, culled);
+        const int acc = chunk_match(job, gp, row0, row1, mine, lane, [&](int i2, int d, int i1) {
+            atomicMin(&m21key[i2], (static_cast<uint32_t>(d) << GRID_KEY_BITS) | static_cast<uint32_t>(i1));
+        });
+        if (lane == 0 && acc) atomicAdd(&s_count, acc);
         __syncthreads();
+        if (gp.best_lr) {
+            int culled = 0;
+            for (int i1 = tid; i1 < n_l; i1 += THREADS) {
+                const int32_t i2 = m12s[i1];
+                if (i2 >= 0) {
+                    const uint32_t k = m21key[i2];
+                    const int back = (k == KEY32_ABSENT) ? -1 : static_cast<int>(k & ((1u << GRID_KEY_BITS) - 1));
+                    if (back != i1) {
+                        m12s[i1] = -1;
+                        ++culled;
+                    }
+                }
+            }
+            if (culled) atomicSub(&s_count, culled);
+            __syncthreads();
+        }
     }
 
     // ---- geometry gates, compaction, back-projection (stereoFrame.cpp:160-183, :359-408) ----------------

@@ -1,18 +1,36 @@
 // Host side of the device-resident stereo-frame pipeline (plm_frames_*; included by plmatch.cu).
+//
+// Frames are handled in CHUNKS of consecutive frames.  A chunk is the unit of host preparation (validation,
+// shared-memory capacities, job tables), of the host -> device copies (the chunk's slice of every arena), of the
+// four launches and of the device -> host copies.  plm_frames_upload / run / fetch use one chunk for the
+// whole upload; plm_frames_process pipelines many chunks over three streams so that the copy engines and the
+// SMs work on different chunks at the same time.
+
+struct plm_frames_chunk {
+    int f0 = 0, f1 = 0; // frames [f0, f1)
+    plm::StereoCaps caps_p{1, 1, 1, 8, 8, 0}, caps_l{1, 1, 1, 4, 8, 0};
+    size_t smem_p = 0, smem_l = 0, smem_fp = 0, smem_fl = 0;
+};
 
 struct plm_frames {
     plm_ctx *ctx = nullptr;
     char *d_buf = nullptr;
     size_t d_cap = 0;
+    char *h_tab = nullptr; // pinned staging of the job tables (all chunks of one call)
+    size_t h_cap = 0;
     int n_frames = 0;
     int64_t NP = 0, NL = 0; // left point / line slots
+    int64_t n_rows = 0, n_kp = 0, n_ln = 0;
     plm::FrameCfg cfg;
     float nnr_p = 0.f, nnr_l = 0.f;
-    plm::StereoCaps caps_p{1, 1, 1, 8}, caps_l{1, 1, 1, 4};
-    size_t smem_p = 0, smem_l = 0, smem_fp = 0, smem_fl = 0;
+    std::vector<int64_t> lp_off, ll_off;
+    std::vector<plm_frames_chunk> chunks;
+    size_t o_desc = 0, o_kp = 0, o_ln = 0, o_cdesc_p = 0, o_cdesc_l = 0;
     size_t o_sjobs_p = 0, o_sjobs_l = 0, o_fjobs_p = 0, o_fjobs_l = 0;
     size_t o_m12_p = 0, o_m12_l = 0, o_kept_p = 0, o_kept_l = 0, o_pt_disp = 0, o_pt_P = 0, o_ls_disp = 0, o_ls_sP = 0,
            o_ls_eP = 0, o_ls_le = 0, o_f2f_p = 0, o_f2f_l = 0, o_counts = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> events;
     int64_t h2d = 0, d2h = 0;
     bool ready = false;
 
@@ -24,6 +42,25 @@ struct plm_frames {
         d_cap = 0;
         CU_TRY(cudaMalloc(reinterpret_cast<void **>(&d_buf), align_up(bytes, 1 << 20)));
         d_cap = align_up(bytes, 1 << 20);
+        return PLM_OK;
+    }
+    int ensure_tab(size_t bytes) {
+        if (bytes <= h_cap) return PLM_OK;
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        if (h_tab) CU_TRY(cudaFreeHost(h_tab));
+        h_tab = nullptr;
+        h_cap = 0;
+        CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_tab), align_up(bytes, 1 << 16), cudaHostAllocDefault));
+        h_cap = align_up(bytes, 1 << 16);
+        return PLM_OK;
+    }
+    int event(size_t i, cudaEvent_t *out) {
+        while (events.size() <= i) {
+            cudaEvent_t e;
+            CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            events.push_back(e);
+        }
+        *out = events[i];
         return PLM_OK;
     }
 };
@@ -70,6 +107,329 @@ int launch_f2f(plm_ctx *ctx, const plm::F2FJob *jobs, int n_jobs, int best_lr, s
     return PLM_OK;
 }
 
+// Argument checks, slot offsets, device layout and allocation for a whole call.
+int frames_layout(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows, const float *kp_arena, int64_t n_kp,
+                  const float *ln_arena, int64_t n_ln, const plm_frame_rec *frames, int n_frames,
+                  const plm_frame_config *c) {
+    if (!fr || !c) return fail(PLM_E_INVALID, "null frames / config");
+    if (n_rows < 0 || n_kp < 0 || n_ln < 0 || n_frames < 0) return fail(PLM_E_INVALID, "negative size");
+    if ((n_rows > 0 && !desc_arena) || (n_kp > 0 && !kp_arena) || (n_ln > 0 && !ln_arena) || (n_frames > 0 && !frames))
+        return fail(PLM_E_INVALID, "null pointer");
+    if (c->grid_rows <= 0 || c->grid_cols <= 0) return fail(PLM_E_GRID, "[GridStructure] invalid dimension");
+    if (static_cast<long long>(c->grid_rows) * c->grid_cols > (1 << 14)) return fail(PLM_E_UNSUPPORTED, "grid too large for the frame pipeline");
+    if (c->min_ratio_12p > 1.0) return fail(PLM_E_RATIO, plm_status_string(PLM_E_RATIO));
+    fr->ready = false;
+    fr->lp_off.assign(static_cast<size_t>(n_frames) + 1, 0);
+    fr->ll_off.assign(static_cast<size_t>(n_frames) + 1, 0);
+    for (int f = 0; f < n_frames; ++f) {
+        const plm_frame_rec &r = frames[f];
+        if (r.n_pl < 0 || r.n_pr < 0 || r.n_ll < 0 || r.n_lr < 0 || r.desc_pl < 0 || r.desc_pr < 0 || r.desc_ll < 0 ||
+            r.desc_lr < 0 || r.kp_l < 0 || r.kp_r < 0 || r.ln_l < 0 || r.ln_r < 0 || r.desc_pl + r.n_pl > n_rows ||
+            r.desc_pr + r.n_pr > n_rows || r.desc_ll + r.n_ll > n_rows || r.desc_lr + r.n_lr > n_rows ||
+            r.kp_l + r.n_pl > n_kp || r.kp_r + r.n_pr > n_kp || r.ln_l + r.n_ll > n_ln || r.ln_r + r.n_lr > n_ln)
+            return fail(PLM_E_INVALID, "frame record outside its arena");
+        if (r.n_pl > FRAMES_MAX_FEATURES || r.n_pr > FRAMES_MAX_FEATURES || r.n_ll > FRAMES_MAX_FEATURES ||
+            r.n_lr > FRAMES_MAX_FEATURES)
+            return fail(PLM_E_UNSUPPORTED, "more than 4096 features of one kind in a frame");
+        fr->lp_off[f + 1] = fr->lp_off[f] + r.n_pl;
+        fr->ll_off[f + 1] = fr->ll_off[f] + r.n_ll;
+    }
+    const int64_t NP = fr->lp_off[n_frames], NL = fr->ll_off[n_frames];
+    const size_t F = size_t(std::max(n_frames, 1));
+    Layout L;
+    fr->o_desc = L.add(size_t(n_rows) * 32);
+    fr->o_kp = L.add(size_t(n_kp) * 8);
+    fr->o_ln = L.add(size_t(n_ln) * 16);
+    fr->o_cdesc_p = L.add(size_t(NP) * 32);
+    fr->o_cdesc_l = L.add(size_t(NL) * 32);
+    fr->o_m12_p = L.add(size_t(NP) * 4);
+    fr->o_m12_l = L.add(size_t(NL) * 4);
+    fr->o_kept_p = L.add(size_t(NP) * 4);
+    fr->o_kept_l = L.add(size_t(NL) * 4);
+    fr->o_pt_disp = L.add(size_t(NP) * 8);
+    fr->o_pt_P = L.add(size_t(NP) * 24);
+    fr->o_ls_disp = L.add(size_t(NL) * 16);
+    fr->o_ls_sP = L.add(size_t(NL) * 24);
+    fr->o_ls_eP = L.add(size_t(NL) * 24);
+    fr->o_ls_le = L.add(size_t(NL) * 24);
+    fr->o_f2f_p = L.add(size_t(NP) * 4);
+    fr->o_f2f_l = L.add(size_t(NL) * 4);
+    fr->o_counts = L.add(F * 6 * 4);
+    fr->o_sjobs_p = L.add(F * sizeof(plm::StereoJob));
+    fr->o_sjobs_l = L.add(F * sizeof(plm::StereoJob));
+    fr->o_fjobs_p = L.add(F * sizeof(plm::F2FJob));
+    fr->o_fjobs_l = L.add(F * sizeof(plm::F2FJob));
+    int st = fr->ensure(L.total);
+    if (st != PLM_OK) return st;
+    if ((st = fr->ensure_tab(2 * F * (sizeof(plm::StereoJob) + sizeof(plm::F2FJob)))) != PLM_OK) return st;
+    fr->n_frames = n_frames;
+    fr->NP = NP;
+    fr->NL = NL;
+    fr->n_rows = n_rows;
+    fr->n_kp = n_kp;
+    fr->n_ln = n_ln;
+    fr->nnr_p = static_cast<float>(c->min_ratio_12p);
+    fr->nnr_l = static_cast<float>(c->min_ratio_12l);
+    plm::FrameCfg &g = fr->cfg;
+    g.inv_w = c->inv_width;
+    g.inv_h = c->inv_height;
+    g.ratio = c->min_ratio_12p;
+    g.line_sim_th = c->line_sim_th;
+    g.max_dist_epip = c->max_dist_epip;
+    g.min_disp = c->min_disp;
+    g.line_horiz_th = c->line_horiz_th;
+    g.stereo_overlap_th = c->stereo_overlap_th;
+    g.ls_min_disp_ratio = c->ls_min_disp_ratio;
+    g.cam_b = c->cam_b;
+    g.cam_fx = c->cam_fx;
+    g.cam_cx = c->cam_cx;
+    g.cam_cy = c->cam_cy;
+    g.grid_rows = c->grid_rows;
+    g.grid_cols = c->grid_cols;
+    g.matching_s_ws = c->matching_s_ws;
+    g.best_lr = c->best_lr ? 1 : 0;
+    fr->chunks.clear();
+    fr->h2d = fr->d2h = 0;
+    return PLM_OK;
+}
+
+// Host preparation of frames [f0, f1): shared-memory capacities, job tables into the pinned staging block
+// (at this chunk's rows), then the host -> device copies of the tables and of the chunk's arena slices on
+// `s`.  Appends the chunk to fr->chunks.
+int frames_chunk_in(plm_frames *fr, const uint8_t *desc_arena, const float *kp_arena, const float *ln_arena,
+                    const plm_frame_rec *frames, int f0, int f1, cudaStream_t s) {
+    plm_ctx *ctx = fr->ctx;
+    const plm::FrameCfg &g = fr->cfg;
+    plm_frames_chunk ch;
+    ch.f0 = f0;
+    ch.f1 = f1;
+    int cap_pl = 1, cap_pr = 1, cap_ll = 1, cap_lr = 1;
+    long long cap_items_l = 1;
+    const long long walk_max = static_cast<long long>(g.grid_rows) + g.grid_cols + 2;
+    // arena slices of the chunk, one running span per feature set (left / right sets usually live in
+    // different regions of an arena); overlapping spans are merged before copying
+    struct Span {
+        int64_t lo = INT64_MAX, hi = 0;
+        void add(int64_t off, int64_t n) {
+            if (n > 0) {
+                lo = std::min(lo, off);
+                hi = std::max(hi, off + n);
+            }
+        }
+    };
+    Span sd[4], sk[2], sn[2];
+    for (int f = f0; f < f1; ++f) {
+        const plm_frame_rec &r = frames[f];
+        cap_pl = std::max(cap_pl, r.n_pl);
+        cap_pr = std::max(cap_pr, r.n_pr);
+        cap_ll = std::max(cap_ll, r.n_ll);
+        cap_lr = std::max(cap_lr, r.n_lr);
+        long long items = 0;
+        for (int j = 0; j < r.n_lr; ++j) {
+            const float *l = ln_arena + 4 * (r.ln_r + j);
+            const long long n = line_walk_cells(double(l[0]) * g.inv_w, double(l[1]) * g.inv_h, double(l[2]) * g.inv_w,
+                                                double(l[3]) * g.inv_h);
+            if (n > walk_max) return fail(PLM_E_UNSUPPORTED, "line segment far outside the image (Bresenham walk too long)");
+            items += n;
+        }
+        cap_items_l = std::max(cap_items_l, items);
+        sd[0].add(r.desc_pl, r.n_pl);
+        sd[1].add(r.desc_pr, r.n_pr);
+        sd[2].add(r.desc_ll, r.n_ll);
+        sd[3].add(r.desc_lr, r.n_lr);
+        sk[0].add(r.kp_l, r.n_pl);
+        sk[1].add(r.kp_r, r.n_pr);
+        sn[0].add(r.ln_l, r.n_ll);
+        sn[1].add(r.ln_r, r.n_lr);
+    }
+    // the temporal jobs of frame f0 read frame f0 - 1: their capacities count too
+    int cap_fp = cap_pl, cap_fl = cap_ll;
+    if (f0 > 0) {
+        cap_fp = std::max(cap_fp, frames[f0 - 1].n_pl);
+        cap_fl = std::max(cap_fl, frames[f0 - 1].n_ll);
+    }
+    const int n_cells = g.grid_rows * g.grid_cols;
+    // pair-list capacity: a stereo window holds 2-3 point candidates per query on EuRoC-like frames; denser
+    // frames take the chunk phases inside the same kernel
+    const int pairs_p = std::min(g_frames_pairs_per_row[0] * cap_pl, 16384);
+    const int pairs_l = std::min(g_frames_pairs_per_row[1] * cap_ll, 16384);
+    ch.caps_p = plm::StereoCaps{cap_pl, cap_pr, cap_pr, FRAMES_THREADS_P / 32, pairs_p, 0};
+    ch.caps_l = plm::StereoCaps{cap_ll, cap_lr, static_cast<int>(cap_items_l), FRAMES_THREADS_L / 32, pairs_l, 0};
+    ch.smem_p = plm::stereo_frame_smem(ch.caps_p, n_cells, false);
+    ch.smem_l = plm::stereo_frame_smem(ch.caps_l, n_cells, true);
+    ch.smem_fp = plm::f2f_smem(cap_fp, cap_fp);
+    ch.smem_fl = plm::f2f_smem(cap_fl, cap_fl);
+    const size_t budget = ctx->smem_optin - 1024;
+    if (ch.smem_p > budget || ch.smem_l > budget || ch.smem_fp > budget || ch.smem_fl > budget)
+        return fail(PLM_E_UNSUPPORTED, "frame too large for shared memory");
+
+    // ---- job tables of the chunk ---------------------------------------------------------------------------
+    char *D = fr->d_buf;
+    const size_t F = size_t(std::max(fr->n_frames, 1));
+    plm::StereoJob *sp = reinterpret_cast<plm::StereoJob *>(fr->h_tab);
+    plm::StereoJob *sl = sp + F;
+    plm::F2FJob *fp = reinterpret_cast<plm::F2FJob *>(sl + F);
+    plm::F2FJob *fl = fp + F;
+    const uint4 *d_desc = reinterpret_cast<const uint4 *>(D + fr->o_desc);
+    const float *d_kp = reinterpret_cast<const float *>(D + fr->o_kp);
+    const float *d_ln = reinterpret_cast<const float *>(D + fr->o_ln);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(D + fr->o_counts);
+    uint4 *cdesc_p = reinterpret_cast<uint4 *>(D + fr->o_cdesc_p), *cdesc_l = reinterpret_cast<uint4 *>(D + fr->o_cdesc_l);
+    const std::vector<int64_t> &lp_off = fr->lp_off, &ll_off = fr->ll_off;
+    for (int f = f0; f < f1; ++f) {
+        const plm_frame_rec &r = frames[f];
+        plm::StereoJob &a = sp[f];
+        std::memset(&a, 0, sizeof(a));
+        a.geo_l = d_kp + 2 * r.kp_l;
+        a.geo_r = d_kp + 2 * r.kp_r;
+        a.d_l = d_desc + 2 * r.desc_pl;
+        a.d_r = d_desc + 2 * r.desc_pr;
+        a.m12 = reinterpret_cast<int32_t *>(D + fr->o_m12_p) + lp_off[f];
+        a.cdesc = cdesc_p + 2 * lp_off[f];
+        a.kept_i1 = reinterpret_cast<int32_t *>(D + fr->o_kept_p) + lp_off[f];
+        a.o0 = reinterpret_cast<double *>(D + fr->o_pt_disp) + lp_off[f];
+        a.o1 = reinterpret_cast<double *>(D + fr->o_pt_P) + 3 * lp_off[f];
+        a.counts = d_counts + 6 * f;
+        a.n_l = r.n_pl;
+        a.n_r = r.n_pr;
+        a.is_lines = 0;
+        plm::StereoJob &b = sl[f];
+        std::memset(&b, 0, sizeof(b));
+        b.geo_l = d_ln + 4 * r.ln_l;
+        b.geo_r = d_ln + 4 * r.ln_r;
+        b.d_l = d_desc + 2 * r.desc_ll;
+        b.d_r = d_desc + 2 * r.desc_lr;
+        b.m12 = reinterpret_cast<int32_t *>(D + fr->o_m12_l) + ll_off[f];
+        b.cdesc = cdesc_l + 2 * ll_off[f];
+        b.kept_i1 = reinterpret_cast<int32_t *>(D + fr->o_kept_l) + ll_off[f];
+        b.o0 = reinterpret_cast<double *>(D + fr->o_ls_disp) + 2 * ll_off[f];
+        b.o1 = reinterpret_cast<double *>(D + fr->o_ls_sP) + 3 * ll_off[f];
+        b.o2 = reinterpret_cast<double *>(D + fr->o_ls_eP) + 3 * ll_off[f];
+        b.o3 = reinterpret_cast<double *>(D + fr->o_ls_le) + 3 * ll_off[f];
+        b.counts = d_counts + 6 * f + 2;
+        b.n_l = r.n_ll;
+        b.n_r = r.n_lr;
+        b.is_lines = 1;
+        // temporal job of (frame f - 1, frame f); row 0 of the tables stays unused
+        plm::F2FJob &p = fp[f];
+        plm::F2FJob &q = fl[f];
+        std::memset(&p, 0, sizeof(p));
+        std::memset(&q, 0, sizeof(q));
+        if (f >= 1) {
+            p.d1 = cdesc_p + 2 * lp_off[f - 1];
+            p.d2 = a.cdesc;
+            p.n1_ptr = d_counts + 6 * (f - 1) + 1;
+            p.n2_ptr = d_counts + 6 * f + 1;
+            p.m12 = reinterpret_cast<int32_t *>(D + fr->o_f2f_p) + lp_off[f - 1];
+            p.count = d_counts + 6 * f + 4;
+            p.cap1 = frames[f - 1].n_pl;
+            p.cap2 = r.n_pl;
+            p.nnr = fr->nnr_p;
+            q.d1 = cdesc_l + 2 * ll_off[f - 1];
+            q.d2 = b.cdesc;
+            q.n1_ptr = d_counts + 6 * (f - 1) + 3;
+            q.n2_ptr = d_counts + 6 * f + 3;
+            q.m12 = reinterpret_cast<int32_t *>(D + fr->o_f2f_l) + ll_off[f - 1];
+            q.count = d_counts + 6 * f + 5;
+            q.cap1 = frames[f - 1].n_ll;
+            q.cap2 = r.n_ll;
+            q.nnr = fr->nnr_l;
+        }
+    }
+    const size_t nf = size_t(f1 - f0);
+    if (nf) {
+        CU_TRY(cudaMemcpyAsync(D + fr->o_sjobs_p + f0 * sizeof(plm::StereoJob), sp + f0, nf * sizeof(plm::StereoJob), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(D + fr->o_sjobs_l + f0 * sizeof(plm::StereoJob), sl + f0, nf * sizeof(plm::StereoJob), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(D + fr->o_fjobs_p + f0 * sizeof(plm::F2FJob), fp + f0, nf * sizeof(plm::F2FJob), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(D + fr->o_fjobs_l + f0 * sizeof(plm::F2FJob), fl + f0, nf * sizeof(plm::F2FJob), cudaMemcpyHostToDevice, s));
+        fr->h2d += static_cast<int64_t>(2 * nf * (sizeof(plm::StereoJob) + sizeof(plm::F2FJob)));
+    }
+    // the chunk's slices of every arena (a scattered layout only makes the slices larger)
+    auto copy_spans = [&](Span *sp_, int n_sp, size_t dev_off, const void *host, size_t elem) -> cudaError_t {
+        std::sort(sp_, sp_ + n_sp, [](const Span &x, const Span &y) { return x.lo < y.lo; });
+        for (int i = 0; i < n_sp; ++i) {
+            if (sp_[i].hi <= sp_[i].lo) continue;
+            int64_t lo = sp_[i].lo, hi = sp_[i].hi;
+            while (i + 1 < n_sp && sp_[i + 1].hi > sp_[i + 1].lo && sp_[i + 1].lo <= hi) hi = std::max(hi, sp_[++i].hi);
+            const cudaError_t e = cudaMemcpyAsync(D + dev_off + size_t(lo) * elem, static_cast<const char *>(host) + size_t(lo) * elem,
+                                                  size_t(hi - lo) * elem, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return e;
+            fr->h2d += (hi - lo) * static_cast<int64_t>(elem);
+        }
+        return cudaSuccess;
+    };
+    CU_TRY(copy_spans(sd, 4, fr->o_desc, desc_arena, 32));
+    CU_TRY(copy_spans(sk, 2, fr->o_kp, kp_arena, 8));
+    CU_TRY(copy_spans(sn, 2, fr->o_ln, ln_arena, 16));
+    fr->chunks.push_back(ch);
+    return PLM_OK;
+}
+
+// The four launches of a chunk on the context's stream (after clearing the slots the kernels do not write).
+int frames_chunk_run(plm_frames *fr, const plm_frames_chunk &ch) {
+    plm_ctx *ctx = fr->ctx;
+    char *D = fr->d_buf;
+    const int n = ch.f1 - ch.f0;
+    if (n <= 0) return PLM_OK;
+    cudaStream_t s = ctx->stream;
+    const int64_t p0 = fr->lp_off[ch.f0], p1 = fr->lp_off[ch.f1], l0 = fr->ll_off[ch.f0], l1 = fr->ll_off[ch.f1];
+    CU_TRY(cudaMemsetAsync(D + fr->o_counts + size_t(ch.f0) * 24, 0, size_t(n) * 24, s));
+    // slots past a frame's kept count (and the last frame's f2f range) read as -1
+    if (p1 > p0) {
+        CU_TRY(cudaMemsetAsync(D + fr->o_kept_p + size_t(p0) * 4, 0xFF, size_t(p1 - p0) * 4, s));
+        CU_TRY(cudaMemsetAsync(D + fr->o_f2f_p + size_t(p0) * 4, 0xFF, size_t(p1 - p0) * 4, s));
+    }
+    if (l1 > l0) {
+        CU_TRY(cudaMemsetAsync(D + fr->o_kept_l + size_t(l0) * 4, 0xFF, size_t(l1 - l0) * 4, s));
+        CU_TRY(cudaMemsetAsync(D + fr->o_f2f_l + size_t(l0) * 4, 0xFF, size_t(l1 - l0) * 4, s));
+    }
+    int st;
+    if ((st = launch_stereo<FRAMES_THREADS_P>(ctx, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n,
+                                              fr->cfg, ch.caps_p, ch.smem_p)) != PLM_OK) return st;
+    if ((st = launch_stereo<FRAMES_THREADS_L>(ctx, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0, n,
+                                              fr->cfg, ch.caps_l, ch.smem_l)) != PLM_OK) return st;
+    const int t0 = std::max(ch.f0, 1); // frame 0 has no predecessor
+    if (ch.f1 > t0) {
+        if ((st = launch_f2f<FRAMES_THREADS_P>(ctx, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
+                                               fr->cfg.best_lr, ch.smem_fp)) != PLM_OK) return st;
+        if ((st = launch_f2f<FRAMES_THREADS_L>(ctx, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0, ch.f1 - t0,
+                                               fr->cfg.best_lr, ch.smem_fl)) != PLM_OK) return st;
+    }
+    return PLM_OK;
+}
+
+// Device -> host copies of the outputs of frames [f0, f1) on `s`.  The f2f vector of frame f is written by
+// the job of frame f + 1, so its slot range lags by one frame: this copies frames [f0 - 1, f1 - 1), plus
+// frame f1 - 1 itself (never written: -1) when it is the last frame of the upload.
+int frames_copy_out(plm_frames *fr, const plm_frames_out *out, int f0, int f1, cudaStream_t s) {
+    char *D = fr->d_buf;
+    auto pull = [&](void *dst, size_t off, size_t elem, int64_t lo, int64_t hi) -> cudaError_t {
+        if (!dst || hi <= lo) return cudaSuccess;
+        fr->d2h += (hi - lo) * static_cast<int64_t>(elem);
+        return cudaMemcpyAsync(static_cast<char *>(dst) + size_t(lo) * elem, D + off + size_t(lo) * elem, size_t(hi - lo) * elem,
+                               cudaMemcpyDeviceToHost, s);
+    };
+    const std::vector<int64_t> &P = fr->lp_off, &Lo = fr->ll_off;
+    const int64_t p0 = P[f0], p1 = P[f1], l0 = Lo[f0], l1 = Lo[f1];
+    CU_TRY(pull(out->stereo_m12_p, fr->o_m12_p, 4, p0, p1));
+    CU_TRY(pull(out->stereo_m12_l, fr->o_m12_l, 4, l0, l1));
+    CU_TRY(pull(out->kept_p, fr->o_kept_p, 4, p0, p1));
+    CU_TRY(pull(out->kept_l, fr->o_kept_l, 4, l0, l1));
+    CU_TRY(pull(out->pt_disp, fr->o_pt_disp, 8, p0, p1));
+    CU_TRY(pull(out->pt_P, fr->o_pt_P, 24, p0, p1));
+    CU_TRY(pull(out->ls_disp, fr->o_ls_disp, 16, l0, l1));
+    CU_TRY(pull(out->ls_sP, fr->o_ls_sP, 24, l0, l1));
+    CU_TRY(pull(out->ls_eP, fr->o_ls_eP, 24, l0, l1));
+    CU_TRY(pull(out->ls_le, fr->o_ls_le, 24, l0, l1));
+    const int g0 = std::max(f0 - 1, 0), g1 = (f1 == fr->n_frames) ? f1 : f1 - 1;
+    if (g1 > g0) {
+        CU_TRY(pull(out->f2f_m12_p, fr->o_f2f_p, 4, P[g0], P[g1]));
+        CU_TRY(pull(out->f2f_m12_l, fr->o_f2f_l, 4, Lo[g0], Lo[g1]));
+    }
+    CU_TRY(pull(out->counts, fr->o_counts, 24, f0, f1));
+    return PLM_OK;
+}
+
 } // namespace
 
 PLM_API int plm_frames_create(plm_ctx *ctx, plm_frames **out) {
@@ -90,7 +450,17 @@ PLM_API int plm_frames_destroy(plm_frames *fr) {
         cudaSetDevice(fr->ctx->device);
         cudaStreamSynchronize(fr->ctx->stream);
     }
+    if (fr->s_in) {
+        cudaStreamSynchronize(fr->s_in);
+        cudaStreamDestroy(fr->s_in);
+    }
+    if (fr->s_out) {
+        cudaStreamSynchronize(fr->s_out);
+        cudaStreamDestroy(fr->s_out);
+    }
+    for (cudaEvent_t e : fr->events) cudaEventDestroy(e);
     if (fr->d_buf) cudaFree(fr->d_buf);
+    if (fr->h_tab) cudaFreeHost(fr->h_tab);
     delete fr;
     return PLM_OK;
 }
@@ -101,198 +471,13 @@ PLM_API int64_t plm_frames_d2h_bytes(const plm_frames *fr) { return fr ? fr->d2h
 PLM_API int plm_frames_upload(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows, const float *kp_arena,
                               int64_t n_kp, const float *ln_arena, int64_t n_ln, const plm_frame_rec *frames,
                               int n_frames, const plm_frame_config *c) {
-    if (!fr || !c) return fail(PLM_E_INVALID, "null frames / config");
-    if (n_rows < 0 || n_kp < 0 || n_ln < 0 || n_frames < 0) return fail(PLM_E_INVALID, "negative size");
-    if ((n_rows > 0 && !desc_arena) || (n_kp > 0 && !kp_arena) || (n_ln > 0 && !ln_arena) || (n_frames > 0 && !frames))
-        return fail(PLM_E_INVALID, "null pointer");
-    if (c->grid_rows <= 0 || c->grid_cols <= 0) return fail(PLM_E_GRID, "[GridStructure] invalid dimension");
-    if (static_cast<long long>(c->grid_rows) * c->grid_cols > (1 << 14)) return fail(PLM_E_UNSUPPORTED, "grid too large for the frame pipeline");
-    if (c->min_ratio_12p > 1.0) return fail(PLM_E_RATIO, plm_status_string(PLM_E_RATIO));
+    if (!fr) return fail(PLM_E_INVALID, "null frames");
     plm_ctx *ctx = fr->ctx;
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
-    fr->ready = false;
-
-    // ---- validation, slot offsets, shared-memory capacities --------------------------------------------
-    std::vector<int64_t> lp_off(static_cast<size_t>(n_frames) + 1, 0), ll_off(static_cast<size_t>(n_frames) + 1, 0);
-    int cap_pl = 1, cap_pr = 1, cap_ll = 1, cap_lr = 1;
-    long long cap_items_l = 1;
-    const long long walk_max = static_cast<long long>(c->grid_rows) + c->grid_cols + 2;
-    for (int f = 0; f < n_frames; ++f) {
-        const plm_frame_rec &r = frames[f];
-        if (r.n_pl < 0 || r.n_pr < 0 || r.n_ll < 0 || r.n_lr < 0 || r.desc_pl < 0 || r.desc_pr < 0 || r.desc_ll < 0 ||
-            r.desc_lr < 0 || r.kp_l < 0 || r.kp_r < 0 || r.ln_l < 0 || r.ln_r < 0 || r.desc_pl + r.n_pl > n_rows ||
-            r.desc_pr + r.n_pr > n_rows || r.desc_ll + r.n_ll > n_rows || r.desc_lr + r.n_lr > n_rows ||
-            r.kp_l + r.n_pl > n_kp || r.kp_r + r.n_pr > n_kp || r.ln_l + r.n_ll > n_ln || r.ln_r + r.n_lr > n_ln)
-            return fail(PLM_E_INVALID, "frame record outside its arena");
-        if (r.n_pl > FRAMES_MAX_FEATURES || r.n_pr > FRAMES_MAX_FEATURES || r.n_ll > FRAMES_MAX_FEATURES ||
-            r.n_lr > FRAMES_MAX_FEATURES)
-            return fail(PLM_E_UNSUPPORTED, "more than 4096 features of one kind in a frame");
-        lp_off[f + 1] = lp_off[f] + r.n_pl;
-        ll_off[f + 1] = ll_off[f] + r.n_ll;
-        cap_pl = std::max(cap_pl, r.n_pl);
-        cap_pr = std::max(cap_pr, r.n_pr);
-        cap_ll = std::max(cap_ll, r.n_ll);
-        cap_lr = std::max(cap_lr, r.n_lr);
-        long long items = 0;
-        for (int j = 0; j < r.n_lr; ++j) {
-            const float *l = ln_arena + 4 * (r.ln_r + j);
-            const long long n = line_walk_cells(double(l[0]) * c->inv_width, double(l[1]) * c->inv_height,
-                                                double(l[2]) * c->inv_width, double(l[3]) * c->inv_height);
-            if (n > walk_max) return fail(PLM_E_UNSUPPORTED, "line segment far outside the image (Bresenham walk too long)");
-            items += n;
-        }
-        cap_items_l = std::max(cap_items_l, items);
-    }
-    const int n_cells = c->grid_rows * c->grid_cols;
-    fr->caps_p = plm::StereoCaps{cap_pl, cap_pr, cap_pr, FRAMES_THREADS_P / 32};
-    fr->caps_l = plm::StereoCaps{cap_ll, cap_lr, static_cast<int>(cap_items_l), FRAMES_THREADS_L / 32};
-    fr->smem_p = plm::stereo_frame_smem(fr->caps_p, n_cells, false);
-    fr->smem_l = plm::stereo_frame_smem(fr->caps_l, n_cells, true);
-    fr->smem_fp = plm::f2f_smem(cap_pl, cap_pl);
-    fr->smem_fl = plm::f2f_smem(cap_ll, cap_ll);
-    const size_t budget = ctx->smem_optin - 1024;
-    if (fr->smem_p > budget || fr->smem_l > budget || fr->smem_fp > budget || fr->smem_fl > budget)
-        return fail(PLM_E_UNSUPPORTED, "frame too large for shared memory");
-
-    const int64_t NP = lp_off[n_frames], NL = ll_off[n_frames];
-    Layout L;
-    const size_t o_desc = L.add(size_t(n_rows) * 32);
-    const size_t o_kp = L.add(size_t(n_kp) * 8);
-    const size_t o_ln = L.add(size_t(n_ln) * 16);
-    const size_t o_cdesc_p = L.add(size_t(NP) * 32), o_cdesc_l = L.add(size_t(NL) * 32);
-    fr->o_m12_p = L.add(size_t(NP) * 4);
-    fr->o_m12_l = L.add(size_t(NL) * 4);
-    fr->o_kept_p = L.add(size_t(NP) * 4);
-    fr->o_kept_l = L.add(size_t(NL) * 4);
-    fr->o_pt_disp = L.add(size_t(NP) * 8);
-    fr->o_pt_P = L.add(size_t(NP) * 24);
-    fr->o_ls_disp = L.add(size_t(NL) * 16);
-    fr->o_ls_sP = L.add(size_t(NL) * 24);
-    fr->o_ls_eP = L.add(size_t(NL) * 24);
-    fr->o_ls_le = L.add(size_t(NL) * 24);
-    fr->o_f2f_p = L.add(size_t(NP) * 4);
-    fr->o_f2f_l = L.add(size_t(NL) * 4);
-    fr->o_counts = L.add(size_t(std::max(n_frames, 1)) * 6 * 4);
-    fr->o_sjobs_p = L.add(size_t(std::max(n_frames, 1)) * sizeof(plm::StereoJob));
-    fr->o_sjobs_l = L.add(size_t(std::max(n_frames, 1)) * sizeof(plm::StereoJob));
-    fr->o_fjobs_p = L.add(size_t(std::max(n_frames, 1)) * sizeof(plm::F2FJob));
-    fr->o_fjobs_l = L.add(size_t(std::max(n_frames, 1)) * sizeof(plm::F2FJob));
-    if ((st = fr->ensure(L.total)) != PLM_OK) return st;
-    char *D = fr->d_buf;
-
-    // ---- job tables ------------------------------------------------------------------------------------
-    const float nnr_p = static_cast<float>(c->min_ratio_12p), nnr_l = static_cast<float>(c->min_ratio_12l);
-    std::vector<plm::StereoJob> sp(static_cast<size_t>(n_frames)), sl(static_cast<size_t>(n_frames));
-    std::vector<plm::F2FJob> fp(static_cast<size_t>(std::max(n_frames - 1, 0))), fl(fp.size());
-    const uint4 *d_desc = reinterpret_cast<const uint4 *>(D + o_desc);
-    const float *d_kp = reinterpret_cast<const float *>(D + o_kp);
-    const float *d_ln = reinterpret_cast<const float *>(D + o_ln);
-    int32_t *d_counts = reinterpret_cast<int32_t *>(D + fr->o_counts);
-    for (int f = 0; f < n_frames; ++f) {
-        const plm_frame_rec &r = frames[f];
-        plm::StereoJob &a = sp[f];
-        std::memset(&a, 0, sizeof(a));
-        a.geo_l = d_kp + 2 * r.kp_l;
-        a.geo_r = d_kp + 2 * r.kp_r;
-        a.d_l = d_desc + 2 * r.desc_pl;
-        a.d_r = d_desc + 2 * r.desc_pr;
-        a.m12 = reinterpret_cast<int32_t *>(D + fr->o_m12_p) + lp_off[f];
-        a.cdesc = reinterpret_cast<uint4 *>(D + o_cdesc_p) + 2 * lp_off[f];
-        a.kept_i1 = reinterpret_cast<int32_t *>(D + fr->o_kept_p) + lp_off[f];
-        a.o0 = reinterpret_cast<double *>(D + fr->o_pt_disp) + lp_off[f];
-        a.o1 = reinterpret_cast<double *>(D + fr->o_pt_P) + 3 * lp_off[f];
-        a.counts = d_counts + 6 * f;
-        a.n_l = r.n_pl;
-        a.n_r = r.n_pr;
-        a.is_lines = 0;
-        plm::StereoJob &b = sl[f];
-        std::memset(&b, 0, sizeof(b));
-        b.geo_l = d_ln + 4 * r.ln_l;
-        b.geo_r = d_ln + 4 * r.ln_r;
-        b.d_l = d_desc + 2 * r.desc_ll;
-        b.d_r = d_desc + 2 * r.desc_lr;
-        b.m12 = reinterpret_cast<int32_t *>(D + fr->o_m12_l) + ll_off[f];
-        b.cdesc = reinterpret_cast<uint4 *>(D + o_cdesc_l) + 2 * ll_off[f];
-        b.kept_i1 = reinterpret_cast<int32_t *>(D + fr->o_kept_l) + ll_off[f];
-        b.o0 = reinterpret_cast<double *>(D + fr->o_ls_disp) + 2 * ll_off[f];
-        b.o1 = reinterpret_cast<double *>(D + fr->o_ls_sP) + 3 * ll_off[f];
-        b.o2 = reinterpret_cast<double *>(D + fr->o_ls_eP) + 3 * ll_off[f];
-        b.o3 = reinterpret_cast<double *>(D + fr->o_ls_le) + 3 * ll_off[f];
-        b.counts = d_counts + 6 * f + 2;
-        b.n_l = r.n_ll;
-        b.n_r = r.n_lr;
-        b.is_lines = 1;
-        if (f >= 1) {
-            plm::F2FJob &p = fp[f - 1];
-            std::memset(&p, 0, sizeof(p));
-            p.d1 = sp[f - 1].cdesc;
-            p.d2 = a.cdesc;
-            p.n1_ptr = d_counts + 6 * (f - 1) + 1;
-            p.n2_ptr = d_counts + 6 * f + 1;
-            p.m12 = reinterpret_cast<int32_t *>(D + fr->o_f2f_p) + lp_off[f - 1];
-            p.count = d_counts + 6 * f + 4;
-            p.cap1 = frames[f - 1].n_pl;
-            p.cap2 = r.n_pl;
-            p.nnr = nnr_p;
-            plm::F2FJob &q = fl[f - 1];
-            std::memset(&q, 0, sizeof(q));
-            q.d1 = sl[f - 1].cdesc;
-            q.d2 = b.cdesc;
-            q.n1_ptr = d_counts + 6 * (f - 1) + 3;
-            q.n2_ptr = d_counts + 6 * f + 3;
-            q.m12 = reinterpret_cast<int32_t *>(D + fr->o_f2f_l) + ll_off[f - 1];
-            q.count = d_counts + 6 * f + 5;
-            q.cap1 = frames[f - 1].n_ll;
-            q.cap2 = r.n_ll;
-            q.nnr = nnr_l;
-        }
-    }
-
-    Layout S;
-    const size_t s_sp = S.add(sp.size() * sizeof(plm::StereoJob)), s_sl = S.add(sl.size() * sizeof(plm::StereoJob));
-    const size_t s_fp = S.add(fp.size() * sizeof(plm::F2FJob)), s_fl = S.add(fl.size() * sizeof(plm::F2FJob));
-    if ((st = ctx->ensure_pinned(std::max<size_t>(S.total, 256))) != PLM_OK) return st;
-    char *H = ctx->h_buf;
-    if (!sp.empty()) std::memcpy(H + s_sp, sp.data(), sp.size() * sizeof(plm::StereoJob));
-    if (!sl.empty()) std::memcpy(H + s_sl, sl.data(), sl.size() * sizeof(plm::StereoJob));
-    if (!fp.empty()) std::memcpy(H + s_fp, fp.data(), fp.size() * sizeof(plm::F2FJob));
-    if (!fl.empty()) std::memcpy(H + s_fl, fl.data(), fl.size() * sizeof(plm::F2FJob));
-    cudaStream_t s = ctx->stream;
-    if (n_rows > 0) CU_TRY(cudaMemcpyAsync(D + o_desc, desc_arena, size_t(n_rows) * 32, cudaMemcpyHostToDevice, s));
-    if (n_kp > 0) CU_TRY(cudaMemcpyAsync(D + o_kp, kp_arena, size_t(n_kp) * 8, cudaMemcpyHostToDevice, s));
-    if (n_ln > 0) CU_TRY(cudaMemcpyAsync(D + o_ln, ln_arena, size_t(n_ln) * 16, cudaMemcpyHostToDevice, s));
-    if (!sp.empty()) CU_TRY(cudaMemcpyAsync(D + fr->o_sjobs_p, H + s_sp, sp.size() * sizeof(plm::StereoJob), cudaMemcpyHostToDevice, s));
-    if (!sl.empty()) CU_TRY(cudaMemcpyAsync(D + fr->o_sjobs_l, H + s_sl, sl.size() * sizeof(plm::StereoJob), cudaMemcpyHostToDevice, s));
-    if (!fp.empty()) CU_TRY(cudaMemcpyAsync(D + fr->o_fjobs_p, H + s_fp, fp.size() * sizeof(plm::F2FJob), cudaMemcpyHostToDevice, s));
-    if (!fl.empty()) CU_TRY(cudaMemcpyAsync(D + fr->o_fjobs_l, H + s_fl, fl.size() * sizeof(plm::F2FJob), cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaStreamSynchronize(s)); // the pinned staging block is reused by the next call
-
-    fr->n_frames = n_frames;
-    fr->NP = NP;
-    fr->NL = NL;
-    fr->nnr_p = nnr_p;
-    fr->nnr_l = nnr_l;
-    plm::FrameCfg &g = fr->cfg;
-    g.inv_w = c->inv_width;
-    g.inv_h = c->inv_height;
-    g.ratio = c->min_ratio_12p;
-    g.line_sim_th = c->line_sim_th;
-    g.max_dist_epip = c->max_dist_epip;
-    g.min_disp = c->min_disp;
-    g.line_horiz_th = c->line_horiz_th;
-    g.stereo_overlap_th = c->stereo_overlap_th;
-    g.ls_min_disp_ratio = c->ls_min_disp_ratio;
-    g.cam_b = c->cam_b;
-    g.cam_fx = c->cam_fx;
-    g.cam_cx = c->cam_cx;
-    g.cam_cy = c->cam_cy;
-    g.grid_rows = c->grid_rows;
-    g.grid_cols = c->grid_cols;
-    g.matching_s_ws = c->matching_s_ws;
-    g.best_lr = c->best_lr ? 1 : 0;
-    fr->h2d = static_cast<int64_t>(size_t(n_rows) * 32 + size_t(n_kp) * 8 + size_t(n_ln) * 16 + S.total);
-    fr->d2h = 0;
+    if ((st = frames_layout(fr, desc_arena, n_rows, kp_arena, n_kp, ln_arena, n_ln, frames, n_frames, c)) != PLM_OK) return st;
+    if ((st = frames_chunk_in(fr, desc_arena, kp_arena, ln_arena, frames, 0, n_frames, ctx->stream)) != PLM_OK) return st;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
     fr->ready = true;
     return PLM_OK;
 }
@@ -302,23 +487,9 @@ PLM_API int plm_frames_run(plm_frames *fr) {
     plm_ctx *ctx = fr->ctx;
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
-    if (fr->n_frames == 0) return PLM_OK;
-    char *D = fr->d_buf;
-    const int F = fr->n_frames;
-    CU_TRY(cudaMemsetAsync(D + fr->o_counts, 0, size_t(F) * 6 * 4, ctx->stream));
-    // slots past a frame's kept count (and the last frame's f2f range) read as -1
-    if (fr->NP) CU_TRY(cudaMemsetAsync(D + fr->o_kept_p, 0xFF, size_t(fr->NP) * 4, ctx->stream));
-    if (fr->NL) CU_TRY(cudaMemsetAsync(D + fr->o_kept_l, 0xFF, size_t(fr->NL) * 4, ctx->stream));
-    if (fr->NP) CU_TRY(cudaMemsetAsync(D + fr->o_f2f_p, 0xFF, size_t(fr->NP) * 4, ctx->stream));
-    if (fr->NL) CU_TRY(cudaMemsetAsync(D + fr->o_f2f_l, 0xFF, size_t(fr->NL) * 4, ctx->stream));
-    if ((st = launch_stereo<FRAMES_THREADS_P>(ctx, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p), F, fr->cfg,
-                                              fr->caps_p, fr->smem_p)) != PLM_OK) return st;
-    if ((st = launch_stereo<FRAMES_THREADS_L>(ctx, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l), F, fr->cfg,
-                                              fr->caps_l, fr->smem_l)) != PLM_OK) return st;
-    if ((st = launch_f2f<FRAMES_THREADS_P>(ctx, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p), F - 1,
-                                           fr->cfg.best_lr, fr->smem_fp)) != PLM_OK) return st;
-    return launch_f2f<FRAMES_THREADS_L>(ctx, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l), F - 1,
-                                        fr->cfg.best_lr, fr->smem_fl);
+    for (const plm_frames_chunk &ch : fr->chunks)
+        if ((st = frames_chunk_run(fr, ch)) != PLM_OK) return st;
+    return PLM_OK;
 }
 
 PLM_API int plm_frames_fetch(plm_frames *fr, const plm_frames_out *out) {
@@ -326,29 +497,52 @@ PLM_API int plm_frames_fetch(plm_frames *fr, const plm_frames_out *out) {
     plm_ctx *ctx = fr->ctx;
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
-    cudaStream_t s = ctx->stream;
-    char *D = fr->d_buf;
-    int64_t bytes = 0;
-    auto pull = [&](void *dst, size_t off, size_t n) -> cudaError_t {
-        if (!dst || n == 0) return cudaSuccess;
-        bytes += static_cast<int64_t>(n);
-        return cudaMemcpyAsync(dst, D + off, n, cudaMemcpyDeviceToHost, s);
-    };
-    const size_t NP = size_t(fr->NP), NL = size_t(fr->NL);
-    CU_TRY(pull(out->stereo_m12_p, fr->o_m12_p, NP * 4));
-    CU_TRY(pull(out->stereo_m12_l, fr->o_m12_l, NL * 4));
-    CU_TRY(pull(out->kept_p, fr->o_kept_p, NP * 4));
-    CU_TRY(pull(out->kept_l, fr->o_kept_l, NL * 4));
-    CU_TRY(pull(out->pt_disp, fr->o_pt_disp, NP * 8));
-    CU_TRY(pull(out->pt_P, fr->o_pt_P, NP * 24));
-    CU_TRY(pull(out->ls_disp, fr->o_ls_disp, NL * 16));
-    CU_TRY(pull(out->ls_sP, fr->o_ls_sP, NL * 24));
-    CU_TRY(pull(out->ls_eP, fr->o_ls_eP, NL * 24));
-    CU_TRY(pull(out->ls_le, fr->o_ls_le, NL * 24));
-    CU_TRY(pull(out->f2f_m12_p, fr->o_f2f_p, NP * 4));
-    CU_TRY(pull(out->f2f_m12_l, fr->o_f2f_l, NL * 4));
-    CU_TRY(pull(out->counts, fr->o_counts, size_t(fr->n_frames) * 6 * 4));
-    CU_TRY(cudaStreamSynchronize(s));
-    fr->d2h = bytes;
+    fr->d2h = 0;
+    if (fr->n_frames > 0 && (st = frames_copy_out(fr, out, 0, fr->n_frames, ctx->stream)) != PLM_OK) return st;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return PLM_OK;
+}
+
+PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows, const float *kp_arena,
+                               int64_t n_kp, const float *ln_arena, int64_t n_ln, const plm_frame_rec *frames,
+                               int n_frames, const plm_frame_config *c, const plm_frames_out *out, int chunk_frames) {
+    if (!fr || !out) return fail(PLM_E_INVALID, "null frames / out");
+    plm_ctx *ctx = fr->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    if ((st = frames_layout(fr, desc_arena, n_rows, kp_arena, n_kp, ln_arena, n_ln, frames, n_frames, c)) != PLM_OK) return st;
+    if (!fr->s_in) CU_TRY(cudaStreamCreateWithFlags(&fr->s_in, cudaStreamNonBlocking));
+    if (!fr->s_out) CU_TRY(cudaStreamCreateWithFlags(&fr->s_out, cudaStreamNonBlocking));
+    if (chunk_frames <= 0) chunk_frames = 256;
+    // everything enqueued earlier on the compute stream (a previous run on the same buffers) comes first
+    cudaEvent_t e_start;
+    if ((st = fr->event(0, &e_start)) != PLM_OK) return st;
+    CU_TRY(cudaEventRecord(e_start, ctx->stream));
+    CU_TRY(cudaStreamWaitEvent(fr->s_in, e_start, 0));
+    size_t k = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk_frames, ++k) {
+        const int f1 = std::min(n_frames, f0 + chunk_frames);
+        cudaEvent_t e_in, e_run;
+        if ((st = fr->event(1 + 2 * k, &e_in)) != PLM_OK) break;
+        if ((st = fr->event(2 + 2 * k, &e_run)) != PLM_OK) break;
+        if ((st = frames_chunk_in(fr, desc_arena, kp_arena, ln_arena, frames, f0, f1, fr->s_in)) != PLM_OK) break;
+        if (cudaEventRecord(e_in, fr->s_in) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, e_in, 0) != cudaSuccess) {
+            st = fail(PLM_E_CUDA, "event record / wait failed");
+            break;
+        }
+        if ((st = frames_chunk_run(fr, fr->chunks.back())) != PLM_OK) break;
+        if (cudaEventRecord(e_run, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(fr->s_out, e_run, 0) != cudaSuccess) {
+            st = fail(PLM_E_CUDA, "event record / wait failed");
+            break;
+        }
+        if ((st = frames_copy_out(fr, out, f0, f1, fr->s_out)) != PLM_OK) break;
+    }
+    // drain all three streams even after a failure: the caller's buffers must not be in flight on return
+    cudaStreamSynchronize(fr->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(fr->s_out);
+    if (st != PLM_OK) return st;
+    CU_TRY(cudaGetLastError());
+    fr->ready = true;
     return PLM_OK;
 }

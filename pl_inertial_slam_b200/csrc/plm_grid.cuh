@@ -128,31 +128,39 @@ struct RowQuery {
     double vx, vy; // normalised query direction (lines)
 };
 
+// Window(s) of row i1 only (no descriptor, no direction).
+__device__ __forceinline__ RowWindows load_windows(const GridJob &job, const GridParams &gp, int i1) {
+    RowWindows rw;
+    if (!job.is_lines) {
+        const long long ci = i1 - job.q_row_base;
+        rw.n_win = 1;
+        clamp_window(rw, 0, job.coords[2 * ci], job.coords[2 * ci + 1], job.win, gp.grid_rows, gp.grid_cols);
+        rw.nx[1] = 0;
+        rw.min_x[1] = rw.min_y[1] = rw.max_y[1] = 0;
+    } else {
+        const int32_t *cp = job.coords + 4 * static_cast<long long>(i1 - job.q_row_base);
+        rw.n_win = 2;
+        clamp_window(rw, 0, cp[0], cp[1], job.win, gp.grid_rows, gp.grid_cols);
+        clamp_window(rw, 1, cp[2], cp[3], job.win, gp.grid_rows, gp.grid_cols);
+    }
+    rw.n_ranges = rw.nx[0] + rw.nx[1];
+    return rw;
+}
+
 __device__ __forceinline__ RowQuery load_row(const GridJob &job, const GridParams &gp, int i1) {
     RowQuery r;
     r.q = load_desc_any(job.d1, i1 - job.q_row_base);
     r.vx = r.vy = 0.0;
-    if (!job.is_lines) {
-        const long long ci = i1 - job.q_row_base;
-        const int2 c = make_int2(job.coords[2 * ci], job.coords[2 * ci + 1]);
-        r.rw.n_win = 1;
-        clamp_window(r.rw, 0, c.x, c.y, job.win, gp.grid_rows, gp.grid_cols);
-        r.rw.nx[1] = 0;
-        r.rw.min_x[1] = r.rw.min_y[1] = r.rw.max_y[1] = 0;
-    } else {
+    r.rw = load_windows(job, gp, i1);
+    if (job.is_lines) {
         const int32_t *cp = job.coords + 4 * static_cast<long long>(i1 - job.q_row_base);
-        const int4 c = make_int4(cp[0], cp[1], cp[2], cp[3]);
-        r.rw.n_win = 2;
-        clamp_window(r.rw, 0, c.x, c.y, job.win, gp.grid_rows, gp.grid_cols);
-        clamp_window(r.rw, 1, c.z, c.w, job.win, gp.grid_rows, gp.grid_cols);
         // matching.cpp:210-211 + matching.h:43-48: v = (ep - sp) as ints -> double, divided by
         // sqrt(x*x + y*y).  Separate roundings (the reference has no FMA); 0/0 = NaN is kept.
-        const double dx = static_cast<double>(c.z - c.x), dy = static_cast<double>(c.w - c.y);
+        const double dx = static_cast<double>(cp[2] - cp[0]), dy = static_cast<double>(cp[3] - cp[1]);
         const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
         r.vx = __ddiv_rn(dx, mag);
         r.vy = __ddiv_rn(dy, mag);
     }
-    r.rw.n_ranges = r.rw.nx[0] + r.rw.nx[1];
     return r;
 }
 
@@ -265,6 +273,217 @@ __host__ __device__ inline size_t grid_fused_smem(int warps, int n2_max, int sta
         if (any_lines) b += static_cast<size_t>(n2_max) * 16;
     }
     return b;
+}
+
+// ---- pair-list form for frame-sized jobs ---------------------------------------------------------------
+// With a few candidates per row (stereo window: 2-3, +-3 cells: 10-15) the warp-per-chunk phases above spend
+// their time in warp-synchronous bookkeeping.  The same semantics without any loop-carried dependence:
+//   P1  thread per row: number of candidate slots of its window(s)              -> block scan -> rowoff
+//   P2  thread per row: walk the slots, range check, in-row de-duplication (the candidate set is a set,
+//       matching.cpp:136 / :213; a line sits in several cells), direction filter, distance
+//                                                                                -> pair[p] = (i2, D), prow[p] = i1
+//   P3  counting sort of the valid pairs by column i2                            -> colstart, cpair
+//   P4  thread per pair: with bestLRMatches the pair is DEAD when an earlier row i1' < i1 holds D' <= D in its
+//       column bucket (it does not improve distances[i2], :145-150)
+//       thread per column: m21[i2] = lowest i1 at the column minimum
+//   P5  thread per row: two smallest D over its live pairs, fp64 ratio test (:160 / :241) -> m12
+//   P6  mutual check (:166-174)
+// Everything lives in shared memory; a job with more slots than the arrays hold reports false and the caller
+// falls back to the chunk phases.
+constexpr uint32_t PAIR_INVALID = 0xFFFFFFFFu;
+constexpr uint16_t PROW_DEAD = 0x8000u;
+
+struct PairArrays {
+    uint32_t *pair;    // [cap]  i2 << 9 | D
+    uint16_t *prow;    // [cap]  i1 | PROW_DEAD
+    uint16_t *cpair;   // [cap]  pair slots grouped by column
+    int32_t *rowoff;   // [n1 + 1]
+    int32_t *colstart; // [n2 + 1]
+    int32_t *colaux;   // [n2]     fill cursors, then m21
+    int cap;           // <= 65535
+};
+
+__host__ __device__ inline size_t pairlist_smem(int cap_pairs, int cap_n1, int cap_n2) {
+    return grid_align16(static_cast<size_t>(cap_pairs) * 4) + 2 * grid_align16(static_cast<size_t>(cap_pairs) * 2) +
+           grid_align16(static_cast<size_t>(cap_n1 + 1) * 4) + grid_align16(static_cast<size_t>(cap_n2 + 1) * 4) +
+           grid_align16(static_cast<size_t>(cap_n2) * 4);
+}
+
+__device__ __forceinline__ PairArrays pairlist_carve(unsigned char *p, int cap_pairs, int cap_n1, int cap_n2) {
+    PairArrays A;
+    A.pair = reinterpret_cast<uint32_t *>(p); p += grid_align16(static_cast<size_t>(cap_pairs) * 4);
+    A.prow = reinterpret_cast<uint16_t *>(p); p += grid_align16(static_cast<size_t>(cap_pairs) * 2);
+    A.cpair = reinterpret_cast<uint16_t *>(p); p += grid_align16(static_cast<size_t>(cap_pairs) * 2);
+    A.rowoff = reinterpret_cast<int32_t *>(p); p += grid_align16(static_cast<size_t>(cap_n1 + 1) * 4);
+    A.colstart = reinterpret_cast<int32_t *>(p); p += grid_align16(static_cast<size_t>(cap_n2 + 1) * 4);
+    A.colaux = reinterpret_cast<int32_t *>(p);
+    A.cap = cap_pairs;
+    return A;
+}
+
+// Inclusive block scan of v[0..n) in shared memory; thread t owns a contiguous strip.
+// s_part needs blockDim.x / 32 ints.  Ends with a barrier.
+__device__ __forceinline__ void block_inclusive_scan(int32_t *v, int n, int32_t *s_part) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + T - 1) / T;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += v[i];
+    int incl = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+        if (lane >= s) incl += t;
+    }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = T >> 5;
+        int w = (lane < nw) ? s_part[lane] : 0;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, w, s);
+            if (lane >= s) w += t;
+        }
+        if (lane < nw) s_part[lane] = w; // inclusive over warps
+    }
+    __syncthreads();
+    int run = incl - sum + (warp ? s_part[warp - 1] : 0);
+    for (int i = lo; i < hi; ++i) {
+        run += v[i];
+        v[i] = run;
+    }
+    __syncthreads();
+}
+
+// Calls f(item slot t) for every slot of the row's window(s), one thread walking them in order.
+template <class F>
+__device__ __forceinline__ void for_each_slot(const RowWindows &rw, const GridJob &job, int grid_rows, F &&f) {
+    for (int k = 0; k < rw.n_win; ++k)
+        for (int x = rw.min_x[k]; x < rw.min_x[k] + rw.nx[k]; ++x) {
+            const int lo = job.cell_start[x * grid_rows + rw.min_y[k]], hi = job.cell_start[x * grid_rows + rw.max_y[k]];
+            for (int t = lo; t < hi; ++t) f(t);
+        }
+}
+
+// Block-wide.  job.m12 must be readable / writable by the whole CTA (shared or global memory); *s_count
+// (shared) receives accepted - culled.  Returns false when the slots do not fit (nothing written).
+__device__ __forceinline__ bool pairlist_match(const GridJob &job, const GridParams &gp, const PairArrays &A,
+                                               int32_t *s_part, int *s_count) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int n1 = job.n1, n2 = job.n2;
+    // P1
+    for (int i1 = tid; i1 < n1; i1 += T) {
+        const RowWindows rw = load_windows(job, gp, i1);
+        int cnt = 0;
+        for (int k = 0; k < rw.n_win; ++k)
+            for (int x = rw.min_x[k]; x < rw.min_x[k] + rw.nx[k]; ++x)
+                cnt += max(0, job.cell_start[x * gp.grid_rows + rw.max_y[k]] - job.cell_start[x * gp.grid_rows + rw.min_y[k]]);
+        A.rowoff[i1 + 1] = cnt;
+    }
+    if (tid == 0) A.rowoff[0] = 0;
+    for (int i = tid; i <= n2; i += T) A.colstart[i] = 0;
+    __syncthreads();
+    block_inclusive_scan(A.rowoff + 1, n1, s_part);
+    const int S = A.rowoff[n1];
+    if (S > A.cap) return false;
+    // P2: a train feature listed in several cells of the window(s) (a line) is kept once -- the candidate
+    // set is a set (matching.cpp:136 / :213); repeats stay PAIR_INVALID and cost no distance
+    for (int i1 = tid; i1 < n1; i1 += T) {
+        const RowQuery r = load_row(job, gp, i1);
+        const int p0 = A.rowoff[i1];
+        int p = p0;
+        for_each_slot(r.rw, job, gp.grid_rows, [&](int t) {
+            const int i2 = job.cell_items[t];
+            uint32_t v = PAIR_INVALID;
+            if (i2 >= 0 && i2 < n2) {
+                bool dup = false;
+                if (job.is_lines)
+                    for (int pp = p0; pp < p; ++pp) dup = dup || (A.pair[pp] >> 9) == static_cast<uint32_t>(i2);
+                if (!dup && candidate_ok(job, gp, r, i2)) {
+                    const int d = hamming256(r.q, load_desc_any(job.d2, i2));
+                    v = (static_cast<uint32_t>(i2) << 9) | static_cast<uint32_t>(d);
+                    atomicAdd(&A.colstart[i2 + 1], 1);
+                }
+            }
+            A.pair[p] = v;
+            A.prow[p] = static_cast<uint16_t>(i1);
+            ++p;
+        });
+    }
+    __syncthreads();
+    // P3
+    block_inclusive_scan(A.colstart + 1, n2, s_part);
+    for (int i = tid; i < n2; i += T) A.colaux[i] = A.colstart[i];
+    __syncthreads();
+    for (int p = tid; p < S; p += T) {
+        const uint32_t v = A.pair[p];
+        if (v != PAIR_INVALID) A.cpair[atomicAdd(&A.colaux[v >> 9], 1)] = static_cast<uint16_t>(p);
+    }
+    __syncthreads();
+    // P4
+    for (int p = tid; p < S; p += T) {
+        const uint32_t v = A.pair[p];
+        if (v == PAIR_INVALID) continue;
+        const int i2 = static_cast<int>(v >> 9), d = static_cast<int>(v & 511u);
+        const int i1 = A.prow[p] & ~PROW_DEAD;
+        bool dead = false;
+        if (gp.best_lr)
+            for (int b = A.colstart[i2]; b < A.colstart[i2 + 1]; ++b) {
+                const int q = A.cpair[b];
+                const int i1q = A.prow[q] & ~PROW_DEAD;
+                dead = dead || (i1q < i1 && static_cast<int>(A.pair[q] & 511u) <= d);
+            }
+        if (dead) A.prow[p] = static_cast<uint16_t>(i1 | PROW_DEAD);
+    }
+    if (gp.best_lr) {
+        for (int i2 = tid; i2 < n2; i2 += T) {
+            uint32_t best = 0xFFFFFFFFu; // D << 16 | i1
+            for (int b = A.colstart[i2]; b < A.colstart[i2 + 1]; ++b) {
+                const int q = A.cpair[b];
+                best = min(best, ((A.pair[q] & 511u) << 16) | static_cast<uint32_t>(A.prow[q] & ~PROW_DEAD));
+            }
+            A.colaux[i2] = (best == 0xFFFFFFFFu) ? -1 : static_cast<int32_t>(best & 0xFFFFu);
+        }
+    }
+    __syncthreads();
+    // P5
+    int accepted = 0;
+    for (int i1 = tid; i1 < n1; i1 += T) {
+        uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT;
+        for (int p = A.rowoff[i1]; p < A.rowoff[i1 + 1]; ++p) {
+            const uint32_t v = A.pair[p];
+            if (v != PAIR_INVALID && !(A.prow[p] & PROW_DEAD))
+                top2_insert(b0, b1, ((v & 511u) << GRID_KEY_BITS) | (v >> 9));
+        }
+        if (b0 != KEY32_ABSENT) {
+            const int best_d = static_cast<int>(b0 >> GRID_KEY_BITS);
+            const int best_d2 = (b1 == KEY32_ABSENT) ? 0x7FFFFFFF : static_cast<int>(b1 >> GRID_KEY_BITS);
+            if (static_cast<double>(best_d) < __dmul_rn(static_cast<double>(best_d2), gp.ratio)) {
+                job.m12[i1] = static_cast<int32_t>(b0 & ((1u << GRID_KEY_BITS) - 1));
+                ++accepted;
+            }
+        }
+    }
+    if (accepted) atomicAdd(s_count, accepted);
+    __syncthreads();
+    // P6: every entry >= 0, stale ones included
+    if (gp.best_lr) {
+        int culled = 0;
+        for (int i1 = tid; i1 < n1; i1 += T) {
+            const int32_t i2 = job.m12[i1];
+            if (i2 >= 0) {
+                const int back = (i2 < n2) ? A.colaux[i2] : -1;
+                if (back != i1) {
+                    job.m12[i1] = -1;
+                    ++culled;
+                }
+            }
+        }
+        if (culled) atomicSub(s_count, culled);
+        __syncthreads();
+    }
+    return true;
 }
 
 // ---- fused single-CTA kernel: one job per CTA (blockIdx.x), everything in one launch --------------

@@ -150,6 +150,11 @@ struct KnnPlan {
     int n_workers = 1;
 };
 
+// frame pipeline: candidate slots per query row the pair-list form is sized for (points, lines); options
+// "frames_pairs_p" / "frames_pairs_l", 0 = chunk phases only.  Lines default to the chunk phases: a segment
+// sits in ~8 cells, so a row holds ~20 slots for ~6 distinct candidates, the slot arrays push the CTA to one
+// per SM and the measured stereo-lines stage is 6x slower than with the chunk phases (profiles/r1_frames.md).
+int g_frames_pairs_per_row[2] = {8, 0};
 int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
 
 // -1 = automatic (variant 2 for long slices, 1 otherwise); 0/1/2 force a variant (measurement only)
@@ -288,6 +293,10 @@ PLM_API int plm_set_option(const char *key, int value) {
     }
     if (std::strcmp(key, "grid_cluster") == 0) {
         g_grid_cluster = value ? 1 : 0;
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "frames_pairs_p") == 0 || std::strcmp(key, "frames_pairs_l") == 0) {
+        g_frames_pairs_per_row[key[13] == 'l' ? 1 : 0] = std::max(0, std::min(value, 64));
         return PLM_OK;
     }
     return fail(PLM_E_INVALID, std::string("unknown option ") + key);

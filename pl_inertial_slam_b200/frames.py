@@ -97,13 +97,32 @@ class FramePipeline:
         L.check(self.lib.plm_frames_upload(self._h, _vp(desc_arena), len(desc_arena), _vp(kp_arena), len(kp_arena),
                                            _vp(ln_arena), len(ln_arena), _vp(frames), len(frames), C.byref(c)),
                 "plm_frames_upload")
+        self.set_layout(frames)
+
+    def run(self) -> None:
+        L.check(self.lib.plm_frames_run(self._h), "plm_frames_run")
+
+    def set_layout(self, frames: np.ndarray) -> None:
         self.n_frames = len(frames)
         self.off_p = np.concatenate([[0], np.cumsum(frames["n_pl"].astype(np.int64))])
         self.off_l = np.concatenate([[0], np.cumsum(frames["n_ll"].astype(np.int64))])
         self.NP, self.NL = int(self.off_p[-1]), int(self.off_l[-1])
 
-    def run(self) -> None:
-        L.check(self.lib.plm_frames_run(self._h), "plm_frames_run")
+    def process(self, desc_arena, kp_arena, ln_arena, frames: np.ndarray, cfg: FrameConfig,
+                out: Optional[Dict[str, np.ndarray]] = None, chunk_frames: int = 256) -> Dict[str, np.ndarray]:
+        """upload + run + fetch as one chunk-pipelined call (plm_frames_process)."""
+        assert frames.dtype == L.FRAME_REC_DTYPE
+        frames = np.ascontiguousarray(frames)
+        self.set_layout(frames)
+        out = self.alloc_outputs() if out is None else out
+        o = L.FramesOut()
+        for name in self.OUTPUTS:
+            setattr(o, name, _vp(out.get(name)))
+        c = cfg.to_c()
+        L.check(self.lib.plm_frames_process(self._h, _vp(desc_arena), len(desc_arena), _vp(kp_arena), len(kp_arena),
+                                            _vp(ln_arena), len(ln_arena), _vp(frames), len(frames), C.byref(c),
+                                            C.byref(o), int(chunk_frames)), "plm_frames_process")
+        return out
 
     def alloc_outputs(self, names=None, pinned: bool = False) -> Dict[str, np.ndarray]:
         out = {}

@@ -193,3 +193,60 @@ def test_repeated_runs_are_identical():
         for k in ("counts", "f2f_m12_p", "f2f_m12_l", "stereo_m12_p", "stereo_m12_l", "kept_p", "kept_l"):
             assert np.array_equal(first[k], again[k]), k
     pipe.close()
+
+
+@pytest.mark.parametrize("pairs_p,pairs_l", [(0, 0), (1, 2), (8, 32), (64, 64)])
+def test_pair_list_and_chunk_paths_agree(pairs_p, pairs_l):
+    """The stereo matcher has two forms (pair list / chunk phases); both must give the oracle's result,
+    also when only some frames overflow the pair list."""
+    lib = L.load()
+    try:
+        L.check(lib.plm_set_option(b"frames_pairs_p", pairs_p), "opt")
+        L.check(lib.plm_set_option(b"frames_pairs_l", pairs_l), "opt")
+        rp = synth.make_replay(synth.SEED0 + 34, 6, mean_pts=400, mean_lines=120)
+        kp, ln, rec = replay_frame_records(rp)
+        # pile the features of two frames into a corner so that windows hold dozens of candidates
+        for f in (2, 4):
+            a, n = int(rec["kp_l"][f]), int(rec["n_pl"][f])
+            kp[a:a + n] = kp[a:a + n] * np.float32(0.08) + np.float32(20.0)
+            b = int(rec["kp_r"][f])
+            kp[b:b + n] = kp[b:b + n] * np.float32(0.08) + np.float32(18.0)
+            a, n = int(rec["ln_l"][f]), int(rec["n_ll"][f])
+            ln[a:a + n] = ln[a:a + n] * np.float32(0.15) + np.float32(25.0)
+            b = int(rec["ln_r"][f])
+            ln[b:b + n] = ln[b:b + n] * np.float32(0.15) + np.float32(23.0)
+        check(rp.arena, kp, ln, rec, FrameConfig())
+    finally:
+        lib.plm_set_option(b"frames_pairs_p", 8)
+        lib.plm_set_option(b"frames_pairs_l", 0)
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 7, 256])
+def test_pipelined_process_equals_staged_calls(chunk):
+    """plm_frames_process (chunks over three streams) gives the same outputs as upload / run / fetch."""
+    import torch
+    rp = synth.make_replay(synth.SEED0 + 35, 20, mean_pts=250, mean_lines=80)
+    kp, ln, rec = replay_frame_records(rp)
+    cfg = FrameConfig()
+    ref_out = check(rp.arena, kp, ln, rec, cfg)
+    pipe = FramePipeline()
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    pipe.set_layout(rec)
+    out = pipe.alloc_outputs(pinned=True)
+    for _ in range(2):  # second pass reuses the buffers of the first
+        for v in out.values():
+            v.fill_(-7)
+        pipe.process(pin(rp.arena), pin(kp), pin(ln), rec, cfg, out, chunk_frames=chunk)
+        for name, want in ref_out.items():
+            got = out[name].numpy()
+            if name.startswith(("kept", "stereo_m12", "f2f", "counts")):
+                assert np.array_equal(got, want), name
+            else:  # double outputs: only the kept prefix of each frame is defined
+                off = pipe.off_p if name.startswith("pt_") else pipe.off_l
+                col = 1 if name.startswith("pt_") else 3
+                for f in range(len(rec)):
+                    k = int(ref_out["counts"][f, col])
+                    lo = int(off[f])
+                    assert np.array_equal(got[lo:lo + k], want[lo:lo + k], equal_nan=True), (name, f)
+    assert pipe.d2h_bytes > 0 and pipe.h2d_bytes >= rp.arena.nbytes + kp.nbytes + ln.nbytes
+    pipe.close()
