@@ -261,8 +261,9 @@ int plm_frames_upload(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows,
 int plm_frames_run(plm_frames *fr);
 /* Device -> host copy of the requested outputs + stream sync. */
 int plm_frames_fetch(plm_frames *fr, const plm_frames_out *out);
-/* upload + run + fetch as ONE pipelined call: the frames are cut into chunks of chunk_frames consecutive
- * frames (<= 0: 256) and the chunks flow through three streams -- host -> device copy of chunk k + 1, the
+/* upload + run + fetch as ONE pipelined call: the frames are cut into chunks of at most chunk_frames
+ * consecutive frames (<= 0: 256; the first chunks are shorter so that copying starts early) and the chunks
+ * flow through three streams -- host -> device copy of chunk k + 1, the
  * four launches of chunk k and the device -> host copy of chunk k - 1 overlap (both copy engines and the SMs
  * busy at once), and the host-side preparation of a chunk overlaps with the device work of the previous ones.
  * Arenas and outputs should be pinned host memory (pageable memory still works, without the overlap).

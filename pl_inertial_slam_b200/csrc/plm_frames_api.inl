@@ -29,7 +29,7 @@ struct plm_frames {
     size_t o_sjobs_p = 0, o_sjobs_l = 0, o_fjobs_p = 0, o_fjobs_l = 0;
     size_t o_m12_p = 0, o_m12_l = 0, o_kept_p = 0, o_kept_l = 0, o_pt_disp = 0, o_pt_P = 0, o_ls_disp = 0, o_ls_sP = 0,
            o_ls_eP = 0, o_ls_le = 0, o_f2f_p = 0, o_f2f_l = 0, o_counts = 0;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_lines = nullptr;
     std::vector<cudaEvent_t> events;
     int64_t h2d = 0, d2h = 0;
     bool ready = false;
@@ -85,23 +85,23 @@ inline long long line_walk_cells(double x1, double y1, double x2, double y2) {
 }
 
 template <int THREADS>
-int launch_stereo(plm_ctx *ctx, const plm::StereoJob *jobs, int n_jobs, const plm::FrameCfg &cfg,
+int launch_stereo(plm_ctx *ctx, cudaStream_t stream, const plm::StereoJob *jobs, int n_jobs, const plm::FrameCfg &cfg,
                   const plm::StereoCaps &caps, size_t smem) {
     if (n_jobs == 0) return PLM_OK;
     CU_TRY(cudaFuncSetAttribute(plm::stereo_frame_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-    plm::stereo_frame_kernel<THREADS><<<n_jobs, THREADS, smem, ctx->stream>>>(jobs, cfg, caps);
+    plm::stereo_frame_kernel<THREADS><<<n_jobs, THREADS, smem, stream>>>(jobs, cfg, caps);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;
 }
 
 template <int THREADS>
-int launch_f2f(plm_ctx *ctx, const plm::F2FJob *jobs, int n_jobs, int best_lr, size_t smem) {
+int launch_f2f(plm_ctx *ctx, cudaStream_t stream, const plm::F2FJob *jobs, int n_jobs, int best_lr, size_t smem) {
     if (n_jobs == 0) return PLM_OK;
     CU_TRY(cudaFuncSetAttribute(plm::f2f_match_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-    plm::f2f_match_kernel<THREADS><<<n_jobs, THREADS, smem, ctx->stream>>>(jobs, best_lr);
+    plm::f2f_match_kernel<THREADS><<<n_jobs, THREADS, smem, stream>>>(jobs, best_lr);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;
@@ -193,45 +193,58 @@ int frames_layout(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows, con
     return PLM_OK;
 }
 
-// Host preparation of frames [f0, f1): shared-memory capacities, job tables into the pinned staging block
-// (at this chunk's rows), then the host -> device copies of the tables and of the chunk's arena slices on
-// `s`.  Appends the chunk to fr->chunks.
-int frames_chunk_in(plm_frames *fr, const uint8_t *desc_arena, const float *kp_arena, const float *ln_arena,
-                    const plm_frame_rec *frames, int f0, int f1, cudaStream_t s) {
-    plm_ctx *ctx = fr->ctx;
-    const plm::FrameCfg &g = fr->cfg;
+struct FrameSpan {
+    int64_t lo = INT64_MAX, hi = 0;
+    void add(int64_t off, int64_t n) {
+        if (n > 0) {
+            lo = std::min(lo, off);
+            hi = std::max(hi, off + n);
+        }
+    }
+};
+
+// Result of the host-only preparation of a chunk (may run on a helper thread: no CUDA calls, no
+// thread-local error state).
+struct FrameChunkPrep {
     plm_frames_chunk ch;
+    FrameSpan sd[4], sk[2], sn[2]; // arena slices: descriptors (4 sets), keypoints (l/r), segments (l/r)
+    int status = PLM_OK;
+    const char *error = "";
+};
+
+// Host preparation of frames [f0, f1): shared-memory capacities, arena slices and the job tables, written
+// into the pinned staging block at this chunk's rows.
+FrameChunkPrep frames_chunk_prep(const plm_frames *fr, const float *ln_arena, const plm_frame_rec *frames, int f0, int f1) {
+    FrameChunkPrep out;
+    const plm_ctx *ctx = fr->ctx;
+    const plm::FrameCfg &g = fr->cfg;
+    plm_frames_chunk &ch = out.ch;
+    FrameSpan *sd = out.sd, *sk = out.sk, *sn = out.sn;
+    auto bad = [&](int status, const char *msg) {
+        out.status = status;
+        out.error = msg;
+        return out;
+    };
     ch.f0 = f0;
     ch.f1 = f1;
     int cap_pl = 1, cap_pr = 1, cap_ll = 1, cap_lr = 1;
     long long cap_items_l = 1;
     const long long walk_max = static_cast<long long>(g.grid_rows) + g.grid_cols + 2;
-    // arena slices of the chunk, one running span per feature set (left / right sets usually live in
-    // different regions of an arena); overlapping spans are merged before copying
-    struct Span {
-        int64_t lo = INT64_MAX, hi = 0;
-        void add(int64_t off, int64_t n) {
-            if (n > 0) {
-                lo = std::min(lo, off);
-                hi = std::max(hi, off + n);
-            }
-        }
-    };
-    Span sd[4], sk[2], sn[2];
     for (int f = f0; f < f1; ++f) {
         const plm_frame_rec &r = frames[f];
         cap_pl = std::max(cap_pl, r.n_pl);
         cap_pr = std::max(cap_pr, r.n_pr);
         cap_ll = std::max(cap_ll, r.n_ll);
         cap_lr = std::max(cap_lr, r.n_lr);
-        long long items = 0;
-        for (int j = 0; j < r.n_lr; ++j) {
-            const float *l = ln_arena + 4 * (r.ln_r + j);
+        long long items = 0, longest = 0;
+        const float *l = ln_arena + 4 * r.ln_r;
+        for (int j = 0; j < r.n_lr; ++j, l += 4) {
             const long long n = line_walk_cells(double(l[0]) * g.inv_w, double(l[1]) * g.inv_h, double(l[2]) * g.inv_w,
                                                 double(l[3]) * g.inv_h);
-            if (n > walk_max) return fail(PLM_E_UNSUPPORTED, "line segment far outside the image (Bresenham walk too long)");
-            items += n;
+            longest = std::max(longest, n);
+            items += std::min(n, walk_max + 1);
         }
+        if (longest > walk_max) return bad(PLM_E_UNSUPPORTED, "line segment far outside the image (Bresenham walk too long)");
         cap_items_l = std::max(cap_items_l, items);
         sd[0].add(r.desc_pl, r.n_pl);
         sd[1].add(r.desc_pr, r.n_pr);
@@ -261,7 +274,7 @@ int frames_chunk_in(plm_frames *fr, const uint8_t *desc_arena, const float *kp_a
     ch.smem_fl = plm::f2f_smem(cap_fl, cap_fl);
     const size_t budget = ctx->smem_optin - 1024;
     if (ch.smem_p > budget || ch.smem_l > budget || ch.smem_fp > budget || ch.smem_fl > budget)
-        return fail(PLM_E_UNSUPPORTED, "frame too large for shared memory");
+        return bad(PLM_E_UNSUPPORTED, "frame too large for shared memory");
 
     // ---- job tables of the chunk ---------------------------------------------------------------------------
     char *D = fr->d_buf;
@@ -336,6 +349,21 @@ int frames_chunk_in(plm_frames *fr, const uint8_t *desc_arena, const float *kp_a
             q.nnr = fr->nnr_l;
         }
     }
+    return out;
+}
+
+// Host -> device copies of a prepared chunk on `s`: its rows of the job tables and its arena slices (a
+// scattered arena layout only makes the slices larger).  Appends the chunk to fr->chunks.
+int frames_chunk_copy(plm_frames *fr, FrameChunkPrep &pr, const uint8_t *desc_arena, const float *kp_arena,
+                      const float *ln_arena, cudaStream_t s) {
+    if (pr.status != PLM_OK) return fail(pr.status, pr.error);
+    char *D = fr->d_buf;
+    const int f0 = pr.ch.f0, f1 = pr.ch.f1;
+    const size_t F = size_t(std::max(fr->n_frames, 1));
+    const plm::StereoJob *sp = reinterpret_cast<const plm::StereoJob *>(fr->h_tab);
+    const plm::StereoJob *sl = sp + F;
+    const plm::F2FJob *fp = reinterpret_cast<const plm::F2FJob *>(sl + F);
+    const plm::F2FJob *fl = fp + F;
     const size_t nf = size_t(f1 - f0);
     if (nf) {
         CU_TRY(cudaMemcpyAsync(D + fr->o_sjobs_p + f0 * sizeof(plm::StereoJob), sp + f0, nf * sizeof(plm::StereoJob), cudaMemcpyHostToDevice, s));
@@ -344,9 +372,8 @@ int frames_chunk_in(plm_frames *fr, const uint8_t *desc_arena, const float *kp_a
         CU_TRY(cudaMemcpyAsync(D + fr->o_fjobs_l + f0 * sizeof(plm::F2FJob), fl + f0, nf * sizeof(plm::F2FJob), cudaMemcpyHostToDevice, s));
         fr->h2d += static_cast<int64_t>(2 * nf * (sizeof(plm::StereoJob) + sizeof(plm::F2FJob)));
     }
-    // the chunk's slices of every arena (a scattered layout only makes the slices larger)
-    auto copy_spans = [&](Span *sp_, int n_sp, size_t dev_off, const void *host, size_t elem) -> cudaError_t {
-        std::sort(sp_, sp_ + n_sp, [](const Span &x, const Span &y) { return x.lo < y.lo; });
+    auto copy_spans = [&](FrameSpan *sp_, int n_sp, size_t dev_off, const void *host, size_t elem) -> cudaError_t {
+        std::sort(sp_, sp_ + n_sp, [](const FrameSpan &x, const FrameSpan &y) { return x.lo < y.lo; });
         for (int i = 0; i < n_sp; ++i) {
             if (sp_[i].hi <= sp_[i].lo) continue;
             int64_t lo = sp_[i].lo, hi = sp_[i].hi;
@@ -358,20 +385,27 @@ int frames_chunk_in(plm_frames *fr, const uint8_t *desc_arena, const float *kp_a
         }
         return cudaSuccess;
     };
-    CU_TRY(copy_spans(sd, 4, fr->o_desc, desc_arena, 32));
-    CU_TRY(copy_spans(sk, 2, fr->o_kp, kp_arena, 8));
-    CU_TRY(copy_spans(sn, 2, fr->o_ln, ln_arena, 16));
-    fr->chunks.push_back(ch);
+    CU_TRY(copy_spans(pr.sd, 4, fr->o_desc, desc_arena, 32));
+    CU_TRY(copy_spans(pr.sk, 2, fr->o_kp, kp_arena, 8));
+    CU_TRY(copy_spans(pr.sn, 2, fr->o_ln, ln_arena, 16));
+    fr->chunks.push_back(pr.ch);
     return PLM_OK;
 }
 
-// The four launches of a chunk on the context's stream (after clearing the slots the kernels do not write).
-int frames_chunk_run(plm_frames *fr, const plm_frames_chunk &ch) {
+// The four launches of chunk number k.  Points and lines are independent chains (stereo stage -> temporal
+// stage), so the line chain runs on a second stream forked from / joined back into the context's stream:
+// a chunk of a few hundred frames does not fill the chip with one kernel at a time.
+int frames_chunk_run(plm_frames *fr, const plm_frames_chunk &ch, size_t k) {
     plm_ctx *ctx = fr->ctx;
     char *D = fr->d_buf;
     const int n = ch.f1 - ch.f0;
     if (n <= 0) return PLM_OK;
     cudaStream_t s = ctx->stream;
+    if (!fr->s_lines) CU_TRY(cudaStreamCreateWithFlags(&fr->s_lines, cudaStreamNonBlocking));
+    cudaEvent_t e_fork, e_join;
+    int st;
+    if ((st = fr->event(4 * k + 3, &e_fork)) != PLM_OK) return st;
+    if ((st = fr->event(4 * k + 4, &e_join)) != PLM_OK) return st;
     const int64_t p0 = fr->lp_off[ch.f0], p1 = fr->lp_off[ch.f1], l0 = fr->ll_off[ch.f0], l1 = fr->ll_off[ch.f1];
     CU_TRY(cudaMemsetAsync(D + fr->o_counts + size_t(ch.f0) * 24, 0, size_t(n) * 24, s));
     // slots past a frame's kept count (and the last frame's f2f range) read as -1
@@ -383,18 +417,21 @@ int frames_chunk_run(plm_frames *fr, const plm_frames_chunk &ch) {
         CU_TRY(cudaMemsetAsync(D + fr->o_kept_l + size_t(l0) * 4, 0xFF, size_t(l1 - l0) * 4, s));
         CU_TRY(cudaMemsetAsync(D + fr->o_f2f_l + size_t(l0) * 4, 0xFF, size_t(l1 - l0) * 4, s));
     }
-    int st;
-    if ((st = launch_stereo<FRAMES_THREADS_P>(ctx, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n,
-                                              fr->cfg, ch.caps_p, ch.smem_p)) != PLM_OK) return st;
-    if ((st = launch_stereo<FRAMES_THREADS_L>(ctx, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0, n,
-                                              fr->cfg, ch.caps_l, ch.smem_l)) != PLM_OK) return st;
+    CU_TRY(cudaEventRecord(e_fork, s));
+    CU_TRY(cudaStreamWaitEvent(fr->s_lines, e_fork, 0));
     const int t0 = std::max(ch.f0, 1); // frame 0 has no predecessor
+    if ((st = launch_stereo<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n,
+                                              fr->cfg, ch.caps_p, ch.smem_p)) != PLM_OK) return st;
+    if ((st = launch_stereo<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0,
+                                              n, fr->cfg, ch.caps_l, ch.smem_l)) != PLM_OK) return st;
     if (ch.f1 > t0) {
-        if ((st = launch_f2f<FRAMES_THREADS_P>(ctx, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
+        if ((st = launch_f2f<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
                                                fr->cfg.best_lr, ch.smem_fp)) != PLM_OK) return st;
-        if ((st = launch_f2f<FRAMES_THREADS_L>(ctx, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0, ch.f1 - t0,
-                                               fr->cfg.best_lr, ch.smem_fl)) != PLM_OK) return st;
+        if ((st = launch_f2f<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0,
+                                               ch.f1 - t0, fr->cfg.best_lr, ch.smem_fl)) != PLM_OK) return st;
     }
+    CU_TRY(cudaEventRecord(e_join, fr->s_lines));
+    CU_TRY(cudaStreamWaitEvent(s, e_join, 0));
     return PLM_OK;
 }
 
@@ -458,6 +495,10 @@ PLM_API int plm_frames_destroy(plm_frames *fr) {
         cudaStreamSynchronize(fr->s_out);
         cudaStreamDestroy(fr->s_out);
     }
+    if (fr->s_lines) {
+        cudaStreamSynchronize(fr->s_lines);
+        cudaStreamDestroy(fr->s_lines);
+    }
     for (cudaEvent_t e : fr->events) cudaEventDestroy(e);
     if (fr->d_buf) cudaFree(fr->d_buf);
     if (fr->h_tab) cudaFreeHost(fr->h_tab);
@@ -476,7 +517,8 @@ PLM_API int plm_frames_upload(plm_frames *fr, const uint8_t *desc_arena, int64_t
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
     if ((st = frames_layout(fr, desc_arena, n_rows, kp_arena, n_kp, ln_arena, n_ln, frames, n_frames, c)) != PLM_OK) return st;
-    if ((st = frames_chunk_in(fr, desc_arena, kp_arena, ln_arena, frames, 0, n_frames, ctx->stream)) != PLM_OK) return st;
+    FrameChunkPrep pr = frames_chunk_prep(fr, ln_arena, frames, 0, n_frames);
+    if ((st = frames_chunk_copy(fr, pr, desc_arena, kp_arena, ln_arena, ctx->stream)) != PLM_OK) return st;
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     fr->ready = true;
     return PLM_OK;
@@ -487,8 +529,8 @@ PLM_API int plm_frames_run(plm_frames *fr) {
     plm_ctx *ctx = fr->ctx;
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
-    for (const plm_frames_chunk &ch : fr->chunks)
-        if ((st = frames_chunk_run(fr, ch)) != PLM_OK) return st;
+    for (size_t k = 0; k < fr->chunks.size(); ++k)
+        if ((st = frames_chunk_run(fr, fr->chunks[k], k)) != PLM_OK) return st;
     return PLM_OK;
 }
 
@@ -510,7 +552,11 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
     plm_ctx *ctx = fr->ctx;
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
+    const bool trace = std::getenv("PLM_FRAMES_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     if ((st = frames_layout(fr, desc_arena, n_rows, kp_arena, n_kp, ln_arena, n_ln, frames, n_frames, c)) != PLM_OK) return st;
+    if (trace) std::fprintf(stderr, "[plm_frames_process] layout done %.3f ms\n", since());
     if (!fr->s_in) CU_TRY(cudaStreamCreateWithFlags(&fr->s_in, cudaStreamNonBlocking));
     if (!fr->s_out) CU_TRY(cudaStreamCreateWithFlags(&fr->s_out, cudaStreamNonBlocking));
     if (chunk_frames <= 0) chunk_frames = 256;
@@ -519,28 +565,57 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
     if ((st = fr->event(0, &e_start)) != PLM_OK) return st;
     CU_TRY(cudaEventRecord(e_start, ctx->stream));
     CU_TRY(cudaStreamWaitEvent(fr->s_in, e_start, 0));
-    size_t k = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += chunk_frames, ++k) {
-        const int f1 = std::min(n_frames, f0 + chunk_frames);
+    // Host preparation of the chunks (capacities, job tables) runs on a few helper threads, in chunk order,
+    // ahead of this thread, which only issues the CUDA calls.
+    // chunk boundaries: the first chunks are short (32, 64, 128, ... frames) so that the copy engine starts
+    // after a few microseconds of host preparation instead of a full chunk's worth
+    std::vector<int> bounds{0};
+    for (int len = std::min(32, chunk_frames); bounds.back() < n_frames; len = std::min(2 * len, chunk_frames))
+        bounds.push_back(std::min(n_frames, bounds.back() + len));
+    const int n_chunks = static_cast<int>(bounds.size()) - 1;
+    std::vector<FrameChunkPrep> preps(static_cast<size_t>(n_chunks));
+    std::vector<std::atomic<int>> prepared(static_cast<size_t>(n_chunks));
+    for (auto &p : prepared) p.store(0, std::memory_order_relaxed);
+    std::atomic<int> next_chunk{0};
+    auto worker = [&]() {
+        for (int k = next_chunk.fetch_add(1); k < n_chunks; k = next_chunk.fetch_add(1)) {
+            preps[k] = frames_chunk_prep(fr, ln_arena, frames, bounds[k], bounds[k + 1]);
+            prepared[k].store(1, std::memory_order_release);
+        }
+    };
+    const int n_helpers = std::max(0, std::min({n_chunks - 1, 6, static_cast<int>(std::thread::hardware_concurrency()) - 1}));
+    std::vector<std::thread> helpers;
+    for (int i = 0; i < n_helpers; ++i) helpers.emplace_back(worker);
+    if (n_helpers == 0) worker();
+    for (int k = 0; k < n_chunks; ++k) {
+        const int f0 = bounds[k], f1 = bounds[k + 1];
         cudaEvent_t e_in, e_run;
-        if ((st = fr->event(1 + 2 * k, &e_in)) != PLM_OK) break;
-        if ((st = fr->event(2 + 2 * k, &e_run)) != PLM_OK) break;
-        if ((st = frames_chunk_in(fr, desc_arena, kp_arena, ln_arena, frames, f0, f1, fr->s_in)) != PLM_OK) break;
+        if ((st = fr->event(4 * size_t(k) + 1, &e_in)) != PLM_OK) break;
+        if ((st = fr->event(4 * size_t(k) + 2, &e_run)) != PLM_OK) break;
+        while (!prepared[k].load(std::memory_order_acquire)) std::this_thread::yield();
+        if ((st = frames_chunk_copy(fr, preps[k], desc_arena, kp_arena, ln_arena, fr->s_in)) != PLM_OK) break;
         if (cudaEventRecord(e_in, fr->s_in) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, e_in, 0) != cudaSuccess) {
             st = fail(PLM_E_CUDA, "event record / wait failed");
             break;
         }
-        if ((st = frames_chunk_run(fr, fr->chunks.back())) != PLM_OK) break;
+        if ((st = frames_chunk_run(fr, fr->chunks.back(), size_t(k))) != PLM_OK) break;
         if (cudaEventRecord(e_run, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(fr->s_out, e_run, 0) != cudaSuccess) {
             st = fail(PLM_E_CUDA, "event record / wait failed");
             break;
         }
         if ((st = frames_copy_out(fr, out, f0, f1, fr->s_out)) != PLM_OK) break;
+        if (trace) std::fprintf(stderr, "[plm_frames_process] chunk %d issued %.3f ms\n", k, since());
     }
+    next_chunk.store(n_chunks); // after a failure: helpers stop picking up chunks
+    for (std::thread &t : helpers) t.join();
     // drain all three streams even after a failure: the caller's buffers must not be in flight on return
     cudaStreamSynchronize(fr->s_in);
+    if (trace) std::fprintf(stderr, "[plm_frames_process] copy-in stream drained %.3f ms\n", since());
     cudaStreamSynchronize(ctx->stream);
+    if (fr->s_lines) cudaStreamSynchronize(fr->s_lines);
+    if (trace) std::fprintf(stderr, "[plm_frames_process] compute streams drained %.3f ms\n", since());
     cudaStreamSynchronize(fr->s_out);
+    if (trace) std::fprintf(stderr, "[plm_frames_process] copy-out stream drained %.3f ms\n", since());
     if (st != PLM_OK) return st;
     CU_TRY(cudaGetLastError());
     fr->ready = true;
