@@ -17,6 +17,8 @@
  *   plm_frames_*            StereoFrame::matchStereoPoints/Lines + StereoFrameHandler::matchF2FPoints/Lines
  *                           on the device (stereoFrame.cpp:131-184,320-409; stereoFrameHandler.cpp:158-207)
  *   plm_db_* / plm_dev_*    keyframe / local-map database  src/mapHandler.cpp:583-803, 3301-3409
+ *   plm_med_desc / plm_dev_med_desc   PLSLAM::MapPoint / MapLine::updateAverageDescDir (the producer of the
+ *                           map's med_desc rows)           src/mapFeatures.cpp:51-93, 121-163
  *
  * The C++ replacement of stvo-pl/src/matching.cpp that keeps the StVO:: signatures and calls this
  * ABI is pl_inertial_slam_b200/csrc/stvo_matching_gpu.cpp.
@@ -329,6 +331,28 @@ int64_t plm_db_size(const plm_db *db);
 void *plm_db_device_ptr(const plm_db *db);
 /* knn2 of host queries against the resident shard (H2D queries, D2H packed top-2). */
 int plm_db_knn2(plm_db *db, const uint8_t *q, int nq, size_t step, uint64_t idx_base, uint64_t *top2);
+
+/* ---- map landmarks: representative descriptor + mean observation direction -------------------- */
+/* PLSLAM::MapPoint::updateAverageDescDir (src/mapFeatures.cpp:51-93) and MapLine::updateAverageDescDir
+ * (:121-163), batched over n_lm landmarks.  Observations of landmark l are rows obs_start[l] ..
+ * obs_start[l+1]-1 of desc_obs (n_obs x 32 bytes, `step` apart) and of dir_obs (n_obs x 3 doubles, may be
+ * NULL together with med_dir).  Per landmark with n observations:
+ *   med_idx  = first row i whose value at sorted position int(1 + 0.5*(n-1)) of its Hamming distances to
+ *              all n rows (self included) is strictly smallest; 0 for n == 1 (constructor, :29-40),
+ *              -1 for an empty list;
+ *   med_desc = that descriptor (n_lm x 32 bytes, may be NULL; zeros for an empty list);
+ *   med_dir  = (sum of the directions in list order, from zero) / n in fp64 (n_lm x 3, may be NULL).
+ * obs_start must be non-decreasing within [0, n_obs] (PLM_E_INVALID otherwise).  Any n is supported;
+ * lists of up to 32 observations take the one-warp-per-landmark kernel. */
+int plm_med_desc(plm_ctx *ctx, const uint8_t *desc_obs, int64_t n_obs, size_t step, const double *dir_obs,
+                 const int32_t *obs_start, int n_lm, int32_t *med_idx, uint8_t *med_desc, double *med_dir);
+/* Same on device-resident arenas (all pointers are device pointers, rows contiguous and 16-byte aligned),
+ * enqueued on the context's stream without a host sync.  dst_rows_dev (may be NULL) scatters: landmark l
+ * writes its descriptor to row dst_rows[l] of med_desc_dev (< 0: not written) -- e.g. straight into the
+ * rows of a resident local-map shard.  A malformed obs_start range is treated as an empty list. */
+int plm_dev_med_desc(plm_ctx *ctx, const void *desc_obs_dev, int64_t n_obs, const double *dir_obs_dev,
+                     const int32_t *obs_start_dev, int n_lm, int32_t *med_idx_dev, void *med_desc_dev,
+                     const int32_t *dst_rows_dev, double *med_dir_dev);
 
 /* Tuning knobs (measurement only; results never depend on them):
  *   "knn_variant"  -1 = automatic (default), 0 = plain 8-POPC Hamming, 1 = carry-save 5-POPC,

@@ -2,7 +2,8 @@
 
 * ``oracle.port``  -- oracle/plm_oracle.c, the plain-C restatement (``_ref/libploracle.so``)
 * ``oracle.ref``   -- the reference itself, /root/reference/stvo-pl/src/{matching,gridStructure,
-  lineIterator}.cpp compiled unmodified (``_ref/libplref.so``; see oracle/Makefile)
+  lineIterator}.cpp and /root/reference/src/mapFeatures.cpp compiled unmodified
+  (``_ref/libplref.so``; see oracle/Makefile)
 
 Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU arms may import this package; the
 product (pl_inertial_slam_b200) never does.  Nothing here reads /root/reference at run time: the
@@ -111,8 +112,25 @@ class _Port:
             L.plo_stereo_lines.argtypes = [_f32p, _u8p, C.c_int, _f32p, _u8p, C.c_int, C.c_double, C.c_double, C.c_int,
                                            C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                            C.c_double, C.c_double, _f64p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]
+            L.plo_med_desc.restype = None
+            L.plo_med_desc.argtypes = [_u8p, C.c_size_t, _f64p, _i32p, C.c_int, _i32p, _u8p, _f64p]
             self._lib = L
         return self._lib
+
+    def med_desc(self, desc, dirs, obs_start):
+        """MapPoint / MapLine::updateAverageDescDir over a batch of landmarks (src/mapFeatures.cpp:51-93,
+        :121-163) -> (med_idx int32[n_lm], med_desc uint8[n_lm, 32], med_dir float64[n_lm, 3])."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        obs_start, osp = _i32(obs_start)
+        n_lm = len(obs_start) - 1
+        dirs_c = None if dirs is None else np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+        med_idx = np.empty(n_lm, np.int32)
+        med = np.zeros((n_lm, 32), np.uint8)
+        med_dir = np.zeros((n_lm, 3), np.float64)
+        self.lib.plo_med_desc(desc.ctypes.data_as(_u8p), 32, None if dirs_c is None else dirs_c.ctypes.data_as(_f64p),
+                              osp, n_lm, med_idx.ctypes.data_as(_i32p), med.ctypes.data_as(_u8p),
+                              med_dir.ctypes.data_as(_f64p))
+        return med_idx, med, med_dir
 
     def distance(self, a, b) -> int:
         a = np.ascontiguousarray(a, np.uint8).reshape(32)
@@ -335,8 +353,25 @@ class _Ref:
             L.plref_line_coords.restype = C.c_int
             L.plref_line_coords.argtypes = [C.c_double] * 4 + [_i32p, C.c_int]
             L.plref_normalize.argtypes = [_f64p]
+            if hasattr(L, "plref_med_desc"):  # the reference build only (not the C++ drop-in harness)
+                L.plref_med_desc.restype = None
+                L.plref_med_desc.argtypes = [C.c_int, _u8p, C.c_size_t, _f64p, _i32p, C.c_int, _i32p, _f64p]
             self._lib = L
         return self._lib
+
+    def med_desc(self, desc, dirs, obs_start, is_line=False):
+        """PLSLAM::MapPoint / MapLine built observation by observation from the reference's own
+        src/mapFeatures.cpp -> (med_idx, med_dir)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        obs_start, osp = _i32(obs_start)
+        n_lm = len(obs_start) - 1
+        dirs_c = None if dirs is None else np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+        med_idx = np.empty(n_lm, np.int32)
+        med_dir = np.zeros((n_lm, 3), np.float64)
+        self.lib.plref_med_desc(int(bool(is_line)), desc.ctypes.data_as(_u8p), 32,
+                                None if dirs_c is None else dirs_c.ctypes.data_as(_f64p), osp, n_lm,
+                                med_idx.ctypes.data_as(_i32p), med_dir.ctypes.data_as(_f64p))
+        return med_idx, med_dir
 
     def set_threads(self, n: int):
         self.lib.plref_set_threads(int(n))

@@ -699,3 +699,78 @@ PLO_API int plo_stereo_lines(const float *ln_l, const uint8_t *d_l, int n_l, con
     free(xyxy); free(cs); free(ci); free(dirs); free(keep); free(dse);
     return kept;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Map landmarks: representative descriptor and mean observation direction.
+ *
+ * src/mapFeatures.cpp:51-93 (PLSLAM::MapPoint::updateAverageDescDir) and :121-163
+ * (PLSLAM::MapLine::updateAverageDescDir) -- the two bodies are identical.  For a landmark with
+ * n observations:
+ *   - conf_desc(i,j) = cv::norm(desc_i, desc_j, NORM_HAMMING) (:59-68; 256-bit popcount of the
+ *     xor, symmetric, zero diagonal, stored as float and read back as int -- exact for 0..256);
+ *   - per row i the distances are sorted and dist[int(1 + 0.5 * (n - 1))] is its "median"
+ *     (:75-79; the self distance 0 takes part);
+ *   - the first row with the strictly smallest median wins (:80-84, start value 99999);
+ *   - med_obs_dir = (sum of dir_list in list order) / n (:88-91).  The reference adds into an
+ *     uninitialised Eigen vector (:88); this restatement starts the sum at zero, which is what
+ *     the code means and what the compiled reference (zero-initialising Eigen stand-in,
+ *     oracle/shim_map/) does.
+ * A landmark is created with one observation (ctor, :29-40: med_desc = that descriptor,
+ * med_obs_dir = its direction) and updateAverageDescDir only runs from n = 2 on (:42-50); for
+ * n = 1 the index int(1 + 0) would be out of range, so n = 1 follows the constructor.
+ *
+ * Batched over landmarks: observations of landmark l are rows obs_start[l] .. obs_start[l+1]-1
+ * of desc (n_obs x 32, `step` bytes apart) and of dirs (n_obs x 3, may be NULL).  Outputs:
+ * med_idx[l] = winning position inside the landmark's list (-1 for an empty list), med_desc
+ * (n_lm x 32, may be NULL), med_dir (n_lm x 3, may be NULL).
+ */
+static int plo_cmp_int(const void *a, const void *b)
+{
+    const int x = *(const int *)a, y = *(const int *)b;
+    return (x > y) - (x < y);
+}
+
+PLO_API void plo_med_desc(const uint8_t *desc, size_t step, const double *dirs, const int32_t *obs_start,
+                          int n_lm, int32_t *med_idx, uint8_t *med_desc, double *med_dir)
+{
+    for (int l = 0; l < n_lm; l++) {
+        const int lo = obs_start[l], n = obs_start[l + 1] - lo;
+        int best = n > 0 ? 0 : -1;
+        if (n >= 2) {
+            int *conf = (int *)malloc(sizeof(int) * (size_t)n * (size_t)n);
+            int *row = (int *)malloc(sizeof(int) * (size_t)n);
+            for (int i = 0; i < n; i++) {
+                conf[(size_t)i * n + i] = 0;
+                for (int j = i + 1; j < n; j++) {
+                    const int d = plo_hamming256(desc + (size_t)(lo + i) * step, desc + (size_t)(lo + j) * step);
+                    conf[(size_t)i * n + j] = d;
+                    conf[(size_t)j * n + i] = d;
+                }
+            }
+            int max_dist = 99999;
+            for (int i = 0; i < n; i++) {
+                memcpy(row, conf + (size_t)i * n, sizeof(int) * (size_t)n);
+                qsort(row, (size_t)n, sizeof(int), plo_cmp_int);
+                const int med = row[(int)(1 + 0.5 * (n - 1))];
+                if (med < max_dist) {
+                    max_dist = med;
+                    best = i;
+                }
+            }
+            free(conf);
+            free(row);
+        }
+        med_idx[l] = best;
+        if (med_desc) {
+            if (best >= 0) memcpy(med_desc + (size_t)l * 32, desc + (size_t)(lo + best) * step, 32);
+            else memset(med_desc + (size_t)l * 32, 0, 32);
+        }
+        if (med_dir && dirs) {
+            double s[3] = {0.0, 0.0, 0.0};
+            for (int i = 0; i < n; i++)
+                for (int c = 0; c < 3; c++) s[c] += dirs[3 * (size_t)(lo + i) + c];
+            for (int c = 0; c < 3; c++) /* n == 1: the constructor's plain copy (:38) */
+                med_dir[3 * (size_t)l + c] = (n >= 2) ? s[c] / n : (n == 1 ? dirs[3 * (size_t)lo + c] : 0.0);
+        }
+    }
+}

@@ -135,6 +135,8 @@ SIGNATURES = {
     "plm_db_size": (C.c_int64, [vp]),
     "plm_db_device_ptr": (vp, [vp]),
     "plm_db_knn2": (C.c_int, [vp, u8p, C.c_int, C.c_size_t, C.c_uint64, u64p]),
+    "plm_med_desc": (C.c_int, [vp, u8p, C.c_int64, C.c_size_t, f64p, i32p, C.c_int, i32p, u8p, f64p]),
+    "plm_dev_med_desc": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp, vp, vp, vp]),
     "plm_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "plm_measure_int_peaks": (C.c_int, [vp, f64p, f64p]),
 }

@@ -22,6 +22,7 @@
 #include "plm_frames.cuh"
 #include "plm_grid.cuh"
 #include "plm_knn2.cuh"
+#include "plm_map.cuh"
 #include "plm_micro.cuh"
 #include "plm_stereo.cuh"
 
@@ -1052,6 +1053,100 @@ PLM_API int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int 
     plm::m21_from_keys_kernel<<<(n2 + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(m21key_dev), n2, m21_dev);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Map landmarks: MapPoint / MapLine::updateAverageDescDir (src/mapFeatures.cpp:51-93, :121-163)
+namespace {
+
+// Both launches of a batch; `work` (1 + n_lm int32) is scratch for the list of long observation lists.
+int launch_med_desc(plm_ctx *ctx, plm::MedArgs a) {
+    CU_TRY(cudaMemsetAsync(a.work, 0, 4, ctx->stream));
+    const int ctas = std::min((a.n_lm + plm::MED_WARPS - 1) / plm::MED_WARPS, ctx->sm_count * 32);
+    plm::med_desc_warp_kernel<<<ctas, 32 * plm::MED_WARPS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    plm::med_desc_cta_kernel<<<ctx->sm_count * 2, plm::MED_CTA_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+} // namespace
+
+PLM_API int plm_dev_med_desc(plm_ctx *ctx, const void *desc_obs_dev, int64_t n_obs, const double *dir_obs_dev,
+                             const int32_t *obs_start_dev, int n_lm, int32_t *med_idx_dev, void *med_desc_dev,
+                             const int32_t *dst_rows_dev, double *med_dir_dev) {
+    if (n_lm < 0 || n_obs < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_lm == 0) return PLM_OK;
+    if (!obs_start_dev || !med_idx_dev || (n_obs > 0 && !desc_obs_dev)) return fail(PLM_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(desc_obs_dev) | reinterpret_cast<uintptr_t>(med_desc_dev)) & 15)
+        return fail(PLM_E_INVALID, "descriptor rows must be 16-byte aligned");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    if ((st = ctx->ensure_device(size_t(n_lm + 1) * 4)) != PLM_OK) return st;
+    plm::MedArgs a{};
+    a.desc = static_cast<const uint4 *>(desc_obs_dev);
+    a.dirs = dir_obs_dev;
+    a.obs_start = obs_start_dev;
+    a.n_obs = n_obs;
+    a.n_lm = n_lm;
+    a.med_idx = med_idx_dev;
+    a.med_desc = static_cast<uint4 *>(med_desc_dev);
+    a.dst_rows = dst_rows_dev;
+    a.med_dir = med_dir_dev;
+    a.work = reinterpret_cast<int32_t *>(ctx->d_buf);
+    return launch_med_desc(ctx, a);
+}
+
+PLM_API int plm_med_desc(plm_ctx *ctx, const uint8_t *desc_obs, int64_t n_obs, size_t step, const double *dir_obs,
+                         const int32_t *obs_start, int n_lm, int32_t *med_idx, uint8_t *med_desc, double *med_dir) {
+    if (n_lm < 0 || n_obs < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_lm == 0) return PLM_OK;
+    if (!obs_start || !med_idx || (n_obs > 0 && !desc_obs)) return fail(PLM_E_INVALID, "null pointer");
+    if (step < 32) return fail(PLM_E_INVALID, "step < 32");
+    if (n_obs > INT32_MAX) return fail(PLM_E_UNSUPPORTED, "more than 2^31 - 1 observations in one call");
+    if (obs_start[0] < 0 || obs_start[n_lm] > n_obs) return fail(PLM_E_INVALID, "obs_start outside [0, n_obs]");
+    for (int l = 0; l < n_lm; ++l)
+        if (obs_start[l + 1] < obs_start[l]) return fail(PLM_E_INVALID, "obs_start must be non-decreasing");
+    const bool want_dir = med_dir != nullptr && dir_obs != nullptr;
+    if (med_dir && !dir_obs) return fail(PLM_E_INVALID, "med_dir requested without dir_obs");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout L;
+    const size_t o_start = L.add(size_t(n_lm + 1) * 4);
+    const size_t o_desc = L.add(size_t(n_obs) * 32);
+    const size_t o_dirs = L.add(want_dir ? size_t(n_obs) * 24 : 0);
+    const size_t in_bytes = L.total;
+    const size_t o_idx = L.add(size_t(n_lm) * 4);
+    const size_t o_med = L.add(med_desc ? size_t(n_lm) * 32 : 0);
+    const size_t o_mdir = L.add(want_dir ? size_t(n_lm) * 24 : 0);
+    const size_t out_end = L.total;
+    const size_t o_work = L.add(size_t(n_lm + 1) * 4);
+    if ((st = ctx->ensure_pinned(out_end)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    std::memcpy(ctx->h_buf + o_start, obs_start, size_t(n_lm + 1) * 4);
+    pack_rows(ctx->h_buf + o_desc, desc_obs, n_obs, step);
+    if (want_dir) std::memcpy(ctx->h_buf + o_dirs, dir_obs, size_t(n_obs) * 24);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    plm::MedArgs a{};
+    a.desc = reinterpret_cast<const uint4 *>(ctx->d_buf + o_desc);
+    a.dirs = want_dir ? reinterpret_cast<const double *>(ctx->d_buf + o_dirs) : nullptr;
+    a.obs_start = reinterpret_cast<const int32_t *>(ctx->d_buf + o_start);
+    a.n_obs = n_obs;
+    a.n_lm = n_lm;
+    a.med_idx = reinterpret_cast<int32_t *>(ctx->d_buf + o_idx);
+    a.med_desc = med_desc ? reinterpret_cast<uint4 *>(ctx->d_buf + o_med) : nullptr;
+    a.dst_rows = nullptr;
+    a.med_dir = want_dir ? reinterpret_cast<double *>(ctx->d_buf + o_mdir) : nullptr;
+    a.work = reinterpret_cast<int32_t *>(ctx->d_buf + o_work);
+    if ((st = launch_med_desc(ctx, a)) != PLM_OK) return st;
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_idx, ctx->d_buf + o_idx, out_end - o_idx, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(med_idx, ctx->h_buf + o_idx, size_t(n_lm) * 4);
+    if (med_desc) std::memcpy(med_desc, ctx->h_buf + o_med, size_t(n_lm) * 32);
+    if (want_dir) std::memcpy(med_dir, ctx->h_buf + o_mdir, size_t(n_lm) * 24);
     return PLM_OK;
 }
 

@@ -222,6 +222,33 @@ def make_keyframe_db(seed: int, n_kf: int, per_kf: int = 800, revisit_frac: floa
     return db
 
 
+# ---- local-map landmarks: observation lists behind the med_desc rows (src/mapFeatures.cpp) -------
+
+def make_landmark_observations(seed: int, n_lm: int, mean_obs: float = 8.0, max_obs: int = 32, flip_p: float = 0.06,
+                               long_lists: int = 0, long_len: int = 100, tie: bool = False, empty_frac: float = 0.0):
+    """Observation arenas of n_lm map landmarks: each landmark has a base descriptor and 1 + Poisson(mean_obs-1)
+    observations (clipped to max_obs) that are noisy copies of it, plus unit observation directions.
+    `long_lists` landmarks get `long_len` observations (the CTA kernel's path); `tie` uses the tie-stress
+    descriptors (many equal medians -> first-row rule); `empty_frac` of the landmarks get no observation.
+    Returns (desc_obs uint8[n_obs, 32], dir_obs float64[n_obs, 3], obs_start int32[n_lm + 1])."""
+    rng = np.random.default_rng(seed)
+    counts = np.clip(1 + rng.poisson(max(mean_obs - 1.0, 0.0), n_lm), 1, max_obs).astype(np.int64)
+    if long_lists:
+        counts[rng.choice(n_lm, min(long_lists, n_lm), replace=False)] = long_len
+    if empty_frac > 0:
+        counts[rng.random(n_lm) < empty_frac] = 0
+    obs_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    n_obs = int(obs_start[-1])
+    owner = np.repeat(np.arange(n_lm), counts)
+    if tie:
+        desc = tie_stress_desc(rng, n_obs)
+    else:
+        desc = flip_bits(rng, rand_desc(rng, n_lm)[owner], flip_p) if n_obs else np.zeros((0, 32), np.uint8)
+    dirs = rng.normal(size=(n_obs, 3))
+    dirs /= np.maximum(np.linalg.norm(dirs, axis=1, keepdims=True), 1e-12)
+    return np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(dirs, np.float64), obs_start
+
+
 # ---- config 3: offline replay of many stereo frames (vectorised over frames) ---------------------
 
 @dataclass

@@ -1,8 +1,8 @@
 """Generate tests/golden/*.npz from the REFERENCE ITSELF (oracle/_ref/libplref.so = the reference's
-matching.cpp / gridStructure.cpp / lineIterator.cpp compiled unmodified, see oracle/Makefile).
+matching.cpp / gridStructure.cpp / lineIterator.cpp / mapFeatures.cpp compiled unmodified, see oracle/Makefile).
 
 Run in the build container (needs /root/reference to build libplref.so):
-    python tools/make_golden.py
+    python tools/make_golden.py [brute] [grid] [line_coords] [med_desc]
 The fixtures are small (a few hundred KB) and committed; tests compare the oracle port and the CUDA
 path against them, so parity stays pinned on machines where the reference cannot be built.
 """
@@ -98,8 +98,27 @@ def line_coord_cases():
     save("line_coords", seg=seg, cells=np.concatenate(flat), offs=np.array(offs, np.int64))
 
 
+def med_desc_cases():
+    """MapPoint / MapLine::updateAverageDescDir from the reference's own src/mapFeatures.cpp (points and
+    lines share one body; both are run and must agree)."""
+    specs = [dict(n_lm=150, mean_obs=6), dict(n_lm=100, mean_obs=10, tie=True),
+             dict(n_lm=40, mean_obs=4, long_lists=4, long_len=50, empty_frac=0.1),
+             dict(n_lm=12, mean_obs=3, long_lists=2, long_len=90, tie=True)]
+    out = {"n_cases": np.int32(len(specs))}
+    for k, kw in enumerate(specs):
+        desc, dirs, obs_start = synth.make_landmark_observations(synth.SEED0 + 300 + k, **kw)
+        i_pt, d_pt = ref.med_desc(desc, dirs, obs_start, is_line=False)
+        i_ln, d_ln = ref.med_desc(desc, dirs, obs_start, is_line=True)
+        assert np.array_equal(i_pt, i_ln) and np.array_equal(d_pt.view(np.uint64), d_ln.view(np.uint64))
+        out.update({f"desc_{k}": desc, f"dirs_{k}": dirs, f"obs_start_{k}": obs_start, f"med_idx_{k}": i_pt,
+                    f"med_dir_{k}": d_pt})
+    save("med_desc", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    brute_cases()
-    grid_cases()
-    line_coord_cases()
+    only = sys.argv[1:]
+    for name, fn in (("brute", brute_cases), ("grid", grid_cases), ("line_coords", line_coord_cases),
+                     ("med_desc", med_desc_cases)):
+        if not only or name in only:
+            fn()

@@ -1,6 +1,7 @@
 """Turn an `ncu --set full` report into the per-kernel table committed under profiles/.
 
     python tools/ncu_summary.py gpurun_out/prof_all.ncu-rep profiles/r1_kernels_ncu.md [--title "..."]
+    python tools/ncu_summary.py gpurun_out/prof_all_raw.csv profiles/r1_kernels_ncu.md      # exported raw page
 
 Runs `ncu -i <rep> --page raw --csv` (works without a GPU) and keeps, per kernel launch: duration, the
 integer / memory pipe utilisations, DRAM bytes and bandwidth against the measured HBM peak, occupancy,
@@ -53,7 +54,10 @@ def fnum(x: str) -> float:
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     title = sys.argv[sys.argv.index("--title") + 1] if "--title" in sys.argv else os.path.basename(rep)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # the raw page already exported on the GPU box (the .ncu-rep itself can exceed gpurun's 64 MiB)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}

@@ -4,7 +4,7 @@
     ncu --set full --clock-control none --import-source on -o gpurun_out/prof_all python tools/profile_kernels.py
 
 Shapes: frame-sized calls of configs 1-2 (600 ORB + 200 LBD), the map-sized matchGrid of config 4
-(200 000 x 600), a 300-frame replay batch (config 3) and one 6400 x 2 000 000 brute-force launch (config 5,
+(200 000 x 600), a 300-frame replay batch (config 3, batched stages and the device-resident frame pipeline) and one 6400 x 2 000 000 brute-force launch (config 5,
 shortened so the ~40 ncu replays stay short).  Every kernel is launched once after one warm-up call.
 """
 import os
@@ -74,6 +74,25 @@ merged = ops.top2_merge(parts)
 m = torch.full((6400,), -1, dtype=torch.int32, device="cuda")
 cntt = torch.zeros(1, dtype=torch.int32, device="cuda")
 ops.nnr_accept(merged, 0.9, m, cntt)
+# device-resident frame pipeline (plm_frames_*): stereo_frame_kernel x2 (points, lines), f2f_match_kernel x2
+from pl_inertial_slam_b200.frames import FrameConfig, FramePipeline, replay_frame_records  # noqa: E402
+kp, ln, rec = replay_frame_records(rp)
+pipe = FramePipeline(ctx)
+pipe.upload(rp.arena, kp, ln, rec, FrameConfig())
+pipe.run()
+pipe.fetch()
+# map landmarks: med_desc of 50 000 landmarks (mean 8 observations, a few long lists) -- med_desc_warp_kernel + med_desc_cta_kernel
+from pl_inertial_slam_b200 import mapfeatures as MF  # noqa: E402
+ldesc, ldirs, lstart = synth.make_landmark_observations(synth.SEED0 + 20, 20_000 if quick else 50_000, mean_obs=8,
+                                                        long_lists=64, long_len=48)
+t_ = lambda x: torch.from_numpy(x).to(dev)  # noqa: E731
+n_lm = len(lstart) - 1
+med_idx = torch.empty(n_lm, dtype=torch.int32, device=dev)
+med_rows = torch.empty((n_lm, 32), dtype=torch.uint8, device=dev)
+med_dir = torch.empty((n_lm, 3), dtype=torch.float64, device=dev)
+ld, ldr, lst = t_(ldesc), t_(ldirs), t_(lstart)
+torch.cuda.synchronize()
+MF.dev_med_desc(ctx, ld, lst, med_idx, med_desc=med_rows, dir_obs=ldr, med_dir=med_dir)
 torch.cuda.synchronize()
 ctx.synchronize()
 print("profile_kernels ok: launches", ctx.launch_count + ops.ctx.launch_count)
