@@ -17,6 +17,9 @@
  *   plm_frames_*            StereoFrame::matchStereoPoints/Lines + StereoFrameHandler::matchF2FPoints/Lines
  *                           on the device (stereoFrame.cpp:131-184,320-409; stereoFrameHandler.cpp:158-207)
  *   plm_db_* / plm_dev_*    keyframe / local-map database  src/mapHandler.cpp:583-803, 3301-3409
+ *   plm_voc_* / plm_bow_*   DBoW2 vocabulary transform + L1 score behind MapHandler::insertKFBowVectorP/L/PL
+ *                           src/mapHandler.cpp:3116-3237; 3rdparty/DBoW2/include/DBoW2/TemplatedVocabulary.h:1045-1238,
+ *                           3rdparty/DBoW2/src/DBoW2/{BowVector.cpp:31-81, ScoringObject.cpp:25-69, FORB.cpp:78-100}
  *   plm_med_desc / plm_dev_med_desc   PLSLAM::MapPoint / MapLine::updateAverageDescDir (the producer of the
  *                           map's med_desc rows)           src/mapFeatures.cpp:51-93, 121-163
  *
@@ -353,6 +356,45 @@ int plm_med_desc(plm_ctx *ctx, const uint8_t *desc_obs, int64_t n_obs, size_t st
 int plm_dev_med_desc(plm_ctx *ctx, const void *desc_obs_dev, int64_t n_obs, const double *dir_obs_dev,
                      const int32_t *obs_start_dev, int n_lm, int32_t *med_idx_dev, void *med_desc_dev,
                      const int32_t *dst_rows_dev, double *med_dir_dev);
+
+/* ---- bag-of-words loop-candidate scoring (the reference's vendored DBoW2) ----------------------- */
+/* A vocabulary tree as flat arrays, copied to the device once (DBoW2::TemplatedVocabulary::m_nodes,
+ * TemplatedVocabulary.h:275-307, 383-408): node 0 is the root; the children of node i are
+ * child_ids[child_start[i] .. child_start[i+1]-1] in the reference's vector order (ties in the descent go to
+ * the FIRST child, :1225); node_desc is n_nodes x 32 bytes; node_weight the idf / tf weight of a node;
+ * node_word[i] >= 0 is the word id of leaf i (-1 on inner nodes).  Requirements (PLM_E_INVALID otherwise):
+ * child ids in (parent, n_nodes), every node except the root listed as a child exactly once, leaves carry a
+ * word id.  weighting = DBoW2::WeightingType (0 TF_IDF, 1 TF, 2 IDF, 3 BINARY); scoring = DBoW2::ScoringType,
+ * only 0 (L1_NORM, the DBoW2 default) is supported (PLM_E_UNSUPPORTED otherwise). */
+typedef struct plm_voc plm_voc;
+int plm_voc_create(plm_ctx *ctx, int n_nodes, const int32_t *child_start, const int32_t *child_ids,
+                   const uint8_t *node_desc, const double *node_weight, const int32_t *node_word, int weighting,
+                   int scoring, plm_voc **out);
+int plm_voc_destroy(plm_voc *voc);
+int plm_voc_words(const plm_voc *voc); /* number of words (max word id + 1) */
+/* TemplatedVocabulary::transform(features, BowVector) for n_sets descriptor sets (set s = rows set_start[s] ..
+ * set_start[s+1]-1 of desc): the L1-normalised BowVector of set s is written, in ascending word id, to
+ * bow_ids / bow_vals at slots set_start[s] .. set_start[s] + bow_len[s] - 1 (so both arrays hold n_rows
+ * entries).  Values are bit-identical to the reference's (same order of the fp64 additions).  A set may hold
+ * at most 8192 features (PLM_E_UNSUPPORTED). */
+int plm_bow_transform(plm_voc *voc, const uint8_t *desc, int64_t n_rows, size_t step, const int32_t *set_start,
+                      int n_sets, uint32_t *bow_ids, double *bow_vals, int32_t *bow_len);
+/* Same on device pointers (rows contiguous, 16-byte aligned), enqueued on the vocabulary's context stream;
+ * max_set >= the largest set. */
+int plm_dev_bow_transform(plm_voc *voc, const void *desc_dev, int64_t n_rows, const int32_t *set_start_dev, int n_sets,
+                          int max_set, uint32_t *bow_ids_dev, double *bow_vals_dev, int32_t *bow_len_dev);
+/* L1Scoring::score(query q, database vector j) for every (q, j): scores[q * n_db + j].  A vector is the
+ * entries [start, start + len) of its ids / vals arrays, ids ascending.  This is the loop of
+ * insertKFBowVectorP / L (mapHandler.cpp:3129-3137): one query (the new keyframe) against all earlier
+ * keyframes; n_q > 1 scores several new keyframes in one launch.  A query may hold at most 8192 entries. */
+int plm_bow_score(plm_ctx *ctx, const uint32_t *q_ids, const double *q_vals, const int64_t *q_start,
+                  const int32_t *q_len, int n_q, const uint32_t *db_ids, const double *db_vals,
+                  const int64_t *db_start, const int32_t *db_len, int n_db, double *scores);
+/* Same on device pointers, no host sync; max_q_len >= the longest query. */
+int plm_dev_bow_score(plm_ctx *ctx, const uint32_t *q_ids_dev, const double *q_vals_dev, const int64_t *q_start_dev,
+                      const int32_t *q_len_dev, int n_q, int max_q_len, const uint32_t *db_ids_dev,
+                      const double *db_vals_dev, const int64_t *db_start_dev, const int32_t *db_len_dev, int n_db,
+                      double *scores_dev);
 
 /* Tuning knobs (measurement only; results never depend on them):
  *   "knn_variant"  -1 = automatic (default), 0 = plain 8-POPC Hamming, 1 = carry-save 5-POPC,

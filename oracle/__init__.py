@@ -112,10 +112,36 @@ class _Port:
             L.plo_stereo_lines.argtypes = [_f32p, _u8p, C.c_int, _f32p, _u8p, C.c_int, C.c_double, C.c_double, C.c_int,
                                            C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                            C.c_double, C.c_double, _f64p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]
+            u32p = C.POINTER(C.c_uint32)
+            L.plo_bow_word.restype = C.c_int
+            L.plo_bow_word.argtypes = [_i32p, _i32p, _u8p, _u8p]
+            L.plo_bow_transform.restype = C.c_int
+            L.plo_bow_transform.argtypes = [_i32p, _i32p, _u8p, _f64p, _i32p, C.c_int, _u8p, C.c_int, C.c_size_t, u32p, _f64p]
+            L.plo_bow_score.restype = C.c_double
+            L.plo_bow_score.argtypes = [u32p, _f64p, C.c_int, u32p, _f64p, C.c_int]
             L.plo_med_desc.restype = None
             L.plo_med_desc.argtypes = [_u8p, C.c_size_t, _f64p, _i32p, C.c_int, _i32p, _u8p, _f64p]
             self._lib = L
         return self._lib
+
+    def bow_transform(self, fv, desc):
+        """TemplatedVocabulary::transform(features, BowVector) on a FlatVocabulary -> (ids uint32, vals float64)."""
+        u32p = C.POINTER(C.c_uint32)
+        p, n, s = _desc(np.ascontiguousarray(desc, np.uint8).reshape(-1, 32))
+        ids, vals = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64)
+        m = self.lib.plo_bow_transform(fv.child_start.ctypes.data_as(_i32p), fv.child_ids.ctypes.data_as(_i32p),
+                                       fv.node_desc.ctypes.data_as(_u8p), fv.node_weight.ctypes.data_as(_f64p),
+                                       fv.node_word.ctypes.data_as(_i32p), fv.weighting, p, n, s,
+                                       ids.ctypes.data_as(u32p), vals.ctypes.data_as(_f64p))
+        return ids[:m].copy(), vals[:m].copy()
+
+    def bow_score(self, v1, v2) -> float:
+        """L1Scoring::score(v1, v2)."""
+        u32p = C.POINTER(C.c_uint32)
+        i1, x1 = np.ascontiguousarray(v1[0], np.uint32), np.ascontiguousarray(v1[1], np.float64)
+        i2, x2 = np.ascontiguousarray(v2[0], np.uint32), np.ascontiguousarray(v2[1], np.float64)
+        return self.lib.plo_bow_score(i1.ctypes.data_as(u32p), x1.ctypes.data_as(_f64p), len(i1),
+                                      i2.ctypes.data_as(u32p), x2.ctypes.data_as(_f64p), len(i2))
 
     def med_desc(self, desc, dirs, obs_start):
         """MapPoint / MapLine::updateAverageDescDir over a batch of landmarks (src/mapFeatures.cpp:51-93,
@@ -452,3 +478,112 @@ class _Ref:
 port = _Port()
 ref = _Ref()
 stvo_gpu = _Ref("libstvo_gpu.so")  # the thing under test in tests/test_cxx_dropin.py, not a checker
+
+
+_u32p = C.POINTER(C.c_uint32)
+
+
+class FlatVocabulary:
+    """A DBoW2 vocabulary tree as flat arrays (the layout of plm_voc_create, include/plmatch.h): node 0 is
+    the root; children of node i are child_ids[child_start[i] : child_start[i+1]] in the reference's vector
+    order; node_word[i] >= 0 marks a leaf (word id)."""
+
+    def __init__(self, child_start, child_ids, node_desc, node_weight, node_word, k, L, weighting=0, scoring=0):
+        self.child_start = np.ascontiguousarray(child_start, np.int32)
+        self.child_ids = np.ascontiguousarray(child_ids, np.int32)
+        self.node_desc = np.ascontiguousarray(node_desc, np.uint8).reshape(-1, 32)
+        self.node_weight = np.ascontiguousarray(node_weight, np.float64)
+        self.node_word = np.ascontiguousarray(node_word, np.int32)
+        self.k, self.L, self.weighting, self.scoring = int(k), int(L), int(weighting), int(scoring)
+
+    @property
+    def n_nodes(self) -> int:
+        return len(self.node_word)
+
+    @property
+    def n_words(self) -> int:
+        return int(self.node_word.max()) + 1 if self.n_nodes else 0
+
+    def arrays(self):
+        return dict(child_start=self.child_start, child_ids=self.child_ids, node_desc=self.node_desc,
+                    node_weight=self.node_weight, node_word=self.node_word,
+                    meta=np.array([self.k, self.L, self.weighting, self.scoring], np.int32))
+
+    @staticmethod
+    def from_arrays(z, prefix=""):
+        k, L, w, s = (int(x) for x in z[prefix + "meta"])
+        return FlatVocabulary(z[prefix + "child_start"], z[prefix + "child_ids"], z[prefix + "node_desc"],
+                              z[prefix + "node_weight"], z[prefix + "node_word"], k, L, w, s)
+
+
+class _RefDbow:
+    """The reference's vendored DBoW2 (3rdparty/DBoW2, compiled unmodified -> _ref/libplref_dbow.so):
+    Vocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB> (include/mapHandler.h:70)."""
+
+    def __init__(self):
+        self._lib = None
+
+    def available(self) -> bool:
+        try:
+            return self.lib is not None
+        except (FileNotFoundError, OSError, RuntimeError):
+            return False
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            L = _load("libplref_dbow.so")
+            L.plref_voc_create.restype = C.c_void_p
+            L.plref_voc_create.argtypes = [_u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+            L.plref_voc_from_flat.restype = C.c_void_p
+            L.plref_voc_from_flat.argtypes = [C.c_int, _i32p, _i32p, _u8p, _f64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int]
+            L.plref_voc_destroy.argtypes = [C.c_void_p]
+            for f in ("plref_voc_n_nodes", "plref_voc_n_children", "plref_voc_n_words"):
+                getattr(L, f).restype = C.c_int
+                getattr(L, f).argtypes = [C.c_void_p]
+            L.plref_voc_export.argtypes = [C.c_void_p, _i32p, _i32p, _u8p, _f64p, _i32p]
+            L.plref_voc_transform.restype = C.c_int
+            L.plref_voc_transform.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_size_t, _u32p, _f64p]
+            L.plref_voc_score.restype = C.c_double
+            L.plref_voc_score.argtypes = [C.c_void_p, _u32p, _f64p, C.c_int, _u32p, _f64p, C.c_int]
+            self._lib = L
+        return self._lib
+
+    def create(self, desc, set_start, k=10, L=3, weighting=0, scoring=0, seed=1):
+        """Vocabulary::create on training sets -> opaque handle (destroy() it)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        ss, ssp = _i32(set_start)
+        return self.lib.plref_voc_create(desc.ctypes.data_as(_u8p), ssp, len(ss) - 1, k, L, weighting, scoring, seed)
+
+    def from_flat(self, fv: FlatVocabulary):
+        return self.lib.plref_voc_from_flat(fv.n_nodes, fv.child_start.ctypes.data_as(_i32p),
+                                            fv.child_ids.ctypes.data_as(_i32p), fv.node_desc.ctypes.data_as(_u8p),
+                                            fv.node_weight.ctypes.data_as(_f64p), fv.node_word.ctypes.data_as(_i32p),
+                                            fv.k, fv.L, fv.weighting, fv.scoring)
+
+    def destroy(self, h):
+        self.lib.plref_voc_destroy(h)
+
+    def export(self, h, k, L, weighting=0, scoring=0) -> FlatVocabulary:
+        n, nc = self.lib.plref_voc_n_nodes(h), self.lib.plref_voc_n_children(h)
+        cs, ci = np.zeros(n + 1, np.int32), np.zeros(max(nc, 1), np.int32)
+        nd, nw, wd = np.zeros((n, 32), np.uint8), np.zeros(n, np.float64), np.zeros(n, np.int32)
+        self.lib.plref_voc_export(h, cs.ctypes.data_as(_i32p), ci.ctypes.data_as(_i32p), nd.ctypes.data_as(_u8p),
+                                  nw.ctypes.data_as(_f64p), wd.ctypes.data_as(_i32p))
+        return FlatVocabulary(cs, ci[:nc], nd, nw, wd, k, L, weighting, scoring)
+
+    def transform(self, h, desc):
+        """Vocabulary::transform(features, BowVector) -> (word ids uint32, values float64), word order."""
+        p, n, s = _desc(np.ascontiguousarray(desc, np.uint8).reshape(-1, 32))
+        ids, vals = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64)
+        m = self.lib.plref_voc_transform(h, p, n, s, ids.ctypes.data_as(_u32p), vals.ctypes.data_as(_f64p))
+        return ids[:m].copy(), vals[:m].copy()
+
+    def score(self, h, v1, v2) -> float:
+        i1, x1 = np.ascontiguousarray(v1[0], np.uint32), np.ascontiguousarray(v1[1], np.float64)
+        i2, x2 = np.ascontiguousarray(v2[0], np.uint32), np.ascontiguousarray(v2[1], np.float64)
+        return self.lib.plref_voc_score(h, i1.ctypes.data_as(_u32p), x1.ctypes.data_as(_f64p), len(i1),
+                                        i2.ctypes.data_as(_u32p), x2.ctypes.data_as(_f64p), len(i2))
+
+
+ref_dbow = _RefDbow()

@@ -774,3 +774,113 @@ PLO_API void plo_med_desc(const uint8_t *desc, size_t step, const double *dirs, 
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Bag-of-words loop-candidate scoring (the reference's vendored DBoW2, 3rdparty/DBoW2).
+ *
+ * The vocabulary is a flat copy of TemplatedVocabulary::m_nodes (include/DBoW2/TemplatedVocabulary.h:
+ * 275-307): node 0 = root, children of node i = child_ids[child_start[i] .. child_start[i+1]-1] in the
+ * reference's vector order, node_desc 32 bytes per node, node_weight, node_word >= 0 on leaves.
+ *
+ * plo_bow_word     TemplatedVocabulary::transform(feature, word_id, weight)  (:1196-1238): from the root,
+ *                  move to the child with the smallest FORB::distance (src/DBoW2/FORB.cpp:78-100, 256-bit
+ *                  Hamming), FIRST child on ties (strict `<`, :1225), until a leaf.
+ * plo_bow_transform  TemplatedVocabulary::transform(features, BowVector)  (:1045-1101) for weighting
+ *                  TF_IDF / TF (0 / 1): v[word] += weight per feature in feature order (BowVector::addWeight,
+ *                  src/DBoW2/BowVector.cpp:31-43; the same weight is added once per occurrence, so the value
+ *                  is the weight summed `count` times), IDF / BINARY (2 / 3): v[word] = weight
+ *                  (addIfNotExist, :47-55); words with weight <= 0 are dropped (:1074, :1094); then
+ *                  L1 normalisation (BowVector::normalize, :59-81: sum of fabs in word order, each /= norm)
+ *                  -- L1_NORM scoring, the DBoW2 default, asks for it (ScoringObject.h:73).
+ * plo_bow_score    L1Scoring::score (src/DBoW2/ScoringObject.cpp:25-69): over the common words in word
+ *                  order, score += fabs(vi - wi) - fabs(vi) - fabs(wi); result -score / 2.
+ * Call sites: src/mapHandler.cpp:3125-3137, :3150-3162, :3176-3235.
+ */
+PLO_API int plo_bow_word(const int32_t *child_start, const int32_t *child_ids, const uint8_t *node_desc,
+                         const uint8_t *feature)
+{
+    int node = 0;
+    if (child_start[1] == child_start[0]) return -1; /* empty vocabulary */
+    do {
+        const int c0 = child_start[node], c1 = child_start[node + 1];
+        int best = child_ids[c0];
+        int best_d = plo_hamming256(feature, node_desc + 32 * (size_t)best);
+        for (int c = c0 + 1; c < c1; c++) {
+            const int id = child_ids[c];
+            const int d = plo_hamming256(feature, node_desc + 32 * (size_t)id);
+            if (d < best_d) {
+                best_d = d;
+                best = id;
+            }
+        }
+        node = best;
+    } while (child_start[node + 1] > child_start[node]);
+    return node; /* leaf node id */
+}
+
+typedef struct { uint32_t word; int32_t order; double w; } plo_bow_item;
+
+static int plo_cmp_bow(const void *a, const void *b)
+{
+    const plo_bow_item *x = (const plo_bow_item *)a, *y = (const plo_bow_item *)b;
+    if (x->word != y->word) return (x->word > y->word) - (x->word < y->word);
+    return (x->order > y->order) - (x->order < y->order);
+}
+
+/* -> number of entries written to ids / vals (capacity n) */
+PLO_API int plo_bow_transform(const int32_t *child_start, const int32_t *child_ids, const uint8_t *node_desc,
+                              const double *node_weight, const int32_t *node_word, int weighting,
+                              const uint8_t *desc, int n, size_t step, uint32_t *ids, double *vals)
+{
+    if (n <= 0 || child_start[1] == child_start[0]) return 0;
+    plo_bow_item *it = (plo_bow_item *)malloc(sizeof(plo_bow_item) * (size_t)n);
+    int m = 0;
+    for (int f = 0; f < n; f++) {
+        const int leaf = plo_bow_word(child_start, child_ids, node_desc, desc + (size_t)f * step);
+        const double w = node_weight[leaf];
+        if (w > 0) {
+            it[m].word = (uint32_t)node_word[leaf];
+            it[m].order = f;
+            it[m].w = w;
+            m++;
+        }
+    }
+    qsort(it, (size_t)m, sizeof(plo_bow_item), plo_cmp_bow); /* std::map order; feature order inside a word */
+    int len = 0;
+    for (int i = 0; i < m;) {
+        int j = i;
+        double v = it[i].w; /* insert(id, w) */
+        for (j = i + 1; j < m && it[j].word == it[i].word; j++)
+            if (weighting == 0 || weighting == 1) v += it[j].w; /* addWeight; addIfNotExist keeps the first */
+        ids[len] = it[i].word;
+        vals[len] = v;
+        len++;
+        i = j;
+    }
+    free(it);
+    double norm = 0.0;
+    for (int i = 0; i < len; i++) norm += fabs(vals[i]);
+    if (norm > 0.0)
+        for (int i = 0; i < len; i++) vals[i] /= norm;
+    return len;
+}
+
+PLO_API double plo_bow_score(const uint32_t *ids1, const double *vals1, int n1, const uint32_t *ids2,
+                             const double *vals2, int n2)
+{
+    double score = 0;
+    int i = 0, j = 0;
+    while (i < n1 && j < n2) {
+        if (ids1[i] == ids2[j]) {
+            const double vi = vals1[i], wi = vals2[j];
+            score += fabs(vi - wi) - fabs(vi) - fabs(wi);
+            i++;
+            j++;
+        } else if (ids1[i] < ids2[j]) {
+            i++; /* lower_bound jump == linear advance on sorted ids */
+        } else {
+            j++;
+        }
+    }
+    return -score / 2.0;
+}

@@ -135,6 +135,13 @@ SIGNATURES = {
     "plm_db_size": (C.c_int64, [vp]),
     "plm_db_device_ptr": (vp, [vp]),
     "plm_db_knn2": (C.c_int, [vp, u8p, C.c_int, C.c_size_t, C.c_uint64, u64p]),
+    "plm_voc_create": (C.c_int, [vp, C.c_int, i32p, i32p, u8p, f64p, i32p, C.c_int, C.c_int, C.POINTER(vp)]),
+    "plm_voc_destroy": (C.c_int, [vp]),
+    "plm_voc_words": (C.c_int, [vp]),
+    "plm_bow_transform": (C.c_int, [vp, u8p, C.c_int64, C.c_size_t, i32p, C.c_int, vp, f64p, i32p]),
+    "plm_dev_bow_transform": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_int, vp, vp, vp]),
+    "plm_bow_score": (C.c_int, [vp, vp, f64p, vp, i32p, C.c_int, vp, f64p, vp, i32p, C.c_int, f64p]),
+    "plm_dev_bow_score": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp]),
     "plm_med_desc": (C.c_int, [vp, u8p, C.c_int64, C.c_size_t, f64p, i32p, C.c_int, i32p, u8p, f64p]),
     "plm_dev_med_desc": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp, vp, vp, vp]),
     "plm_set_option": (C.c_int, [C.c_char_p, C.c_int]),

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "plm_bow.cuh"
 #include "plm_common.cuh"
 #include "plm_frames.cuh"
 #include "plm_grid.cuh"
@@ -1147,6 +1148,282 @@ PLM_API int plm_med_desc(plm_ctx *ctx, const uint8_t *desc_obs, int64_t n_obs, s
     std::memcpy(med_idx, ctx->h_buf + o_idx, size_t(n_lm) * 4);
     if (med_desc) std::memcpy(med_desc, ctx->h_buf + o_med, size_t(n_lm) * 32);
     if (want_dir) std::memcpy(med_dir, ctx->h_buf + o_mdir, size_t(n_lm) * 24);
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bag-of-words: DBoW2 vocabulary transform + L1 score (src/mapHandler.cpp:3116-3237)
+struct plm_voc {
+    plm_ctx *ctx = nullptr;
+    char *d_buf = nullptr;
+    plm::VocDev dev{};
+    int n_words = 0;
+    bool smem_attr_set = false;
+};
+
+namespace {
+
+constexpr int BOW_MAX_SET = 8192;
+
+int pow2_at_least(int n) {
+    int p = 32;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+int launch_bow_transform(plm_voc *voc, plm::BowTransformArgs a, int max_set) {
+    plm_ctx *ctx = voc->ctx;
+    a.voc = voc->dev;
+    a.cap = pow2_at_least(std::max(max_set, 1));
+    const size_t smem = plm::bow_transform_smem(a.cap);
+    if (smem > 48 * 1024 || !voc->smem_attr_set) {
+        CU_TRY(cudaFuncSetAttribute(plm::bow_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(plm::bow_transform_smem(BOW_MAX_SET))));
+        voc->smem_attr_set = true;
+    }
+    plm::bow_transform_kernel<<<std::min(a.n_sets, ctx->sm_count * 8), plm::BOW_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+int launch_bow_score(plm_ctx *ctx, plm::BowScoreArgs a, int max_q_len) {
+    a.q_cap = std::max(max_q_len, 1);
+    const size_t smem = plm::bow_score_smem(a.q_cap);
+    CU_TRY(cudaFuncSetAttribute(plm::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(plm::bow_score_smem(BOW_MAX_SET))));
+    const int warps = plm::BOW_THREADS / 32;
+    const int ctas = std::max(1, std::min((a.n_db + warps - 1) / warps, ctx->sm_count * 8));
+    plm::bow_score_kernel<<<dim3(ctas, a.n_q), plm::BOW_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+} // namespace
+
+PLM_API int plm_voc_create(plm_ctx *ctx, int n_nodes, const int32_t *child_start, const int32_t *child_ids,
+                           const uint8_t *node_desc, const double *node_weight, const int32_t *node_word, int weighting,
+                           int scoring, plm_voc **out) {
+    if (!out) return fail(PLM_E_INVALID, "null out");
+    *out = nullptr;
+    if (n_nodes < 1 || !child_start || !node_desc || !node_weight || !node_word) return fail(PLM_E_INVALID, "null pointer / empty tree");
+    if (weighting < 0 || weighting > 3) return fail(PLM_E_INVALID, "unknown DBoW2 weighting type");
+    if (scoring != 0) return fail(PLM_E_UNSUPPORTED, "only L1_NORM scoring (the DBoW2 default) is implemented");
+    if (child_start[0] != 0) return fail(PLM_E_INVALID, "child_start[0] != 0");
+    const int n_child = child_start[n_nodes];
+    if (n_child != n_nodes - 1 || (n_child > 0 && !child_ids)) return fail(PLM_E_INVALID, "every node except the root must be a child exactly once");
+    std::vector<char> seen(static_cast<size_t>(n_nodes), 0);
+    int n_words = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        if (child_start[i + 1] < child_start[i] || child_start[i + 1] > n_child) return fail(PLM_E_INVALID, "child_start must be non-decreasing");
+        for (int c = child_start[i]; c < child_start[i + 1]; ++c) {
+            const int id = child_ids[c];
+            if (id <= i || id >= n_nodes || seen[id]) return fail(PLM_E_INVALID, "child id outside (parent, n_nodes) or listed twice");
+            seen[id] = 1;
+        }
+        const bool leaf = child_start[i + 1] == child_start[i];
+        if (leaf && i > 0) {
+            if (node_word[i] < 0) return fail(PLM_E_INVALID, "leaf without a word id");
+            n_words = std::max(n_words, node_word[i] + 1);
+        }
+    }
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm_voc *v = new (std::nothrow) plm_voc();
+    if (!v) return fail(PLM_E_NOMEM, "host allocation failed");
+    v->ctx = ctx;
+    v->n_words = n_words;
+    Layout L;
+    const size_t o_desc = L.add(size_t(n_nodes) * 32), o_w = L.add(size_t(n_nodes) * 8), o_cs = L.add(size_t(n_nodes + 1) * 4),
+                 o_ci = L.add(size_t(std::max(n_child, 1)) * 4), o_word = L.add(size_t(n_nodes) * 4);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&v->d_buf), L.total);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v->d_buf + o_desc, node_desc, size_t(n_nodes) * 32, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v->d_buf + o_w, node_weight, size_t(n_nodes) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v->d_buf + o_cs, child_start, size_t(n_nodes + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n_child > 0) e = cudaMemcpyAsync(v->d_buf + o_ci, child_ids, size_t(n_child) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v->d_buf + o_word, node_word, size_t(n_nodes) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (v->d_buf) cudaFree(v->d_buf);
+        delete v;
+        return fail(e == cudaErrorMemoryAllocation ? PLM_E_NOMEM : PLM_E_CUDA, std::string("plm_voc_create: ") + cudaGetErrorString(e));
+    }
+    v->dev.node_desc = reinterpret_cast<const uint4 *>(v->d_buf + o_desc);
+    v->dev.node_weight = reinterpret_cast<const double *>(v->d_buf + o_w);
+    v->dev.child_start = reinterpret_cast<const int32_t *>(v->d_buf + o_cs);
+    v->dev.child_ids = reinterpret_cast<const int32_t *>(v->d_buf + o_ci);
+    v->dev.node_word = reinterpret_cast<const int32_t *>(v->d_buf + o_word);
+    v->dev.n_nodes = n_nodes;
+    v->dev.weighting = weighting;
+    *out = v;
+    return PLM_OK;
+}
+
+PLM_API int plm_voc_destroy(plm_voc *voc) {
+    if (!voc) return PLM_OK;
+    if (voc->ctx) {
+        cudaSetDevice(voc->ctx->device);
+        cudaStreamSynchronize(voc->ctx->stream);
+    }
+    if (voc->d_buf) cudaFree(voc->d_buf);
+    delete voc;
+    return PLM_OK;
+}
+
+PLM_API int plm_voc_words(const plm_voc *voc) { return voc ? voc->n_words : 0; }
+
+PLM_API int plm_dev_bow_transform(plm_voc *voc, const void *desc_dev, int64_t n_rows, const int32_t *set_start_dev, int n_sets,
+                                  int max_set, uint32_t *bow_ids_dev, double *bow_vals_dev, int32_t *bow_len_dev) {
+    if (!voc) return fail(PLM_E_INVALID, "null vocabulary");
+    if (n_sets < 0 || n_rows < 0 || max_set < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_sets == 0) return PLM_OK;
+    if (!set_start_dev || !bow_len_dev || (n_rows > 0 && (!desc_dev || !bow_ids_dev || !bow_vals_dev))) return fail(PLM_E_INVALID, "null pointer");
+    if (reinterpret_cast<uintptr_t>(desc_dev) & 15) return fail(PLM_E_INVALID, "descriptor rows must be 16-byte aligned");
+    if (max_set > BOW_MAX_SET) return fail(PLM_E_UNSUPPORTED, "more than 8192 features in one set");
+    plm_ctx *ctx = voc->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::BowTransformArgs a{};
+    a.desc = static_cast<const uint4 *>(desc_dev);
+    a.set_start = set_start_dev;
+    a.n_sets = n_sets;
+    a.bow_ids = bow_ids_dev;
+    a.bow_vals = bow_vals_dev;
+    a.bow_len = bow_len_dev;
+    return launch_bow_transform(voc, a, max_set);
+}
+
+PLM_API int plm_bow_transform(plm_voc *voc, const uint8_t *desc, int64_t n_rows, size_t step, const int32_t *set_start,
+                              int n_sets, uint32_t *bow_ids, double *bow_vals, int32_t *bow_len) {
+    if (!voc) return fail(PLM_E_INVALID, "null vocabulary");
+    if (n_sets < 0 || n_rows < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_sets == 0) return PLM_OK;
+    if (!set_start || !bow_len || (n_rows > 0 && (!desc || !bow_ids || !bow_vals))) return fail(PLM_E_INVALID, "null pointer");
+    if (step < 32) return fail(PLM_E_INVALID, "step < 32");
+    if (n_rows > INT32_MAX) return fail(PLM_E_UNSUPPORTED, "more than 2^31 - 1 rows in one call");
+    if (set_start[0] < 0 || set_start[n_sets] > n_rows) return fail(PLM_E_INVALID, "set_start outside [0, n_rows]");
+    int max_set = 0;
+    for (int s = 0; s < n_sets; ++s) {
+        if (set_start[s + 1] < set_start[s]) return fail(PLM_E_INVALID, "set_start must be non-decreasing");
+        max_set = std::max(max_set, set_start[s + 1] - set_start[s]);
+    }
+    if (max_set > BOW_MAX_SET) return fail(PLM_E_UNSUPPORTED, "more than 8192 features in one set");
+    plm_ctx *ctx = voc->ctx;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout L;
+    const size_t o_start = L.add(size_t(n_sets + 1) * 4), o_desc = L.add(size_t(n_rows) * 32);
+    const size_t in_bytes = L.total;
+    const size_t o_vals = L.add(size_t(n_rows) * 8), o_ids = L.add(size_t(n_rows) * 4), o_len = L.add(size_t(n_sets) * 4);
+    if ((st = ctx->ensure_pinned(L.total)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    std::memcpy(ctx->h_buf + o_start, set_start, size_t(n_sets + 1) * 4);
+    pack_rows(ctx->h_buf + o_desc, desc, n_rows, step);
+    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    plm::BowTransformArgs a{};
+    a.desc = reinterpret_cast<const uint4 *>(ctx->d_buf + o_desc);
+    a.set_start = reinterpret_cast<const int32_t *>(ctx->d_buf + o_start);
+    a.n_sets = n_sets;
+    a.bow_vals = reinterpret_cast<double *>(ctx->d_buf + o_vals);
+    a.bow_ids = reinterpret_cast<uint32_t *>(ctx->d_buf + o_ids);
+    a.bow_len = reinterpret_cast<int32_t *>(ctx->d_buf + o_len);
+    if ((st = launch_bow_transform(voc, a, max_set)) != PLM_OK) return st;
+    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_vals, ctx->d_buf + o_vals, L.total - o_vals, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(bow_len, ctx->h_buf + o_len, size_t(n_sets) * 4);
+    // only the written slots of a set are defined on the device; copy those
+    for (int s = 0; s < n_sets; ++s) {
+        const size_t lo = size_t(set_start[s]), n = size_t(bow_len[s]);
+        std::memcpy(bow_ids + lo, ctx->h_buf + o_ids + lo * 4, n * 4);
+        std::memcpy(bow_vals + lo, ctx->h_buf + o_vals + lo * 8, n * 8);
+    }
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_bow_score(plm_ctx *ctx, const uint32_t *q_ids_dev, const double *q_vals_dev, const int64_t *q_start_dev,
+                              const int32_t *q_len_dev, int n_q, int max_q_len, const uint32_t *db_ids_dev,
+                              const double *db_vals_dev, const int64_t *db_start_dev, const int32_t *db_len_dev, int n_db,
+                              double *scores_dev) {
+    if (n_q < 0 || n_db < 0 || max_q_len < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_q == 0 || n_db == 0) return PLM_OK;
+    if (!q_start_dev || !q_len_dev || !db_start_dev || !db_len_dev || !scores_dev) return fail(PLM_E_INVALID, "null pointer");
+    if (max_q_len > BOW_MAX_SET) return fail(PLM_E_UNSUPPORTED, "more than 8192 entries in a query vector");
+    if (n_q > 65535) return fail(PLM_E_UNSUPPORTED, "more than 65535 queries in one launch");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::BowScoreArgs a{};
+    a.q_ids = q_ids_dev;
+    a.q_vals = q_vals_dev;
+    a.q_start = reinterpret_cast<const long long *>(q_start_dev);
+    a.q_len = q_len_dev;
+    a.n_q = n_q;
+    a.db_ids = db_ids_dev;
+    a.db_vals = db_vals_dev;
+    a.db_start = reinterpret_cast<const long long *>(db_start_dev);
+    a.db_len = db_len_dev;
+    a.n_db = n_db;
+    a.scores = scores_dev;
+    return launch_bow_score(ctx, a, max_q_len);
+}
+
+namespace {
+
+// Extent (in entries) of a set of sparse vectors and their validity: every [start, start + len) inside [0, cap_hint].
+int bow_vectors_extent(const int64_t *start, const int32_t *len, int n, int64_t *extent, int *max_len) {
+    int64_t hi = 0;
+    int ml = 0;
+    for (int i = 0; i < n; ++i) {
+        if (start[i] < 0 || len[i] < 0) return fail(PLM_E_INVALID, "negative vector start / length");
+        hi = std::max<int64_t>(hi, start[i] + len[i]);
+        ml = std::max(ml, len[i]);
+    }
+    *extent = hi;
+    *max_len = ml;
+    return PLM_OK;
+}
+
+} // namespace
+
+PLM_API int plm_bow_score(plm_ctx *ctx, const uint32_t *q_ids, const double *q_vals, const int64_t *q_start,
+                          const int32_t *q_len, int n_q, const uint32_t *db_ids, const double *db_vals,
+                          const int64_t *db_start, const int32_t *db_len, int n_db, double *scores) {
+    if (n_q < 0 || n_db < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_q == 0 || n_db == 0) return PLM_OK;
+    if (!q_start || !q_len || !db_start || !db_len || !scores) return fail(PLM_E_INVALID, "null pointer");
+    int64_t q_ext = 0, db_ext = 0;
+    int q_max = 0, db_max = 0;
+    int st;
+    if ((st = bow_vectors_extent(q_start, q_len, n_q, &q_ext, &q_max)) != PLM_OK) return st;
+    if ((st = bow_vectors_extent(db_start, db_len, n_db, &db_ext, &db_max)) != PLM_OK) return st;
+    if ((q_ext > 0 && (!q_ids || !q_vals)) || (db_ext > 0 && (!db_ids || !db_vals))) return fail(PLM_E_INVALID, "null pointer");
+    if (q_max > BOW_MAX_SET) return fail(PLM_E_UNSUPPORTED, "more than 8192 entries in a query vector");
+    if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+    Layout L;
+    const size_t o_qv = L.add(size_t(q_ext) * 8), o_dv = L.add(size_t(db_ext) * 8), o_qs = L.add(size_t(n_q) * 8),
+                 o_ds = L.add(size_t(n_db) * 8), o_qi = L.add(size_t(q_ext) * 4), o_di = L.add(size_t(db_ext) * 4),
+                 o_ql = L.add(size_t(n_q) * 4), o_dl = L.add(size_t(n_db) * 4);
+    const size_t in_bytes = L.total;
+    const size_t o_out = L.add(size_t(n_q) * size_t(n_db) * 8);
+    if ((st = ctx->ensure_pinned(L.total)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    char *H = ctx->h_buf, *D = ctx->d_buf;
+    if (q_ext) std::memcpy(H + o_qv, q_vals, size_t(q_ext) * 8), std::memcpy(H + o_qi, q_ids, size_t(q_ext) * 4);
+    if (db_ext) std::memcpy(H + o_dv, db_vals, size_t(db_ext) * 8), std::memcpy(H + o_di, db_ids, size_t(db_ext) * 4);
+    std::memcpy(H + o_qs, q_start, size_t(n_q) * 8);
+    std::memcpy(H + o_ds, db_start, size_t(n_db) * 8);
+    std::memcpy(H + o_ql, q_len, size_t(n_q) * 4);
+    std::memcpy(H + o_dl, db_len, size_t(n_db) * 4);
+    CU_TRY(cudaMemcpyAsync(D, H, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((st = plm_dev_bow_score(ctx, reinterpret_cast<const uint32_t *>(D + o_qi), reinterpret_cast<const double *>(D + o_qv),
+                                reinterpret_cast<const int64_t *>(D + o_qs), reinterpret_cast<const int32_t *>(D + o_ql), n_q, q_max,
+                                reinterpret_cast<const uint32_t *>(D + o_di), reinterpret_cast<const double *>(D + o_dv),
+                                reinterpret_cast<const int64_t *>(D + o_ds), reinterpret_cast<const int32_t *>(D + o_dl), n_db,
+                                reinterpret_cast<double *>(D + o_out))) != PLM_OK)
+        return st;
+    CU_TRY(cudaMemcpyAsync(H + o_out, D + o_out, size_t(n_q) * size_t(n_db) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(scores, H + o_out, size_t(n_q) * size_t(n_db) * 8);
     return PLM_OK;
 }
 
