@@ -249,6 +249,86 @@ def make_landmark_observations(seed: int, n_lm: int, mean_obs: float = 8.0, max_
     return np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(dirs, np.float64), obs_start
 
 
+# ---- bag-of-words vocabulary (the DBoW2 blobs are not in the mount) -------------------------------
+
+@dataclass
+class FlatVoc:
+    """A DBoW2 vocabulary tree as the flat arrays plm_voc_create takes (same attribute names as
+    oracle.FlatVocabulary)."""
+    child_start: np.ndarray
+    child_ids: np.ndarray
+    node_desc: np.ndarray
+    node_weight: np.ndarray
+    node_word: np.ndarray
+    k: int
+    L: int
+    weighting: int = 0
+    scoring: int = 0
+
+    @property
+    def n_nodes(self) -> int:
+        return len(self.node_word)
+
+    @property
+    def n_words(self) -> int:
+        return int(self.node_word.max()) + 1 if len(self.node_word) else 0
+
+
+def make_vocabulary(seed: int, k: int = 10, L: int = 3, weighting: int = 0, flip_p: float = 0.12, ragged: float = 0.1,
+                    stop_frac: float = 0.02) -> FlatVoc:
+    """Random hierarchical vocabulary shaped like DBoW2's k-means tree: children are noisy copies of their
+    parent, ids are assigned level by level within a parent (children contiguous, larger than the parent, as
+    HKmeansStep creates them); `ragged` of the inner nodes get fewer than k children or stay leaves above depth
+    L; leaves get idf-like weights log(N / n_i), `stop_frac` of them weight 0 (stopped words)."""
+    rng = np.random.default_rng(seed)
+    desc = [rand_desc(rng, 1)[0]]
+    children = [[]]
+    depth = [0]
+
+    def grow(node):
+        if depth[node] >= L:
+            return
+        if node != 0 and rng.random() < ragged / 2:
+            return                                   # a leaf above the last level
+        nk = k if rng.random() >= ragged else int(rng.integers(1, k + 1))
+        first = len(desc)
+        for _ in range(nk):
+            desc.append(flip_bits(rng, desc[node][None, :], flip_p)[0])
+            children.append([])
+            depth.append(depth[node] + 1)
+        children[node] = list(range(first, first + nk))
+        for c in children[node]:
+            grow(c)
+
+    import sys
+    sys.setrecursionlimit(max(10000, sys.getrecursionlimit()))
+    grow(0)
+    n = len(desc)
+    child_start = np.zeros(n + 1, np.int32)
+    child_start[1:] = np.cumsum([len(c) for c in children])
+    child_ids = np.array([c for cs in children for c in cs], np.int32)
+    node_word = np.full(n, -1, np.int32)
+    leaves = [i for i in range(1, n) if not children[i]]
+    node_word[leaves] = np.arange(len(leaves), dtype=np.int32)
+    node_weight = np.zeros(n, np.float64)
+    w = np.log(1000.0 / rng.integers(1, 400, len(leaves)))
+    if weighting in (1, 3):                          # TF / BINARY: weight 1 (setNodeWeights, :984-997)
+        w[:] = 1.0
+    w[rng.random(len(leaves)) < stop_frac] = 0.0
+    node_weight[leaves] = w
+    return FlatVoc(child_start, child_ids, np.ascontiguousarray(np.stack(desc), np.uint8), node_weight, node_word, k, L,
+                   weighting, 0)
+
+
+def vocabulary_features(seed: int, voc: FlatVoc, n: int, flip_p: float = 0.1) -> np.ndarray:
+    """n descriptors that are noisy copies of random leaves of the vocabulary (so that images share words)."""
+    rng = np.random.default_rng(seed)
+    leaves = np.nonzero(voc.node_word >= 0)[0]
+    if n == 0 or len(leaves) == 0:
+        return np.zeros((0, 32), np.uint8)
+    return flip_bits(rng, voc.node_desc[rng.choice(leaves, n)], flip_p)
+
+
 # ---- config 3: offline replay of many stereo frames (vectorised over frames) ---------------------
 
 @dataclass

@@ -2,7 +2,7 @@
 matching.cpp / gridStructure.cpp / lineIterator.cpp / mapFeatures.cpp compiled unmodified, see oracle/Makefile).
 
 Run in the build container (needs /root/reference to build libplref.so):
-    python tools/make_golden.py [brute] [grid] [line_coords] [med_desc]
+    python tools/make_golden.py [brute] [grid] [line_coords] [med_desc] [bow]
 The fixtures are small (a few hundred KB) and committed; tests compare the oracle port and the CUDA
 path against them, so parity stays pinned on machines where the reference cannot be built.
 """
@@ -115,10 +115,39 @@ def med_desc_cases():
     save("med_desc", **out)
 
 
+def bow_cases():
+    """DBoW2 from the reference's vendored sources (oracle/_ref/libplref_dbow.so): vocabularies built by its own
+    create() (hierarchical k-means++ on synthetic training descriptors; seeds pinned), then transform() of a
+    few descriptor sets and the full score() matrix between them, for every weighting type."""
+    rdb = oracle.ref_dbow
+    assert rdb.available(), "build oracle/_ref/libplref_dbow.so first (make -C oracle ref)"
+    rng = np.random.default_rng(synth.SEED0 + 400)
+    centres = synth.rand_desc(rng, 300)
+    train = [synth.flip_bits(rng, centres[rng.integers(0, 300, 150)], 0.15) for _ in range(30)]
+    tdesc, tstart = np.concatenate(train), np.arange(31, dtype=np.int32) * 150
+    sets = [synth.flip_bits(rng, centres[rng.integers(0, 300, n)], 0.15) for n in (200, 180, 260, 90, 33, 1)]
+    sets += [train[0], synth.rand_desc(rng, 150), synth.tie_stress_desc(rng, 64), np.zeros((0, 32), np.uint8)]
+    out = {"n_sets": np.int32(len(sets)), "n_voc": np.int32(4)}
+    for k, d in enumerate(sets):
+        out[f"set_{k}"] = d
+    for weighting in range(4):
+        h = rdb.create(tdesc, tstart, k=8, L=3, weighting=weighting, seed=11 + weighting)
+        fv = rdb.export(h, 8, 3, weighting)
+        for name, arr in fv.arrays().items():
+            out[f"voc{weighting}_{name}"] = arr
+        bows = [rdb.transform(h, d) for d in sets]
+        for k, (ids, vals) in enumerate(bows):
+            out[f"voc{weighting}_ids_{k}"] = ids
+            out[f"voc{weighting}_vals_{k}"] = vals
+        out[f"voc{weighting}_scores"] = np.array([[rdb.score(h, a, b) for b in bows] for a in bows])
+        rdb.destroy(h)
+    save("bow", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("brute", brute_cases), ("grid", grid_cases), ("line_coords", line_coord_cases),
-                     ("med_desc", med_desc_cases)):
+                     ("med_desc", med_desc_cases), ("bow", bow_cases)):
         if not only or name in only:
             fn()

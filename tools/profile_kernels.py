@@ -93,6 +93,15 @@ med_dir = torch.empty((n_lm, 3), dtype=torch.float64, device=dev)
 ld, ldr, lst = t_(ldesc), t_(ldirs), t_(lstart)
 torch.cuda.synchronize()
 MF.dev_med_desc(ctx, ld, lst, med_idx, med_desc=med_rows, dir_obs=ldr, med_dir=med_dir)
+# bag of words: DBoW2 transform of 300 keyframes (k = 10, L = 4 vocabulary) and one keyframe scored against 20 000 database vectors
+from pl_inertial_slam_b200 import bow as B  # noqa: E402
+fvoc = synth.make_vocabulary(synth.SEED0 + 40, k=10, L=4)
+voc = B.Vocabulary.from_flat(fvoc, ctx=ctx)
+n_kf = 100 if quick else 300
+feats = synth.vocabulary_features(synth.SEED0 + 41, fvoc, n_kf * 600)
+bows = voc.transform_batch(feats, np.arange(n_kf + 1, dtype=np.int32) * 600)
+db = [bows[i % n_kf] for i in range(5_000 if quick else 20_000)]
+B.score_matrix(bows[:1], db, ctx=ctx)
 torch.cuda.synchronize()
 ctx.synchronize()
 print("profile_kernels ok: launches", ctx.launch_count + ops.ctx.launch_count)
