@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--n-kf", type=int, default=N_KF, help="keyframes in the database")
     ap.add_argument("--nnr", type=float, default=0.9)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU top-2 merge: the library's peer-memory kernel (auto falls back to NCCL) or NCCL all_gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-frame / replay side metrics")
     return ap.parse_args()
@@ -270,7 +272,7 @@ def run_b200(args):
     shard_host = gen_rows(lo // PER_KF, hi // PER_KF)
     shard = torch.from_numpy(shard_host).to(dev)
     del shard_host
-    db = ShardedDescriptorDB(n_rows=n_rows, shard=shard, device=local_rank)
+    db = ShardedDescriptorDB(n_rows=n_rows, shard=shard, device=local_rank, exchange=args.exchange)
     ctx = db.ops.ctx
     n_q = args.kf_batch * PER_KF
     total_steps = args.warmup + args.steps
@@ -342,6 +344,8 @@ def run_b200(args):
         flush.fill_(s & 0xFF)
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev)
+    if db.peer is not None:
+        db.peer.check()  # raises if any peer-memory exchange timed out
 
     # ---- max over ranks ------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_ms, e2e_wall * 1e3, slice_ms], dtype=torch.float64, device=dev)
@@ -396,7 +400,10 @@ def run_b200(args):
             "config": {"workload": "config 5: loop-closure all-pairs keyframe matching (matchNNR, flat database)",
                        "keyframes": args.n_kf, "descriptors_per_kf": PER_KF, "db_rows": n_rows,
                        "db_bytes": n_rows * 32, "kf_batch": args.kf_batch, "queries_per_step": n_q, "nnr": args.nnr,
-                       "parallelism": f"database row-sharded over {world} GPU(s), NCCL all_gather of packed top-2",
+                       "parallelism": f"database row-sharded over {world} GPU(s), " + (
+                           "no exchange" if world == 1 else
+                           "per-query top-2 pushed into every rank's buffer over NVLink peer memory and merged by one kernel"
+                           if db.peer is not None else "NCCL all_gather of packed top-2 + merge kernel"),
                        "l2": f"{L2_FLUSH_BYTES >> 20} MiB flush write between timed iterations"},
             "pairs_per_step": pairs_per_step,
             "reference_equivalent_pairs_per_s": value,
@@ -411,7 +418,7 @@ def run_b200(args):
         }
         if not args.no_extras:
             try:
-                from pl_inertial_slam_b200 import bench_extras
+                import bench_extras
                 line["extras"] = bench_extras.run(ctx, args)
             except Exception as e:  # noqa: BLE001 -- side metrics must never kill the headline line
                 line["extras"] = {"error": repr(e)}

@@ -1,4 +1,5 @@
-"""Side metrics of bench.py for the frame-scale configs of BASELINE.json (1-3): per-call latency of the
+"""(Part of bench.py, kept outside the product package because its CPU legs load oracle/.)
+Side metrics of bench.py for the frame-scale configs of BASELINE.json (1-3): per-call latency of the
 stereo / temporal matchers through the host-buffer C ABI, and replay throughput (matched stereo
 frames/s) of the batched path, device-resident and end to end.  The CPU figures next to them come
 from the oracle builds (reference sources where available) on this box's host cores."""
@@ -9,8 +10,8 @@ import time
 
 import numpy as np
 
-from . import matching as M
-from . import replay, synth
+from pl_inertial_slam_b200 import matching as M
+from pl_inertial_slam_b200 import replay, synth
 
 
 def _median_ms(fn, reps=30, warm=5):
@@ -132,7 +133,7 @@ def replay_pipeline(ctx, n_frames: int, rp=None, chunk: int = 250) -> dict:
     descriptors in, per frame the stereo drivers (grid build, matchGrid, gates, compaction, back-projection)
     and the frame-to-frame match on the compacted descriptors; two launches per feature type for the replay."""
     import torch
-    from .frames import FrameConfig, FramePipeline, replay_frame_records
+    from pl_inertial_slam_b200.frames import FrameConfig, FramePipeline, replay_frame_records
     rp = synth.make_replay(synth.SEED0 + 3, n_frames) if rp is None else rp
     kp, ln, rec = replay_frame_records(rp)
     pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
@@ -196,7 +197,7 @@ def replay_pipeline_cpu_baseline(n_frames: int) -> dict:
     drivers, then of StVO::match on the compacted descriptors."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
-    from .frames import FrameConfig, replay_frame_records
+    from pl_inertial_slam_b200.frames import FrameConfig, replay_frame_records
     cores = len(os.sched_getaffinity(0))
     rp = synth.make_replay(synth.SEED0 + 3, n_frames)
     kp, ln, rec = replay_frame_records(rp)
@@ -279,8 +280,8 @@ def map_to_frame(ctx) -> dict:
     brute-force match() fallback on the same vector.  Device-resident timings (CUDA events) plus the
     host-buffer call."""
     import torch
-    from .database import GridFrame, ShardedMap
-    from . import grid as G
+    from pl_inertial_slam_b200.database import GridFrame, ShardedMap
+    from pl_inertial_slam_b200 import grid as G
     sp = synth.make_stereo_pair(synth.SEED0 + 4)
     out = {}
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -298,11 +299,11 @@ def map_to_frame(ctx) -> dict:
             s = np.stack([rng.integers(-2, 66, n_map), rng.integers(-2, 50, n_map)], 1)
             coords = np.concatenate([s, s + rng.integers(-8, 9, (n_map, 2))], 1).astype(np.int32)
             d2 = sp.ldesc_l
-            from .drivers import line_grid
+            from pl_inertial_slam_b200.drivers import line_grid
             cs, ci, dirs = line_grid(sp.ln_l, synth.INV_W, synth.INV_H)
         frame = GridFrame(torch.from_numpy(d2).to(dev), torch.from_numpy(cs).to(dev), torch.from_numpy(ci).to(dev),
                           G.GRID_ROWS, G.GRID_COLS, torch.from_numpy(dirs).to(dev) if dirs is not None else None)
-        from .database import DeviceOps
+        from pl_inertial_slam_b200.database import DeviceOps
         ops = DeviceOps(dev.index)
         smap = ShardedMap(n_map, torch.from_numpy(d1).to(dev), torch.from_numpy(coords).to(dev), ops=ops)
         win = np.array([3, 3, 3, 3], np.int32)
@@ -331,8 +332,154 @@ def map_to_frame(ctx) -> dict:
     return out
 
 
+def _timed_dev(fn, reps=10):
+    """Average device time of fn() (ms) with CUDA events on the context's stream."""
+    import torch
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def map_landmarks(ctx, cpu: bool = True) -> dict:
+    """The producer of config 4's database rows: MapPoint / MapLine::updateAverageDescDir for the whole
+    200 000-point + 50 000-line local map (mean 8 observations per landmark) in one batch -- device-resident
+    (CUDA events, arenas in HBM) and through the host-buffer call; the reference's own mapFeatures.cpp on one
+    host core beside it (bounded sample)."""
+    import torch
+    from pl_inertial_slam_b200 import mapfeatures as MF
+    n_lm = 250_000
+    desc, dirs, start = synth.make_landmark_observations(synth.SEED0 + 21, n_lm, mean_obs=8, long_lists=50, long_len=60)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    d_desc, d_dirs, d_start = t(desc), t(dirs), t(start)
+    med_idx = torch.empty(n_lm, dtype=torch.int32, device=dev)
+    med_rows = torch.empty((n_lm, 32), dtype=torch.uint8, device=dev)
+    med_dir = torch.empty((n_lm, 3), dtype=torch.float64, device=dev)
+    run_dev = lambda: MF.dev_med_desc(ctx, d_desc, d_start, med_idx, med_desc=med_rows, dir_obs=d_dirs, med_dir=med_dir)  # noqa: E731
+    torch.cuda.synchronize()
+    run_dev(); ctx.synchronize()
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run_dev()
+    ctx.synchronize()
+    dev_ms = (time.perf_counter() - t0) / reps * 1e3
+    host_ms = _median_ms(lambda: MF.med_desc_batch(desc, start, dirs, ctx=ctx), reps=5, warm=1)
+    n_obs = int(start[-1])
+    alg_bytes = 56.0 * n_obs + 4.0 * (n_lm + 1) + 60.0 * n_lm   # descriptors + directions + offsets in, idx + row + dir out
+    out = {"landmarks": n_lm, "observations": n_obs, "device_ms": dev_ms, "host_call_ms": host_ms,
+           "landmarks_per_s_device": n_lm / (dev_ms * 1e-3), "algorithmic_bytes": alg_bytes,
+           "achieved_gb_s": alg_bytes / (dev_ms * 1e-3) / 1e9,
+           "note": "device_ms = wall clock around 10 back-to-back enqueues + one stream sync (two launches each)",
+           "gpu_launches": 2}
+    if cpu:
+        import oracle
+        m = 20_000
+        sub = slice(0, int(start[m]))
+        if oracle.ref.available() and hasattr(oracle.ref.lib, "plref_med_desc"):
+            t0 = time.perf_counter(); oracle.ref.med_desc(desc[sub], dirs[sub], start[:m + 1]); dt = time.perf_counter() - t0
+            kind = "reference"
+        else:
+            t0 = time.perf_counter(); oracle.port.med_desc(desc[sub], dirs[sub], start[:m + 1]); dt = time.perf_counter() - t0
+            kind = "port"
+        out["cpu_baseline"] = {"landmarks_per_s": m / dt, "cores": 1, "kind": kind,
+                               "sample": f"{m} landmarks built observation by observation (mapFeatures.cpp), one thread"}
+    return out
+
+
+def bow_scoring(ctx, cpu: bool = True) -> dict:
+    """The loop-candidate selector in front of config 5 (mapHandler.cpp:3116-3237): DBoW2 transform of new
+    keyframes (800 descriptors each, k = 10 / L = 5 vocabulary with ~10^5 words) and the L1 score of one new
+    keyframe against a 20 000-keyframe database, device-resident; the reference's own DBoW2 on one host core
+    beside it (bounded sample)."""
+    import ctypes as C
+    import torch
+    from pl_inertial_slam_b200 import _lib as L
+    from pl_inertial_slam_b200 import bow as B
+    fvoc = synth.make_vocabulary(synth.SEED0 + 42, k=10, L=5, ragged=0.02)
+    voc = B.Vocabulary.from_flat(fvoc, ctx=ctx)
+    n_kf, per = 2000, 800
+    feats = synth.vocabulary_features(synth.SEED0 + 43, fvoc, n_kf * per, flip_p=0.05)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_desc = torch.from_numpy(feats).to(dev)
+    d_start = torch.arange(0, (n_kf + 1) * per, per, dtype=torch.int32, device=dev)
+    ids = torch.zeros(n_kf * per, dtype=torch.int32, device=dev)
+    vals = torch.zeros(n_kf * per, dtype=torch.float64, device=dev)
+    lens = torch.zeros(n_kf, dtype=torch.int32, device=dev)
+    lib = L.load()
+    ptr = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+
+    def transform():
+        L.check(lib.plm_dev_bow_transform(voc._h, ptr(d_desc), n_kf * per, ptr(d_start), n_kf, per, ptr(ids), ptr(vals),
+                                          ptr(lens)), "plm_dev_bow_transform")
+    torch.cuda.synchronize()
+    transform(); ctx.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        transform()
+    ctx.synchronize()
+    tr_ms = (time.perf_counter() - t0) / 5 * 1e3
+    # database of 20 000 keyframe vectors: the 2000 transformed keyframes replicated 10 x in HBM (distinct
+    # addresses: 16 M entry slots x 12 B = 192 MB, larger than the 126 MB L2)
+    n_db, rep = 20_000, 10
+    db_ids, db_vals = ids.repeat(rep), vals.repeat(rep)
+    db_start = torch.arange(n_db, device=dev, dtype=torch.int64) * per
+    db_len = lens.repeat(rep).contiguous()
+    q_start = torch.zeros(1, dtype=torch.int64, device=dev)
+    q_len = lens[:1].contiguous()
+    scores = torch.zeros(n_db, dtype=torch.float64, device=dev)
+
+    def score():
+        L.check(lib.plm_dev_bow_score(ctx.handle, ptr(ids), ptr(vals), ptr(q_start), ptr(q_len), 1, per, ptr(db_ids),
+                                      ptr(db_vals), ptr(db_start), ptr(db_len), n_db, ptr(scores)), "plm_dev_bow_score")
+    torch.cuda.synchronize()
+    score(); ctx.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        score()
+    ctx.synchronize()
+    sc_ms = (time.perf_counter() - t0) / 10 * 1e3
+    entries = int(db_len.sum().item())
+    out = {"vocabulary": {"k": 10, "L": 5, "nodes": fvoc.n_nodes, "words": fvoc.n_words},
+           "transform": {"keyframes": n_kf, "descriptors_per_kf": per, "device_ms": tr_ms,
+                         "keyframes_per_s": n_kf / (tr_ms * 1e-3), "descriptors_per_s": n_kf * per / (tr_ms * 1e-3)},
+           "score": {"database_keyframes": n_db, "database_entries": entries, "device_ms": sc_ms,
+                     "scores_per_s": n_db / (sc_ms * 1e-3), "algorithmic_bytes": 12.0 * entries + 12.0 * n_db + 8.0 * n_db,
+                     "achieved_gb_s": (12.0 * entries + 20.0 * n_db) / (sc_ms * 1e-3) / 1e9,
+                     "self_score": float(scores[0].item())},
+           "note": "device times = wall clock around back-to-back enqueues + one stream sync", "gpu_launches": 2}
+    if cpu:
+        import oracle
+        if oracle.ref_dbow.available():
+            h = oracle.ref_dbow.from_flat(fvoc)
+            m = 20
+            t0 = time.perf_counter()
+            bows = [oracle.ref_dbow.transform(h, feats[i * per:(i + 1) * per]) for i in range(m)]
+            t_tr = (time.perf_counter() - t0) / m
+            t0 = time.perf_counter()
+            for j in range(2000):
+                oracle.ref_dbow.score(h, bows[0], bows[j % m])
+            t_sc = (time.perf_counter() - t0) / 2000
+            oracle.ref_dbow.destroy(h)
+            out["cpu_baseline"] = {"transform_keyframes_per_s": 1.0 / t_tr, "scores_per_s": 1.0 / t_sc, "cores": 1,
+                                   "kind": "reference",
+                                   "sample": f"{m} keyframes transformed, 2000 scores; the reference's DBoW2 through "
+                                             "ctypes (score includes rebuilding two std::map BowVectors per call)"}
+    voc.close()
+    return out
+
+
 def run(ctx, args) -> dict:
     out = {"frame_latency": frame_latency(ctx)}
+    for name, fn in (("map_landmarks", map_landmarks), ("bow_scoring", bow_scoring)):
+        try:
+            out[name] = fn(ctx, cpu=not args.no_cpu_baseline)
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": repr(e)}
     try:
         out["map_to_frame"] = map_to_frame(ctx)
     except Exception as e:  # noqa: BLE001

@@ -325,6 +325,31 @@ int plm_dev_grid_colmin(plm_ctx *ctx, const plm_dev_grid_args *a, uint16_t *col_
 int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const uint16_t *seed_dev, uint64_t *m21key_dev);
 int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int n2, int32_t *m21_dev);
 
+/* ---- top-2 exchange over NVLink peer memory (multi-GPU merge without a gather collective) ------ */
+/* The per-query top-2 merge of a row-sharded database (config 5) / local map (config 4) as ONE kernel: every
+ * rank pushes its packed keys straight into every other rank's exchange buffer (peer stores over NVLink /
+ * NVSwitch), signals, waits for the other ranks' flags and merges -- see csrc/plm_peer.cuh.  Setup, once:
+ *   1. each rank:  plm_peer_alloc(ctx, world, q_cap, &buf, handle)      (cudaMalloc + CUDA IPC handle, 64 bytes)
+ *   2. the 64-byte handles are exchanged by the caller (any transport; torch.distributed all_gather here)
+ *   3. each rank:  plm_peer_open(ctx, handle_of_rank_r, &ptr_r) for r != own rank
+ * then per exchange plm_dev_top2_exchange with the same, strictly increasing `epoch` (> 0) on every rank.
+ * All ranks must call it with the same n1 <= q_cap.  Results equal plm_dev_top2_merge over an all-gather
+ * bit for bit (unsigned min over packed keys). */
+#define PLM_PEER_HANDLE_BYTES 64
+#define PLM_PEER_MAX_RANKS 16
+size_t plm_peer_buffer_bytes(int world, int q_cap);
+int plm_peer_alloc(plm_ctx *ctx, int world, int q_cap, void **buf_dev, uint8_t handle[PLM_PEER_HANDLE_BYTES]);
+int plm_peer_open(plm_ctx *ctx, const uint8_t handle[PLM_PEER_HANDLE_BYTES], void **buf_dev);
+int plm_peer_close(plm_ctx *ctx, void *buf_dev); /* a buffer obtained from plm_peer_open */
+int plm_peer_free(plm_ctx *ctx, void *buf_dev);  /* a buffer obtained from plm_peer_alloc */
+/* peers[r] = rank r's exchange buffer as mapped in this process (peers[rank] = own).  local_top2_dev: n1 x 2
+ * packed keys of this rank.  Outputs (each may be NULL): top2_out_dev n1 x 2 merged keys; m12_dev_inout +
+ * count_dev: matchNNR acceptance of the merged keys with ratio nnr (as plm_dev_nnr_accept).  error_dev
+ * (int32, required) is set to 1 if a peer did not arrive within ~2 s (nothing is written then). */
+int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, int world, int q_cap, uint32_t epoch,
+                          const uint64_t *local_top2_dev, int n1, uint64_t *top2_out_dev, float nnr,
+                          int32_t *m12_dev_inout, int32_t *count_dev, int32_t *error_dev);
+
 /* A device-resident descriptor database shard (keyframe DB / local map). */
 int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out);
 int plm_db_destroy(plm_db *db);

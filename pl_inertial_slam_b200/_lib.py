@@ -129,6 +129,13 @@ SIGNATURES = {
     "plm_dev_grid_colmin": (C.c_int, [vp, C.POINTER(DevGridArgs), vp]),
     "plm_dev_grid_match": (C.c_int, [vp, C.POINTER(DevGridArgs), vp, vp]),
     "plm_dev_m21_from_keys": (C.c_int, [vp, vp, C.c_int, vp]),
+    "plm_peer_buffer_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "plm_peer_alloc": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), u8p]),
+    "plm_peer_open": (C.c_int, [vp, u8p, C.POINTER(vp)]),
+    "plm_peer_close": (C.c_int, [vp, vp]),
+    "plm_peer_free": (C.c_int, [vp, vp]),
+    "plm_dev_top2_exchange": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, vp, C.c_int, vp,
+                                        C.c_float, vp, vp, vp]),
     "plm_db_create": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
     "plm_db_destroy": (C.c_int, [vp]),
     "plm_db_upload": (C.c_int, [vp, vp, C.c_int64, C.c_size_t, C.c_int64]),

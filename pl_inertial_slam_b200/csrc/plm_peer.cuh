@@ -1,0 +1,122 @@
+// Multi-GPU top-2 merge over NVLink peer memory ("K5"): the per-query top-2 exchange of the
+// row-sharded keyframe database / local map done by ONE kernel instead of a gather collective plus a merge.
+//
+// Every rank owns one exchange buffer (cudaMalloc + CUDA IPC, mapped into every other rank's address
+// space) laid out as   [parity 2][rank G][q_cap] ulonglong2 keys  |  [parity 2][rank G][blocks] uint32 flags.
+// A CTA handles 128 queries:
+//   push   its packed keys go straight into slot [parity][my rank][q] of EVERY rank's buffer
+//          (16-byte stores over NVLink / NVSwitch; the local copy is an ordinary store);
+//   signal __threadfence_system, then flag [parity][my rank][block] = epoch on every rank;
+//   wait   until the G flags [parity][r][block] of the OWN buffer read `epoch` (bounded spin);
+//   merge  the G x 2 keys per query with unsigned min (== the reference's lowest-index tie-breaking),
+//          optionally followed by the matchNNR ratio test.
+// A CTA only ever waits for the SAME block index of the other ranks, which depends on nothing but that
+// rank's own progress, so there is no intra-grid dependency and no deadlock for any grid size.  Buffers are
+// double-buffered by epoch parity: a rank can run at most one exchange ahead of the slowest one (it cannot
+// pass the wait of epoch e+1 before every rank has pushed e+1, i.e. has finished reading e).
+#pragma once
+#include "plm_common.cuh"
+
+namespace plm {
+
+constexpr int PEER_MAX_RANKS = 16;
+constexpr int PEER_THREADS = 128;
+
+struct PeerExchangeArgs {
+    unsigned char *peer[PEER_MAX_RANKS]; // base of every rank's exchange buffer as mapped HERE (own included)
+    int rank, world;
+    int q_cap, blocks_cap;
+    uint32_t epoch;                // > 0, the same on every rank, increases by one per exchange
+    const ulonglong2 *local;       // n1 x 2 packed keys of this rank
+    int n1;
+    ulonglong2 *out;               // merged keys (may be null)
+    float nnr;
+    int32_t *m12;                  // optional matchNNR acceptance on the merged keys
+    int32_t *count;
+    int32_t *error;                // set to 1 when a wait timed out
+    long long spin_limit;          // clock64 ticks
+};
+
+__host__ __device__ inline size_t peer_keys_bytes(int world, int q_cap) { return size_t(2) * world * q_cap * 16; }
+__host__ __device__ inline size_t peer_buffer_bytes(int world, int q_cap, int blocks_cap) {
+    return peer_keys_bytes(world, q_cap) + size_t(2) * world * blocks_cap * 4;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ ulonglong2 ld_volatile_u64x2(const ulonglong2 *p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerExchangeArgs a) {
+    const int q = blockIdx.x * PEER_THREADS + threadIdx.x;
+    const int par = a.epoch & 1;
+    const size_t key_slot = (size_t(par) * a.world + a.rank) * a.q_cap;       // [par][my rank][.]
+    const size_t keys_bytes = peer_keys_bytes(a.world, a.q_cap);
+    // push
+    if (q < a.n1) {
+        const ulonglong2 v = a.local[q];
+        for (int p = 0; p < a.world; ++p) {
+            const int dst = (a.rank + p) % a.world; // start with the local copy, spread the remote stores
+            reinterpret_cast<ulonglong2 *>(a.peer[dst])[key_slot + q] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // signal
+    if (threadIdx.x < a.world) {
+        const int dst = (a.rank + threadIdx.x) % a.world;
+        uint32_t *flags = reinterpret_cast<uint32_t *>(a.peer[dst] + keys_bytes);
+        st_release_sys(flags + (size_t(par) * a.world + a.rank) * a.blocks_cap + blockIdx.x, a.epoch);
+    }
+    // wait for block `blockIdx.x` of every rank
+    __shared__ int s_fail;
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        const uint32_t *flags = reinterpret_cast<const uint32_t *>(a.peer[a.rank] + keys_bytes);
+        const uint32_t *f = flags + (size_t(par) * a.world + threadIdx.x) * a.blocks_cap + blockIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != a.epoch) {
+            if (clock64() - t0 > a.spin_limit) {
+                s_fail = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (threadIdx.x == 0) atomicExch(a.error, 1);
+        return;
+    }
+    __threadfence_system();
+    // merge
+    if (q >= a.n1) return;
+    const ulonglong2 *keys = reinterpret_cast<const ulonglong2 *>(a.peer[a.rank]) + size_t(par) * a.world * a.q_cap;
+    unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
+    for (int r = 0; r < a.world; ++r) {
+        const ulonglong2 v = ld_volatile_u64x2(keys + size_t(r) * a.q_cap + q);
+        top2_insert(b0, b1, v.x);
+        top2_insert(b0, b1, v.y);
+    }
+    if (a.out) a.out[q] = make_ulonglong2(b0, b1);
+    if (a.m12 && b1 != KEY64_ABSENT) {
+        const float d0 = static_cast<float>(static_cast<int>(b0 >> 32));
+        const float d1 = static_cast<float>(static_cast<int>(b1 >> 32));
+        if (d0 < __fmul_rn(d1, a.nnr)) { // matchNNR ratio test in fp32 (matching.cpp:54)
+            a.m12[q] = static_cast<int32_t>(b0 & 0xFFFFFFFFull);
+            if (a.count) atomicAdd(a.count, 1);
+        }
+    }
+}
+
+} // namespace plm

@@ -25,6 +25,7 @@
 #include "plm_knn2.cuh"
 #include "plm_map.cuh"
 #include "plm_micro.cuh"
+#include "plm_peer.cuh"
 #include "plm_stereo.cuh"
 
 #define PLM_API extern "C" __attribute__((visibility("default")))
@@ -1148,6 +1149,101 @@ PLM_API int plm_med_desc(plm_ctx *ctx, const uint8_t *desc_obs, int64_t n_obs, s
     std::memcpy(med_idx, ctx->h_buf + o_idx, size_t(n_lm) * 4);
     if (med_desc) std::memcpy(med_desc, ctx->h_buf + o_med, size_t(n_lm) * 32);
     if (want_dir) std::memcpy(med_dir, ctx->h_buf + o_mdir, size_t(n_lm) * 24);
+    return PLM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-2 exchange over NVLink peer memory (csrc/plm_peer.cuh)
+namespace {
+inline int peer_blocks_cap(int q_cap) { return (q_cap + plm::PEER_THREADS - 1) / plm::PEER_THREADS; }
+} // namespace
+
+PLM_API size_t plm_peer_buffer_bytes(int world, int q_cap) {
+    if (world <= 0 || q_cap <= 0) return 0;
+    return plm::peer_buffer_bytes(world, q_cap, peer_blocks_cap(q_cap));
+}
+
+PLM_API int plm_peer_alloc(plm_ctx *ctx, int world, int q_cap, void **buf_dev, uint8_t handle[PLM_PEER_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == PLM_PEER_HANDLE_BYTES, "IPC handle size");
+    if (!buf_dev || !handle) return fail(PLM_E_INVALID, "null pointer");
+    *buf_dev = nullptr;
+    if (world <= 0 || world > PLM_PEER_MAX_RANKS || q_cap <= 0) return fail(PLM_E_INVALID, "world in 1..16 and q_cap > 0 required");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    const size_t bytes = plm_peer_buffer_bytes(world, q_cap);
+    void *p = nullptr;
+    CU_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, ctx->stream); // flags start at epoch 0 = "nothing arrived"
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(PLM_E_CUDA, std::string("plm_peer_alloc: ") + cudaGetErrorString(e));
+    }
+    std::memcpy(handle, &h, sizeof(h));
+    *buf_dev = p;
+    return PLM_OK;
+}
+
+PLM_API int plm_peer_open(plm_ctx *ctx, const uint8_t handle[PLM_PEER_HANDLE_BYTES], void **buf_dev) {
+    if (!buf_dev || !handle) return fail(PLM_E_INVALID, "null pointer");
+    *buf_dev = nullptr;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CU_TRY(cudaIpcOpenMemHandle(buf_dev, h, cudaIpcMemLazyEnablePeerAccess));
+    return PLM_OK;
+}
+
+PLM_API int plm_peer_close(plm_ctx *ctx, void *buf_dev) {
+    if (!buf_dev) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaIpcCloseMemHandle(buf_dev));
+    return PLM_OK;
+}
+
+PLM_API int plm_peer_free(plm_ctx *ctx, void *buf_dev) {
+    if (!buf_dev) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaFree(buf_dev));
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, int world, int q_cap, uint32_t epoch,
+                                  const uint64_t *local_top2_dev, int n1, uint64_t *top2_out_dev, float nnr,
+                                  int32_t *m12_dev_inout, int32_t *count_dev, int32_t *error_dev) {
+    if (world <= 0 || world > PLM_PEER_MAX_RANKS || rank < 0 || rank >= world) return fail(PLM_E_INVALID, "bad rank / world");
+    if (n1 < 0 || n1 > q_cap || epoch == 0) return fail(PLM_E_INVALID, "n1 outside [0, q_cap] or epoch == 0");
+    if (!peers || !error_dev || (n1 > 0 && !local_top2_dev)) return fail(PLM_E_INVALID, "null pointer");
+    for (int r = 0; r < world; ++r)
+        if (!peers[r]) return fail(PLM_E_INVALID, "null peer buffer");
+    if (n1 == 0) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::PeerExchangeArgs a{};
+    for (int r = 0; r < world; ++r) a.peer[r] = static_cast<unsigned char *>(peers[r]);
+    a.rank = rank;
+    a.world = world;
+    a.q_cap = q_cap;
+    a.blocks_cap = peer_blocks_cap(q_cap);
+    a.epoch = epoch;
+    a.local = reinterpret_cast<const ulonglong2 *>(local_top2_dev);
+    a.n1 = n1;
+    a.out = reinterpret_cast<ulonglong2 *>(top2_out_dev);
+    a.nnr = nnr;
+    a.m12 = m12_dev_inout;
+    a.count = count_dev;
+    a.error = error_dev;
+    a.spin_limit = 4000000000ll; // ~2 s of SM clock
+    plm::top2_exchange_merge_kernel<<<(n1 + plm::PEER_THREADS - 1) / plm::PEER_THREADS, plm::PEER_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
     return PLM_OK;
 }
 

@@ -9,6 +9,9 @@ streams, the NCCL collective), all arithmetic is in the CUDA library:
   with GLOBAL row indices, all_gather of the packed keys, lexicographic merge.  Unsigned min over
   (distance << 32 | global index) is the reference's lowest-index tie-breaking, so any number of
   shards gives bit-identical results.
+  The exchange itself is the library's own kernel over NVLink peer memory (``PeerExchange``: push into every
+  rank's buffer, flag, wait, merge, ratio test -- csrc/plm_peer.cuh); NCCL's all_gather + a merge kernel is
+  the equivalent form used when CUDA IPC peer mapping is unavailable.
 * ``ShardedMap`` -- the local map is desc1 (the QUERY side) of matchMap2KF* (config 4): rows
   sharded, the frame (desc2 + its grid) replicated.  ``match`` needs one exchange (the 21 direction's
   top-2), ``match_grid`` needs the per-column running minima of lower-ranked shards before matching
@@ -165,6 +168,87 @@ class _Group:
         return t
 
 
+class PeerExchange:
+    """Top-2 exchange over NVLink peer memory (plm_peer_* / plm_dev_top2_exchange, csrc/plm_peer.cuh): one
+    kernel pushes this rank's packed keys into every rank's exchange buffer, waits for the others and merges.
+    torch.distributed only carries the 64-byte CUDA IPC handles once, at construction.
+
+    ``PeerExchange.create`` returns None when peer mapping is not possible on some rank (e.g. every process is
+    restricted to its own device); the callers then keep using the NCCL all_gather + merge-kernel form, which
+    gives bit-identical results."""
+
+    def __init__(self, g: "_Group", ops: "DeviceOps", q_cap: int):
+        self.g, self.ops, self.q_cap = g, ops, int(q_cap)
+        self.lib = ops.lib
+        self.world, self.rank = g.world, g.rank
+        self.epoch = 0
+        self._own = C.c_void_p()
+        self._opened = []
+        dev = torch.device("cuda", ops.device)
+        handle = (C.c_uint8 * 64)()
+        st = self.lib.plm_peer_alloc(ops.ctx.handle, self.world, self.q_cap, C.byref(self._own), handle)
+        ok = torch.tensor([1 if st == L.PLM_OK else 0], dtype=torch.int32, device=dev)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        handles = g.all_gather(mine).cpu().numpy()                      # [world, 64]
+        ptrs = (C.c_void_p * self.world)()
+        if st == L.PLM_OK:
+            ptrs[self.rank] = self._own
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                h = (C.c_uint8 * 64)(*handles[r].tolist())
+                if self.lib.plm_peer_open(ops.ctx.handle, h, C.byref(p)) != L.PLM_OK:
+                    ok[0] = 0
+                    break
+                self._opened.append(p)
+                ptrs[r] = p
+        g.dist.all_reduce(ok, op=g.dist.ReduceOp.MIN, group=g.group)
+        self.ok = bool(ok.item())
+        self.ptrs = ptrs
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        if not self.ok:
+            self.close()
+
+    @classmethod
+    def create(cls, g: "_Group", ops, q_cap: int) -> Optional["PeerExchange"]:
+        if g.world <= 1 or g.world > 16 or not isinstance(ops, DeviceOps):
+            return None
+        x = cls(g, ops, q_cap)
+        return x if x.ok else None
+
+    def exchange(self, local: torch.Tensor, out: Optional[torch.Tensor] = None, nnr: float = 0.0,
+                 m12: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """local: n1 x 2 int64 packed keys of this rank -> merged keys over all ranks (and / or the matchNNR
+        acceptance written to m12 / count).  Every rank must call this with the same n1, in the same order."""
+        n1 = int(local.shape[0])
+        assert n1 <= self.q_cap and local.dtype == torch.int64 and local.is_contiguous()
+        if out is None and m12 is None:
+            out = torch.empty((n1, 2), dtype=torch.int64, device=local.device)
+        self.epoch += 1
+        self.ops._bind_stream()
+        L.check(self.lib.plm_dev_top2_exchange(self.ops.ctx.handle, self.ptrs, self.rank, self.world, self.q_cap,
+                                               self.epoch, _ptr(local), n1, _ptr(out), C.c_float(nnr), _ptr(m12),
+                                               _ptr(count), _ptr(self.error)), "plm_dev_top2_exchange")
+        return out
+
+    def check(self) -> None:
+        """Host sync: raises if any exchange since the last check timed out waiting for a peer."""
+        if int(self.error.item()) != 0:
+            raise RuntimeError("plm_dev_top2_exchange: a peer rank did not arrive (timeout)")
+
+    def close(self) -> None:
+        for p in self._opened:
+            self.lib.plm_peer_close(self.ops.ctx.handle, p)
+        self._opened = []
+        if self._own:
+            if self.g.dist is not None and self.ok:
+                torch.cuda.synchronize()
+                self.g.dist.barrier(group=self.g.group)   # nobody may still be writing into this buffer
+            self.lib.plm_peer_free(self.ops.ctx.handle, self._own)
+            self._own = C.c_void_p()
+
+
 class ShardedDescriptorDB:
     """Flat descriptor database (config 5), row-sharded over the ranks of a process group.
 
@@ -173,10 +257,16 @@ class ShardedDescriptorDB:
     """
 
     def __init__(self, rows: Optional[np.ndarray] = None, n_rows: Optional[int] = None, device: Optional[int] = None,
-                 group=None, shard: Optional[torch.Tensor] = None, ops=None):
+                 group=None, shard: Optional[torch.Tensor] = None, ops=None, exchange: str = "auto", q_cap: int = 8192):
+        """exchange: "peer" / "auto" = per-query top-2 merged by the peer-memory kernel (falls back to NCCL when
+        peer mapping is unavailable; "peer" raises instead), "nccl" = all_gather + merge kernel.  q_cap = the
+        largest query batch the peer buffers are sized for (larger batches take the NCCL form)."""
         self.g = _Group(group)
         self.world, self.rank = self.g.world, self.g.rank
         self.ops = ops if ops is not None else DeviceOps(device)
+        self.peer = PeerExchange.create(self.g, self.ops, q_cap) if exchange in ("peer", "auto") else None
+        if exchange == "peer" and self.world > 1 and self.peer is None:
+            raise RuntimeError("peer-memory exchange requested but CUDA IPC peer mapping is unavailable")
         if shard is not None:
             assert n_rows is not None
             self.n_rows = int(n_rows)
@@ -198,13 +288,19 @@ class ShardedDescriptorDB:
         local = self.knn2_local(q)
         if self.world == 1:
             return local
+        if self.peer is not None and q.shape[0] <= self.peer.q_cap:
+            return self.peer.exchange(local)
         return self.ops.top2_merge(self.g.all_gather(local))
 
     def match_nnr(self, q: torch.Tensor, nnr: float):
         """StVO::matchNNR of the queries against the whole (sharded) database -> (count, m12)."""
-        top2 = self.knn2(q)
         m12 = torch.full((q.shape[0],), -1, dtype=torch.int32, device=q.device)
         count = torch.zeros(1, dtype=torch.int32, device=q.device)
+        if self.world > 1 and self.peer is not None and q.shape[0] <= self.peer.q_cap:
+            # local slices -> ONE kernel: push to the peers, wait, merge, ratio test
+            self.peer.exchange(self.knn2_local(q), nnr=nnr, m12=m12, count=count)
+            return count, m12
+        top2 = self.knn2(q)
         self.ops.nnr_accept(top2, nnr, m12, count)
         return count, m12
 
@@ -217,10 +313,13 @@ class ShardedMap:
     """
 
     def __init__(self, n_rows: int, d1_shard: torch.Tensor, coords_shard: Optional[torch.Tensor] = None, group=None,
-                 ops=None, device: Optional[int] = None):
+                 ops=None, device: Optional[int] = None, exchange: str = "auto", q_cap: int = 4096):
         self.g = _Group(group)
         self.world, self.rank = self.g.world, self.g.rank
         self.ops = ops if ops is not None else DeviceOps(device)
+        self.peer = PeerExchange.create(self.g, self.ops, q_cap) if exchange in ("peer", "auto") else None
+        if exchange == "peer" and self.world > 1 and self.peer is None:
+            raise RuntimeError("peer-memory exchange requested but CUDA IPC peer mapping is unavailable")
         self.n_rows = int(n_rows)
         self.lo, self.hi = shard_bounds(self.n_rows, self.world, self.rank)
         assert d1_shard.shape[0] == self.hi - self.lo
@@ -254,9 +353,12 @@ class ShardedMap:
         if best_lr:
             # direction 21: per-shard top-2 with global map indices -> gather -> merge -> ratio test
             part = self.ops.knn2(d2, self.d1, idx_base=self.lo)
-            top21 = part if self.world == 1 else self.ops.top2_merge(self.g.all_gather(part))
             m21 = torch.full((d2.shape[0],), -1, dtype=torch.int32, device=dev)
-            self.ops.nnr_accept(top21, nnr, m21, None)
+            if self.world > 1 and self.peer is not None and d2.shape[0] <= self.peer.q_cap:
+                self.peer.exchange(part, nnr=nnr, m12=m21)       # push / wait / merge / ratio test in one kernel
+            else:
+                top21 = part if self.world == 1 else self.ops.top2_merge(self.g.all_gather(part))
+                self.ops.nnr_accept(top21, nnr, m21, None)
             self.ops.cross_check(m12, self.lo, m21, count)
         self.g.all_reduce_sum(count)
         return count, self._gather_rows(m12)

@@ -35,6 +35,23 @@ def main():
     count, m12 = sdb.match_nnr(torch.from_numpy(q).to(dev), 0.9)
     n_o, m_o = port.match_nnr(q, db, 0.9)
     assert int(count.item()) == n_o and (m12.cpu().numpy() == m_o).all(), "sharded matchNNR"
+    # the same through both exchange forms, many epochs in a row (double-buffered peer slots, ragged sizes)
+    mode = os.environ.get("PLM_EXPECT_EXCHANGE", "")
+    if mode == "peer":
+        assert sdb.peer is not None, "peer-memory exchange unavailable"
+    nccl_db = ShardedDescriptorDB(n_rows=len(db), shard=sdb.shard, device=local, ops=sdb.ops, exchange="nccl")
+    assert nccl_db.peer is None
+    for n1 in (1, 127, 128, 129, 801, 640, 5, 800, 333, 802):
+        qq = synth.tie_stress_desc(rng, n1)
+        qd = torch.from_numpy(qq).to(dev)
+        want = port.knn2_packed(qq, db)
+        for d in (sdb, nccl_db):
+            assert (d.knn2(qd).cpu().numpy().view(np.uint64) == want).all(), ("knn2", n1, d.peer is not None)
+            c, m = d.match_nnr(qd, 0.9)
+            n_o, m_o = port.match_nnr(qq, db, 0.9)
+            assert int(c.item()) == n_o and (m.cpu().numpy() == m_o).all(), ("matchNNR", n1, d.peer is not None)
+    if sdb.peer is not None:
+        sdb.peer.check()
 
     # map -> frame (config 4 shape, scaled)
     for is_lines in (False, True):
@@ -55,7 +72,7 @@ def main():
             assert int(count2.item()) == n_o2 and (m12b.cpu().numpy() == m_o2).all(), ("sharded match fallback", is_lines)
     dist.barrier()
     if rank == 0:
-        print("DIST_GPU_CHECK_OK world", world)
+        print("DIST_GPU_CHECK_OK world", world, "exchange", "peer" if sdb.peer is not None else "nccl")
     dist.destroy_process_group()
 
 

@@ -77,3 +77,16 @@ def test_host_mirror_raises_reference_messages(plm_lib):
         M.matchGrid(np.zeros((3, 2), np.int32), d, g, d, GridWindow(), [])
     with pytest.raises(RuntimeError, match=r"\[matchGrid\] Each line needs"):
         M.matchGrid(np.zeros((3, 4), np.int32), d, g, d, np.zeros((4, 2)), GridWindow(), [])
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under pl_inertial_slam_b200/ may import or load it."""
+    pkg = os.path.join(ROOT, "pl_inertial_slam_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(import oracle|from oracle)\b", text, flags=re.M) or "libploracle" in text or "libplref" in text:
+                    offenders.append(f)
+    assert not offenders, offenders

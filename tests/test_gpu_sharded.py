@@ -109,3 +109,54 @@ def test_nccl_two_ranks():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DIST_GPU_CHECK_OK" in res.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_exchange_kernel_one_gpu(plm_lib, world):
+    """top2_exchange_merge_kernel with `world` ranks emulated on ONE GPU: one context (stream) and one exchange
+    buffer per rank, plain device pointers instead of CUDA IPC mappings.  The kernels of the ranks run
+    concurrently and wait for each other's flags exactly as they do across GPUs."""
+    import ctypes as C
+    from pl_inertial_slam_b200 import _lib as L
+    from pl_inertial_slam_b200.database import DeviceOps, shard_bounds
+    rng = np.random.default_rng(77 + world)
+    db = synth.tie_stress_desc(rng, 9001)
+    q_cap = 1500
+    ranks = [DeviceOps(0) for _ in range(world)]
+    bufs = (C.c_void_p * world)()
+    for r, o in enumerate(ranks):
+        p, h = C.c_void_p(), (C.c_uint8 * 64)()
+        L.check(plm_lib.plm_peer_alloc(o.ctx.handle, world, q_cap, C.byref(p), h), "plm_peer_alloc")
+        bufs[r] = p
+    shards = [torch.from_numpy(db[slice(*shard_bounds(len(db), world, r))].copy()).cuda() for r in range(world)]
+    err = torch.zeros(world, dtype=torch.int32, device="cuda")
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    epoch = 0
+    for n1 in (1, 128, 129, 1500, 700, 33, 1024):            # several epochs: both parities, ragged last block
+        q = synth.tie_stress_desc(rng, n1)
+        qd = torch.from_numpy(q).cuda()
+        want = port.knn2_packed(q, db)
+        n_o, m_o = port.match_nnr(q, db, 0.9)
+        epoch += 1
+        outs, m12s, cnts = [], [], []
+        torch.cuda.synchronize()
+        for r, o in enumerate(ranks):
+            with torch.cuda.stream(streams[r]):
+                lo, _ = shard_bounds(len(db), world, r)
+                local = o.knn2(qd, shards[r], idx_base=lo)
+                out = torch.empty((n1, 2), dtype=torch.int64, device="cuda")
+                m12 = torch.full((n1,), -1, dtype=torch.int32, device="cuda")
+                cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+                o._bind_stream()
+                L.check(plm_lib.plm_dev_top2_exchange(o.ctx.handle, bufs, r, world, q_cap, epoch, C.c_void_p(local.data_ptr()),
+                                                      n1, C.c_void_p(out.data_ptr()), C.c_float(0.9), C.c_void_p(m12.data_ptr()),
+                                                      C.c_void_p(cnt.data_ptr()), C.c_void_p(err[r:].data_ptr())),
+                        "plm_dev_top2_exchange")
+                outs.append(out); m12s.append(m12); cnts.append(cnt)
+        torch.cuda.synchronize()
+        assert not err.any().item(), "a rank timed out"
+        for r in range(world):
+            assert (outs[r].cpu().numpy().view(np.uint64) == want).all(), (n1, r)
+            assert int(cnts[r].item()) == n_o and (m12s[r].cpu().numpy() == m_o).all(), (n1, r)
+    for r, o in enumerate(ranks):
+        plm_lib.plm_peer_free(o.ctx.handle, bufs[r])

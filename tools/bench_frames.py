@@ -4,7 +4,8 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pl_inertial_slam_b200 import bench_extras, matching as M  # noqa: E402
+import bench_extras  # noqa: E402
+from pl_inertial_slam_b200 import matching as M  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 ctx = M.Context(0)
