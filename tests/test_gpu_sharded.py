@@ -138,21 +138,24 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
         want = port.knn2_packed(q, db)
         n_o, m_o = port.match_nnr(q, db, 0.9)
         epoch += 1
-        outs, m12s, cnts = [], [], []
+        # everything that allocates or may synchronise the device first (allocations between the launches would
+        # serialise the ranks' kernels on this single GPU; across processes every rank has its own context) ...
+        locals_, outs, m12s, cnts = [], [], [], []
+        for r, o in enumerate(ranks):
+            lo, _ = shard_bounds(len(db), world, r)
+            locals_.append(o.knn2(qd, shards[r], idx_base=lo))
+            outs.append(torch.empty((n1, 2), dtype=torch.int64, device="cuda"))
+            m12s.append(torch.full((n1,), -1, dtype=torch.int32, device="cuda"))
+            cnts.append(torch.zeros(1, dtype=torch.int32, device="cuda"))
         torch.cuda.synchronize()
+        # ... then only the exchange kernels, one stream per rank, back to back
         for r, o in enumerate(ranks):
             with torch.cuda.stream(streams[r]):
-                lo, _ = shard_bounds(len(db), world, r)
-                local = o.knn2(qd, shards[r], idx_base=lo)
-                out = torch.empty((n1, 2), dtype=torch.int64, device="cuda")
-                m12 = torch.full((n1,), -1, dtype=torch.int32, device="cuda")
-                cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
                 o._bind_stream()
-                L.check(plm_lib.plm_dev_top2_exchange(o.ctx.handle, bufs, r, world, q_cap, epoch, C.c_void_p(local.data_ptr()),
-                                                      n1, C.c_void_p(out.data_ptr()), C.c_float(0.9), C.c_void_p(m12.data_ptr()),
-                                                      C.c_void_p(cnt.data_ptr()), C.c_void_p(err[r:].data_ptr())),
-                        "plm_dev_top2_exchange")
-                outs.append(out); m12s.append(m12); cnts.append(cnt)
+                L.check(plm_lib.plm_dev_top2_exchange(o.ctx.handle, bufs, r, world, q_cap, epoch, C.c_void_p(locals_[r].data_ptr()),
+                                                      n1, C.c_void_p(outs[r].data_ptr()), C.c_float(0.9),
+                                                      C.c_void_p(m12s[r].data_ptr()), C.c_void_p(cnts[r].data_ptr()),
+                                                      C.c_void_p(err[r:].data_ptr())), "plm_dev_top2_exchange")
         torch.cuda.synchronize()
         assert not err.any().item(), "a rank timed out"
         for r in range(world):
