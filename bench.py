@@ -416,13 +416,13 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": roofline,
         }
-        if not args.no_extras:
+        if not args.no_extras and world == 1:  # side metrics are single-GPU workloads (configs 1-4 on one GPU)
             try:
                 import bench_extras
                 line["extras"] = bench_extras.run(ctx, args)
             except Exception as e:  # noqa: BLE001 -- side metrics must never kill the headline line
                 line["extras"] = {"error": repr(e)}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N=1 only
             base = cpu_reference_arm(sample_rows=400_000, n_q=PER_KF, seconds=args.cpu_seconds, nnr=args.nnr)
             cv = cv2_all_core(PER_KF, 200_000)
             if cv:
