@@ -1065,7 +1065,8 @@ namespace {
 // Both launches of a batch; `work` (1 + n_lm int32) is scratch for the list of long observation lists.
 int launch_med_desc(plm_ctx *ctx, plm::MedArgs a) {
     CU_TRY(cudaMemsetAsync(a.work, 0, 4, ctx->stream));
-    const int ctas = std::min((a.n_lm + plm::MED_WARPS - 1) / plm::MED_WARPS, ctx->sm_count * 32);
+    const int per_cta = 4 * plm::MED_WARPS; // a warp takes 4 landmarks at a time
+    const int ctas = std::min((a.n_lm + per_cta - 1) / per_cta, ctx->sm_count * 32);
     plm::med_desc_warp_kernel<<<ctas, 32 * plm::MED_WARPS, 0, ctx->stream>>>(a);
     ctx->launches++;
     CU_TRY(cudaGetLastError());

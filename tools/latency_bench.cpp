@@ -1,7 +1,10 @@
 // C-level latency of the host-buffer entry points (no Python in the loop).
 //   g++ -O2 -std=c++17 tools/latency_bench.cpp -Iinclude -Lpl_inertial_slam_b200/lib -lplmatch -Wl,-rpath,$PWD/pl_inertial_slam_b200/lib -o /tmp/latency_bench
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <cmath>
+#include <thread>
 #include <cstdint>
 #include <cstdio>
 #include <random>
@@ -21,6 +24,103 @@ template <class F> double median_us(F &&f, int reps) {
     }
     std::sort(t.begin(), t.end());
     return t[t.size() / 2];
+}
+
+// One stereo frame the way the reference drives the matcher: StereoFrame::extractStereoFeatures runs points and
+// lines on two threads (stereoFrame.cpp:75-76), then StereoFrameHandler::f2fTracking does the same for the
+// temporal matches (stereoFrameHandler.cpp:142-143).  Two persistent host threads (each with its own per-thread
+// plm context = its own CUDA stream), two stages per frame with a join after each: wall time per frame.
+struct Feat {
+    int n;
+    std::vector<uint8_t> d1, d2;
+    std::vector<int32_t> coords, cell_start, cell_items, m12;
+    std::vector<double> dirs2;
+};
+
+static Feat make_feat(std::mt19937_64 &rng, int n, bool lines) {
+    const int rows = 48, cols = 64;
+    Feat f;
+    f.n = n;
+    f.d1.resize(size_t(n) * 32);
+    f.d2.resize(size_t(n) * 32);
+    for (auto &b : f.d1) b = uint8_t(rng());
+    for (size_t i = 0; i < f.d2.size(); ++i) f.d2[i] = f.d1[i] ^ ((rng() % 12 == 0) ? uint8_t(1u << (rng() % 8)) : 0);
+    f.coords.resize(size_t(n) * (lines ? 4 : 2));
+    f.cell_start.assign(rows * cols + 1, 0);
+    f.cell_items.resize(n);
+    f.m12.resize(n);
+    std::vector<int> cx(n), cy(n);
+    for (int i = 0; i < n; ++i) {
+        cx[i] = 10 + int(rng() % (cols - 10));
+        cy[i] = int(rng() % rows);
+        const int qx = std::min(cols - 1, cx[i] + int(rng() % 8)), qy = cy[i]; // left feature: right one shifted by a disparity
+        if (lines) {
+            const int dx = int(rng() % 7) - 3, dy = int(rng() % 7) - 3;
+            f.coords[4 * i] = qx; f.coords[4 * i + 1] = qy; f.coords[4 * i + 2] = qx + dx; f.coords[4 * i + 3] = qy + dy;
+            const double nrm = std::sqrt(double(dx * dx + dy * dy));
+            f.dirs2.push_back(nrm > 0 ? dx / nrm : 1.0);
+            f.dirs2.push_back(nrm > 0 ? dy / nrm : 0.0);
+        } else {
+            f.coords[2 * i] = qx; f.coords[2 * i + 1] = qy;
+        }
+        f.cell_start[cx[i] * rows + cy[i] + 1]++;
+    }
+    for (int c = 0; c < rows * cols; ++c) f.cell_start[c + 1] += f.cell_start[c];
+    std::vector<int32_t> cur(f.cell_start.begin(), f.cell_start.end() - 1);
+    for (int i = 0; i < n; ++i) f.cell_items[cur[cx[i] * rows + cy[i]]++] = i;
+    return f;
+}
+
+static void frame_mode(int reps) {
+    std::mt19937_64 rng(7);
+    Feat P = make_feat(rng, 600, false), Ln = make_feat(rng, 200, true);
+    const int32_t win_st[4] = {10, 0, 0, 0};
+    auto stereo = [&](Feat &f, bool lines) {
+        int cnt = 0;
+        std::fill(f.m12.begin(), f.m12.end(), -1);
+        if (lines)
+            plm_match_grid_lines(nullptr, f.coords.data(), f.d1.data(), f.n, 32, f.cell_start.data(), f.cell_items.data(), 48, 64,
+                                 f.d2.data(), f.n, 32, f.dirs2.data(), 0.75, win_st, 0.9, 1, f.m12.data(), &cnt);
+        else
+            plm_match_grid_points(nullptr, f.coords.data(), f.d1.data(), f.n, 32, f.cell_start.data(), f.cell_items.data(), 48, 64,
+                                  f.d2.data(), f.n, 32, win_st, 0.9, 1, f.m12.data(), &cnt);
+    };
+    auto temporal = [&](Feat &f) {
+        int cnt = 0;
+        std::fill(f.m12.begin(), f.m12.end(), -1);
+        plm_match(nullptr, f.d1.data(), f.n, 32, f.d2.data(), f.n, 32, 0.9f, 1, f.m12.data(), &cnt);
+    };
+    // serial: the four calls one after the other on one thread
+    const double serial = median_us([&] { stereo(P, false); stereo(Ln, true); temporal(P); temporal(Ln); }, reps);
+    // two threads, as the reference: a generation counter starts a stage, a done counter joins it
+    std::atomic<int> go{0}, done{0};
+    std::atomic<bool> quit{false};
+    auto worker = [&](Feat *f, bool lines) {
+        int seen = 0;
+        while (true) {
+            while (go.load(std::memory_order_acquire) == seen)
+                if (quit.load()) return;
+            ++seen;
+            if (seen & 1) stereo(*f, lines);
+            else temporal(*f);
+            done.fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::thread tp(worker, &P, false), tl(worker, &Ln, true);
+    auto frame = [&] {
+        for (int stage = 0; stage < 2; ++stage) {
+            const int target = done.load() + 2;
+            go.fetch_add(1, std::memory_order_release);
+            while (done.load(std::memory_order_acquire) < target) {
+            }
+        }
+    };
+    const double threaded = median_us(frame, reps);
+    quit.store(true);
+    tp.join();
+    tl.join();
+    printf("frame (600 pts + 200 lines): stereo matchGrid + temporal match, 4 calls serial %7.1f us; points || lines on two host threads "
+           "(the reference's std::async structure) %7.1f us\n", serial, threaded);
 }
 
 int main(int argc, char **argv) {
@@ -69,5 +169,6 @@ int main(int argc, char **argv) {
         printf("n=%4d  matchGrid(+-3) %7.1f us (%d matches)  matchGrid(10,0,0,0) %7.1f us  match %7.1f us (%d)  matchNNR %7.1f us\n", n, a,
                int(a_cnt), b, c, int(c_cnt), d);
     }
+    frame_mode(reps);
     return 0;
 }
