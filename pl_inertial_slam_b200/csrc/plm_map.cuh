@@ -14,9 +14,9 @@
 //  * med_desc_warp_kernel: lists of up to 32 observations (every list the SLAM system produces in practice: a
 //    landmark is seen from a few dozen keyframes at most).  A warp takes 4 consecutive landmarks and packs them
 //    by their longest list -- 4 landmarks x 8 lanes, 2 x 16 or 1 x 32 -- so short lists do not idle most of the
-//    warp.  Sub-lane i of a group owns observation i in registers; row j is re-read from L1; the n distances of a
-//    lane go to a private column of shared memory; the order statistic is a 9-step binary search on the value
-//    range [0, 256]; the winner is a butterfly min over the group on (value << 5 | sub-lane) -- lowest row on ties
+//    warp.  Sub-lane i of a group owns observation i in registers; row j is re-read from L1; the distances of a
+//    lane's row stay in registers, padded to the group width, and go through a bitonic sorting network (all
+//    indices compile-time); the winner is a butterfly min over the group on (value << 5 | sub-lane) -- lowest row on ties
 //    like the reference's strict `<`.
 //  * med_desc_cta_kernel: landmarks with more than 32 observations are appended to a device work list by
 //    the first kernel and handled by persistent CTAs (one thread per row, distances recomputed in each
@@ -68,77 +68,125 @@ __device__ __forceinline__ double med_dir_component(const double *__restrict__ d
     return __ddiv_rn(s, static_cast<double>(n));
 }
 
-// One pass of a warp over 32 / G landmarks, G lanes each (G = 8, 16 or 32): sub-lane i of a group owns observation i.
-// `n_in` / `lo_in` are this lane's group values (n_in = 0 for a group without a landmark in this pass; lists longer
-// than G never get here).  `nmax` is the warp-uniform maximum of n over the groups of the pass.
+// One pass of a warp over 32 / G landmarks, G lanes each (G = 8, 16 or 32): sub-lane i of a group owns observation i
+// and keeps the G distances of its row in REGISTERS (every loop below is unrolled over compile-time indices).
+// `n` / `lo` are this lane's group values (n = 0 for a group without a landmark in this pass; lists longer than G
+// never get here); `nmax` is the warp-uniform maximum of n over the groups of the pass.
 template <int G>
-__device__ __forceinline__ void med_desc_pass(const MedArgs &a, uint16_t *sd, long long lm, long long lo, int n, int nmax,
+__device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, long long lm, long long lo, int n, int nmax,
                                               bool valid) {
     const int lane = threadIdx.x & 31, sl = lane & (G - 1);
     Desc q{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    if (sl < n) q = load_desc(a.desc, lo + sl);
+    const bool want_dir = a.med_dir && a.dirs;
+    if (sl < n) {
+        q = load_desc(a.desc, lo + sl);
+        if (want_dir) { // the owner lane fetches its observation's direction now, next to the descriptor (one HBM round trip)
+            const double *dp = a.dirs + 3 * (lo + sl);
+            sdir[3 * lane] = __ldg(dp);
+            sdir[3 * lane + 1] = __ldg(dp + 1);
+            sdir[3 * lane + 2] = __ldg(dp + 2);
+        }
+    }
     int best = n > 0 ? 0 : -1;
     if (nmax >= 2) {
         // distances of row `sl` to every row j of its own landmark (L1-resident re-read of row j; the 4-POPC
-        // carry-save form keeps the POPC pipe, 16 lanes/clk/SM, from binding)
-        for (int j = 0; j < nmax; ++j) {
-            if (j < n) {
-                const Desc t = load_desc(a.desc, lo + j);
-                sd[j * 32 + lane] = static_cast<uint16_t>(hamming256_csa4(q, t.lo, t.hi));
+        // carry-save form keeps the POPC pipe, 16 lanes/clk/SM, from binding); 0xFFFF pads the row to G entries
+        int d[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            d[j] = 0xFFFF;
+            if (j < nmax) { // warp-uniform
+                if (j < n) {
+                    const Desc t = load_desc(a.desc, lo + j);
+                    d[j] = hamming256_csa4(q, t.lo, t.hi);
+                }
             }
         }
-        // smallest v with #{j : d_j <= v} >= rank + 1  ==  the element at sorted position `rank`
-        const int need = med_rank(n) + 1;
-        int v_lo = 0, v_hi = 256;
-#pragma unroll 1
-        for (int step = 0; step < 9; ++step) { // 2^9 > 257 values: the interval is a single value after 9 halvings
-            const int mid = (v_lo + v_hi) >> 1;
-            int c = 0;
-            for (int j = 0; j < nmax; ++j) c += (j < n && sd[j * 32 + lane] <= mid);
-            if (v_lo < v_hi) {
-                if (c >= need) v_hi = mid;
-                else v_lo = mid + 1;
+        // bitonic sorting network over the register row (ascending; the pads sink to the end)
+#pragma unroll
+        for (int k = 2; k <= G; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const int x = d[i], y = d[l];
+                        const bool up = (i & k) == 0;
+                        d[i] = up ? min(x, y) : max(x, y);
+                        d[l] = up ? max(x, y) : min(x, y);
+                    }
+                }
             }
         }
-        uint32_t key = (sl < n && n >= 2) ? (static_cast<uint32_t>(v_lo) << 5) | sl : KEY32_ABSENT;
+        // the element at sorted position int(1 + 0.5*(n-1)) (mapFeatures.cpp:79)
+        const int rank = med_rank(n);
+        int med = d[0];
+#pragma unroll
+        for (int j = 1; j < G; ++j) med = (j == rank) ? d[j] : med;
+        uint32_t key = (sl < n && n >= 2) ? (static_cast<uint32_t>(med) << 5) | sl : KEY32_ABSENT;
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
         if (n >= 2) best = static_cast<int>(key & 31u);
     }
-    if (!valid) return;
-    if (sl == 0) a.med_idx[lm] = best;
-    if (a.med_desc) {
-        const long long row = a.dst_rows ? __ldg(a.dst_rows + lm) : lm;
-        if (row >= 0 && sl == (best < 0 ? 0 : best)) { // the winner writes its own registers (zeros for an empty list)
-            a.med_desc[2 * row] = q.lo;
-            a.med_desc[2 * row + 1] = q.hi;
+    if (valid) {
+        if (sl == 0) a.med_idx[lm] = best;
+        if (a.med_desc) {
+            const long long row = a.dst_rows ? __ldg(a.dst_rows + lm) : lm;
+            if (row >= 0 && sl == (best < 0 ? 0 : best)) { // the winner writes its own registers (zeros for an empty list)
+                a.med_desc[2 * row] = q.lo;
+                a.med_desc[2 * row + 1] = q.hi;
+            }
         }
     }
-    if (a.med_dir && a.dirs && sl < 3) a.med_dir[3 * lm + sl] = med_dir_component(a.dirs, lo, n, sl);
+    if (want_dir) {
+        __syncwarp();
+        if (valid && sl < 3) { // mean direction (mapFeatures.cpp:88-91): sequential sum in list order from zero, / n
+            const double *g = sdir + 3 * (lane - sl) + sl; // component sl of the group's observation 0
+            double r = 0.0;
+            if (n == 1) {
+                r = g[0]; // a single observation keeps its direction (constructor, :38)
+            } else if (n >= 2) {
+                double acc = 0.0;
+                for (int j = 0; j < n; ++j) acc = __dadd_rn(acc, g[3 * j]);
+                r = __ddiv_rn(acc, static_cast<double>(n));
+            }
+            a.med_dir[3 * lm + sl] = r;
+        }
+        __syncwarp();
+    }
 }
 
 // A warp takes 4 consecutive landmarks and packs them by the longest list among them: 4 x 8 lanes, 2 x 16 lanes
 // (two passes) or 1 x 32 lanes (four passes).
 __global__ void __launch_bounds__(32 * MED_WARPS) med_desc_warp_kernel(MedArgs a) {
-    __shared__ uint16_t sd_all[MED_WARPS][32 * 32];
+    __shared__ double sdir_all[MED_WARPS][32 * 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint16_t *sd = sd_all[warp];
+    double *sdir = sdir_all[warp];
     const long long n_blocks = (static_cast<long long>(a.n_lm) + 3) / 4;
-    for (long long blk = static_cast<long long>(blockIdx.x) * MED_WARPS + warp; blk < n_blocks;
-         blk += static_cast<long long>(gridDim.x) * MED_WARPS) {
-        // lanes 0..3 read the block's landmarks
+    const long long stride = static_cast<long long>(gridDim.x) * MED_WARPS;
+    // lanes read the offsets of the block's 4 landmarks; the next block's are fetched one iteration ahead
+    auto fetch = [&](long long blk, long long &lo, long long &n) {
         const long long my_lm = blk * 4 + (lane & 3);
-        long long my_lo = 0, my_n = 0;
-        if (my_lm < a.n_lm) {
-            my_lo = __ldg(a.obs_start + my_lm);
-            my_n = static_cast<long long>(__ldg(a.obs_start + my_lm + 1)) - my_lo;
+        lo = 0;
+        n = -2; // past the end
+        if (blk < n_blocks && my_lm < a.n_lm) {
+            lo = __ldg(a.obs_start + my_lm);
+            n = static_cast<long long>(__ldg(a.obs_start + my_lm + 1)) - lo;
+        }
+    };
+    long long blk = static_cast<long long>(blockIdx.x) * MED_WARPS + warp;
+    long long nx_lo, nx_n;
+    fetch(blk, nx_lo, nx_n);
+    for (; blk < n_blocks; blk += stride) {
+        long long my_lo = nx_lo, my_n = nx_n;
+        fetch(blk + stride, nx_lo, nx_n);
+        if (my_n > -2) {
             if (my_lo < 0 || my_n < 0 || my_lo + my_n > a.n_obs) my_n = 0; // malformed range: treated as empty
             if (my_n > 32) {
-                if (lane < 4) a.work[1 + atomicAdd(a.work, 1)] = static_cast<int32_t>(my_lm);
+                if (lane < 4) a.work[1 + atomicAdd(a.work, 1)] = static_cast<int32_t>(blk * 4 + lane);
                 my_n = -1; // handled by med_desc_cta_kernel
             }
-        } else {
-            my_n = -2; // past the end
         }
         int nmax = static_cast<int>(my_n);
         nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, 1));
@@ -148,36 +196,43 @@ __global__ void __launch_bounds__(32 * MED_WARPS) med_desc_warp_kernel(MedArgs a
             const int g = lane >> 3;
             const int n = static_cast<int>(__shfl_sync(0xFFFFFFFFu, my_n, g));
             const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, g);
-            med_desc_pass<8>(a, sd, blk * 4 + g, lo, max(n, 0), nmax, n >= 0);
+            med_desc_pass<8>(a, sdir, blk * 4 + g, lo, max(n, 0), nmax, n >= 0);
         } else if (nmax <= 16) {
             for (int pass = 0; pass < 2; ++pass) {
                 const int g = 2 * pass + (lane >> 4);
                 const int n = static_cast<int>(__shfl_sync(0xFFFFFFFFu, my_n, g));
                 const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, g);
-                int pmax = max(n, __shfl_xor_sync(0xFFFFFFFFu, n, 16));
-                med_desc_pass<16>(a, sd, blk * 4 + g, lo, max(n, 0), pmax, n >= 0);
-                __syncwarp();
+                const int pmax = max(n, __shfl_xor_sync(0xFFFFFFFFu, n, 16));
+                med_desc_pass<16>(a, sdir, blk * 4 + g, lo, max(n, 0), pmax, n >= 0);
             }
         } else {
             for (int pass = 0; pass < 4; ++pass) {
                 const int n = static_cast<int>(__shfl_sync(0xFFFFFFFFu, my_n, pass));
                 const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, pass);
-                if (n >= 0) med_desc_pass<32>(a, sd, blk * 4 + pass, lo, n, n, true);
-                __syncwarp();
+                if (n >= 0) med_desc_pass<32>(a, sdir, blk * 4 + pass, lo, n, n, true);
             }
         }
-        __syncwarp();
     }
 }
 
+constexpr int MED_CTA_CACHE_N = 128; // lists up to this length keep their distance matrix in shared memory
+
 __global__ void __launch_bounds__(MED_CTA_THREADS) med_desc_cta_kernel(MedArgs a) {
     __shared__ unsigned long long s_best;
+    __shared__ uint16_t s_dist[MED_CTA_CACHE_N * MED_CTA_CACHE_N];
     const int n_work = a.work[0];
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const long long lm = a.work[1 + w];
         const long long lo = __ldg(a.obs_start + lm);
         const int n = static_cast<int>(static_cast<long long>(__ldg(a.obs_start + lm + 1)) - lo);
         if (threadIdx.x == 0) s_best = KEY64_ABSENT;
+        const bool cached = n <= MED_CTA_CACHE_N;
+        if (cached) { // every pair once, all threads (row-major n x n)
+            for (int idx = threadIdx.x; idx < n * n; idx += MED_CTA_THREADS) {
+                const int i = idx / n, j = idx - i * n;
+                s_dist[idx] = static_cast<uint16_t>(hamming256(load_desc(a.desc, lo + i), load_desc(a.desc, lo + j)));
+            }
+        }
         __syncthreads();
         const int need = med_rank(n) + 1;
         for (int i = threadIdx.x; i < n; i += MED_CTA_THREADS) {
@@ -186,7 +241,11 @@ __global__ void __launch_bounds__(MED_CTA_THREADS) med_desc_cta_kernel(MedArgs a
             while (v_lo < v_hi) {
                 const int mid = (v_lo + v_hi) >> 1;
                 int c = 0;
-                for (int j = 0; j < n; ++j) c += (hamming256(q, load_desc(a.desc, lo + j)) <= mid);
+                if (cached) {
+                    for (int j = 0; j < n; ++j) c += (s_dist[i * n + j] <= mid);
+                } else {
+                    for (int j = 0; j < n; ++j) c += (hamming256(q, load_desc(a.desc, lo + j)) <= mid);
+                }
                 if (c >= need) v_hi = mid;
                 else v_lo = mid + 1;
             }
