@@ -33,7 +33,7 @@ def build(verbose: bool = False) -> None:
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "stvo-pl", "src")):
         targets.append("ref")
         if os.path.exists(os.path.join(_HERE, "..", "pl_inertial_slam_b200", "lib", "libplmatch.so")):
-            targets.append("stvo_gpu")  # the C++ drop-in over the CUDA library, same harness
+            targets += ["stvo_gpu", "map_gpu"]  # the C++ drop-ins over the CUDA library, same harnesses
     out = subprocess.run(["make", "-C", _HERE] + targets, capture_output=True, text=True)
     if verbose or out.returncode != 0:
         print(out.stdout, out.stderr)
@@ -475,8 +475,42 @@ class _Ref:
         return v
 
 
+class _MapDropIn:
+    """The product's C++ drop-in for src/mapFeatures.cpp (pl_inertial_slam_b200/csrc/map_features_gpu.cpp) behind the
+    harness of oracle/shim/ref_map_capi.cpp -- the thing under test in tests/test_cxx_dropin.py, not a checker."""
+
+    def __init__(self, libname="libmapfeatures_gpu.so"):
+        self._libname, self._lib = libname, None
+
+    def available(self) -> bool:
+        return os.path.exists(os.path.join(_REF_DIR, self._libname))
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            L = C.CDLL(os.path.join(_REF_DIR, self._libname))
+            for f in ("plref_med_desc", "plref_med_desc_batch"):
+                getattr(L, f).restype = None
+                getattr(L, f).argtypes = [C.c_int, _u8p, C.c_size_t, _f64p, _i32p, C.c_int, _i32p, _f64p]
+            self._lib = L
+        return self._lib
+
+    def med_desc(self, desc, dirs, obs_start, is_line=False, batch=False):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        obs_start, osp = _i32(obs_start)
+        n_lm = len(obs_start) - 1
+        dirs_c = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+        med_idx = np.empty(n_lm, np.int32)
+        med_dir = np.zeros((n_lm, 3), np.float64)
+        fn = self.lib.plref_med_desc_batch if batch else self.lib.plref_med_desc
+        fn(int(bool(is_line)), desc.ctypes.data_as(_u8p), 32, dirs_c.ctypes.data_as(_f64p), osp, n_lm,
+           med_idx.ctypes.data_as(_i32p), med_dir.ctypes.data_as(_f64p))
+        return med_idx, med_dir
+
+
 port = _Port()
 ref = _Ref()
+map_gpu = _MapDropIn()
 stvo_gpu = _Ref("libstvo_gpu.so")  # the thing under test in tests/test_cxx_dropin.py, not a checker
 
 

@@ -63,3 +63,23 @@ def test_stvo_match_grid(plm_lib, is_lines):
                     n_g, m_g = gpu.match_grid_points(case["coords"], case["d1"], case["cell_start"], case["cell_items"],
                                                      case["rows"], case["cols"], case["d2"], case["win"], ratio, blr)
                 assert n_g == n_o and (m_g == m_o).all()
+
+
+needs_map_lib = pytest.mark.skipif(not oracle.map_gpu.available(),
+                                   reason="oracle/_ref/libmapfeatures_gpu.so not built (needs the reference headers)")
+
+
+@needs_map_lib
+@pytest.mark.parametrize("is_line", [False, True])
+def test_map_features_dropin(plm_lib, is_line):
+    """PLSLAM::MapPoint / MapLine from pl_inertial_slam_b200/csrc/map_features_gpu.cpp, built against the
+    reference's include/mapFeatures.h: observation-by-observation use (one plm_med_desc per append, as the
+    reference recomputes) and the batch entry point, against the restatement."""
+    for seed, kw in [(1, dict(n_lm=40, mean_obs=5)), (2, dict(n_lm=25, mean_obs=9, tie=True, empty_frac=0.1)),
+                     (3, dict(n_lm=6, mean_obs=3, long_lists=2, long_len=40))]:
+        desc, dirs, start = synth.make_landmark_observations(synth.SEED0 + 500 + seed, **kw)
+        i_p, _, d_p = port.med_desc(desc, dirs, start)
+        for batch in (False, True):
+            i_g, d_g = oracle.map_gpu.med_desc(desc, dirs, start, is_line=is_line, batch=batch)
+            assert np.array_equal(i_g, i_p), (seed, batch)
+            assert np.array_equal(d_g.view(np.uint64), d_p.view(np.uint64)), (seed, batch)
