@@ -33,7 +33,7 @@ def build(verbose: bool = False) -> None:
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "stvo-pl", "src")):
         targets.append("ref")
         if os.path.exists(os.path.join(_HERE, "..", "pl_inertial_slam_b200", "lib", "libplmatch.so")):
-            targets += ["stvo_gpu", "map_gpu"]  # the C++ drop-ins over the CUDA library, same harnesses
+            targets += ["stvo_gpu", "map_gpu", "dbow_gpu"]  # the C++ drop-ins over the CUDA library, same harnesses
     out = subprocess.run(["make", "-C", _HERE] + targets, capture_output=True, text=True)
     if verbose or out.returncode != 0:
         print(out.stdout, out.stderr)
@@ -552,12 +552,17 @@ class FlatVocabulary:
 
 class _RefDbow:
     """The reference's vendored DBoW2 (3rdparty/DBoW2, compiled unmodified -> _ref/libplref_dbow.so):
-    Vocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB> (include/mapHandler.h:70)."""
+    Vocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB> (include/mapHandler.h:70).  With
+    libname="libdbow_gpu.so": the same harness over the product's drop-in vocabulary type PLM::GpuVocabulary
+    (pl_inertial_slam_b200/csrc/dbow_vocabulary_gpu.h) -- the thing under test, not a checker."""
 
-    def __init__(self):
+    def __init__(self, libname="libplref_dbow.so"):
         self._lib = None
+        self._libname = libname
 
     def available(self) -> bool:
+        if self._libname != "libplref_dbow.so":
+            return os.path.exists(os.path.join(_REF_DIR, self._libname))
         try:
             return self.lib is not None
         except (FileNotFoundError, OSError, RuntimeError):
@@ -566,7 +571,10 @@ class _RefDbow:
     @property
     def lib(self):
         if self._lib is None:
-            L = _load("libplref_dbow.so")
+            if self._libname == "libplref_dbow.so":
+                L = _load(self._libname)
+            else:
+                L = C.CDLL(os.path.join(_REF_DIR, self._libname))
             L.plref_voc_create.restype = C.c_void_p
             L.plref_voc_create.argtypes = [_u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
             L.plref_voc_from_flat.restype = C.c_void_p
@@ -580,6 +588,9 @@ class _RefDbow:
             L.plref_voc_transform.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_size_t, _u32p, _f64p]
             L.plref_voc_score.restype = C.c_double
             L.plref_voc_score.argtypes = [C.c_void_p, _u32p, _f64p, C.c_int, _u32p, _f64p, C.c_int]
+            if hasattr(L, "plref_voc_score_all"):
+                L.plref_voc_score_all.restype = None
+                L.plref_voc_score_all.argtypes = [C.c_void_p, _u32p, _f64p, C.c_int, _u32p, _f64p, _i32p, C.c_int, _f64p]
             self._lib = L
         return self._lib
 
@@ -620,4 +631,17 @@ class _RefDbow:
                                         i2.ctypes.data_as(_u32p), x2.ctypes.data_as(_f64p), len(i2))
 
 
+    def score_all(self, h, q, db):
+        """GpuVocabulary::scoreAll (drop-in library only)."""
+        qi, qv = np.ascontiguousarray(q[0], np.uint32), np.ascontiguousarray(q[1], np.float64)
+        lens = np.array([len(v[0]) for v in db], np.int32)
+        di = np.ascontiguousarray(np.concatenate([np.asarray(v[0], np.uint32) for v in db]) if len(db) else np.zeros(1, np.uint32))
+        dv = np.ascontiguousarray(np.concatenate([np.asarray(v[1], np.float64) for v in db]) if len(db) else np.zeros(1))
+        out = np.zeros(len(db), np.float64)
+        self.lib.plref_voc_score_all(h, qi.ctypes.data_as(_u32p), qv.ctypes.data_as(_f64p), len(qi), di.ctypes.data_as(_u32p),
+                                     dv.ctypes.data_as(_f64p), lens.ctypes.data_as(_i32p), len(db), out.ctypes.data_as(_f64p))
+        return out
+
+
 ref_dbow = _RefDbow()
+dbow_gpu = _RefDbow("libdbow_gpu.so")  # the thing under test in tests/test_cxx_dropin.py

@@ -14,9 +14,18 @@
 
 #define PLREF_API extern "C" __attribute__((visibility("default")))
 
+#ifdef PLREF_DBOW_GPU
+// the same harness over the product's drop-in vocabulary type (pl_inertial_slam_b200/csrc/dbow_vocabulary_gpu.h)
+#include "dbow_vocabulary_gpu.h"
+#endif
+
 namespace {
 
+#ifdef PLREF_DBOW_GPU
+typedef PLM::GpuVocabulary Vocabulary;
+#else
 typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> Vocabulary; // mapHandler.h:70
+#endif
 
 class Voc : public Vocabulary {
 public:
@@ -64,7 +73,13 @@ public:
         m_words.resize(n_words, nullptr);
         for (int i = 0; i < n; i++)
             if (word[i] >= 0) m_words[word[i]] = &m_nodes[i];
+#ifdef PLREF_DBOW_GPU
+        sync();
+#endif
     }
+#ifdef PLREF_DBOW_GPU
+    using Vocabulary::scoreAll;
+#endif
 };
 
 std::vector<cv::Mat> rows_of(const uint8_t *desc, int n, size_t step) {
@@ -123,6 +138,24 @@ PLREF_API int plref_voc_transform(void *h, const uint8_t *desc, int n, size_t st
     }
     return i;
 }
+
+#ifdef PLREF_DBOW_GPU
+// GpuVocabulary::scoreAll: query (ids1, vals1) against n_db vectors laid out back to back in (ids2, vals2), lengths len2
+PLREF_API void plref_voc_score_all(void *h, const uint32_t *ids1, const double *vals1, int n1, const uint32_t *ids2,
+                                   const double *vals2, const int32_t *len2, int n_db, double *out) {
+    std::vector<DBoW2::BowVector> db(n_db);
+    std::vector<const DBoW2::BowVector *> ptrs(n_db);
+    size_t pos = 0;
+    for (int j = 0; j < n_db; j++) {
+        db[j] = bow_of(ids2 + pos, vals2 + pos, len2[j]);
+        ptrs[j] = &db[j];
+        pos += len2[j];
+    }
+    std::vector<double> res;
+    static_cast<Voc *>(h)->scoreAll(bow_of(ids1, vals1, n1), ptrs, res);
+    for (int j = 0; j < n_db; j++) out[j] = res[j];
+}
+#endif
 
 // Vocabulary::score(v1, v2) (src/mapHandler.cpp:3133,3158,3218-3219)
 PLREF_API double plref_voc_score(void *h, const uint32_t *ids1, const double *vals1, int n1, const uint32_t *ids2,

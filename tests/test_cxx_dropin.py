@@ -83,3 +83,33 @@ def test_map_features_dropin(plm_lib, is_line):
             i_g, d_g = oracle.map_gpu.med_desc(desc, dirs, start, is_line=is_line, batch=batch)
             assert np.array_equal(i_g, i_p), (seed, batch)
             assert np.array_equal(d_g.view(np.uint64), d_p.view(np.uint64)), (seed, batch)
+
+
+needs_dbow_lib = pytest.mark.skipif(not oracle.dbow_gpu.available(),
+                                    reason="oracle/_ref/libdbow_gpu.so not built (needs the reference's DBoW2 headers)")
+
+
+@needs_dbow_lib
+@pytest.mark.parametrize("w", [0, 1, 2, 3])
+def test_dbow_vocabulary_dropin(plm_lib, w):
+    """PLM::GpuVocabulary (csrc/dbow_vocabulary_gpu.h), a subclass of the reference's own DBoW2 vocabulary type:
+    transform() / score() / scoreAll() through DBoW2's BowVector interface against the restatement."""
+    gpu = oracle.dbow_gpu
+    fv = synth.make_vocabulary(synth.SEED0 + 600 + w, k=7, L=3, weighting=w)
+    h = gpu.from_flat(fv)
+    try:
+        sets = [synth.vocabulary_features(700 + i, fv, n) for i, n in enumerate((250, 120, 1, 0, 400))]
+        bows = []
+        for d in sets:
+            ids, vals = gpu.transform(h, d)
+            wi, wv = port.bow_transform(fv, d)
+            assert np.array_equal(ids, wi) and np.array_equal(vals.view(np.uint64), wv.view(np.uint64))
+            bows.append((ids, vals))
+        for a in bows[:3]:
+            for b in bows:
+                assert np.float64(gpu.score(h, a, b)).view(np.uint64) == np.float64(port.bow_score(a, b)).view(np.uint64)
+        got = gpu.score_all(h, bows[0], bows)
+        want = np.array([port.bow_score(bows[0], b) for b in bows])
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    finally:
+        gpu.destroy(h)
