@@ -415,9 +415,11 @@ int plm_dev_bow_transform(plm_voc *voc, const void *desc_dev, int64_t n_rows, co
 int plm_bow_score(plm_ctx *ctx, const uint32_t *q_ids, const double *q_vals, const int64_t *q_start,
                   const int32_t *q_len, int n_q, const uint32_t *db_ids, const double *db_vals,
                   const int64_t *db_start, const int32_t *db_len, int n_db, double *scores);
-/* Same on device pointers, no host sync; max_q_len >= the longest query. */
+/* Same on device pointers, no host sync; max_q_len >= the longest query; n_words = number of words of the
+ * vocabulary (plm_voc_words; sizes the shared-memory membership bitmap of the query -- 0 = unknown: every database
+ * entry is then looked up by binary search, same results). */
 int plm_dev_bow_score(plm_ctx *ctx, const uint32_t *q_ids_dev, const double *q_vals_dev, const int64_t *q_start_dev,
-                      const int32_t *q_len_dev, int n_q, int max_q_len, const uint32_t *db_ids_dev,
+                      const int32_t *q_len_dev, int n_q, int max_q_len, int64_t n_words, const uint32_t *db_ids_dev,
                       const double *db_vals_dev, const int64_t *db_start_dev, const int32_t *db_len_dev, int n_db,
                       double *scores_dev);
 

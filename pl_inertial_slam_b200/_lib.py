@@ -148,7 +148,7 @@ SIGNATURES = {
     "plm_bow_transform": (C.c_int, [vp, u8p, C.c_int64, C.c_size_t, i32p, C.c_int, vp, f64p, i32p]),
     "plm_dev_bow_transform": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_int, vp, vp, vp]),
     "plm_bow_score": (C.c_int, [vp, vp, f64p, vp, i32p, C.c_int, vp, f64p, vp, i32p, C.c_int, f64p]),
-    "plm_dev_bow_score": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp]),
+    "plm_dev_bow_score": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int, vp]),
     "plm_med_desc": (C.c_int, [vp, u8p, C.c_int64, C.c_size_t, f64p, i32p, C.c_int, i32p, u8p, f64p]),
     "plm_dev_med_desc": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp, vp, vp, vp]),
     "plm_set_option": (C.c_int, [C.c_char_p, C.c_int]),

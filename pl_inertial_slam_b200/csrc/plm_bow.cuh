@@ -14,8 +14,9 @@
 //   * a score is one sequential sum over the common words in ascending word id.
 // The parallel parts are the tree descent (one thread per feature; the node table stays L2-resident), the
 // per-set sort of (word, leaf) keys in shared memory, the per-word folds, and -- for scoring -- one warp per
-// database vector: 32 coalesced entries at a time are looked up in the query (binary search in shared
-// memory), the hit lanes' terms are then added in lane order, which is word order.
+// database vector: 128 coalesced entries at a time are tested against a shared-memory bitmap of the query's word
+// ids, the rare candidates find the query value through a shared-memory hash table, and the hit lanes' terms are
+// then added in lane order, which is word order.
 #pragma once
 #include "plm_common.cuh"
 
@@ -166,54 +167,84 @@ struct BowScoreArgs {
     const long long *db_start;
     const int32_t *db_len;
     int n_db;
-    int q_cap;       // >= the longest query (shared-memory staging)
-    double *scores;  // n_q x n_db: scores[q * n_db + j] = score(query q, db j)
+    int q_cap;        // >= the longest query (shared-memory staging)
+    int table_slots;  // power of two >= 2 * q_cap: open-addressing hash table word id -> position in the query
+    int bitmap_words; // 32-bit words of the query-membership bitmap in shared memory (0: none, hash table only)
+    double *scores;   // n_q x n_db: scores[q * n_db + j] = score(query q, db j)
 };
 
-inline size_t bow_score_smem(int q_cap) { return size_t(q_cap) * 12 + 16; }
+inline size_t bow_score_smem(int q_cap, int table_slots, int bitmap_words) {
+    return size_t(q_cap) * 8 + size_t(table_slots) * 8 + size_t(bitmap_words) * 4 + 16;
+}
 
-// grid = (CTAs over the database, queries); a warp per database vector.
-__global__ void __launch_bounds__(BOW_THREADS) bow_score_kernel(BowScoreArgs a) {
+__device__ __forceinline__ uint32_t bow_hash(uint32_t id, int slots) { return (id * 2654435761u) & static_cast<uint32_t>(slots - 1); }
+
+// grid = (CTAs over the database, queries); a warp per database vector, 128 coalesced entries in flight.  Two
+// keyframes share only a handful of the vocabulary's 10^5 - 10^6 words, so membership of a database entry in the
+// query is first tested against a BITMAP of the query's word ids in shared memory (one LDS); the rare candidates
+// find the query value through a shared-memory hash table (1-2 probes) and only then load the database value.
+// The kernel is then a coalesced stream over the database ids.  The hit lanes' terms are accumulated in lane
+// order = ascending word id = the reference's summation order.
+__global__ void __launch_bounds__(1024) bow_score_kernel(BowScoreArgs a) {
     extern __shared__ __align__(16) unsigned char bow_smem[];
     double *qv = reinterpret_cast<double *>(bow_smem);
-    uint32_t *qi = reinterpret_cast<uint32_t *>(bow_smem + size_t(a.q_cap) * 8);
+    uint2 *table = reinterpret_cast<uint2 *>(bow_smem + size_t(a.q_cap) * 8);
+    uint32_t *bitmap = reinterpret_cast<uint32_t *>(table + a.table_slots);
     const int q = blockIdx.y;
     const long long qs = __ldg(a.q_start + q);
     const int qn = min(__ldg(a.q_len + q), a.q_cap);
-    for (int i = threadIdx.x; i < qn; i += BOW_THREADS) {
-        qi[i] = __ldg(a.q_ids + qs + i);
+    for (int i = threadIdx.x; i < a.bitmap_words; i += blockDim.x) bitmap[i] = 0u;
+    for (int i = threadIdx.x; i < a.table_slots; i += blockDim.x) table[i] = make_uint2(0xFFFFFFFFu, 0u);
+    __syncthreads();
+    const uint32_t bitmap_bits = static_cast<uint32_t>(a.bitmap_words) * 32u;
+    for (int i = threadIdx.x; i < qn; i += blockDim.x) {
+        const uint32_t id = __ldg(a.q_ids + qs + i);
         qv[i] = __ldg(a.q_vals + qs + i);
+        if (id < bitmap_bits) atomicOr(bitmap + (id >> 5), 1u << (id & 31u));
+        uint32_t h = bow_hash(id, a.table_slots); // ids of a BowVector are distinct: every insert claims an empty slot
+        while (atomicCAS(&table[h].x, 0xFFFFFFFFu, id) != 0xFFFFFFFFu) h = (h + 1) & static_cast<uint32_t>(a.table_slots - 1);
+        table[h].y = static_cast<uint32_t>(i);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int warps = BOW_THREADS / 32;
+    const int warps = blockDim.x >> 5;
     for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < a.n_db; j += gridDim.x * warps) {
         const long long ds = __ldg(a.db_start + j);
         const int dn = __ldg(a.db_len + j);
         double score = 0.0;
-        for (int base = 0; base < dn; base += 32) {
-            const int e = base + lane;
-            double term = 0.0;
-            bool hit = false;
-            if (e < dn) {
-                const uint32_t id = __ldg(a.db_ids + ds + e);
-                int lo = 0, hi = qn; // lower_bound in the query ids
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (qi[mid] < id) lo = mid + 1;
-                    else hi = mid;
-                }
-                if (lo < qn && qi[lo] == id) {
-                    const double vi = qv[lo], wi = __ldg(a.db_vals + ds + e);
-                    term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
-                    hit = true;
-                }
+        for (int base = 0; base < dn; base += 128) {
+            uint32_t id[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int e = base + 32 * c + lane;
+                id[c] = e < dn ? __ldg(a.db_ids + ds + e) : 0xFFFFFFFFu; // no word has this id
             }
-            unsigned mask = __ballot_sync(0xFFFFFFFFu, hit);
-            while (mask) { // common words in ascending id: the reference's summation order
-                const int src = __ffs(mask) - 1;
-                score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, term, src));
-                mask &= mask - 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int e = base + 32 * c + lane;
+                bool maybe = id[c] != 0xFFFFFFFFu;
+                if (maybe && id[c] < bitmap_bits) maybe = (bitmap[id[c] >> 5] >> (id[c] & 31u)) & 1u;
+                double term = 0.0;
+                bool hit = false;
+                if (maybe) {
+                    uint32_t h = bow_hash(id[c], a.table_slots);
+                    uint2 t = table[h];
+                    while (t.x != id[c] && t.x != 0xFFFFFFFFu) {
+                        h = (h + 1) & static_cast<uint32_t>(a.table_slots - 1);
+                        t = table[h];
+                    }
+                    if (t.x == id[c]) {
+                        const double vi = qv[t.y], wi = __ldg(a.db_vals + ds + e);
+                        term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+                        hit = true;
+                    }
+                }
+                unsigned mask = __ballot_sync(0xFFFFFFFFu, hit);
+                while (mask) { // common words in ascending id: the reference's summation order
+                    const int src = __ffs(mask) - 1;
+                    score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, term, src));
+                    mask &= mask - 1;
+                }
             }
         }
         if (lane == 0) a.scores[static_cast<size_t>(q) * a.n_db + j] = __ddiv_rn(-score, 2.0);

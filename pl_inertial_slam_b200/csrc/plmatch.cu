@@ -1284,14 +1284,24 @@ int launch_bow_transform(plm_voc *voc, plm::BowTransformArgs a, int max_set) {
     return PLM_OK;
 }
 
-int launch_bow_score(plm_ctx *ctx, plm::BowScoreArgs a, int max_q_len) {
+int launch_bow_score(plm_ctx *ctx, plm::BowScoreArgs a, int max_q_len, int64_t n_words) {
     a.q_cap = std::max(max_q_len, 1);
-    const size_t smem = plm::bow_score_smem(a.q_cap);
-    CU_TRY(cudaFuncSetAttribute(plm::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(plm::bow_score_smem(BOW_MAX_SET))));
-    const int warps = plm::BOW_THREADS / 32;
-    const int ctas = std::max(1, std::min((a.n_db + warps - 1) / warps, ctx->sm_count * 8));
-    plm::bow_score_kernel<<<dim3(ctas, a.n_q), plm::BOW_THREADS, smem, ctx->stream>>>(a);
+    a.table_slots = pow2_at_least(2 * a.q_cap);
+    // membership bitmap over word ids [0, n_words): as large as fits next to the staged query and its hash table;
+    // word ids beyond it (or n_words unknown) go to the hash table directly
+    const size_t budget = ctx->smem_optin > 2048 ? ctx->smem_optin - 2048 : 0;
+    const size_t fixed = plm::bow_score_smem(a.q_cap, a.table_slots, 0);
+    size_t words = n_words > 0 ? static_cast<size_t>((n_words + 31) / 32) : 0;
+    if (fixed + words * 4 > budget) words = budget > fixed ? (budget - fixed) / 4 : 0;
+    a.bitmap_words = static_cast<int>(words);
+    const size_t smem = plm::bow_score_smem(a.q_cap, a.table_slots, a.bitmap_words);
+    if (smem > budget) return fail(PLM_E_UNSUPPORTED, "query vector too long for shared memory");
+    CU_TRY(cudaFuncSetAttribute(plm::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
+    // a large bitmap leaves room for few CTAs per SM: make them wide so that enough warps stream the database
+    const int threads = smem > 64 * 1024 ? 1024 : (smem > 24 * 1024 ? 512 : plm::BOW_THREADS);
+    const int warps = threads / 32;
+    const int ctas = std::max(1, std::min((a.n_db + warps - 1) / warps, ctx->sm_count * (threads == 1024 ? 2 : 8)));
+    plm::bow_score_kernel<<<dim3(ctas, a.n_q), threads, smem, ctx->stream>>>(a);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;
@@ -1439,7 +1449,7 @@ PLM_API int plm_bow_transform(plm_voc *voc, const uint8_t *desc, int64_t n_rows,
 }
 
 PLM_API int plm_dev_bow_score(plm_ctx *ctx, const uint32_t *q_ids_dev, const double *q_vals_dev, const int64_t *q_start_dev,
-                              const int32_t *q_len_dev, int n_q, int max_q_len, const uint32_t *db_ids_dev,
+                              const int32_t *q_len_dev, int n_q, int max_q_len, int64_t n_words, const uint32_t *db_ids_dev,
                               const double *db_vals_dev, const int64_t *db_start_dev, const int32_t *db_len_dev, int n_db,
                               double *scores_dev) {
     if (n_q < 0 || n_db < 0 || max_q_len < 0) return fail(PLM_E_INVALID, "negative size");
@@ -1461,7 +1471,7 @@ PLM_API int plm_dev_bow_score(plm_ctx *ctx, const uint32_t *q_ids_dev, const dou
     a.db_len = db_len_dev;
     a.n_db = n_db;
     a.scores = scores_dev;
-    return launch_bow_score(ctx, a, max_q_len);
+    return launch_bow_score(ctx, a, max_q_len, n_words);
 }
 
 namespace {
@@ -1512,8 +1522,12 @@ PLM_API int plm_bow_score(plm_ctx *ctx, const uint32_t *q_ids, const double *q_v
     std::memcpy(H + o_ql, q_len, size_t(n_q) * 4);
     std::memcpy(H + o_dl, db_len, size_t(n_db) * 4);
     CU_TRY(cudaMemcpyAsync(D, H, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // word ids reach up to the largest query id: the bitmap covers [0, that]
+    int64_t q_words = 0;
+    for (int i = 0; i < n_q; ++i)
+        if (q_len[i] > 0) q_words = std::max<int64_t>(q_words, int64_t(q_ids[q_start[i] + q_len[i] - 1]) + 1);
     if ((st = plm_dev_bow_score(ctx, reinterpret_cast<const uint32_t *>(D + o_qi), reinterpret_cast<const double *>(D + o_qv),
-                                reinterpret_cast<const int64_t *>(D + o_qs), reinterpret_cast<const int32_t *>(D + o_ql), n_q, q_max,
+                                reinterpret_cast<const int64_t *>(D + o_qs), reinterpret_cast<const int32_t *>(D + o_ql), n_q, q_max, q_words,
                                 reinterpret_cast<const uint32_t *>(D + o_di), reinterpret_cast<const double *>(D + o_dv),
                                 reinterpret_cast<const int64_t *>(D + o_ds), reinterpret_cast<const int32_t *>(D + o_dl), n_db,
                                 reinterpret_cast<double *>(D + o_out))) != PLM_OK)
