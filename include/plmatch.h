@@ -350,6 +350,18 @@ int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, int world,
                           const uint64_t *local_top2_dev, int n1, uint64_t *top2_out_dev, float nnr,
                           int32_t *m12_dev_inout, int32_t *count_dev, int32_t *error_dev);
 
+/* Element-wise reductions over the ranks through the same exchange buffers (the two exchanges of the row-sharded
+ * matchGrid, see plm_dev_grid_colmin / plm_dev_grid_match above).  src_dev / out_dev hold n_chunks 16-byte chunks
+ * (n_chunks <= q_cap; pad the arrays to a multiple of 16 bytes with the identity of the reduction):
+ *   PLM_PEER_MIN_U64         out = min over ALL ranks, 2 x uint64 per chunk (pad UINT64_MAX)
+ *   PLM_PEER_PREFIX_MIN_U16  out = min over the ranks BELOW this one, 8 x uint16 per chunk; 0xFFFF where there is
+ *                            none (pad 0xFFFF)
+ * Same epoch / error conventions as plm_dev_top2_exchange (one epoch counter per set of buffers). */
+#define PLM_PEER_MIN_U64 0
+#define PLM_PEER_PREFIX_MIN_U16 1
+int plm_dev_peer_reduce(plm_ctx *ctx, void *const *peers, int rank, int world, int q_cap, uint32_t epoch, int op,
+                        const void *src_dev, int n_chunks, void *out_dev, int32_t *error_dev);
+
 /* A device-resident descriptor database shard (keyframe DB / local map). */
 int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out);
 int plm_db_destroy(plm_db *db);

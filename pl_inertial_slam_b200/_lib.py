@@ -136,6 +136,7 @@ SIGNATURES = {
     "plm_peer_free": (C.c_int, [vp, vp]),
     "plm_dev_top2_exchange": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, vp, C.c_int, vp,
                                         C.c_float, vp, vp, vp]),
+    "plm_dev_peer_reduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_int, vp, vp]),
     "plm_db_create": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
     "plm_db_destroy": (C.c_int, [vp]),
     "plm_db_upload": (C.c_int, [vp, vp, C.c_int64, C.c_size_t, C.c_int64]),

@@ -56,14 +56,14 @@ __device__ __forceinline__ ulonglong2 ld_volatile_u64x2(const ulonglong2 *p) {
     return v;
 }
 
-__global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerExchangeArgs a) {
-    const int q = blockIdx.x * PEER_THREADS + threadIdx.x;
+// push + signal + wait of one CTA: element q of this rank (16 bytes) goes to slot [parity][my rank][q] of every
+// rank's buffer; returns false when a peer did not arrive in time.  After a true return the G slots
+// [parity][r][q] of the OWN buffer hold every rank's element (read them with ld_volatile_u64x2).
+__device__ __forceinline__ bool peer_push_wait(const PeerExchangeArgs &a, int q, bool active, ulonglong2 v) {
     const int par = a.epoch & 1;
-    const size_t key_slot = (size_t(par) * a.world + a.rank) * a.q_cap;       // [par][my rank][.]
+    const size_t key_slot = (size_t(par) * a.world + a.rank) * a.q_cap; // [par][my rank][.]
     const size_t keys_bytes = peer_keys_bytes(a.world, a.q_cap);
-    // push
-    if (q < a.n1) {
-        const ulonglong2 v = a.local[q];
+    if (active) {
         for (int p = 0; p < a.world; ++p) {
             const int dst = (a.rank + p) % a.world; // start with the local copy, spread the remote stores
             reinterpret_cast<ulonglong2 *>(a.peer[dst])[key_slot + q] = v;
@@ -71,17 +71,15 @@ __global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerE
     }
     __threadfence_system();
     __syncthreads();
-    // signal
-    if (threadIdx.x < a.world) {
+    if (threadIdx.x < a.world) { // signal
         const int dst = (a.rank + threadIdx.x) % a.world;
         uint32_t *flags = reinterpret_cast<uint32_t *>(a.peer[dst] + keys_bytes);
         st_release_sys(flags + (size_t(par) * a.world + a.rank) * a.blocks_cap + blockIdx.x, a.epoch);
     }
-    // wait for block `blockIdx.x` of every rank
     __shared__ int s_fail;
     if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
-    if (threadIdx.x < a.world) {
+    if (threadIdx.x < a.world) { // wait for block `blockIdx.x` of every rank
         const uint32_t *flags = reinterpret_cast<const uint32_t *>(a.peer[a.rank] + keys_bytes);
         const uint32_t *f = flags + (size_t(par) * a.world + threadIdx.x) * a.blocks_cap + blockIdx.x;
         const long long t0 = clock64();
@@ -96,12 +94,22 @@ __global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerE
     __syncthreads();
     if (s_fail) {
         if (threadIdx.x == 0) atomicExch(a.error, 1);
-        return;
+        return false;
     }
     __threadfence_system();
-    // merge
-    if (q >= a.n1) return;
-    const ulonglong2 *keys = reinterpret_cast<const ulonglong2 *>(a.peer[a.rank]) + size_t(par) * a.world * a.q_cap;
+    return true;
+}
+
+__device__ __forceinline__ const ulonglong2 *peer_slots(const PeerExchangeArgs &a) {
+    return reinterpret_cast<const ulonglong2 *>(a.peer[a.rank]) + size_t(a.epoch & 1) * a.world * a.q_cap;
+}
+
+__global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerExchangeArgs a) {
+    const int q = blockIdx.x * PEER_THREADS + threadIdx.x;
+    const bool active = q < a.n1;
+    if (!peer_push_wait(a, q, active, active ? a.local[q] : make_ulonglong2(0, 0))) return;
+    if (!active) return;
+    const ulonglong2 *keys = peer_slots(a);
     unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
     for (int r = 0; r < a.world; ++r) {
         const ulonglong2 v = ld_volatile_u64x2(keys + size_t(r) * a.q_cap + q);
@@ -116,6 +124,47 @@ __global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerE
             a.m12[q] = static_cast<int32_t>(b0 & 0xFFFFFFFFull);
             if (a.count) atomicAdd(a.count, 1);
         }
+    }
+}
+
+// Element-wise reductions over the ranks with the same push / signal / wait: the two exchanges of the row-sharded
+// matchGrid (database.py ShardedMap.match_grid).  The payload travels in 16-byte chunks (a.local /
+// a.out are arrays of n1 chunks):
+//   OP 0  min over ALL ranks of 2 x uint64 per chunk  -- the per-column best pairs (distance << 32 | global row)
+//   OP 1  min over the LOWER ranks (r < rank) of 8 x uint16 per chunk, 0xFFFF where there is none -- the running
+//         column minima that seed a shard's thresholds
+template <int OP> __global__ void __launch_bounds__(PEER_THREADS) peer_reduce_kernel(PeerExchangeArgs a) {
+    const int q = blockIdx.x * PEER_THREADS + threadIdx.x;
+    const bool active = q < a.n1;
+    if (!peer_push_wait(a, q, active, active ? a.local[q] : make_ulonglong2(0, 0))) return;
+    if (!active) return;
+    const ulonglong2 *slots = peer_slots(a);
+    if (OP == 0) {
+        unsigned long long m0 = KEY64_ABSENT, m1 = KEY64_ABSENT;
+        for (int r = 0; r < a.world; ++r) {
+            const ulonglong2 v = ld_volatile_u64x2(slots + size_t(r) * a.q_cap + q);
+            m0 = min(m0, v.x);
+            m1 = min(m1, v.y);
+        }
+        a.out[q] = make_ulonglong2(m0, m1);
+    } else {
+        unsigned long long m0 = KEY64_ABSENT, m1 = KEY64_ABSENT; // 8 x 0xFFFF
+        for (int r = 0; r < a.rank; ++r) {
+            const ulonglong2 v = ld_volatile_u64x2(slots + size_t(r) * a.q_cap + q);
+            // lane-wise unsigned 16-bit minimum of two 64-bit words (4 lanes each)
+            auto min16x4 = [](unsigned long long x, unsigned long long y) {
+                unsigned long long out = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned long long xa = (x >> (16 * k)) & 0xFFFFull, ya = (y >> (16 * k)) & 0xFFFFull;
+                    out |= (xa < ya ? xa : ya) << (16 * k);
+                }
+                return out;
+            };
+            m0 = min16x4(m0, v.x);
+            m1 = min16x4(m1, v.y);
+        }
+        a.out[q] = make_ulonglong2(m0, m1);
     }
 }
 

@@ -1248,6 +1248,38 @@ PLM_API int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, in
     return PLM_OK;
 }
 
+PLM_API int plm_dev_peer_reduce(plm_ctx *ctx, void *const *peers, int rank, int world, int q_cap, uint32_t epoch, int op,
+                                const void *src_dev, int n_chunks, void *out_dev, int32_t *error_dev) {
+    if (world <= 0 || world > PLM_PEER_MAX_RANKS || rank < 0 || rank >= world) return fail(PLM_E_INVALID, "bad rank / world");
+    if (n_chunks < 0 || n_chunks > q_cap || epoch == 0) return fail(PLM_E_INVALID, "n_chunks outside [0, q_cap] or epoch == 0");
+    if (op != PLM_PEER_MIN_U64 && op != PLM_PEER_PREFIX_MIN_U16) return fail(PLM_E_INVALID, "unknown reduction");
+    if (!peers || !error_dev || (n_chunks > 0 && (!src_dev || !out_dev))) return fail(PLM_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(src_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15) return fail(PLM_E_INVALID, "16-byte alignment required");
+    for (int r = 0; r < world; ++r)
+        if (!peers[r]) return fail(PLM_E_INVALID, "null peer buffer");
+    if (n_chunks == 0) return PLM_OK;
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::PeerExchangeArgs a{};
+    for (int r = 0; r < world; ++r) a.peer[r] = static_cast<unsigned char *>(peers[r]);
+    a.rank = rank;
+    a.world = world;
+    a.q_cap = q_cap;
+    a.blocks_cap = peer_blocks_cap(q_cap);
+    a.epoch = epoch;
+    a.local = static_cast<const ulonglong2 *>(src_dev);
+    a.n1 = n_chunks;
+    a.out = static_cast<ulonglong2 *>(out_dev);
+    a.error = error_dev;
+    a.spin_limit = 4000000000ll;
+    const int grid = (n_chunks + plm::PEER_THREADS - 1) / plm::PEER_THREADS;
+    if (op == PLM_PEER_MIN_U64) plm::peer_reduce_kernel<0><<<grid, plm::PEER_THREADS, 0, ctx->stream>>>(a);
+    else plm::peer_reduce_kernel<1><<<grid, plm::PEER_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Bag-of-words: DBoW2 vocabulary transform + L1 score (src/mapHandler.cpp:3116-3237)
 struct plm_voc {

@@ -232,6 +232,32 @@ class PeerExchange:
                                                _ptr(count), _ptr(self.error)), "plm_dev_top2_exchange")
         return out
 
+    def _reduce(self, op: int, src: torch.Tensor, n_chunks: int) -> torch.Tensor:
+        out = torch.empty_like(src)
+        self.epoch += 1
+        self.ops._bind_stream()
+        L.check(self.lib.plm_dev_peer_reduce(self.ops.ctx.handle, self.ptrs, self.rank, self.world, self.q_cap, self.epoch,
+                                             op, _ptr(src), n_chunks, _ptr(out), _ptr(self.error)), "plm_dev_peer_reduce")
+        return out
+
+    def min_u64(self, keys: torch.Tensor) -> torch.Tensor:
+        """Element-wise unsigned minimum over ALL ranks of an int64-bits-of-uint64 vector (the per-column best pairs)."""
+        n = int(keys.shape[0])
+        pad = torch.full((n + (n & 1),), -1, dtype=torch.int64, device=keys.device)  # -1 == UINT64_MAX
+        pad[:n] = keys
+        return self._reduce(0, pad, pad.shape[0] // 2)[:n]
+
+    def prefix_min_u16(self, vals: torch.Tensor) -> torch.Tensor:
+        """Element-wise unsigned minimum over the ranks BELOW this one of an int16-bits-of-uint16 vector (0xFFFF where
+        there is none): the running column minima that seed this shard's matchGrid thresholds."""
+        n = int(vals.shape[0])
+        pad = torch.full(((n + 7) // 8 * 8,), -1, dtype=torch.int16, device=vals.device)  # -1 == 0xFFFF
+        pad[:n] = vals
+        return self._reduce(1, pad, pad.shape[0] // 8)[:n]
+
+    def fits(self, n_bytes: int) -> bool:
+        return (n_bytes + 15) // 16 <= self.q_cap
+
     def check(self) -> None:
         """Host sync: raises if any exchange since the last check timed out waiting for a peer."""
         if int(self.error.item()) != 0:
@@ -371,16 +397,22 @@ class ShardedMap:
         m12 = self._local_m12(m12_inout, dev)
         count = torch.zeros(1, dtype=torch.int32, device=dev)
         seed = None
+        use_peer = self.peer is not None and n2 > 0 and self.peer.fits(8 * n2)
         if best_lr and self.world > 1:
             # running column minima left behind by the rows of lower-ranked shards
             cm = self.ops.grid_colmin(self.coords, self.d1, self.lo, frame, win, ratio, line_sim_th, best_lr)
-            # uint16 bits travel as int32 (neither NCCL nor gloo carries 16-bit integers)
-            allcm = self.g.all_gather(cm.to(torch.int32) & 0xFFFF)          # [world, n2], 0xFFFF = none
-            if self.rank > 0:
-                seed = allcm[: self.rank].min(dim=0).values.to(torch.int16).contiguous()
+            if use_peer:
+                seed = self.peer.prefix_min_u16(cm).contiguous()            # one kernel over NVLink peer memory
+            else:
+                # uint16 bits travel as int32 (neither NCCL nor gloo carries 16-bit integers)
+                allcm = self.g.all_gather(cm.to(torch.int32) & 0xFFFF)      # [world, n2], 0xFFFF = none
+                if self.rank > 0:
+                    seed = allcm[: self.rank].min(dim=0).values.to(torch.int16).contiguous()
         key = self.ops.grid_match(self.coords, self.d1, self.lo, frame, win, ratio, line_sim_th, best_lr, m12, count, seed)
         if best_lr:
-            if self.world > 1:
+            if self.world > 1 and use_peer:
+                key = self.peer.min_u64(key).contiguous()                   # unsigned min over the shards, one kernel
+            elif self.world > 1:
                 # unsigned min over shards of (distance << 32 | global row): flip the sign bit so that
                 # signed min orders like unsigned
                 allk = self.g.all_gather(key) ^ INT64_MIN

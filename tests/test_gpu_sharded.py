@@ -161,5 +161,34 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
         for r in range(world):
             assert (outs[r].cpu().numpy().view(np.uint64) == want).all(), (n1, r)
             assert int(cnts[r].item()) == n_o and (m12s[r].cpu().numpy() == m_o).all(), (n1, r)
+    # element-wise reductions through the same buffers (the two exchanges of the row-sharded matchGrid)
+    for n in (1, 7, 600, 1333):
+        u16 = rng.integers(0, 300, (world, n)).astype(np.uint16)
+        u16[rng.random((world, n)) < 0.3] = 0xFFFF
+        u64 = rng.integers(0, 1 << 62, (world, n), dtype=np.uint64)
+        u64[rng.random((world, n)) < 0.2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        for op, host, pad_to, fill in ((1, u16, 8, 0xFFFF), (0, u64, 2, 0xFFFFFFFFFFFFFFFF)):
+            npad = (n + pad_to - 1) // pad_to * pad_to
+            padded = np.full((world, npad), fill, host.dtype)
+            padded[:, :n] = host
+            src = [torch.from_numpy(padded[r].view(np.int16 if op == 1 else np.int64).copy()).cuda() for r in range(world)]
+            outs = [torch.empty_like(x) for x in src]
+            epoch += 1
+            torch.cuda.synchronize()
+            for r, o in enumerate(ranks):
+                with torch.cuda.stream(streams[r]):
+                    o._bind_stream()
+                    L.check(plm_lib.plm_dev_peer_reduce(o.ctx.handle, bufs, r, world, q_cap, epoch, op, C.c_void_p(src[r].data_ptr()),
+                                                        npad // pad_to, C.c_void_p(outs[r].data_ptr()),
+                                                        C.c_void_p(err[r:].data_ptr())), "plm_dev_peer_reduce")
+            torch.cuda.synchronize()
+            assert not err.any().item(), "a rank timed out"
+            for r in range(world):
+                got = outs[r].cpu().numpy().view(host.dtype)[:n]
+                if op == 0:
+                    want = host.min(axis=0)
+                else:
+                    want = host[:r].min(axis=0) if r > 0 else np.full(n, 0xFFFF, np.uint16)
+                assert np.array_equal(got, want), (op, n, r)
     for r, o in enumerate(ranks):
         plm_lib.plm_peer_free(o.ctx.handle, bufs[r])
