@@ -170,3 +170,36 @@ def test_gpu_insert_kf_bow_vectors():
         assert np.array_equal(bits(conf.conf_matrix), bits(want)), mode
         if mode == "P":
             assert conf.conf_matrix[5, 1] > 0.99      # the revisit scores like the keyframe itself
+
+
+@pytest.mark.gpu
+def test_gpu_bow_limits_and_large_sets():
+    """The largest supported set (8192 features: widest shared-memory sort, hash table of 16384 slots), one feature
+    more (rejected), a vocabulary whose bitmap does not fit next to a long query (hash table only) and the
+    no-common-word / identical-vector scores."""
+    from pl_inertial_slam_b200 import _lib as L
+    from pl_inertial_slam_b200 import bow as B
+    fv = synth.make_vocabulary(synth.SEED0 + 80, k=10, L=4, ragged=0.0, stop_frac=0.0)
+    voc = B.Vocabulary.from_flat(fv)
+    big = synth.vocabulary_features(synth.SEED0 + 81, fv, 8192, flip_p=0.04)
+    small = synth.vocabulary_features(synth.SEED0 + 82, fv, 50, flip_p=0.04)
+    bows = voc.transform_batch(np.concatenate([big, small]), [0, 8192, 8242])
+    want = [port.bow_transform(fv, big), port.bow_transform(fv, small)]
+    for (i, v), (wi, wv) in zip(bows, want):
+        assert np.array_equal(i, wi) and np.array_equal(bits(v), bits(wv))
+    got = B.score_matrix(bows, bows)
+    ref = np.array([[port.bow_score(a, b) for b in want] for a in want])
+    assert np.array_equal(bits(got), bits(ref))
+    with pytest.raises(L.PlmError) as e:
+        voc.transform(np.concatenate([big, small[:1]]))
+    assert e.value.status == L.PLM_E_UNSUPPORTED
+    # word ids far beyond any bitmap: synthetic vectors with ids up to 2^31 - 2
+    rng = np.random.default_rng(3)
+    ids_a = np.unique(rng.integers(0, 2**31 - 1, 3000)).astype(np.uint32)
+    ids_b = np.unique(np.concatenate([ids_a[::7], rng.integers(0, 2**31 - 1, 2000).astype(np.uint32)]))
+    va, vb = rng.random(len(ids_a)), rng.random(len(ids_b))
+    va /= va.sum(); vb /= vb.sum()
+    a, b, empty = (ids_a, va), (ids_b, vb), (np.zeros(0, np.uint32), np.zeros(0))
+    got = B.score_matrix([a, b, empty], [a, b, empty])
+    ref = np.array([[port.bow_score(x, y) for y in (a, b, empty)] for x in (a, b, empty)])
+    assert np.array_equal(bits(got), bits(ref))

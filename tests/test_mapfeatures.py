@@ -180,3 +180,28 @@ def test_gpu_map_landmark_classes():
         for lm in (p, q):
             assert np.array_equal(lm.med_desc, med_p[l])
             assert np.array_equal(np.asarray(lm.med_obs_dir).view(np.uint64), d_p[l].view(np.uint64))
+
+
+@pytest.mark.gpu
+def test_gpu_med_desc_group_boundaries():
+    """Lists of exactly 1, 2, 8, 9, 16, 17, 32 and 33 observations next to each other: every packing mode of the warp
+    kernel (4 x 8, 2 x 16, 1 x 32 lanes), the hand-over to the CTA kernel at 33, its shared-memory cache limit at
+    128 / 129, and identical descriptors (all medians equal -> first row)."""
+    from pl_inertial_slam_b200 import mapfeatures as MF
+    rng = np.random.default_rng(12)
+    counts = np.array([1, 2, 8, 9, 16, 17, 32, 33, 8, 8, 8, 8, 16, 16, 3, 32, 128, 129, 5, 0, 7], np.int64)
+    counts = np.concatenate([counts, rng.integers(0, 34, 200)])
+    start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    n_obs = int(start[-1])
+    owner = np.repeat(np.arange(len(counts)), counts)
+    desc = synth.flip_bits(rng, synth.rand_desc(rng, len(counts))[owner], 0.05)
+    same = np.nonzero(counts >= 3)[0][::5]
+    for l in same:                                   # all observations identical
+        desc[start[l]:start[l + 1]] = desc[start[l]]
+    dirs = rng.normal(size=(n_obs, 3))
+    i_p, med_p, d_p = port.med_desc(desc, dirs, start)
+    i_g, med_g, d_g = MF.med_desc_batch(desc, start, dirs)
+    assert np.array_equal(i_g, i_p)
+    assert np.array_equal(med_g, med_p)
+    assert np.array_equal(d_g.view(np.uint64), d_p.view(np.uint64))
+    assert (i_p[same] == 0).all()
