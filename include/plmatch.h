@@ -362,6 +362,35 @@ int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, int world,
 int plm_dev_peer_reduce(plm_ctx *ctx, void *const *peers, int rank, int world, int q_cap, uint32_t epoch, int op,
                         const void *src_dev, int n_chunks, void *out_dev, int32_t *error_dev);
 
+/* All-gather of the per-shard match vectors and sum of the per-shard counts (the last step of the row-sharded match /
+ * matchGrid) as one kernel over a second set of peer-mapped buffers: plm_peer_gather_bytes(world, n_rows_cap) bytes
+ * each, from plm_peer_alloc_bytes (zero-initialised; handles exchanged and opened like the exchange buffers).  Rank r
+ * contributes rows [row_lo, row_lo + n_local) of the n_rows-long vector and one count; every rank receives the whole
+ * vector in out_dev and the sum of the counts in out_count_dev (may be NULL).  Own epoch counter per set of gather
+ * buffers, same conventions as plm_dev_top2_exchange. */
+size_t plm_peer_gather_bytes(int world, int64_t n_rows_cap);
+int plm_peer_alloc_bytes(plm_ctx *ctx, size_t bytes, void **buf_dev, uint8_t handle[PLM_PEER_HANDLE_BYTES]);
+int plm_dev_peer_allgather_i32(plm_ctx *ctx, void *const *peers, int rank, int world, int64_t n_rows_cap, uint32_t epoch,
+                               const int32_t *local_dev, int64_t row_lo, int64_t n_local, int64_t n_rows,
+                               const int32_t *local_count_dev, int32_t *out_dev, int32_t *out_count_dev,
+                               int32_t *error_dev);
+
+/* The whole row-sharded matchGrid of one rank in ONE call (config 4 across GPUs): one minima pass, the prefix-min of the
+ * column minima over the lower ranks, the match pass, the min of the per-column best pairs, the mutual check and the
+ * all-gather of the match vectors + counts -- ten launches back to back, three of them exchanges over peer memory.
+ * `a` describes this rank's shard exactly as for plm_dev_grid_colmin / plm_dev_grid_match (m12_inout = the shard's slice
+ * of the in/out vector, count = a zeroed int32).  The call consumes exchange epochs xchg_epoch and xchg_epoch + 1 and
+ * gather epoch gather_epoch.  Every rank receives the global vector (n_rows_total) and the global count. */
+typedef struct plm_peer_group {
+    void *const *xchg;   /* world exchange buffers (plm_peer_alloc), as mapped in this process */
+    void *const *gather; /* world gather buffers (plm_peer_alloc_bytes(plm_peer_gather_bytes(..))) */
+    int32_t rank, world, q_cap, pad_;
+    int64_t n_rows_cap;
+    uint32_t xchg_epoch, gather_epoch;
+} plm_peer_group;
+int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a, const plm_peer_group *g, int64_t n_rows_total,
+                               int32_t *m12_global_dev, int32_t *count_global_dev, int32_t *error_dev);
+
 /* A device-resident descriptor database shard (keyframe DB / local map). */
 int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out);
 int plm_db_destroy(plm_db *db);

@@ -43,6 +43,12 @@ class DevGridArgs(C.Structure):
                 ("grid_cols", C.c_int32), ("is_lines", C.c_int32), ("best_lr", C.c_int32), ("win", C.c_int32 * 4)]
 
 
+class PeerGroup(C.Structure):
+    _fields_ = [("xchg", C.POINTER(vp)), ("gather", C.POINTER(vp)), ("rank", C.c_int32), ("world", C.c_int32),
+                ("q_cap", C.c_int32), ("pad_", C.c_int32), ("n_rows_cap", C.c_int64), ("xchg_epoch", C.c_uint32),
+                ("gather_epoch", C.c_uint32)]
+
+
 class FrameRec(C.Structure):
     _fields_ = [("desc_pl", C.c_int64), ("desc_pr", C.c_int64), ("desc_ll", C.c_int64), ("desc_lr", C.c_int64),
                 ("kp_l", C.c_int64), ("kp_r", C.c_int64), ("ln_l", C.c_int64), ("ln_r", C.c_int64),
@@ -136,6 +142,11 @@ SIGNATURES = {
     "plm_peer_free": (C.c_int, [vp, vp]),
     "plm_dev_top2_exchange": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, vp, C.c_int, vp,
                                         C.c_float, vp, vp, vp]),
+    "plm_peer_gather_bytes": (C.c_size_t, [C.c_int, C.c_int64]),
+    "plm_peer_alloc_bytes": (C.c_int, [vp, C.c_size_t, C.POINTER(vp), u8p]),
+    "plm_dev_peer_allgather_i32": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int64, C.c_uint32, vp, C.c_int64,
+                                             C.c_int64, C.c_int64, vp, vp, vp, vp]),
+    "plm_dev_sharded_match_grid": (C.c_int, [vp, C.POINTER(DevGridArgs), C.POINTER(PeerGroup), C.c_int64, vp, vp, vp]),
     "plm_dev_peer_reduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_int, vp, vp]),
     "plm_db_create": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
     "plm_db_destroy": (C.c_int, [vp]),

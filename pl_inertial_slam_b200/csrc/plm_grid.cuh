@@ -772,6 +772,15 @@ __global__ void grid_scan_kernel(uint16_t *__restrict__ cta_min, int n_cta, int 
     if (col_min && lane == 0) col_min[i2] = static_cast<uint16_t>(run);
 }
 
+// cta_min[c][i2] <- min(cta_min[c][i2], seed[i2]): the thresholds of a shard that were scanned without the minima of
+// the lower-ranked shards receive them afterwards (sharded matchGrid with ONE minima pass).
+__global__ void grid_seed_kernel(uint16_t *__restrict__ cta_min, int n_cta, int n2, const uint16_t *__restrict__ seed) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(n_cta) * n2) return;
+    const uint16_t s = seed[i % n2];
+    if (s < cta_min[i]) cta_min[i] = s;
+}
+
 // m21[i2] = row of the best live pair (or -1), from the 64-bit keys of the chunked launch.
 __global__ void m21_from_keys_kernel(const unsigned long long *__restrict__ m21key, int n2,
                                      int32_t *__restrict__ m21) {

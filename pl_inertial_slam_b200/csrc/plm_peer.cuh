@@ -168,4 +168,96 @@ template <int OP> __global__ void __launch_bounds__(PEER_THREADS) peer_reduce_ke
     }
 }
 
+// All-gather of the per-shard match vectors + sum of the per-shard counts (the last step of the row-sharded
+// match / matchGrid: every rank ends with the global matches_12 vector and the global count) as one kernel.
+// Every rank owns a second peer-mapped buffer:
+//   [parity 2][n_rows_cap] int32 rows | [parity 2][G] int32 counts | [parity 2][G] uint32 flags | [2] uint32 done
+// push   grid-stride: this rank's rows go to [parity][row_lo + i] of every rank's buffer, its count to slot
+//        [parity][my rank];
+// signal the LAST block of the grid to finish pushing (device-scope counter) raises flag [parity][my rank] = epoch on
+//        every rank;
+// wait   every block waits for the G flags of the own buffer (bounded spin) -- they depend only on the other ranks'
+//        own pushes, never on this grid, so there is no circular wait;
+// copy   grid-stride copy of the assembled vector into the caller's output, block 0 sums the G counts.
+struct PeerGatherArgs {
+    unsigned char *peer[PEER_MAX_RANKS];
+    int rank, world;
+    long long n_rows_cap;
+    uint32_t epoch;
+    const int32_t *local;       // n_local rows of this rank
+    long long row_lo, n_local, n_rows;
+    const int32_t *local_count; // 1 (may be null: 0)
+    int32_t *out;               // n_rows
+    int32_t *out_count;         // 1 (may be null)
+    int32_t *error;
+    long long spin_limit;
+};
+
+__host__ __device__ inline size_t peer_gather_bytes(int world, long long n_rows_cap) {
+    return size_t(2) * size_t(n_rows_cap) * 4 + size_t(2) * world * 4 + size_t(2) * world * 4 + 16;
+}
+
+__global__ void __launch_bounds__(256) peer_allgather_kernel(PeerGatherArgs a) {
+    const int par = a.epoch & 1;
+    const size_t rows_bytes = size_t(2) * size_t(a.n_rows_cap) * 4;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    // push
+    for (int p = 0; p < a.world; ++p) {
+        const int dst = (a.rank + p) % a.world;
+        int32_t *rows = reinterpret_cast<int32_t *>(a.peer[dst]) + size_t(par) * a.n_rows_cap + a.row_lo;
+        for (long long i = tid; i < a.n_local; i += nthreads) rows[i] = a.local[i];
+        if (tid == 0) {
+            int32_t *counts = reinterpret_cast<int32_t *>(a.peer[dst] + rows_bytes);
+            counts[par * a.world + a.rank] = a.local_count ? *a.local_count : 0;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // signal: the last block of this grid to get here
+    uint32_t *own_flags = reinterpret_cast<uint32_t *>(a.peer[a.rank] + rows_bytes + size_t(2) * a.world * 4);
+    uint32_t *done = own_flags + 2 * a.world + par;
+    __shared__ int s_last, s_fail;
+    if (threadIdx.x == 0) {
+        s_fail = 0;
+        s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x == 0) *done = 0; // ready for the next use of this parity
+        if (threadIdx.x < a.world) {
+            const int dst = (a.rank + threadIdx.x) % a.world;
+            uint32_t *flags = reinterpret_cast<uint32_t *>(a.peer[dst] + rows_bytes + size_t(2) * a.world * 4);
+            st_release_sys(flags + par * a.world + a.rank, a.epoch);
+        }
+    }
+    // wait
+    if (threadIdx.x < a.world) {
+        const uint32_t *f = own_flags + par * a.world + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != a.epoch) {
+            if (clock64() - t0 > a.spin_limit) {
+                s_fail = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (threadIdx.x == 0) atomicExch(a.error, 1);
+        return;
+    }
+    __threadfence_system();
+    // copy out
+    const volatile int32_t *rows = reinterpret_cast<const volatile int32_t *>(a.peer[a.rank]) + size_t(par) * a.n_rows_cap;
+    for (long long i = tid; i < a.n_rows; i += nthreads) a.out[i] = rows[i];
+    if (tid == 0 && a.out_count) {
+        const volatile int32_t *counts = reinterpret_cast<const volatile int32_t *>(a.peer[a.rank] + rows_bytes);
+        int32_t sum = 0;
+        for (int r = 0; r < a.world; ++r) sum += counts[par * a.world + r];
+        *a.out_count = sum;
+    }
+}
+
 } // namespace plm

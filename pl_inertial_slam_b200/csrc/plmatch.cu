@@ -941,7 +941,7 @@ PLM_API int plm_match_grid_lines(plm_ctx *ctx, const int32_t *xyxy, const uint8_
 namespace {
 
 int dev_grid_setup(plm_ctx *&ctx, const plm_dev_grid_args *a, plm::GridJob &job, plm::GridParams &gp, int &warps, int &n_cta,
-                   size_t &smem) {
+                   size_t &smem, size_t extra_bytes = 0, char **extra = nullptr) {
     if (!a) return fail(PLM_E_INVALID, "null args");
     if (a->n1 < 0 || a->n2 < 0) return fail(PLM_E_INVALID, "negative size");
     if (a->grid_rows <= 0 || a->grid_cols <= 0) return fail(PLM_E_GRID, "[GridStructure] invalid dimension");
@@ -991,9 +991,11 @@ int dev_grid_setup(plm_ctx *&ctx, const plm_dev_grid_args *a, plm::GridJob &job,
             ctx->chunked_attr[pass] = ctx->smem_optin - 2048;
         }
     }
-    st = ctx->ensure_device(align_up(size_t(std::max(n_cta, 1)) * std::max(a->n2, 1) * 2));
+    const size_t cta_min_bytes = align_up(size_t(std::max(n_cta, 1)) * std::max(a->n2, 1) * 2);
+    st = ctx->ensure_device(cta_min_bytes + extra_bytes);
     if (st != PLM_OK) return st;
     gp.cta_min = reinterpret_cast<uint16_t *>(ctx->d_buf);
+    if (extra) *extra = ctx->d_buf + cta_min_bytes;
     return PLM_OK;
 }
 
@@ -1044,6 +1046,75 @@ PLM_API int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const u
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;
+}
+
+// The whole row-sharded matchGrid of one rank, launched back to back from C: minima pass, the two peer-memory
+// reductions around the match pass, mutual check and the peer-memory all-gather of the match vectors.
+PLM_API int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a, const plm_peer_group *g, int64_t n_rows_total,
+                                       int32_t *m12_global_dev, int32_t *count_global_dev, int32_t *error_dev) {
+    if (!g || !g->xchg || !g->gather || !m12_global_dev || !count_global_dev || !error_dev) return fail(PLM_E_INVALID, "null pointer");
+    if (g->world < 2 || g->world > PLM_PEER_MAX_RANKS || g->rank < 0 || g->rank >= g->world) return fail(PLM_E_INVALID, "bad rank / world");
+    plm::GridJob job;
+    plm::GridParams gp;
+    int warps = 0, n_cta = 0;
+    size_t smem = 0;
+    const int n2 = a ? std::max(a->n2, 0) : 0;
+    const size_t n2p8 = (size_t(n2) + 7) / 8 * 8, n2p2 = (size_t(n2) + 1) / 2 * 2;
+    Layout L;
+    const size_t o_colmin = L.add(n2p8 * 2), o_seed = L.add(n2p8 * 2), o_key = L.add(n2p2 * 8), o_keyg = L.add(n2p2 * 8),
+                 o_m21 = L.add(size_t(std::max(n2, 1)) * 4);
+    char *X = nullptr;
+    int st = dev_grid_setup(ctx, a, job, gp, warps, n_cta, smem, L.total, &X);
+    if (st != PLM_OK) return st;
+    if (n_rows_total > g->n_rows_cap || a->i1_base < 0 || a->i1_base + a->n1 > n_rows_total) return fail(PLM_E_INVALID, "rows outside the gather buffers");
+    if (n2 > 0 && (n2p8 / 8 > size_t(g->q_cap) || n2p2 / 2 > size_t(g->q_cap))) return fail(PLM_E_UNSUPPORTED, "frame too large for the exchange buffers");
+    uint16_t *col_min = reinterpret_cast<uint16_t *>(X + o_colmin), *seed = reinterpret_cast<uint16_t *>(X + o_seed);
+    uint64_t *key = reinterpret_cast<uint64_t *>(X + o_key), *key_g = reinterpret_cast<uint64_t *>(X + o_keyg);
+    int32_t *m21 = reinterpret_cast<int32_t *>(X + o_m21);
+    uint32_t epoch = g->xchg_epoch;
+    if (gp.best_lr && n2 > 0) {
+        CU_TRY(cudaMemsetAsync(X, 0xFF, L.total, ctx->stream)); // identities of both reductions, absent keys, m21 = -1
+        if (n_cta > 0) {
+            plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+            plm::grid_scan_kernel<<<(n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, n2, nullptr, col_min);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+        // running column minima of the lower-ranked shards
+        if ((st = plm_dev_peer_reduce(ctx, g->xchg, g->rank, g->world, g->q_cap, epoch++, PLM_PEER_PREFIX_MIN_U16, col_min,
+                                      static_cast<int>(n2p8 / 8), seed, error_dev)) != PLM_OK)
+            return st;
+        if (n_cta > 0) {
+            const long long cells = static_cast<long long>(n_cta) * n2;
+            plm::grid_seed_kernel<<<static_cast<int>((cells + 255) / 256), 256, 0, ctx->stream>>>(gp.cta_min, n_cta, n2, seed);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+    }
+    gp.m21key = reinterpret_cast<unsigned long long *>(key);
+    if (n_cta > 0 && n2 > 0) {
+        plm::grid_match_chunked_kernel<1><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    if (gp.best_lr && n2 > 0) {
+        // per-column best pairs over all shards, then the mutual check on this shard's rows
+        if ((st = plm_dev_peer_reduce(ctx, g->xchg, g->rank, g->world, g->q_cap, epoch++, PLM_PEER_MIN_U64, key,
+                                      static_cast<int>(n2p2 / 2), key_g, error_dev)) != PLM_OK)
+            return st;
+        plm::m21_from_keys_kernel<<<(n2 + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(key_g), n2, m21);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        if (a->n1 > 0) {
+            plm::cross_check_kernel<<<(a->n1 + 127) / 128, 128, 0, ctx->stream>>>(a->m12_inout, a->n1, a->i1_base, m21, n2, a->count);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+    }
+    return plm_dev_peer_allgather_i32(ctx, g->gather, g->rank, g->world, g->n_rows_cap, g->gather_epoch, a->m12_inout, a->i1_base,
+                                      a->n1, n_rows_total, a->count, m12_global_dev, count_global_dev, error_dev);
 }
 
 PLM_API int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int n2, int32_t *m21_dev) {
@@ -1164,14 +1235,23 @@ PLM_API size_t plm_peer_buffer_bytes(int world, int q_cap) {
     return plm::peer_buffer_bytes(world, q_cap, peer_blocks_cap(q_cap));
 }
 
+PLM_API size_t plm_peer_gather_bytes(int world, int64_t n_rows_cap) {
+    if (world <= 0 || n_rows_cap <= 0) return 0;
+    return plm::peer_gather_bytes(world, n_rows_cap);
+}
+
 PLM_API int plm_peer_alloc(plm_ctx *ctx, int world, int q_cap, void **buf_dev, uint8_t handle[PLM_PEER_HANDLE_BYTES]) {
+    if (world <= 0 || world > PLM_PEER_MAX_RANKS || q_cap <= 0) return fail(PLM_E_INVALID, "world in 1..16 and q_cap > 0 required");
+    return plm_peer_alloc_bytes(ctx, plm_peer_buffer_bytes(world, q_cap), buf_dev, handle);
+}
+
+PLM_API int plm_peer_alloc_bytes(plm_ctx *ctx, size_t bytes, void **buf_dev, uint8_t handle[PLM_PEER_HANDLE_BYTES]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == PLM_PEER_HANDLE_BYTES, "IPC handle size");
     if (!buf_dev || !handle) return fail(PLM_E_INVALID, "null pointer");
     *buf_dev = nullptr;
-    if (world <= 0 || world > PLM_PEER_MAX_RANKS || q_cap <= 0) return fail(PLM_E_INVALID, "world in 1..16 and q_cap > 0 required");
+    if (bytes == 0) return fail(PLM_E_INVALID, "empty buffer");
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
-    const size_t bytes = plm_peer_buffer_bytes(world, q_cap);
     void *p = nullptr;
     CU_TRY(cudaMalloc(&p, bytes));
     cudaError_t e = cudaMemsetAsync(p, 0, bytes, ctx->stream); // flags start at epoch 0 = "nothing arrived"
@@ -1243,6 +1323,43 @@ PLM_API int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, in
     a.error = error_dev;
     a.spin_limit = 4000000000ll; // ~2 s of SM clock
     plm::top2_exchange_merge_kernel<<<(n1 + plm::PEER_THREADS - 1) / plm::PEER_THREADS, plm::PEER_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_peer_allgather_i32(plm_ctx *ctx, void *const *peers, int rank, int world, int64_t n_rows_cap, uint32_t epoch,
+                                       const int32_t *local_dev, int64_t row_lo, int64_t n_local, int64_t n_rows,
+                                       const int32_t *local_count_dev, int32_t *out_dev, int32_t *out_count_dev,
+                                       int32_t *error_dev) {
+    if (world <= 0 || world > PLM_PEER_MAX_RANKS || rank < 0 || rank >= world) return fail(PLM_E_INVALID, "bad rank / world");
+    if (epoch == 0 || n_rows < 0 || n_rows > n_rows_cap || row_lo < 0 || n_local < 0 || row_lo + n_local > n_rows)
+        return fail(PLM_E_INVALID, "rows outside [0, n_rows_cap] or epoch == 0");
+    if (!peers || !error_dev || (n_local > 0 && !local_dev) || (n_rows > 0 && !out_dev)) return fail(PLM_E_INVALID, "null pointer");
+    for (int r = 0; r < world; ++r)
+        if (!peers[r]) return fail(PLM_E_INVALID, "null peer buffer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::PeerGatherArgs a{};
+    for (int r = 0; r < world; ++r) a.peer[r] = static_cast<unsigned char *>(peers[r]);
+    a.rank = rank;
+    a.world = world;
+    a.n_rows_cap = n_rows_cap;
+    a.epoch = epoch;
+    a.local = local_dev;
+    a.row_lo = row_lo;
+    a.n_local = n_local;
+    a.n_rows = n_rows;
+    a.local_count = local_count_dev;
+    a.out = out_dev;
+    a.out_count = out_count_dev;
+    a.error = error_dev;
+    a.spin_limit = 4000000000ll;
+    // every rank must launch the SAME grid size is not required (flags are per rank), but the grid must fit the device at
+    // once so that no block waits behind spinning ones: at most one CTA per SM
+    const int64_t work = std::max<int64_t>(std::max<int64_t>(n_rows, n_local), 1);
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((work + 1023) / 1024, ctx->sm_count)));
+    plm::peer_allgather_kernel<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;

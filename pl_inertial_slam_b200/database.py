@@ -178,7 +178,12 @@ class PeerExchange:
     gives bit-identical results."""
 
     def __init__(self, g: "_Group", ops: "DeviceOps", q_cap: int):
-        self.g, self.ops, self.q_cap = g, ops, int(q_cap)
+        self.q_cap = int(q_cap)
+        self._setup(g, ops, int(ops.lib.plm_peer_buffer_bytes(g.world, self.q_cap)))
+
+    def _setup(self, g: "_Group", ops: "DeviceOps", n_bytes: int) -> None:
+        """Allocate this rank's buffer, exchange the CUDA IPC handles, map the other ranks' buffers."""
+        self.g, self.ops = g, ops
         self.lib = ops.lib
         self.world, self.rank = g.world, g.rank
         self.epoch = 0
@@ -186,7 +191,7 @@ class PeerExchange:
         self._opened = []
         dev = torch.device("cuda", ops.device)
         handle = (C.c_uint8 * 64)()
-        st = self.lib.plm_peer_alloc(ops.ctx.handle, self.world, self.q_cap, C.byref(self._own), handle)
+        st = self.lib.plm_peer_alloc_bytes(ops.ctx.handle, n_bytes, C.byref(self._own), handle)
         ok = torch.tensor([1 if st == L.PLM_OK else 0], dtype=torch.int32, device=dev)
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         handles = g.all_gather(mine).cpu().numpy()                      # [world, 64]
@@ -275,6 +280,35 @@ class PeerExchange:
             self._own = C.c_void_p()
 
 
+class PeerGather(PeerExchange):
+    """All-gather of the per-shard match vectors + sum of the per-shard counts over NVLink peer memory
+    (plm_dev_peer_allgather_i32): the last step of the row-sharded match / matchGrid as one kernel."""
+
+    def __init__(self, g: "_Group", ops: "DeviceOps", n_rows_cap: int):
+        self.n_rows_cap = int(n_rows_cap)
+        self._setup(g, ops, int(ops.lib.plm_peer_gather_bytes(g.world, self.n_rows_cap)))
+
+    @classmethod
+    def create(cls, g: "_Group", ops, n_rows_cap: int) -> Optional["PeerGather"]:
+        if g.world <= 1 or g.world > 16 or not isinstance(ops, DeviceOps):
+            return None
+        x = cls(g, ops, n_rows_cap)
+        return x if x.ok else None
+
+    def gather(self, local: torch.Tensor, row_lo: int, n_rows: int, count: Optional[torch.Tensor]):
+        """-> (global int32 vector [n_rows], summed count [1]) on every rank."""
+        assert local.dtype == torch.int32 and local.is_contiguous() and n_rows <= self.n_rows_cap
+        out = torch.empty(n_rows, dtype=torch.int32, device=local.device)
+        total = torch.empty(1, dtype=torch.int32, device=local.device)
+        self.epoch += 1
+        self.ops._bind_stream()
+        L.check(self.lib.plm_dev_peer_allgather_i32(self.ops.ctx.handle, self.ptrs, self.rank, self.world, self.n_rows_cap,
+                                                    self.epoch, _ptr(local), int(row_lo), int(local.shape[0]), int(n_rows),
+                                                    _ptr(count), _ptr(out), _ptr(total), _ptr(self.error)),
+                "plm_dev_peer_allgather_i32")
+        return out, total
+
+
 class ShardedDescriptorDB:
     """Flat descriptor database (config 5), row-sharded over the ranks of a process group.
 
@@ -346,6 +380,7 @@ class ShardedMap:
         self.peer = PeerExchange.create(self.g, self.ops, q_cap) if exchange in ("peer", "auto") else None
         if exchange == "peer" and self.world > 1 and self.peer is None:
             raise RuntimeError("peer-memory exchange requested but CUDA IPC peer mapping is unavailable")
+        self.gatherer = PeerGather.create(self.g, self.ops, int(n_rows)) if self.peer is not None else None
         self.n_rows = int(n_rows)
         self.lo, self.hi = shard_bounds(self.n_rows, self.world, self.rank)
         assert d1_shard.shape[0] == self.hi - self.lo
@@ -361,6 +396,14 @@ class ShardedMap:
         pad = torch.full((self.per,), -1, dtype=m12_local.dtype, device=m12_local.device)
         pad[: m12_local.shape[0]] = m12_local
         return self.g.all_gather(pad).reshape(-1)[: self.n_rows]
+
+    def _finish(self, m12_local: torch.Tensor, count: torch.Tensor):
+        """Global match vector + global count on every rank: one peer-memory kernel, or all_reduce + all_gather."""
+        if self.gatherer is not None:
+            m12, total = self.gatherer.gather(m12_local, self.lo, self.n_rows, count)
+            return total, m12
+        self.g.all_reduce_sum(count)
+        return count, self._gather_rows(m12_local)
 
     def _local_m12(self, m12_global: Optional[torch.Tensor], device) -> torch.Tensor:
         if m12_global is None:
@@ -386,8 +429,7 @@ class ShardedMap:
                 top21 = part if self.world == 1 else self.ops.top2_merge(self.g.all_gather(part))
                 self.ops.nnr_accept(top21, nnr, m21, None)
             self.ops.cross_check(m12, self.lo, m21, count)
-        self.g.all_reduce_sum(count)
-        return count, self._gather_rows(m12)
+        return self._finish(m12, count)
 
     # -- StVO::matchGrid (mapHandler.cpp:637-642 / :752-757) --------------------------------------
     def match_grid(self, frame: GridFrame, win, ratio: float, line_sim_th: float = 0.75, best_lr: bool = True,
@@ -396,6 +438,22 @@ class ShardedMap:
         n2 = frame.d2.shape[0]
         m12 = self._local_m12(m12_inout, dev)
         count = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.peer is not None and self.gatherer is not None and (n2 == 0 or self.peer.fits(8 * n2)):
+            # everything in one C call: the launches go out back to back, the three exchanges are peer-memory kernels
+            a = self.ops._grid_args(self.coords, self.d1, self.lo, frame, win, ratio, line_sim_th, best_lr, m12, count)
+            grp = L.PeerGroup()
+            grp.xchg, grp.gather = self.peer.ptrs, self.gatherer.ptrs
+            grp.rank, grp.world, grp.q_cap = self.rank, self.world, self.peer.q_cap
+            grp.n_rows_cap = self.gatherer.n_rows_cap
+            grp.xchg_epoch, grp.gather_epoch = self.peer.epoch + 1, self.gatherer.epoch + 1
+            self.peer.epoch += 2
+            self.gatherer.epoch += 1
+            out = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
+            total = torch.empty(1, dtype=torch.int32, device=dev)
+            self.ops._bind_stream()
+            L.check(self.ops.lib.plm_dev_sharded_match_grid(self.ops.ctx.handle, C.byref(a), C.byref(grp), self.n_rows, _ptr(out),
+                                                            _ptr(total), _ptr(self.peer.error)), "plm_dev_sharded_match_grid")
+            return total, out
         seed = None
         use_peer = self.peer is not None and n2 > 0 and self.peer.fits(8 * n2)
         if best_lr and self.world > 1:
@@ -419,5 +477,4 @@ class ShardedMap:
                 key = (allk.min(dim=0).values ^ INT64_MIN).contiguous()
             m21 = self.ops.m21_from_keys(key) if n2 else torch.empty(0, dtype=torch.int32, device=dev)
             self.ops.cross_check(m12, self.lo, m21, count)
-        self.g.all_reduce_sum(count)
-        return count, self._gather_rows(m12)
+        return self._finish(m12, count)

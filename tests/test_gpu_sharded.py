@@ -190,5 +190,38 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
                 else:
                     want = host[:r].min(axis=0) if r > 0 else np.full(n, 0xFFFF, np.uint16)
                 assert np.array_equal(got, want), (op, n, r)
+    # all-gather of per-rank int32 shards + sum of per-rank counts through a second set of buffers
+    n_cap = 5000
+    gbufs = (C.c_void_p * world)()
     for r, o in enumerate(ranks):
+        p, h = C.c_void_p(), (C.c_uint8 * 64)()
+        L.check(plm_lib.plm_peer_alloc_bytes(o.ctx.handle, plm_lib.plm_peer_gather_bytes(world, n_cap), C.byref(p), h),
+                "plm_peer_alloc_bytes")
+        gbufs[r] = p
+    g_epoch = 0
+    for n_rows in (5000, 1, 4097, 37, 5000):
+        full = rng.integers(-1, 1000, n_rows).astype(np.int32)
+        counts = rng.integers(-50, 500, world).astype(np.int32)
+        spans = [shard_bounds(n_rows, world, r) for r in range(world)]
+        loc = [torch.from_numpy(full[lo:hi].copy()).cuda() for lo, hi in spans]
+        cnt = [torch.from_numpy(counts[r:r + 1].copy()).cuda() for r in range(world)]
+        outs = [torch.full((n_rows,), -7, dtype=torch.int32, device="cuda") for _ in range(world)]
+        tot = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+        g_epoch += 1
+        torch.cuda.synchronize()
+        for r, o in enumerate(ranks):
+            with torch.cuda.stream(streams[r]):
+                o._bind_stream()
+                L.check(plm_lib.plm_dev_peer_allgather_i32(o.ctx.handle, gbufs, r, world, n_cap, g_epoch, C.c_void_p(loc[r].data_ptr()),
+                                                           spans[r][0], spans[r][1] - spans[r][0], n_rows,
+                                                           C.c_void_p(cnt[r].data_ptr()), C.c_void_p(outs[r].data_ptr()),
+                                                           C.c_void_p(tot[r].data_ptr()), C.c_void_p(err[r:].data_ptr())),
+                        "plm_dev_peer_allgather_i32")
+        torch.cuda.synchronize()
+        assert not err.any().item(), "a rank timed out"
+        for r in range(world):
+            assert np.array_equal(outs[r].cpu().numpy(), full), (n_rows, r)
+            assert int(tot[r].item()) == int(counts.sum()), (n_rows, r)
+    for r, o in enumerate(ranks):
+        plm_lib.plm_peer_free(o.ctx.handle, gbufs[r])
         plm_lib.plm_peer_free(o.ctx.handle, bufs[r])

@@ -1,5 +1,6 @@
 """Config 4 at N GPUs (torchrun): the 200k-point / 50k-line local map row-sharded over the ranks,
-matchGrid (+-3 window) then the forced match() fallback, NCCL exchanges included.  Prints one JSON line."""
+matchGrid (+-3 window) then the forced match() fallback, exchanges included (the peer-memory kernels and, beside
+them, the NCCL form).  Prints one JSON line."""
 import json
 import os
 import sys
@@ -30,8 +31,26 @@ def main():
     frame = GridFrame(torch.from_numpy(sp.pdesc_l).to(dev), torch.from_numpy(cs).to(dev), torch.from_numpy(ci).to(dev),
                       G.GRID_ROWS, G.GRID_COLS)
     lo, hi = shard_bounds(n_map, world, rank)
-    smap = ShardedMap(n_map, torch.from_numpy(d1[lo:hi].copy()).to(dev), torch.from_numpy(xy[lo:hi].copy()).to(dev), device=local)
+    d1_dev, xy_dev = torch.from_numpy(d1[lo:hi].copy()).to(dev), torch.from_numpy(xy[lo:hi].copy()).to(dev)
     win = np.array([3, 3, 3, 3], np.int32)
+    out = {"workload": "config 4: 200k map points x 600 frame points", "n_gpus": world}
+    forms = ["auto"] if world == 1 else ["auto", "nccl"]
+    ops = None
+    for form in forms:
+        smap = ShardedMap(n_map, d1_dev, xy_dev, device=local, exchange=form, ops=ops)
+        ops = smap.ops
+        name = "single" if world == 1 else ("peer_memory" if smap.peer is not None else "nccl")
+        out[name] = run(smap, frame, win, world, rank, dev, n_map)
+        if smap.peer is not None:
+            smap.peer.check()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run(smap, frame, win, world, rank, dev, n_map):
 
     def timed(fn, reps=20):
         for _ in range(3):
@@ -52,13 +71,8 @@ def main():
 
     g_ms, (cnt, m12) = timed(lambda: smap.match_grid(frame, win, 0.9, 0.75, True))
     f_ms, (cnt2, _) = timed(lambda: smap.match(frame.d2, 0.9, True, m12_inout=m12))
-    if rank == 0:
-        print(json.dumps({"workload": "config 4: 200k map points x 600 frame points", "n_gpus": world,
-                          "matchGrid_ms": g_ms, "matchGrid_matches": int(cnt.item()), "match_fallback_ms": f_ms,
-                          "match_fallback_count": int(cnt2.item()),
-                          "match_fallback_unique_pairs_per_s": n_map * 600.0 / (f_ms * 1e-3)}))
-    if world > 1:
-        dist.destroy_process_group()
+    return {"matchGrid_ms": g_ms, "matchGrid_matches": int(cnt.item()), "match_fallback_ms": f_ms,
+            "match_fallback_count": int(cnt2.item()), "match_fallback_unique_pairs_per_s": n_map * 600.0 / (f_ms * 1e-3)}
 
 
 if __name__ == "__main__":
