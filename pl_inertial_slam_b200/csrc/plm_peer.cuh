@@ -6,7 +6,7 @@
 // A CTA handles 128 queries:
 //   push   its packed keys go straight into slot [parity][my rank][q] of EVERY rank's buffer
 //          (16-byte stores over NVLink / NVSwitch; the local copy is an ordinary store);
-//   signal __threadfence_system, then flag [parity][my rank][block] = epoch on every rank;
+//   signal CTA barrier, then flag [parity][my rank][block] = epoch on every rank with st.release.sys (cumulative);
 //   wait   until the G flags [parity][r][block] of the OWN buffer read `epoch` (bounded spin);
 //   merge  the G x 2 keys per query with unsigned min (== the reference's lowest-index tie-breaking),
 //          optionally followed by the matchNNR ratio test.
@@ -50,6 +50,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ ulonglong2 ld_volatile_u64x2(const ulonglong2 *p) {
     ulonglong2 v;
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
@@ -69,7 +74,8 @@ __device__ __forceinline__ bool peer_push_wait(const PeerExchangeArgs &a, int q,
             reinterpret_cast<ulonglong2 *>(a.peer[dst])[key_slot + q] = v;
         }
     }
-    __threadfence_system();
+    // Release pattern of the PTX memory model: the CTA barrier orders every thread's stores before the signalling
+    // threads, whose st.release.sys is cumulative over that order -- no membar.sys (it alone costs ~10 us here).
     __syncthreads();
     if (threadIdx.x < a.world) { // signal
         const int dst = (a.rank + threadIdx.x) % a.world;
@@ -96,8 +102,7 @@ __device__ __forceinline__ bool peer_push_wait(const PeerExchangeArgs &a, int q,
         if (threadIdx.x == 0) atomicExch(a.error, 1);
         return false;
     }
-    __threadfence_system();
-    return true;
+    return true; // acquire pattern: ld.acquire.sys by the waiting threads, then the CTA barrier above
 }
 
 __device__ __forceinline__ const ulonglong2 *peer_slots(const PeerExchangeArgs &a) {
@@ -212,15 +217,15 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(PeerGatherArgs a) {
             counts[par * a.world + a.rank] = a.local_count ? *a.local_count : 0;
         }
     }
-    __threadfence_system();
     __syncthreads();
-    // signal: the last block of this grid to get here
+    // signal: the last block of this grid to get here (acq_rel counter: the other blocks' stores happen before the
+    // last block's st.release.sys, which is cumulative)
     uint32_t *own_flags = reinterpret_cast<uint32_t *>(a.peer[a.rank] + rows_bytes + size_t(2) * a.world * 4);
     uint32_t *done = own_flags + 2 * a.world + par;
     __shared__ int s_last, s_fail;
     if (threadIdx.x == 0) {
         s_fail = 0;
-        s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1 : 0;
+        s_last = (atom_add_acq_rel_gpu(done, 1u) == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
     if (s_last) {
@@ -248,7 +253,6 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(PeerGatherArgs a) {
         if (threadIdx.x == 0) atomicExch(a.error, 1);
         return;
     }
-    __threadfence_system();
     // copy out
     const volatile int32_t *rows = reinterpret_cast<const volatile int32_t *>(a.peer[a.rank]) + size_t(par) * a.n_rows_cap;
     for (long long i = tid; i < a.n_rows; i += nthreads) a.out[i] = rows[i];

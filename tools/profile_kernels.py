@@ -102,6 +102,31 @@ feats = synth.vocabulary_features(synth.SEED0 + 41, fvoc, n_kf * 600)
 bows = voc.transform_batch(feats, np.arange(n_kf + 1, dtype=np.int32) * 600)
 db = [bows[i % n_kf] for i in range(5_000 if quick else 20_000)]
 B.score_matrix(bows[:1], db, ctx=ctx)
+# peer-memory exchange kernels with a world of ONE rank (under ncu kernels are serialised, so several ranks on one GPU
+# would wait for each other until the time-out): push into the own buffer, flag, wait (satisfied at once), merge
+import ctypes as C  # noqa: E402
+from pl_inertial_slam_b200 import _lib as L  # noqa: E402
+lib = L.load()
+xb, gb_, hdl = C.c_void_p(), C.c_void_p(), (C.c_uint8 * 64)()
+L.check(lib.plm_peer_alloc(ctx.handle, 1, 8192, C.byref(xb), hdl), "plm_peer_alloc")
+L.check(lib.plm_peer_alloc_bytes(ctx.handle, lib.plm_peer_gather_bytes(1, 200_000), C.byref(gb_), hdl), "plm_peer_alloc_bytes")
+xs, gs = (C.c_void_p * 1)(xb), (C.c_void_p * 1)(gb_)
+err = torch.zeros(1, dtype=torch.int32, device=dev)
+pm12 = torch.full((6400,), -1, dtype=torch.int32, device=dev)
+pcnt = torch.zeros(1, dtype=torch.int32, device=dev)
+pout = torch.empty_like(t2)
+p_ = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+L.check(lib.plm_dev_top2_exchange(ctx.handle, xs, 0, 1, 8192, 1, p_(t2), 6400, p_(pout), C.c_float(0.9), p_(pm12), p_(pcnt), p_(err)),
+        "plm_dev_top2_exchange")
+keys = torch.randint(0, 1 << 40, (600,), dtype=torch.int64, device=dev)
+kout = torch.empty_like(keys)
+L.check(lib.plm_dev_peer_reduce(ctx.handle, xs, 0, 1, 8192, 2, 0, p_(keys), 300, p_(kout), p_(err)), "plm_dev_peer_reduce")
+rows = torch.randint(-1, 600, (200_000,), dtype=torch.int32, device=dev)
+rout, rtot = torch.empty_like(rows), torch.zeros(1, dtype=torch.int32, device=dev)
+L.check(lib.plm_dev_peer_allgather_i32(ctx.handle, gs, 0, 1, 200_000, 1, p_(rows), 0, 200_000, 200_000, p_(pcnt), p_(rout), p_(rtot),
+                                       p_(err)), "plm_dev_peer_allgather_i32")
+ctx.synchronize()
+assert int(err.item()) == 0 and torch.equal(rout, rows)
 torch.cuda.synchronize()
 ctx.synchronize()
 print("profile_kernels ok: launches", ctx.launch_count + ops.ctx.launch_count)
