@@ -469,6 +469,8 @@ int plm_dev_bow_score(plm_ctx *ctx, const uint32_t *q_ids_dev, const double *q_v
  *                  2 = carry-save 4-POPC with blocked top-2 update.
  *   "grid_cluster" 1 = single matchGrid calls run on an 8-CTA thread-block cluster (default),
  *                  0 = on one CTA.
+ *   "frames_threads_p" / "frames_threads_l"  CTA width of the frame pipeline's point chain (256 or 512, default 512)
+ *                  and line chain (128 or 256, default 256).
  *   "frames_pairs_p" / "frames_pairs_l"  candidate slots per query row the frame pipeline's pair-list
  *                  matcher is sized for (default 8 / 0; 0 = always use the chunk phases). */
 int plm_set_option(const char *key, int value);

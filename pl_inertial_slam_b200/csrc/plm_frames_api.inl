@@ -266,8 +266,8 @@ FrameChunkPrep frames_chunk_prep(const plm_frames *fr, const float *ln_arena, co
     // frames take the chunk phases inside the same kernel
     const int pairs_p = std::min(g_frames_pairs_per_row[0] * cap_pl, 16384);
     const int pairs_l = std::min(g_frames_pairs_per_row[1] * cap_ll, 16384);
-    ch.caps_p = plm::StereoCaps{cap_pl, cap_pr, cap_pr, FRAMES_THREADS_P / 32, pairs_p, 0};
-    ch.caps_l = plm::StereoCaps{cap_ll, cap_lr, static_cast<int>(cap_items_l), FRAMES_THREADS_L / 32, pairs_l, 0};
+    ch.caps_p = plm::StereoCaps{cap_pl, cap_pr, cap_pr, g_frames_threads_p / 32, pairs_p, 0};
+    ch.caps_l = plm::StereoCaps{cap_ll, cap_lr, static_cast<int>(cap_items_l), g_frames_threads_l / 32, pairs_l, 0};
     ch.smem_p = plm::stereo_frame_smem(ch.caps_p, n_cells, false);
     ch.smem_l = plm::stereo_frame_smem(ch.caps_l, n_cells, true);
     ch.smem_fp = plm::f2f_smem(cap_fp, cap_fp);
@@ -420,15 +420,25 @@ int frames_chunk_run(plm_frames *fr, const plm_frames_chunk &ch, size_t k) {
     CU_TRY(cudaEventRecord(e_fork, s));
     CU_TRY(cudaStreamWaitEvent(fr->s_lines, e_fork, 0));
     const int t0 = std::max(ch.f0, 1); // frame 0 has no predecessor
-    if ((st = launch_stereo<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n,
-                                              fr->cfg, ch.caps_p, ch.smem_p)) != PLM_OK) return st;
-    if ((st = launch_stereo<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0,
-                                              n, fr->cfg, ch.caps_l, ch.smem_l)) != PLM_OK) return st;
+    const bool wide_p = ch.caps_p.warps * 32 == 512;
+    if ((st = wide_p ? launch_stereo<512>(ctx, s, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n, fr->cfg,
+                                          ch.caps_p, ch.smem_p)
+                     : launch_stereo<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n,
+                                                       fr->cfg, ch.caps_p, ch.smem_p)) != PLM_OK) return st;
+    const bool wide_l = ch.caps_l.warps * 32 == FRAMES_THREADS_P;
+    if ((st = wide_l ? launch_stereo<FRAMES_THREADS_P>(ctx, fr->s_lines, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0,
+                                                       n, fr->cfg, ch.caps_l, ch.smem_l)
+                     : launch_stereo<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0,
+                                                       n, fr->cfg, ch.caps_l, ch.smem_l)) != PLM_OK) return st;
     if (ch.f1 > t0) {
-        if ((st = launch_f2f<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
-                                               fr->cfg.best_lr, ch.smem_fp)) != PLM_OK) return st;
-        if ((st = launch_f2f<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0,
-                                               ch.f1 - t0, fr->cfg.best_lr, ch.smem_fl)) != PLM_OK) return st;
+        if ((st = wide_p ? launch_f2f<512>(ctx, s, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
+                                           fr->cfg.best_lr, ch.smem_fp)
+                         : launch_f2f<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
+                                                        fr->cfg.best_lr, ch.smem_fp)) != PLM_OK) return st;
+        if ((st = wide_l ? launch_f2f<FRAMES_THREADS_P>(ctx, fr->s_lines, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0,
+                                                        ch.f1 - t0, fr->cfg.best_lr, ch.smem_fl)
+                         : launch_f2f<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0,
+                                                        ch.f1 - t0, fr->cfg.best_lr, ch.smem_fl)) != PLM_OK) return st;
     }
     CU_TRY(cudaEventRecord(e_join, fr->s_lines));
     CU_TRY(cudaStreamWaitEvent(s, e_join, 0));

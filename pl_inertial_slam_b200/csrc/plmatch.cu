@@ -162,6 +162,8 @@ struct KnnPlan {
 // sits in ~8 cells, so a row holds ~20 slots for ~6 distinct candidates, the slot arrays push the CTA to one
 // per SM and the measured stereo-lines stage is 6x slower than with the chunk phases (profiles/r1_frames.md).
 int g_frames_pairs_per_row[2] = {8, 0};
+int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame pipeline (128 or 256; measurement knob)
+int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
 
 // -1 = automatic (variant 2 for long slices, 1 otherwise); 0/1/2 force a variant (measurement only)
@@ -300,6 +302,14 @@ PLM_API int plm_set_option(const char *key, int value) {
     }
     if (std::strcmp(key, "grid_cluster") == 0) {
         g_grid_cluster = value ? 1 : 0;
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "frames_threads_l") == 0) {
+        g_frames_threads_l = value >= 256 ? 256 : 128;
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "frames_threads_p") == 0) {
+        g_frames_threads_p = value >= 512 ? 512 : 256;
         return PLM_OK;
     }
     if (std::strcmp(key, "frames_pairs_p") == 0 || std::strcmp(key, "frames_pairs_l") == 0) {
