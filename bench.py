@@ -298,6 +298,16 @@ def run_b200(args):
         step_device(q_dev[s])
         flush.fill_(s & 0xFF)
     barrier()
+    if db.peer is not None and not db.peer.healthy():
+        # a peer-memory exchange timed out on some rank during warm-up (peer stores not visible on this box?):
+        # every rank switches to the NCCL form -- bit-identical results -- and warms up again
+        if args.exchange == "peer":
+            raise SystemExit("peer-memory exchange requested but an exchange timed out")
+        db.peer = None
+        for s in range(args.warmup):
+            step_device(q_dev[s])
+            flush.fill_(s & 0xFF)
+        barrier()
 
     # ---- timed: device-resident inputs ---------------------------------------------------------
     sampler = ClockSampler(local_rank)

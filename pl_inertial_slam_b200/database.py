@@ -263,6 +263,12 @@ class PeerExchange:
     def fits(self, n_bytes: int) -> bool:
         return (n_bytes + 15) // 16 <= self.q_cap
 
+    def healthy(self) -> bool:
+        """Host sync + one all_reduce: True when no exchange timed out on ANY rank since construction."""
+        bad = (self.error != 0).to(torch.int32)
+        self.g.dist.all_reduce(bad, op=self.g.dist.ReduceOp.MAX, group=self.g.group)
+        return int(bad.item()) == 0
+
     def check(self) -> None:
         """Host sync: raises if any exchange since the last check timed out waiting for a peer."""
         if int(self.error.item()) != 0:
