@@ -391,6 +391,14 @@ typedef struct plm_peer_group {
 int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a, const plm_peer_group *g, int64_t n_rows_total,
                                int32_t *m12_global_dev, int32_t *count_global_dev, int32_t *error_dev);
 
+/* The row-sharded StVO::match of one rank (the brute-force fallback of matchMap2KF*, mapHandler.cpp:645-650, on the same
+ * in/out vector) in one call: direction 12 local, direction 21 through the peer-memory top-2 exchange (epoch xchg_epoch),
+ * mutual check, all-gather of the match vectors + counts (epoch gather_epoch).  m12_local_inout_dev = this shard's
+ * slice of the in/out vector (n1 rows starting at global row i1_base); n2 <= q_cap frame descriptors. */
+int plm_dev_sharded_match(plm_ctx *ctx, const void *d1_shard_dev, int n1, int64_t i1_base, const void *d2_dev, int n2,
+                          float nnr, int best_lr, int32_t *m12_local_inout_dev, const plm_peer_group *g,
+                          int64_t n_rows_total, int32_t *m12_global_dev, int32_t *count_global_dev, int32_t *error_dev);
+
 /* A device-resident descriptor database shard (keyframe DB / local map). */
 int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out);
 int plm_db_destroy(plm_db *db);

@@ -147,6 +147,8 @@ SIGNATURES = {
     "plm_dev_peer_allgather_i32": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int64, C.c_uint32, vp, C.c_int64,
                                              C.c_int64, C.c_int64, vp, vp, vp, vp]),
     "plm_dev_sharded_match_grid": (C.c_int, [vp, C.POINTER(DevGridArgs), C.POINTER(PeerGroup), C.c_int64, vp, vp, vp]),
+    "plm_dev_sharded_match": (C.c_int, [vp, vp, C.c_int, C.c_int64, vp, C.c_int, C.c_float, C.c_int, vp, C.POINTER(PeerGroup),
+                                        C.c_int64, vp, vp, vp]),
     "plm_dev_peer_reduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_int, vp, vp]),
     "plm_db_create": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
     "plm_db_destroy": (C.c_int, [vp]),

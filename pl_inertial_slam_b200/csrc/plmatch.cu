@@ -72,6 +72,8 @@ struct plm_ctx {
     size_t d_cap = 0;
     char *h_buf = nullptr; // pinned
     size_t h_cap = 0;
+    char *d_aux = nullptr; // second device scratch: survives the ensure_device of nested entry points
+    size_t aux_cap = 0;
     uint64_t launches = 0;
     bool fused_attr_set = false;
     bool cluster_attr_set = false;
@@ -91,6 +93,17 @@ struct plm_ctx {
         const size_t cap = align_up(bytes + bytes / 4, 1 << 20);
         CU_TRY(cudaMalloc(reinterpret_cast<void **>(&d_buf), cap));
         d_cap = cap;
+        return PLM_OK;
+    }
+    int ensure_aux(size_t bytes) {
+        if (bytes <= aux_cap) return PLM_OK;
+        CU_TRY(cudaStreamSynchronize(stream));
+        if (d_aux) CU_TRY(cudaFree(d_aux));
+        d_aux = nullptr;
+        aux_cap = 0;
+        const size_t cap = align_up(bytes + bytes / 4, 1 << 20);
+        CU_TRY(cudaMalloc(reinterpret_cast<void **>(&d_aux), cap));
+        aux_cap = cap;
         return PLM_OK;
     }
     int ensure_pinned(size_t bytes) {
@@ -374,6 +387,11 @@ PLM_API int plm_ctx_create(int device, plm_ctx **out) {
 }
 
 PLM_API int plm_ctx_destroy(plm_ctx *ctx) {
+    if (ctx && ctx->d_aux) {
+        cudaSetDevice(ctx->device);
+        cudaFree(ctx->d_aux);
+        ctx->d_aux = nullptr;
+    }
     if (!ctx) return PLM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) {
@@ -1125,6 +1143,47 @@ PLM_API int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a,
     }
     return plm_dev_peer_allgather_i32(ctx, g->gather, g->rank, g->world, g->n_rows_cap, g->gather_epoch, a->m12_inout, a->i1_base,
                                       a->n1, n_rows_total, a->count, m12_global_dev, count_global_dev, error_dev);
+}
+
+// The row-sharded StVO::match of one rank (the brute-force fallback of matchMap2KF*, mapHandler.cpp:645-650) in one
+// call: 12 direction local, 21 direction through the peer-memory top-2 exchange, mutual check, all-gather.
+PLM_API int plm_dev_sharded_match(plm_ctx *ctx, const void *d1_shard_dev, int n1, int64_t i1_base, const void *d2_dev, int n2,
+                                  float nnr, int best_lr, int32_t *m12_local_inout_dev, const plm_peer_group *g,
+                                  int64_t n_rows_total, int32_t *m12_global_dev, int32_t *count_global_dev, int32_t *error_dev) {
+    if (!g || !g->xchg || !g->gather || !m12_global_dev || !count_global_dev || !error_dev) return fail(PLM_E_INVALID, "null pointer");
+    if (g->world < 2 || g->world > PLM_PEER_MAX_RANKS || g->rank < 0 || g->rank >= g->world) return fail(PLM_E_INVALID, "bad rank / world");
+    if (n1 < 0 || n2 < 0 || i1_base < 0 || i1_base + n1 > n_rows_total || n_rows_total > g->n_rows_cap)
+        return fail(PLM_E_INVALID, "rows outside the gather buffers");
+    if (n1 > 0 && (!d1_shard_dev || !m12_local_inout_dev)) return fail(PLM_E_INVALID, "null pointer");
+    if (n2 < 2) return fail(PLM_E_TRAIN, plm_status_string(PLM_E_TRAIN)); // UB in the reference (matching.cpp:54)
+    if (n2 > g->q_cap) return fail(PLM_E_UNSUPPORTED, "frame too large for the exchange buffers");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout L;
+    const size_t o_top12 = L.add(size_t(std::max(n1, 1)) * 16), o_part = L.add(size_t(n2) * 16), o_m21 = L.add(size_t(n2) * 4),
+                 o_cnt = L.add(16);
+    if ((st = ctx->ensure_aux(L.total)) != PLM_OK) return st;
+    char *X = ctx->d_aux;
+    uint64_t *top12 = reinterpret_cast<uint64_t *>(X + o_top12), *part = reinterpret_cast<uint64_t *>(X + o_part);
+    int32_t *m21 = reinterpret_cast<int32_t *>(X + o_m21), *cnt = reinterpret_cast<int32_t *>(X + o_cnt);
+    CU_TRY(cudaMemsetAsync(cnt, 0, 4, ctx->stream));
+    // direction 12: this shard's rows against the whole frame are final locally
+    if (n1 > 0) {
+        if ((st = plm_dev_knn2(ctx, d1_shard_dev, n1, d2_dev, n2, 0, top12)) != PLM_OK) return st;
+        if ((st = plm_dev_nnr_accept(ctx, top12, n1, nnr, m12_local_inout_dev, cnt)) != PLM_OK) return st;
+    }
+    if (best_lr) {
+        // direction 21: per-shard top-2 with global map indices -> push / wait / merge / ratio test in one kernel
+        CU_TRY(cudaMemsetAsync(part, 0xFF, size_t(n2) * 16, ctx->stream)); // an empty shard contributes absent keys
+        CU_TRY(cudaMemsetAsync(m21, 0xFF, size_t(n2) * 4, ctx->stream));
+        if (n1 > 0 && (st = plm_dev_knn2(ctx, d2_dev, n2, d1_shard_dev, n1, static_cast<uint64_t>(i1_base), part)) != PLM_OK) return st;
+        if ((st = plm_dev_top2_exchange(ctx, g->xchg, g->rank, g->world, g->q_cap, g->xchg_epoch, part, n2, nullptr, nnr, m21, nullptr,
+                                        error_dev)) != PLM_OK)
+            return st;
+        if (n1 > 0 && (st = plm_dev_cross_check(ctx, m12_local_inout_dev, n1, i1_base, m21, n2, cnt)) != PLM_OK) return st;
+    }
+    return plm_dev_peer_allgather_i32(ctx, g->gather, g->rank, g->world, g->n_rows_cap, g->gather_epoch, m12_local_inout_dev, i1_base,
+                                      n1, n_rows_total, cnt, m12_global_dev, count_global_dev, error_dev);
 }
 
 PLM_API int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int n2, int32_t *m21_dev) {

@@ -403,6 +403,17 @@ class ShardedMap:
         pad[: m12_local.shape[0]] = m12_local
         return self.g.all_gather(pad).reshape(-1)[: self.n_rows]
 
+    def _peer_group(self, n_xchg_epochs: int) -> "L.PeerGroup":
+        """The two sets of peer buffers + the epochs the next fused call consumes."""
+        grp = L.PeerGroup()
+        grp.xchg, grp.gather = self.peer.ptrs, self.gatherer.ptrs
+        grp.rank, grp.world, grp.q_cap = self.rank, self.world, self.peer.q_cap
+        grp.n_rows_cap = self.gatherer.n_rows_cap
+        grp.xchg_epoch, grp.gather_epoch = self.peer.epoch + 1, self.gatherer.epoch + 1
+        self.peer.epoch += n_xchg_epochs
+        self.gatherer.epoch += 1
+        return grp
+
     def _finish(self, m12_local: torch.Tensor, count: torch.Tensor):
         """Global match vector + global count on every rank: one peer-memory kernel, or all_reduce + all_gather."""
         if self.gatherer is not None:
@@ -421,6 +432,17 @@ class ShardedMap:
         """-> (count tensor [1], m12 global int32[n_rows]); m12_inout is the global in/out vector."""
         dev = d2.device
         m12 = self._local_m12(m12_inout, dev)
+        if self.peer is not None and self.gatherer is not None and 2 <= d2.shape[0] <= self.peer.q_cap:
+            # one C call: both directions, the peer-memory exchange, mutual check and the all-gather back to back
+            grp = self._peer_group(1 if best_lr else 0)   # only epochs that are really used are consumed
+            out = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
+            total = torch.empty(1, dtype=torch.int32, device=dev)
+            self.ops._bind_stream()
+            L.check(self.ops.lib.plm_dev_sharded_match(self.ops.ctx.handle, _ptr(self.d1), int(self.d1.shape[0]), self.lo, _ptr(d2),
+                                                       int(d2.shape[0]), C.c_float(nnr), int(bool(best_lr)), _ptr(m12), C.byref(grp),
+                                                       self.n_rows, _ptr(out), _ptr(total), _ptr(self.peer.error)),
+                    "plm_dev_sharded_match")
+            return total, out
         count = torch.zeros(1, dtype=torch.int32, device=dev)
         # direction 12: the shard's rows are final locally
         top12 = self.ops.knn2(self.d1, d2, idx_base=0)
@@ -447,13 +469,7 @@ class ShardedMap:
         if self.peer is not None and self.gatherer is not None and (n2 == 0 or self.peer.fits(8 * n2)):
             # everything in one C call: the launches go out back to back, the three exchanges are peer-memory kernels
             a = self.ops._grid_args(self.coords, self.d1, self.lo, frame, win, ratio, line_sim_th, best_lr, m12, count)
-            grp = L.PeerGroup()
-            grp.xchg, grp.gather = self.peer.ptrs, self.gatherer.ptrs
-            grp.rank, grp.world, grp.q_cap = self.rank, self.world, self.peer.q_cap
-            grp.n_rows_cap = self.gatherer.n_rows_cap
-            grp.xchg_epoch, grp.gather_epoch = self.peer.epoch + 1, self.gatherer.epoch + 1
-            self.peer.epoch += 2
-            self.gatherer.epoch += 1
+            grp = self._peer_group(2 if (best_lr and n2 > 0) else 0)
             out = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
             total = torch.empty(1, dtype=torch.int32, device=dev)
             self.ops._bind_stream()
