@@ -90,3 +90,30 @@ def test_product_package_never_imports_the_oracle():
                 if re.search(r"^\s*(import oracle|from oracle)\b", text, flags=re.M) or "libploracle" in text or "libplref" in text:
                     offenders.append(f)
     assert not offenders, offenders
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Every struct of include/plmatch.h that the Python binding mirrors has the same size and field offsets when
+    compiled by the C compiler."""
+    import ctypes as C
+    import subprocess
+    from pl_inertial_slam_b200 import _lib as L
+    pairs = [("plm_pair_job", L.PairJob), ("plm_grid_job", L.GridJob), ("plm_dev_grid_args", L.DevGridArgs),
+             ("plm_frame_rec", L.FrameRec), ("plm_frame_config", L.FrameConfig), ("plm_frames_out", L.FramesOut),
+             ("plm_peer_group", L.PeerGroup)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "plmatch.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for (cname, cls), line in zip(pairs, out):
+        nums = [int(x) for x in line.split()[1:]]
+        assert nums[0] == C.sizeof(cls), cname
+        assert nums[1:] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
