@@ -13,6 +13,8 @@
  *   plm_stereo_filter_points  gates of matchStereoPoints   stvo-pl/src/stereoFrame.cpp:162-171
  *   plm_stereo_filter_lines   gates of matchStereoLines    stvo-pl/src/stereoFrame.cpp:359-385,
  *                             filterLineSegmentDisparity :416-426, lineSegmentOverlapStereo :484-519
+ *   plm_line_pair_filter    overlap / angle filter for matched line pairs: StereoFrame::lineSegmentOverlap
+ *                           stvo-pl/src/stereoFrame.cpp:521-627 + the direction test of matching.cpp:221
  *   plm_batch_*             the per-frame loop             app/plslam_dataset.cpp:114-172
  *   plm_frames_*            StereoFrame::matchStereoPoints/Lines + StereoFrameHandler::matchF2FPoints/Lines
  *                           on the device (stereoFrame.cpp:131-184,320-409; stereoFrameHandler.cpp:158-207)
@@ -151,6 +153,16 @@ int plm_stereo_filter_lines(plm_ctx *ctx, const float *ln_l, int n1, const float
 
 /* One brute-force job: rows [off1, off1+n1) x rows [off2, off2+n2) of the descriptor arena;
  * results land at m12_arena[off_m .. off_m + n1). */
+/* Opt-in geometric filter for matched line pairs (BASELINE config 2 "NNR line matching with overlap/angle filter").
+ * The fork's temporal line matcher applies none (stereoFrameHandler.cpp:182-207); this evaluates the reference's own
+ * two tests per matched pair (i1, m12[i1]):
+ *   overlap = StereoFrame::lineSegmentOverlap(observed = ln1[i1], other = ln2[m12[i1]])   stereoFrame.cpp:521-627
+ *   sim     = |dot(normalize(e1 - s1), normalize(e2 - s2))|   matching.h:39-48, the test of matching.cpp:221
+ * keep[i1] = overlap > overlap_th && !(sim < line_sim_th)  (a NaN similarity passes, as in matchGrid); unmatched rows
+ * get keep 0, overlap 0, sim 0.  m12 is not modified.  ln1 / ln2 are n x (sx, sy, ex, ey) float pixels. */
+int plm_line_pair_filter(plm_ctx *ctx, const float *ln1, int n1, const float *ln2, int n2, const int32_t *m12,
+                         double overlap_th, double line_sim_th, uint8_t *keep, double *overlap, double *sim, int *n_kept);
+
 typedef struct plm_pair_job {
     int64_t off1, off2, off_m;
     int32_t n1, n2;

@@ -119,6 +119,8 @@ class _Port:
             L.plo_bow_transform.argtypes = [_i32p, _i32p, _u8p, _f64p, _i32p, C.c_int, _u8p, C.c_int, C.c_size_t, u32p, _f64p]
             L.plo_bow_score.restype = C.c_double
             L.plo_bow_score.argtypes = [u32p, _f64p, C.c_int, u32p, _f64p, C.c_int]
+            L.plo_line_pair_filter.restype = C.c_int
+            L.plo_line_pair_filter.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, C.c_double, C.c_double, _u8p, _f64p, _f64p]
             L.plo_med_desc.restype = None
             L.plo_med_desc.argtypes = [_u8p, C.c_size_t, _f64p, _i32p, C.c_int, _i32p, _u8p, _f64p]
             self._lib = L
@@ -142,6 +144,19 @@ class _Port:
         i2, x2 = np.ascontiguousarray(v2[0], np.uint32), np.ascontiguousarray(v2[1], np.float64)
         return self.lib.plo_bow_score(i1.ctypes.data_as(u32p), x1.ctypes.data_as(_f64p), len(i1),
                                       i2.ctypes.data_as(u32p), x2.ctypes.data_as(_f64p), len(i2))
+
+    def line_pair_filter(self, ln1, ln2, m12, overlap_th=0.75, line_sim_th=0.75):
+        """lineSegmentOverlap + direction similarity per matched line pair -> (n_kept, keep, overlap, sim)."""
+        ln1 = np.ascontiguousarray(ln1, np.float32).reshape(-1, 4)
+        ln2 = np.ascontiguousarray(ln2, np.float32).reshape(-1, 4)
+        m, mp = _i32(m12)
+        n1 = len(m)
+        keep = np.zeros(max(n1, 1), np.uint8)
+        ov, sim = np.zeros(max(n1, 1), np.float64), np.zeros(max(n1, 1), np.float64)
+        n = self.lib.plo_line_pair_filter(ln1.ctypes.data_as(_f32p), n1, ln2.ctypes.data_as(_f32p), len(ln2), mp,
+                                          overlap_th, line_sim_th, keep.ctypes.data_as(_u8p), ov.ctypes.data_as(_f64p),
+                                          sim.ctypes.data_as(_f64p))
+        return n, keep[:n1], ov[:n1], sim[:n1]
 
     def med_desc(self, desc, dirs, obs_start):
         """MapPoint / MapLine::updateAverageDescDir over a batch of landmarks (src/mapFeatures.cpp:51-93,

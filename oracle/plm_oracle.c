@@ -884,3 +884,85 @@ PLO_API double plo_bow_score(const uint32_t *ids1, const double *vals1, int n1, 
     }
     return -score / 2.0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Opt-in geometric filter for matched line pairs (BASELINE config 2 "NNR line matching with overlap/angle
+ * filter"; SURVEY 8 note 6).  In this fork the temporal line matcher applies no geometric filter
+ * (stereoFrameHandler.cpp:182-207); the two tests below are the reference's own functions, evaluated per
+ * matched pair:
+ *   plo_line_segment_overlap  StereoFrame::lineSegmentOverlap (stvo-pl/src/stereoFrame.cpp:521-627): the
+ *       fraction of the observed segment covered by the other segment projected onto its line, with the
+ *       vertical (|dx| < 1) and horizontal (|dy| < 1) special cases; all double, float literals promoted.
+ *   direction similarity      |dot(normalize(e1 - s1), normalize(e2 - s2))| with dot / normalize of
+ *       stvo-pl/include/matching.h:39-48 and the test of matching.cpp:221 (`abs(dot) < lineSimTh` rejects,
+ *       so a NaN similarity passes).
+ * The reference's stereoFrame.cpp cannot be compiled here (OpenCV / line_descriptor), so this function is
+ * restated from the source only: parity for it is unpinned by a reference build.
+ */
+static double plo_overlap_from_lambdas(double lambda_s, double lambda_e)
+{
+    const double lambda_min = plo_min(lambda_s, lambda_e);
+    const double lambda_max = plo_max(lambda_s, lambda_e);
+    if (lambda_min < 0.f && lambda_max > 1.f) return 1.f;
+    if (lambda_max < 0.f || lambda_min > 1.f) return 0.f;
+    if (lambda_min < 0.f) return lambda_max;
+    if (lambda_max > 1.f) return 1.f - lambda_min;
+    return lambda_max - lambda_min;
+}
+
+PLO_API double plo_line_segment_overlap(const double spl_obs[2], const double epl_obs[2],
+                                        const double spl_proj[2], const double epl_proj[2])
+{
+    const double l0 = epl_obs[0] - spl_obs[0], l1 = epl_obs[1] - spl_obs[1];
+    if (fabs(spl_obs[0] - epl_obs[0]) < 1.0) { /* vertical lines, :526-554 */
+        const double lambda_s = (spl_proj[1] - spl_obs[1]) / l1;
+        const double lambda_e = (epl_proj[1] - spl_obs[1]) / l1;
+        return plo_overlap_from_lambdas(lambda_s, lambda_e);
+    }
+    if (fabs(spl_obs[1] - epl_obs[1]) < 1.0) { /* horizontal lines, :555-584 */
+        const double lambda_s = (spl_proj[0] - spl_obs[0]) / l0;
+        const double lambda_e = (epl_proj[0] - spl_obs[0]) / l0;
+        return plo_overlap_from_lambdas(lambda_s, lambda_e);
+    }
+    /* non-degenerate, :585-622: foot points of the other segment's endpoints on the observed line */
+    const double a = spl_obs[1] - epl_obs[1];
+    const double b = epl_obs[0] - spl_obs[0];
+    const double c = spl_obs[0] * epl_obs[1] - epl_obs[0] * spl_obs[1];
+    const double lxy = 1.f / (a * a + b * b);
+    const double sx = (b * (b * spl_proj[0] - a * spl_proj[1]) - a * c) * lxy;
+    const double ex = (b * (b * epl_proj[0] - a * epl_proj[1]) - a * c) * lxy;
+    const double lambda_s = (sx - spl_obs[0]) / l0;
+    const double lambda_e = (ex - spl_obs[0]) / l0;
+    return plo_overlap_from_lambdas(lambda_s, lambda_e);
+}
+
+/* ln1 / ln2: n x (sx, sy, ex, ey) float32.  keep[i1] = 1 iff m12[i1] in [0, n2), overlap > overlap_th and
+ * !(sim < line_sim_th); overlap / sim are written for every matched row (0 elsewhere).  Returns #kept. */
+PLO_API int plo_line_pair_filter(const float *ln1, int n1, const float *ln2, int n2, const int32_t *m12,
+                                 double overlap_th, double line_sim_th, uint8_t *keep, double *overlap,
+                                 double *sim)
+{
+    int kept = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        keep[i1] = 0;
+        overlap[i1] = 0.0;
+        sim[i1] = 0.0;
+        const int i2 = m12[i1];
+        if (i2 < 0 || i2 >= n2) continue;
+        const double so[2] = {ln1[4 * i1], ln1[4 * i1 + 1]}, eo[2] = {ln1[4 * i1 + 2], ln1[4 * i1 + 3]};
+        const double sp[2] = {ln2[4 * i2], ln2[4 * i2 + 1]}, ep[2] = {ln2[4 * i2 + 2], ln2[4 * i2 + 3]};
+        const double ov = plo_line_segment_overlap(so, eo, sp, ep);
+        double v[2] = {eo[0] - so[0], eo[1] - so[1]}, w[2] = {ep[0] - sp[0], ep[1] - sp[1]};
+        const double mv = sqrt(v[0] * v[0] + v[1] * v[1]), mw = sqrt(w[0] * w[0] + w[1] * w[1]);
+        v[0] /= mv; v[1] /= mv;
+        w[0] /= mw; w[1] /= mw;
+        const double s = fabs(v[0] * w[0] + v[1] * w[1]);
+        overlap[i1] = ov;
+        sim[i1] = s;
+        if (ov > overlap_th && !(s < line_sim_th)) {
+            keep[i1] = 1;
+            kept++;
+        }
+    }
+    return kept;
+}

@@ -108,6 +108,7 @@ SIGNATURES = {
                                            intp]),
     "plm_stereo_filter_lines": (C.c_int, [vp, f32p, C.c_int, f32p, C.c_int, i32p, C.c_double, C.c_double, C.c_double,
                                           C.c_double, u8p, f64p, intp]),
+    "plm_line_pair_filter": (C.c_int, [vp, f32p, C.c_int, f32p, C.c_int, i32p, C.c_double, C.c_double, u8p, f64p, f64p, intp]),
     "plm_batch_create": (C.c_int, [vp, C.POINTER(vp)]),
     "plm_batch_destroy": (C.c_int, [vp]),
     "plm_batch_set_match": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_float, C.c_int, vp, C.c_int64]),

@@ -117,4 +117,68 @@ __global__ void stereo_filter_lines_kernel(const float4 *__restrict__ ln_l, cons
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
 }
 
+// ---- opt-in geometric filter for matched line pairs (BASELINE config 2; SURVEY 8 note 6) ---------------------------
+
+__device__ __forceinline__ double overlap_from_lambdas(double lambda_s, double lambda_e) {
+    const double lambda_min = std_min(lambda_s, lambda_e);
+    const double lambda_max = std_max(lambda_s, lambda_e);
+    if (lambda_min < 0.0 && lambda_max > 1.0) return 1.0;
+    if (lambda_max < 0.0 || lambda_min > 1.0) return 0.0;
+    if (lambda_min < 0.0) return lambda_max;
+    if (lambda_max > 1.0) return __dsub_rn(1.0, lambda_min);
+    return __dsub_rn(lambda_max, lambda_min);
+}
+
+// StereoFrame::lineSegmentOverlap (stvo-pl/src/stereoFrame.cpp:521-627): fraction of the observed segment (so, eo)
+// covered by the other segment (sp, ep) projected onto its line; every product / sum rounded separately (the
+// reference is built without FMA contraction).
+__device__ __forceinline__ double line_segment_overlap(double sox, double soy, double eox, double eoy, double spx, double spy,
+                                                       double epx, double epy) {
+    const double l0 = __dsub_rn(eox, sox), l1 = __dsub_rn(eoy, soy);
+    if (fabs(__dsub_rn(sox, eox)) < 1.0) // vertical lines
+        return overlap_from_lambdas(__ddiv_rn(__dsub_rn(spy, soy), l1), __ddiv_rn(__dsub_rn(epy, soy), l1));
+    if (fabs(__dsub_rn(soy, eoy)) < 1.0) // horizontal lines
+        return overlap_from_lambdas(__ddiv_rn(__dsub_rn(spx, sox), l0), __ddiv_rn(__dsub_rn(epx, sox), l0));
+    const double a = __dsub_rn(soy, eoy), b = __dsub_rn(eox, sox);
+    const double c = __dsub_rn(__dmul_rn(sox, eoy), __dmul_rn(eox, soy));
+    const double lxy = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+    const double ac = __dmul_rn(a, c);
+    const double sx = __dmul_rn(__dsub_rn(__dmul_rn(b, __dsub_rn(__dmul_rn(b, spx), __dmul_rn(a, spy))), ac), lxy);
+    const double ex = __dmul_rn(__dsub_rn(__dmul_rn(b, __dsub_rn(__dmul_rn(b, epx), __dmul_rn(a, epy))), ac), lxy);
+    return overlap_from_lambdas(__ddiv_rn(__dsub_rn(sx, sox), l0), __ddiv_rn(__dsub_rn(ex, sox), l0));
+}
+
+// keep[i1] = matched && overlap > overlap_th && !(|cos| < line_sim_th)   (a NaN similarity passes, matching.cpp:221)
+__global__ void line_pair_filter_kernel(const float4 *__restrict__ ln1, int n1, const float4 *__restrict__ ln2, int n2,
+                                        const int32_t *__restrict__ m12, double overlap_th, double line_sim_th,
+                                        uint8_t *__restrict__ keep, double *__restrict__ overlap, double *__restrict__ sim,
+                                        int32_t *__restrict__ count) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    bool kept = false;
+    if (i1 < n1) {
+        double ov = 0.0, s = 0.0;
+        const int i2 = m12[i1];
+        if (i2 >= 0 && i2 < n2) {
+            const float4 o = ln1[i1], p = ln2[i2];
+            ov = line_segment_overlap(o.x, o.y, o.z, o.w, p.x, p.y, p.z, p.w);
+            // dot / normalize of stvo-pl/include/matching.h:39-48
+            double vx = __dsub_rn(double(o.z), double(o.x)), vy = __dsub_rn(double(o.w), double(o.y));
+            double wx = __dsub_rn(double(p.z), double(p.x)), wy = __dsub_rn(double(p.w), double(p.y));
+            const double mv = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+            const double mw = __dsqrt_rn(__dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)));
+            vx = __ddiv_rn(vx, mv);
+            vy = __ddiv_rn(vy, mv);
+            wx = __ddiv_rn(wx, mw);
+            wy = __ddiv_rn(wy, mw);
+            s = fabs(__dadd_rn(__dmul_rn(vx, wx), __dmul_rn(vy, wy)));
+            kept = ov > overlap_th && !(s < line_sim_th);
+        }
+        keep[i1] = kept ? 1 : 0;
+        overlap[i1] = ov;
+        sim[i1] = s;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, kept);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
+
 } // namespace plm

@@ -1198,6 +1198,44 @@ PLM_API int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int 
     return PLM_OK;
 }
 
+PLM_API int plm_line_pair_filter(plm_ctx *ctx, const float *ln1, int n1, const float *ln2, int n2, const int32_t *m12,
+                                 double overlap_th, double line_sim_th, uint8_t *keep, double *overlap, double *sim, int *n_kept) {
+    if (n1 < 0 || n2 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (!n_kept) return fail(PLM_E_INVALID, "null n_kept");
+    *n_kept = 0;
+    if (n1 == 0) return PLM_OK;
+    if (!ln1 || !m12 || !keep || !overlap || !sim || (n2 > 0 && !ln2)) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout L;
+    const size_t o_l1 = L.add(size_t(n1) * 16), o_l2 = L.add(size_t(std::max(n2, 1)) * 16), o_m = L.add(size_t(n1) * 4);
+    const size_t in_bytes = L.total;
+    const size_t o_ov = L.add(size_t(n1) * 8), o_sim = L.add(size_t(n1) * 8), o_keep = L.add(size_t(n1)), o_cnt = L.add(4);
+    if ((st = ctx->ensure_pinned(L.total)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    char *H = ctx->h_buf, *D = ctx->d_buf;
+    std::memcpy(H + o_l1, ln1, size_t(n1) * 16);
+    if (n2 > 0) std::memcpy(H + o_l2, ln2, size_t(n2) * 16);
+    std::memcpy(H + o_m, m12, size_t(n1) * 4);
+    CU_TRY(cudaMemcpyAsync(D, H, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemsetAsync(D + o_cnt, 0, 4, ctx->stream));
+    plm::line_pair_filter_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(
+        reinterpret_cast<const float4 *>(D + o_l1), n1, reinterpret_cast<const float4 *>(D + o_l2), n2,
+        reinterpret_cast<const int32_t *>(D + o_m), overlap_th, line_sim_th, reinterpret_cast<uint8_t *>(D + o_keep),
+        reinterpret_cast<double *>(D + o_ov), reinterpret_cast<double *>(D + o_sim), reinterpret_cast<int32_t *>(D + o_cnt));
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(H + o_ov, D + o_ov, L.total - o_ov, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(overlap, H + o_ov, size_t(n1) * 8);
+    std::memcpy(sim, H + o_sim, size_t(n1) * 8);
+    std::memcpy(keep, H + o_keep, size_t(n1));
+    int32_t cnt;
+    std::memcpy(&cnt, H + o_cnt, 4);
+    *n_kept = cnt;
+    return PLM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Map landmarks: MapPoint / MapLine::updateAverageDescDir (src/mapFeatures.cpp:51-93, :121-163)
 namespace {

@@ -272,3 +272,25 @@ def stereo_filter_lines(ln_l: np.ndarray, ln_r: np.ndarray, matches_12: Sequence
                                              float(Config.lsMinDispRatio), keep.ctypes.data_as(L.u8p),
                                              disp.ctypes.data_as(L.f64p), C.byref(n)), "stereo_filter_lines")
     return n.value, keep, disp
+
+
+def line_pair_filter(lines1: np.ndarray, lines2: np.ndarray, matches_12: Sequence[int], overlap_th: float = 0.75,
+                     line_sim_th: Optional[float] = None, ctx: Optional[Context] = None):
+    """Opt-in geometric filter for matched line pairs (BASELINE config 2): StereoFrame::lineSegmentOverlap
+    (stereoFrame.cpp:521-627) of line1[i1] against line2[m12[i1]] and the direction test of matchGrid (matching.cpp:221)
+    -> (n_kept, keep, overlap, sim).  line_sim_th defaults to Config.lineSimTh."""
+    ln1 = np.ascontiguousarray(lines1, np.float32).reshape(-1, 4)
+    ln2 = np.ascontiguousarray(lines2, np.float32).reshape(-1, 4)
+    m = np.ascontiguousarray(matches_12, np.int32)
+    n1 = len(m)
+    if len(ln1) != n1:
+        raise RuntimeError("[line_pair_filter] Each line needs a match entry!")
+    keep = np.zeros(n1, np.uint8)
+    overlap, sim = np.zeros(n1, np.float64), np.zeros(n1, np.float64)
+    n = C.c_int(0)
+    th = float(Config.lineSimTh if line_sim_th is None else line_sim_th)
+    L.check(L.load().plm_line_pair_filter(_h(ctx), ln1.ctypes.data_as(L.f32p), n1, ln2.ctypes.data_as(L.f32p), len(ln2),
+                                          m.ctypes.data_as(L.i32p), float(overlap_th), th, keep.ctypes.data_as(L.u8p),
+                                          overlap.ctypes.data_as(L.f64p), sim.ctypes.data_as(L.f64p), C.byref(n)),
+            "line_pair_filter")
+    return n.value, keep, overlap, sim
