@@ -100,13 +100,22 @@ def matchF2FPoints(prev_pdesc_l: np.ndarray, curr_pdesc_l: np.ndarray, ctx=None)
     return np.asarray(m12, np.int32)
 
 
-def matchF2FLines(prev_ldesc_l: np.ndarray, curr_ldesc_l: np.ndarray, ctx=None) -> np.ndarray:
-    """stereoFrameHandler.cpp:182-207: match(prev, curr, minRatio12L)."""
+def matchF2FLines(prev_ldesc_l: np.ndarray, curr_ldesc_l: np.ndarray, ctx=None, prev_lines_px: np.ndarray = None,
+                  curr_lines_px: np.ndarray = None, overlap_th: float = None) -> np.ndarray:
+    """stereoFrameHandler.cpp:182-207: match(prev, curr, minRatio12L).
+
+    The fork applies no geometric filter here.  Passing the two segment arrays (n x (sx, sy, ex, ey) pixels) and
+    ``overlap_th`` turns on the opt-in overlap / angle filter of BASELINE config 2 (M.line_pair_filter:
+    StereoFrame::lineSegmentOverlap + the lineSimTh direction test); filtered matches are set to -1."""
     if len(prev_ldesc_l) == 0 or len(curr_ldesc_l) == 0:
         return np.zeros(0, np.int32)
     m12: List[int] = []
     M.match(prev_ldesc_l, curr_ldesc_l, np.float32(M.Config.minRatio12L), m12, ctx=ctx)
-    return np.asarray(m12, np.int32)
+    out = np.asarray(m12, np.int32)
+    if overlap_th is not None and prev_lines_px is not None and curr_lines_px is not None:
+        _, keep, _, _ = M.line_pair_filter(prev_lines_px, curr_lines_px, out, overlap_th, ctx=ctx)
+        out = np.where(keep.astype(bool), out, -1).astype(np.int32)
+    return out
 
 
 def _grid_then_fallback(coords, desc1, grid, desc2, dirs2, ws, min_matches, nnr, n1_feats, n2_feats, ctx):
