@@ -476,9 +476,55 @@ def bow_scoring(ctx, cpu: bool = True) -> dict:
     return out
 
 
+def loop_closure_per_pair(ctx, cpu: bool = True) -> dict:
+    """Config 5 in the reference's own form (SURVEY 8d "Mode A"): isLoopClosure runs StVO::match per keyframe PAIR, each
+    with both ratio tests and its own mutual check (mapHandler.cpp:3325-3378).  One query keyframe (800 descriptors)
+    against every keyframe of a resident 2000-keyframe database in one batched launch; the reference's match() on one
+    core (its own two std::async threads) beside it."""
+    import torch
+    from pl_inertial_slam_b200.database import KeyframeDB
+    n_kf, per = 2000, 800
+    rng = np.random.default_rng(synth.SEED0 + 55)
+    rows = synth.rand_desc(rng, n_kf * per)
+    kf_start = np.arange(n_kf + 1, dtype=np.int64) * per
+    db = KeyframeDB(rows, kf_start, device=torch.cuda.current_device(), q_cap=per, ctx=ctx)
+    q = synth.flip_bits(rng, rows[77 * per:78 * per], 0.05)      # revisits keyframe 77
+    counts, _ = db.match_all(q, 0.9, True)
+    assert int(np.argmax(counts)) == 77
+    launches0 = ctx.launch_count
+    reps = 5
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        db.batch.run()
+    ctx.synchronize()
+    dev_ms = (time.perf_counter() - t0) / reps * 1e3
+    call_ms = _median_ms(lambda: db.match_all(q, 0.9, True), reps=5, warm=1)
+    pairs = float(n_kf) * per * per
+    out = {"keyframes": n_kf, "descriptors_per_kf": per, "device_ms": dev_ms, "host_call_ms": call_ms,
+           "keyframe_pairs_per_s": n_kf / (dev_ms * 1e-3), "unique_pairs_per_s": pairs / (dev_ms * 1e-3),
+           "reference_equivalent_pairs_per_s": 2 * pairs / (dev_ms * 1e-3), "best_match_count": int(counts.max()),
+           "gpu_launches": (ctx.launch_count - launches0) // (reps + 6),
+           "note": "device_ms = kernels of one query against all keyframes (both directions + mutual check per pair), "
+                   "database resident; host_call_ms adds the query upload and the read-back of the 2000 counts"}
+    if cpu:
+        import oracle
+        eng = oracle.ref if oracle.ref.available() else oracle.port
+        m = 20
+        t0 = time.perf_counter()
+        for j in range(m):
+            eng.match(q, rows[j * per:(j + 1) * per], np.float32(0.9), True)
+        dt = (time.perf_counter() - t0) / m
+        out["cpu_baseline"] = {"keyframe_pairs_per_s": 1.0 / dt, "reference_equivalent_pairs_per_s": 2.0 * per * per / dt,
+                               "cores": 2, "kind": "reference" if oracle.ref.available() else "port",
+                               "sample": f"{m} keyframe pairs, StVO::match with its two std::async threads"}
+    return out
+
+
 def run(ctx, args) -> dict:
     out = {"frame_latency": frame_latency(ctx)}
-    for name, fn in (("map_landmarks", map_landmarks), ("bow_scoring", bow_scoring)):
+    for name, fn in (("loop_closure_per_pair", loop_closure_per_pair), ("map_landmarks", map_landmarks),
+                     ("bow_scoring", bow_scoring)):
         try:
             out[name] = fn(ctx, cpu=not args.no_cpu_baseline)
         except Exception as e:  # noqa: BLE001

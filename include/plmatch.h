@@ -149,10 +149,6 @@ int plm_stereo_filter_lines(plm_ctx *ctx, const float *ln_l, int n1, const float
                             double stereo_overlap_th, double ls_min_disp_ratio, uint8_t *keep,
                             double *disp_se, int *n_kept);
 
-/* ---- batched replay (one launch per stage over a frame arena) -------------------------------- */
-
-/* One brute-force job: rows [off1, off1+n1) x rows [off2, off2+n2) of the descriptor arena;
- * results land at m12_arena[off_m .. off_m + n1). */
 /* Opt-in geometric filter for matched line pairs (BASELINE config 2 "NNR line matching with overlap/angle filter").
  * The fork's temporal line matcher applies none (stereoFrameHandler.cpp:182-207); this evaluates the reference's own
  * two tests per matched pair (i1, m12[i1]):
@@ -163,6 +159,10 @@ int plm_stereo_filter_lines(plm_ctx *ctx, const float *ln_l, int n1, const float
 int plm_line_pair_filter(plm_ctx *ctx, const float *ln1, int n1, const float *ln2, int n2, const int32_t *m12,
                          double overlap_th, double line_sim_th, uint8_t *keep, double *overlap, double *sim, int *n_kept);
 
+/* ---- batched replay (one launch per stage over a frame arena) -------------------------------- */
+
+/* One brute-force job: rows [off1, off1+n1) x rows [off2, off2+n2) of the descriptor arena;
+ * results land at m12_arena[off_m .. off_m + n1). */
 typedef struct plm_pair_job {
     int64_t off1, off2, off_m;
     int32_t n1, n2;
@@ -195,6 +195,14 @@ int plm_batch_destroy(plm_batch *b);
  * m12_arena (n_m entries) is the IN value of every job's match vector. */
 int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_rows, const plm_pair_job *jobs,
                         int n_jobs, float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m);
+
+/* Same with the descriptor arena ALREADY RESIDENT on the context's device (used in place, never copied; it must stay
+ * valid and its rows may be rewritten between runs): the per-keyframe-pair form of loop-closure matching -- StVO::match
+ * of one query keyframe against every keyframe of a resident database (isLoopClosure, mapHandler.cpp:3325-3378, at
+ * scale; SURVEY 8d "Mode A").  Prepare once with the query rows in a fixed slot of the arena, then per query: rewrite
+ * the slot, plm_batch_run, plm_batch_fetch.  m12_arena may be NULL: every match vector then starts at -1. */
+int plm_batch_set_match_dev(plm_batch *b, const void *arena_dev, int64_t n_rows, const plm_pair_job *jobs,
+                            int n_jobs, float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m);
 
 /* StVO::matchGrid (points or lines per job) for every job, one CTA per job. */
 int plm_batch_set_match_grid(plm_batch *b, const uint8_t *arena, int64_t n_rows, const int32_t *coords,

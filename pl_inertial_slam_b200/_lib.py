@@ -112,6 +112,7 @@ SIGNATURES = {
     "plm_batch_create": (C.c_int, [vp, C.POINTER(vp)]),
     "plm_batch_destroy": (C.c_int, [vp]),
     "plm_batch_set_match": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_float, C.c_int, vp, C.c_int64]),
+    "plm_batch_set_match_dev": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_float, C.c_int, vp, C.c_int64]),
     "plm_batch_set_match_grid": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp,
                                            C.c_int64, C.c_int, C.c_int, vp, C.c_int, C.c_double, C.c_double, C.c_int,
                                            vp, C.c_int64]),

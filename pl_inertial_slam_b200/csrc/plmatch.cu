@@ -2062,11 +2062,32 @@ namespace {
 constexpr int BATCH_THREADS = 64;
 }
 
+namespace {
+int batch_set_match_impl(plm_batch *b, const uint8_t *arena, const void *arena_dev, int64_t n_rows, const plm_pair_job *jobs,
+                         int n_jobs, float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m);
+} // namespace
+
 PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_rows, const plm_pair_job *jobs, int n_jobs,
                                 float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m) {
+    if (n_rows > 0 && !arena) return fail(PLM_E_INVALID, "null pointer");
+    if (n_m > 0 && !m12_arena) return fail(PLM_E_INVALID, "null pointer");
+    return batch_set_match_impl(b, arena, nullptr, n_rows, jobs, n_jobs, nnr, best_lr, m12_arena, n_m);
+}
+
+PLM_API int plm_batch_set_match_dev(plm_batch *b, const void *arena_dev, int64_t n_rows, const plm_pair_job *jobs, int n_jobs,
+                                    float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m) {
+    if (n_rows > 0 && !arena_dev) return fail(PLM_E_INVALID, "null pointer");
+    if (reinterpret_cast<uintptr_t>(arena_dev) & 15) return fail(PLM_E_INVALID, "device descriptor pointers must be 16-byte aligned");
+    return batch_set_match_impl(b, nullptr, arena_dev ? arena_dev : reinterpret_cast<const void *>(16), n_rows, jobs, n_jobs, nnr,
+                                best_lr, m12_arena, n_m);
+}
+
+namespace {
+int batch_set_match_impl(plm_batch *b, const uint8_t *arena, const void *arena_dev, int64_t n_rows, const plm_pair_job *jobs,
+                         int n_jobs, float nnr, int best_lr, const int32_t *m12_arena, int64_t n_m) {
     if (!b) return fail(PLM_E_INVALID, "null batch");
     if (n_rows < 0 || n_jobs < 0 || n_m < 0) return fail(PLM_E_INVALID, "negative size");
-    if ((n_rows > 0 && !arena) || (n_jobs > 0 && !jobs) || (n_m > 0 && !m12_arena)) return fail(PLM_E_INVALID, "null pointer");
+    if (n_jobs > 0 && !jobs) return fail(PLM_E_INVALID, "null pointer");
     plm_ctx *ctx = b->ctx;
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
@@ -2146,7 +2167,7 @@ PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_ro
     }
 
     Layout L;
-    const size_t o_arena = L.add(size_t(n_rows) * 32);
+    const size_t o_arena = L.add(arena_dev ? 0 : size_t(n_rows) * 32); // a resident arena is used in place
     b->work_bytes = align_up(size_t(n_m) * 4, 16) + size_t(n_jobs) * 4;
     b->o_work = L.add(b->work_bytes);
     b->o_init = L.add(b->work_bytes);
@@ -2164,7 +2185,7 @@ PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_ro
     int32_t *d_m12 = reinterpret_cast<int32_t *>(D + b->o_work);
     int32_t *d_counts = reinterpret_cast<int32_t *>(D + b->o_work + align_up(size_t(n_m) * 4, 16));
     int32_t *d_m21 = reinterpret_cast<int32_t *>(D + b->o_m21);
-    const uint4 *d_arena = reinterpret_cast<const uint4 *>(D + o_arena);
+    const uint4 *d_arena = arena_dev ? static_cast<const uint4 *>(arena_dev) : reinterpret_cast<const uint4 *>(D + o_arena);
     for (size_t i = 0; i < tasks.size(); ++i) {
         plm::KnnTask &t = tasks[i];
         const bool dir = t.pad_ != 0;
@@ -2185,8 +2206,10 @@ PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_ro
     // uploads: arenas straight from the caller's memory, tables through the pinned staging block
     const size_t tbl_bytes = L.total - b->o_tasks; // generous upper bound of the table region
     (void)tbl_bytes;
+    // without an IN vector every match vector starts at -1: filled on the device, only the counts are staged
+    const size_t counts_off = align_up(size_t(n_m) * 4, 16);
     Layout S;
-    const size_t s_init = S.add(b->work_bytes);
+    const size_t s_init = S.add(m12_arena ? b->work_bytes : size_t(n_jobs) * 4);
     const size_t s_tasks = S.add(tasks.size() * sizeof(plm::KnnTask));
     const size_t s_cta = S.add(cta_map.size() * sizeof(int4));
     const size_t s_merge = S.add(merge_map.size() * sizeof(int2));
@@ -2194,16 +2217,25 @@ PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_ro
     const size_t s_xmap = S.add(xmap.size() * sizeof(int2));
     if ((st = ctx->ensure_pinned(S.total)) != PLM_OK) return st;
     char *H = ctx->h_buf;
-    if (n_m > 0) std::memcpy(H + s_init, m12_arena, size_t(n_m) * 4);
-    if (n_jobs > 0) std::memcpy(H + s_init + align_up(size_t(n_m) * 4, 16), counts_init.data(), size_t(n_jobs) * 4);
+    if (m12_arena) {
+        if (n_m > 0) std::memcpy(H + s_init, m12_arena, size_t(n_m) * 4);
+        if (n_jobs > 0) std::memcpy(H + s_init + counts_off, counts_init.data(), size_t(n_jobs) * 4);
+    } else if (n_jobs > 0) {
+        std::memcpy(H + s_init, counts_init.data(), size_t(n_jobs) * 4);
+    }
     if (!tasks.empty()) std::memcpy(H + s_tasks, tasks.data(), tasks.size() * sizeof(plm::KnnTask));
     if (!cta_map.empty()) std::memcpy(H + s_cta, cta_map.data(), cta_map.size() * sizeof(int4));
     if (!merge_map.empty()) std::memcpy(H + s_merge, merge_map.data(), merge_map.size() * sizeof(int2));
     if (!xjobs.empty()) std::memcpy(H + s_xjobs, xjobs.data(), xjobs.size() * sizeof(plm::XJob));
     if (!xmap.empty()) std::memcpy(H + s_xmap, xmap.data(), xmap.size() * sizeof(int2));
     cudaStream_t s = ctx->stream;
-    if (n_rows > 0) CU_TRY(cudaMemcpyAsync(D + o_arena, arena, size_t(n_rows) * 32, cudaMemcpyHostToDevice, s));
-    if (b->work_bytes) CU_TRY(cudaMemcpyAsync(D + b->o_init, H + s_init, b->work_bytes, cudaMemcpyHostToDevice, s));
+    if (n_rows > 0 && !arena_dev) CU_TRY(cudaMemcpyAsync(D + o_arena, arena, size_t(n_rows) * 32, cudaMemcpyHostToDevice, s));
+    if (m12_arena) {
+        if (b->work_bytes) CU_TRY(cudaMemcpyAsync(D + b->o_init, H + s_init, b->work_bytes, cudaMemcpyHostToDevice, s));
+    } else {
+        if (n_m > 0) CU_TRY(cudaMemsetAsync(D + b->o_init, 0xFF, size_t(n_m) * 4, s));
+        if (n_jobs > 0) CU_TRY(cudaMemcpyAsync(D + b->o_init + counts_off, H + s_init, size_t(n_jobs) * 4, cudaMemcpyHostToDevice, s));
+    }
     if (!tasks.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_tasks, H + s_tasks, tasks.size() * sizeof(plm::KnnTask), cudaMemcpyHostToDevice, s));
     if (!cta_map.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_cta_map, H + s_cta, cta_map.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
     if (!merge_map.empty()) CU_TRY(cudaMemcpyAsync(D + b->o_merge_map, H + s_merge, merge_map.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
@@ -2219,10 +2251,11 @@ PLM_API int plm_batch_set_match(plm_batch *b, const uint8_t *arena, int64_t n_ro
     b->n_slice_ctas = static_cast<int>(cta_map.size());
     b->n_merge_ctas = static_cast<int>(merge_map.size());
     b->n_x_ctas = static_cast<int>(xmap.size());
-    b->h2d = static_cast<int64_t>(size_t(n_rows) * 32 + S.total);
+    b->h2d = static_cast<int64_t>((arena_dev ? 0 : size_t(n_rows) * 32) + S.total);
     b->d2h = static_cast<int64_t>(size_t(n_m) * 4 + size_t(n_jobs) * 4);
     return PLM_OK;
 }
+} // namespace
 
 PLM_API int plm_batch_set_match_grid(plm_batch *b, const uint8_t *arena, int64_t n_rows, const int32_t *coords,
                                      int64_t n_coords, const int32_t *cell_start, int64_t n_cell_start,

@@ -371,6 +371,60 @@ class ShardedDescriptorDB:
         return count, m12
 
 
+class KeyframeDB:
+    """Loop-closure matching per keyframe pair against a resident keyframe database (SURVEY 8d "Mode A"):
+    MapHandler::isLoopClosure runs StVO::match(kf0.desc, kf1.desc) for ONE candidate pair (mapHandler.cpp:3325-3378,
+    each pair with its own ratio tests and mutual check); here one query keyframe is matched against EVERY keyframe of
+    the database in one batched launch (plm_batch_set_match_dev over the resident arena).  For several GPUs give every
+    rank a contiguous range of keyframes: the pairs are independent, only the per-keyframe counts are gathered.
+
+    ``rows``: all descriptors of the database keyframes back to back (n x 32 uint8), ``kf_start``: n_kf + 1 row offsets;
+    ``q_cap``: the largest query keyframe (rows reserved behind the database for the query slot)."""
+
+    def __init__(self, rows, kf_start, device: int = 0, q_cap: int = 2048, ctx: Optional[Context] = None):
+        from .replay import MatchBatch
+        self.ctx = ctx if ctx is not None else Context(device)
+        dev = torch.device("cuda", device)
+        rows_t = torch.as_tensor(rows)
+        self.n_rows = int(rows_t.shape[0])
+        self.q_cap = int(q_cap)
+        self.kf_start = np.ascontiguousarray(kf_start, np.int64)
+        self.n_kf = len(self.kf_start) - 1
+        self.arena = torch.zeros((self.n_rows + self.q_cap, 32), dtype=torch.uint8, device=dev)
+        self.arena[: self.n_rows] = rows_t.to(dev)
+        self.batch = MatchBatch(self.ctx)
+        self._prepared = None      # (nq, nnr, best_lr) the job tables were built for
+
+    def _prepare(self, nq: int, nnr: float, best_lr: bool) -> None:
+        if self._prepared == (nq, nnr, best_lr):
+            return
+        jobs = np.zeros(self.n_kf, L.PAIR_JOB_DTYPE)
+        jobs["off1"] = self.n_rows                             # the query slot
+        jobs["n1"] = nq
+        jobs["off2"] = self.kf_start[:-1]
+        jobs["n2"] = np.diff(self.kf_start)
+        jobs["off_m"] = np.arange(self.n_kf, dtype=np.int64) * nq
+        self.batch.set_match_dev(self.arena, jobs, nnr, best_lr, self.n_kf * nq)
+        self._prepared = (nq, nnr, best_lr)
+
+    def match_all(self, query, nnr: float, best_lr: bool = True, want_matches: bool = False):
+        """StVO::match(query, keyframe k) for every k -> counts int32[n_kf] (INT32_MIN where the reference would be
+        UB: a keyframe with fewer than 2 descriptors) and, with want_matches, the match vectors int32[n_kf, nq]."""
+        q = torch.as_tensor(query)
+        nq = int(q.shape[0])
+        if nq > self.q_cap:
+            raise ValueError("query keyframe larger than q_cap")
+        self._prepare(nq, float(np.float32(nnr)), bool(best_lr))
+        self.ctx.synchronize()                                  # earlier runs have finished reading the slot
+        self.arena[self.n_rows: self.n_rows + nq] = q.to(self.arena.device)
+        torch.cuda.current_stream(self.arena.device).synchronize()
+        self.batch.run()
+        if want_matches:
+            m12, counts = self.batch.fetch()
+            return counts, m12.reshape(self.n_kf, nq)
+        return self.batch.fetch_counts(), None
+
+
 class ShardedMap:
     """The local map as the row-sharded QUERY side (desc1) of matchMap2KF* (config 4).
 

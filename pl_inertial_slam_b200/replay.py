@@ -39,6 +39,15 @@ class MatchBatch:
                                              C.c_float(nnr), int(bool(best_lr)), self._vp(m12_arena), len(m12_arena)),
                 "plm_batch_set_match")
 
+    def set_match_dev(self, arena_dev, jobs: np.ndarray, nnr: float, best_lr: bool, n_m: int, m12_arena=None) -> None:
+        """plm_batch_set_match_dev: the descriptor arena is a resident torch CUDA tensor, used in place."""
+        assert jobs.dtype == L.PAIR_JOB_DTYPE and arena_dev.is_cuda and arena_dev.is_contiguous()
+        self.n_jobs, self.n_m = len(jobs), int(n_m)
+        self._arena_ref = arena_dev           # keep the tensor alive as long as the batch uses it
+        L.check(self.lib.plm_batch_set_match_dev(self._h, self._vp(arena_dev), int(arena_dev.shape[0]), self._vp(jobs), len(jobs),
+                                                 C.c_float(nnr), int(bool(best_lr)), self._vp(m12_arena), int(n_m)),
+                "plm_batch_set_match_dev")
+
     def set_match_grid(self, arena, coords, cell_start, cell_items, dirs2, rows: int, cols: int, jobs: np.ndarray,
                        ratio: float, line_sim_th: float, best_lr: bool, m12_arena) -> None:
         assert jobs.dtype == L.GRID_JOB_DTYPE
@@ -52,6 +61,12 @@ class MatchBatch:
 
     def run(self) -> None:
         L.check(self.lib.plm_batch_run(self._h), "plm_batch_run")
+
+    def fetch_counts(self) -> np.ndarray:
+        """Only the per-job return values (the match vectors stay on the device)."""
+        counts = np.empty(self.n_jobs, np.int32)
+        L.check(self.lib.plm_batch_fetch(self._h, C.c_void_p(0), self._vp(counts)), "plm_batch_fetch")
+        return counts
 
     def fetch(self, m12_out=None, counts_out=None) -> Tuple[np.ndarray, np.ndarray]:
         m12 = np.empty(self.n_m, np.int32) if m12_out is None else m12_out

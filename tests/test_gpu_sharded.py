@@ -225,3 +225,33 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
     for r, o in enumerate(ranks):
         plm_lib.plm_peer_free(o.ctx.handle, gbufs[r])
         plm_lib.plm_peer_free(o.ctx.handle, bufs[r])
+
+
+def test_keyframe_db_mode_a(plm_lib):
+    """Per-keyframe-pair loop-closure matching against a resident database (plm_batch_set_match_dev): StVO::match of
+    one query keyframe against every keyframe, each pair with its own mutual check, against the restatement."""
+    from pl_inertial_slam_b200.database import KeyframeDB
+    rng = np.random.default_rng(31)
+    sizes = rng.integers(30, 90, 40)
+    sizes[3], sizes[17] = 1, 0                                  # the reference would be UB / throw: INT32_MIN
+    kf_start = np.concatenate([[0], np.cumsum(sizes)])
+    rows = synth.rand_desc(rng, int(kf_start[-1]))
+    db = KeyframeDB(rows, kf_start, device=0, q_cap=128)
+    for trial, nq in enumerate((64, 64, 90, 2)):
+        q = synth.rand_desc(rng, nq)
+        k = 5 + trial                                           # the query revisits keyframe k
+        m = min(nq, sizes[k])
+        q[:m] = synth.flip_bits(rng, rows[kf_start[k]:kf_start[k] + m], 0.05)
+        for best_lr in (True, False):
+            counts, m12 = db.match_all(q, 0.9, best_lr, want_matches=True)
+            for j in range(len(sizes)):
+                d2 = rows[kf_start[j]:kf_start[j + 1]]
+                if len(d2) < 2 or (best_lr and nq < 2):
+                    assert counts[j] == np.iinfo(np.int32).min
+                    continue
+                n_o, m_o = port.match(q, d2, np.float32(0.9), best_lr)
+                assert counts[j] == n_o and (m12[j] == m_o).all(), (trial, best_lr, j)
+            c2, _ = db.match_all(q, 0.9, best_lr)
+            assert (c2 == counts).all()
+            if m >= 20:
+                assert counts[k] == counts[counts > np.iinfo(np.int32).min].max()   # the revisited keyframe wins
