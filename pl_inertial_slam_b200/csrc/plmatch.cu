@@ -387,11 +387,6 @@ PLM_API int plm_ctx_create(int device, plm_ctx **out) {
 }
 
 PLM_API int plm_ctx_destroy(plm_ctx *ctx) {
-    if (ctx && ctx->d_aux) {
-        cudaSetDevice(ctx->device);
-        cudaFree(ctx->d_aux);
-        ctx->d_aux = nullptr;
-    }
     if (!ctx) return PLM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) {
@@ -399,6 +394,7 @@ PLM_API int plm_ctx_destroy(plm_ctx *ctx) {
         cudaStreamDestroy(ctx->own_stream);
     }
     if (ctx->d_buf) cudaFree(ctx->d_buf);
+    if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
     if (g_tls.ctx == ctx) g_tls.ctx = nullptr;
     delete ctx;
