@@ -6,14 +6,23 @@
  * and there only as the checker (or the CPU arm), never as the thing shipped.
  *
  * Parity status: the reference holds no golden vectors / known-answer tests for this path
- * (SURVEY.md section 4).  This restatement is therefore pinned against the reference ITSELF:
- * oracle/_ref/libplref.so is /root/reference/stvo-pl/src/{matching,gridStructure,lineIterator}.cpp
- * compiled unmodified (oracle/Makefile) and tests/test_oracle_vs_ref.py compares the two on
- * random + tie-stress inputs; tests/golden/ holds vectors generated from that build
- * (tools/make_golden.py).  The one third-party piece absent from /root/reference is
- * cv::BFMatcher::knnMatch (OpenCV 3.3, features2d; call site matching.cpp:47-48): its K=2
- * batchDistance insertion rule is restated in plo_knn2() and cross-checked against the
- * in-container cv2 4.13 wheel (tests/test_oracle_vs_ref.py::test_knn2_vs_cv2).
+ * (SURVEY.md section 4).  This restatement is therefore pinned against the reference ITSELF where its
+ * sources compile here (oracle/Makefile, outputs in oracle/_ref/):
+ *   - libplref.so = /root/reference/stvo-pl/src/{matching,gridStructure,lineIterator}.cpp and
+ *     /root/reference/src/mapFeatures.cpp compiled unmodified  -> plo_hamming256, plo_match*, plo_match_grid*,
+ *     plo_line_coords, plo_med_desc (tests/test_oracle.py, tests/test_mapfeatures.py);
+ *   - libplref_dbow.so = the reference's vendored DBoW2 (3rdparty/DBoW2) compiled unmodified
+ *     -> plo_bow_word, plo_bow_transform, plo_bow_score (tests/test_bow.py);
+ *   tests/golden/ holds vectors generated from those builds (tools/make_golden.py) for machines without
+ *   /root/reference.
+ * PARITY UNPINNED (restated from the source only, no reference build possible here):
+ *   - cv::BFMatcher::knnMatch (OpenCV 3.3, features2d; call site matching.cpp:47-48) is not in
+ *     /root/reference: its K=2 batchDistance insertion rule is restated in plo_knn2() and cross-checked
+ *     against the in-container cv2 4.13 wheel (tests/test_oracle.py::test_knn2_vs_cv2);
+ *   - the stereo drivers and gates of stvo-pl/src/stereoFrame.cpp (plo_stereo_*, plo_csr_from_*,
+ *     plo_line_overlap_stereo, plo_line_segment_overlap / plo_line_pair_filter): stereoFrame.cpp needs
+ *     OpenCV and line_descriptor to compile; the restatements are cross-checked against independent numpy
+ *     forms in the tests.
  *
  * Every function cites the reference lines it follows (paths relative to /root/reference).
  */
