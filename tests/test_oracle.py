@@ -175,3 +175,64 @@ def test_stereo_filter_port_properties():
     assert port.lib.plo_line_overlap_stereo(0.0, 10.0, 0.0, 10.0, 0.1) == 1.0
     assert port.lib.plo_line_overlap_stereo(0.0, 10.0, 20.0, 30.0, 0.1) == 0.0
     assert port.lib.plo_line_overlap_stereo(5.0, 5.05, 20.0, 30.0, 0.1) == 1.0  # horizontal: untouched
+
+
+def _np_min(a, b):   # std::min(a, b) = (b < a) ? b : a
+    return np.where(b < a, b, a)
+
+
+def _np_max(a, b):   # std::max(a, b) = (a < b) ? b : a
+    return np.where(a < b, b, a)
+
+
+def numpy_stereo_line_gates(ln_l, ln_r, m12, min_disp, horiz_th, overlap_th, ratio_th):
+    """Independent vectorised form of stereoFrame.cpp:359-385 + :416-426 + :484-519 (float64, numpy never contracts to
+    FMA): endpoint interpolation with the reference's quirk (sp_r is overwritten before ep_r is interpolated)."""
+    n2 = len(ln_r)
+    ok = (m12 >= 0) & (m12 < n2)
+    j = np.where(ok, m12, 0)
+    spl_x, spl_y, epl_x, epl_y = ln_l.astype(np.float64).T
+    spr_x, spr_y, epr_x, epr_y = ln_r.astype(np.float64)[j].T
+    with np.errstate(all="ignore"):
+        # lineSegmentOverlapStereo on the y coordinates
+        sln, eln = _np_min(spl_y, epl_y), _np_max(spl_y, epl_y)
+        spn, epn = _np_min(spr_y, epr_y), _np_max(spr_y, epr_y)
+        length = eln - spn
+        inner = np.where((epn > eln) & (spn < sln), eln - sln, _np_min(eln, epn) - _np_max(sln, spn))
+        ov = np.where((epn < sln) | (spn > eln), 0.0, inner)
+        ov = np.where(length > np.float64(np.float32(0.01)), ov / length, 0.0)
+        ov = np.where(ov > 1.0, 1.0, ov)
+        overlap = np.where(np.abs(epl_y - spl_y) > horiz_th, ov, 1.0)
+        # endpoint interpolation: sp_r first, then ep_r with the UPDATED sp_r
+        sx = (spr_x * (spl_y - epr_y) + epr_x * (spr_y - spl_y)) / (spr_y - epr_y)
+        sy = spl_y
+        ex = (sx * (epl_y - epr_y) + epr_x * (sy - epl_y)) / (sy - epr_y)
+        ey = epl_y
+        disp_s, disp_e = spl_x - sx, epl_x - ex
+        bad = _np_min(disp_s, disp_e) / _np_max(disp_s, disp_e) < ratio_th
+        disp_s, disp_e = np.where(bad, -1.0, disp_s), np.where(bad, -1.0, disp_e)
+        keep = ok & (disp_s >= min_disp) & (disp_e >= min_disp) & (np.abs(spl_y - epl_y) > horiz_th) \
+            & (np.abs(sy - ey) > horiz_th) & (overlap > overlap_th)
+    return keep.astype(np.uint8), np.where(ok, disp_s, 0.0), np.where(ok, disp_e, 0.0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_stereo_line_gates_port_vs_numpy(seed):
+    """plo_stereo_filter_lines (restated from stereoFrame.cpp, which cannot be compiled here) against an independent
+    numpy form, bit for bit on the disparities."""
+    sp = synth.make_stereo_pair(synth.SEED0 + 30 + seed)
+    rng = np.random.default_rng(seed)
+    n1, n2 = len(sp.ln_l), len(sp.ln_r)
+    m12 = np.arange(n1, dtype=np.int32) % n2
+    m12[rng.random(n1) < 0.2] = -1
+    wrong = rng.random(n1) < 0.2
+    m12[wrong] = rng.integers(0, n2, int(wrong.sum()))            # wrong partners: every reject branch occurs
+    ln_l, ln_r = sp.ln_l.copy(), sp.ln_r.copy()
+    ln_l[:10, 3] = ln_l[:10, 1] + 0.05                            # near-horizontal segments
+    n, keep, disp = port.stereo_filter_lines(ln_l, ln_r, m12, 1.0, 0.1, 0.75, 0.7)
+    k2, ds, de = numpy_stereo_line_gates(ln_l, ln_r, m12, 1.0, 0.1, 0.75, 0.7)
+    assert np.array_equal(keep, k2) and n == int(k2.sum()) and 0 < n < (m12 >= 0).sum()
+    fin = np.isfinite(ds) & np.isfinite(de)
+    assert np.array_equal(disp[fin, 0].view(np.uint64), ds[fin].view(np.uint64))
+    assert np.array_equal(disp[fin, 1].view(np.uint64), de[fin].view(np.uint64))
+    assert np.array_equal(np.isnan(disp[:, 0]), np.isnan(ds))
