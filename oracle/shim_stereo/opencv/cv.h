@@ -1,0 +1,2 @@
+#include <opencv2/core.hpp>
+#include <opencv2/features2d.hpp>

@@ -86,6 +86,35 @@ __device__ __forceinline__ int hamming256_csa4(const Desc &a, const uint4 &blo, 
     return static_cast<int>(imad(__popc(ce), 4u, imad(__popc(se), 2u, imad(__popc(sc), 1u, __popc(x7)))));
 }
 
+// Thirteen-LOP3 form.  Both descriptors are first mapped through the same invertible GF(2)-linear transform
+//     T(w) = (w0, w1, w0^w1^w2, w3, w4, w3^w4^w5, w0^w1^w2^w3^w4^w5^w6, w7)
+// (the query once per thread, a train row once per shared-memory stage, i.e. amortised over >= 64 pairs).  With
+// x_k = a_k ^ b_k, the eight xors y = T(a) ^ T(b) then ARE x0, x1, sa = x0^x1^x2, x3, x4, sb = x3^x4^x5,
+// sc = sa^sb^x6 and x7: the three "sum" outputs of the first carry-save level cost nothing, and each carry is one
+// LOP3 of (two addends, their sum): maj(p, q, r) with r = p^q^s is the 3-input function 0xD4 of (p, q, s).
+// 8 xor + 3 carries + 1 full adder on the carries = 13 LOP3 + 4 POPC per pair, same integer result as
+// StVO::distance (stvo-pl/src/matching.cpp:93-109).
+__device__ __forceinline__ uint32_t lop3_carry_from_sum(uint32_t p, uint32_t q, uint32_t s) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(r) : "r"(p), "r"(q), "r"(s));
+    return r;
+}
+__device__ __forceinline__ void desc_transform13(uint4 &lo, uint4 &hi) {
+    lo.z = lop3_xor3(lo.x, lo.y, lo.z);
+    hi.y = lop3_xor3(lo.w, hi.x, hi.y);
+    hi.z = lop3_xor3(lo.z, hi.y, hi.z);
+}
+// a, blo, bhi are TRANSFORMED descriptors.
+__device__ __forceinline__ int hamming256_t13(const Desc &a, const uint4 &blo, const uint4 &bhi) {
+    const uint32_t x0 = a.lo.x ^ blo.x, x1 = a.lo.y ^ blo.y, sa = a.lo.z ^ blo.z, x3 = a.lo.w ^ blo.w;
+    const uint32_t x4 = a.hi.x ^ bhi.x, sb = a.hi.y ^ bhi.y, sc = a.hi.z ^ bhi.z, x7 = a.hi.w ^ bhi.w;
+    const uint32_t ca = lop3_carry_from_sum(x0, x1, sa);
+    const uint32_t cb = lop3_carry_from_sum(x3, x4, sb);
+    const uint32_t cc = lop3_carry_from_sum(sa, sb, sc);
+    const uint32_t se = lop3_xor3(ca, cb, cc), ce = lop3_maj(ca, cb, cc);
+    return static_cast<int>(imad(__popc(ce), 4u, imad(__popc(se), 2u, imad(__popc(sc), 1u, __popc(x7)))));
+}
+
 // Packed 64-bit key: (distance << 32) | global train index.  Unsigned min == (dist, idx) lexicographic.
 __device__ __forceinline__ unsigned long long make_key64(uint32_t dist, uint32_t idx) {
     return (static_cast<unsigned long long>(dist) << 32) | idx;

@@ -62,6 +62,16 @@ struct KnnTaskPair {
 //            second-best distance.  Train rows are scanned in increasing index order, so a row that
 //            merely ties the second best can never displace it (its key is larger) and the strict
 //            test is exact.  For long scans the update path is almost never taken.
+// VARIANT 3: as 2 with the 13-LOP3 distance (plm_common.cuh): the query is transformed once, every stage of
+//            train rows is transformed in place in shared memory before it is scanned.
+template <int VARIANT>
+__device__ __forceinline__ int knn_dist(const Desc &a, const uint4 &blo, const uint4 &bhi) {
+    if (VARIANT == 3) return hamming256_t13(a, blo, bhi);
+    if (VARIANT == 2) return hamming256_csa4(a, blo, bhi);
+    if (VARIANT == 1) return hamming256_csa(a, blo, bhi);
+    return hamming256(a, blo, bhi);
+}
+
 template <int THREADS, int VARIANT>
 __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, int worker, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
     const int tid = threadIdx.x;
@@ -74,6 +84,7 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
         a.lo = make_uint4(0, 0, 0, 0);
         a.hi = a.lo;
     }
+    if (VARIANT == 3) desc_transform13(a.lo, a.hi);
     const uint4 *db = t.db;
     const int unit_rows = t.unit_rows, n_units = t.n_units, step = t.n_workers;
     const uint32_t idx_base = static_cast<uint32_t>(t.idx_base); // idx_base + n2 <= 2^32 (checked by the host)
@@ -100,14 +111,24 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
         }
         __syncthreads();
         const int rows = rows_of(u);
+        if (VARIANT == 3) {
+            uint4 *w = stage[buf];
+            for (int r = tid; r < rows; r += THREADS) {
+                uint4 lo = w[2 * r], hi = w[2 * r + 1];
+                desc_transform13(lo, hi);
+                w[2 * r] = lo;
+                w[2 * r + 1] = hi;
+            }
+            __syncthreads();
+        }
         const uint4 *sb = stage[buf];
         const uint32_t gbase = idx_base + static_cast<uint32_t>(u) * static_cast<uint32_t>(unit_rows);
-        if (VARIANT == 2) {
+        if (VARIANT >= 2) {
             int j = 0;
             for (; j + 8 <= rows; j += 8) {
                 int d[8];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) d[v] = hamming256_csa4(a, sb[2 * (j + v)], sb[2 * (j + v) + 1]);
+                for (int v = 0; v < 8; ++v) d[v] = knn_dist<VARIANT>(a, sb[2 * (j + v)], sb[2 * (j + v) + 1]);
                 const int m = min(min(min(d[0], d[1]), min(d[2], d[3])), min(min(d[4], d[5]), min(d[6], d[7])));
                 if (m < thr) {
 #pragma unroll
@@ -116,7 +137,7 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
                 }
             }
             for (; j < rows; ++j) {
-                const int d = hamming256_csa4(a, sb[2 * j], sb[2 * j + 1]);
+                const int d = knn_dist<VARIANT>(a, sb[2 * j], sb[2 * j + 1]);
                 if (d < thr) {
                     top2_insert(B0, B1, make_key64(d, gbase + j));
                     thr = (B1 == KEY64_ABSENT) ? 1023 : static_cast<int>(B1 >> 32);
@@ -127,7 +148,7 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
 #pragma unroll 8
             for (int j = 0; j < rows; ++j) {
                 const uint4 blo = sb[2 * j], bhi = sb[2 * j + 1];
-                const int d = (VARIANT == 1) ? hamming256_csa(a, blo, bhi) : hamming256(a, blo, bhi);
+                const int d = knn_dist<VARIANT>(a, blo, bhi);
                 top2_insert(b0, b1, (static_cast<uint32_t>(d) << KNN_IDX_BITS) + static_cast<uint32_t>(j));
             }
             top2_insert(B0, B1, expand_key(b0, gbase));

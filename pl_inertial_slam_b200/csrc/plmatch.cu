@@ -77,7 +77,7 @@ struct plm_ctx {
     uint64_t launches = 0;
     bool fused_attr_set = false;
     bool cluster_attr_set = false;
-    int knn_occ[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int knn_occ[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
     // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
     bool profiling = false;
@@ -179,7 +179,7 @@ int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame 
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
 
-// -1 = automatic (variant 2 for long slices, 1 otherwise); 0/1/2 force a variant (measurement only)
+// -1 = automatic (variant 3 for long slices, 1 otherwise); 0..3 force a variant (measurement only)
 int g_knn_variant = -2;
 int knn_variant_for(int slice_rows) {
     if (g_knn_variant == -2) {
@@ -188,9 +188,10 @@ int knn_variant_for(int slice_rows) {
         if (e && std::strcmp(e, "popc8") == 0) g_knn_variant = 0;
         if (e && std::strcmp(e, "csa5") == 0) g_knn_variant = 1;
         if (e && std::strcmp(e, "csa4") == 0) g_knn_variant = 2;
+        if (e && std::strcmp(e, "t13") == 0) g_knn_variant = 3;
     }
     if (g_knn_variant >= 0) return g_knn_variant;
-    return slice_rows >= 2048 ? 2 : 1;
+    return slice_rows >= 2048 ? 3 : 1;
 }
 
 // CTAs of the brute-force kernel that are resident on one SM (per CTA width and variant).
@@ -199,15 +200,19 @@ int knn_ctas_per_sm(plm_ctx *ctx, int threads, int variant) {
     if (cached > 0) return cached;
     int nb = 0;
     cudaError_t e = cudaErrorUnknown;
+#define PLM_KNN_OCC(T, V) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<T, V>, T, 0)
     if (threads == 128) {
-        if (variant == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<128, 2>, 128, 0);
-        else if (variant == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<128, 1>, 128, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<128, 0>, 128, 0);
+        if (variant == 3) PLM_KNN_OCC(128, 3);
+        else if (variant == 2) PLM_KNN_OCC(128, 2);
+        else if (variant == 1) PLM_KNN_OCC(128, 1);
+        else PLM_KNN_OCC(128, 0);
     } else {
-        if (variant == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<64, 2>, 64, 0);
-        else if (variant == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<64, 1>, 64, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<64, 0>, 64, 0);
+        if (variant == 3) PLM_KNN_OCC(64, 3);
+        else if (variant == 2) PLM_KNN_OCC(64, 2);
+        else if (variant == 1) PLM_KNN_OCC(64, 1);
+        else PLM_KNN_OCC(64, 0);
     }
+#undef PLM_KNN_OCC
     cached = (e == cudaSuccess && nb > 0) ? nb : 8;
     return cached;
 }
@@ -256,15 +261,19 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
         }
         CU_TRY(cudaEventRecord(ev.first, ctx->stream));
     }
+#define PLM_KNN_LAUNCH(T, V) plm::knn2_slice_kernel<T, V><<<grid, T, 0, ctx->stream>>>(tp)
     if (threads == 128) {
-        if (variant == 2) plm::knn2_slice_kernel<128, 2><<<grid, 128, 0, ctx->stream>>>(tp);
-        else if (variant == 1) plm::knn2_slice_kernel<128, 1><<<grid, 128, 0, ctx->stream>>>(tp);
-        else plm::knn2_slice_kernel<128, 0><<<grid, 128, 0, ctx->stream>>>(tp);
+        if (variant == 3) PLM_KNN_LAUNCH(128, 3);
+        else if (variant == 2) PLM_KNN_LAUNCH(128, 2);
+        else if (variant == 1) PLM_KNN_LAUNCH(128, 1);
+        else PLM_KNN_LAUNCH(128, 0);
     } else {
-        if (variant == 2) plm::knn2_slice_kernel<64, 2><<<grid, 64, 0, ctx->stream>>>(tp);
-        else if (variant == 1) plm::knn2_slice_kernel<64, 1><<<grid, 64, 0, ctx->stream>>>(tp);
-        else plm::knn2_slice_kernel<64, 0><<<grid, 64, 0, ctx->stream>>>(tp);
+        if (variant == 3) PLM_KNN_LAUNCH(64, 3);
+        else if (variant == 2) PLM_KNN_LAUNCH(64, 2);
+        else if (variant == 1) PLM_KNN_LAUNCH(64, 1);
+        else PLM_KNN_LAUNCH(64, 0);
     }
+#undef PLM_KNN_LAUNCH
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     if (ctx->profiling) {
@@ -310,7 +319,7 @@ int check_desc(const uint8_t *d, int n, size_t step) {
 PLM_API int plm_set_option(const char *key, int value) {
     if (!key) return fail(PLM_E_INVALID, "null key");
     if (std::strcmp(key, "knn_variant") == 0) {
-        g_knn_variant = (value >= 0 && value <= 2) ? value : -1;
+        g_knn_variant = (value >= 0 && value <= 3) ? value : -1;
         return PLM_OK;
     }
     if (std::strcmp(key, "grid_cluster") == 0) {
