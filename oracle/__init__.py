@@ -4,6 +4,8 @@
 * ``oracle.ref``   -- the reference itself, /root/reference/stvo-pl/src/{matching,gridStructure,
   lineIterator}.cpp and /root/reference/src/mapFeatures.cpp compiled unmodified
   (``_ref/libplref.so``; see oracle/Makefile)
+* ``oracle.ref_stereo`` -- the reference's stereo drivers and gates, stvo-pl/src/{stereoFrame,stereoFeatures,
+  pinholeStereoCamera}.cpp compiled unmodified (``_ref/libplref_stereo.so``)
 
 Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU arms may import this package; the
 product (pl_inertial_slam_b200) never does.  Nothing here reads /root/reference at run time: the
@@ -490,6 +492,137 @@ class _Ref:
         return v
 
 
+class _RefStereo:
+    """The reference's own stereo drivers and gates: stvo-pl/src/{stereoFrame,stereoFeatures,pinholeStereoCamera}.cpp
+    (+ matching / gridStructure / lineIterator) compiled unmodified into ``_ref/libplref_stereo.so``
+    (oracle/Makefile, stand-in headers under oracle/shim_stereo/).  Outputs use the layouts of ``oracle.port``'s
+    ``stereo_points`` / ``stereo_lines``; the left index of a kept feature travels through KeyPoint/KeyLine::octave
+    (StereoFrame copies it into PointFeature/LineFeature::level, stereoFrame.cpp:176,394)."""
+
+    def __init__(self, libname: str = "libplref_stereo.so"):
+        self._lib = None
+        self._libname = libname
+
+    def available(self) -> bool:
+        try:
+            return self.lib is not None
+        except (FileNotFoundError, OSError, RuntimeError):
+            return False
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            L = _load(self._libname)
+            L.plref_set_config.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+            L.plref_set_stereo_config.argtypes = [C.c_int] + [C.c_double] * 7
+            L.plref_stereo_points.restype = C.c_int
+            L.plref_stereo_points.argtypes = [_f32p, _i32p, _u8p, C.c_int, _f32p, _u8p, C.c_int, C.c_int, C.c_int, _f64p,
+                                              C.c_int, _f64p, _f64p, _f64p, _i32p, _i32p, _f64p, _u8p, _i32p]
+            L.plref_stereo_lines.restype = C.c_int
+            L.plref_stereo_lines.argtypes = [_f32p, _f32p, _i32p, _u8p, C.c_int, _f32p, _u8p, C.c_int, C.c_int, C.c_int,
+                                             _f64p, C.c_int] + [_f64p] * 7 + [_i32p, _i32p, _f64p, _u8p, _i32p]
+            L.plref_filter_line_disparity.argtypes = [C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p]
+            L.plref_filter_disparity_pair.argtypes = [C.c_int, _f64p]
+            L.plref_line_overlap_stereo.argtypes = [C.c_int, _f64p, _f64p]
+            L.plref_line_overlap.argtypes = [C.c_int, _f64p, _f64p]
+            L.plref_back_projection.argtypes = [C.c_int, C.c_int, _f64p, C.c_int, _f64p, _f64p]
+            self._lib = L
+        return self._lib
+
+    def configure(self, best_lr=True, ratio=0.9, line_sim_th=0.75, matching_s_ws=10, max_dist_epip=1.0, min_disp=1.0,
+                  line_horiz_th=0.1, stereo_overlap_th=0.75, ls_min_disp_ratio=0.7, orb_scale_factor=1.2, lsd_scale=1.2):
+        self.lib.plref_set_config(int(bool(best_lr)), 1, float(ratio), float(line_sim_th))
+        self.lib.plref_set_stereo_config(int(matching_s_ws), float(max_dist_epip), float(min_disp), float(line_horiz_th),
+                                         float(stereo_overlap_th), float(ls_min_disp_ratio), float(orb_scale_factor),
+                                         float(lsd_scale))
+
+    def stereo_points(self, kp_l, d_l, kp_r, d_r, img_w, img_h, cam, initial=False, octave=None, **cfg):
+        """StereoFrame::matchStereoPoints -> dict(kept_i1, disp, P, pl, idx, level, sigma2, desc)."""
+        self.configure(**cfg)
+        kp_l = np.ascontiguousarray(kp_l, np.float32).reshape(-1, 2)
+        kp_r = np.ascontiguousarray(kp_r, np.float32).reshape(-1, 2)
+        d_l = np.ascontiguousarray(d_l, np.uint8).reshape(-1, 32)
+        d_r = np.ascontiguousarray(d_r, np.uint8).reshape(-1, 32)
+        n_l, n_r, cap = len(kp_l), len(kp_r), max(1, len(kp_l))
+        cam = np.ascontiguousarray(cam, np.float64)
+        tag = octave is None
+        octv = np.arange(n_l, dtype=np.int32) if tag else np.ascontiguousarray(octave, np.int32)
+        pl, disp, P = np.zeros((cap, 2)), np.zeros(cap), np.zeros((cap, 3))
+        idx, level, sigma2 = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        desc, nd = np.zeros((cap, 32), np.uint8), C.c_int32(0)
+        n = self.lib.plref_stereo_points(kp_l.ctypes.data_as(_f32p), octv.ctypes.data_as(_i32p), d_l.ctypes.data_as(_u8p),
+                                         n_l, kp_r.ctypes.data_as(_f32p), d_r.ctypes.data_as(_u8p), n_r, int(img_w),
+                                         int(img_h), cam.ctypes.data_as(_f64p), int(bool(initial)),
+                                         pl.ctypes.data_as(_f64p), disp.ctypes.data_as(_f64p), P.ctypes.data_as(_f64p),
+                                         idx.ctypes.data_as(_i32p), level.ctypes.data_as(_i32p),
+                                         sigma2.ctypes.data_as(_f64p), desc.ctypes.data_as(_u8p), C.byref(nd))
+        n = max(n, 0)
+        out = dict(disp=disp[:n].copy(), P=P[:n].copy(), pl=pl[:n].copy(), idx=idx[:n].copy(), level=level[:n].copy(),
+                   sigma2=sigma2[:n].copy(), desc=desc[:nd.value].copy())
+        if tag:
+            out["kept_i1"] = level[:n].copy()
+        return out
+
+    def stereo_lines(self, ln_l, d_l, ln_r, d_r, img_w, img_h, cam, initial=False, octave=None, angle=None, **cfg):
+        """StereoFrame::matchStereoLines -> dict(kept_i1, disp_se, sP, eP, le, spl, epl, angle, idx, level, sigma2, desc)."""
+        self.configure(**cfg)
+        ln_l = np.ascontiguousarray(ln_l, np.float32).reshape(-1, 4)
+        ln_r = np.ascontiguousarray(ln_r, np.float32).reshape(-1, 4)
+        d_l = np.ascontiguousarray(d_l, np.uint8).reshape(-1, 32)
+        d_r = np.ascontiguousarray(d_r, np.uint8).reshape(-1, 32)
+        n_l, n_r, cap = len(ln_l), len(ln_r), max(1, len(ln_l))
+        cam = np.ascontiguousarray(cam, np.float64)
+        tag = octave is None
+        octv = np.arange(n_l, dtype=np.int32) if tag else np.ascontiguousarray(octave, np.int32)
+        ang = np.zeros(n_l, np.float32) if angle is None else np.ascontiguousarray(angle, np.float32)
+        spl, epl, dse = np.zeros((cap, 2)), np.zeros((cap, 2)), np.zeros((cap, 2))
+        sP, eP, le = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3))
+        ang_o, idx, level, sigma2 = np.zeros(cap), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        desc, nd = np.zeros((cap, 32), np.uint8), C.c_int32(0)
+        f64 = lambda a: a.ctypes.data_as(_f64p)  # noqa: E731
+        n = self.lib.plref_stereo_lines(ln_l.ctypes.data_as(_f32p), ang.ctypes.data_as(_f32p), octv.ctypes.data_as(_i32p),
+                                        d_l.ctypes.data_as(_u8p), n_l, ln_r.ctypes.data_as(_f32p),
+                                        d_r.ctypes.data_as(_u8p), n_r, int(img_w), int(img_h), f64(cam), int(bool(initial)),
+                                        f64(spl), f64(epl), f64(dse), f64(sP), f64(eP), f64(le), f64(ang_o),
+                                        idx.ctypes.data_as(_i32p), level.ctypes.data_as(_i32p), f64(sigma2),
+                                        desc.ctypes.data_as(_u8p), C.byref(nd))
+        n = max(n, 0)
+        out = dict(disp_se=dse[:n].copy(), sP=sP[:n].copy(), eP=eP[:n].copy(), le=le[:n].copy(), spl=spl[:n].copy(),
+                   epl=epl[:n].copy(), angle=ang_o[:n].copy(), idx=idx[:n].copy(), level=level[:n].copy(),
+                   sigma2=sigma2[:n].copy(), desc=desc[:nd.value].copy())
+        if tag:
+            out["kept_i1"] = level[:n].copy()
+        return out
+
+    def filter_line_disparity(self, spl, epl, spr, epr, ls_min_disp_ratio=0.7):
+        self.configure(ls_min_disp_ratio=ls_min_disp_ratio)
+        a = [np.ascontiguousarray(x, np.float64).reshape(-1, 2) for x in (spl, epl, spr, epr)]
+        out = np.zeros((len(a[0]), 2))
+        self.lib.plref_filter_line_disparity(len(a[0]), *[x.ctypes.data_as(_f64p) for x in a], out.ctypes.data_as(_f64p))
+        return out
+
+    def line_overlap_stereo(self, v4, line_horiz_th=0.1):
+        self.configure(line_horiz_th=line_horiz_th)
+        v4 = np.ascontiguousarray(v4, np.float64).reshape(-1, 4)
+        out = np.zeros(len(v4))
+        self.lib.plref_line_overlap_stereo(len(v4), v4.ctypes.data_as(_f64p), out.ctypes.data_as(_f64p))
+        return out
+
+    def line_overlap(self, v8):
+        v8 = np.ascontiguousarray(v8, np.float64).reshape(-1, 8)
+        out = np.zeros(len(v8))
+        self.lib.plref_line_overlap(len(v8), v8.ctypes.data_as(_f64p), out.ctypes.data_as(_f64p))
+        return out
+
+    def back_projection(self, cam, uvd, img_w=752, img_h=480):
+        cam = np.ascontiguousarray(cam, np.float64)
+        uvd = np.ascontiguousarray(uvd, np.float64).reshape(-1, 3)
+        out = np.zeros((len(uvd), 3))
+        self.lib.plref_back_projection(int(img_w), int(img_h), cam.ctypes.data_as(_f64p), len(uvd),
+                                       uvd.ctypes.data_as(_f64p), out.ctypes.data_as(_f64p))
+        return out
+
+
 class _MapDropIn:
     """The product's C++ drop-in for src/mapFeatures.cpp (pl_inertial_slam_b200/csrc/map_features_gpu.cpp) behind the
     harness of oracle/shim/ref_map_capi.cpp -- the thing under test in tests/test_cxx_dropin.py, not a checker."""
@@ -525,6 +658,7 @@ class _MapDropIn:
 
 port = _Port()
 ref = _Ref()
+ref_stereo = _RefStereo()
 map_gpu = _MapDropIn()
 stvo_gpu = _Ref("libstvo_gpu.so")  # the thing under test in tests/test_cxx_dropin.py, not a checker
 

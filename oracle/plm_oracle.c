@@ -13,16 +13,17 @@
  *     plo_line_coords, plo_med_desc (tests/test_oracle.py, tests/test_mapfeatures.py);
  *   - libplref_dbow.so = the reference's vendored DBoW2 (3rdparty/DBoW2) compiled unmodified
  *     -> plo_bow_word, plo_bow_transform, plo_bow_score (tests/test_bow.py);
+ *   - libplref_stereo.so = /root/reference/stvo-pl/src/{stereoFrame,stereoFeatures,pinholeStereoCamera}.cpp (+ matching /
+ *     gridStructure / lineIterator) compiled unmodified against the stand-in headers under oracle/shim_stereo/
+ *     -> plo_stereo_points, plo_stereo_lines (grid fill, matchGrid, gates, compaction, back-projection),
+ *     plo_stereo_filter_*, plo_csr_from_*, plo_line_overlap_stereo, plo_line_segment_overlap / plo_line_pair_filter
+ *     (tests/test_ref_stereo.py; tests/golden/stereo.npz);
  *   tests/golden/ holds vectors generated from those builds (tools/make_golden.py) for machines without
  *   /root/reference.
  * PARITY UNPINNED (restated from the source only, no reference build possible here):
  *   - cv::BFMatcher::knnMatch (OpenCV 3.3, features2d; call site matching.cpp:47-48) is not in
  *     /root/reference: its K=2 batchDistance insertion rule is restated in plo_knn2() and cross-checked
- *     against the in-container cv2 4.13 wheel (tests/test_oracle.py::test_knn2_vs_cv2);
- *   - the stereo drivers and gates of stvo-pl/src/stereoFrame.cpp (plo_stereo_*, plo_csr_from_*,
- *     plo_line_overlap_stereo, plo_line_segment_overlap / plo_line_pair_filter): stereoFrame.cpp needs
- *     OpenCV and line_descriptor to compile; the restatements are cross-checked against independent numpy
- *     forms in the tests.
+ *     against the in-container cv2 4.13 wheel (tests/test_oracle.py::test_knn2_vs_cv2).
  *
  * Every function cites the reference lines it follows (paths relative to /root/reference).
  */
@@ -905,8 +906,8 @@ PLO_API double plo_bow_score(const uint32_t *ids1, const double *vals1, int n1, 
  *   direction similarity      |dot(normalize(e1 - s1), normalize(e2 - s2))| with dot / normalize of
  *       stvo-pl/include/matching.h:39-48 and the test of matching.cpp:221 (`abs(dot) < lineSimTh` rejects,
  *       so a NaN similarity passes).
- * The reference's stereoFrame.cpp cannot be compiled here (OpenCV / line_descriptor), so this function is
- * restated from the source only: parity for it is unpinned by a reference build.
+ * Pinned on the reference's own stereoFrame.cpp compiled unmodified (oracle/_ref/libplref_stereo.so,
+ * tests/test_ref_stereo.py::test_scalar_gates_vs_reference; golden outputs in tests/golden/stereo.npz).
  */
 static double plo_overlap_from_lambdas(double lambda_s, double lambda_e)
 {

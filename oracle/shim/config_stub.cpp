@@ -26,6 +26,8 @@ Config::Config() {
     matching_strategy = 0;
     matching_s_ws = 10;
     matching_f2f_ws = 3;
+    orb_scale_factor = 1.2;
+    lsd_scale = 1.2;
 }
 
 Config::~Config() {}

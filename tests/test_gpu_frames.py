@@ -250,3 +250,67 @@ def test_pipelined_process_equals_staged_calls(chunk):
                     assert np.array_equal(got[lo:lo + k], want[lo:lo + k], equal_nan=True), (name, f)
     assert pipe.d2h_bytes > 0 and pipe.h2d_bytes >= rp.arena.nbytes + kp.nbytes + ln.nbytes
     pipe.close()
+
+
+def _golden_stereo():
+    import os
+    from conftest import ROOT
+    return np.load(os.path.join(ROOT, "tests", "golden", "stereo.npz"))
+
+
+def _golden_cfg(z, c):
+    g = lambda k, d: float(z[f"cfg{c}_{k}"]) if f"cfg{c}_{k}" in z.files else d  # noqa: E731
+    fx, _, cx, cy, b = z["cam_ref"]
+    return FrameConfig(img_width=int(z["img_wh"][0]), img_height=int(z["img_wh"][1]), matchingSWs=int(g("matching_s_ws", 10)),
+                       bestLRMatches=bool(g("best_lr", 1)), minRatio12P=g("ratio", 0.9), maxDistEpip=g("max_dist_epip", 1.0),
+                       minDisp=g("min_disp", 1.0), lineHorizTh=g("line_horiz_th", 0.1), stereoOverlapTh=g("stereo_overlap_th", 0.75),
+                       lsMinDispRatio=g("ls_min_disp_ratio", 0.7), cam_b=float(b), cam_fx=float(fx), cam_cx=float(cx), cam_cy=float(cy))
+
+
+def test_frame_pipeline_vs_reference_golden():
+    """tests/golden/stereo.npz holds the outputs of the reference's OWN StereoFrame::matchStereoPoints / matchStereoLines
+    (stereoFrame.cpp compiled unmodified, tools/make_golden.py stereo): kept features, disparities, back-projected
+    3-D points / segments and line equations must be bit-identical."""
+    from types import SimpleNamespace
+    z = _golden_stereo()
+    pairs = [SimpleNamespace(**{k: z[f"f{f}_{k}"] for k in ("kp_l", "kp_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r", "ldesc_l", "ldesc_r")})
+             for f in range(int(z["n_frames"]))]
+    desc, kp, ln, rec = arenas_from_pairs(pairs)
+    bits = lambda a: np.ascontiguousarray(a, np.float64).view(np.uint64)  # noqa: E731
+    for c in range(int(z["n_cfg"])):
+        pipe = FramePipeline()
+        pipe.upload(desc, kp, ln, rec, _golden_cfg(z, c))
+        pipe.run()
+        out = pipe.fetch()
+        for f in range(len(pairs)):
+            lo = int(pipe.off_p[f])
+            want = z[f"f{f}_c{c}_pt_kept_i1"]
+            k = len(want)
+            assert out["counts"][f, 1] == k and np.array_equal(out["kept_p"][lo:lo + k], want), (c, f)
+            assert np.array_equal(bits(out["pt_disp"][lo:lo + k]), bits(z[f"f{f}_c{c}_pt_disp"])), (c, f)
+            assert np.array_equal(bits(out["pt_P"][lo:lo + k]), bits(z[f"f{f}_c{c}_pt_P"])), (c, f)
+            lo = int(pipe.off_l[f])
+            want = z[f"f{f}_c{c}_ls_kept_i1"]
+            k = len(want)
+            assert out["counts"][f, 3] == k and np.array_equal(out["kept_l"][lo:lo + k], want), (c, f)
+            for name, key in (("ls_disp", "disp_se"), ("ls_sP", "sP"), ("ls_eP", "eP"), ("ls_le", "le")):
+                assert np.array_equal(bits(out[name][lo:lo + k]), bits(z[f"f{f}_c{c}_ls_{key}"])), (c, f, name)
+        pipe.close()
+
+
+def test_line_overlap_kernel_vs_reference_golden():
+    """StereoFrame::lineSegmentOverlap (stereoFrame.cpp:521-627) outputs of the compiled reference against
+    line_pair_filter_kernel: segment i of set 1 is the projection, segment i of set 2 the observation."""
+    from pl_inertial_slam_b200 import matching as M
+    z = _golden_stereo()
+    v = z["ov_in"]
+    n = len(v)
+    # inputs are float32 in the ABI (KeyLine fields): round them first and take the reference of the rounded values
+    # from the restatement, which tests/test_ref_stereo.py pins on the compiled reference for arbitrary doubles
+    obs = v[:, 0:4].astype(np.float32)
+    proj = v[:, 4:8].astype(np.float32)
+    m12 = np.arange(n, dtype=np.int32)
+    n_g, keep_g, ov_g, sim_g = M.line_pair_filter(proj, obs, m12, 0.75, 0.75)
+    n_o, keep_o, ov_o, sim_o = oracle.port.line_pair_filter(proj, obs, m12, 0.75, 0.75)
+    assert n_g == n_o and np.array_equal(keep_g, keep_o)
+    assert np.array_equal(ov_g.view(np.uint64), ov_o.view(np.uint64))

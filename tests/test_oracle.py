@@ -236,3 +236,41 @@ def test_stereo_line_gates_port_vs_numpy(seed):
     assert np.array_equal(disp[fin, 0].view(np.uint64), ds[fin].view(np.uint64))
     assert np.array_equal(disp[fin, 1].view(np.uint64), de[fin].view(np.uint64))
     assert np.array_equal(np.isnan(disp[:, 0]), np.isnan(ds))
+
+
+def test_port_stereo_drivers_vs_reference_golden():
+    """tests/golden/stereo.npz = outputs of the reference's own stereoFrame.cpp (tools/make_golden.py stereo): the
+    restatement must reproduce them bit for bit also where the reference build is not available."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stereo.npz"))
+    fx, _, cx, cy, b = z["cam_ref"]
+    cam = np.array([b, fx, cx, cy])
+    w, h = (int(x) for x in z["img_wh"])
+    bits = lambda a: np.ascontiguousarray(a, np.float64).view(np.uint64)  # noqa: E731
+    for c in range(int(z["n_cfg"])):
+        g = lambda k, d: float(z[f"cfg{c}_{k}"]) if f"cfg{c}_{k}" in z.files else d  # noqa: E731
+        for f in range(int(z["n_frames"])):
+            d = {k: z[f"f{f}_{k}"] for k in ("kp_l", "kp_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r", "ldesc_l", "ldesc_r")}
+            p = port.stereo_points(d["kp_l"], d["pdesc_l"], d["kp_r"], d["pdesc_r"], 64.0 / w, 48.0 / h, cam,
+                                   matching_s_ws=int(g("matching_s_ws", 10)), ratio=g("ratio", 0.9), best_lr=bool(g("best_lr", 1)),
+                                   max_dist_epip=g("max_dist_epip", 1.0), min_disp=g("min_disp", 1.0))
+            assert np.array_equal(p["kept_i1"], z[f"f{f}_c{c}_pt_kept_i1"])
+            assert np.array_equal(bits(p["disp"]), bits(z[f"f{f}_c{c}_pt_disp"]))
+            assert np.array_equal(bits(p["P"]), bits(z[f"f{f}_c{c}_pt_P"]))
+            q = port.stereo_lines(d["ln_l"], d["ldesc_l"], d["ln_r"], d["ldesc_r"], 64.0 / w, 48.0 / h, cam,
+                                  matching_s_ws=int(g("matching_s_ws", 10)), ratio=g("ratio", 0.9), best_lr=bool(g("best_lr", 1)),
+                                  min_disp=g("min_disp", 1.0), line_horiz_th=g("line_horiz_th", 0.1),
+                                  stereo_overlap_th=g("stereo_overlap_th", 0.75), ls_min_disp_ratio=g("ls_min_disp_ratio", 0.7))
+            assert np.array_equal(q["kept_i1"], z[f"f{f}_c{c}_ls_kept_i1"])
+            for key in ("disp_se", "sP", "eP", "le"):
+                assert np.array_equal(bits(q[key]), bits(z[f"f{f}_c{c}_ls_{key}"])), key
+    import ctypes as C
+    lib = port.lib
+    lib.plo_line_segment_overlap.restype = C.c_double
+    lib.plo_line_overlap_stereo.restype = C.c_double
+    lib.plo_line_overlap_stereo.argtypes = [C.c_double] * 5
+    p2 = C.c_double * 2
+    got = np.array([lib.plo_line_segment_overlap(p2(*r[0:2]), p2(*r[2:4]), p2(*r[4:6]), p2(*r[6:8])) for r in z["ov_in"]])
+    assert np.array_equal(bits(got), bits(z["ov_out"]))
+    got = np.array([lib.plo_line_overlap_stereo(*r, 0.1) for r in z["ovs_in"]])
+    assert np.array_equal(bits(got), bits(z["ovs_out"]))

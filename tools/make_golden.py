@@ -2,7 +2,7 @@
 matching.cpp / gridStructure.cpp / lineIterator.cpp / mapFeatures.cpp compiled unmodified, see oracle/Makefile).
 
 Run in the build container (needs /root/reference to build libplref.so):
-    python tools/make_golden.py [brute] [grid] [line_coords] [med_desc] [bow]
+    python tools/make_golden.py [brute] [grid] [line_coords] [med_desc] [bow] [stereo]
 The fixtures are small (a few hundred KB) and committed; tests compare the oracle port and the CUDA
 path against them, so parity stays pinned on machines where the reference cannot be built.
 """
@@ -144,10 +144,47 @@ def bow_cases():
     save("bow", **out)
 
 
+def stereo_cases():
+    """StereoFrame::matchStereoPoints / matchStereoLines + the scalar gates from the reference's own stereoFrame.cpp /
+    stereoFeatures.cpp / pinholeStereoCamera.cpp (oracle/_ref/libplref_stereo.so), on frames salted with the
+    degenerate inputs the gates special-case (see tests/test_ref_stereo.py::degenerate_pair)."""
+    from test_ref_stereo import CAM_REF, H, W, degenerate_pair
+    rs = oracle.ref_stereo
+    assert rs.available(), "build oracle/_ref/libplref_stereo.so first (make -C oracle ref)"
+    cfgs = [dict(ratio=0.9, best_lr=True, matching_s_ws=10), dict(ratio=0.75, best_lr=False, matching_s_ws=10),
+            dict(ratio=0.9, best_lr=True, matching_s_ws=4, max_dist_epip=1.5, min_disp=5.0, line_horiz_th=1.0,
+                 stereo_overlap_th=0.6, ls_min_disp_ratio=0.8)]
+    out = {"n_frames": np.int32(3), "n_cfg": np.int32(len(cfgs)), "cam_ref": CAM_REF, "img_wh": np.array([W, H], np.int32)}
+    for f in range(3):
+        names = ("kp_l", "pdesc_l", "kp_r", "pdesc_r", "ln_l", "ldesc_l", "ln_r", "ldesc_r")
+        data = dict(zip(names, degenerate_pair(40 + f)))
+        for k, v in data.items():
+            out[f"f{f}_{k}"] = v
+        for c, cfg in enumerate(cfgs):
+            r = rs.stereo_points(data["kp_l"], data["pdesc_l"], data["kp_r"], data["pdesc_r"], W, H, CAM_REF, **cfg)
+            q = rs.stereo_lines(data["ln_l"], data["ldesc_l"], data["ln_r"], data["ldesc_r"], W, H, CAM_REF, **cfg)
+            for k in ("kept_i1", "disp", "P"):
+                out[f"f{f}_c{c}_pt_{k}"] = r[k]
+            for k in ("kept_i1", "disp_se", "sP", "eP", "le"):
+                out[f"f{f}_c{c}_ls_{k}"] = q[k]
+    for c, cfg in enumerate(cfgs):
+        for k, v in cfg.items():
+            out[f"cfg{c}_{k}"] = np.float64(v)
+    rng = np.random.default_rng(synth.SEED0 + 500)
+    v8 = rng.uniform(0, 700, (600, 8))
+    v8[::5, 2] = v8[::5, 0] + rng.uniform(-1.5, 1.5, 120)
+    v8[1::5, 3] = v8[1::5, 1] + rng.uniform(-1.5, 1.5, 120)
+    v8[2::31, 2:4] = v8[2::31, 0:2]
+    v4 = rng.uniform(0, 480, (600, 4))
+    v4[::7, 1] = v4[::7, 0] + rng.uniform(-0.2, 0.2, len(v4[::7]))
+    out.update(ov_in=v8, ov_out=rs.line_overlap(v8), ovs_in=v4, ovs_out=rs.line_overlap_stereo(v4, 0.1))
+    save("stereo", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("brute", brute_cases), ("grid", grid_cases), ("line_coords", line_coord_cases),
-                     ("med_desc", med_desc_cases), ("bow", bow_cases)):
+                     ("med_desc", med_desc_cases), ("bow", bow_cases), ("stereo", stereo_cases)):
         if not only or name in only:
             fn()
