@@ -45,6 +45,7 @@ struct GridParams {
     int grid_rows, grid_cols;
     int best_lr;
     int rows_per_warp;          // chunked launch only; the fused kernel derives it from n1
+    int rows_per_cta, cap_pairs; // row-parallel launch (grid_rows_kernel): rows per CTA, pair-list capacity
     // fused kernel: when staged != 0 every input of the job is first copied into shared memory with
     // coalesced 128-bit loads (capacities below, in elements), so the per-row dependent accesses
     // (coords -> cell_start -> cell_items -> descriptor / threshold) cost shared-memory latency
@@ -359,7 +360,8 @@ __device__ __forceinline__ void block_inclusive_scan(int32_t *v, int n, int32_t 
 // Calls f(item slot t) for every slot of the row's window(s), one thread walking them in order.
 template <class F>
 __device__ __forceinline__ void for_each_slot(const RowWindows &rw, const GridJob &job, int grid_rows, F &&f) {
-    for (int k = 0; k < rw.n_win; ++k)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) // nx[1] == 0 for points; constant indices keep the window in registers
         for (int x = rw.min_x[k]; x < rw.min_x[k] + rw.nx[k]; ++x) {
             const int lo = job.cell_start[x * grid_rows + rw.min_y[k]], hi = job.cell_start[x * grid_rows + rw.max_y[k]];
             for (int t = lo; t < hi; ++t) f(t);
@@ -745,6 +747,332 @@ grid_match_chunked_kernel(GridJob job, GridParams gp) {
     }
 }
 
+// ---- row-parallel launch for map-sized jobs ---------------------------------------------------------------------
+// The warp-per-chunk kernels above replay the rows of a chunk in order; at map scale (200 000 rows x ~10 candidates)
+// that serial dependent chain (coords -> cell_start -> cell_items -> descriptor) is what the time goes into.  Here
+// a CTA takes blocks of 256 consecutive rows and turns each block into a FLAT PAIR LIST in shared memory:
+//   phase A  thread = row: window clamp, slot count, block scan, then the row's (row, i2) entries are written out
+//   phase B  thread = entry (stride 256, no divergence): direction filter, distance, and
+//              pass 0:  cmin[i2] = min D                                          -> cta_min[c][:]
+//              pass 1:  D < T[i2] ("survivor": it beats every earlier block, CTA and lower-ranked shard) ?
+//                       the entry stays in the list as (i2, row, D) and proposes K[i2] = min (D << 16 | row)
+//   rounds   among the survivors of a block the live pairs are the strict prefix minima of their column in row
+//            order: the entry that owns K[i2] is live, later rows of the column are dead, earlier rows stay
+//            undecided and propose again (one record of the column's chain per round, ~log of the survivors per
+//            column rounds; after the first CTAs a block has almost no survivors).  Live pairs go into the row's
+//            top-2 with a linearisable shared-memory insert; fp64 ratio test and the m21 key follow as before.
+//   scan     between the passes grid_scan_kernel turns cta_min into exclusive thresholds (+ seed of lower shards).
+// A train feature listed in several cells of a row's window(s) (a line) yields repeated entries: every update is
+// an idempotent min and the row top-2 ignores a key it already holds, so no de-duplication pass is needed.
+// A block whose slots exceed the list capacity (very dense windows) is handled by the same rounds with every
+// thread re-walking its own row instead (slower, same result).
+constexpr int GRID_ROW_THREADS = 256;
+
+struct GridRowsSmem { // layout of the work area, in bytes from the start of dynamic shared memory
+    size_t K, T, Tnew, B, rb0, rb1, d1s, rowdir, ent, stage, total;
+};
+__host__ __device__ inline GridRowsSmem grid_rows_layout(int n2, bool lines, int cap_pairs, int n_cells, int cap_items, int staged) {
+    GridRowsSmem L;
+    size_t o = 0;
+    L.K = o; o += grid_align16(static_cast<size_t>(n2) * 4);
+    L.T = o; o += grid_align16(static_cast<size_t>(n2) * 2);
+    L.Tnew = o; o += grid_align16(static_cast<size_t>(n2) * 2);
+    L.B = o; o += grid_align16(static_cast<size_t>(n2) * 2);
+    L.rb0 = o; o += static_cast<size_t>(GRID_ROW_THREADS) * 4;
+    L.rb1 = o; o += static_cast<size_t>(GRID_ROW_THREADS) * 4;
+    L.d1s = o; o += static_cast<size_t>(GRID_ROW_THREADS) * 32;
+    L.rowdir = o; o += lines ? static_cast<size_t>(GRID_ROW_THREADS) * 16 : 0;
+    L.ent = o; o += grid_align16(static_cast<size_t>(cap_pairs) * 4);
+    L.stage = o;
+    if (staged)
+        o += grid_align16(static_cast<size_t>(n_cells + 1) * 4) + static_cast<size_t>(n2) * 32 +
+             (lines ? static_cast<size_t>(n2) * 16 : 0) + grid_align16(static_cast<size_t>(cap_items) * 4);
+    L.total = o;
+    return L;
+}
+
+// Concurrent insert of key k into the sorted pair (b0 <= b1) held in shared memory.  Linearisable: the insert that
+// lowers b0 hands the previous minimum down to b1, every later insert sees the new minimum and hands itself down, so
+// b1 ends as the second smallest DISTINCT key (a repeated key is ignored).
+__device__ __forceinline__ void top2_insert_atomic(uint32_t *b0, uint32_t *b1, uint32_t k) {
+    const uint32_t old = atomicMin(b0, k);
+    if (old != k) atomicMin(b1, max(old, k));
+}
+
+// f(i2, D) for every candidate of the row that passes the range check and the direction filter.
+template <class F>
+__device__ __forceinline__ void row_walk(const GridJob &job, const GridParams &gp, const RowQuery &r, F &&f) {
+    for_each_slot(r.rw, job, gp.grid_rows, [&](int t) {
+        const int i2 = job.cell_items[t];
+        if (candidate_ok(job, gp, r, i2)) f(i2, hamming256(r.q, load_desc_any(job.d2, i2)));
+    });
+}
+
+// STAGED: the frame side (cell_start, d2, dirs2 and -- when they fit -- cell_items) is copied into shared memory first;
+// the accesses below then go through pointers the compiler can prove to be shared (LDS instead of generic loads).
+template <int PASS, int STAGED>
+__global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
+grid_rows_kernel(GridJob job, GridParams gp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_warp_tot[GRID_ROW_THREADS / 32];
+    const int tid = threadIdx.x, NT = GRID_ROW_THREADS, lane = tid & 31, warp = tid >> 5;
+    const int n1 = job.n1, n2 = job.n2;
+    const int n_cells = gp.grid_rows * gp.grid_cols;
+    const GridRowsSmem L = grid_rows_layout(n2, job.is_lines != 0, gp.cap_pairs, n_cells, gp.cap_items, STAGED);
+    uint32_t *K = reinterpret_cast<uint32_t *>(smem_raw + L.K);
+    uint16_t *T = reinterpret_cast<uint16_t *>(smem_raw + L.T);
+    uint16_t *Tnew = reinterpret_cast<uint16_t *>(smem_raw + L.Tnew);
+    uint16_t *B = reinterpret_cast<uint16_t *>(smem_raw + L.B);
+    uint32_t *rb0 = reinterpret_cast<uint32_t *>(smem_raw + L.rb0), *rb1 = reinterpret_cast<uint32_t *>(smem_raw + L.rb1);
+    uint4 *d1s = reinterpret_cast<uint4 *>(smem_raw + L.d1s);
+    double2 *rowdir = reinterpret_cast<double2 *>(smem_raw + L.rowdir);
+    uint32_t *ent = reinterpret_cast<uint32_t *>(smem_raw + L.ent);
+    const size_t o_cs = L.stage, o_d2 = o_cs + grid_align16(static_cast<size_t>(n_cells + 1) * 4),
+                 o_dir = o_d2 + static_cast<size_t>(n2) * 32, o_ci = o_dir + (job.is_lines ? static_cast<size_t>(n2) * 16 : 0);
+    const int32_t *cs = STAGED ? reinterpret_cast<const int32_t *>(smem_raw + o_cs) : job.cell_start;
+    const uint4 *d2p = STAGED ? reinterpret_cast<const uint4 *>(smem_raw + o_d2) : job.d2;
+    const double2 *dirp = STAGED ? reinterpret_cast<const double2 *>(smem_raw + o_dir) : reinterpret_cast<const double2 *>(job.dirs2);
+    const int32_t *s_items = reinterpret_cast<const int32_t *>(smem_raw + o_ci);
+    bool items_staged = false;
+    if (STAGED) {
+        const int n_items = job.cell_start[n_cells];
+        stage_bytes(smem_raw + o_cs, job.cell_start, static_cast<size_t>(n_cells + 1) * 4);
+        stage_bytes(smem_raw + o_d2, job.d2, static_cast<size_t>(n2) * 32);
+        if (job.is_lines) stage_bytes(smem_raw + o_dir, job.dirs2, static_cast<size_t>(n2) * 16);
+        items_staged = n_items <= gp.cap_items;
+        if (items_staged) stage_bytes(smem_raw + o_ci, job.cell_items, static_cast<size_t>(max(n_items, 0)) * 4);
+        // the re-walk form (list overflow) goes through the job's pointers
+        job.cell_start = cs;
+        job.d2 = d2p;
+        if (job.is_lines) job.dirs2 = reinterpret_cast<const double *>(dirp);
+        if (items_staged) job.cell_items = s_items;
+    }
+    const long long cta_row0 = static_cast<long long>(blockIdx.x) * gp.rows_per_cta;
+    const int row_end = static_cast<int>(min(static_cast<long long>(n1), cta_row0 + gp.rows_per_cta));
+    uint16_t *cta_min = gp.cta_min + static_cast<size_t>(blockIdx.x) * n2;
+    const bool thresholds = PASS == 1 && gp.best_lr;
+
+    if (PASS == 0) {
+        for (int i = tid; i < n2; i += NT) K[i] = KEY32_ABSENT;
+    } else if (thresholds) {
+        for (int i = tid; i < n2; i += NT) {
+            const uint16_t t = cta_min[i]; // exclusive prefix over the earlier CTAs (and lower-ranked shards)
+            T[i] = t;
+            Tnew[i] = t;
+            B[i] = D_INF;
+            K[i] = KEY32_ABSENT;
+        }
+    }
+    __syncthreads();
+    const uint32_t utid = static_cast<uint32_t>(tid);
+    int accepted = 0;
+    for (long long base = cta_row0; base < row_end; base += NT) { // uniform over the CTA
+        const long long i1 = base + tid;
+        const bool has_row = i1 < row_end;
+        // ---- phase A: windows, slot counts, block scan ----
+        RowQuery r;
+        int S = 0;
+        if (has_row) {
+            r = load_row(job, gp, static_cast<int>(i1));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) // nx[1] == 0 for points
+                for (int x = r.rw.min_x[k]; x < r.rw.min_x[k] + r.rw.nx[k]; ++x)
+                    S += max(0, cs[x * gp.grid_rows + r.rw.max_y[k]] - cs[x * gp.grid_rows + r.rw.min_y[k]]);
+            d1s[2 * tid] = r.q.lo;
+            d1s[2 * tid + 1] = r.q.hi;
+            if (job.is_lines) rowdir[tid] = make_double2(r.vx, r.vy);
+        }
+        int incl = S;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+            if (lane >= s) incl += v;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        if (PASS == 1) {
+            rb0[tid] = KEY32_ABSENT;
+            rb1[tid] = KEY32_ABSENT;
+        }
+        __syncthreads();
+        int off = incl - S, total = 0;
+#pragma unroll
+        for (int w = 0; w < GRID_ROW_THREADS / 32; ++w) {
+            const int t = s_warp_tot[w];
+            if (w < warp) off += t;
+            total += t;
+        }
+        const bool listed = total <= gp.cap_pairs;
+        uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT; // register top-2 of the re-walk form
+        auto take = [&](int i2, int d) {
+            const uint32_t k2 = (static_cast<uint32_t>(d) << GRID_KEY_BITS) | static_cast<uint32_t>(i2);
+            if (k2 != b0 && k2 != b1) top2_insert(b0, b1, k2);
+        };
+        bool und = false;
+        if (listed) {
+            if (has_row) {
+                int p = off;
+                auto emit = [&](const int32_t *items) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        for (int x = r.rw.min_x[k]; x < r.rw.min_x[k] + r.rw.nx[k]; ++x) {
+                            const int lo = cs[x * gp.grid_rows + r.rw.min_y[k]], hi = cs[x * gp.grid_rows + r.rw.max_y[k]];
+                            for (int t = lo; t < hi; ++t) {
+                                const int i2 = items[t];
+                                ent[p++] = (i2 >= 0 && i2 < n2) ? ((utid << 16) | static_cast<uint32_t>(i2)) : PAIR_INVALID;
+                            }
+                        }
+                };
+                if (STAGED && items_staged) emit(s_items);
+                else emit(job.cell_items);
+            }
+            __syncthreads();
+            // ---- phase B: one thread per entry ----
+            for (int e = tid; e < total; e += NT) {
+                const uint32_t v = ent[e];
+                uint32_t out = PAIR_INVALID;
+                if (v != PAIR_INVALID) {
+                    const uint32_t row = v >> 16, i2 = v & 0xFFFFu;
+                    bool ok = true;
+                    if (job.is_lines) {
+                        const double2 q = rowdir[row];
+                        const double2 t2 = dirp[i2];
+                        const double dp = __dadd_rn(__dmul_rn(q.x, t2.x), __dmul_rn(q.y, t2.y));
+                        ok = !(fabs(dp) < gp.line_sim_th); // matching.cpp:221, NaN passes
+                    }
+                    if (ok) {
+                        Desc a;
+                        a.lo = d1s[2 * row];
+                        a.hi = d1s[2 * row + 1];
+                        const uint32_t d = static_cast<uint32_t>(hamming256(a, d2p[2 * i2], d2p[2 * i2 + 1]));
+                        if (PASS == 0) {
+                            if (d < K[i2]) atomicMin(&K[i2], d);
+                        } else if (!gp.best_lr) {
+                            top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
+                        } else if (d < T[i2]) {
+                            atomicMin(&K[i2], (d << 16) | row);
+                            out = (i2 << 17) | (row << 9) | d;
+                        }
+                    }
+                }
+                if (thresholds) ent[e] = out;
+            }
+            __syncthreads();
+        } else {
+            // the block does not fit the list: every thread walks its own row
+            if (has_row) {
+                if (PASS == 0) {
+                    row_walk(job, gp, r, [&](int i2, int d) {
+                        if (static_cast<uint32_t>(d) < K[i2]) atomicMin(&K[i2], static_cast<uint32_t>(d));
+                    });
+                } else if (!gp.best_lr) {
+                    row_walk(job, gp, r, take);
+                } else {
+                    row_walk(job, gp, r, [&](int i2, int d) {
+                        if (d < T[i2]) {
+                            und = true;
+                            atomicMin(&K[i2], (static_cast<uint32_t>(d) << 16) | utid);
+                        }
+                    });
+                }
+            }
+            __syncthreads();
+        }
+        if (PASS == 0) continue; // every path above ends with a block barrier; K accumulates over the blocks of the CTA
+        if (thresholds) {
+            auto fold = [&](int round) { // per column: this round's record becomes the bound of the next one
+                for (int i2 = tid; i2 < n2; i2 += NT) {
+                    const uint32_t k = K[i2];
+                    if (k != KEY32_ABSENT) {
+                        if (round == 0) { // the block's best pair of the column: new threshold, m21 candidate
+                            Tnew[i2] = static_cast<uint16_t>(k >> 16);
+                            atomicMin(&gp.m21key[i2], make_key64(k >> 16, static_cast<uint32_t>(job.i1_base + base + (k & 0xFFFFu))));
+                        }
+                        B[i2] = static_cast<uint16_t>(k & 0xFFFFu);
+                        K[i2] = KEY32_ABSENT;
+                    }
+                }
+            };
+            if (listed) {
+                // rounds over the list: a decided entry is overwritten with PAIR_INVALID
+                for (int round = 0;; ++round) {
+                    bool again = false;
+                    for (int e = tid; e < total; e += NT) {
+                        const uint32_t v = ent[e];
+                        if (v == PAIR_INVALID) continue;
+                        const uint32_t i2 = v >> 17, row = (v >> 9) & 0xFFu, d = v & 0x1FFu;
+                        const uint32_t key = (d << 16) | row, k = K[i2];
+                        if (key == k) {
+                            top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
+                            ent[e] = PAIR_INVALID;
+                        } else if (row > (k & 0xFFFFu)) {
+                            ent[e] = PAIR_INVALID;
+                        } else {
+                            again = true;
+                        }
+                    }
+                    __syncthreads();
+                    fold(round);
+                    if (!__syncthreads_or(again ? 1 : 0)) break;
+                    for (int e = tid; e < total; e += NT) {
+                        const uint32_t v = ent[e];
+                        if (v == PAIR_INVALID) continue;
+                        atomicMin(&K[v >> 17], ((v & 0x1FFu) << 16) | ((v >> 9) & 0xFFu));
+                    }
+                    __syncthreads();
+                }
+            } else {
+                for (int round = 0;; ++round) {
+                    if (und) {
+                        bool again = false;
+                        row_walk(job, gp, r, [&](int i2, int d) {
+                            if (d < T[i2] && utid < B[i2]) {
+                                const uint32_t key = (static_cast<uint32_t>(d) << 16) | utid, k = K[i2];
+                                if (key == k) take(i2, d);
+                                else if (utid < (k & 0xFFFFu)) again = true;
+                            }
+                        });
+                        und = again;
+                    }
+                    __syncthreads();
+                    fold(round);
+                    if (!__syncthreads_or(und ? 1 : 0)) break;
+                    if (und)
+                        row_walk(job, gp, r, [&](int i2, int d) {
+                            if (d < T[i2] && utid < B[i2]) atomicMin(&K[i2], (static_cast<uint32_t>(d) << 16) | utid);
+                        });
+                    __syncthreads();
+                }
+            }
+            if (base + NT < row_end) { // thresholds for the next block of rows of this CTA
+                for (int i2 = tid; i2 < n2; i2 += NT) {
+                    T[i2] = Tnew[i2];
+                    B[i2] = D_INF;
+                }
+            }
+        }
+        if (listed) {
+            b0 = rb0[tid];
+            b1 = rb1[tid];
+        }
+        __syncthreads(); // rb / ent / T are rewritten by the next block
+        if (has_row && b0 != KEY32_ABSENT) {
+            // matching.cpp:160 / :241 -- int -> double, one double multiply, strict compare
+            const int best_d = static_cast<int>(b0 >> GRID_KEY_BITS);
+            const int best_d2 = (b1 == KEY32_ABSENT) ? 0x7FFFFFFF : static_cast<int>(b1 >> GRID_KEY_BITS);
+            if (static_cast<double>(best_d) < __dmul_rn(static_cast<double>(best_d2), gp.ratio)) {
+                job.m12[i1] = static_cast<int32_t>(b0 & ((1u << GRID_KEY_BITS) - 1));
+                ++accepted;
+            }
+        }
+    }
+    if (PASS == 0) {
+        __syncthreads();
+        for (int i = tid; i < n2; i += NT) cta_min[i] = static_cast<uint16_t>(min(K[i], 0xFFFFu));
+        return;
+    }
+    if (accepted) atomicAdd(job.count, accepted);
+}
+
 // cta_min[c][i2] <- min(seed[i2], min over c' < c of cta_min[c'][i2]); col_min[i2] = overall minimum.
 // seed (may be null) carries the minima of lower-ranked database shards (multi-GPU).
 // One WARP per column: lanes take 32 consecutive CTAs at a time and scan them with shuffles, so the
@@ -755,19 +1083,30 @@ __global__ void grid_scan_kernel(uint16_t *__restrict__ cta_min, int n_cta, int 
     const int i2 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i2 >= n2) return;
     uint32_t run = seed ? seed[i2] : D_INF;
-    for (int c0 = 0; c0 < n_cta; c0 += 32) {
-        const int c = c0 + lane;
-        const uint32_t t = (c < n_cta) ? cta_min[static_cast<size_t>(c) * n2 + i2] : D_INF;
-        uint32_t incl = t;
+    // 8 x 32 CTAs per trip: the loads of a trip are issued together (they alias the stores of the scan, so the
+    // compiler cannot hoist them itself) and the dependent chain is n_cta / 256 L2 round trips long
+    constexpr int TRIP = 8;
+    for (int c0 = 0; c0 < n_cta; c0 += 32 * TRIP) {
+        uint32_t t[TRIP];
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, s);
-            if (lane >= s) incl = min(incl, v);
+        for (int k = 0; k < TRIP; ++k) {
+            const int c = c0 + 32 * k + lane;
+            t[k] = (c < n_cta) ? cta_min[static_cast<size_t>(c) * n2 + i2] : D_INF;
         }
-        uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-        if (lane == 0) excl = D_INF;
-        if (c < n_cta) cta_min[static_cast<size_t>(c) * n2 + i2] = static_cast<uint16_t>(min(run, excl));
-        run = min(run, __shfl_sync(0xFFFFFFFFu, incl, 31));
+#pragma unroll
+        for (int k = 0; k < TRIP; ++k) {
+            const int c = c0 + 32 * k + lane;
+            uint32_t incl = t[k];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+                if (lane >= s) incl = min(incl, v);
+            }
+            uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+            if (lane == 0) excl = D_INF;
+            if (c < n_cta) cta_min[static_cast<size_t>(c) * n2 + i2] = static_cast<uint16_t>(min(run, excl));
+            run = min(run, __shfl_sync(0xFFFFFFFFu, incl, 31));
+        }
     }
     if (col_min && lane == 0) col_min[i2] = static_cast<uint16_t>(run);
 }

@@ -79,6 +79,7 @@ struct plm_ctx {
     bool cluster_attr_set = false;
     int knn_occ[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
+    bool rows_attr_set = false;
     // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -178,6 +179,7 @@ int g_frames_pairs_per_row[2] = {8, 0};
 int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame pipeline (128 or 256; measurement knob)
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
+int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
 
 // -1 = automatic (variant 3 for long slices, 1 otherwise); 0..3 force a variant (measurement only)
 int g_knn_variant = -2;
@@ -320,6 +322,10 @@ PLM_API int plm_set_option(const char *key, int value) {
     if (!key) return fail(PLM_E_INVALID, "null key");
     if (std::strcmp(key, "knn_variant") == 0) {
         g_knn_variant = (value >= 0 && value <= 3) ? value : -1;
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "grid_rows") == 0) {
+        g_grid_rows = value ? 1 : 0;
         return PLM_OK;
     }
     if (std::strcmp(key, "grid_cluster") == 0) {
@@ -808,38 +814,96 @@ int launch_grid_cluster(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, 
     return PLM_OK;
 }
 
-// Map-sized job: pass 0 (per-CTA minima) -> scan -> pass 1 (match) -> mutual check.
-// scratch: cta_min [n_cta][n2] u16, m21key [n2] u64, m21 [n2] i32 -- offsets into ctx->d_buf.
-int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams gp, size_t off_cta_min, size_t off_m21key,
-                        size_t off_m21, int warps, int n_cta) {
-    const size_t smem = size_t(warps) * job.n2 * 2;
+
+// Map-sized jobs.  Row-parallel kernels (one thread per row, csrc/plm_grid.cuh grid_rows_kernel) whenever their
+// per-column work arrays fit shared memory, else the warp-per-chunk kernels.  warps == 0 selects the row-parallel
+// form; n_cta is sized so that the whole launch is one wave of co-resident CTAs.
+
+int plan_map_grid(plm_ctx *ctx, long long n1, int n2, int n_cells, bool is_lines, plm::GridParams &gp, int &warps, int &n_cta,
+                  size_t &smem) {
+    const size_t optin = ctx->smem_optin - 2048;
+    const int n2c = std::max(n2, 1);
+    // shared memory: per-column work arrays + block arrays are fixed; the frame side is staged when everything stays
+    // under ~72 KB (3 CTAs per SM); the pair list takes what is left, at least 2048 entries
+    const size_t fixed = plm::grid_rows_layout(n2c, is_lines, 0, n_cells, 0, 0).total;
+    if (g_grid_rows && n2c <= 0xFFFF && fixed + 2048 * 4 <= std::min<size_t>(optin, 160 * 1024)) {
+        warps = 0;
+        const size_t target = 72 * 1024;
+        const size_t frame = plm::grid_rows_layout(n2c, is_lines, 0, n_cells, 0, 1).total - fixed;
+        gp.staged = (fixed + frame + 3072 * 4 <= target) ? 1 : 0;
+        size_t room = std::max<size_t>(target, fixed + 2048 * 4 + 64) - fixed - (gp.staged ? frame : 0);
+        gp.cap_items = gp.staged ? static_cast<int>(std::min<size_t>(room / 4 / 4, 8192)) : 0; // <= a quarter of the room
+        room -= plm::grid_align16(size_t(gp.cap_items) * 4);
+        gp.cap_pairs = static_cast<int>(std::min<size_t>(room / 4 - 8, 16384));
+        smem = plm::grid_rows_layout(n2c, is_lines, gp.cap_pairs, n_cells, gp.cap_items, gp.staged).total;
+        if (!ctx->rows_attr_set) {
+            CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+            CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+            CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+            CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+            ctx->rows_attr_set = true;
+        }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plm::grid_rows_kernel<1, 1>, plm::GRID_ROW_THREADS, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        const long long resident = static_cast<long long>(ctx->sm_count) * per_sm;
+        const long long blocks = (n1 + plm::GRID_ROW_THREADS - 1) / plm::GRID_ROW_THREADS;
+        const long long per_cta = std::max<long long>(1, (blocks + resident - 1) / resident); // blocks of rows per CTA
+        gp.rows_per_cta = static_cast<int>(per_cta * plm::GRID_ROW_THREADS);
+        n_cta = static_cast<int>((n1 + gp.rows_per_cta - 1) / gp.rows_per_cta);
+        return PLM_OK;
+    }
+    const size_t budget = std::min<size_t>(optin, 200 * 1024);
+    warps = 16;
+    while (warps > 1 && size_t(warps) * n2c * 2 > budget) warps >>= 1;
+    const long long rows_per_cta = static_cast<long long>(warps) * GRID_CHUNK_ROWS_PER_WARP;
+    n_cta = static_cast<int>((n1 + rows_per_cta - 1) / rows_per_cta);
+    smem = size_t(warps) * n2c * 2;
+    gp.rows_per_warp = GRID_CHUNK_ROWS_PER_WARP;
     for (int pass = 0; pass < 2; ++pass) {
         if (ctx->chunked_attr[pass] < smem) {
             if (pass == 0)
-                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(ctx->smem_optin - 2048)));
+                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
             else
-                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(ctx->smem_optin - 2048)));
-            ctx->chunked_attr[pass] = ctx->smem_optin - 2048;
+                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+            ctx->chunked_attr[pass] = optin;
         }
     }
-    gp.rows_per_warp = GRID_CHUNK_ROWS_PER_WARP;
+    return PLM_OK;
+}
+
+int launch_map_grid(plm_ctx *ctx, int pass, const plm::GridJob &job, const plm::GridParams &gp, int warps, int n_cta, size_t smem) {
+    if (n_cta <= 0) return PLM_OK;
+    if (warps == 0) {
+        if (pass == 0 && gp.staged) plm::grid_rows_kernel<0, 1><<<n_cta, plm::GRID_ROW_THREADS, smem, ctx->stream>>>(job, gp);
+        else if (pass == 0) plm::grid_rows_kernel<0, 0><<<n_cta, plm::GRID_ROW_THREADS, smem, ctx->stream>>>(job, gp);
+        else if (gp.staged) plm::grid_rows_kernel<1, 1><<<n_cta, plm::GRID_ROW_THREADS, smem, ctx->stream>>>(job, gp);
+        else plm::grid_rows_kernel<1, 0><<<n_cta, plm::GRID_ROW_THREADS, smem, ctx->stream>>>(job, gp);
+    } else {
+        if (pass == 0) plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+        else plm::grid_match_chunked_kernel<1><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
+    }
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// Map-sized job: pass 0 (per-CTA minima) -> scan -> pass 1 (match) -> mutual check.
+// scratch: cta_min [n_cta][n2] u16, m21key [n2] u64, m21 [n2] i32 -- offsets into ctx->d_buf.
+int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams gp, size_t off_cta_min, size_t off_m21key,
+                        size_t off_m21, int warps, int n_cta, size_t smem) {
+    int st;
     gp.cta_min = reinterpret_cast<uint16_t *>(ctx->d_buf + off_cta_min);
     gp.m21key = reinterpret_cast<unsigned long long *>(ctx->d_buf + off_m21key);
     int32_t *m21 = reinterpret_cast<int32_t *>(ctx->d_buf + off_m21);
     if (gp.best_lr) {
         CU_TRY(cudaMemsetAsync(gp.m21key, 0xFF, size_t(job.n2) * 8, ctx->stream));
-        plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
-        ctx->launches++;
-        CU_TRY(cudaGetLastError());
+        if ((st = launch_map_grid(ctx, 0, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
         plm::grid_scan_kernel<<<(job.n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, job.n2, nullptr, nullptr);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
     }
-    plm::grid_match_chunked_kernel<1><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
-    ctx->launches++;
-    CU_TRY(cudaGetLastError());
+    if ((st = launch_map_grid(ctx, 1, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
     if (gp.best_lr) {
         plm::m21_from_keys_kernel<<<(job.n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.m21key, job.n2, m21);
         ctx->launches++;
@@ -884,13 +948,12 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
 
     const bool fused = n1 <= GRID_FUSED_MAX_ROWS && n1 < (1 << plm::GRID_KEY_BITS);
     int warps = 0, n_cta = 0;
+    size_t map_smem = 0;
     size_t o_cta_min = 0, o_m21key = 0, o_m21 = 0;
+    plm::GridParams gp;
+    std::memset(&gp, 0, sizeof(gp));
     if (!fused) {
-        const size_t budget = std::min<size_t>(ctx->smem_optin - 2048, 200 * 1024);
-        warps = 16;
-        while (warps > 1 && size_t(warps) * std::max(n2, 1) * 2 > budget) warps >>= 1;
-        const long long rows_per_cta = static_cast<long long>(warps) * GRID_CHUNK_ROWS_PER_WARP;
-        n_cta = static_cast<int>((n1 + rows_per_cta - 1) / rows_per_cta);
+        if ((st = plan_map_grid(ctx, n1, n2, n_cells, is_lines != 0, gp, warps, n_cta, map_smem)) != PLM_OK) return st;
         o_cta_min = L.add(size_t(n_cta) * std::max(n2, 1) * 2);
         o_m21key = L.add(size_t(std::max(n2, 1)) * 8);
         o_m21 = L.add(size_t(std::max(n2, 1)) * 4);
@@ -926,8 +989,6 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
 
     CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
 
-    plm::GridParams gp;
-    std::memset(&gp, 0, sizeof(gp));
     gp.grid_rows = grid_rows;
     gp.grid_cols = grid_cols;
     gp.best_lr = best_lr ? 1 : 0;
@@ -939,7 +1000,7 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     } else if (fused) {
         st = launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(ctx->d_buf + o_job), 1, gp, n1, std::max(n2, 1), std::max(n_items, 1), is_lines != 0);
     } else {
-        st = launch_grid_chunked(ctx, job, gp, o_cta_min, o_m21key, o_m21, warps, n_cta);
+        st = launch_grid_chunked(ctx, job, gp, o_cta_min, o_m21key, o_m21, warps, n_cta, map_smem);
     }
     if (st != PLM_OK) return st;
     CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_m12, ctx->d_buf + o_m12, size_t(n1) * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1006,24 +1067,7 @@ int dev_grid_setup(plm_ctx *&ctx, const plm_dev_grid_args *a, plm::GridJob &job,
     gp.best_lr = a->best_lr ? 1 : 0;
     gp.ratio = a->ratio;
     gp.line_sim_th = a->line_sim_th;
-    gp.rows_per_warp = GRID_CHUNK_ROWS_PER_WARP;
-    const size_t budget = std::min<size_t>(ctx->smem_optin - 2048, 200 * 1024);
-    warps = 16;
-    while (warps > 1 && size_t(warps) * std::max(a->n2, 1) * 2 > budget) warps >>= 1;
-    const long long rows_per_cta = static_cast<long long>(warps) * GRID_CHUNK_ROWS_PER_WARP;
-    n_cta = static_cast<int>((a->n1 + rows_per_cta - 1) / rows_per_cta);
-    smem = size_t(warps) * std::max(a->n2, 1) * 2;
-    for (int pass = 0; pass < 2; ++pass) {
-        if (ctx->chunked_attr[pass] < smem) {
-            if (pass == 0)
-                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(ctx->smem_optin - 2048)));
-            else
-                CU_TRY(cudaFuncSetAttribute(plm::grid_match_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(ctx->smem_optin - 2048)));
-            ctx->chunked_attr[pass] = ctx->smem_optin - 2048;
-        }
-    }
+    if ((st = plan_map_grid(ctx, a->n1, a->n2, a->grid_rows * a->grid_cols, a->is_lines != 0, gp, warps, n_cta, smem)) != PLM_OK) return st;
     const size_t cta_min_bytes = align_up(size_t(std::max(n_cta, 1)) * std::max(a->n2, 1) * 2);
     st = ctx->ensure_device(cta_min_bytes + extra_bytes);
     if (st != PLM_OK) return st;
@@ -1047,9 +1091,7 @@ PLM_API int plm_dev_grid_colmin(plm_ctx *ctx, const plm_dev_grid_args *a, uint16
         CU_TRY(cudaMemsetAsync(col_min_dev, 0xFF, size_t(a->n2) * 2, ctx->stream));
         return PLM_OK;
     }
-    plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
-    ctx->launches++;
-    CU_TRY(cudaGetLastError());
+    if ((st = launch_map_grid(ctx, 0, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
     plm::grid_scan_kernel<<<(a->n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, nullptr, col_min_dev);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
@@ -1068,17 +1110,12 @@ PLM_API int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const u
     if (gp.best_lr && a->n2 > 0) CU_TRY(cudaMemsetAsync(m21key_dev, 0xFF, size_t(a->n2) * 8, ctx->stream));
     if (n_cta == 0 || a->n2 == 0) return PLM_OK;
     if (gp.best_lr) {
-        plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
-        ctx->launches++;
-        CU_TRY(cudaGetLastError());
+        if ((st = launch_map_grid(ctx, 0, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
         plm::grid_scan_kernel<<<(a->n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, seed_dev, nullptr);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
     }
-    plm::grid_match_chunked_kernel<1><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
-    ctx->launches++;
-    CU_TRY(cudaGetLastError());
-    return PLM_OK;
+    return launch_map_grid(ctx, 1, job, gp, warps, n_cta, smem);
 }
 
 // The whole row-sharded matchGrid of one rank, launched back to back from C: minima pass, the two peer-memory
@@ -1108,9 +1145,7 @@ PLM_API int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a,
     if (gp.best_lr && n2 > 0) {
         CU_TRY(cudaMemsetAsync(X, 0xFF, L.total, ctx->stream)); // identities of both reductions, absent keys, m21 = -1
         if (n_cta > 0) {
-            plm::grid_match_chunked_kernel<0><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
-            ctx->launches++;
-            CU_TRY(cudaGetLastError());
+            if ((st = launch_map_grid(ctx, 0, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
             plm::grid_scan_kernel<<<(n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, n2, nullptr, col_min);
             ctx->launches++;
             CU_TRY(cudaGetLastError());
@@ -1127,11 +1162,7 @@ PLM_API int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a,
         }
     }
     gp.m21key = reinterpret_cast<unsigned long long *>(key);
-    if (n_cta > 0 && n2 > 0) {
-        plm::grid_match_chunked_kernel<1><<<n_cta, warps * 32, smem, ctx->stream>>>(job, gp);
-        ctx->launches++;
-        CU_TRY(cudaGetLastError());
-    }
+    if (n_cta > 0 && n2 > 0 && (st = launch_map_grid(ctx, 1, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
     if (gp.best_lr && n2 > 0) {
         // per-column best pairs over all shards, then the mutual check on this shard's rows
         if ((st = plm_dev_peer_reduce(ctx, g->xchg, g->rank, g->world, g->q_cap, epoch++, PLM_PEER_MIN_U64, key,

@@ -274,3 +274,83 @@ def test_gpu_vs_golden(M):
                 for blr in (0, 1):
                     n, m = gpu_grid(case, ratio, blr)
                     assert n == int(z[f"n_{ratio}_{blr}"]) and (m == z[f"m_{ratio}_{blr}"]).all(), name
+
+
+def test_match_grid_map_scale_record_chains(M):
+    """Row-parallel map-scale kernel (grid_rows_kernel): every row of a block improves the running column minimum
+    of the same train feature, so the rounds that resolve the live pairs run one record at a time (the worst case
+    of matching.cpp:145-150 for the parallel form), next to ordinary rows."""
+    rng = np.random.default_rng(5)
+    n2, n1 = 64, 6000
+    d2 = synth.rand_desc(rng, n2)
+    case = random_grid_case(rng, n1, n2, tie=False, win=(2, 2, 2, 2), off_grid=0)
+    case["d2"] = d2
+    # all train features in distinct cells of a small patch; rows 1000..1511 sit on train feature 7's cell and get
+    # closer to it row by row (distance 255, 254, ... then a plateau of equal distances, then closer again)
+    cs = np.zeros(48 * 64 + 1, np.int32)
+    cells = (np.arange(n2) % 8) * 48 + (np.arange(n2) // 8)          # cell id = x * rows + y
+    order = np.argsort(cells, kind="stable")
+    counts = np.bincount(cells, minlength=48 * 64)
+    cs[1:] = np.cumsum(counts)
+    case["cell_start"], case["cell_items"] = cs, order.astype(np.int32)
+    x7, y7 = int(cells[7] // 48), int(cells[7] % 48)
+    rows = np.arange(1000, 1512)
+    case["coords"][rows] = (x7, y7)
+    flips = np.concatenate([np.arange(255, 55, -1), np.full(112, 55), np.arange(54, -146, -1).clip(1)])[:512]
+    bits = np.unpackbits(d2[7])
+    for r, k in zip(rows, flips):
+        b = bits.copy()
+        b[rng.choice(256, int(k), replace=False)] ^= 1
+        case["d1"][r] = np.packbits(b)
+    for best_lr in (1, 0):
+        for ratio in (0.9, 1.0):
+            n_o, m_o = oracle_grid(port, case, ratio, best_lr)
+            n_g, m_g = gpu_grid(case, ratio, best_lr)
+            assert n_g == n_o and (m_g == m_o).all(), (best_lr, ratio, np.flatnonzero(m_g != m_o)[:10])
+
+
+@pytest.mark.parametrize("is_lines", [False, True])
+def test_match_grid_map_scale_both_kernel_families(M, plm_lib, is_lines):
+    """Config 4 at full row count (200 000 points / 50 000 lines against one frame): the row-parallel kernels
+    (several blocks of rows per CTA) and the warp-per-chunk kernels (option grid_rows = 0) against the oracle."""
+    rng = np.random.default_rng(3030 + int(is_lines))
+    n1, n2 = (200_000, 600) if not is_lines else (50_000, 200)
+    case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=False, win=(3, 3, 3, 3), zero_len=7 if is_lines else 0)
+    stale = np.full(n1, -1, np.int32)
+    stale[rng.choice(n1, 500, replace=False)] = rng.integers(0, n2, 500)
+    n_o, m_o = oracle_grid(port, case, 0.9, 1, m12=stale)
+    for rows_mode in (1, 0):
+        assert plm_lib.plm_set_option(b"grid_rows", rows_mode) == 0
+        try:
+            n_g, m_g = gpu_grid(case, 0.9, 1, m12=stale)
+        finally:
+            plm_lib.plm_set_option(b"grid_rows", 1)
+        assert n_g == n_o and (m_g == m_o).all(), rows_mode
+
+
+def test_match_grid_map_scale_wide_frame(M):
+    """A train side too large for the shared-memory staging (n2 = 9000) and one too large for the row-parallel
+    work arrays (n2 = 20000 -> warp-per-chunk kernels)."""
+    for n2 in (9000, 20000):
+        rng = np.random.default_rng(n2)
+        case = random_grid_case(rng, 7000, n2, tie=False, win=(1, 1, 1, 1))
+        n_o, m_o = oracle_grid(port, case, 0.9, 1)
+        n_g, m_g = gpu_grid(case, 0.9, 1)
+        assert n_g == n_o and (m_g == m_o).all(), n2
+
+
+@pytest.mark.parametrize("is_lines", [False, True])
+def test_match_grid_map_scale_dense_windows(M, is_lines):
+    """Windows so wide that a block of 256 rows has more slots than the shared-memory pair list holds: the
+    row-parallel kernel takes its re-walk form (same rounds, every thread walking its own row)."""
+    rng = np.random.default_rng(91 + int(is_lines))
+    n1, n2 = 6000, (300 if not is_lines else 120)
+    case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=False, win=(20, 20, 16, 16), zero_len=3 if is_lines else 0)
+    for best_lr in (1, 0):
+        n_o, m_o = oracle_grid(port, case, 0.9, best_lr)
+        n_g, m_g = gpu_grid(case, 0.9, best_lr)
+        assert n_g == n_o and (m_g == m_o).all(), best_lr
+    case = random_grid_case(rng, 5000, 200, is_lines=is_lines, tie=True, win=(30, 30, 30, 30))
+    n_o, m_o = oracle_grid(port, case, 0.9, 1)
+    n_g, m_g = gpu_grid(case, 0.9, 1)
+    assert n_g == n_o and (m_g == m_o).all()
