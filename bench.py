@@ -39,9 +39,11 @@ METRIC = "descriptor_pairs_per_s"
 UNIT = "pairs/s"
 N_KF, PER_KF = 20000, 800
 POPC_PER_PAIR = 8                 # one pair = 8 POPC.32 + 8 LOP(xor) + 7 adds
-# ALU-pipe instructions per pair counted from the SASS main loop of knn2_slice_kernel<128, V>
-ALU_INSTR_PER_PAIR = {"csa4": 17.0, "csa5": 22.0, "popc8": 16.0}
-POPC_ISSUED_PER_PAIR = {"csa4": 4, "csa5": 5, "popc8": 8}
+# instructions per pair on the two integer pipes, counted from the SASS main loop of knn2_slice_kernel<128, V>
+# (cuobjdump of the shipped library): ALU pipe = LOP3 + VIMNMX(3), XU pipe = POPC
+ALU_INSTR_PER_PAIR = {"t13": 13.625, "csa4": 16.75, "csa5": 22.0, "popc8": 16.0}
+POPC_ISSUED_PER_PAIR = {"t13": 4, "csa4": 4, "csa5": 5, "popc8": 8}
+DEFAULT_VARIANT = "t13"
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -59,6 +61,7 @@ def parse_args():
                     help="multi-GPU top-2 merge: the library's peer-memory kernel (auto falls back to NCCL) or NCCL all_gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-frame / replay side metrics")
+    ap.add_argument("--no-verify", action="store_true", help="skip the untimed verification step / multi-GPU check")
     return ap.parse_args()
 
 
@@ -248,6 +251,59 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+VERIFY_STEP = 777_000          # query seed of the untimed verification step (the same at every N)
+VERIFY_SAMPLE = 64             # queries checked against the reference on the WHOLE database
+
+
+def verify_step(db, args, dev, rank: int) -> dict:
+    """One untimed step whose result is (a) summarised as (count, crc32 of the match vector) -- identical at
+    N = 1/2/4/8 by construction -- and (b) checked on rank 0, for the first VERIFY_SAMPLE queries, against the
+    reference's own matchNNR (oracle/_ref, matching.cpp compiled unmodified) on all 16 M database rows."""
+    import zlib
+    import torch
+    q = gen_queries(VERIFY_STEP, args.kf_batch, args.n_kf)
+    count, m12 = db.match_nnr(torch.from_numpy(q).to(dev), args.nnr)
+    torch.cuda.synchronize()
+    m12_h = m12.cpu().numpy()
+    out = {"step_seed": VERIFY_STEP, "count": int(count.item()), "crc32_m12": zlib.crc32(m12_h.tobytes()) & 0xFFFFFFFF}
+    if rank == 0:
+        import oracle
+        full = gen_rows(0, args.n_kf)
+        if oracle.ref.available():
+            oracle.ref.set_threads(len(os.sched_getaffinity(0)))
+            n_s, m_s = oracle.ref.match_nnr(q[:VERIFY_SAMPLE], full, args.nnr)
+            out["checker"] = "oracle/_ref matchNNR (reference matching.cpp) on all database rows"
+        else:
+            n_s, m_s = oracle.port.match_nnr(q[:VERIFY_SAMPLE], full, args.nnr)
+            out["checker"] = "oracle port matchNNR on all database rows"
+        del full
+        out["sampled_queries"] = VERIFY_SAMPLE
+        out["sample_matches"] = int(n_s)
+        out["oracle_ok"] = bool((m12_h[:VERIFY_SAMPLE] == m_s).all() and int((m12_h[:VERIFY_SAMPLE] >= 0).sum()) == int(n_s))
+        out["ok"] = out["oracle_ok"]
+    return out
+
+
+def dist_check(rank: int, world: int, local_rank: int, dev) -> dict:
+    """N > 1: every sharded path (flat database through both exchange forms, row-sharded matchGrid + match fallback)
+    against the oracle on every rank before anything is timed (tests/dist_gpu_check.py, compact sizes)."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    info = {}
+    try:
+        import dist_gpu_check
+        info = dist_gpu_check.run_checks(rank, world, local_rank, dev, compact=True)
+    except Exception as e:  # noqa: BLE001 -- reported in the line, the run still fails below
+        ok.zero_()
+        info = {"ok": False, "error": repr(e)[:300]}
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    info["ok"] = bool(ok.item())
+    return info
+
+
+# ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -263,8 +319,10 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        import datetime
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that dies in the pre-timing check must take the job down instead of hanging its peers
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     n_rows = args.n_kf * PER_KF
     lo, hi = shard_bounds(n_rows, world, rank)
@@ -289,6 +347,14 @@ def run_b200(args):
     def step_device(q):
         count, m12 = db.match_nnr(q, args.nnr)
         return count, m12
+
+    # ---- correctness before anything is timed ------------------------------------------------
+    dcheck = dist_check(rank, world, local_rank, dev) if (world > 1 and not args.no_verify) else None
+    if dcheck is not None and not dcheck["ok"]:
+        raise SystemExit(f"dist_check failed: {dcheck}")
+    verify = verify_step(db, args, dev, rank) if not args.no_verify else None
+    if rank == 0 and verify is not None and not verify["ok"]:
+        raise SystemExit(f"verification against the reference failed: {verify}")
 
     # ---- live integer-pipe peaks (roofline denominators) -------------------------------------
     popc_gops, lop3_gops = ctx.measure_int_peaks()
@@ -357,6 +423,16 @@ def run_b200(args):
     if db.peer is not None:
         db.peer.check()  # raises if any peer-memory exchange timed out
 
+    # ---- config 4 (map -> frame, row-sharded map) at this N: collective, every rank takes part -----------
+    config4 = None
+    if not args.no_extras:
+        try:
+            import bench_extras
+            config4 = bench_extras.map_to_frame(ctx, world, rank)
+        except Exception as e:  # noqa: BLE001 -- a side metric must never kill the headline line
+            config4 = {"error": repr(e)[:300]}
+        barrier()
+
     # ---- max over ranks ------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_ms, e2e_wall * 1e3, slice_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -370,38 +446,50 @@ def run_b200(args):
         pairs_per_launch = float(n_q) * float(hi - lo)
         launch_ms = slice_ms / max(slice_n, 1)
         popc_equiv = pairs_per_launch * POPC_PER_PAIR / (launch_ms * 1e-3) * 1e-9  # Gop/s
-        variant = os.environ.get("PLM_KNN_VARIANT", "csa4")
-        variant = variant if variant in ALU_INSTR_PER_PAIR else "csa4"
-        variant_csa = variant != "popc8"
-        alu_per_pair = ALU_INSTR_PER_PAIR[variant]
-        alu_rate = pairs_per_launch * alu_per_pair / (launch_ms * 1e-3) * 1e-9
+        variant = os.environ.get("PLM_KNN_VARIANT", DEFAULT_VARIANT)
+        variant = variant if variant in ALU_INSTR_PER_PAIR else DEFAULT_VARIANT
+        pairs_rate = pairs_per_launch / (launch_ms * 1e-3) * 1e-9                   # G pairs/s inside the kernel
+        pipes = {
+            "xu_popc": {"instr_per_pair": POPC_ISSUED_PER_PAIR[variant], "achieved": pairs_rate * POPC_ISSUED_PER_PAIR[variant],
+                        "peak": popc_gops},
+            "alu_lop3": {"instr_per_pair": ALU_INSTR_PER_PAIR[variant], "achieved": pairs_rate * ALU_INSTR_PER_PAIR[variant],
+                         "peak": lop3_gops},
+        }
+        for v in pipes.values():
+            v["frac"] = v["achieved"] / v["peak"]
+            v["unit"] = "Ginstr/s"
+        binding = max(pipes, key=lambda k: pipes[k]["frac"])
         algo_bytes = 32.0 * (n_q + (hi - lo)) + 16.0 * n_q
         hbm_peak = 6535.4
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             pass
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "knn2_slice_traffic.json")))["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "knn2_slice_traffic.json")))
+            if tj.get("variant") == variant:     # only a capture of the kernel that actually ran counts
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
         except Exception:
             pass
         roofline = {
-            "kernel": "knn2_slice_kernel (brute-force Hamming top-2)",
+            "kernel": f"knn2_slice_kernel<128, {variant}> (brute-force Hamming top-2)",
             "bound": "int",
-            "unit": "Gop/s (POPC.32-equivalents, 8 per descriptor pair as SURVEY 8d defines the unit of work)",
-            "achieved": popc_equiv, "peak": popc_gops, "frac": popc_equiv / popc_gops,
-            "peak_source": "measured in this run (plm_measure_int_peaks, independent POPC chains)",
+            "pipe": binding,
+            "unit": "Ginstr/s issued on the binding integer pipe (instructions per pair counted from the SASS main loop)",
+            "achieved": pipes[binding]["achieved"], "peak": pipes[binding]["peak"], "frac": pipes[binding]["frac"],
+            "peak_source": "measured in this run (plm_measure_int_peaks: independent POPC / LOP3 chains on every SM)",
+            "pipes": pipes,
             "kernel_ms_per_launch": launch_ms, "launches_timed": slice_n,
             "share_of_step": slice_ms / dev_ms,
-            "variant": variant, "popc_issued_per_pair": POPC_ISSUED_PER_PAIR[variant],
-            "note": ("the kernel uses a carry-save form (4 POPC + 16 LOP3 per pair), so it can exceed the 8-POPC "
-                     "roofline; the pipe that actually binds is the ALU pipe below") if variant_csa else "plain 8-POPC form",
-            "alu_pipe": {"unit": "Ginstr/s", "achieved": alu_rate, "peak": lop3_gops, "frac": alu_rate / lop3_gops,
-                         "instr_per_pair": alu_per_pair},
+            "variant": variant,
+            "popc8_equivalent": {"unit": "Gop/s (8 POPC.32 per pair, the unit of work of SURVEY 8d)", "achieved": popc_equiv,
+                                 "peak": popc_gops, "frac": popc_equiv / popc_gops,
+                                 "note": "secondary figure: the kernel issues 4 POPC + 13 LOP3 per pair (carry-save form in a "
+                                         "transformed domain), so it exceeds a roofline that assumes 8 POPC per pair"},
             "hbm": {"unit": "GB/s", "achieved": algo_bytes / (launch_ms * 1e-3) * 1e-9, "peak": hbm_peak,
                     "frac": algo_bytes / (launch_ms * 1e-3) * 1e-9 / hbm_peak, "algorithmic_bytes_per_launch": algo_bytes},
-            "traffic": traffic,
+            "traffic": traffic, "traffic_source": traffic_src,
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -418,6 +506,8 @@ def run_b200(args):
             "pairs_per_step": pairs_per_step,
             "reference_equivalent_pairs_per_s": value,
             "matches_last_step": n_matches,
+            "verify": verify, "dist_check": dcheck,
+            "config4_map_to_frame": config4,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_q * 32,
                     "d2h_bytes_per_step": n_q * 4 + 4, "ms_per_step_device": e2e_ms / args.steps,
                     "ms_per_step_wall": e2e_wall_ms / args.steps,

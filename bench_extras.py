@@ -274,17 +274,20 @@ def replay_cpu_baseline(n_frames: int, seconds: float = 8.0) -> dict:
                       "(popcount-SWAR distance, scalar), all stages of the replay"}
 
 
-def map_to_frame(ctx) -> dict:
-    """Config 4 on one GPU: a 200 000-point / 50 000-line local map (desc1, with projected cell
-    coordinates) against one frame (600 / 200 features): matchGrid with a +-3 window, then the forced
-    brute-force match() fallback on the same vector.  Device-resident timings (CUDA events) plus the
+def map_to_frame(ctx, world: int = 1, rank: int = 0, host_call: bool = True) -> dict:
+    """Config 4 at N GPUs: a 200 000-point / 50 000-line local map (desc1, with projected cell coordinates),
+    row-sharded over the ranks, against one frame (600 / 200 features): matchGrid with a +-3 window, then the
+    forced brute-force match() fallback on the same vector (mapHandler.cpp:637-650, :752-765), exchanges included.
+    Collective: every rank calls it.  Device-resident timings (CUDA events, max over ranks); at N = 1 also the
     host-buffer call."""
     import torch
-    from pl_inertial_slam_b200.database import GridFrame, ShardedMap
+    import torch.distributed as dist
+    from pl_inertial_slam_b200.database import DeviceOps, GridFrame, ShardedMap, shard_bounds
     from pl_inertial_slam_b200 import grid as G
     sp = synth.make_stereo_pair(synth.SEED0 + 4)
-    out = {}
+    out = {"n_gpus": world}
     dev = torch.device("cuda", torch.cuda.current_device())
+    ops = DeviceOps(dev.index)
     for name, n_map, is_lines in (("points_200k_x_600", 200_000, False), ("lines_50k_x_200", 50_000, True)):
         rng = np.random.default_rng(synth.SEED0 + 40 + int(is_lines))
         if not is_lines:
@@ -303,32 +306,47 @@ def map_to_frame(ctx) -> dict:
             cs, ci, dirs = line_grid(sp.ln_l, synth.INV_W, synth.INV_H)
         frame = GridFrame(torch.from_numpy(d2).to(dev), torch.from_numpy(cs).to(dev), torch.from_numpy(ci).to(dev),
                           G.GRID_ROWS, G.GRID_COLS, torch.from_numpy(dirs).to(dev) if dirs is not None else None)
-        from pl_inertial_slam_b200.database import DeviceOps
-        ops = DeviceOps(dev.index)
-        smap = ShardedMap(n_map, torch.from_numpy(d1).to(dev), torch.from_numpy(coords).to(dev), ops=ops)
+        lo, hi = shard_bounds(n_map, world, rank)
+        smap = ShardedMap(n_map, torch.from_numpy(np.ascontiguousarray(d1[lo:hi])).to(dev),
+                          torch.from_numpy(np.ascontiguousarray(coords[lo:hi])).to(dev), ops=ops)
         win = np.array([3, 3, 3, 3], np.int32)
 
-        def timed(fn, reps=10):
-            fn(); torch.cuda.synchronize()
+        def timed(fn, reps=20):
+            for _ in range(3):
+                r = fn()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
                 r = fn()
             e1.record(); torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps, r
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()), r
 
         g_ms, (cnt, m12) = timed(lambda: smap.match_grid(frame, win, 0.9, 0.75, True))
-        f_ms, (cnt2, _) = timed(lambda: smap.match(frame.d2, 0.9, True, m12_inout=m12))
-        grid_arg = (cs, ci, G.GRID_ROWS, G.GRID_COLS)
-        M.Config.minRatio12P = 0.9
-        if dirs is None:
-            host_ms = _median_ms(lambda: M.matchGrid(coords, d1, grid_arg, d2, win, np.full(n_map, -1, np.int32), ctx=ctx), reps=8, warm=2)
-        else:
-            host_ms = _median_ms(lambda: M.matchGrid(coords, d1, grid_arg, d2, dirs, win, np.full(n_map, -1, np.int32), ctx=ctx), reps=8, warm=2)
+        f_ms, (cnt2, m12b) = timed(lambda: smap.match(frame.d2, 0.9, True, m12_inout=m12))
         pairs = float(n_map) * len(d2)
-        out[name] = {"matchGrid_device_ms": g_ms, "matchGrid_host_call_ms": host_ms, "matchGrid_matches": int(cnt.item()),
-                     "match_fallback_device_ms": f_ms, "match_fallback_unique_pairs_per_s": pairs / (f_ms * 1e-3),
-                     "match_fallback_count": int(cnt2.item())}
+        import zlib
+        res = {"matchGrid_device_ms": g_ms, "matchGrid_matches": int(cnt.item()),
+               "matchGrid_crc32": zlib.crc32(m12.cpu().numpy().tobytes()) & 0xFFFFFFFF,
+               "match_fallback_device_ms": f_ms, "match_fallback_unique_pairs_per_s": pairs / (f_ms * 1e-3),
+               "match_fallback_count": int(cnt2.item()),
+               "match_fallback_crc32": zlib.crc32(m12b.cpu().numpy().tobytes()) & 0xFFFFFFFF,
+               "exchange": "none" if world == 1 else ("peer-memory kernels" if smap.peer is not None else "nccl")}
+        if world == 1 and host_call:
+            grid_arg = (cs, ci, G.GRID_ROWS, G.GRID_COLS)
+            M.Config.minRatio12P = 0.9
+            if dirs is None:
+                res["matchGrid_host_call_ms"] = _median_ms(lambda: M.matchGrid(coords, d1, grid_arg, d2, win, np.full(n_map, -1, np.int32), ctx=ctx), reps=8, warm=2)
+            else:
+                res["matchGrid_host_call_ms"] = _median_ms(lambda: M.matchGrid(coords, d1, grid_arg, d2, dirs, win, np.full(n_map, -1, np.int32), ctx=ctx), reps=8, warm=2)
+        if smap.peer is not None:
+            smap.peer.check()
+        out[name] = res
     return out
 
 
@@ -529,10 +547,6 @@ def run(ctx, args) -> dict:
             out[name] = fn(ctx, cpu=not args.no_cpu_baseline)
         except Exception as e:  # noqa: BLE001
             out[name] = {"error": repr(e)}
-    try:
-        out["map_to_frame"] = map_to_frame(ctx)
-    except Exception as e:  # noqa: BLE001
-        out["map_to_frame"] = {"error": repr(e)}
     n = int(os.environ.get("PLM_REPLAY_FRAMES", "10000"))
     rp = synth.make_replay(synth.SEED0 + 3, n)
     out["replay"] = replay_pipeline(ctx, n, rp)

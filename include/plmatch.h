@@ -40,7 +40,9 @@
  *    every compute entry point returns PLM_E_CUDA.
  *  - A plm_ctx owns one CUDA stream, device scratch and pinned staging.  It may be used by one
  *    host thread at a time; pass NULL to use a lazily created per-thread default context
- *    (re-entrant from any number of host threads).
+ *    (re-entrant from any number of host threads).  A call makes the context's device current for the
+ *    calling thread and leaves it current (like cudaSetDevice); callers that run their own CUDA code on another
+ *    device on the same thread must switch back themselves.
  *  - Packed top-2 keys: key = (uint64)distance << 32 | train_index, UINT64_MAX when absent;
  *    unsigned min over keys == the reference's lowest-index tie-breaking.
  */
@@ -60,13 +62,15 @@ extern "C" {
 #define PLM_E_INVALID     -1 /* null pointer, negative size, step < 32, misaligned device pointer  */
 #define PLM_E_SIZE        -2 /* size mismatch: "[matchNNR] Different size for matches and descriptors!",
                                 "[matchGrid] Each point/line needs a corresponding descriptor!"      */
-#define PLM_E_TRAIN       -3 /* fewer than 2 train rows for an NNR test (UB in the reference)        */
+#define PLM_E_TRAIN       -3 /* empty train set with a non-empty query: the reference throws
+                                "[matchNNR] Different size for matches and descriptors!" (matching.cpp:50-51) */
 #define PLM_E_GRID        -4 /* "[GridStructure] invalid dimension" or malformed CSR                  */
 #define PLM_E_RATIO       -5 /* matchGrid ratio > 1: the reference's result then depends on
                                 unordered_set iteration order                                        */
 #define PLM_E_CUDA        -6 /* CUDA runtime failure (see plm_last_error)                            */
 #define PLM_E_NOMEM       -7
 #define PLM_E_UNSUPPORTED -8 /* size outside what the kernels support (documented per function)      */
+#define PLM_E_PEER        -9 /* a device did not arrive at a peer-memory exchange within the spin limit  */
 
 typedef struct plm_ctx plm_ctx;
 typedef struct plm_db plm_db;
@@ -106,11 +110,15 @@ int plm_hamming256(plm_ctx *ctx, const uint8_t *a, size_t step_a, const uint8_t 
 int plm_knn2(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
              size_t step2, uint64_t idx_base, uint64_t *top2);
 
-/* StVO::matchNNR.  Accept row i iff (float)d0 < (float)d1 * nnr (float arithmetic, as :54). */
+/* StVO::matchNNR.  Accept row i iff (float)d0 < (float)d1 * nnr (float arithmetic, as :54).
+ * Degenerate sizes: n1 == 0 -> 0 matches (as the reference); n2 == 0 with n1 > 0 -> PLM_E_TRAIN (the reference
+ * throws); n2 == 1 -> no row has a second neighbour, none is accepted, m12 stays as it was (the reference reads
+ * matches_[idx][1] out of bounds there, :54 -- undefined, but it does not throw). */
 int plm_match_nnr(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
                   size_t step2, float nnr, int32_t *m12_inout, int *n_matches);
 
-/* StVO::match.  best_lr = Config::bestLRMatches(): both directions + mutual check. */
+/* StVO::match.  best_lr = Config::bestLRMatches(): both directions + mutual check.  One-row sides follow the rule
+ * above per direction (with n1 == 1 no reverse match exists, so the mutual check culls every entry of m12). */
 int plm_match(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
               size_t step2, float nnr, int best_lr, int32_t *m12_inout, int *n_matches);
 
@@ -418,6 +426,42 @@ int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a, const p
 int plm_dev_sharded_match(plm_ctx *ctx, const void *d1_shard_dev, int n1, int64_t i1_base, const void *d2_dev, int n2,
                           float nnr, int best_lr, int32_t *m12_local_inout_dev, const plm_peer_group *g,
                           int64_t n_rows_total, int32_t *m12_global_dev, int32_t *count_global_dev, int32_t *error_dev);
+
+/* ---- multi-device keyframe database / local map inside ONE process ----------------------------------- */
+/* The entry point a single C++ host process (the reference's MapHandler: matchMap2KFPoints / Lines
+ * src/mapHandler.cpp:583-803, isLoopClosure :3301-3409) uses to spread the local map or the keyframe database over the
+ * GPUs of one box: the library owns the per-device contexts, enables peer access between every pair of devices,
+ * allocates the exchange buffers and drives the peer-memory kernels itself -- no launcher, no IPC, no NCCL.
+ * Rows are sharded contiguously (shard g = rows [g * per, (g + 1) * per), per = ceil(n_rows / n_devices)); every index
+ * in a result is GLOBAL, so results are bit-identical to the single-GPU calls.  devices[] must be distinct and
+ * mutually peer-accessible (PLM_E_UNSUPPORTED otherwise); n_devices == 1 is allowed (no exchange).
+ * q_cap = the largest query batch / frame (rows) one exchange carries; rows_cap = the largest database / map.
+ * One host thread at a time per plm_shard.  A timed-out exchange (option "peer_spin_ms", default ~2 s) makes the
+ * current or the next call return PLM_E_PEER and every later one too: outputs are never silently wrong. */
+typedef struct plm_shard plm_shard;
+int plm_shard_create(const int *devices, int n_devices, int q_cap, int64_t rows_cap, plm_shard **out);
+int plm_shard_destroy(plm_shard *s);
+int plm_shard_n_devices(const plm_shard *s);
+int64_t plm_shard_n_rows(const plm_shard *s);
+int plm_shard_range(const plm_shard *s, int i, int64_t *row_lo, int64_t *row_hi);
+uint64_t plm_shard_launch_count(const plm_shard *s);
+int plm_shard_synchronize(plm_shard *s);
+/* (Re)load the database / map: n_rows descriptors `step` bytes apart and, optionally (config 4), the grid-cell
+ * coordinates of the same rows: n_rows x coords_per_row int32, 2 = points (x, y), 4 = lines (sx, sy, ex, ey). */
+int plm_shard_upload(plm_shard *s, const uint8_t *rows, int64_t n_rows, size_t step, const int32_t *coords, int coords_per_row);
+/* Config 5, flat database: StVO::matchNNR / knnMatch(k = 2) of n1 host queries against all rows.  top2 (n1 x 2 packed
+ * keys), m12_inout + n_matches may each be NULL.  Batches above q_cap are processed in slices. */
+int plm_shard_match_nnr(plm_shard *s, const uint8_t *q, int n1, size_t step, float nnr, uint64_t *top2, int32_t *m12_inout,
+                        int *n_matches);
+/* Config 4: StVO::matchGrid with the sharded map as desc1 (mapHandler.cpp:637-642, :752-757).  Frame side as in
+ * plm_match_grid_points / _lines (lines when the uploaded coordinates have 4 columns; dirs2 then required);
+ * m12_inout = the global in/out vector (n_rows). */
+int plm_shard_match_grid(plm_shard *s, const int32_t *cell_start, const int32_t *cell_items, int grid_rows, int grid_cols,
+                         const uint8_t *d2, int n2, size_t step2, const double *dirs2, double line_sim_th, const int32_t win[4],
+                         double ratio, int best_lr, int32_t *m12_inout, int *n_matches);
+/* Config 4 fallback: StVO::match(map, frame) on the same in/out vector (mapHandler.cpp:645-650, :760-765). */
+int plm_shard_match(plm_shard *s, const uint8_t *d2, int n2, size_t step2, float nnr, int best_lr, int32_t *m12_inout,
+                    int *n_matches);
 
 /* A device-resident descriptor database shard (keyframe DB / local map). */
 int plm_db_create(plm_ctx *ctx, int64_t capacity_rows, plm_db **out);

@@ -152,6 +152,18 @@ SIGNATURES = {
     "plm_dev_sharded_match": (C.c_int, [vp, vp, C.c_int, C.c_int64, vp, C.c_int, C.c_float, C.c_int, vp, C.POINTER(PeerGroup),
                                         C.c_int64, vp, vp, vp]),
     "plm_dev_peer_reduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_int, vp, vp]),
+    "plm_shard_create": (C.c_int, [intp, C.c_int, C.c_int, C.c_int64, C.POINTER(vp)]),
+    "plm_shard_destroy": (C.c_int, [vp]),
+    "plm_shard_n_devices": (C.c_int, [vp]),
+    "plm_shard_n_rows": (C.c_int64, [vp]),
+    "plm_shard_range": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "plm_shard_launch_count": (C.c_uint64, [vp]),
+    "plm_shard_synchronize": (C.c_int, [vp]),
+    "plm_shard_upload": (C.c_int, [vp, u8p, C.c_int64, C.c_size_t, i32p, C.c_int]),
+    "plm_shard_match_nnr": (C.c_int, [vp, u8p, C.c_int, C.c_size_t, C.c_float, u64p, i32p, intp]),
+    "plm_shard_match_grid": (C.c_int, [vp, i32p, i32p, C.c_int, C.c_int] + _DESC + [f64p, C.c_double, i32p, C.c_double, C.c_int,
+                                       i32p, intp]),
+    "plm_shard_match": (C.c_int, [vp] + _DESC + [C.c_float, C.c_int, i32p, intp]),
     "plm_db_create": (C.c_int, [vp, C.c_int64, C.POINTER(vp)]),
     "plm_db_destroy": (C.c_int, [vp]),
     "plm_db_upload": (C.c_int, [vp, vp, C.c_int64, C.c_size_t, C.c_int64]),

@@ -815,6 +815,7 @@ __global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
 grid_rows_kernel(GridJob job, GridParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_warp_tot[GRID_ROW_THREADS / 32];
+    __shared__ int s_seg_end;
     const int tid = threadIdx.x, NT = GRID_ROW_THREADS, lane = tid & 31, warp = tid >> 5;
     const int n1 = job.n1, n2 = job.n2;
     const int n_cells = gp.grid_rows * gp.grid_cols;
@@ -901,64 +902,142 @@ grid_rows_kernel(GridJob job, GridParams gp) {
             if (w < warp) off += t;
             total += t;
         }
-        const bool listed = total <= gp.cap_pairs;
+        // The block goes through the pair list in one piece when its slots fit, else as consecutive row ranges
+        // ("segments": a row joins the segment its first slot falls into, every segment holds <= cap entries as long as
+        // no single row has more than cap / 2 slots); segments are processed in row order like blocks.
+        const int cap = gp.cap_pairs, half = cap >> 1;
+        bool listed = total <= cap;
+        int n_seg = 1;
+        if (!listed && !__syncthreads_or(S > half ? 1 : 0)) {
+            listed = true;
+            n_seg = (total + half - 1) / half;
+        }
         uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT; // register top-2 of the re-walk form
         auto take = [&](int i2, int d) {
             const uint32_t k2 = (static_cast<uint32_t>(d) << GRID_KEY_BITS) | static_cast<uint32_t>(i2);
             if (k2 != b0 && k2 != b1) top2_insert(b0, b1, k2);
         };
+        auto fold = [&](int round) { // per column: this round's record becomes the bound of the next one
+            for (int i2 = tid; i2 < n2; i2 += NT) {
+                const uint32_t k = K[i2];
+                if (k != KEY32_ABSENT) {
+                    if (round == 0) { // the best pair of the column in this block / segment: new threshold, m21 candidate
+                        Tnew[i2] = static_cast<uint16_t>(k >> 16);
+                        atomicMin(&gp.m21key[i2], make_key64(k >> 16, static_cast<uint32_t>(job.i1_base + base + (k & 0xFFFFu))));
+                    }
+                    B[i2] = static_cast<uint16_t>(k & 0xFFFFu);
+                    K[i2] = KEY32_ABSENT;
+                }
+            }
+        };
+        auto next_thresholds = [&]() {
+            for (int i2 = tid; i2 < n2; i2 += NT) {
+                T[i2] = Tnew[i2];
+                B[i2] = D_INF;
+            }
+        };
         bool und = false;
         if (listed) {
-            if (has_row) {
-                int p = off;
-                auto emit = [&](const int32_t *items) {
+            auto entry_distance = [&](uint32_t v, uint32_t &row, uint32_t &i2) -> uint32_t { // 0xFFFF = rejected
+                if (v == PAIR_INVALID) return 0xFFFFu;
+                row = v >> 16;
+                i2 = v & 0xFFFFu;
+                if (job.is_lines) {
+                    const double2 q = rowdir[row];
+                    const double2 t2 = dirp[i2];
+                    const double dp = __dadd_rn(__dmul_rn(q.x, t2.x), __dmul_rn(q.y, t2.y));
+                    if (fabs(dp) < gp.line_sim_th) return 0xFFFFu; // matching.cpp:221, NaN passes
+                }
+                Desc a;
+                a.lo = d1s[2 * row];
+                a.hi = d1s[2 * row + 1];
+                return static_cast<uint32_t>(hamming256(a, d2p[2 * i2], d2p[2 * i2 + 1]));
+            };
+            auto entry_apply = [&](uint32_t d, uint32_t row, uint32_t i2) -> uint32_t { // survivor encoding or INVALID
+                if (d == 0xFFFFu) return PAIR_INVALID;
+                if (PASS == 0) {
+                    if (d < K[i2]) atomicMin(&K[i2], d);
+                } else if (!gp.best_lr) {
+                    top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
+                } else if (d < T[i2]) {
+                    atomicMin(&K[i2], (d << 16) | row);
+                    return (i2 << 17) | (row << 9) | d;
+                }
+                return PAIR_INVALID;
+            };
+            for (int seg = 0; seg < n_seg; ++seg) {
+                bool mine = has_row;
+                int p = off, seg_total = total;
+                if (n_seg > 1) {
+                    for (int e = tid; e < half; e += NT) ent[e] = PAIR_INVALID; // slots below the segment's first row
+                    if (tid == 0) s_seg_end = 0;
+                    __syncthreads();
+                    mine = has_row && S > 0 && off / half == seg;
+                    p = off - seg * half;
+                    if (mine) atomicMax(&s_seg_end, p + S);
+                }
+                if (mine) {
+                    auto emit = [&](const int32_t *items) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        for (int x = r.rw.min_x[k]; x < r.rw.min_x[k] + r.rw.nx[k]; ++x) {
-                            const int lo = cs[x * gp.grid_rows + r.rw.min_y[k]], hi = cs[x * gp.grid_rows + r.rw.max_y[k]];
-                            for (int t = lo; t < hi; ++t) {
-                                const int i2 = items[t];
-                                ent[p++] = (i2 >= 0 && i2 < n2) ? ((utid << 16) | static_cast<uint32_t>(i2)) : PAIR_INVALID;
+                        for (int k = 0; k < 2; ++k)
+                            for (int x = r.rw.min_x[k]; x < r.rw.min_x[k] + r.rw.nx[k]; ++x) {
+                                const int lo = cs[x * gp.grid_rows + r.rw.min_y[k]], hi = cs[x * gp.grid_rows + r.rw.max_y[k]];
+                                for (int t = lo; t < hi; ++t) {
+                                    const int i2 = items[t];
+                                    ent[p++] = (i2 >= 0 && i2 < n2) ? ((utid << 16) | static_cast<uint32_t>(i2)) : PAIR_INVALID;
+                                }
                             }
-                        }
-                };
-                if (STAGED && items_staged) emit(s_items);
-                else emit(job.cell_items);
-            }
-            __syncthreads();
-            // ---- phase B: one thread per entry ----
-            for (int e = tid; e < total; e += NT) {
-                const uint32_t v = ent[e];
-                uint32_t out = PAIR_INVALID;
-                if (v != PAIR_INVALID) {
-                    const uint32_t row = v >> 16, i2 = v & 0xFFFFu;
-                    bool ok = true;
-                    if (job.is_lines) {
-                        const double2 q = rowdir[row];
-                        const double2 t2 = dirp[i2];
-                        const double dp = __dadd_rn(__dmul_rn(q.x, t2.x), __dmul_rn(q.y, t2.y));
-                        ok = !(fabs(dp) < gp.line_sim_th); // matching.cpp:221, NaN passes
-                    }
-                    if (ok) {
-                        Desc a;
-                        a.lo = d1s[2 * row];
-                        a.hi = d1s[2 * row + 1];
-                        const uint32_t d = static_cast<uint32_t>(hamming256(a, d2p[2 * i2], d2p[2 * i2 + 1]));
-                        if (PASS == 0) {
-                            if (d < K[i2]) atomicMin(&K[i2], d);
-                        } else if (!gp.best_lr) {
-                            top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
-                        } else if (d < T[i2]) {
-                            atomicMin(&K[i2], (d << 16) | row);
-                            out = (i2 << 17) | (row << 9) | d;
-                        }
+                    };
+                    if (STAGED && items_staged) emit(s_items);
+                    else emit(job.cell_items);
+                }
+                __syncthreads();
+                if (n_seg > 1) seg_total = s_seg_end;
+                // ---- phase B: one thread per entry, two independent entries in flight per trip ----
+                for (int e = tid; e < seg_total; e += 2 * NT) {
+                    const int e2 = e + NT;
+                    const uint32_t va = ent[e], vb = (e2 < seg_total) ? ent[e2] : PAIR_INVALID;
+                    uint32_t ra = 0, ia = 0, rb = 0, ib = 0;
+                    const uint32_t da = entry_distance(va, ra, ia), db = entry_distance(vb, rb, ib);
+                    const uint32_t oa = entry_apply(da, ra, ia), ob = entry_apply(db, rb, ib);
+                    if (thresholds) {
+                        ent[e] = oa;
+                        if (e2 < seg_total) ent[e2] = ob;
                     }
                 }
-                if (thresholds) ent[e] = out;
+                __syncthreads();
+                if (!thresholds) continue;
+                // rounds over the list: a decided entry is overwritten with PAIR_INVALID
+                for (int round = 0;; ++round) {
+                    bool again = false;
+                    for (int e = tid; e < seg_total; e += NT) {
+                        const uint32_t v = ent[e];
+                        if (v == PAIR_INVALID) continue;
+                        const uint32_t i2 = v >> 17, row = (v >> 9) & 0xFFu, d = v & 0x1FFu;
+                        const uint32_t key = (d << 16) | row, k = K[i2];
+                        if (key == k) {
+                            top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
+                            ent[e] = PAIR_INVALID;
+                        } else if (row > (k & 0xFFFFu)) {
+                            ent[e] = PAIR_INVALID;
+                        } else {
+                            again = true;
+                        }
+                    }
+                    __syncthreads();
+                    fold(round);
+                    if (!__syncthreads_or(again ? 1 : 0)) break;
+                    for (int e = tid; e < seg_total; e += NT) {
+                        const uint32_t v = ent[e];
+                        if (v == PAIR_INVALID) continue;
+                        atomicMin(&K[v >> 17], ((v & 0x1FFu) << 16) | ((v >> 9) & 0xFFu));
+                    }
+                    __syncthreads();
+                }
+                if (seg + 1 < n_seg || base + NT < row_end) next_thresholds(); // for the rows that follow
             }
-            __syncthreads();
         } else {
-            // the block does not fit the list: every thread walks its own row
+            // a single row has more slots than half the list: every thread walks its own row
             if (has_row) {
                 if (PASS == 0) {
                     row_walk(job, gp, r, [&](int i2, int d) {
@@ -976,51 +1055,7 @@ grid_rows_kernel(GridJob job, GridParams gp) {
                 }
             }
             __syncthreads();
-        }
-        if (PASS == 0) continue; // every path above ends with a block barrier; K accumulates over the blocks of the CTA
-        if (thresholds) {
-            auto fold = [&](int round) { // per column: this round's record becomes the bound of the next one
-                for (int i2 = tid; i2 < n2; i2 += NT) {
-                    const uint32_t k = K[i2];
-                    if (k != KEY32_ABSENT) {
-                        if (round == 0) { // the block's best pair of the column: new threshold, m21 candidate
-                            Tnew[i2] = static_cast<uint16_t>(k >> 16);
-                            atomicMin(&gp.m21key[i2], make_key64(k >> 16, static_cast<uint32_t>(job.i1_base + base + (k & 0xFFFFu))));
-                        }
-                        B[i2] = static_cast<uint16_t>(k & 0xFFFFu);
-                        K[i2] = KEY32_ABSENT;
-                    }
-                }
-            };
-            if (listed) {
-                // rounds over the list: a decided entry is overwritten with PAIR_INVALID
-                for (int round = 0;; ++round) {
-                    bool again = false;
-                    for (int e = tid; e < total; e += NT) {
-                        const uint32_t v = ent[e];
-                        if (v == PAIR_INVALID) continue;
-                        const uint32_t i2 = v >> 17, row = (v >> 9) & 0xFFu, d = v & 0x1FFu;
-                        const uint32_t key = (d << 16) | row, k = K[i2];
-                        if (key == k) {
-                            top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
-                            ent[e] = PAIR_INVALID;
-                        } else if (row > (k & 0xFFFFu)) {
-                            ent[e] = PAIR_INVALID;
-                        } else {
-                            again = true;
-                        }
-                    }
-                    __syncthreads();
-                    fold(round);
-                    if (!__syncthreads_or(again ? 1 : 0)) break;
-                    for (int e = tid; e < total; e += NT) {
-                        const uint32_t v = ent[e];
-                        if (v == PAIR_INVALID) continue;
-                        atomicMin(&K[v >> 17], ((v & 0x1FFu) << 16) | ((v >> 9) & 0xFFu));
-                    }
-                    __syncthreads();
-                }
-            } else {
+            if (thresholds) {
                 for (int round = 0;; ++round) {
                     if (und) {
                         bool again = false;
@@ -1042,14 +1077,10 @@ grid_rows_kernel(GridJob job, GridParams gp) {
                         });
                     __syncthreads();
                 }
-            }
-            if (base + NT < row_end) { // thresholds for the next block of rows of this CTA
-                for (int i2 = tid; i2 < n2; i2 += NT) {
-                    T[i2] = Tnew[i2];
-                    B[i2] = D_INF;
-                }
+                if (base + NT < row_end) next_thresholds();
             }
         }
+        if (PASS == 0) continue; // every path above ends with a block barrier; K accumulates over the blocks of the CTA
         if (listed) {
             b0 = rb0[tid];
             b1 = rb1[tid];

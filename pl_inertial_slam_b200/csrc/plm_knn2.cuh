@@ -304,6 +304,28 @@ __global__ void cross_check_kernel(int32_t *__restrict__ m12, int n1, long long 
     if ((threadIdx.x & 31) == 0 && m) atomicSub(count, __popc(m));
 }
 
+// The same mutual check straight from the per-column keys of matchGrid (distance << 32 | global row; all ones = no
+// live pair): saves the separate key -> row conversion launch.
+__global__ void cross_check_keys_kernel(int32_t *__restrict__ m12, int n1, long long i1_base,
+                                        const unsigned long long *__restrict__ m21key, long long n2,
+                                        int32_t *__restrict__ count) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    bool cull = false;
+    if (i1 < n1) {
+        const int32_t i2 = m12[i1];
+        if (i2 >= 0) {
+            const unsigned long long k = (i2 < n2) ? m21key[i2] : KEY64_ABSENT;
+            const long long back = (k == KEY64_ABSENT) ? -1 : static_cast<long long>(static_cast<int32_t>(k & 0xFFFFFFFFull));
+            if (back != i1_base + i1) {
+                m12[i1] = -1;
+                cull = true;
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, cull);
+    if ((threadIdx.x & 31) == 0 && m) atomicSub(count, __popc(m));
+}
+
 // StVO::distance for n independent pairs.
 __global__ void hamming_pairs_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, int n,
                                      int32_t *__restrict__ dist) {

@@ -137,9 +137,12 @@ struct TlsCtx {
 };
 thread_local TlsCtx g_tls;
 
+// Makes the context's device current for the calling thread.  NOTE: like cudaSetDevice itself this is sticky -- a call
+// with an explicit context on another GPU leaves that GPU current afterwards (documented in include/plmatch.h).
 int resolve_ctx(plm_ctx *&ctx) {
     if (ctx) {
-        CU_TRY(cudaSetDevice(ctx->device));
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) CU_TRY(cudaSetDevice(ctx->device));
         return PLM_OK;
     }
     if (!g_tls.ctx) {
@@ -179,6 +182,7 @@ int g_frames_pairs_per_row[2] = {8, 0};
 int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame pipeline (128 or 256; measurement knob)
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
+long long g_peer_spin_ticks = 4000000000ll; // bounded spin of the peer-memory kernels (~2 s of SM clock); option "peer_spin_ms"
 int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
 
 // -1 = automatic (variant 3 for long slices, 1 otherwise); 0..3 force a variant (measurement only)
@@ -324,6 +328,10 @@ PLM_API int plm_set_option(const char *key, int value) {
         g_knn_variant = (value >= 0 && value <= 3) ? value : -1;
         return PLM_OK;
     }
+    if (std::strcmp(key, "peer_spin_ms") == 0) {
+        g_peer_spin_ticks = static_cast<long long>(std::max(1, value)) * 2000000ll; // ~2 GHz SM clock
+        return PLM_OK;
+    }
     if (std::strcmp(key, "grid_rows") == 0) {
         g_grid_rows = value ? 1 : 0;
         return PLM_OK;
@@ -360,6 +368,7 @@ PLM_API const char *plm_status_string(int status) {
     case PLM_E_CUDA: return "CUDA failure";
     case PLM_E_NOMEM: return "out of memory";
     case PLM_E_UNSUPPORTED: return "unsupported size";
+    case PLM_E_PEER: return "peer-memory exchange timed out";
     default: return "unknown status";
     }
 }
@@ -634,11 +643,13 @@ static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, con
     if (!n_matches) return fail(PLM_E_INVALID, "null n_matches");
     if (n1 > 0 && !m12_inout) return fail(PLM_E_INVALID, "null m12");
     *n_matches = 0;
-    // matches_[idx][1] is read unconditionally (matching.cpp:54): fewer than 2 train rows is UB /
-    // a throw in the reference.  With best_lr the roles swap, so both sides need >= 2 rows.
-    if (n2 < 2) return fail(PLM_E_TRAIN, "matchNNR needs at least 2 train descriptors");
-    if (best_lr && n1 < 2) return fail(PLM_E_TRAIN, "match (bestLRMatches) needs at least 2 descriptors on both sides");
+    // Degenerate sizes (sparse frames).  The reference: an empty query matches nothing and returns 0 (knnMatch yields no
+    // rows, matching.cpp:50 holds; the throw of the 21 direction is swallowed by future::wait, :74); an empty train set
+    // with a non-empty query throws (:50-51) -> PLM_E_TRAIN; a SINGLE train row makes it read matches_[idx][1] out of
+    // bounds (:54, UB, it does not throw).  Here a row without a second neighbour is simply not accepted (the merge
+    // kernels require both keys), so one-row inputs leave m12 untouched in that direction and the mutual check culls.
     if (n1 == 0) return PLM_OK;
+    if (n2 == 0) return fail(PLM_E_TRAIN, "matchNNR: empty train set");
     if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
 
     Layout L;
@@ -905,11 +916,9 @@ int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams g
     }
     if ((st = launch_map_grid(ctx, 1, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
     if (gp.best_lr) {
-        plm::m21_from_keys_kernel<<<(job.n2 + 127) / 128, 128, 0, ctx->stream>>>(gp.m21key, job.n2, m21);
-        ctx->launches++;
-        CU_TRY(cudaGetLastError());
-        plm::cross_check_kernel<<<(job.n1 + 127) / 128, 128, 0, ctx->stream>>>(job.m12, job.n1, job.i1_base, m21, job.n2,
-                                                                              job.count);
+        (void)m21;
+        plm::cross_check_keys_kernel<<<(job.n1 + 255) / 256, 256, 0, ctx->stream>>>(job.m12, job.n1, job.i1_base, gp.m21key, job.n2,
+                                                                                   job.count);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
     }
@@ -1118,6 +1127,46 @@ PLM_API int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const u
     return launch_map_grid(ctx, 1, job, gp, warps, n_cta, smem);
 }
 
+namespace {
+
+size_t sharded_grid_extra_bytes(int n2) {
+    const size_t n2p8 = (size_t(n2) + 7) / 8 * 8, n2p2 = (size_t(n2) + 1) / 2 * 2;
+    Layout L;
+    L.add(n2p8 * 2); L.add(n2p8 * 2); L.add(n2p2 * 8); L.add(n2p2 * 8); L.add(size_t(std::max(n2, 1)) * 4);
+    return L.total;
+}
+
+// Everything plm_dev_sharded_match_grid / plm_dev_sharded_match may allocate, done up front: an in-process caller
+// driving several devices (plm_shard_*) sizes every context before the first kernel that waits for a peer is enqueued.
+int plm_dev_sharded_match_grid_prepare(plm_ctx *ctx, const plm_dev_grid_args *a) {
+    plm::GridJob job;
+    plm::GridParams gp;
+    int warps = 0, n_cta = 0;
+    size_t smem = 0;
+    char *X = nullptr;
+    return dev_grid_setup(ctx, a, job, gp, warps, n_cta, smem, sharded_grid_extra_bytes(a ? std::max(a->n2, 0) : 0), &X);
+}
+
+int plm_dev_sharded_match_prepare(plm_ctx *ctx, int n1, int n2) {
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    Layout A;
+    A.add(size_t(std::max(n1, 1)) * 16); A.add(size_t(n2) * 16); A.add(size_t(n2) * 4); A.add(16);
+    if ((st = ctx->ensure_aux(A.total)) != PLM_OK) return st;
+    size_t need = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+        Layout L;
+        plm::KnnTask t;
+        KnnPlan plan;
+        size_t off = 0;
+        build_knn_task(ctx, L, t, plan, nullptr, dir ? n2 : n1, nullptr, dir ? n1 : n2, 0, off);
+        need = std::max(need, L.total);
+    }
+    return ctx->ensure_device(need);
+}
+
+} // namespace
+
 // The whole row-sharded matchGrid of one rank, launched back to back from C: minima pass, the two peer-memory
 // reductions around the match pass, mutual check and the peer-memory all-gather of the match vectors.
 PLM_API int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a, const plm_peer_group *g, int64_t n_rows_total,
@@ -1168,11 +1217,9 @@ PLM_API int plm_dev_sharded_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a,
         if ((st = plm_dev_peer_reduce(ctx, g->xchg, g->rank, g->world, g->q_cap, epoch++, PLM_PEER_MIN_U64, key,
                                       static_cast<int>(n2p2 / 2), key_g, error_dev)) != PLM_OK)
             return st;
-        plm::m21_from_keys_kernel<<<(n2 + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(key_g), n2, m21);
-        ctx->launches++;
-        CU_TRY(cudaGetLastError());
+        (void)m21;
         if (a->n1 > 0) {
-            plm::cross_check_kernel<<<(a->n1 + 127) / 128, 128, 0, ctx->stream>>>(a->m12_inout, a->n1, a->i1_base, m21, n2, a->count);
+            plm::cross_check_keys_kernel<<<(a->n1 + 255) / 256, 256, 0, ctx->stream>>>(a->m12_inout, a->n1, a->i1_base, reinterpret_cast<const unsigned long long *>(key_g), n2, a->count);
             ctx->launches++;
             CU_TRY(cudaGetLastError());
         }
@@ -1191,7 +1238,7 @@ PLM_API int plm_dev_sharded_match(plm_ctx *ctx, const void *d1_shard_dev, int n1
     if (n1 < 0 || n2 < 0 || i1_base < 0 || i1_base + n1 > n_rows_total || n_rows_total > g->n_rows_cap)
         return fail(PLM_E_INVALID, "rows outside the gather buffers");
     if (n1 > 0 && (!d1_shard_dev || !m12_local_inout_dev)) return fail(PLM_E_INVALID, "null pointer");
-    if (n2 < 2) return fail(PLM_E_TRAIN, plm_status_string(PLM_E_TRAIN)); // UB in the reference (matching.cpp:54)
+    if (n2 < 1) return fail(PLM_E_TRAIN, plm_status_string(PLM_E_TRAIN)); // empty train set: the reference throws (matching.cpp:50-51)
     if (n2 > g->q_cap) return fail(PLM_E_UNSUPPORTED, "frame too large for the exchange buffers");
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
@@ -1464,7 +1511,7 @@ PLM_API int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, in
     a.m12 = m12_dev_inout;
     a.count = count_dev;
     a.error = error_dev;
-    a.spin_limit = 4000000000ll; // ~2 s of SM clock
+    a.spin_limit = g_peer_spin_ticks;
     plm::top2_exchange_merge_kernel<<<(n1 + plm::PEER_THREADS - 1) / plm::PEER_THREADS, plm::PEER_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
@@ -1497,7 +1544,7 @@ PLM_API int plm_dev_peer_allgather_i32(plm_ctx *ctx, void *const *peers, int ran
     a.out = out_dev;
     a.out_count = out_count_dev;
     a.error = error_dev;
-    a.spin_limit = 4000000000ll;
+    a.spin_limit = g_peer_spin_ticks;
     // every rank must launch the SAME grid size is not required (flags are per rank), but the grid must fit the device at
     // once so that no block waits behind spinning ones: at most one CTA per SM
     const int64_t work = std::max<int64_t>(std::max<int64_t>(n_rows, n_local), 1);
@@ -1531,7 +1578,7 @@ PLM_API int plm_dev_peer_reduce(plm_ctx *ctx, void *const *peers, int rank, int 
     a.n1 = n_chunks;
     a.out = static_cast<ulonglong2 *>(out_dev);
     a.error = error_dev;
-    a.spin_limit = 4000000000ll;
+    a.spin_limit = g_peer_spin_ticks;
     const int grid = (n_chunks + plm::PEER_THREADS - 1) / plm::PEER_THREADS;
     if (op == PLM_PEER_MIN_U64) plm::peer_reduce_kernel<0><<<grid, plm::PEER_THREADS, 0, ctx->stream>>>(a);
     else plm::peer_reduce_kernel<1><<<grid, plm::PEER_THREADS, 0, ctx->stream>>>(a);
@@ -2451,3 +2498,4 @@ PLM_API int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts) {
 
 // ---------------------------------------------------------------------------------------------
 #include "plm_frames_api.inl"
+#include "plm_shard_api.inl"

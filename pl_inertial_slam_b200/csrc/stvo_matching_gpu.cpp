@@ -107,10 +107,14 @@ int match(const cv::Mat &desc1, const cv::Mat &desc2, float nnr, std::vector<int
     return matches;
 }
 
+// One 256-bit pair is not worth a host <-> device round trip: the same 8 x (xor, popcount) as matching.cpp:93-109 on
+// the host (the batched device form is plm_hamming256).
 int distance(const cv::Mat &a, const cv::Mat &b) {
-    int32_t d = 0;
-    throw_status(plm_hamming256(nullptr, rows_of(a), 32, rows_of(b), 32, 1, &d), "distance");
-    return d;
+    const int32_t *pa = a.ptr<int32_t>();
+    const int32_t *pb = b.ptr<int32_t>();
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) dist += __builtin_popcount(static_cast<unsigned>(pa[i] ^ pb[i]));
+    return dist;
 }
 
 int matchGrid(const std::vector<point_2d> &points1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,

@@ -24,7 +24,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Sequence, Optional, Tuple
 
 import numpy as np
 import torch
@@ -211,9 +211,20 @@ class PeerExchange:
         g.dist.all_reduce(ok, op=g.dist.ReduceOp.MIN, group=g.group)
         self.ok = bool(ok.item())
         self.ptrs = ptrs
-        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        # timeout flag of the peer kernels: pinned host memory that the device writes through its unified address, so
+        # the host can look at it on every call without a stream synchronisation
+        self.error = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.failed = False
         if not self.ok:
             self.close()
+
+    def _raise_if_failed(self) -> None:
+        """A wait that timed out leaves results unwritten and the double-buffer invariant broken: the first call after
+        the flag became visible raises, and so does every later one (no silent garbage, no silent fallback)."""
+        if self.failed or int(self.error[0]) != 0:
+            self.failed = True
+            raise RuntimeError("peer-memory exchange: a rank did not arrive within the spin limit "
+                               "(option peer_spin_ms); this exchange object is unusable -- rebuild it or use exchange='nccl'")
 
     @classmethod
     def create(cls, g: "_Group", ops, q_cap: int) -> Optional["PeerExchange"]:
@@ -228,8 +239,9 @@ class PeerExchange:
         acceptance written to m12 / count).  Every rank must call this with the same n1, in the same order."""
         n1 = int(local.shape[0])
         assert n1 <= self.q_cap and local.dtype == torch.int64 and local.is_contiguous()
+        self._raise_if_failed()
         if out is None and m12 is None:
-            out = torch.empty((n1, 2), dtype=torch.int64, device=local.device)
+            out = torch.full((n1, 2), -1, dtype=torch.int64, device=local.device)   # absent keys if a wait times out
         self.epoch += 1
         self.ops._bind_stream()
         L.check(self.lib.plm_dev_top2_exchange(self.ops.ctx.handle, self.ptrs, self.rank, self.world, self.q_cap,
@@ -238,7 +250,8 @@ class PeerExchange:
         return out
 
     def _reduce(self, op: int, src: torch.Tensor, n_chunks: int) -> torch.Tensor:
-        out = torch.empty_like(src)
+        self._raise_if_failed()
+        out = torch.full_like(src, -1)                                               # identity of both reductions
         self.epoch += 1
         self.ops._bind_stream()
         L.check(self.lib.plm_dev_peer_reduce(self.ops.ctx.handle, self.ptrs, self.rank, self.world, self.q_cap, self.epoch,
@@ -265,14 +278,16 @@ class PeerExchange:
 
     def healthy(self) -> bool:
         """Host sync + one all_reduce: True when no exchange timed out on ANY rank since construction."""
-        bad = (self.error != 0).to(torch.int32)
+        torch.cuda.synchronize()
+        bad = torch.tensor([1 if (self.failed or int(self.error[0]) != 0) else 0], dtype=torch.int32,
+                           device=torch.device("cuda", self.ops.device))
         self.g.dist.all_reduce(bad, op=self.g.dist.ReduceOp.MAX, group=self.g.group)
         return int(bad.item()) == 0
 
     def check(self) -> None:
         """Host sync: raises if any exchange since the last check timed out waiting for a peer."""
-        if int(self.error.item()) != 0:
-            raise RuntimeError("plm_dev_top2_exchange: a peer rank did not arrive (timeout)")
+        torch.cuda.synchronize()
+        self._raise_if_failed()
 
     def close(self) -> None:
         for p in self._opened:
@@ -304,8 +319,9 @@ class PeerGather(PeerExchange):
     def gather(self, local: torch.Tensor, row_lo: int, n_rows: int, count: Optional[torch.Tensor]):
         """-> (global int32 vector [n_rows], summed count [1]) on every rank."""
         assert local.dtype == torch.int32 and local.is_contiguous() and n_rows <= self.n_rows_cap
-        out = torch.empty(n_rows, dtype=torch.int32, device=local.device)
-        total = torch.empty(1, dtype=torch.int32, device=local.device)
+        self._raise_if_failed()
+        out = torch.full((n_rows,), -1, dtype=torch.int32, device=local.device)
+        total = torch.full((1,), torch.iinfo(torch.int32).min, dtype=torch.int32, device=local.device)
         self.epoch += 1
         self.ops._bind_stream()
         L.check(self.lib.plm_dev_peer_allgather_i32(self.ops.ctx.handle, self.ptrs, self.rank, self.world, self.n_rows_cap,
@@ -313,6 +329,98 @@ class PeerGather(PeerExchange):
                                                     _ptr(count), _ptr(out), _ptr(total), _ptr(self.error)),
                 "plm_dev_peer_allgather_i32")
         return out, total
+
+
+class ShardSet:
+    """The keyframe database / local map row-sharded over several GPUs INSIDE ONE PROCESS (plm_shard_* of
+    include/plmatch.h): what a single C++ host such as the reference's MapHandler calls; host buffers in and out,
+    every index global.  No torch.distributed involved -- the library enables peer access and drives the peer-memory
+    kernels itself."""
+
+    def __init__(self, devices: Sequence[int], q_cap: int, rows_cap: int):
+        self.lib = L.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        L.check(self.lib.plm_shard_create(devs, len(devices), int(q_cap), int(rows_cap), C.byref(h)), "plm_shard_create")
+        self._h = h
+        self.n_devices = len(devices)
+
+    def upload(self, rows: np.ndarray, coords: Optional[np.ndarray] = None) -> None:
+        d, p, n, step = L.desc_args(rows)
+        self._keep = (d, None)
+        cp, per = None, 0
+        if coords is not None:
+            c = np.ascontiguousarray(coords, np.int32)
+            assert c.shape[0] == n and c.shape[1] in (2, 4)
+            cp, per = c.ctypes.data_as(L.i32p), int(c.shape[1])
+        L.check(self.lib.plm_shard_upload(self._h, p, n, step, cp, per), "plm_shard_upload")
+        self.n_rows = n
+
+    def ranges(self):
+        out = []
+        for i in range(self.n_devices):
+            lo, hi = C.c_int64(), C.c_int64()
+            L.check(self.lib.plm_shard_range(self._h, i, C.byref(lo), C.byref(hi)), "plm_shard_range")
+            out.append((lo.value, hi.value))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.plm_shard_launch_count(self._h))
+
+    def knn2(self, q: np.ndarray) -> np.ndarray:
+        d, p, n1, step = L.desc_args(q)
+        top2 = np.empty((n1, 2), np.uint64)
+        L.check(self.lib.plm_shard_match_nnr(self._h, p, n1, step, C.c_float(0.0), top2.ctypes.data_as(L.u64p), None, None),
+                "plm_shard_match_nnr")
+        return top2
+
+    def match_nnr(self, q: np.ndarray, nnr: float, m12: Optional[np.ndarray] = None):
+        d, p, n1, step = L.desc_args(q)
+        buf = np.full(n1, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = C.c_int(0)
+        st = self.lib.plm_shard_match_nnr(self._h, p, n1, step, C.c_float(nnr), None, buf.ctypes.data_as(L.i32p), C.byref(n))
+        if st == L.PLM_E_TRAIN:
+            raise RuntimeError("[matchNNR] Different size for matches and descriptors!")
+        L.check(st, "plm_shard_match_nnr")
+        return n.value, buf
+
+    def match_grid(self, grid, d2: np.ndarray, win, ratio: float, best_lr: bool = True, dirs2: Optional[np.ndarray] = None,
+                   line_sim_th: float = 0.75, m12: Optional[np.ndarray] = None):
+        cs, ci, rows, cols = grid
+        cs = np.ascontiguousarray(cs, np.int32)
+        ci = np.ascontiguousarray(ci, np.int32)
+        d, p2, n2, step2 = L.desc_args(d2)
+        w = np.ascontiguousarray(win, np.int32)
+        dr = None if dirs2 is None else np.ascontiguousarray(dirs2, np.float64)
+        buf = np.full(self.n_rows, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = C.c_int(0)
+        L.check(self.lib.plm_shard_match_grid(self._h, cs.ctypes.data_as(L.i32p), ci.ctypes.data_as(L.i32p), int(rows), int(cols), p2, n2,
+                                              step2, None if dr is None else dr.ctypes.data_as(L.f64p), float(line_sim_th),
+                                              w.ctypes.data_as(L.i32p), float(ratio), int(bool(best_lr)), buf.ctypes.data_as(L.i32p),
+                                              C.byref(n)), "plm_shard_match_grid")
+        return n.value, buf
+
+    def match(self, d2: np.ndarray, nnr: float, best_lr: bool = True, m12: Optional[np.ndarray] = None):
+        d, p2, n2, step2 = L.desc_args(d2)
+        buf = np.full(self.n_rows, -1, np.int32) if m12 is None else np.array(m12, np.int32)
+        n = C.c_int(0)
+        st = self.lib.plm_shard_match(self._h, p2, n2, step2, C.c_float(nnr), int(bool(best_lr)), buf.ctypes.data_as(L.i32p), C.byref(n))
+        if st == L.PLM_E_TRAIN:
+            raise RuntimeError("[matchNNR] Different size for matches and descriptors!")
+        L.check(st, "plm_shard_match")
+        return n.value, buf
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.plm_shard_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class ShardedDescriptorDB:
@@ -488,9 +596,11 @@ class ShardedMap:
         m12 = self._local_m12(m12_inout, dev)
         if self.peer is not None and self.gatherer is not None and 2 <= d2.shape[0] <= self.peer.q_cap:
             # one C call: both directions, the peer-memory exchange, mutual check and the all-gather back to back
+            self.peer._raise_if_failed()
+            self.gatherer._raise_if_failed()
             grp = self._peer_group(1 if best_lr else 0)   # only epochs that are really used are consumed
-            out = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
-            total = torch.empty(1, dtype=torch.int32, device=dev)
+            out = torch.full((self.n_rows,), -1, dtype=torch.int32, device=dev)
+            total = torch.full((1,), torch.iinfo(torch.int32).min, dtype=torch.int32, device=dev)
             self.ops._bind_stream()
             L.check(self.ops.lib.plm_dev_sharded_match(self.ops.ctx.handle, _ptr(self.d1), int(self.d1.shape[0]), self.lo, _ptr(d2),
                                                        int(d2.shape[0]), C.c_float(nnr), int(bool(best_lr)), _ptr(m12), C.byref(grp),
@@ -523,9 +633,11 @@ class ShardedMap:
         if self.peer is not None and self.gatherer is not None and (n2 == 0 or self.peer.fits(8 * n2)):
             # everything in one C call: the launches go out back to back, the three exchanges are peer-memory kernels
             a = self.ops._grid_args(self.coords, self.d1, self.lo, frame, win, ratio, line_sim_th, best_lr, m12, count)
+            self.peer._raise_if_failed()
+            self.gatherer._raise_if_failed()
             grp = self._peer_group(2 if (best_lr and n2 > 0) else 0)
-            out = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
-            total = torch.empty(1, dtype=torch.int32, device=dev)
+            out = torch.full((self.n_rows,), -1, dtype=torch.int32, device=dev)
+            total = torch.full((1,), torch.iinfo(torch.int32).min, dtype=torch.int32, device=dev)
             self.ops._bind_stream()
             L.check(self.ops.lib.plm_dev_sharded_match_grid(self.ops.ctx.handle, C.byref(a), C.byref(grp), self.n_rows, _ptr(out),
                                                             _ptr(total), _ptr(self.peer.error)), "plm_dev_sharded_match_grid")

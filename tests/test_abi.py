@@ -45,9 +45,12 @@ def test_argument_validation_needs_no_gpu(plm_lib):
     m = np.full(4, -1, np.int32)
     n = C.c_int(0)
     p = d.ctypes.data_as(L.u8p)
-    # fewer than two train rows: UB in the reference (matching.cpp:54)
-    assert plm_lib.plm_match_nnr(None, p, 4, 32, p, 1, 32, C.c_float(0.9), m.ctypes.data_as(L.i32p), C.byref(n)) == L.PLM_E_TRAIN
-    assert plm_lib.plm_match(None, p, 1, 32, p, 4, 32, C.c_float(0.9), 1, m.ctypes.data_as(L.i32p), C.byref(n)) == L.PLM_E_TRAIN
+    # empty train set with a non-empty query: the reference throws (matching.cpp:50-51); an empty query matches nothing
+    assert plm_lib.plm_match_nnr(None, p, 4, 32, p, 0, 32, C.c_float(0.9), m.ctypes.data_as(L.i32p), C.byref(n)) == L.PLM_E_TRAIN
+    assert plm_lib.plm_match(None, p, 4, 32, p, 0, 32, C.c_float(0.9), 1, m.ctypes.data_as(L.i32p), C.byref(n)) == L.PLM_E_TRAIN
+    n.value = 7
+    assert plm_lib.plm_match(None, p, 0, 32, p, 4, 32, C.c_float(0.9), 1, m.ctypes.data_as(L.i32p), C.byref(n)) == L.PLM_OK
+    assert n.value == 0
     # step smaller than a descriptor
     assert plm_lib.plm_match_nnr(None, p, 4, 16, p, 4, 32, C.c_float(0.9), m.ctypes.data_as(L.i32p), C.byref(n)) == L.PLM_E_INVALID
     # invalid grid dimension / ratio > 1
@@ -69,7 +72,7 @@ def test_host_mirror_raises_reference_messages(plm_lib):
     from pl_inertial_slam_b200.grid import GridStructure, GridWindow
     d = np.zeros((4, 32), np.uint8)
     with pytest.raises(RuntimeError, match=r"\[matchNNR\] Different size"):
-        M.matchNNR(d, d[:1], 0.9, [])
+        M.matchNNR(d, d[:0], 0.9, [])
     with pytest.raises(RuntimeError, match=r"\[GridStructure\] invalid dimension"):
         GridStructure(0, 4)
     g = GridStructure(4, 4)

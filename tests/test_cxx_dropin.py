@@ -40,9 +40,37 @@ def test_stvo_match_and_distance(plm_lib):
 @needs_lib
 def test_stvo_match_throws_like_the_reference(plm_lib):
     gpu = oracle.stvo_gpu
-    d = np.zeros((4, 32), np.uint8)
+    d = synth.rand_desc(np.random.default_rng(4), 4)
     with pytest.raises(RuntimeError):
-        gpu.match_nnr(d, d[:1], 0.9)  # "[matchNNR] Different size for matches and descriptors!"
+        gpu.match_nnr(d, d[:0], 0.9)  # empty train set: "[matchNNR] Different size for matches and descriptors!"
+    with pytest.raises(RuntimeError):
+        gpu.match(d, d[:0], 0.9, best_lr=1)
+
+
+@needs_lib
+def test_stvo_match_sparse_frames_do_not_throw(plm_lib):
+    """A frame with a single stereo point / line on one side (low-texture scenes) reaches StVO::match through
+    matchF2FPoints/Lines and mapHandler.cpp:328/475/648/763/3332 without any try/catch: the reference carries on
+    there (it reads matches_[idx][1] out of bounds, matching.cpp:54, but does not throw), so the drop-in must not
+    terminate the process either.  A row without a second neighbour is not accepted."""
+    gpu = oracle.stvo_gpu
+    d = synth.rand_desc(np.random.default_rng(4), 4)
+    n, m = gpu.match_nnr(d, d[:1], 0.9)
+    assert n == 0 and (m == -1).all()
+    n, m = gpu.match(d[:0], d, 0.9, best_lr=1)
+    assert n == 0 and len(m) == 0
+    # one query row: accepted in the 12 direction (it IS train row 0), no reverse match exists -> culled
+    n, m = gpu.match(d[:1], d, 0.9, best_lr=1)
+    assert n == 0 and (m == -1).all()
+    n, m = gpu.match(d[:1], d, 0.9, best_lr=0)
+    assert n == 1 and m[0] == 0
+    # one train row + stale entries from a preceding matchGrid: nothing new is accepted, the mutual check culls
+    stale = np.array([2, -1, 0, 1], np.int32)
+    n, m = gpu.match(d, d[:1], 0.9, best_lr=1, m12=stale)
+    assert n == -3 and (m == -1).all()
+    stale = np.array([0, -1, -1, -1], np.int32)       # row 0 <-> train 0 is mutual: survives
+    n, m = gpu.match(d, d[:1], 0.9, best_lr=1, m12=stale)
+    assert n == 0 and m[0] == 0 and (m[1:] == -1).all()
 
 
 @needs_lib

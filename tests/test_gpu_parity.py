@@ -354,3 +354,16 @@ def test_match_grid_map_scale_dense_windows(M, is_lines):
     n_o, m_o = oracle_grid(port, case, 0.9, 1)
     n_g, m_g = gpu_grid(case, 0.9, 1)
     assert n_g == n_o and (m_g == m_o).all()
+
+
+def test_match_one_row_sides(M):
+    """Sparse frames: one descriptor on a side must not raise (only an EMPTY train set does, matching.cpp:50-51)."""
+    d = synth.rand_desc(np.random.default_rng(4), 5)
+    m = []
+    assert M.match(d[:1], d, 0.9, m) == 0 and m == [-1]
+    m = np.full(5, -1, np.int32)
+    assert M.matchNNR(d, d[:1], 0.9, m) == 0 and (m == -1).all()
+    m = []
+    assert M.match(d[:0], d, 0.9, m) == 0 and m == []
+    with pytest.raises(RuntimeError):
+        M.match(d, d[:0], 0.9, [])
