@@ -495,6 +495,37 @@ int plm_dev_med_desc(plm_ctx *ctx, const void *desc_obs_dev, int64_t n_obs, cons
                      const int32_t *obs_start_dev, int n_lm, int32_t *med_idx_dev, void *med_desc_dev,
                      const int32_t *dst_rows_dev, double *med_dir_dev);
 
+/* ---- local-map selection and reprojection gates of matchMap2KF*  ------------------- */
+/* MapHandler::matchMap2KFPoints / Lines (src/mapHandler.cpp:583-682, :685-803) around the matcher:
+ *   select  Pf = R X + t with Twf = [R | t]; pf = (cx + fx Pf0 / Pf2, cy + fy Pf1 / Pf2); a landmark is kept when its
+ *           `active` byte is non-zero (local and not yet observed from this keyframe; NULL = all) and pf lies strictly
+ *           inside the image with Pf2 > 0 (:602, :705-706; segments: both endpoints).  Kept landmarks are compacted in
+ *           order: sel[j] = landmark index, coords[j] = (int)(pf * inv_width), (int)(pf * inv_height) per endpoint
+ *           (the matchGrid query coordinates, :605, :709-710), pf[j] = the projection(s) for the gate.
+ *   gate    per compacted row i1 with i2 = m12[i1] >= 0: points |pf - pl[i2]| < max_epip (:661-662); lines
+ *           le[i2] . (spf, 1) < max_epip && le[i2] . (epf, 1) < max_epip, signed as written (:784-786).
+ *           ok[i1] = 1 for an accepted pair, else 0; *count -= rejected pairs (the reference's --matches).
+ * X: n x 3 doubles (points) or n x 6 (segment endpoints); feat: n2 x 2 (pl) or n2 x 3 (le).  fp64, every operation
+ * rounded separately, the 3x3 product summed left to right (Eigen's own order for it is not reproducible here:
+ * these fp64 values are "parity unpinned"). */
+typedef struct plm_map_view {
+    double T[12];                 /* Twf rows 0..2, row-major: r00 r01 r02 tx | r10 r11 r12 ty | r20 r21 r22 tz */
+    double fx, fy, cx, cy;
+    double inv_width, inv_height; /* GRID_COLS / image width, GRID_ROWS / image height */
+    int32_t width, height;
+} plm_map_view;
+int plm_map_select(plm_ctx *ctx, int is_lines, const double *X, const uint8_t *active, int n, const plm_map_view *v, int32_t *sel,
+                   int32_t *coords, double *pf, int *n_sel);
+int plm_map_gate(plm_ctx *ctx, int is_lines, const double *pf, const int32_t *m12, int n_sel, const double *feat, int n2, double max_epip,
+                 uint8_t *ok, int *count_inout);
+/* Device-resident forms (no host sync; *n_sel_dev is produced / consumed on the device, n_max bounds the launch). */
+int plm_dev_map_select(plm_ctx *ctx, int is_lines, const double *X_dev, const uint8_t *active_dev, int n, const plm_map_view *v,
+                       int32_t *sel_dev, int32_t *coords_dev, double *pf_dev, int32_t *n_sel_dev);
+/* out[j] = rows[sel[j]], j < *n_sel: the representative descriptors of the selected landmarks (:606, :711). */
+int plm_dev_gather_rows(plm_ctx *ctx, const void *rows_dev, const int32_t *sel_dev, const int32_t *n_sel_dev, int n_max, void *out_dev);
+int plm_dev_map_gate(plm_ctx *ctx, int is_lines, const double *pf_dev, const int32_t *m12_dev, const int32_t *n_sel_dev, int n_max,
+                     const double *feat_dev, int n2, double max_epip, uint8_t *ok_dev, int32_t *count_inout_dev);
+
 /* ---- bag-of-words loop-candidate scoring (the reference's vendored DBoW2) ----------------------- */
 /* A vocabulary tree as flat arrays, copied to the device once (DBoW2::TemplatedVocabulary::m_nodes,
  * TemplatedVocabulary.h:275-307, 383-408): node 0 is the root; the children of node i are

@@ -160,6 +160,43 @@ class _Port:
                                           sim.ctypes.data_as(_f64p))
         return n, keep[:n1], ov[:n1], sim[:n1]
 
+    # ---- local-map selection / reprojection gates (mapHandler.cpp:583-682, :685-803) -------------------------
+    @staticmethod
+    def _view(T, cam, inv_w, inv_h, width, height):
+        class V(C.Structure):
+            _fields_ = [("T", C.c_double * 12), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                        ("inv_width", C.c_double), ("inv_height", C.c_double), ("width", C.c_int32), ("height", C.c_int32)]
+        v = V()
+        v.T[:] = [float(x) for x in np.asarray(T, np.float64).reshape(-1)[:12]]
+        v.fx, v.fy, v.cx, v.cy = [float(x) for x in cam]
+        v.inv_width, v.inv_height, v.width, v.height = float(inv_w), float(inv_h), int(width), int(height)
+        return v
+
+    def map_select(self, X, active, T, cam, inv_w, inv_h, width, height):
+        """-> (sel, coords, pf) of the landmarks projected inside the image, in order."""
+        X = np.ascontiguousarray(X, np.float64)
+        is_lines = X.shape[1] == 6
+        n, per = len(X), 2 if is_lines else 1
+        act = None if active is None else np.ascontiguousarray(active, np.uint8)
+        sel, coords, pf = np.zeros(max(n, 1), np.int32), np.zeros((max(n, 1), 2 * per), np.int32), np.zeros((max(n, 1), 2 * per))
+        v = self._view(T, cam, inv_w, inv_h, width, height)
+        self.lib.plo_map_select.restype = C.c_int
+        m = self.lib.plo_map_select(int(is_lines), X.ctypes.data_as(_f64p), None if act is None else act.ctypes.data_as(_u8p), n,
+                                    C.byref(v), sel.ctypes.data_as(_i32p), coords.ctypes.data_as(_i32p), pf.ctypes.data_as(_f64p))
+        return sel[:m].copy(), coords[:m].copy(), pf[:m].copy()
+
+    def map_gate(self, pf, m12, feat, max_epip, count):
+        pf = np.ascontiguousarray(pf, np.float64)
+        is_lines = pf.shape[1] == 4
+        m, mp = _i32(m12)
+        feat = np.ascontiguousarray(feat, np.float64)
+        ok = np.zeros(max(len(m), 1), np.uint8)
+        self.lib.plo_map_gate.restype = C.c_int
+        self.lib.plo_map_gate.argtypes = [C.c_int, _f64p, _i32p, C.c_int, _f64p, C.c_int, C.c_double, _u8p, C.c_int]
+        c = self.lib.plo_map_gate(int(is_lines), pf.ctypes.data_as(_f64p), mp, len(m), feat.ctypes.data_as(_f64p), len(feat),
+                                  float(max_epip), ok.ctypes.data_as(_u8p), int(count))
+        return c, ok[:len(m)].copy()
+
     def med_desc(self, desc, dirs, obs_start):
         """MapPoint / MapLine::updateAverageDescDir over a batch of landmarks (src/mapFeatures.cpp:51-93,
         :121-163) -> (med_idx int32[n_lm], med_desc uint8[n_lm, 32], med_dir float64[n_lm, 3])."""

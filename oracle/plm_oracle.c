@@ -976,3 +976,79 @@ PLO_API int plo_line_pair_filter(const float *ln1, int n1, const float *ln2, int
     }
     return kept;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Local-map selection and reprojection gates of MapHandler::matchMap2KFPoints / matchMap2KFLines
+ * (src/mapHandler.cpp:583-682, :685-803; PinholeStereoCamera::projection stvo-pl/src/pinholeStereoCamera.cpp:239-245).
+ * PARITY UNPINNED: src/mapHandler.cpp needs g2o / Eigen / OpenCV to compile, and the summation order of Eigen's fixed
+ * 3x3 * 3x1 product (Twf.block(0,0,3,3) * X) is not reproducible without Eigen.  Restated from the source with the
+ * product summed left to right; tests/test_reproj.py cross-checks selections, cell coordinates and gate decisions
+ * against an independent numpy form and bounds the fp64 difference to it.
+ */
+typedef struct plo_map_view {
+    double T[12];
+    double fx, fy, cx, cy;
+    double inv_width, inv_height;
+    int32_t width, height;
+} plo_map_view;
+
+static void plo_view_point(const plo_map_view *v, const double *X, double P[3], double uv[2])
+{
+    for (int r = 0; r < 3; r++)
+        P[r] = ((v->T[4 * r] * X[0] + v->T[4 * r + 1] * X[1]) + v->T[4 * r + 2] * X[2]) + v->T[4 * r + 3];
+    uv[0] = v->cx + v->fx * P[0] / P[2];
+    uv[1] = v->cy + v->fy * P[1] / P[2];
+}
+
+/* mapHandler.cpp:596-609 / :698-714 -> number of selected landmarks */
+PLO_API int plo_map_select(int is_lines, const double *X, const uint8_t *active, int n, const plo_map_view *v,
+                           int32_t *sel, int32_t *coords, double *pf)
+{
+    const int per = is_lines ? 2 : 1;
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (active && !active[i]) continue;
+        double uv[2][2];
+        int keep = 1;
+        for (int k = 0; k < per; k++) {
+            double P[3];
+            plo_view_point(v, X + (size_t)i * 3 * per + 3 * k, P, uv[k]);
+            keep = keep && uv[k][0] > 0 && uv[k][0] < v->width && uv[k][1] > 0 && uv[k][1] < v->height && P[2] > 0.0;
+        }
+        if (!keep) continue;
+        sel[m] = i;
+        for (int k = 0; k < per; k++) {
+            coords[(size_t)m * 2 * per + 2 * k] = (int32_t)(uv[k][0] * v->inv_width);      /* pair<int,int>(double, double) */
+            coords[(size_t)m * 2 * per + 2 * k + 1] = (int32_t)(uv[k][1] * v->inv_height);
+            pf[(size_t)m * 2 * per + 2 * k] = uv[k][0];
+            pf[(size_t)m * 2 * per + 2 * k + 1] = uv[k][1];
+        }
+        m++;
+    }
+    return m;
+}
+
+/* mapHandler.cpp:652-680 / :767-800 -> count after the rejections */
+PLO_API int plo_map_gate(int is_lines, const double *pf, const int32_t *m12, int n_sel, const double *feat, int n2,
+                         double max_epip, uint8_t *ok, int count)
+{
+    for (int i1 = 0; i1 < n_sel; i1++) {
+        const int i2 = m12[i1];
+        ok[i1] = 0;
+        if (i2 < 0 || i2 >= n2) continue;
+        int pass;
+        if (!is_lines) {
+            const double dx = pf[2 * (size_t)i1] - feat[2 * (size_t)i2], dy = pf[2 * (size_t)i1 + 1] - feat[2 * (size_t)i2 + 1];
+            pass = sqrt(dx * dx + dy * dy) < max_epip;
+        } else {
+            const double *l = feat + 3 * (size_t)i2, *p = pf + 4 * (size_t)i1;
+            const double e0 = l[0] * p[0] + l[1] * p[1] + l[2];
+            const double e1 = l[0] * p[2] + l[1] * p[3] + l[2];
+            pass = e0 < max_epip && e1 < max_epip;
+        }
+        if (pass) ok[i1] = 1;
+        else --count;
+    }
+    return count;
+}

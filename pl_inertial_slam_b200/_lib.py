@@ -43,6 +43,11 @@ class DevGridArgs(C.Structure):
                 ("grid_cols", C.c_int32), ("is_lines", C.c_int32), ("best_lr", C.c_int32), ("win", C.c_int32 * 4)]
 
 
+class MapView(C.Structure):
+    _fields_ = [("T", C.c_double * 12), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("inv_width", C.c_double), ("inv_height", C.c_double), ("width", C.c_int32), ("height", C.c_int32)]
+
+
 class PeerGroup(C.Structure):
     _fields_ = [("xchg", C.POINTER(vp)), ("gather", C.POINTER(vp)), ("rank", C.c_int32), ("world", C.c_int32),
                 ("q_cap", C.c_int32), ("pad_", C.c_int32), ("n_rows_cap", C.c_int64), ("xchg_epoch", C.c_uint32),
@@ -152,6 +157,11 @@ SIGNATURES = {
     "plm_dev_sharded_match": (C.c_int, [vp, vp, C.c_int, C.c_int64, vp, C.c_int, C.c_float, C.c_int, vp, C.POINTER(PeerGroup),
                                         C.c_int64, vp, vp, vp]),
     "plm_dev_peer_reduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_int, vp, vp]),
+    "plm_map_select": (C.c_int, [vp, C.c_int, f64p, u8p, C.c_int, C.POINTER(MapView), i32p, i32p, f64p, intp]),
+    "plm_map_gate": (C.c_int, [vp, C.c_int, f64p, i32p, C.c_int, f64p, C.c_int, C.c_double, u8p, intp]),
+    "plm_dev_map_select": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.POINTER(MapView), vp, vp, vp, vp]),
+    "plm_dev_gather_rows": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
+    "plm_dev_map_gate": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_double, vp, vp]),
     "plm_shard_create": (C.c_int, [intp, C.c_int, C.c_int, C.c_int64, C.POINTER(vp)]),
     "plm_shard_destroy": (C.c_int, [vp]),
     "plm_shard_n_devices": (C.c_int, [vp]),

@@ -115,6 +115,47 @@ __device__ __forceinline__ int hamming256_t13(const Desc &a, const uint4 &blo, c
     return static_cast<int>(imad(__popc(ce), 4u, imad(__popc(se), 2u, imad(__popc(sc), 1u, __popc(x7)))));
 }
 
+// Three-POPC LOWER BOUND (the "B" rows of knn2 variant 4).  Transform as above except the last word, which becomes
+// the parity of all eight words: the xor y7 is then s1 = x0 ^ ... ^ x7, the ones digit of the per-column count.
+// The count of a column (0..8) is s1 + 2 s2 + 4 s4 + 8 c8; c8 (all eight words differ in that column) is dropped:
+//     lb = popc(s1) + 2 popc(s2) + 4 popc(s4)  <=  d,   d - lb = 8 popc(c8)   (mean 1 for random descriptors).
+// 16 LOP3 + 3 POPC: more ALU work, less XU work than the 13 / 4 form -- a block mixes both to balance the two pipes.
+// The exact distance (update path only) adds 8 popc(ce & se & c1).
+__device__ __forceinline__ uint32_t lop3_andn(uint32_t a, uint32_t b) { // a & ~b
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %2, 0x30;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_xor_and(uint32_t a, uint32_t b, uint32_t c) { // a ^ (b & c)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_and3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ void desc_transform16(uint4 &lo, uint4 &hi) {
+    desc_transform13(lo, hi);
+    hi.w ^= hi.z;
+}
+// a, blo, bhi are descriptors in the parity-transformed domain.  EXACT selects the exact distance.
+template <bool EXACT>
+__device__ __forceinline__ int hamming256_t16(const Desc &a, const uint4 &blo, const uint4 &bhi) {
+    const uint32_t x0 = a.lo.x ^ blo.x, x1 = a.lo.y ^ blo.y, sa = a.lo.z ^ blo.z, x3 = a.lo.w ^ blo.w;
+    const uint32_t x4 = a.hi.x ^ bhi.x, sb = a.hi.y ^ bhi.y, sc = a.hi.z ^ bhi.z, s1 = a.hi.w ^ bhi.w;
+    const uint32_t ca = lop3_carry_from_sum(x0, x1, sa);
+    const uint32_t cb = lop3_carry_from_sum(x3, x4, sb);
+    const uint32_t cc = lop3_carry_from_sum(sa, sb, sc);
+    const uint32_t c1 = lop3_andn(sc, s1);                   // sc & x7 with x7 = sc ^ s1
+    const uint32_t se = lop3_xor3(ca, cb, cc), ce = lop3_maj(ca, cb, cc);
+    const uint32_t s2 = se ^ c1, s4 = lop3_xor_and(ce, se, c1);
+    uint32_t d = imad(__popc(s4), 4u, imad(__popc(s2), 2u, __popc(s1)));
+    if (EXACT) d = imad(__popc(lop3_and3(ce, se, c1)), 8u, d);
+    return static_cast<int>(d);
+}
+
 // Packed 64-bit key: (distance << 32) | global train index.  Unsigned min == (dist, idx) lexicographic.
 __device__ __forceinline__ unsigned long long make_key64(uint32_t dist, uint32_t idx) {
     return (static_cast<unsigned long long>(dist) << 32) | idx;

@@ -47,8 +47,16 @@ struct KnnTask {
     unsigned long long idx_base;
     long long n2;
     int n1, unit_rows, n_workers, n_units;
-    int pad_, pad2_;
+    // the first extra_qb query blocks (of `threads` queries each) have n_workers + 1 workers, so that qblocks x workers
+    // can equal the number of resident CTA slots exactly; 0 = every block has n_workers
+    int extra_qb, threads;
+    // optional per-query bound shared by the workers of a launch (long scans only): the smallest second-best DISTANCE
+    // any worker has found so far.  A row farther than that cannot be among the two nearest of the whole train set,
+    // whichever worker scans it, so workers skip it -- the merged result is unchanged (rows AT the bound are kept:
+    // their index may be lower).
+    uint32_t *gthr;
 };
+__device__ __forceinline__ int knn_workers_of(const KnnTask &t, int qblock) { return t.n_workers + (qblock < t.extra_qb ? 1 : 0); }
 struct KnnTaskPair {
     KnnTask t[2];
     int cta_split; // CTAs [0, cta_split) belong to t[0], the rest to t[1]
@@ -64,16 +72,22 @@ struct KnnTaskPair {
 //            test is exact.  For long scans the update path is almost never taken.
 // VARIANT 3: as 2 with the 13-LOP3 distance (plm_common.cuh): the query is transformed once, every stage of
 //            train rows is transformed in place in shared memory before it is scanned.
+// VARIANT 4: as 3, but the first KNN_B_ROWS rows of every group of 8 carry the parity transform and go through the
+//            16-LOP3 / 3-POPC lower bound: the blocked test min(...) < thr stays exact (a lower bound can only make the
+//            update path run more often, and that path recomputes those rows exactly), while the XU pipe (POPC), the
+//            binding one in variant 3, does 29 instead of 32 instructions per 8 pairs and the ALU pipe 118 instead of 109.
+constexpr int KNN_B_ROWS = 3;
+
 template <int VARIANT>
 __device__ __forceinline__ int knn_dist(const Desc &a, const uint4 &blo, const uint4 &bhi) {
-    if (VARIANT == 3) return hamming256_t13(a, blo, bhi);
+    if (VARIANT >= 3) return hamming256_t13(a, blo, bhi);
     if (VARIANT == 2) return hamming256_csa4(a, blo, bhi);
     if (VARIANT == 1) return hamming256_csa(a, blo, bhi);
     return hamming256(a, blo, bhi);
 }
 
 template <int THREADS, int VARIANT>
-__device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, int worker, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
+__device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, int worker, int n_workers, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
     const int tid = threadIdx.x;
     const int n1 = t.n1;
     const int qi = qblock * THREADS + tid;
@@ -84,12 +98,21 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
         a.lo = make_uint4(0, 0, 0, 0);
         a.hi = a.lo;
     }
-    if (VARIANT == 3) desc_transform13(a.lo, a.hi);
+    if (VARIANT >= 3) desc_transform13(a.lo, a.hi);
+    Desc ab = a; // variant 4: the query in the parity-transformed domain
+    if (VARIANT == 4) ab.hi.w ^= ab.hi.z;
     const uint4 *db = t.db;
-    const int unit_rows = t.unit_rows, n_units = t.n_units, step = t.n_workers;
+    const int unit_rows = t.unit_rows, n_units = t.n_units, step = n_workers;
     const uint32_t idx_base = static_cast<uint32_t>(t.idx_base); // idx_base + n2 <= 2^32 (checked by the host)
     unsigned long long B0 = KEY64_ABSENT, B1 = KEY64_ABSENT;     // running top-2 over all units of this worker
-    int thr = 1023;                                              // variant 2: distance a row must beat (> 256: none yet)
+    int thr = 1023;                                              // variant >= 2: distance a row must beat (> 256: none yet)
+    int gcap = 1023;                                             // ... and the cap taken from the launch-wide bound
+    uint32_t *gthr = (VARIANT >= 2 && t.gthr && qi < n1) ? t.gthr + qi : nullptr;
+    auto lower_thr = [&]() { // own second best changed: new strict threshold, published to the other workers
+        const int own = (B1 == KEY64_ABSENT) ? 1023 : static_cast<int>(B1 >> 32);
+        if (gthr && own < 1023) atomicMin(gthr, static_cast<uint32_t>(own));
+        thr = min(own, gcap);
+    };
 
     auto rows_of = [&](int u) { return static_cast<int>(min(static_cast<long long>(unit_rows), t.n2 - static_cast<long long>(u) * unit_rows)); };
     auto issue = [&](int u, int buf) {
@@ -111,15 +134,21 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
         }
         __syncthreads();
         const int rows = rows_of(u);
-        if (VARIANT == 3) {
+        if (VARIANT >= 3) {
             uint4 *w = stage[buf];
             for (int r = tid; r < rows; r += THREADS) {
                 uint4 lo = w[2 * r], hi = w[2 * r + 1];
                 desc_transform13(lo, hi);
+                if (VARIANT == 4 && (r & 7) < KNN_B_ROWS) hi.w ^= hi.z;
                 w[2 * r] = lo;
                 w[2 * r + 1] = hi;
             }
             __syncthreads();
+        }
+        if (VARIANT >= 2 && gthr) { // once per stage: the bound the other workers have reached (rows AT the bound stay in)
+            const uint32_t g = *reinterpret_cast<volatile uint32_t *>(gthr);
+            gcap = static_cast<int>(min(g, 1022u)) + 1;
+            thr = min(thr, gcap);
         }
         const uint4 *sb = stage[buf];
         const uint32_t gbase = idx_base + static_cast<uint32_t>(u) * static_cast<uint32_t>(unit_rows);
@@ -128,19 +157,26 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
             for (; j + 8 <= rows; j += 8) {
                 int d[8];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) d[v] = knn_dist<VARIANT>(a, sb[2 * (j + v)], sb[2 * (j + v) + 1]);
+                for (int v = 0; v < 8; ++v)
+                    d[v] = (VARIANT == 4 && v < KNN_B_ROWS) ? hamming256_t16<false>(ab, sb[2 * (j + v)], sb[2 * (j + v) + 1])
+                                                            : knn_dist<VARIANT>(a, sb[2 * (j + v)], sb[2 * (j + v) + 1]);
                 const int m = min(min(min(d[0], d[1]), min(d[2], d[3])), min(min(d[4], d[5]), min(d[6], d[7])));
                 if (m < thr) {
+                    if (VARIANT == 4) {
+#pragma unroll
+                        for (int v = 0; v < KNN_B_ROWS; ++v) d[v] = hamming256_t16<true>(ab, sb[2 * (j + v)], sb[2 * (j + v) + 1]);
+                    }
 #pragma unroll
                     for (int v = 0; v < 8; ++v) top2_insert(B0, B1, make_key64(d[v], gbase + j + v));
-                    thr = (B1 == KEY64_ABSENT) ? 1023 : static_cast<int>(B1 >> 32);
+                    lower_thr();
                 }
             }
             for (; j < rows; ++j) {
-                const int d = knn_dist<VARIANT>(a, sb[2 * j], sb[2 * j + 1]);
+                const int d = (VARIANT == 4 && (j & 7) < KNN_B_ROWS) ? hamming256_t16<true>(ab, sb[2 * j], sb[2 * j + 1])
+                                                                     : knn_dist<VARIANT>(a, sb[2 * j], sb[2 * j + 1]);
                 if (d < thr) {
                     top2_insert(B0, B1, make_key64(d, gbase + j));
-                    thr = (B1 == KEY64_ABSENT) ? 1023 : static_cast<int>(B1 >> 32);
+                    lower_thr();
                 }
             }
         } else {
@@ -165,8 +201,16 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128) ? 9 : 12) knn2_slice
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
     const int which = static_cast<int>(blockIdx.x) >= tasks.cta_split ? 1 : 0;
     const KnnTask &t = tasks.t[which];
-    const int local = static_cast<int>(blockIdx.x) - (which ? tasks.cta_split : 0);
-    knn2_slice_body<THREADS, VARIANT>(t, local / t.n_workers, local % t.n_workers, stage);
+    int local = static_cast<int>(blockIdx.x) - (which ? tasks.cta_split : 0);
+    int nw = t.n_workers, qb0 = 0;
+    const int wide = t.extra_qb * (t.n_workers + 1); // CTAs of the query blocks that have one more worker
+    if (local < wide) {
+        nw = t.n_workers + 1;
+    } else {
+        local -= wide;
+        qb0 = t.extra_qb;
+    }
+    knn2_slice_body<THREADS, VARIANT>(t, qb0 + local / nw, local % nw, nw, stage);
 }
 
 // Batched form: cta_map[cta] = (task, qblock, worker); tasks live in device memory.
@@ -175,7 +219,7 @@ __global__ void __launch_bounds__(THREADS) knn2_slice_list_kernel(const KnnTask 
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
     const int4 m = __ldg(cta_map + blockIdx.x);
     const KnnTask t = tasks[m.x];
-    knn2_slice_body<THREADS, VARIANT>(t, m.y, m.z, stage);
+    knn2_slice_body<THREADS, VARIANT>(t, m.y, m.z, t.n_workers, stage);
 }
 
 // Slice merge + (optionally) the matchNNR acceptance (stvo-pl/src/matching.cpp:53-58).
@@ -187,7 +231,8 @@ __device__ __forceinline__ void knn2_merge_body(const KnnTask &t, int q, float n
     bool acc = false;
     if (q < t.n1) {
         unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
-        for (int p = 0; p < t.n_workers; ++p) {
+        const int nw = t.extra_qb ? knn_workers_of(t, q / t.threads) : t.n_workers;
+        for (int p = 0; p < nw; ++p) {
             const ulonglong2 v = t.part[static_cast<size_t>(p) * t.n1 + q];
             top2_insert(b0, b1, v.x);
             top2_insert(b0, b1, v.y);
@@ -222,7 +267,8 @@ __global__ void knn2_merge_wide_kernel(const KnnTaskPair tasks, int task0, float
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= t.n1) return;
     unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
-    for (int p = lane; p < t.n_workers; p += 32) {
+    const int nw = t.extra_qb ? knn_workers_of(t, q / t.threads) : t.n_workers;
+    for (int p = lane; p < nw; p += 32) {
         const ulonglong2 v = t.part[static_cast<size_t>(p) * t.n1 + q];
         top2_insert(b0, b1, v.x);
         top2_insert(b0, b1, v.y);

@@ -24,6 +24,7 @@
 #include "plm_grid.cuh"
 #include "plm_knn2.cuh"
 #include "plm_map.cuh"
+#include "plm_reproj.cuh"
 #include "plm_micro.cuh"
 #include "plm_peer.cuh"
 #include "plm_stereo.cuh"
@@ -77,7 +78,7 @@ struct plm_ctx {
     uint64_t launches = 0;
     bool fused_attr_set = false;
     bool cluster_attr_set = false;
-    int knn_occ[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    int knn_occ[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
     bool rows_attr_set = false;
     // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
@@ -172,6 +173,8 @@ struct KnnPlan {
     int unit_rows = plm::KNN_STAGE_ROWS;
     int n_units = 1;
     int n_workers = 1;
+    int extra_qb = 0;     // query blocks with n_workers + 1 workers (fills the last resident CTA slots)
+    bool share_thr = false; // long scans: the workers of a query share their second-best bound
 };
 
 // frame pipeline: candidate slots per query row the pair-list form is sized for (points, lines); options
@@ -183,6 +186,7 @@ int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame 
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
 long long g_peer_spin_ticks = 4000000000ll; // bounded spin of the peer-memory kernels (~2 s of SM clock); option "peer_spin_ms"
+int g_knn_fill = 1;     // long brute-force scans: uneven workers fill every CTA slot + shared second-best bound (0: off, measurement)
 int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
 
 // -1 = automatic (variant 3 for long slices, 1 otherwise); 0..3 force a variant (measurement only)
@@ -195,6 +199,9 @@ int knn_variant_for(int slice_rows) {
         if (e && std::strcmp(e, "csa5") == 0) g_knn_variant = 1;
         if (e && std::strcmp(e, "csa4") == 0) g_knn_variant = 2;
         if (e && std::strcmp(e, "t13") == 0) g_knn_variant = 3;
+        if (e && std::strcmp(e, "mix") == 0) g_knn_variant = 4;
+        const char *f = std::getenv("PLM_KNN_FILL"); // measurement knob, same as option "knn_fill"
+        if (f) g_knn_fill = std::atoi(f) ? 1 : 0;
     }
     if (g_knn_variant >= 0) return g_knn_variant;
     return slice_rows >= 2048 ? 3 : 1;
@@ -208,12 +215,14 @@ int knn_ctas_per_sm(plm_ctx *ctx, int threads, int variant) {
     cudaError_t e = cudaErrorUnknown;
 #define PLM_KNN_OCC(T, V) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<T, V>, T, 0)
     if (threads == 128) {
-        if (variant == 3) PLM_KNN_OCC(128, 3);
+        if (variant == 4) PLM_KNN_OCC(128, 4);
+        else if (variant == 3) PLM_KNN_OCC(128, 3);
         else if (variant == 2) PLM_KNN_OCC(128, 2);
         else if (variant == 1) PLM_KNN_OCC(128, 1);
         else PLM_KNN_OCC(128, 0);
     } else {
-        if (variant == 3) PLM_KNN_OCC(64, 3);
+        if (variant == 4) PLM_KNN_OCC(64, 4);
+        else if (variant == 3) PLM_KNN_OCC(64, 3);
         else if (variant == 2) PLM_KNN_OCC(64, 2);
         else if (variant == 1) PLM_KNN_OCC(64, 1);
         else PLM_KNN_OCC(64, 0);
@@ -239,13 +248,19 @@ KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2) {
     p.unit_rows = static_cast<int>(rows);
     p.n_units = static_cast<int>(std::max<long long>(1, (n2 + rows - 1) / rows));
     p.n_workers = static_cast<int>(std::min<long long>(p.n_units, want));
+    if (variant >= 2 && g_knn_fill) {
+        // long scans: qblocks x workers rarely divides the resident CTA slots (50 x 26 = 1300 of 1332): the first
+        // `extra_qb` query blocks get one more worker, so that a launch fills every slot
+        if (p.n_workers == want && p.n_units > want && qblocks * want < capacity) p.extra_qb = static_cast<int>(std::min<long long>(qblocks, capacity - qblocks * want));
+        p.share_thr = true;
+    }
     return p;
 }
 
 int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threads) {
     long long total = 0;
     for (int i = 0; i < n_tasks; ++i) {
-        const long long c = static_cast<long long>((tp.t[i].n1 + threads - 1) / threads) * tp.t[i].n_workers;
+        const long long c = static_cast<long long>((tp.t[i].n1 + threads - 1) / threads) * tp.t[i].n_workers + tp.t[i].extra_qb;
         if (i == 0) tp.cta_split = static_cast<int>(c);
         total += c;
     }
@@ -256,6 +271,15 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
     int min_rows = INT_MAX;
     for (int i = 0; i < n_tasks; ++i) min_rows = std::min<long long>(min_rows, std::min<long long>(tp.t[i].n2, INT_MAX));
     const int variant = knn_variant_for(min_rows >= 65536 ? 4096 : 64);
+    if (variant >= 2 && g_knn_fill) {
+        // the shared second-best bounds live behind each task's partial results (build_knn_task reserved the room)
+        for (int i = 0; i < n_tasks; ++i) {
+            plm::KnnTask &t = tp.t[i];
+            if (!t.part || t.n1 <= 0) continue;
+            t.gthr = reinterpret_cast<uint32_t *>(t.part + size_t(t.n_workers + (t.extra_qb ? 1 : 0)) * size_t(t.n1));
+            CU_TRY(cudaMemsetAsync(t.gthr, 0xFF, size_t(t.n1) * 4, ctx->stream));
+        }
+    }
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (ctx->profiling) {
         if (!ctx->prof_free.empty()) {
@@ -269,12 +293,14 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
     }
 #define PLM_KNN_LAUNCH(T, V) plm::knn2_slice_kernel<T, V><<<grid, T, 0, ctx->stream>>>(tp)
     if (threads == 128) {
-        if (variant == 3) PLM_KNN_LAUNCH(128, 3);
+        if (variant == 4) PLM_KNN_LAUNCH(128, 4);
+        else if (variant == 3) PLM_KNN_LAUNCH(128, 3);
         else if (variant == 2) PLM_KNN_LAUNCH(128, 2);
         else if (variant == 1) PLM_KNN_LAUNCH(128, 1);
         else PLM_KNN_LAUNCH(128, 0);
     } else {
-        if (variant == 3) PLM_KNN_LAUNCH(64, 3);
+        if (variant == 4) PLM_KNN_LAUNCH(64, 4);
+        else if (variant == 3) PLM_KNN_LAUNCH(64, 3);
         else if (variant == 2) PLM_KNN_LAUNCH(64, 2);
         else if (variant == 1) PLM_KNN_LAUNCH(64, 1);
         else PLM_KNN_LAUNCH(64, 0);
@@ -325,11 +351,15 @@ int check_desc(const uint8_t *d, int n, size_t step) {
 PLM_API int plm_set_option(const char *key, int value) {
     if (!key) return fail(PLM_E_INVALID, "null key");
     if (std::strcmp(key, "knn_variant") == 0) {
-        g_knn_variant = (value >= 0 && value <= 3) ? value : -1;
+        g_knn_variant = (value >= 0 && value <= 4) ? value : -1;
         return PLM_OK;
     }
     if (std::strcmp(key, "peer_spin_ms") == 0) {
         g_peer_spin_ticks = static_cast<long long>(std::max(1, value)) * 2000000ll; // ~2 GHz SM clock
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "knn_fill") == 0) {
+        g_knn_fill = value ? 1 : 0;
         return PLM_OK;
     }
     if (std::strcmp(key, "grid_rows") == 0) {
@@ -519,13 +549,15 @@ int build_knn_task(plm_ctx *ctx, Layout &L, plm::KnnTask &t, KnnPlan &plan, cons
     t.unit_rows = plan.unit_rows;
     t.n_units = plan.n_units;
     t.n_workers = plan.n_workers;
-    t.pad2_ = 0;
+    t.extra_qb = plan.extra_qb;
+    t.threads = plan.threads;
     t.part = nullptr;
     t.top2 = nullptr;
     t.m = nullptr;
     t.count = nullptr;
-    t.pad_ = 0;
-    part_off = L.add(size_t(plan.n_workers) * size_t(std::max(n1, 1)) * sizeof(ulonglong2));
+    t.gthr = nullptr;
+    part_off = L.add(size_t(plan.n_workers + (plan.extra_qb ? 1 : 0)) * size_t(std::max(n1, 1)) * sizeof(ulonglong2) +
+                     (plan.share_thr ? align_up(size_t(std::max(n1, 1)) * 4) : 0));
     return PLM_OK;
 }
 
@@ -2226,7 +2258,7 @@ int batch_set_match_impl(plm_batch *b, const uint8_t *arena, const void *arena_d
             t.db = reinterpret_cast<const uint4 *>(static_cast<uintptr_t>(dir ? jb.off1 : jb.off2));
             t.m = reinterpret_cast<int32_t *>(static_cast<uintptr_t>(dir ? m21_off[j] : jb.off_m));
             t.count = dir ? nullptr : reinterpret_cast<int32_t *>(static_cast<uintptr_t>(j) + 1); // +1: non-null marker
-            t.pad_ = dir;
+            t.threads = dir; // direction marker until the pointers are patched
             part_off.push_back(part_bytes);
             part_bytes += align_up(size_t(slices) * nq * sizeof(ulonglong2));
             const int task_id = static_cast<int>(tasks.size());
@@ -2271,14 +2303,14 @@ int batch_set_match_impl(plm_batch *b, const uint8_t *arena, const void *arena_d
     const uint4 *d_arena = arena_dev ? static_cast<const uint4 *>(arena_dev) : reinterpret_cast<const uint4 *>(D + o_arena);
     for (size_t i = 0; i < tasks.size(); ++i) {
         plm::KnnTask &t = tasks[i];
-        const bool dir = t.pad_ != 0;
+        const bool dir = t.threads != 0;
         t.q = d_arena + 2 * reinterpret_cast<uintptr_t>(t.q);
         t.db = d_arena + 2 * reinterpret_cast<uintptr_t>(t.db);
         t.m = (dir ? d_m21 : d_m12) + reinterpret_cast<uintptr_t>(t.m);
         t.count = t.count ? d_counts + (reinterpret_cast<uintptr_t>(t.count) - 1) : nullptr;
         t.part = reinterpret_cast<ulonglong2 *>(D + o_part + part_off[i]);
         t.top2 = nullptr;
-        t.pad_ = 0;
+        t.threads = 0;
     }
     for (plm::XJob &x : xjobs) {
         x.m12 = d_m12 + reinterpret_cast<uintptr_t>(x.m12);
@@ -2497,5 +2529,139 @@ PLM_API int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts) {
 }
 
 // ---------------------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------------------
+// Local-map selection and reprojection gates of matchMap2KF* (csrc/plm_reproj.cuh)
+namespace {
+
+plm::MapView to_view(const plm_map_view *v) {
+    plm::MapView m;
+    for (int i = 0; i < 12; ++i) m.T[i] = v->T[i];
+    m.fx = v->fx; m.fy = v->fy; m.cx = v->cx; m.cy = v->cy;
+    m.inv_width = v->inv_width; m.inv_height = v->inv_height;
+    m.width = v->width; m.height = v->height;
+    return m;
+}
+
+} // namespace
+
+PLM_API int plm_dev_map_select(plm_ctx *ctx, int is_lines, const double *X_dev, const uint8_t *active_dev, int n, const plm_map_view *v,
+                               int32_t *sel_dev, int32_t *coords_dev, double *pf_dev, int32_t *n_sel_dev) {
+    if (n < 0 || !v || !n_sel_dev) return fail(PLM_E_INVALID, "negative size / null view / null n_sel");
+    if (n > 0 && (!X_dev || !sel_dev || !coords_dev || !pf_dev)) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    if (n == 0) {
+        CU_TRY(cudaMemsetAsync(n_sel_dev, 0, 4, ctx->stream));
+        return PLM_OK;
+    }
+    const int n_cta = (n + 255) / 256;
+    if ((st = ctx->ensure_aux(size_t(n_cta) * 4)) != PLM_OK) return st;
+    int32_t *cnt = reinterpret_cast<int32_t *>(ctx->d_aux);
+    const plm::MapView mv = to_view(v);
+    for (int pass = 0; pass < 2; ++pass) {
+        if (is_lines) plm::map_select_kernel<2><<<n_cta, 256, 0, ctx->stream>>>(X_dev, active_dev, n, mv, pass, cnt, sel_dev, coords_dev, pf_dev, n_sel_dev);
+        else plm::map_select_kernel<1><<<n_cta, 256, 0, ctx->stream>>>(X_dev, active_dev, n, mv, pass, cnt, sel_dev, coords_dev, pf_dev, n_sel_dev);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        if (pass == 0) {
+            plm::map_count_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, n_cta);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+    }
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_gather_rows(plm_ctx *ctx, const void *rows_dev, const int32_t *sel_dev, const int32_t *n_sel_dev, int n_max, void *out_dev) {
+    if (n_max < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_max == 0) return PLM_OK;
+    if (!rows_dev || !sel_dev || !n_sel_dev || !out_dev) return fail(PLM_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(rows_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15) return fail(PLM_E_INVALID, "device descriptor pointers must be 16-byte aligned");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    plm::gather_rows_kernel<<<(n_max + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint4 *>(rows_dev), sel_dev, n_sel_dev, static_cast<uint4 *>(out_dev));
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+PLM_API int plm_dev_map_gate(plm_ctx *ctx, int is_lines, const double *pf_dev, const int32_t *m12_dev, const int32_t *n_sel_dev, int n_max,
+                             const double *feat_dev, int n2, double max_epip, uint8_t *ok_dev, int32_t *count_inout_dev) {
+    if (n_max < 0 || n2 < 0) return fail(PLM_E_INVALID, "negative size");
+    if (n_max == 0) return PLM_OK;
+    if (!pf_dev || !m12_dev || !n_sel_dev || !ok_dev || !count_inout_dev || (n2 > 0 && !feat_dev)) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    if (is_lines) plm::map_gate_kernel<1><<<(n_max + 255) / 256, 256, 0, ctx->stream>>>(pf_dev, m12_dev, n_sel_dev, feat_dev, n2, max_epip, ok_dev, count_inout_dev);
+    else plm::map_gate_kernel<0><<<(n_max + 255) / 256, 256, 0, ctx->stream>>>(pf_dev, m12_dev, n_sel_dev, feat_dev, n2, max_epip, ok_dev, count_inout_dev);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// Host-buffer forms (tests, hosts that keep the landmarks in host memory).
+PLM_API int plm_map_select(plm_ctx *ctx, int is_lines, const double *X, const uint8_t *active, int n, const plm_map_view *v, int32_t *sel,
+                           int32_t *coords, double *pf, int *n_sel) {
+    if (n < 0 || !v || !n_sel) return fail(PLM_E_INVALID, "negative size / null view / null n_sel");
+    *n_sel = 0;
+    if (n == 0) return PLM_OK;
+    if (!X || !sel || !coords || !pf) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    const int per = is_lines ? 2 : 1;
+    Layout L;
+    const size_t o_x = L.add(size_t(n) * 24 * per), o_act = L.add(active ? size_t(n) : 0), o_sel = L.add(size_t(n) * 4 + 16),
+                 o_co = L.add(size_t(n) * 8 * per), o_pf = L.add(size_t(n) * 16 * per);
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    char *D = ctx->d_buf;
+    CU_TRY(cudaMemcpyAsync(D + o_x, X, size_t(n) * 24 * per, cudaMemcpyHostToDevice, ctx->stream));
+    if (active) CU_TRY(cudaMemcpyAsync(D + o_act, active, size_t(n), cudaMemcpyHostToDevice, ctx->stream));
+    int32_t *d_sel = reinterpret_cast<int32_t *>(D + o_sel), *d_n = d_sel + n;
+    if ((st = plm_dev_map_select(ctx, is_lines, reinterpret_cast<const double *>(D + o_x), active ? reinterpret_cast<const uint8_t *>(D + o_act) : nullptr, n,
+                                 v, d_sel, reinterpret_cast<int32_t *>(D + o_co), reinterpret_cast<double *>(D + o_pf), d_n)) != PLM_OK)
+        return st;
+    int32_t cnt = 0;
+    CU_TRY(cudaMemcpyAsync(&cnt, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (cnt > 0) {
+        CU_TRY(cudaMemcpyAsync(sel, d_sel, size_t(cnt) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(coords, D + o_co, size_t(cnt) * 8 * per, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(pf, D + o_pf, size_t(cnt) * 16 * per, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    *n_sel = cnt;
+    return PLM_OK;
+}
+
+PLM_API int plm_map_gate(plm_ctx *ctx, int is_lines, const double *pf, const int32_t *m12, int n_sel, const double *feat, int n2, double max_epip,
+                         uint8_t *ok, int *count_inout) {
+    if (n_sel < 0 || n2 < 0 || !count_inout) return fail(PLM_E_INVALID, "negative size / null count");
+    if (n_sel == 0) return PLM_OK;
+    if (!pf || !m12 || !ok || (n2 > 0 && !feat)) return fail(PLM_E_INVALID, "null pointer");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    const int per = is_lines ? 2 : 1, fw = is_lines ? 3 : 2;
+    Layout L;
+    const size_t o_pf = L.add(size_t(n_sel) * 16 * per), o_m = L.add(size_t(n_sel) * 4), o_f = L.add(size_t(std::max(n2, 1)) * 8 * fw),
+                 o_ok = L.add(size_t(n_sel)), o_c = L.add(16);
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    char *D = ctx->d_buf;
+    int32_t head[2] = {n_sel, *count_inout};
+    CU_TRY(cudaMemcpyAsync(D + o_pf, pf, size_t(n_sel) * 16 * per, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(D + o_m, m12, size_t(n_sel) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n2 > 0) CU_TRY(cudaMemcpyAsync(D + o_f, feat, size_t(n2) * 8 * fw, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(D + o_c, head, 8, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t *d_head = reinterpret_cast<int32_t *>(D + o_c);
+    if ((st = plm_dev_map_gate(ctx, is_lines, reinterpret_cast<const double *>(D + o_pf), reinterpret_cast<const int32_t *>(D + o_m), d_head, n_sel,
+                               reinterpret_cast<const double *>(D + o_f), n2, max_epip, reinterpret_cast<uint8_t *>(D + o_ok), d_head + 1)) != PLM_OK)
+        return st;
+    CU_TRY(cudaMemcpyAsync(ok, D + o_ok, size_t(n_sel), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(head, d_head, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *count_inout = head[1];
+    return PLM_OK;
+}
+
 #include "plm_frames_api.inl"
 #include "plm_shard_api.inl"

@@ -11,11 +11,13 @@ and the pose maths stay with the caller.  Every arithmetic step runs on the GPU 
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import List, Optional, Sequence
 
 import numpy as np
 
+from . import _lib as L
 from . import grid as G
 from . import matching as M
 
@@ -26,6 +28,8 @@ class SlamConfig:
     minPointMatches: int = 10
     minLineMatches: int = 6
     lcInlierRatio: float = 30.0
+    maxKFEpipP: float = 1.0          # slamConfig.cpp:51
+    maxKFEpipL: float = 1.0          # slamConfig.cpp:52
 
 
 @dataclass
@@ -187,6 +191,76 @@ def matchMap2KFLines(pj_lines_px: np.ndarray, map_lls_desc: np.ndarray, unmatche
     return _grid_then_fallback(coords, map_lls_desc, (cs, ci, G.GRID_ROWS, G.GRID_COLS), unmatched_ls_desc, dirs,
                                M.Config.matchingF2FWs, SlamConfig.minLineMatches, M.Config.minRatio12L,
                                len(map_lls_desc), len(coords), ctx)
+
+
+def map_view(Twf: np.ndarray, cam: Sequence[float], inv_width: float, inv_height: float, width: int, height: int) -> L.MapView:
+    """Twf (4x4 or 3x4, world -> frame), cam = (fx, fy, cx, cy)."""
+    v = L.MapView()
+    T = np.asarray(Twf, np.float64).reshape(-1, 4)[:3]
+    v.T[:] = [float(x) for x in T.reshape(-1)]
+    v.fx, v.fy, v.cx, v.cy = [float(x) for x in cam]
+    v.inv_width, v.inv_height, v.width, v.height = float(inv_width), float(inv_height), int(width), int(height)
+    return v
+
+
+def mapSelect(X: np.ndarray, active: Optional[np.ndarray], view: L.MapView, ctx=None):
+    """The local-map selection of matchMap2KFPoints / Lines (mapHandler.cpp:596-609, :698-714): landmarks (n x 3
+    points or n x 6 segments) that are active and project inside the image -> (sel, coords, pf), compacted in order."""
+    X = np.ascontiguousarray(X, np.float64)
+    is_lines = X.shape[1] == 6
+    n, per = len(X), 2 if is_lines else 1
+    act = None if active is None else np.ascontiguousarray(active, np.uint8)
+    sel, coords, pf = np.zeros(max(n, 1), np.int32), np.zeros((max(n, 1), 2 * per), np.int32), np.zeros((max(n, 1), 2 * per))
+    m = C.c_int(0)
+    L.check(L.load().plm_map_select(M._h(ctx), int(is_lines), X.ctypes.data_as(L.f64p), None if act is None else act.ctypes.data_as(L.u8p),
+                                    n, C.byref(view), sel.ctypes.data_as(L.i32p), coords.ctypes.data_as(L.i32p), pf.ctypes.data_as(L.f64p),
+                                    C.byref(m)), "plm_map_select")
+    return sel[:m.value].copy(), coords[:m.value].copy(), pf[:m.value].copy()
+
+
+def mapGate(pf: np.ndarray, m12: np.ndarray, feat: np.ndarray, max_epip: float, count: int, ctx=None):
+    """The reprojection gate after the matcher (mapHandler.cpp:652-680 points: feat = pl of the keyframe points;
+    :767-800 lines: feat = line equations le) -> (count after the rejections, ok flags per compacted row)."""
+    pf = np.ascontiguousarray(pf, np.float64)
+    is_lines = pf.shape[1] == 4
+    m = np.ascontiguousarray(m12, np.int32)
+    feat = np.ascontiguousarray(feat, np.float64)
+    ok = np.zeros(max(len(m), 1), np.uint8)
+    c = C.c_int(int(count))
+    L.check(L.load().plm_map_gate(M._h(ctx), int(is_lines), pf.ctypes.data_as(L.f64p), m.ctypes.data_as(L.i32p), len(m),
+                                  feat.ctypes.data_as(L.f64p), len(feat), float(max_epip), ok.ctypes.data_as(L.u8p), C.byref(c)),
+            "plm_map_gate")
+    return c.value, ok[:len(m)].copy()
+
+
+def matchMap2KFPointsFull(X: np.ndarray, active, med_desc: np.ndarray, view: L.MapView, unmatched_points_px: np.ndarray,
+                          unmatched_pt_desc: np.ndarray, ctx=None):
+    """MapHandler::matchMap2KFPoints end to end (mapHandler.cpp:583-682): selection, matchGrid (+ match fallback),
+    epipolar gate -> dict(sel, m12, ok, matches)."""
+    sel, coords, pf = mapSelect(X, active, view, ctx)
+    if len(sel) == 0 or len(unmatched_pt_desc) == 0:
+        return dict(sel=sel, m12=np.zeros(len(sel), np.int32) - 1, ok=np.zeros(len(sel), np.uint8), matches=0)
+    c = np.asarray(unmatched_points_px, np.float64)
+    cs, ci = G.csr_from_points(c[:, 0] * view.inv_width, c[:, 1] * view.inv_height)
+    d1 = np.ascontiguousarray(med_desc[sel])
+    n, m12 = _grid_then_fallback(coords, d1, (cs, ci, G.GRID_ROWS, G.GRID_COLS), unmatched_pt_desc, None, M.Config.matchingF2FWs,
+                                 SlamConfig.minPointMatches, M.Config.minRatio12P, len(d1), len(coords), ctx)
+    n, ok = mapGate(pf, m12, c, SlamConfig.maxKFEpipP, n, ctx)
+    return dict(sel=sel, m12=m12, ok=ok, matches=n)
+
+
+def matchMap2KFLinesFull(X: np.ndarray, active, med_desc: np.ndarray, view: L.MapView, unmatched_lines_px: np.ndarray,
+                         unmatched_le: np.ndarray, unmatched_ls_desc: np.ndarray, ctx=None):
+    """MapHandler::matchMap2KFLines end to end (mapHandler.cpp:685-803)."""
+    sel, coords, pf = mapSelect(X, active, view, ctx)
+    if len(sel) == 0 or len(unmatched_ls_desc) == 0:
+        return dict(sel=sel, m12=np.zeros(len(sel), np.int32) - 1, ok=np.zeros(len(sel), np.uint8), matches=0)
+    cs, ci, dirs = line_grid(unmatched_lines_px, view.inv_width, view.inv_height)
+    d1 = np.ascontiguousarray(med_desc[sel])
+    n, m12 = _grid_then_fallback(coords, d1, (cs, ci, G.GRID_ROWS, G.GRID_COLS), unmatched_ls_desc, dirs, M.Config.matchingF2FWs,
+                                 SlamConfig.minLineMatches, M.Config.minRatio12L, len(d1), len(coords), ctx)
+    n, ok = mapGate(pf, m12, unmatched_le, SlamConfig.maxKFEpipL, n, ctx)
+    return dict(sel=sel, m12=m12, ok=ok, matches=n)
 
 
 def loopClosureMatch(kf0_pdesc: np.ndarray, kf1_pdesc: np.ndarray, kf0_ldesc: np.ndarray, kf1_ldesc: np.ndarray, ctx=None):

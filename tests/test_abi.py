@@ -103,7 +103,7 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     from pl_inertial_slam_b200 import _lib as L
     pairs = [("plm_pair_job", L.PairJob), ("plm_grid_job", L.GridJob), ("plm_dev_grid_args", L.DevGridArgs),
              ("plm_frame_rec", L.FrameRec), ("plm_frame_config", L.FrameConfig), ("plm_frames_out", L.FramesOut),
-             ("plm_peer_group", L.PeerGroup)]
+             ("plm_peer_group", L.PeerGroup), ("plm_map_view", L.MapView)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "plmatch.h"', 'int main(void) {']
     for cname, cls in pairs:
         lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
