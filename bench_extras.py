@@ -501,7 +501,7 @@ def loop_closure_per_pair(ctx, cpu: bool = True) -> dict:
     core (its own two std::async threads) beside it."""
     import torch
     from pl_inertial_slam_b200.database import KeyframeDB
-    n_kf, per = 2000, 800
+    n_kf, per = int(os.environ.get("PLM_MODE_A_KFS", "2000")), 800       # 20000 = the full config-5 database
     rng = np.random.default_rng(synth.SEED0 + 55)
     rows = synth.rand_desc(rng, n_kf * per)
     kf_start = np.arange(n_kf + 1, dtype=np.int64) * per

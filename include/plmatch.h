@@ -122,6 +122,17 @@ int plm_match_nnr(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const u
 int plm_match(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2,
               size_t step2, float nnr, int best_lr, int32_t *m12_inout, int *n_matches);
 
+/* Frame session: the matcher calls of ONE frame as one host <-> device round trip.  Between plm_frame_begin and
+ * plm_frame_end the plm_match_nnr / plm_match / plm_match_grid_points / plm_match_grid_lines calls made on this context
+ * (NULL = the calling thread's default context) validate their arguments and are RECORDED; plm_frame_end then packs
+ * all inputs into one pinned block, issues the copies and kernels of the independent calls on three streams so that
+ * they overlap, synchronises once and writes every m12_inout / n_matches.  The recorded pointers (descriptors, grids,
+ * m12_inout, n_matches) must stay valid until plm_frame_end returns; results are only defined after it.  This is the
+ * stereo (points || lines) + temporal (points || lines) structure of StereoFrame::extractStereoFeatures /
+ * StereoFrameHandler::f2fTracking (stereoFrame.cpp:75-76, stereoFrameHandler.cpp:142-143) without host threads. */
+int plm_frame_begin(plm_ctx *ctx);
+int plm_frame_end(plm_ctx *ctx);
+
 /* StVO::matchGrid, points.  xy = n1 x (x, y) grid-cell coordinates of the queries.
  * Grid = CSR of GridStructure over the train features: cell (x, y) has id x * grid_rows + y,
  * cell_start has grid_rows * grid_cols + 1 entries, cell_items the bucket contents.
@@ -402,6 +413,15 @@ int plm_dev_peer_allgather_i32(plm_ctx *ctx, void *const *peers, int rank, int w
                                const int32_t *local_dev, int64_t row_lo, int64_t n_local, int64_t n_rows,
                                const int32_t *local_count_dev, int32_t *out_dev, int32_t *out_count_dev,
                                int32_t *error_dev);
+
+/* Single-GPU emulation of the peer kernels, for boxes with fewer GPUs than ranks (tests).  Kernels that wait for one
+ * another must never be separate launches on one GPU (nothing guarantees that they run at the same time), so between
+ * plm_peer_emulate_begin(world) and plm_peer_emulate_run the calling thread's plm_dev_top2_exchange /
+ * plm_dev_peer_reduce / plm_dev_peer_allgather_i32 calls (one per rank, same kind and size, buffers = plain device
+ * allocations of that GPU) are recorded instead of launched, and _run executes all of them as ONE cooperative launch
+ * (blockIdx.y = rank): every waiting CTA is co-resident with the CTAs it waits for.  world <= 4. */
+int plm_peer_emulate_begin(int world);
+int plm_peer_emulate_run(plm_ctx *ctx);
 
 /* The whole row-sharded matchGrid of one rank in ONE call (config 4 across GPUs): one minima pass, the prefix-min of the
  * column minima over the lower ranks, the match pass, the min of the per-column best pairs, the mutual check and the

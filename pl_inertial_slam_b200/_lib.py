@@ -105,6 +105,8 @@ SIGNATURES = {
     "plm_knn2": (C.c_int, [vp] + _DESC + _DESC + [C.c_uint64, u64p]),
     "plm_match_nnr": (C.c_int, [vp] + _DESC + _DESC + [C.c_float, i32p, intp]),
     "plm_match": (C.c_int, [vp] + _DESC + _DESC + [C.c_float, C.c_int, i32p, intp]),
+    "plm_frame_begin": (C.c_int, [vp]),
+    "plm_frame_end": (C.c_int, [vp]),
     "plm_match_grid_points": (C.c_int, [vp, i32p] + _DESC + [i32p, i32p, C.c_int, C.c_int] + _DESC +
                               [i32p, C.c_double, C.c_int, i32p, intp]),
     "plm_match_grid_lines": (C.c_int, [vp, i32p] + _DESC + [i32p, i32p, C.c_int, C.c_int] + _DESC +
@@ -149,6 +151,8 @@ SIGNATURES = {
     "plm_peer_free": (C.c_int, [vp, vp]),
     "plm_dev_top2_exchange": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint32, vp, C.c_int, vp,
                                         C.c_float, vp, vp, vp]),
+    "plm_peer_emulate_begin": (C.c_int, [C.c_int]),
+    "plm_peer_emulate_run": (C.c_int, [vp]),
     "plm_peer_gather_bytes": (C.c_size_t, [C.c_int, C.c_int64]),
     "plm_peer_alloc_bytes": (C.c_int, [vp, C.c_size_t, C.POINTER(vp), u8p]),
     "plm_dev_peer_allgather_i32": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int64, C.c_uint32, vp, C.c_int64,

@@ -64,7 +64,7 @@ __device__ __forceinline__ ulonglong2 ld_volatile_u64x2(const ulonglong2 *p) {
 // push + signal + wait of one CTA: element q of this rank (16 bytes) goes to slot [parity][my rank][q] of every
 // rank's buffer; returns false when a peer did not arrive in time.  After a true return the G slots
 // [parity][r][q] of the OWN buffer hold every rank's element (read them with ld_volatile_u64x2).
-__device__ __forceinline__ bool peer_push_wait(const PeerExchangeArgs &a, int q, bool active, ulonglong2 v) {
+__device__ __forceinline__ bool peer_push_wait(const PeerExchangeArgs &a, int bx, int q, bool active, ulonglong2 v) {
     const int par = a.epoch & 1;
     const size_t key_slot = (size_t(par) * a.world + a.rank) * a.q_cap; // [par][my rank][.]
     const size_t keys_bytes = peer_keys_bytes(a.world, a.q_cap);
@@ -80,14 +80,14 @@ __device__ __forceinline__ bool peer_push_wait(const PeerExchangeArgs &a, int q,
     if (threadIdx.x < a.world) { // signal
         const int dst = (a.rank + threadIdx.x) % a.world;
         uint32_t *flags = reinterpret_cast<uint32_t *>(a.peer[dst] + keys_bytes);
-        st_release_sys(flags + (size_t(par) * a.world + a.rank) * a.blocks_cap + blockIdx.x, a.epoch);
+        st_release_sys(flags + (size_t(par) * a.world + a.rank) * a.blocks_cap + bx, a.epoch);
     }
     __shared__ int s_fail;
     if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
     if (threadIdx.x < a.world) { // wait for block `blockIdx.x` of every rank
         const uint32_t *flags = reinterpret_cast<const uint32_t *>(a.peer[a.rank] + keys_bytes);
-        const uint32_t *f = flags + (size_t(par) * a.world + threadIdx.x) * a.blocks_cap + blockIdx.x;
+        const uint32_t *f = flags + (size_t(par) * a.world + threadIdx.x) * a.blocks_cap + bx;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != a.epoch) {
             if (clock64() - t0 > a.spin_limit) {
@@ -109,10 +109,10 @@ __device__ __forceinline__ const ulonglong2 *peer_slots(const PeerExchangeArgs &
     return reinterpret_cast<const ulonglong2 *>(a.peer[a.rank]) + size_t(a.epoch & 1) * a.world * a.q_cap;
 }
 
-__global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerExchangeArgs a) {
-    const int q = blockIdx.x * PEER_THREADS + threadIdx.x;
+__device__ __forceinline__ void top2_exchange_merge_body(const PeerExchangeArgs &a, int bx) {
+    const int q = bx * PEER_THREADS + threadIdx.x;
     const bool active = q < a.n1;
-    if (!peer_push_wait(a, q, active, active ? a.local[q] : make_ulonglong2(0, 0))) return;
+    if (!peer_push_wait(a, bx, q, active, active ? a.local[q] : make_ulonglong2(0, 0))) return;
     if (!active) return;
     const ulonglong2 *keys = peer_slots(a);
     unsigned long long b0 = KEY64_ABSENT, b1 = KEY64_ABSENT;
@@ -132,16 +132,18 @@ __global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerE
     }
 }
 
+__global__ void __launch_bounds__(PEER_THREADS) top2_exchange_merge_kernel(PeerExchangeArgs a) { top2_exchange_merge_body(a, blockIdx.x); }
+
 // Element-wise reductions over the ranks with the same push / signal / wait: the two exchanges of the row-sharded
 // matchGrid (database.py ShardedMap.match_grid).  The payload travels in 16-byte chunks (a.local /
 // a.out are arrays of n1 chunks):
 //   OP 0  min over ALL ranks of 2 x uint64 per chunk  -- the per-column best pairs (distance << 32 | global row)
 //   OP 1  min over the LOWER ranks (r < rank) of 8 x uint16 per chunk, 0xFFFF where there is none -- the running
 //         column minima that seed a shard's thresholds
-template <int OP> __global__ void __launch_bounds__(PEER_THREADS) peer_reduce_kernel(PeerExchangeArgs a) {
-    const int q = blockIdx.x * PEER_THREADS + threadIdx.x;
+template <int OP> __device__ __forceinline__ void peer_reduce_body(const PeerExchangeArgs &a, int bx) {
+    const int q = bx * PEER_THREADS + threadIdx.x;
     const bool active = q < a.n1;
-    if (!peer_push_wait(a, q, active, active ? a.local[q] : make_ulonglong2(0, 0))) return;
+    if (!peer_push_wait(a, bx, q, active, active ? a.local[q] : make_ulonglong2(0, 0))) return;
     if (!active) return;
     const ulonglong2 *slots = peer_slots(a);
     if (OP == 0) {
@@ -173,6 +175,8 @@ template <int OP> __global__ void __launch_bounds__(PEER_THREADS) peer_reduce_ke
     }
 }
 
+template <int OP> __global__ void __launch_bounds__(PEER_THREADS) peer_reduce_kernel(PeerExchangeArgs a) { peer_reduce_body<OP>(a, blockIdx.x); }
+
 // All-gather of the per-shard match vectors + sum of the per-shard counts (the last step of the row-sharded
 // match / matchGrid: every rank ends with the global matches_12 vector and the global count) as one kernel.
 // Every rank owns a second peer-mapped buffer:
@@ -202,11 +206,11 @@ __host__ __device__ inline size_t peer_gather_bytes(int world, long long n_rows_
     return size_t(2) * size_t(n_rows_cap) * 4 + size_t(2) * world * 4 + size_t(2) * world * 4 + 16;
 }
 
-__global__ void __launch_bounds__(256) peer_allgather_kernel(PeerGatherArgs a) {
+__device__ __forceinline__ void peer_allgather_body(const PeerGatherArgs &a, int bx, int nbx) {
     const int par = a.epoch & 1;
     const size_t rows_bytes = size_t(2) * size_t(a.n_rows_cap) * 4;
-    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long tid = static_cast<long long>(bx) * blockDim.x + threadIdx.x;
+    const long long nthreads = static_cast<long long>(nbx) * blockDim.x;
     // push
     for (int p = 0; p < a.world; ++p) {
         const int dst = (a.rank + p) % a.world;
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(PeerGatherArgs a) {
     __shared__ int s_last, s_fail;
     if (threadIdx.x == 0) {
         s_fail = 0;
-        s_last = (atom_add_acq_rel_gpu(done, 1u) == gridDim.x - 1) ? 1 : 0;
+        s_last = (atom_add_acq_rel_gpu(done, 1u) == static_cast<uint32_t>(nbx) - 1) ? 1 : 0;
     }
     __syncthreads();
     if (s_last) {
@@ -263,5 +267,23 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(PeerGatherArgs a) {
         *a.out_count = sum;
     }
 }
+__global__ void __launch_bounds__(256) peer_allgather_kernel(PeerGatherArgs a) { peer_allgather_body(a, blockIdx.x, gridDim.x); }
+
+// ---- all ranks of an exchange inside ONE cooperative kernel (blockIdx.y = rank) ---------------------------------
+// For boxes with fewer GPUs than ranks (tests): kernels that wait for one another must not be separate launches on one
+// GPU -- nothing guarantees that they run at the same time.  A cooperative launch makes every CTA co-resident, so the
+// CTAs of "rank" y can wait for the flags the CTAs of the other ranks raise.  The ranks' buffers are plain device
+// allocations on the same GPU; the code path is the one the real multi-GPU launches run.
+constexpr int PEER_EMU_MAX_RANKS = 4;
+struct PeerEmuExchange { PeerExchangeArgs a[PEER_EMU_MAX_RANKS]; };
+struct PeerEmuGather { PeerGatherArgs a[PEER_EMU_MAX_RANKS]; };
+// KIND 0: top-2 exchange + merge, 1: min over all ranks (u64), 2: prefix-min over the lower ranks (u16)
+template <int KIND> __global__ void __launch_bounds__(PEER_THREADS) peer_emu_exchange_kernel(PeerEmuExchange e) {
+    const PeerExchangeArgs &a = e.a[blockIdx.y];
+    if (KIND == 0) top2_exchange_merge_body(a, blockIdx.x);
+    else if (KIND == 1) peer_reduce_body<0>(a, blockIdx.x);
+    else peer_reduce_body<1>(a, blockIdx.x);
+}
+__global__ void __launch_bounds__(256) peer_emu_gather_kernel(PeerEmuGather e) { peer_allgather_body(e.a[blockIdx.y], blockIdx.x, gridDim.x); }
 
 } // namespace plm

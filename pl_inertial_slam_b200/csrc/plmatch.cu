@@ -81,6 +81,24 @@ struct plm_ctx {
     int knn_occ[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
     bool rows_attr_set = false;
+    // frame session: the calls recorded between plm_frame_begin and plm_frame_end
+    struct FrameCall {
+        int kind = 0; // 0 match / matchNNR, 1 matchGrid
+        int is_lines = 0, n1 = 0, n2 = 0, grid_rows = 0, grid_cols = 0, best_lr = 0;
+        const uint8_t *d1 = nullptr, *d2 = nullptr;
+        size_t step1 = 0, step2 = 0;
+        const int32_t *coords = nullptr, *cell_start = nullptr, *cell_items = nullptr;
+        const double *dirs2 = nullptr;
+        double line_sim_th = 0.0, ratio = 0.0;
+        float nnr = 0.f;
+        int32_t win[4] = {0, 0, 0, 0};
+        int32_t *m12 = nullptr;
+        int *n_matches = nullptr;
+    };
+    bool in_frame = false;
+    std::vector<FrameCall> frame_calls;
+    cudaStream_t frame_streams[2] = {nullptr, nullptr};
+    cudaEvent_t frame_events[3] = {nullptr, nullptr, nullptr};
     // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -119,6 +137,17 @@ struct plm_ctx {
         h_cap = cap;
         return PLM_OK;
     }
+};
+
+// How one host-buffer call is executed.  A stand-alone call runs every phase at once on the context's buffers; inside
+// a frame session (plm_frame_begin / plm_frame_end) the call is recorded and its phases run later, interleaved with the
+// other calls of the frame: SIZE (layout only), PACK (inputs into the shared pinned block), LAUNCH (H2D of this call's
+// inputs, kernels, D2H of its outputs -- all asynchronous on the current stream), UNPACK (after the one sync).
+enum ExecPhase { EXEC_ALL = 0, EXEC_SIZE = 1, EXEC_PACK = 2, EXEC_LAUNCH = 3, EXEC_UNPACK = 4 };
+struct Exec {
+    int phase = EXEC_ALL;
+    char *h_base = nullptr, *d_base = nullptr; // this call's sub-blocks (phases PACK .. UNPACK)
+    size_t h_bytes = 0, d_bytes = 0;            // reported by phase SIZE
 };
 
 struct plm_db {
@@ -447,6 +476,10 @@ PLM_API int plm_ctx_destroy(plm_ctx *ctx) {
         cudaStreamSynchronize(ctx->own_stream);
         cudaStreamDestroy(ctx->own_stream);
     }
+    for (int i = 0; i < 2; ++i)
+        if (ctx->frame_streams[i]) cudaStreamDestroy(ctx->frame_streams[i]);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->frame_events[i]) cudaEventDestroy(ctx->frame_events[i]);
     if (ctx->d_buf) cudaFree(ctx->d_buf);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
@@ -668,7 +701,7 @@ PLM_API int plm_knn2(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, cons
 // StVO::matchNNR / StVO::match share one implementation: direction 21 + mutual check are added
 // when best_lr is set.
 static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2, size_t step2,
-                      float nnr, int best_lr, int32_t *m12_inout, int *n_matches) {
+                      float nnr, int best_lr, int32_t *m12_inout, int *n_matches, Exec *ex = nullptr) {
     int st = check_desc(d1, n1, step1);
     if (st == PLM_OK) st = check_desc(d2, n2, step2);
     if (st != PLM_OK) return st;
@@ -683,6 +716,14 @@ static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, con
     if (n1 == 0) return PLM_OK;
     if (n2 == 0) return fail(PLM_E_TRAIN, "matchNNR: empty train set");
     if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+    if (ctx->in_frame && !ex) { // frame session: record, run at plm_frame_end
+        plm_ctx::FrameCall c;
+        c.kind = 0; c.d1 = d1; c.n1 = n1; c.step1 = step1; c.d2 = d2; c.n2 = n2; c.step2 = step2; c.nnr = nnr; c.best_lr = best_lr;
+        c.m12 = m12_inout; c.n_matches = n_matches;
+        ctx->frame_calls.push_back(c);
+        return PLM_OK;
+    }
+    const int phase = ex ? ex->phase : EXEC_ALL;
 
     Layout L;
     const size_t o_d1 = L.add(size_t(n1) * 32), o_d2 = L.add(size_t(n2) * 32);
@@ -696,23 +737,41 @@ static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, con
     size_t part_off[2] = {0, 0};
     build_knn_task(ctx, L, tp.t[0], plan[0], nullptr, n1, nullptr, n2, 0, part_off[0]);
     if (best_lr) build_knn_task(ctx, L, tp.t[1], plan[1], nullptr, n2, nullptr, n1, 0, part_off[1]);
-    if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
-    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    (void)staged;
+    if (phase == EXEC_SIZE) {
+        ex->h_bytes = in_bytes;
+        ex->d_bytes = L.total;
+        return PLM_OK;
+    }
+    if (phase == EXEC_ALL) {
+        if ((st = ctx->ensure_pinned(in_bytes)) != PLM_OK) return st;
+        if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    }
+    char *HB = ex && phase != EXEC_ALL ? ex->h_base : ctx->h_buf, *DB = ex && phase != EXEC_ALL ? ex->d_base : ctx->d_buf;
+    if (phase == EXEC_ALL || phase == EXEC_PACK) {
+        pack_rows(HB + o_d1, d1, n1, step1);
+        pack_rows(HB + o_d2, d2, n2, step2);
+        std::memcpy(HB + o_m12, m12_inout, size_t(n1) * 4);
+        std::memset(HB + o_m12 + size_t(n1) * 4, 0, 4);
+        if (phase == EXEC_PACK) return PLM_OK;
+    }
+    if (phase == EXEC_UNPACK) {
+        std::memcpy(m12_inout, HB + o_m12, size_t(n1) * 4);
+        int32_t cnt_u;
+        std::memcpy(&cnt_u, HB + o_m12 + size_t(n1) * 4, 4);
+        *n_matches = cnt_u;
+        return PLM_OK;
+    }
+    CU_TRY(cudaMemcpyAsync(DB, HB, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
 
-    pack_rows(ctx->h_buf + o_d1, d1, n1, step1);
-    pack_rows(ctx->h_buf + o_d2, d2, n2, step2);
-    std::memcpy(ctx->h_buf + o_m12, m12_inout, size_t(n1) * 4);
-    std::memset(ctx->h_buf + o_m12 + size_t(n1) * 4, 0, 4);
-    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-
-    const uint4 *dd1 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d1);
-    const uint4 *dd2 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d2);
-    int32_t *dm12 = reinterpret_cast<int32_t *>(ctx->d_buf + o_m12);
+    const uint4 *dd1 = reinterpret_cast<const uint4 *>(DB + o_d1);
+    const uint4 *dd2 = reinterpret_cast<const uint4 *>(DB + o_d2);
+    int32_t *dm12 = reinterpret_cast<int32_t *>(DB + o_m12);
     int32_t *dcount = dm12 + n1;
-    int32_t *dm21 = reinterpret_cast<int32_t *>(ctx->d_buf + o_m21);
+    int32_t *dm21 = reinterpret_cast<int32_t *>(DB + o_m21);
     tp.t[0].q = dd1;
     tp.t[0].db = dd2;
-    tp.t[0].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off[0]);
+    tp.t[0].part = reinterpret_cast<ulonglong2 *>(DB + part_off[0]);
     tp.t[0].m = dm12;
     tp.t[0].count = dcount;
     int n_tasks = 1;
@@ -720,7 +779,7 @@ static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, con
         CU_TRY(cudaMemsetAsync(dm21, 0xFF, size_t(n2) * 4, ctx->stream));
         tp.t[1].q = dd2;
         tp.t[1].db = dd1;
-        tp.t[1].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off[1]);
+        tp.t[1].part = reinterpret_cast<ulonglong2 *>(DB + part_off[1]);
         tp.t[1].m = dm21;
         tp.t[1].count = nullptr; // the reference ignores the 21 count (matching.cpp:72,77)
         n_tasks = 2;
@@ -734,11 +793,12 @@ static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, con
         ctx->launches++;
         CU_TRY(cudaGetLastError());
     }
-    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_m12, ctx->d_buf + o_m12, size_t(n1) * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(HB + o_m12, DB + o_m12, size_t(n1) * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (phase == EXEC_LAUNCH) return PLM_OK;
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(m12_inout, ctx->h_buf + o_m12, size_t(n1) * 4);
+    std::memcpy(m12_inout, HB + o_m12, size_t(n1) * 4);
     int32_t cnt;
-    std::memcpy(&cnt, ctx->h_buf + o_m12 + size_t(n1) * 4, 4);
+    std::memcpy(&cnt, HB + o_m12 + size_t(n1) * 4, 4);
     *n_matches = cnt;
     return PLM_OK;
 }
@@ -933,12 +993,12 @@ int launch_map_grid(plm_ctx *ctx, int pass, const plm::GridJob &job, const plm::
 
 // Map-sized job: pass 0 (per-CTA minima) -> scan -> pass 1 (match) -> mutual check.
 // scratch: cta_min [n_cta][n2] u16, m21key [n2] u64, m21 [n2] i32 -- offsets into ctx->d_buf.
-int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams gp, size_t off_cta_min, size_t off_m21key,
+int launch_grid_chunked(plm_ctx *ctx, char *DB, const plm::GridJob &job, plm::GridParams gp, size_t off_cta_min, size_t off_m21key,
                         size_t off_m21, int warps, int n_cta, size_t smem) {
     int st;
-    gp.cta_min = reinterpret_cast<uint16_t *>(ctx->d_buf + off_cta_min);
-    gp.m21key = reinterpret_cast<unsigned long long *>(ctx->d_buf + off_m21key);
-    int32_t *m21 = reinterpret_cast<int32_t *>(ctx->d_buf + off_m21);
+    gp.cta_min = reinterpret_cast<uint16_t *>(DB + off_cta_min);
+    gp.m21key = reinterpret_cast<unsigned long long *>(DB + off_m21key);
+    int32_t *m21 = reinterpret_cast<int32_t *>(DB + off_m21);
     if (gp.best_lr) {
         CU_TRY(cudaMemsetAsync(gp.m21key, 0xFF, size_t(job.n2) * 8, ctx->stream));
         if ((st = launch_map_grid(ctx, 0, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
@@ -960,7 +1020,7 @@ int launch_grid_chunked(plm_ctx *ctx, const plm::GridJob &job, plm::GridParams g
 int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uint8_t *d1, int n1, size_t step1,
                     const int32_t *cell_start, const int32_t *cell_items, int grid_rows, int grid_cols, const uint8_t *d2,
                     int n2, size_t step2, const double *dirs2, double line_sim_th, const int32_t win[4], double ratio,
-                    int best_lr, int32_t *m12_inout, int *n_matches) {
+                    int best_lr, int32_t *m12_inout, int *n_matches, Exec *ex = nullptr) {
     int st = check_desc(d1, n1, step1);
     if (st == PLM_OK) st = check_desc(d2, n2, step2);
     if (st != PLM_OK) return st;
@@ -974,6 +1034,16 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     if (n2 > GRID_N2_MAX) return fail(PLM_E_UNSUPPORTED, "matchGrid supports at most 32768 train features");
     if (n1 == 0) return PLM_OK;
     if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
+    if (ctx->in_frame && !ex) { // frame session: record, run at plm_frame_end
+        plm_ctx::FrameCall c;
+        c.kind = 1; c.is_lines = is_lines; c.coords = coords; c.d1 = d1; c.n1 = n1; c.step1 = step1; c.cell_start = cell_start;
+        c.cell_items = cell_items; c.grid_rows = grid_rows; c.grid_cols = grid_cols; c.d2 = d2; c.n2 = n2; c.step2 = step2; c.dirs2 = dirs2;
+        c.line_sim_th = line_sim_th; c.ratio = ratio; c.best_lr = best_lr; c.m12 = m12_inout; c.n_matches = n_matches;
+        for (int i = 0; i < 4; ++i) c.win[i] = win[i];
+        ctx->frame_calls.push_back(c);
+        return PLM_OK;
+    }
+    const int phase = ex ? ex->phase : EXEC_ALL;
 
     const int n_cells = grid_rows * grid_cols;
     const int cpq = is_lines ? 4 : 2;
@@ -999,36 +1069,53 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
         o_m21key = L.add(size_t(std::max(n2, 1)) * 8);
         o_m21 = L.add(size_t(std::max(n2, 1)) * 4);
     }
-    if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
-    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
-
-    pack_rows(ctx->h_buf + o_d1, d1, n1, step1);
-    pack_rows(ctx->h_buf + o_d2, d2, n2, step2);
-    std::memcpy(ctx->h_buf + o_xy, coords, size_t(n1) * cpq * 4);
-    std::memcpy(ctx->h_buf + o_cs, cell_start, size_t(n_cells + 1) * 4);
-    if (n_items > 0) std::memcpy(ctx->h_buf + o_ci, cell_items, size_t(n_items) * 4);
-    if (is_lines && n2 > 0) std::memcpy(ctx->h_buf + o_dir, dirs2, size_t(n2) * 16);
-    std::memcpy(ctx->h_buf + o_m12, m12_inout, size_t(n1) * 4);
-    std::memset(ctx->h_buf + o_m12 + size_t(n1) * 4, 0, 4);
+    if (phase == EXEC_SIZE) {
+        ex->h_bytes = staged;
+        ex->d_bytes = L.total;
+        return PLM_OK;
+    }
+    if (phase == EXEC_ALL) {
+        if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
+        if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    }
+    char *HB = ex && phase != EXEC_ALL ? ex->h_base : ctx->h_buf, *DB = ex && phase != EXEC_ALL ? ex->d_base : ctx->d_buf;
+    if (phase == EXEC_UNPACK) {
+        std::memcpy(m12_inout, HB + o_m12, size_t(n1) * 4);
+        int32_t cnt_u;
+        std::memcpy(&cnt_u, HB + o_m12 + size_t(n1) * 4, 4);
+        *n_matches = cnt_u;
+        return PLM_OK;
+    }
 
     plm::GridJob job;
     std::memset(&job, 0, sizeof(job));
-    job.coords = reinterpret_cast<const int32_t *>(ctx->d_buf + o_xy);
-    job.d1 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d1);
-    job.cell_start = reinterpret_cast<const int32_t *>(ctx->d_buf + o_cs);
-    job.cell_items = reinterpret_cast<const int32_t *>(ctx->d_buf + o_ci);
-    job.d2 = reinterpret_cast<const uint4 *>(ctx->d_buf + o_d2);
-    job.dirs2 = reinterpret_cast<const double *>(ctx->d_buf + o_dir);
-    job.m12 = reinterpret_cast<int32_t *>(ctx->d_buf + o_m12);
+    job.coords = reinterpret_cast<const int32_t *>(DB + o_xy);
+    job.d1 = reinterpret_cast<const uint4 *>(DB + o_d1);
+    job.cell_start = reinterpret_cast<const int32_t *>(DB + o_cs);
+    job.cell_items = reinterpret_cast<const int32_t *>(DB + o_ci);
+    job.d2 = reinterpret_cast<const uint4 *>(DB + o_d2);
+    job.dirs2 = reinterpret_cast<const double *>(DB + o_dir);
+    job.m12 = reinterpret_cast<int32_t *>(DB + o_m12);
     job.count = job.m12 + n1;
     job.n1 = n1;
     job.n2 = n2;
     job.is_lines = is_lines;
     for (int i = 0; i < 4; ++i) job.win[i] = win[i];
     job.i1_base = 0;
-    std::memcpy(ctx->h_buf + o_job, &job, sizeof(job));
+    if (phase == EXEC_ALL || phase == EXEC_PACK) {
+        pack_rows(HB + o_d1, d1, n1, step1);
+        pack_rows(HB + o_d2, d2, n2, step2);
+        std::memcpy(HB + o_xy, coords, size_t(n1) * cpq * 4);
+        std::memcpy(HB + o_cs, cell_start, size_t(n_cells + 1) * 4);
+        if (n_items > 0) std::memcpy(HB + o_ci, cell_items, size_t(n_items) * 4);
+        if (is_lines && n2 > 0) std::memcpy(HB + o_dir, dirs2, size_t(n2) * 16);
+        std::memcpy(HB + o_m12, m12_inout, size_t(n1) * 4);
+        std::memset(HB + o_m12 + size_t(n1) * 4, 0, 4);
+        std::memcpy(HB + o_job, &job, sizeof(job));
+        if (phase == EXEC_PACK) return PLM_OK;
+    }
 
-    CU_TRY(cudaMemcpyAsync(ctx->d_buf, ctx->h_buf, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(DB, HB, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
 
     gp.grid_rows = grid_rows;
     gp.grid_cols = grid_cols;
@@ -1036,19 +1123,20 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     gp.ratio = ratio;
     gp.line_sim_th = line_sim_th;
     if (fused && n1 >= 64 && g_grid_cluster) {
-        st = launch_grid_cluster(ctx, reinterpret_cast<const plm::GridJob *>(ctx->d_buf + o_job), 1, gp, n1, std::max(n2, 1),
+        st = launch_grid_cluster(ctx, reinterpret_cast<const plm::GridJob *>(DB + o_job), 1, gp, n1, std::max(n2, 1),
                                  std::max(n_items, 1), is_lines != 0);
     } else if (fused) {
-        st = launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(ctx->d_buf + o_job), 1, gp, n1, std::max(n2, 1), std::max(n_items, 1), is_lines != 0);
+        st = launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(DB + o_job), 1, gp, n1, std::max(n2, 1), std::max(n_items, 1), is_lines != 0);
     } else {
-        st = launch_grid_chunked(ctx, job, gp, o_cta_min, o_m21key, o_m21, warps, n_cta, map_smem);
+        st = launch_grid_chunked(ctx, DB, job, gp, o_cta_min, o_m21key, o_m21, warps, n_cta, map_smem);
     }
     if (st != PLM_OK) return st;
-    CU_TRY(cudaMemcpyAsync(ctx->h_buf + o_m12, ctx->d_buf + o_m12, size_t(n1) * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(HB + o_m12, DB + o_m12, size_t(n1) * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (phase == EXEC_LAUNCH) return PLM_OK;
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(m12_inout, ctx->h_buf + o_m12, size_t(n1) * 4);
+    std::memcpy(m12_inout, HB + o_m12, size_t(n1) * 4);
     int32_t cnt;
-    std::memcpy(&cnt, ctx->h_buf + o_m12 + size_t(n1) * 4, 4);
+    std::memcpy(&cnt, HB + o_m12 + size_t(n1) * 4, 4);
     *n_matches = cnt;
     return PLM_OK;
 }
@@ -1518,6 +1606,62 @@ PLM_API int plm_peer_free(plm_ctx *ctx, void *buf_dev) {
     return PLM_OK;
 }
 
+// Single-GPU emulation of the peer kernels (see csrc/plm_peer.cuh): calls are recorded per thread, then run as ONE
+// cooperative launch with blockIdx.y = rank.
+namespace {
+struct PeerEmu {
+    int world = 0;   // > 0 while recording
+    int kind = -1;   // 0 exchange, 1 min_u64, 2 prefix_min_u16, 3 gather
+    int grid_x = 0;
+    int n = 0;
+    plm::PeerEmuExchange ex;
+    plm::PeerEmuGather ga;
+};
+thread_local PeerEmu g_emu;
+
+int emu_record_exchange(int kind, const plm::PeerExchangeArgs &a, int grid) {
+    if (g_emu.n >= g_emu.world || g_emu.n >= plm::PEER_EMU_MAX_RANKS) return fail(PLM_E_INVALID, "peer emulation: more calls than ranks");
+    if (g_emu.n > 0 && (g_emu.kind != kind || g_emu.grid_x != grid)) return fail(PLM_E_INVALID, "peer emulation: the recorded calls differ in kind or size");
+    g_emu.kind = kind;
+    g_emu.grid_x = grid;
+    g_emu.ex.a[g_emu.n++] = a;
+    return PLM_OK;
+}
+} // namespace
+
+PLM_API int plm_peer_emulate_begin(int world) {
+    if (world < 1 || world > plm::PEER_EMU_MAX_RANKS) return fail(PLM_E_INVALID, "peer emulation supports 1 .. 4 ranks");
+    g_emu = PeerEmu();
+    g_emu.world = world;
+    return PLM_OK;
+}
+
+PLM_API int plm_peer_emulate_run(plm_ctx *ctx) {
+    PeerEmu e = g_emu;
+    g_emu = PeerEmu();
+    if (e.world == 0) return fail(PLM_E_INVALID, "peer emulation: no recording in progress");
+    if (e.n == 0) return PLM_OK;
+    if (e.n != e.world) return fail(PLM_E_INVALID, "peer emulation: every rank must have recorded its call");
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    const dim3 grid(e.grid_x, e.world, 1);
+    void *params[1];
+    cudaError_t err;
+    if (e.kind == 3) {
+        params[0] = &e.ga;
+        err = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(plm::peer_emu_gather_kernel), grid, dim3(256), params, 0, ctx->stream);
+    } else {
+        params[0] = &e.ex;
+        const void *fn = e.kind == 0 ? reinterpret_cast<const void *>(plm::peer_emu_exchange_kernel<0>)
+                         : e.kind == 1 ? reinterpret_cast<const void *>(plm::peer_emu_exchange_kernel<1>)
+                                       : reinterpret_cast<const void *>(plm::peer_emu_exchange_kernel<2>);
+        err = cudaLaunchCooperativeKernel(fn, grid, dim3(plm::PEER_THREADS), params, 0, ctx->stream);
+    }
+    if (err != cudaSuccess) return fail(PLM_E_CUDA, std::string("peer emulation (cooperative launch): ") + cudaGetErrorString(err));
+    ctx->launches++;
+    return PLM_OK;
+}
+
 PLM_API int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, int world, int q_cap, uint32_t epoch,
                                   const uint64_t *local_top2_dev, int n1, uint64_t *top2_out_dev, float nnr,
                                   int32_t *m12_dev_inout, int32_t *count_dev, int32_t *error_dev) {
@@ -1544,6 +1688,7 @@ PLM_API int plm_dev_top2_exchange(plm_ctx *ctx, void *const *peers, int rank, in
     a.count = count_dev;
     a.error = error_dev;
     a.spin_limit = g_peer_spin_ticks;
+    if (g_emu.world > 0) return emu_record_exchange(0, a, (n1 + plm::PEER_THREADS - 1) / plm::PEER_THREADS);
     plm::top2_exchange_merge_kernel<<<(n1 + plm::PEER_THREADS - 1) / plm::PEER_THREADS, plm::PEER_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
@@ -1581,6 +1726,15 @@ PLM_API int plm_dev_peer_allgather_i32(plm_ctx *ctx, void *const *peers, int ran
     // once so that no block waits behind spinning ones: at most one CTA per SM
     const int64_t work = std::max<int64_t>(std::max<int64_t>(n_rows, n_local), 1);
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((work + 1023) / 1024, ctx->sm_count)));
+    if (g_emu.world > 0) {
+        const int eg = std::max(1, std::min(grid, ctx->sm_count / std::max(1, g_emu.world))); // all ranks' CTAs must be co-resident
+        if (g_emu.n >= g_emu.world || g_emu.n >= plm::PEER_EMU_MAX_RANKS) return fail(PLM_E_INVALID, "peer emulation: more calls than ranks");
+        if (g_emu.n > 0 && (g_emu.kind != 3 || g_emu.grid_x != eg)) return fail(PLM_E_INVALID, "peer emulation: the recorded calls differ in kind or size");
+        g_emu.kind = 3;
+        g_emu.grid_x = eg;
+        g_emu.ga.a[g_emu.n++] = a;
+        return PLM_OK;
+    }
     plm::peer_allgather_kernel<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
@@ -1612,6 +1766,7 @@ PLM_API int plm_dev_peer_reduce(plm_ctx *ctx, void *const *peers, int rank, int 
     a.error = error_dev;
     a.spin_limit = g_peer_spin_ticks;
     const int grid = (n_chunks + plm::PEER_THREADS - 1) / plm::PEER_THREADS;
+    if (g_emu.world > 0) return emu_record_exchange(op == PLM_PEER_MIN_U64 ? 1 : 2, a, grid);
     if (op == PLM_PEER_MIN_U64) plm::peer_reduce_kernel<0><<<grid, plm::PEER_THREADS, 0, ctx->stream>>>(a);
     else plm::peer_reduce_kernel<1><<<grid, plm::PEER_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
@@ -2529,6 +2684,88 @@ PLM_API int plm_batch_fetch(plm_batch *b, int32_t *m12_arena, int32_t *counts) {
 }
 
 // ---------------------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------------------
+// Frame session: the host-buffer calls of one frame (stereo matchGrid for points and lines, temporal match for
+// points and lines, ...) executed as ONE round trip.
+namespace {
+
+int frame_run(plm_ctx *ctx, const plm_ctx::FrameCall &c, Exec *ex) {
+    if (c.kind == 0) return match_impl(ctx, c.d1, c.n1, c.step1, c.d2, c.n2, c.step2, c.nnr, c.best_lr, c.m12, c.n_matches, ex);
+    return match_grid_impl(ctx, c.is_lines, c.coords, c.d1, c.n1, c.step1, c.cell_start, c.cell_items, c.grid_rows, c.grid_cols, c.d2, c.n2,
+                           c.step2, c.dirs2, c.line_sim_th, c.win, c.ratio, c.best_lr, c.m12, c.n_matches, ex);
+}
+
+} // namespace
+
+PLM_API int plm_frame_begin(plm_ctx *ctx) {
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    if (ctx->in_frame) return fail(PLM_E_INVALID, "plm_frame_begin: a frame session is already open on this context");
+    ctx->in_frame = true;
+    ctx->frame_calls.clear();
+    return PLM_OK;
+}
+
+PLM_API int plm_frame_end(plm_ctx *ctx) {
+    int st = resolve_ctx(ctx);
+    if (st != PLM_OK) return st;
+    if (!ctx->in_frame) return fail(PLM_E_INVALID, "plm_frame_end without plm_frame_begin");
+    ctx->in_frame = false;
+    std::vector<plm_ctx::FrameCall> calls;
+    calls.swap(ctx->frame_calls);
+    const int n = static_cast<int>(calls.size());
+    if (n == 0) return PLM_OK;
+    std::vector<Exec> ex(n);
+    size_t h_total = 0, d_total = 0;
+    std::vector<size_t> h_off(n), d_off(n);
+    for (int k = 0; k < n; ++k) {
+        ex[k].phase = EXEC_SIZE;
+        if ((st = frame_run(ctx, calls[k], &ex[k])) != PLM_OK) return st;
+        h_off[k] = h_total;
+        d_off[k] = d_total;
+        h_total += align_up(ex[k].h_bytes);
+        d_total += align_up(ex[k].d_bytes);
+    }
+    if ((st = ctx->ensure_pinned(h_total)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(d_total)) != PLM_OK) return st;
+    if (!ctx->frame_streams[0]) {
+        for (int i = 0; i < 2; ++i) CU_TRY(cudaStreamCreateWithFlags(&ctx->frame_streams[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) CU_TRY(cudaEventCreateWithFlags(&ctx->frame_events[i], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < n; ++k) {
+        ex[k].h_base = ctx->h_buf + h_off[k];
+        ex[k].d_base = ctx->d_buf + d_off[k];
+        ex[k].phase = EXEC_PACK;
+        if ((st = frame_run(ctx, calls[k], &ex[k])) != PLM_OK) return st;
+    }
+    // the calls are independent: their copies and kernels go round-robin over three streams and run concurrently
+    cudaStream_t main_stream = ctx->stream;
+    cudaStream_t lanes[3] = {main_stream, ctx->frame_streams[0], ctx->frame_streams[1]};
+    const int n_lanes = std::min(n, 3);
+    if (n_lanes > 1) {
+        CU_TRY(cudaEventRecord(ctx->frame_events[0], main_stream)); // earlier work of this context comes first
+        for (int i = 1; i < n_lanes; ++i) CU_TRY(cudaStreamWaitEvent(lanes[i], ctx->frame_events[0], 0));
+    }
+    int rc = PLM_OK;
+    for (int k = 0; k < n && rc == PLM_OK; ++k) {
+        ctx->stream = lanes[k % n_lanes];
+        ex[k].phase = EXEC_LAUNCH;
+        rc = frame_run(ctx, calls[k], &ex[k]);
+    }
+    ctx->stream = main_stream;
+    for (int i = 1; i < n_lanes; ++i) {
+        cudaEventRecord(ctx->frame_events[i], lanes[i]);
+        cudaStreamWaitEvent(main_stream, ctx->frame_events[i], 0);
+    }
+    CU_TRY(cudaStreamSynchronize(main_stream));
+    if (rc != PLM_OK) return rc;
+    for (int k = 0; k < n; ++k) {
+        ex[k].phase = EXEC_UNPACK;
+        if ((st = frame_run(ctx, calls[k], &ex[k])) != PLM_OK) return st;
+    }
+    return PLM_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Local-map selection and reprojection gates of matchMap2KF* (csrc/plm_reproj.cuh)

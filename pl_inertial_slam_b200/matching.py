@@ -119,6 +119,66 @@ def _m12_out(matches_12: Optional[MatchVec], buf: np.ndarray) -> None:
         matches_12[:] = buf.tolist()
 
 
+class Pending:
+    """Result of a matcher call recorded inside a FrameSession: `.value` (the reference's int return) and the match
+    vector are defined once the session has ended."""
+
+    def __init__(self):
+        self.value = None
+
+    def __int__(self):
+        if self.value is None:
+            raise RuntimeError("the frame session has not ended yet")
+        return int(self.value)
+
+
+_sessions = {}
+
+
+def _session_key(ctx: Optional[Context]):
+    import threading
+    return ("ctx", id(ctx)) if ctx is not None else ("tls", threading.get_ident())
+
+
+class FrameSession:
+    """plm_frame_begin / plm_frame_end: the matcher calls of one frame (stereo matchGrid for points and lines, temporal
+    match for points and lines) recorded and executed as ONE host <-> device round trip.
+
+        with M.FrameSession(ctx) as fs:
+            a = M.matchGrid(xy, d1, grid, d2, w, m_stereo, ctx=ctx)    # -> Pending
+            b = M.match(prev, curr, 0.9, m_temporal, ctx=ctx)           # -> Pending
+        int(a), int(b), m_stereo, m_temporal                           # defined after the `with` block
+    """
+
+    def __init__(self, ctx: Optional[Context] = None):
+        self.ctx = ctx
+        self._fin = []
+
+    def __enter__(self):
+        L.check(L.load().plm_frame_begin(_h(self.ctx)), "plm_frame_begin")
+        _sessions[_session_key(self.ctx)] = self
+        return self
+
+    def _defer(self, n, matches_12, buf, keep):
+        p = Pending()
+
+        def fin(keep=keep):
+            _m12_out(matches_12, buf)
+            p.value = n.value
+        self._fin.append(fin)
+        return p
+
+    def __exit__(self, exc_type, exc, tb):
+        _sessions.pop(_session_key(self.ctx), None)
+        st = L.load().plm_frame_end(_h(self.ctx))
+        if exc_type is None:
+            L.check(st, "plm_frame_end")
+            for f in self._fin:
+                f()
+        self._fin = []
+        return False
+
+
 def distance(a: np.ndarray, b: np.ndarray, ctx: Optional[Context] = None) -> int:
     a = np.ascontiguousarray(a, np.uint8).reshape(1, 32)
     b = np.ascontiguousarray(b, np.uint8).reshape(1, 32)
@@ -160,6 +220,9 @@ def matchNNR(desc1: np.ndarray, desc2: np.ndarray, nnr: float, matches_12: Optio
         # knnMatch yields < 2 neighbours per row (or no rows at all): matching.cpp:50-51 / :54
         raise RuntimeError("[matchNNR] Different size for matches and descriptors!")
     L.check(st, "matchNNR")
+    sess = _sessions.get(_session_key(ctx))
+    if sess is not None:
+        return sess._defer(n, matches_12, buf, (d1, d2))
     _m12_out(matches_12, buf)
     return n.value
 
@@ -175,6 +238,9 @@ def match(desc1: np.ndarray, desc2: np.ndarray, nnr: float, matches_12: Optional
     if st == L.PLM_E_TRAIN:
         raise RuntimeError("[matchNNR] Different size for matches and descriptors!")
     L.check(st, "match")
+    sess = _sessions.get(_session_key(ctx))
+    if sess is not None:
+        return sess._defer(n, matches_12, buf, (d1, d2))
     _m12_out(matches_12, buf)
     return n.value
 
@@ -235,6 +301,9 @@ def matchGrid(features1, desc1: np.ndarray, grid, desc2: np.ndarray, *args, ctx:
     if st == L.PLM_E_GRID:
         raise RuntimeError("[GridStructure] invalid dimension")
     L.check(st, "matchGrid")
+    sess = _sessions.get(_session_key(ctx))
+    if sess is not None:
+        return sess._defer(n, matches_12, buf, (d1, d2, coords, cs, ci, win, directions2 if not is_lines else dirs))
     _m12_out(matches_12, buf)
     return n.value
 

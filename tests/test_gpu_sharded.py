@@ -113,24 +113,36 @@ def test_nccl_two_ranks():
 
 @pytest.mark.parametrize("world", [2, 4])
 def test_peer_exchange_kernel_one_gpu(plm_lib, world):
-    """top2_exchange_merge_kernel with `world` ranks emulated on ONE GPU: one context (stream) and one exchange
-    buffer per rank, plain device pointers instead of CUDA IPC mappings.  The kernels of the ranks run
-    concurrently and wait for each other's flags exactly as they do across GPUs."""
+    """The peer-memory kernels (top-2 exchange + merge, the two element-wise reductions, the all-gather) with `world`
+    ranks emulated on ONE GPU.  Kernels that wait for each other must not be separate launches on one GPU, so the
+    ranks' calls are recorded (plm_peer_emulate_begin) and executed as ONE cooperative launch with blockIdx.y = rank
+    (plm_peer_emulate_run): every CTA that waits is co-resident with the CTAs it waits for.  Buffers are plain
+    device allocations instead of peer mappings; the device code is the one the multi-GPU launches run."""
     import ctypes as C
     from pl_inertial_slam_b200 import _lib as L
     from pl_inertial_slam_b200.database import DeviceOps, shard_bounds
     rng = np.random.default_rng(77 + world)
     db = synth.tie_stress_desc(rng, 9001)
     q_cap = 1500
-    ranks = [DeviceOps(0) for _ in range(world)]
+    ops = DeviceOps(0)
+    ctx = ops.ctx.handle
+    ops._bind_stream()
     bufs = (C.c_void_p * world)()
-    for r, o in enumerate(ranks):
+    for r in range(world):
         p, h = C.c_void_p(), (C.c_uint8 * 64)()
-        L.check(plm_lib.plm_peer_alloc(o.ctx.handle, world, q_cap, C.byref(p), h), "plm_peer_alloc")
+        L.check(plm_lib.plm_peer_alloc(ctx, world, q_cap, C.byref(p), h), "plm_peer_alloc")
         bufs[r] = p
     shards = [torch.from_numpy(db[slice(*shard_bounds(len(db), world, r))].copy()).cuda() for r in range(world)]
     err = torch.zeros(world, dtype=torch.int32, device="cuda")
-    streams = [torch.cuda.Stream() for _ in range(world)]
+
+    def run_all(record):
+        L.check(plm_lib.plm_peer_emulate_begin(world), "plm_peer_emulate_begin")
+        for r in range(world):
+            record(r)
+        L.check(plm_lib.plm_peer_emulate_run(ctx), "plm_peer_emulate_run")
+        torch.cuda.synchronize()
+        assert not err.any().item(), "a rank timed out"
+
     epoch = 0
     for n1 in (1, 128, 129, 1500, 700, 33, 1024):            # several epochs: both parities, ragged last block
         q = synth.tie_stress_desc(rng, n1)
@@ -138,26 +150,14 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
         want = port.knn2_packed(q, db)
         n_o, m_o = port.match_nnr(q, db, 0.9)
         epoch += 1
-        # everything that allocates or may synchronise the device first (allocations between the launches would
-        # serialise the ranks' kernels on this single GPU; across processes every rank has its own context) ...
-        locals_, outs, m12s, cnts = [], [], [], []
-        for r, o in enumerate(ranks):
-            lo, _ = shard_bounds(len(db), world, r)
-            locals_.append(o.knn2(qd, shards[r], idx_base=lo))
-            outs.append(torch.empty((n1, 2), dtype=torch.int64, device="cuda"))
-            m12s.append(torch.full((n1,), -1, dtype=torch.int32, device="cuda"))
-            cnts.append(torch.zeros(1, dtype=torch.int32, device="cuda"))
-        torch.cuda.synchronize()
-        # ... then only the exchange kernels, one stream per rank, back to back
-        for r, o in enumerate(ranks):
-            with torch.cuda.stream(streams[r]):
-                o._bind_stream()
-                L.check(plm_lib.plm_dev_top2_exchange(o.ctx.handle, bufs, r, world, q_cap, epoch, C.c_void_p(locals_[r].data_ptr()),
-                                                      n1, C.c_void_p(outs[r].data_ptr()), C.c_float(0.9),
-                                                      C.c_void_p(m12s[r].data_ptr()), C.c_void_p(cnts[r].data_ptr()),
-                                                      C.c_void_p(err[r:].data_ptr())), "plm_dev_top2_exchange")
-        torch.cuda.synchronize()
-        assert not err.any().item(), "a rank timed out"
+        locals_ = [ops.knn2(qd, shards[r], idx_base=shard_bounds(len(db), world, r)[0]) for r in range(world)]
+        outs = [torch.empty((n1, 2), dtype=torch.int64, device="cuda") for _ in range(world)]
+        m12s = [torch.full((n1,), -1, dtype=torch.int32, device="cuda") for _ in range(world)]
+        cnts = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+        run_all(lambda r: L.check(plm_lib.plm_dev_top2_exchange(ctx, bufs, r, world, q_cap, epoch, C.c_void_p(locals_[r].data_ptr()), n1,
+                                                                C.c_void_p(outs[r].data_ptr()), C.c_float(0.9), C.c_void_p(m12s[r].data_ptr()),
+                                                                C.c_void_p(cnts[r].data_ptr()), C.c_void_p(err[r:].data_ptr())),
+                                  "plm_dev_top2_exchange"))
         for r in range(world):
             assert (outs[r].cpu().numpy().view(np.uint64) == want).all(), (n1, r)
             assert int(cnts[r].item()) == n_o and (m12s[r].cpu().numpy() == m_o).all(), (n1, r)
@@ -174,15 +174,9 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
             src = [torch.from_numpy(padded[r].view(np.int16 if op == 1 else np.int64).copy()).cuda() for r in range(world)]
             outs = [torch.empty_like(x) for x in src]
             epoch += 1
-            torch.cuda.synchronize()
-            for r, o in enumerate(ranks):
-                with torch.cuda.stream(streams[r]):
-                    o._bind_stream()
-                    L.check(plm_lib.plm_dev_peer_reduce(o.ctx.handle, bufs, r, world, q_cap, epoch, op, C.c_void_p(src[r].data_ptr()),
-                                                        npad // pad_to, C.c_void_p(outs[r].data_ptr()),
-                                                        C.c_void_p(err[r:].data_ptr())), "plm_dev_peer_reduce")
-            torch.cuda.synchronize()
-            assert not err.any().item(), "a rank timed out"
+            run_all(lambda r: L.check(plm_lib.plm_dev_peer_reduce(ctx, bufs, r, world, q_cap, epoch, op, C.c_void_p(src[r].data_ptr()),
+                                                                  npad // pad_to, C.c_void_p(outs[r].data_ptr()), C.c_void_p(err[r:].data_ptr())),
+                                      "plm_dev_peer_reduce"))
             for r in range(world):
                 got = outs[r].cpu().numpy().view(host.dtype)[:n]
                 if op == 0:
@@ -191,15 +185,14 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
                     want = host[:r].min(axis=0) if r > 0 else np.full(n, 0xFFFF, np.uint16)
                 assert np.array_equal(got, want), (op, n, r)
     # all-gather of per-rank int32 shards + sum of per-rank counts through a second set of buffers
-    n_cap = 5000
+    n_cap = 50_000
     gbufs = (C.c_void_p * world)()
-    for r, o in enumerate(ranks):
+    for r in range(world):
         p, h = C.c_void_p(), (C.c_uint8 * 64)()
-        L.check(plm_lib.plm_peer_alloc_bytes(o.ctx.handle, plm_lib.plm_peer_gather_bytes(world, n_cap), C.byref(p), h),
-                "plm_peer_alloc_bytes")
+        L.check(plm_lib.plm_peer_alloc_bytes(ctx, plm_lib.plm_peer_gather_bytes(world, n_cap), C.byref(p), h), "plm_peer_alloc_bytes")
         gbufs[r] = p
     g_epoch = 0
-    for n_rows in (5000, 1, 4097, 37, 5000):
+    for n_rows in (5000, 1, 4097, 37, 50_000, 5000):
         full = rng.integers(-1, 1000, n_rows).astype(np.int32)
         counts = rng.integers(-50, 500, world).astype(np.int32)
         spans = [shard_bounds(n_rows, world, r) for r in range(world)]
@@ -208,23 +201,16 @@ def test_peer_exchange_kernel_one_gpu(plm_lib, world):
         outs = [torch.full((n_rows,), -7, dtype=torch.int32, device="cuda") for _ in range(world)]
         tot = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
         g_epoch += 1
-        torch.cuda.synchronize()
-        for r, o in enumerate(ranks):
-            with torch.cuda.stream(streams[r]):
-                o._bind_stream()
-                L.check(plm_lib.plm_dev_peer_allgather_i32(o.ctx.handle, gbufs, r, world, n_cap, g_epoch, C.c_void_p(loc[r].data_ptr()),
-                                                           spans[r][0], spans[r][1] - spans[r][0], n_rows,
-                                                           C.c_void_p(cnt[r].data_ptr()), C.c_void_p(outs[r].data_ptr()),
-                                                           C.c_void_p(tot[r].data_ptr()), C.c_void_p(err[r:].data_ptr())),
-                        "plm_dev_peer_allgather_i32")
-        torch.cuda.synchronize()
-        assert not err.any().item(), "a rank timed out"
+        run_all(lambda r: L.check(plm_lib.plm_dev_peer_allgather_i32(ctx, gbufs, r, world, n_cap, g_epoch, C.c_void_p(loc[r].data_ptr()),
+                                                                     spans[r][0], spans[r][1] - spans[r][0], n_rows, C.c_void_p(cnt[r].data_ptr()),
+                                                                     C.c_void_p(outs[r].data_ptr()), C.c_void_p(tot[r].data_ptr()),
+                                                                     C.c_void_p(err[r:].data_ptr())), "plm_dev_peer_allgather_i32"))
         for r in range(world):
             assert np.array_equal(outs[r].cpu().numpy(), full), (n_rows, r)
             assert int(tot[r].item()) == int(counts.sum()), (n_rows, r)
-    for r, o in enumerate(ranks):
-        plm_lib.plm_peer_free(o.ctx.handle, gbufs[r])
-        plm_lib.plm_peer_free(o.ctx.handle, bufs[r])
+    for r in range(world):
+        plm_lib.plm_peer_free(ctx, gbufs[r])
+        plm_lib.plm_peer_free(ctx, bufs[r])
 
 
 def test_keyframe_db_mode_a(plm_lib):

@@ -92,6 +92,25 @@ static void frame_mode(int reps) {
     };
     // serial: the four calls one after the other on one thread
     const double serial = median_us([&] { stereo(P, false); stereo(Ln, true); temporal(P); temporal(Ln); }, reps);
+    // frame session: the same four calls recorded and executed as ONE round trip (plm_frame_begin / plm_frame_end)
+    int c4[4];
+    auto session_frame = [&] {
+        std::fill(P.m12.begin(), P.m12.end(), -1);
+        std::fill(Ln.m12.begin(), Ln.m12.end(), -1);
+        std::vector<int32_t> &tp12 = P.m12, &tl12 = Ln.m12;
+        static std::vector<int32_t> t_p, t_l;
+        t_p.assign(P.n, -1);
+        t_l.assign(Ln.n, -1);
+        plm_frame_begin(nullptr);
+        plm_match_grid_points(nullptr, P.coords.data(), P.d1.data(), P.n, 32, P.cell_start.data(), P.cell_items.data(), 48, 64, P.d2.data(), P.n, 32,
+                              win_st, 0.9, 1, tp12.data(), &c4[0]);
+        plm_match_grid_lines(nullptr, Ln.coords.data(), Ln.d1.data(), Ln.n, 32, Ln.cell_start.data(), Ln.cell_items.data(), 48, 64, Ln.d2.data(), Ln.n,
+                             32, Ln.dirs2.data(), 0.75, win_st, 0.9, 1, tl12.data(), &c4[1]);
+        plm_match(nullptr, P.d1.data(), P.n, 32, P.d2.data(), P.n, 32, 0.9f, 1, t_p.data(), &c4[2]);
+        plm_match(nullptr, Ln.d1.data(), Ln.n, 32, Ln.d2.data(), Ln.n, 32, 0.9f, 1, t_l.data(), &c4[3]);
+        plm_frame_end(nullptr);
+    };
+    const double session = median_us(session_frame, reps);
     // two threads, as the reference: a generation counter starts a stage, a done counter joins it
     std::atomic<int> go{0}, done{0};
     std::atomic<bool> quit{false};
@@ -120,7 +139,8 @@ static void frame_mode(int reps) {
     tp.join();
     tl.join();
     printf("frame (600 pts + 200 lines): stereo matchGrid + temporal match, 4 calls serial %7.1f us; points || lines on two host threads "
-           "(the reference's std::async structure) %7.1f us\n", serial, threaded);
+           "(the reference's std::async structure) %7.1f us; one frame session (plm_frame_begin/end, one round trip) %7.1f us "
+           "[matches %d %d %d %d]\n", serial, threaded, session, c4[0], c4[1], c4[2], c4[3]);
 }
 
 int main(int argc, char **argv) {
