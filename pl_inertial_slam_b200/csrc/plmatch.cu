@@ -97,8 +97,8 @@ struct plm_ctx {
     };
     bool in_frame = false;
     std::vector<FrameCall> frame_calls;
-    cudaStream_t frame_streams[2] = {nullptr, nullptr};
-    cudaEvent_t frame_events[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t frame_streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t frame_events[4] = {nullptr, nullptr, nullptr, nullptr};
     // optional per-launch timing of the brute-force slice kernel (bench.py's roofline)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -476,9 +476,9 @@ PLM_API int plm_ctx_destroy(plm_ctx *ctx) {
         cudaStreamSynchronize(ctx->own_stream);
         cudaStreamDestroy(ctx->own_stream);
     }
-    for (int i = 0; i < 2; ++i)
-        if (ctx->frame_streams[i]) cudaStreamDestroy(ctx->frame_streams[i]);
     for (int i = 0; i < 3; ++i)
+        if (ctx->frame_streams[i]) cudaStreamDestroy(ctx->frame_streams[i]);
+    for (int i = 0; i < 4; ++i)
         if (ctx->frame_events[i]) cudaEventDestroy(ctx->frame_events[i]);
     if (ctx->d_buf) cudaFree(ctx->d_buf);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
@@ -2730,25 +2730,25 @@ PLM_API int plm_frame_end(plm_ctx *ctx) {
     if ((st = ctx->ensure_pinned(h_total)) != PLM_OK) return st;
     if ((st = ctx->ensure_device(d_total)) != PLM_OK) return st;
     if (!ctx->frame_streams[0]) {
-        for (int i = 0; i < 2; ++i) CU_TRY(cudaStreamCreateWithFlags(&ctx->frame_streams[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 3; ++i) CU_TRY(cudaEventCreateWithFlags(&ctx->frame_events[i], cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) CU_TRY(cudaStreamCreateWithFlags(&ctx->frame_streams[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) CU_TRY(cudaEventCreateWithFlags(&ctx->frame_events[i], cudaEventDisableTiming));
     }
-    for (int k = 0; k < n; ++k) {
-        ex[k].h_base = ctx->h_buf + h_off[k];
-        ex[k].d_base = ctx->d_buf + d_off[k];
-        ex[k].phase = EXEC_PACK;
-        if ((st = frame_run(ctx, calls[k], &ex[k])) != PLM_OK) return st;
-    }
-    // the calls are independent: their copies and kernels go round-robin over three streams and run concurrently
+    // the calls are independent: each is packed and immediately launched (copy in, kernels, copy out) on its own lane,
+    // round-robin over four streams, so the packing of call k + 1 overlaps the device work of call k and the kernels
+    // of different calls run side by side
     cudaStream_t main_stream = ctx->stream;
-    cudaStream_t lanes[3] = {main_stream, ctx->frame_streams[0], ctx->frame_streams[1]};
-    const int n_lanes = std::min(n, 3);
+    cudaStream_t lanes[4] = {main_stream, ctx->frame_streams[0], ctx->frame_streams[1], ctx->frame_streams[2]};
+    const int n_lanes = std::min(n, 4);
     if (n_lanes > 1) {
         CU_TRY(cudaEventRecord(ctx->frame_events[0], main_stream)); // earlier work of this context comes first
         for (int i = 1; i < n_lanes; ++i) CU_TRY(cudaStreamWaitEvent(lanes[i], ctx->frame_events[0], 0));
     }
     int rc = PLM_OK;
     for (int k = 0; k < n && rc == PLM_OK; ++k) {
+        ex[k].h_base = ctx->h_buf + h_off[k];
+        ex[k].d_base = ctx->d_buf + d_off[k];
+        ex[k].phase = EXEC_PACK;
+        if ((rc = frame_run(ctx, calls[k], &ex[k])) != PLM_OK) break;
         ctx->stream = lanes[k % n_lanes];
         ex[k].phase = EXEC_LAUNCH;
         rc = frame_run(ctx, calls[k], &ex[k]);
