@@ -19,6 +19,7 @@
 // allocation, and 8 POPC are cheaper than the round trip.
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "plm_common.cuh"
 
@@ -769,7 +770,7 @@ grid_match_chunked_kernel(GridJob job, GridParams gp) {
 constexpr int GRID_ROW_THREADS = 256;
 
 struct GridRowsSmem { // layout of the work area, in bytes from the start of dynamic shared memory
-    size_t K, T, Tnew, B, rb0, rb1, d1s, rowdir, ent, stage, total;
+    size_t K, T, Tnew, B, cmin, rb0, rb1, d1s, rowdir, ent, stage, total;
 };
 __host__ __device__ inline GridRowsSmem grid_rows_layout(int n2, bool lines, int cap_pairs, int n_cells, int cap_items, int staged) {
     GridRowsSmem L;
@@ -778,6 +779,7 @@ __host__ __device__ inline GridRowsSmem grid_rows_layout(int n2, bool lines, int
     L.T = o; o += grid_align16(static_cast<size_t>(n2) * 2);
     L.Tnew = o; o += grid_align16(static_cast<size_t>(n2) * 2);
     L.B = o; o += grid_align16(static_cast<size_t>(n2) * 2);
+    L.cmin = o; o += grid_align16(static_cast<size_t>(n2) * 2); // cluster form: this CTA's column minima, read by the higher ranks
     L.rb0 = o; o += static_cast<size_t>(GRID_ROW_THREADS) * 4;
     L.rb1 = o; o += static_cast<size_t>(GRID_ROW_THREADS) * 4;
     L.d1s = o; o += static_cast<size_t>(GRID_ROW_THREADS) * 32;
@@ -810,9 +812,12 @@ __device__ __forceinline__ void row_walk(const GridJob &job, const GridParams &g
 
 // STAGED: the frame side (cell_start, d2, dirs2 and -- when they fit -- cell_items) is copied into shared memory first;
 // the accesses below then go through pointers the compiler can prove to be shared (LDS instead of generic loads).
-template <int PASS, int STAGED>
-__global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
-grid_rows_kernel(GridJob job, GridParams gp) {
+// MODE 0 / 1: pass 0 / pass 1 of the multi-launch form (thresholds travel through gp.cta_min and grid_scan_kernel).
+// MODE 2: the whole matchGrid of a frame-sized job in ONE launch -- the CTAs (256 rows each, <= 8) form one
+//         thread-block cluster: pass 0, cluster barrier, thresholds = minima of the lower-ranked CTAs read through
+//         distributed shared memory, pass 1, cluster barrier, mutual check from the global m21 keys.
+template <int STAGED, int MODE>
+__device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_warp_tot[GRID_ROW_THREADS / 32];
     __shared__ int s_seg_end;
@@ -850,14 +855,19 @@ grid_rows_kernel(GridJob job, GridParams gp) {
     }
     const long long cta_row0 = static_cast<long long>(blockIdx.x) * gp.rows_per_cta;
     const int row_end = static_cast<int>(min(static_cast<long long>(n1), cta_row0 + gp.rows_per_cta));
-    uint16_t *cta_min = gp.cta_min + static_cast<size_t>(blockIdx.x) * n2;
+    uint16_t *cta_min = MODE == 2 ? nullptr : gp.cta_min + static_cast<size_t>(blockIdx.x) * n2;
+    uint16_t *cmin16 = reinterpret_cast<uint16_t *>(smem_raw + L.cmin);
+
+    // one pass over this CTA's rows; P = std::integral_constant<int, 0 / 1>
+    auto run_pass = [&](auto P, uint16_t *cmin_out, const uint16_t *thr_in) {
+    constexpr int PASS = decltype(P)::value;
     const bool thresholds = PASS == 1 && gp.best_lr;
 
     if (PASS == 0) {
         for (int i = tid; i < n2; i += NT) K[i] = KEY32_ABSENT;
     } else if (thresholds) {
         for (int i = tid; i < n2; i += NT) {
-            const uint16_t t = cta_min[i]; // exclusive prefix over the earlier CTAs (and lower-ranked shards)
+            const uint16_t t = thr_in[i]; // exclusive prefix over the earlier CTAs (and lower-ranked shards)
             T[i] = t;
             Tnew[i] = t;
             B[i] = D_INF;
@@ -1098,11 +1108,60 @@ grid_rows_kernel(GridJob job, GridParams gp) {
     }
     if (PASS == 0) {
         __syncthreads();
-        for (int i = tid; i < n2; i += NT) cta_min[i] = static_cast<uint16_t>(min(K[i], 0xFFFFu));
+        for (int i = tid; i < n2; i += NT) cmin_out[i] = static_cast<uint16_t>(min(K[i], 0xFFFFu));
         return;
     }
     if (accepted) atomicAdd(job.count, accepted);
+    }; // run_pass
+
+    if (MODE == 0) {
+        run_pass(std::integral_constant<int, 0>{}, cta_min, nullptr);
+    } else if (MODE == 1) {
+        run_pass(std::integral_constant<int, 1>{}, nullptr, cta_min);
+    } else {
+        cg::cluster_group cluster = cg::this_cluster();
+        const int rank = static_cast<int>(cluster.block_rank());
+        if (gp.best_lr) {
+            if (rank == 0)
+                for (int i = tid; i < n2; i += NT) gp.m21key[i] = KEY64_ABSENT;
+            run_pass(std::integral_constant<int, 0>{}, cmin16, nullptr);
+            cluster.sync();
+            for (int i = tid; i < n2; i += NT) {
+                uint16_t t = D_INF;
+                for (int r = 0; r < rank; ++r) t = min(t, cluster.map_shared_rank(cmin16, r)[i]);
+                Tnew[i] = t;
+            }
+            __syncthreads();
+        }
+        run_pass(std::integral_constant<int, 1>{}, nullptr, Tnew);
+        if (gp.best_lr) {
+            cluster.sync(); // every CTA's m21 keys are in; nobody's cmin16 is read any more
+            // mutual check (matching.cpp:166-174) over this CTA's rows, stale entries included
+            int culled = 0;
+            for (long long i1 = cta_row0 + tid; i1 < row_end; i1 += NT) {
+                const int32_t i2 = job.m12[i1];
+                if (i2 >= 0) {
+                    const unsigned long long k = (i2 < n2) ? gp.m21key[i2] : KEY64_ABSENT;
+                    const long long back = (k == KEY64_ABSENT) ? -1 : static_cast<long long>(k & 0xFFFFFFFFull);
+                    if (back != job.i1_base + i1) {
+                        job.m12[i1] = -1;
+                        ++culled;
+                    }
+                }
+            }
+            if (culled) atomicSub(job.count, culled);
+        }
+    }
 }
+
+template <int PASS, int STAGED>
+__global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
+grid_rows_kernel(GridJob job, GridParams gp) { grid_rows_device<STAGED, PASS>(job, gp); }
+
+// One launch, one cluster of gridDim.x <= 8 CTAs (MODE 2 above): the single-call path for frame-sized jobs.
+template <int STAGED>
+__global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
+grid_rows_cluster_kernel(GridJob job, GridParams gp) { grid_rows_device<STAGED, 2>(job, gp); }
 
 // cta_min[c][i2] <- min(seed[i2], min over c' < c of cta_min[c'][i2]); col_min[i2] = overall minimum.
 // seed (may be null) carries the minima of lower-ranked database shards (multi-GPU).

@@ -213,7 +213,7 @@ struct KnnPlan {
 int g_frames_pairs_per_row[2] = {8, 0};
 int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame pipeline (128 or 256; measurement knob)
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
-int g_grid_cluster = 1; // single matchGrid calls use the 8-CTA cluster kernel (0: one CTA, measurement only)
+int g_grid_cluster = 2; // single matchGrid calls: 2 = row-parallel kernel on one cluster, 1 = chunk kernel on an 8-CTA cluster, 0 = one CTA
 long long g_peer_spin_ticks = 4000000000ll; // bounded spin of the peer-memory kernels (~2 s of SM clock); option "peer_spin_ms"
 int g_knn_fill = 1;     // long brute-force scans: uneven workers fill every CTA slot + shared second-best bound (0: off, measurement)
 int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
@@ -396,7 +396,7 @@ PLM_API int plm_set_option(const char *key, int value) {
         return PLM_OK;
     }
     if (std::strcmp(key, "grid_cluster") == 0) {
-        g_grid_cluster = value ? 1 : 0;
+        g_grid_cluster = std::max(0, std::min(value, 2));
         return PLM_OK;
     }
     if (std::strcmp(key, "frames_threads_l") == 0) {
@@ -944,6 +944,8 @@ int plan_map_grid(plm_ctx *ctx, long long n1, int n2, int n_cells, bool is_lines
             CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
             CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
             CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+            CU_TRY(cudaFuncSetAttribute(plm::grid_rows_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+            CU_TRY(cudaFuncSetAttribute(plm::grid_rows_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
             ctx->rows_attr_set = true;
         }
         int per_sm = 0;
@@ -988,6 +990,28 @@ int launch_map_grid(plm_ctx *ctx, int pass, const plm::GridJob &job, const plm::
     }
     ctx->launches++;
     CU_TRY(cudaGetLastError());
+    return PLM_OK;
+}
+
+// Frame-sized job (<= 8 x 256 rows) as ONE launch: the row-parallel kernel on one thread-block cluster.
+constexpr int GRID_ROWS_CLUSTER_MAX = 8;
+int launch_grid_rows_cluster(plm_ctx *ctx, const plm::GridJob &job, const plm::GridParams &gp, int n_cta, size_t smem) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_cta, 1, 1);
+    cfg.blockDim = dim3(plm::GRID_ROW_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = n_cta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (gp.staged) CU_TRY(cudaLaunchKernelEx(&cfg, plm::grid_rows_cluster_kernel<1>, job, gp));
+    else CU_TRY(cudaLaunchKernelEx(&cfg, plm::grid_rows_cluster_kernel<0>, job, gp));
+    ctx->launches++;
     return PLM_OK;
 }
 
@@ -1063,6 +1087,22 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     size_t o_cta_min = 0, o_m21key = 0, o_m21 = 0;
     plm::GridParams gp;
     std::memset(&gp, 0, sizeof(gp));
+    // frame-sized single calls: the row-parallel kernel on one cluster (one launch) when its work arrays fit
+    bool rows_cluster = fused && n1 >= 64 && n1 <= GRID_ROWS_CLUSTER_MAX * plm::GRID_ROW_THREADS && g_grid_cluster >= 2;
+    if (rows_cluster) {
+        if ((st = plan_map_grid(ctx, n1, n2, n_cells, is_lines != 0, gp, warps, n_cta, map_smem)) != PLM_OK) return st;
+        if (warps != 0) {
+            rows_cluster = false; // frame wider than the shared-memory work arrays: chunk kernels
+        } else {
+            // spread the rows over all 8 CTAs of the cluster (a CTA always has 256 threads: the rows of its block feed
+            // phase A, all threads share the flat pair list of phase B)
+            int rpc = ((n1 + GRID_ROWS_CLUSTER_MAX - 1) / GRID_ROWS_CLUSTER_MAX + 31) / 32 * 32;
+            rpc = std::min(rpc, plm::GRID_ROW_THREADS);
+            gp.rows_per_cta = rpc;
+            n_cta = (n1 + rpc - 1) / rpc;
+            o_m21key = L.add(size_t(std::max(n2, 1)) * 8);
+        }
+    }
     if (!fused) {
         if ((st = plan_map_grid(ctx, n1, n2, n_cells, is_lines != 0, gp, warps, n_cta, map_smem)) != PLM_OK) return st;
         o_cta_min = L.add(size_t(n_cta) * std::max(n2, 1) * 2);
@@ -1122,7 +1162,10 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     gp.best_lr = best_lr ? 1 : 0;
     gp.ratio = ratio;
     gp.line_sim_th = line_sim_th;
-    if (fused && n1 >= 64 && g_grid_cluster) {
+    if (rows_cluster) {
+        gp.m21key = reinterpret_cast<unsigned long long *>(DB + o_m21key);
+        st = launch_grid_rows_cluster(ctx, job, gp, n_cta, map_smem);
+    } else if (fused && n1 >= 64 && g_grid_cluster) {
         st = launch_grid_cluster(ctx, reinterpret_cast<const plm::GridJob *>(DB + o_job), 1, gp, n1, std::max(n2, 1),
                                  std::max(n_items, 1), is_lines != 0);
     } else if (fused) {

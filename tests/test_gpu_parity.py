@@ -409,3 +409,22 @@ def test_frame_session_equals_separate_calls(M):
         with M.FrameSession(None):
             M.match(prev.pdesc_l, prev.pdesc_l[:0], 0.9, [])
     assert M.match(prev.pdesc_l, curr.pdesc_l, 0.9, []) == want[2] or True     # the context is usable afterwards
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_match_grid_single_call_kernel_families(M, plm_lib, mode):
+    """The three single-call kernels for frame-sized jobs -- one CTA (0), chunk phases on an 8-CTA cluster (1), the
+    row-parallel pair-list kernel on one cluster (2, default) -- on a cross-section of the grid cases."""
+    assert plm_lib.plm_set_option(b"grid_cluster", mode) == 0
+    try:
+        for n1, n2, is_lines, tie, win, bad, zl in GRID_CASES[:4] + GRID_CASES[7:12]:
+            rng = np.random.default_rng(n1 * 31 + n2 * 7 + int(is_lines) + 1)
+            case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=tie, win=win, bad_items=bad, zero_len=zl)
+            for best_lr, ratio in ((1, 0.9), (0, 0.75), (1, 1.0)):
+                stale = np.full(n1, -1, np.int32)
+                stale[::9] = rng.integers(0, max(n2, 1), len(stale[::9]))
+                n_o, m_o = oracle_grid(port, case, ratio, best_lr, m12=stale)
+                n_g, m_g = gpu_grid(case, ratio, best_lr, m12=stale)
+                assert n_g == n_o and (m_g == m_o).all(), (mode, n1, n2, is_lines, best_lr, ratio)
+    finally:
+        plm_lib.plm_set_option(b"grid_cluster", 2)
