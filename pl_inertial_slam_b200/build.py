@@ -20,6 +20,9 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-shared",
+    # the CUDA runtime as a shared library (libcudart.so.12: the toolkit's under /usr/local/cuda/lib64, or the copy a
+    # host process such as PyTorch has already loaded) instead of the default static archive
+    "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64",
 ]
 
 
