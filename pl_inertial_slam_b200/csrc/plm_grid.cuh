@@ -47,6 +47,14 @@ struct GridParams {
     int best_lr;
     int rows_per_warp;          // chunked launch only; the fused kernel derives it from n1
     int rows_per_cta, cap_pairs; // row-parallel launch (grid_rows_kernel): rows per CTA, pair-list capacity
+    // pass 0 -> pass 1 hand-over of the row-parallel launch: pass 0 leaves every pair it evaluated (i2 | row | D) in
+    // ent_g (a fixed region of ent_per_cta entries per CTA) with one seg_tab record per list segment, so that pass 1
+    // only streams them against its thresholds instead of walking the windows and computing the distances again.
+    // seg_cnt[cta] = number of records, -1 when the CTA's pairs did not fit (pass 1 then recomputes).  Null = off.
+    uint32_t *ent_g;
+    int4 *seg_tab;      // [n_cta][GRID_SEG_TAB]: (offset in ent_g, entries, block of rows, 0)
+    int32_t *seg_cnt;   // [n_cta]
+    int ent_per_cta, pad4_;
     // fused kernel: when staged != 0 every input of the job is first copied into shared memory with
     // coalesced 128-bit loads (capacities below, in elements), so the per-row dependent accesses
     // (coords -> cell_start -> cell_items -> descriptor / threshold) cost shared-memory latency
@@ -768,14 +776,17 @@ grid_match_chunked_kernel(GridJob job, GridParams gp) {
 // A block whose slots exceed the list capacity (very dense windows) is handled by the same rounds with every
 // thread re-walking its own row instead (slower, same result).
 constexpr int GRID_ROW_THREADS = 256;
+constexpr int GRID_SEG_TAB = 32;          // list segments a CTA can hand from pass 0 to pass 1
+constexpr int GRID_ENT_PER_ROW = 64;      // hand-over capacity per row (slots; ~10 are used for points, ~50 for lines)
 
 struct GridRowsSmem { // layout of the work area, in bytes from the start of dynamic shared memory
-    size_t K, T, Tnew, B, cmin, rb0, rb1, d1s, rowdir, ent, stage, total;
+    size_t K, K2, T, Tnew, B, cmin, rb0, rb1, d1s, rowdir, ent, stage, total;
 };
 __host__ __device__ inline GridRowsSmem grid_rows_layout(int n2, bool lines, int cap_pairs, int n_cells, int cap_items, int staged) {
     GridRowsSmem L;
     size_t o = 0;
     L.K = o; o += grid_align16(static_cast<size_t>(n2) * 4);
+    L.K2 = o; o += grid_align16(static_cast<size_t>(n2) * 4); // second proposal array: the rounds over a pair list ping-pong
     L.T = o; o += grid_align16(static_cast<size_t>(n2) * 2);
     L.Tnew = o; o += grid_align16(static_cast<size_t>(n2) * 2);
     L.B = o; o += grid_align16(static_cast<size_t>(n2) * 2);
@@ -826,6 +837,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
     const int n_cells = gp.grid_rows * gp.grid_cols;
     const GridRowsSmem L = grid_rows_layout(n2, job.is_lines != 0, gp.cap_pairs, n_cells, gp.cap_items, STAGED);
     uint32_t *K = reinterpret_cast<uint32_t *>(smem_raw + L.K);
+    uint32_t *K2 = reinterpret_cast<uint32_t *>(smem_raw + L.K2);
     uint16_t *T = reinterpret_cast<uint16_t *>(smem_raw + L.T);
     uint16_t *Tnew = reinterpret_cast<uint16_t *>(smem_raw + L.Tnew);
     uint16_t *B = reinterpret_cast<uint16_t *>(smem_raw + L.B);
@@ -840,7 +852,9 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
     const double2 *dirp = STAGED ? reinterpret_cast<const double2 *>(smem_raw + o_dir) : reinterpret_cast<const double2 *>(job.dirs2);
     const int32_t *s_items = reinterpret_cast<const int32_t *>(smem_raw + o_ci);
     bool items_staged = false;
-    if (STAGED) {
+    // pass 1 in its replay form (every pair of this CTA was handed over by pass 0) never touches the frame side
+    const bool replay_only = MODE == 1 && gp.best_lr && gp.ent_g && gp.seg_cnt[blockIdx.x] >= 0;
+    if (STAGED && !replay_only) {
         const int n_items = job.cell_start[n_cells];
         stage_bytes(smem_raw + o_cs, job.cell_start, static_cast<size_t>(n_cells + 1) * 4);
         stage_bytes(smem_raw + o_d2, job.d2, static_cast<size_t>(n2) * 32);
@@ -872,14 +886,104 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
             Tnew[i] = t;
             B[i] = D_INF;
             K[i] = KEY32_ABSENT;
+            K2[i] = KEY32_ABSENT;
         }
     }
     __syncthreads();
     const uint32_t utid = static_cast<uint32_t>(tid);
+    // Rounds over the survivors in ent[0, seg_total) (entry = i2 << 17 | row << 9 | D; the proposals of round 0 are
+    // already in K).  Per round ONE pass over the list: the entry that owns the column's minimum key is live, later
+    // rows of the column are dead, earlier rows stay undecided and propose straight into the other array for the next
+    // round; then the touched columns are folded (round 0: new threshold + m21 candidate) and cleared.
+    auto list_rounds = [&](int seg_total, long long base) {
+        uint32_t *Kc = K, *Kn = K2;
+        for (int round = 0;; ++round) {
+            bool again = false;
+            for (int e = tid; e < seg_total; e += NT) {
+                const uint32_t v = ent[e];
+                if (v == PAIR_INVALID) continue;
+                const uint32_t i2 = v >> 17, row = (v >> 9) & 0xFFu, d = v & 0x1FFu;
+                const uint32_t key = (d << 16) | row, k = Kc[i2];
+                if (key == k) {
+                    top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
+                    ent[e] = PAIR_INVALID;
+                } else if (row > (k & 0xFFFFu)) {
+                    ent[e] = PAIR_INVALID;
+                } else {
+                    atomicMin(&Kn[i2], key);
+                    again = true;
+                }
+            }
+            const int more = __syncthreads_or(again ? 1 : 0);
+            for (int i2 = tid; i2 < n2; i2 += NT) {
+                const uint32_t k = Kc[i2];
+                if (k != KEY32_ABSENT) {
+                    if (round == 0) { // the best pair of the column in this block / segment: new threshold, m21 candidate
+                        Tnew[i2] = static_cast<uint16_t>(k >> 16);
+                        atomicMin(&gp.m21key[i2], make_key64(k >> 16, static_cast<uint32_t>(job.i1_base + base + (k & 0xFFFFu))));
+                    }
+                    Kc[i2] = KEY32_ABSENT;
+                }
+            }
+            __syncthreads();
+            if (!more) break;
+            uint32_t *t = Kc;
+            Kc = Kn;
+            Kn = t;
+        }
+    };
     int accepted = 0;
+    // pass 0 records its pairs for pass 1 (MODE 0 / 1 only; the one-launch cluster form keeps everything on chip)
+    const bool recording = PASS == 0 && MODE == 0 && gp.ent_g != nullptr;
+    uint32_t *rec_base = recording || (PASS == 1 && MODE == 1 && gp.ent_g) ? gp.ent_g + static_cast<size_t>(blockIdx.x) * gp.ent_per_cta : nullptr;
+    int4 *rec_tab = gp.seg_tab ? gp.seg_tab + static_cast<size_t>(blockIdx.x) * GRID_SEG_TAB : nullptr;
+    bool rec_ok = true;   // uniform
+    int rec_n = 0, rec_used = 0;
+    const int n_rec = (PASS == 1 && MODE == 1 && thresholds && gp.ent_g) ? gp.seg_cnt[blockIdx.x] : -1;
+    int rec_i = 0;
     for (long long base = cta_row0; base < row_end; base += NT) { // uniform over the CTA
         const long long i1 = base + tid;
         const bool has_row = i1 < row_end;
+        const int blk = static_cast<int>((base - cta_row0) / NT);
+        if (n_rec >= 0) {
+            // ---- pass 1, replay form: stream the pairs pass 0 left behind against the thresholds ----
+            rb0[tid] = KEY32_ABSENT;
+            rb1[tid] = KEY32_ABSENT;
+            __syncthreads();
+            while (rec_i < n_rec && rec_tab[rec_i].z == blk) {
+                const int4 rec = rec_tab[rec_i];
+                ++rec_i;
+                const uint32_t *src = rec_base + rec.x;
+                const int seg_total = rec.y;
+                for (int e = tid; e < seg_total; e += NT) {
+                    uint32_t v = src[e];
+                    if (v != PAIR_INVALID) {
+                        const uint32_t i2 = v >> 17, d = v & 0x1FFu;
+                        if (d < T[i2]) atomicMin(&K[i2], (d << 16) | ((v >> 9) & 0xFFu));
+                        else v = PAIR_INVALID;
+                    }
+                    ent[e] = v;
+                }
+                __syncthreads();
+                list_rounds(seg_total, base);
+                for (int i2 = tid; i2 < n2; i2 += NT) { // thresholds for the rows that follow
+                    T[i2] = Tnew[i2];
+                    B[i2] = D_INF;
+                }
+                __syncthreads();
+            }
+            const uint32_t b0 = rb0[tid], b1 = rb1[tid];
+            __syncthreads(); // rb / ent are rewritten by the next block
+            if (has_row && b0 != KEY32_ABSENT) {
+                const int best_d = static_cast<int>(b0 >> GRID_KEY_BITS);
+                const int best_d2 = (b1 == KEY32_ABSENT) ? 0x7FFFFFFF : static_cast<int>(b1 >> GRID_KEY_BITS);
+                if (static_cast<double>(best_d) < __dmul_rn(static_cast<double>(best_d2), gp.ratio)) { // matching.cpp:160 / :241
+                    job.m12[i1] = static_cast<int32_t>(b0 & ((1u << GRID_KEY_BITS) - 1));
+                    ++accepted;
+                }
+            }
+            continue;
+        }
         // ---- phase A: windows, slot counts, block scan ----
         RowQuery r;
         int S = 0;
@@ -952,6 +1056,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
                 if (v == PAIR_INVALID) return 0xFFFFu;
                 row = v >> 16;
                 i2 = v & 0xFFFFu;
+                if (thresholds && T[i2] == 0) return 0xFFFFu; // column without a live pair in this CTA (grid_scan_kernel)
                 if (job.is_lines) {
                     const double2 q = rowdir[row];
                     const double2 t2 = dirp[i2];
@@ -1003,6 +1108,18 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
                 }
                 __syncthreads();
                 if (n_seg > 1) seg_total = s_seg_end;
+                // pass 0: room for this segment's pairs in the CTA's hand-over region (uniform decision)
+                uint32_t *rec_dst = nullptr;
+                if (recording && rec_ok) {
+                    if (rec_n < GRID_SEG_TAB && rec_used + seg_total <= gp.ent_per_cta) {
+                        rec_dst = rec_base + rec_used;
+                        if (tid == 0) rec_tab[rec_n] = make_int4(rec_used, seg_total, blk, 0);
+                        rec_used += seg_total;
+                        ++rec_n;
+                    } else {
+                        rec_ok = false;
+                    }
+                }
                 // ---- phase B: one thread per entry, two independent entries in flight per trip ----
                 for (int e = tid; e < seg_total; e += 2 * NT) {
                     const int e2 = e + NT;
@@ -1014,40 +1131,19 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
                         ent[e] = oa;
                         if (e2 < seg_total) ent[e2] = ob;
                     }
+                    if (rec_dst) {
+                        rec_dst[e] = (da == 0xFFFFu) ? PAIR_INVALID : ((ia << 17) | (ra << 9) | da);
+                        if (e2 < seg_total) rec_dst[e2] = (db == 0xFFFFu) ? PAIR_INVALID : ((ib << 17) | (rb << 9) | db);
+                    }
                 }
                 __syncthreads();
                 if (!thresholds) continue;
-                // rounds over the list: a decided entry is overwritten with PAIR_INVALID
-                for (int round = 0;; ++round) {
-                    bool again = false;
-                    for (int e = tid; e < seg_total; e += NT) {
-                        const uint32_t v = ent[e];
-                        if (v == PAIR_INVALID) continue;
-                        const uint32_t i2 = v >> 17, row = (v >> 9) & 0xFFu, d = v & 0x1FFu;
-                        const uint32_t key = (d << 16) | row, k = K[i2];
-                        if (key == k) {
-                            top2_insert_atomic(&rb0[row], &rb1[row], (d << GRID_KEY_BITS) | i2);
-                            ent[e] = PAIR_INVALID;
-                        } else if (row > (k & 0xFFFFu)) {
-                            ent[e] = PAIR_INVALID;
-                        } else {
-                            again = true;
-                        }
-                    }
-                    __syncthreads();
-                    fold(round);
-                    if (!__syncthreads_or(again ? 1 : 0)) break;
-                    for (int e = tid; e < seg_total; e += NT) {
-                        const uint32_t v = ent[e];
-                        if (v == PAIR_INVALID) continue;
-                        atomicMin(&K[v >> 17], ((v & 0x1FFu) << 16) | ((v >> 9) & 0xFFu));
-                    }
-                    __syncthreads();
-                }
+                list_rounds(seg_total, base);
                 if (seg + 1 < n_seg || base + NT < row_end) next_thresholds(); // for the rows that follow
             }
         } else {
             // a single row has more slots than half the list: every thread walks its own row
+            rec_ok = false;
             if (has_row) {
                 if (PASS == 0) {
                     row_walk(job, gp, r, [&](int i2, int d) {
@@ -1109,6 +1205,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
     if (PASS == 0) {
         __syncthreads();
         for (int i = tid; i < n2; i += NT) cmin_out[i] = static_cast<uint16_t>(min(K[i], 0xFFFFu));
+        if (recording && tid == 0) gp.seg_cnt[blockIdx.x] = rec_ok ? rec_n : -1;
         return;
     }
     if (accepted) atomicAdd(job.count, accepted);
@@ -1163,7 +1260,8 @@ template <int STAGED>
 __global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
 grid_rows_cluster_kernel(GridJob job, GridParams gp) { grid_rows_device<STAGED, 2>(job, gp); }
 
-// cta_min[c][i2] <- min(seed[i2], min over c' < c of cta_min[c'][i2]); col_min[i2] = overall minimum.
+// cta_min[c][i2] <- min(seed[i2], min over c' < c of cta_min[c'][i2]) when CTA c's own minimum beats it, else 0;
+// col_min[i2] = overall minimum.
 // seed (may be null) carries the minima of lower-ranked database shards (multi-GPU).
 // One WARP per column: lanes take 32 consecutive CTAs at a time and scan them with shuffles, so the
 // dependent chain is n_cta / 32 steps long instead of n_cta (the map-sized launch has ~400 CTAs).
@@ -1194,7 +1292,10 @@ __global__ void grid_scan_kernel(uint16_t *__restrict__ cta_min, int n_cta, int 
             }
             uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
             if (lane == 0) excl = D_INF;
-            if (c < n_cta) cta_min[static_cast<size_t>(c) * n2 + i2] = static_cast<uint16_t>(min(run, excl));
+            // a CTA whose own minimum does not beat what it inherits has no live pair in this column: threshold 0 tells
+            // pass 1 to skip the column's pairs without computing their distances
+            const uint32_t inherit = min(run, excl);
+            if (c < n_cta) cta_min[static_cast<size_t>(c) * n2 + i2] = static_cast<uint16_t>(t[k] < inherit ? inherit : 0u);
             run = min(run, __shfl_sync(0xFFFFFFFFu, incl, 31));
         }
     }

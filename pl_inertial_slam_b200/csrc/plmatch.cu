@@ -977,6 +977,26 @@ int plan_map_grid(plm_ctx *ctx, long long n1, int n2, int n_cells, bool is_lines
     return PLM_OK;
 }
 
+// Hand-over scratch of the row-parallel launch (pass 0 -> pass 1): [seg_tab][seg_cnt][ent_g]
+size_t map_grid_handover_bytes(int warps, int n_cta, int rows_per_cta) {
+    if (warps != 0 || n_cta <= 0) return 0;
+    return align_up(size_t(n_cta) * plm::GRID_SEG_TAB * sizeof(int4)) + align_up(size_t(n_cta) * 4) +
+           align_up(size_t(n_cta) * rows_per_cta * plm::GRID_ENT_PER_ROW * 4);
+}
+void map_grid_handover_bind(plm::GridParams &gp, char *base, int warps, int n_cta, bool best_lr) {
+    gp.ent_g = nullptr;
+    gp.seg_tab = nullptr;
+    gp.seg_cnt = nullptr;
+    gp.ent_per_cta = 0;
+    if (warps != 0 || n_cta <= 0 || !best_lr || !base) return;
+    gp.seg_tab = reinterpret_cast<int4 *>(base);
+    base += align_up(size_t(n_cta) * plm::GRID_SEG_TAB * sizeof(int4));
+    gp.seg_cnt = reinterpret_cast<int32_t *>(base);
+    base += align_up(size_t(n_cta) * 4);
+    gp.ent_g = reinterpret_cast<uint32_t *>(base);
+    gp.ent_per_cta = gp.rows_per_cta * plm::GRID_ENT_PER_ROW;
+}
+
 int launch_map_grid(plm_ctx *ctx, int pass, const plm::GridJob &job, const plm::GridParams &gp, int warps, int n_cta, size_t smem) {
     if (n_cta <= 0) return PLM_OK;
     if (warps == 0) {
@@ -1084,7 +1104,7 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     const bool fused = n1 <= GRID_FUSED_MAX_ROWS && n1 < (1 << plm::GRID_KEY_BITS);
     int warps = 0, n_cta = 0;
     size_t map_smem = 0;
-    size_t o_cta_min = 0, o_m21key = 0, o_m21 = 0;
+    size_t o_cta_min = 0, o_m21key = 0, o_m21 = 0, o_handover = 0;
     plm::GridParams gp;
     std::memset(&gp, 0, sizeof(gp));
     // frame-sized single calls: the row-parallel kernel on one cluster (one launch) when its work arrays fit
@@ -1106,6 +1126,7 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     if (!fused) {
         if ((st = plan_map_grid(ctx, n1, n2, n_cells, is_lines != 0, gp, warps, n_cta, map_smem)) != PLM_OK) return st;
         o_cta_min = L.add(size_t(n_cta) * std::max(n2, 1) * 2);
+        o_handover = L.add(map_grid_handover_bytes(warps, n_cta, gp.rows_per_cta));
         o_m21key = L.add(size_t(std::max(n2, 1)) * 8);
         o_m21 = L.add(size_t(std::max(n2, 1)) * 4);
     }
@@ -1171,6 +1192,7 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     } else if (fused) {
         st = launch_grid_fused(ctx, reinterpret_cast<const plm::GridJob *>(DB + o_job), 1, gp, n1, std::max(n2, 1), std::max(n_items, 1), is_lines != 0);
     } else {
+        map_grid_handover_bind(gp, DB + o_handover, warps, n_cta, best_lr != 0);
         st = launch_grid_chunked(ctx, DB, job, gp, o_cta_min, o_m21key, o_m21, warps, n_cta, map_smem);
     }
     if (st != PLM_OK) return st;
@@ -1241,10 +1263,12 @@ int dev_grid_setup(plm_ctx *&ctx, const plm_dev_grid_args *a, plm::GridJob &job,
     gp.line_sim_th = a->line_sim_th;
     if ((st = plan_map_grid(ctx, a->n1, a->n2, a->grid_rows * a->grid_cols, a->is_lines != 0, gp, warps, n_cta, smem)) != PLM_OK) return st;
     const size_t cta_min_bytes = align_up(size_t(std::max(n_cta, 1)) * std::max(a->n2, 1) * 2);
-    st = ctx->ensure_device(cta_min_bytes + extra_bytes);
+    const size_t handover = map_grid_handover_bytes(warps, n_cta, gp.rows_per_cta);
+    st = ctx->ensure_device(cta_min_bytes + handover + extra_bytes);
     if (st != PLM_OK) return st;
     gp.cta_min = reinterpret_cast<uint16_t *>(ctx->d_buf);
-    if (extra) *extra = ctx->d_buf + cta_min_bytes;
+    map_grid_handover_bind(gp, ctx->d_buf + cta_min_bytes, warps, n_cta, gp.best_lr != 0);
+    if (extra) *extra = ctx->d_buf + cta_min_bytes + handover;
     return PLM_OK;
 }
 
