@@ -62,12 +62,33 @@ def frame_latency(ctx) -> dict:
         }
     for k in gpu:
         out[k] = {"gpu_ms": _median_ms(gpu[k]), "cpu_ms": _median_ms(cpu[k], reps=10, warm=2)}
-    out["per_frame_total_gpu_ms"] = sum(v["gpu_ms"] for v in out.values() if isinstance(v, dict))
-    out["per_frame_total_cpu_ms"] = sum(v["cpu_ms"] for v in out.values() if isinstance(v, dict))
+    out["per_frame_total_gpu_ms"] = sum(v["gpu_ms"] for v in out.values() if isinstance(v, dict) and "gpu_ms" in v)
+    out["per_frame_total_cpu_ms"] = sum(v["cpu_ms"] for v in out.values() if isinstance(v, dict) and "cpu_ms" in v)
     out["cpu_kind"] = "reference (matching.cpp, its own 2 std::async threads for match)" if ref else "port (scalar C)"
     out["note"] = ("wall clock per host-buffer call incl. ctypes, pinned staging, H2D, kernels, D2H and the "
                    "stream sync; includes the Python binding overhead on both sides")
     out["gpu_launches"] = ctx.launch_count - launches0
+    # the same four calls at the reference's C++ signature level (StVO::matchGrid / match with cv::Mat, GridStructure,
+    # std::vector<int>&): the GPU drop-in (libstvo_gpu.so: GridStructure -> CSR flattening, staging, copies and sync
+    # inside the number) next to the reference's own matching.cpp, timed by the same C++ harness, no Python in the loop
+    try:
+        dropin = oracle.stvo_gpu
+        if ref and dropin.available():
+            ref.set_config(True, True, 0.9, 0.75)
+            dropin.set_config(True, True, 0.9, 0.75)
+            sig = {}
+            for tag, eng in (("gpu_dropin_us", dropin), ("cpu_reference_us", ref)):
+                reps = 100 if tag.startswith("gpu") else 15
+                sig[tag] = {
+                    "stereo_matchGrid_points_600": eng.time_match_grid(a["xy"], a["d1"], a["cell_start"], a["cell_items"], a["rows"], a["cols"], a["d2"], a["win"], reps=reps),
+                    "stereo_matchGrid_lines_200": eng.time_match_grid(b["xyxy"], b["d1"], b["cell_start"], b["cell_items"], b["rows"], b["cols"], b["d2"], b["win"], dirs2=b["dirs2"], reps=reps),
+                    "temporal_match_points_600": eng.time_match(prev.pdesc_l, curr.pdesc_l, 0.9, reps=reps),
+                    "temporal_match_lines_200": eng.time_match(prev.ldesc_l, curr.ldesc_l, 0.9, reps=reps),
+                }
+                sig[tag]["per_frame_total"] = sum(sig[tag].values())
+            out["stvo_signature_level"] = sig
+    except Exception as e:  # noqa: BLE001
+        out["stvo_signature_level"] = {"error": repr(e)[:200]}
     return out
 
 

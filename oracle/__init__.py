@@ -453,6 +453,30 @@ class _Ref:
                                 med_idx.ctypes.data_as(_i32p), med_dir.ctypes.data_as(_f64p))
         return med_idx, med_dir
 
+    def time_match(self, d1, d2, nnr, reps=100) -> float:
+        """Median microseconds of StVO::match at the C++ signature level (reference build or GPU drop-in)."""
+        p1, n1, s1 = _desc(np.ascontiguousarray(d1))
+        p2, n2, s2 = _desc(np.ascontiguousarray(d2))
+        self.lib.plref_time_match.restype = C.c_double
+        self.lib.plref_time_match.argtypes = [_u8p, C.c_int, C.c_size_t, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_int]
+        return float(self.lib.plref_time_match(p1, n1, s1, p2, n2, s2, C.c_float(nnr), int(reps)))
+
+    def time_match_grid(self, coords, d1, cell_start, cell_items, rows, cols, d2, win, dirs2=None, reps=100) -> float:
+        """Median microseconds of StVO::matchGrid (points or, with dirs2, lines) for a prebuilt GridStructure."""
+        is_lines = dirs2 is not None
+        co, cop = _i32(np.ascontiguousarray(coords, np.int32).reshape(-1))
+        p1, n1, s1 = _desc(np.ascontiguousarray(d1))
+        p2, n2, s2 = _desc(np.ascontiguousarray(d2))
+        cs, csp = _i32(cell_start)
+        ci, cip = _i32(cell_items if len(cell_items) else np.zeros(1, np.int32))
+        w, wp = _i32(win)
+        dr = None if dirs2 is None else np.ascontiguousarray(dirs2, np.float64)
+        self.lib.plref_time_match_grid.restype = C.c_double
+        self.lib.plref_time_match_grid.argtypes = [C.c_int, _i32p, _u8p, C.c_int, C.c_size_t, _i32p, _i32p, C.c_int, C.c_int, _u8p, C.c_int,
+                                                   C.c_size_t, _f64p, _i32p, C.c_int]
+        return float(self.lib.plref_time_match_grid(int(is_lines), cop, p1, n1, s1, csp, cip, int(rows), int(cols), p2, n2, s2,
+                                                    None if dr is None else dr.ctypes.data_as(_f64p), wp, int(reps)))
+
     def set_threads(self, n: int):
         self.lib.plref_set_threads(int(n))
 

@@ -115,6 +115,62 @@ PLREF_API int plref_match_grid_lines(const int32_t *xyxy, const uint8_t *d1, int
     return 0;
 }
 
+// ---- timing at the StVO:: signature level (the same harness is linked against the reference's matching.cpp and
+// against the GPU drop-in, so the two numbers compare what a caller of StVO::matchGrid / match sees: for the drop-in
+// the GridStructure -> CSR flattening, staging, copies and the synchronisation are inside) ----
+#include <algorithm>
+#include <chrono>
+
+namespace {
+template <class F> double median_us(F &&f, int reps) {
+    std::vector<double> t;
+    for (int i = 0; i < 3; i++) f();
+    for (int i = 0; i < reps; i++) {
+        auto a = std::chrono::steady_clock::now();
+        f();
+        t.push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count());
+    }
+    std::sort(t.begin(), t.end());
+    return t.empty() ? 0.0 : t[t.size() / 2];
+}
+} // namespace
+
+PLREF_API double plref_time_match(const uint8_t *d1, int n1, size_t step1, const uint8_t *d2, int n2, size_t step2, float nnr, int reps) {
+    const cv::Mat a = wrap(d1, n1, step1), b = wrap(d2, n2, step2);
+    return median_us([&] {
+        std::vector<int> v;
+        StVO::match(a, b, nnr, v);
+    }, reps);
+}
+
+PLREF_API double plref_time_match_grid(int is_lines, const int32_t *coords, const uint8_t *d1, int n1, size_t step1, const int32_t *cell_start,
+                                       const int32_t *cell_items, int rows, int cols, const uint8_t *d2, int n2, size_t step2,
+                                       const double *dirs2, const int32_t *win, int reps) {
+    StVO::GridStructure grid(rows, cols);
+    fill_grid(grid, cell_start, cell_items);
+    StVO::GridWindow w;
+    w.width = std::make_pair(win[0], win[1]);
+    w.height = std::make_pair(win[2], win[3]);
+    const cv::Mat a = wrap(d1, n1, step1), b = wrap(d2, n2, step2);
+    if (!is_lines) {
+        std::vector<StVO::point_2d> pts(n1);
+        for (int i = 0; i < n1; i++) pts[i] = std::make_pair(coords[2 * i], coords[2 * i + 1]);
+        return median_us([&] {
+            std::vector<int> v;
+            StVO::matchGrid(pts, a, grid, b, w, v);
+        }, reps);
+    }
+    std::vector<StVO::line_2d> lines(n1);
+    for (int i = 0; i < n1; i++)
+        lines[i] = std::make_pair(std::make_pair(coords[4 * i], coords[4 * i + 1]), std::make_pair(coords[4 * i + 2], coords[4 * i + 3]));
+    std::vector<std::pair<double, double>> dirs(n2);
+    for (int i = 0; i < n2; i++) dirs[i] = std::make_pair(dirs2[2 * i], dirs2[2 * i + 1]);
+    return median_us([&] {
+        std::vector<int> v;
+        StVO::matchGrid(lines, a, grid, b, dirs, w, v);
+    }, reps);
+}
+
 // getLineCoords (gridStructure.cpp:33-41): writes up to max_cells (x, y) pairs, returns the count
 PLREF_API int plref_line_coords(double x1, double y1, double x2, double y2, int32_t *cells,
                                 int max_cells) {

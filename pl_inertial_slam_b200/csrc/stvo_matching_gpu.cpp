@@ -66,15 +66,14 @@ void flatten(const StVO::GridStructure &grid, GridCsr &csr) {
             csr.cell_start[static_cast<size_t>(x) * rows + y + 1] = static_cast<int32_t>(csr.cell_items.size());
         }
 #else
-    StVO::GridWindow one;
-    one.width = std::make_pair(0, 0);
-    one.height = std::make_pair(0, 0);
-    std::unordered_set<int> bucket;
+    // GridStructure::at is the reference's own public accessor (gridStructure.h:48); it is not const-qualified although
+    // it only returns a reference to the cell's list, hence the const_cast.  One list walk per cell -- the portable
+    // alternative, get(x, y, {0,0}x{0,0}, unordered_set), costs a hash-set build per cell (3072 per call).
+    StVO::GridStructure &g = const_cast<StVO::GridStructure &>(grid);
     for (int x = 0; x < cols; ++x)
         for (int y = 0; y < rows; ++y) {
-            bucket.clear();
-            grid.get(x, y, one, bucket);
-            csr.cell_items.insert(csr.cell_items.end(), bucket.begin(), bucket.end());
+            const std::list<int> &cell = g.at(x, y);
+            csr.cell_items.insert(csr.cell_items.end(), cell.begin(), cell.end());
             csr.cell_start[static_cast<size_t>(x) * rows + y + 1] = static_cast<int32_t>(csr.cell_items.size());
         }
 #endif
