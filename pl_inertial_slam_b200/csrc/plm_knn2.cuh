@@ -76,6 +76,8 @@ struct KnnTaskPair {
 //            16-LOP3 / 3-POPC lower bound: the blocked test min(...) < thr stays exact (a lower bound can only make the
 //            update path run more often, and that path recomputes those rows exactly), while the XU pipe (POPC), the
 //            binding one in variant 3, does 29 instead of 32 instructions per 8 pairs and the ALU pipe 118 instead of 109.
+// VARIANT 5: the 13-LOP3 distance of variant 3 with the per-pair top-2 update of variant 1 -- for short train sets
+//            (frame-sized calls, per-keyframe-pair batches), where the blocked threshold never gets tight.
 constexpr int KNN_B_ROWS = 3;
 
 template <int VARIANT>
@@ -152,7 +154,7 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
         }
         const uint4 *sb = stage[buf];
         const uint32_t gbase = idx_base + static_cast<uint32_t>(u) * static_cast<uint32_t>(unit_rows);
-        if (VARIANT >= 2) {
+        if (VARIANT >= 2 && VARIANT <= 4) {
             int j = 0;
             for (; j + 8 <= rows; j += 8) {
                 int d[8];

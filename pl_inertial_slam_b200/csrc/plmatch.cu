@@ -78,7 +78,7 @@ struct plm_ctx {
     uint64_t launches = 0;
     bool fused_attr_set = false;
     bool cluster_attr_set = false;
-    int knn_occ[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    int knn_occ[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
     bool rows_attr_set = false;
     // frame session: the calls recorded between plm_frame_begin and plm_frame_end
@@ -229,6 +229,7 @@ int knn_variant_for(int slice_rows) {
         if (e && std::strcmp(e, "csa4") == 0) g_knn_variant = 2;
         if (e && std::strcmp(e, "t13") == 0) g_knn_variant = 3;
         if (e && std::strcmp(e, "mix") == 0) g_knn_variant = 4;
+        if (e && std::strcmp(e, "t13s") == 0) g_knn_variant = 5;
         const char *f = std::getenv("PLM_KNN_FILL"); // measurement knob, same as option "knn_fill"
         if (f) g_knn_fill = std::atoi(f) ? 1 : 0;
     }
@@ -244,13 +245,15 @@ int knn_ctas_per_sm(plm_ctx *ctx, int threads, int variant) {
     cudaError_t e = cudaErrorUnknown;
 #define PLM_KNN_OCC(T, V) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<T, V>, T, 0)
     if (threads == 128) {
-        if (variant == 4) PLM_KNN_OCC(128, 4);
+        if (variant == 5) PLM_KNN_OCC(128, 5);
+        else if (variant == 4) PLM_KNN_OCC(128, 4);
         else if (variant == 3) PLM_KNN_OCC(128, 3);
         else if (variant == 2) PLM_KNN_OCC(128, 2);
         else if (variant == 1) PLM_KNN_OCC(128, 1);
         else PLM_KNN_OCC(128, 0);
     } else {
-        if (variant == 4) PLM_KNN_OCC(64, 4);
+        if (variant == 5) PLM_KNN_OCC(64, 5);
+        else if (variant == 4) PLM_KNN_OCC(64, 4);
         else if (variant == 3) PLM_KNN_OCC(64, 3);
         else if (variant == 2) PLM_KNN_OCC(64, 2);
         else if (variant == 1) PLM_KNN_OCC(64, 1);
@@ -322,13 +325,15 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
     }
 #define PLM_KNN_LAUNCH(T, V) plm::knn2_slice_kernel<T, V><<<grid, T, 0, ctx->stream>>>(tp)
     if (threads == 128) {
-        if (variant == 4) PLM_KNN_LAUNCH(128, 4);
+        if (variant == 5) PLM_KNN_LAUNCH(128, 5);
+        else if (variant == 4) PLM_KNN_LAUNCH(128, 4);
         else if (variant == 3) PLM_KNN_LAUNCH(128, 3);
         else if (variant == 2) PLM_KNN_LAUNCH(128, 2);
         else if (variant == 1) PLM_KNN_LAUNCH(128, 1);
         else PLM_KNN_LAUNCH(128, 0);
     } else {
-        if (variant == 4) PLM_KNN_LAUNCH(64, 4);
+        if (variant == 5) PLM_KNN_LAUNCH(64, 5);
+        else if (variant == 4) PLM_KNN_LAUNCH(64, 4);
         else if (variant == 3) PLM_KNN_LAUNCH(64, 3);
         else if (variant == 2) PLM_KNN_LAUNCH(64, 2);
         else if (variant == 1) PLM_KNN_LAUNCH(64, 1);
@@ -380,7 +385,7 @@ int check_desc(const uint8_t *d, int n, size_t step) {
 PLM_API int plm_set_option(const char *key, int value) {
     if (!key) return fail(PLM_E_INVALID, "null key");
     if (std::strcmp(key, "knn_variant") == 0) {
-        g_knn_variant = (value >= 0 && value <= 4) ? value : -1;
+        g_knn_variant = (value >= 0 && value <= 5) ? value : -1;
         return PLM_OK;
     }
     if (std::strcmp(key, "peer_spin_ms") == 0) {
@@ -2716,10 +2721,16 @@ PLM_API int plm_batch_run(plm_batch *b) {
         if (b->n_slice_ctas == 0) return PLM_OK;
         const plm::KnnTask *tasks = reinterpret_cast<const plm::KnnTask *>(D + b->o_tasks);
         if (b->best_lr && b->m21_bytes) CU_TRY(cudaMemsetAsync(D + b->o_m21, 0xFF, b->m21_bytes, s));
-        if (knn_variant_for(0) == 0)
+        // batches of short train sets (per-keyframe-pair loop closure, replay stages) are throughput work: the 13-LOP3
+        // distance with the per-pair update (variant 5) unless a variant is forced; single calls keep variant 1, whose
+        // stages need no in-place transform (lower latency)
+        const int forced = g_knn_variant;
+        if (forced == 0)
             plm::knn2_slice_list_kernel<BATCH_THREADS, 0><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
-        else
+        else if (forced == 1)
             plm::knn2_slice_list_kernel<BATCH_THREADS, 1><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
+        else
+            plm::knn2_slice_list_kernel<BATCH_THREADS, 5><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
         ctx->launches++;
         CU_TRY(cudaGetLastError());
         plm::knn2_merge_list_kernel<<<b->n_merge_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int2 *>(D + b->o_merge_map), b->nnr, 1);

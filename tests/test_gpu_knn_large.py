@@ -50,7 +50,7 @@ def test_knn2_large_train_sets(M, n1, n2, tie):
     assert (got == want).all(), np.flatnonzero((got != want).any(1))[:10]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("n1,n2", [(300, 66000), (4100, 66000), (200, 3000)])
 def test_knn2_every_variant(M, plm_lib, variant, n1, n2):
     d1, d2 = _case(99 + n1, n1, n2, tie=(variant % 2 == 0))
