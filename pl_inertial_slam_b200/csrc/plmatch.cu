@@ -2724,6 +2724,7 @@ PLM_API int plm_batch_run(plm_batch *b) {
         // batches of short train sets (per-keyframe-pair loop closure, replay stages) are throughput work: the 13-LOP3
         // distance with the per-pair update (variant 5) unless a variant is forced; single calls keep variant 1, whose
         // stages need no in-place transform (lower latency)
+        (void)knn_variant_for(0); // reads PLM_KNN_VARIANT on first use
         const int forced = g_knn_variant;
         if (forced == 0)
             plm::knn2_slice_list_kernel<BATCH_THREADS, 0><<<b->n_slice_ctas, BATCH_THREADS, 0, s>>>(tasks, reinterpret_cast<const int4 *>(D + b->o_cta_map));
