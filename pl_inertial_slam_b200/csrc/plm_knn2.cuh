@@ -197,9 +197,128 @@ __device__ __forceinline__ void knn2_slice_body(const KnnTask &t, int qblock, in
     if (qi < n1) t.part[static_cast<size_t>(worker) * n1 + qi] = make_ulonglong2(B0, B1);
 }
 
+
+// VARIANT 6: variant 3 with TWO queries per thread (a CTA of 128 threads owns 256 queries: thread t holds queries
+// t and t + 128 of its block).  Every train row fetched from shared memory (2 LDS.128) now serves two pairs, and the
+// loop overhead is shared: the MIO queue, through which both the LDS and the POPC instructions issue, sees 16 LDS per
+// 16 pairs instead of per 8.  Same blocked threshold logic per query.
+template <int THREADS>
+__device__ __forceinline__ void knn2_slice_body2(const KnnTask &t, int qblock, int worker, int n_workers, uint4 (*stage)[KNN_STAGE_ROWS * 2]) {
+    const int tid = threadIdx.x;
+    const int n1 = t.n1;
+    int qi[2];
+    Desc a[2];
+    unsigned long long B0[2], B1[2];
+    int thr[2], gcap[2];
+    uint32_t *gthr[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        qi[k] = qblock * (2 * THREADS) + k * THREADS + tid;
+        if (qi[k] < n1) {
+            a[k] = load_desc(t.q, qi[k]);
+        } else {
+            a[k].lo = make_uint4(0, 0, 0, 0);
+            a[k].hi = a[k].lo;
+        }
+        desc_transform13(a[k].lo, a[k].hi);
+        B0[k] = KEY64_ABSENT;
+        B1[k] = KEY64_ABSENT;
+        thr[k] = 1023;
+        gcap[k] = 1023;
+        gthr[k] = (t.gthr && qi[k] < n1) ? t.gthr + qi[k] : nullptr;
+    }
+    const uint4 *db = t.db;
+    const int unit_rows = t.unit_rows, n_units = t.n_units, step = n_workers;
+    const uint32_t idx_base = static_cast<uint32_t>(t.idx_base);
+    auto rows_of = [&](int u) { return static_cast<int>(min(static_cast<long long>(unit_rows), t.n2 - static_cast<long long>(u) * unit_rows)); };
+    auto issue = [&](int u, int buf) {
+        const int rows = rows_of(u);
+        const uint4 *src = db + 2 * (static_cast<long long>(u) * unit_rows);
+        uint4 *dst = stage[buf];
+        for (int i = tid; i < rows * 2; i += THREADS) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    int buf = 0;
+    if (worker < n_units) issue(worker, 0);
+    for (int u = worker; u < n_units; u += step, buf ^= 1) {
+        if (u + step < n_units) {
+            issue(u + step, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int rows = rows_of(u);
+        {
+            uint4 *w = stage[buf];
+            for (int r = tid; r < rows; r += THREADS) {
+                uint4 lo = w[2 * r], hi = w[2 * r + 1];
+                desc_transform13(lo, hi);
+                w[2 * r] = lo;
+                w[2 * r + 1] = hi;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (gthr[k]) {
+                const uint32_t g = *reinterpret_cast<volatile uint32_t *>(gthr[k]);
+                gcap[k] = static_cast<int>(min(g, 1022u)) + 1;
+                thr[k] = min(thr[k], gcap[k]);
+            }
+        const uint4 *sb = stage[buf];
+        const uint32_t gbase = idx_base + static_cast<uint32_t>(u) * static_cast<uint32_t>(unit_rows);
+        auto update = [&](int k, int d, uint32_t row) {
+            top2_insert(B0[k], B1[k], make_key64(d, row));
+        };
+        auto lower = [&](int k) {
+            const int own = (B1[k] == KEY64_ABSENT) ? 1023 : static_cast<int>(B1[k] >> 32);
+            if (gthr[k] && own < 1023) atomicMin(gthr[k], static_cast<uint32_t>(own));
+            thr[k] = min(own, gcap[k]);
+        };
+        int j = 0;
+        for (; j + 8 <= rows; j += 8) {
+            int d0[8], d1[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const uint4 blo = sb[2 * (j + v)], bhi = sb[2 * (j + v) + 1];
+                d0[v] = hamming256_t13(a[0], blo, bhi);
+                d1[v] = hamming256_t13(a[1], blo, bhi);
+            }
+            const int m0 = min(min(min(d0[0], d0[1]), min(d0[2], d0[3])), min(min(d0[4], d0[5]), min(d0[6], d0[7])));
+            const int m1 = min(min(min(d1[0], d1[1]), min(d1[2], d1[3])), min(min(d1[4], d1[5]), min(d1[6], d1[7])));
+            if (m0 < thr[0]) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) update(0, d0[v], gbase + j + v);
+                lower(0);
+            }
+            if (m1 < thr[1]) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) update(1, d1[v], gbase + j + v);
+                lower(1);
+            }
+        }
+        for (; j < rows; ++j) {
+            const uint4 blo = sb[2 * j], bhi = sb[2 * j + 1];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int d = hamming256_t13(a[k], blo, bhi);
+                if (d < thr[k]) {
+                    update(k, d, gbase + j);
+                    lower(k);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (qi[k] < n1) t.part[static_cast<size_t>(worker) * n1 + qi[k]] = make_ulonglong2(B0[k], B1[k]);
+}
+
 // 1-D grid over (task, query block, worker): both directions of StVO::match in one launch.
 template <int THREADS, int VARIANT>
-__global__ void __launch_bounds__(THREADS, (THREADS == 128) ? 9 : 12) knn2_slice_kernel(const KnnTaskPair tasks) {
+__global__ void __launch_bounds__(THREADS, (VARIANT == 6) ? 6 : ((THREADS == 128) ? 9 : 12)) knn2_slice_kernel(const KnnTaskPair tasks) {
     __shared__ __align__(16) uint4 stage[2][KNN_STAGE_ROWS * 2];
     const int which = static_cast<int>(blockIdx.x) >= tasks.cta_split ? 1 : 0;
     const KnnTask &t = tasks.t[which];
@@ -212,7 +331,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128) ? 9 : 12) knn2_slice
         local -= wide;
         qb0 = t.extra_qb;
     }
-    knn2_slice_body<THREADS, VARIANT>(t, qb0 + local / nw, local % nw, nw, stage);
+    if (VARIANT == 6) knn2_slice_body2<THREADS>(t, qb0 + local / nw, local % nw, nw, stage);
+    else knn2_slice_body<THREADS, VARIANT == 6 ? 3 : VARIANT>(t, qb0 + local / nw, local % nw, nw, stage);
 }
 
 // Batched form: cta_map[cta] = (task, qblock, worker); tasks live in device memory.

@@ -78,7 +78,7 @@ struct plm_ctx {
     uint64_t launches = 0;
     bool fused_attr_set = false;
     bool cluster_attr_set = false;
-    int knn_occ[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    int knn_occ[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
     bool rows_attr_set = false;
     // frame session: the calls recorded between plm_frame_begin and plm_frame_end
@@ -202,6 +202,7 @@ struct KnnPlan {
     int unit_rows = plm::KNN_STAGE_ROWS;
     int n_units = 1;
     int n_workers = 1;
+    int qpb = 128;        // queries per CTA (threads, or 2 x threads in the two-queries-per-thread form)
     int extra_qb = 0;     // query blocks with n_workers + 1 workers (fills the last resident CTA slots)
     bool share_thr = false; // long scans: the workers of a query share their second-best bound
 };
@@ -215,6 +216,7 @@ int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame 
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 2; // single matchGrid calls: 2 = row-parallel kernel on one cluster, 1 = chunk kernel on an 8-CTA cluster, 0 = one CTA
 long long g_peer_spin_ticks = 4000000000ll; // bounded spin of the peer-memory kernels (~2 s of SM clock); option "peer_spin_ms"
+int g_knn_qpt = 1;      // 2: long scans with >= 8192 queries keep two queries per thread (variant 6); option "knn_qpt"
 int g_knn_fill = 1;     // long brute-force scans: uneven workers fill every CTA slot + shared second-best bound (0: off, measurement)
 int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
 
@@ -232,6 +234,8 @@ int knn_variant_for(int slice_rows) {
         if (e && std::strcmp(e, "t13s") == 0) g_knn_variant = 5;
         const char *f = std::getenv("PLM_KNN_FILL"); // measurement knob, same as option "knn_fill"
         if (f) g_knn_fill = std::atoi(f) ? 1 : 0;
+        const char *q2 = std::getenv("PLM_KNN_QPT");
+        if (q2) g_knn_qpt = std::atoi(q2) == 2 ? 2 : 1;
     }
     if (g_knn_variant >= 0) return g_knn_variant;
     return slice_rows >= 2048 ? 3 : 1;
@@ -245,7 +249,8 @@ int knn_ctas_per_sm(plm_ctx *ctx, int threads, int variant) {
     cudaError_t e = cudaErrorUnknown;
 #define PLM_KNN_OCC(T, V) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plm::knn2_slice_kernel<T, V>, T, 0)
     if (threads == 128) {
-        if (variant == 5) PLM_KNN_OCC(128, 5);
+        if (variant == 6) PLM_KNN_OCC(128, 6);
+        else if (variant == 5) PLM_KNN_OCC(128, 5);
         else if (variant == 4) PLM_KNN_OCC(128, 4);
         else if (variant == 3) PLM_KNN_OCC(128, 3);
         else if (variant == 2) PLM_KNN_OCC(128, 2);
@@ -268,11 +273,14 @@ int knn_ctas_per_sm(plm_ctx *ctx, int threads, int variant) {
 // workers per query block as fit on the chip at once: one wave of co-resident CTAs, no last-wave tail,
 // W partials per query.  Frame-sized problems get narrow CTAs and small units so that a single call
 // still spreads over the whole chip.
-KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2) {
+KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2, bool allow_two = false) {
     KnnPlan p;
     p.threads = (n1 >= 4096) ? 128 : 64;
-    const long long qblocks = std::max<long long>(1, (n1 + p.threads - 1) / p.threads);
-    const int variant = knn_variant_for(n2 >= 65536 ? 4096 : 64);
+    int variant = knn_variant_for(n2 >= 65536 ? 4096 : 64);
+    // long scans with many queries: two queries per thread (variant 6), single-direction launches only
+    if (allow_two && variant == 3 && g_knn_qpt == 2 && p.threads == 128 && n1 >= 8192) variant = 6;
+    p.qpb = (variant == 6) ? 2 * p.threads : p.threads;
+    const long long qblocks = std::max<long long>(1, (n1 + p.qpb - 1) / p.qpb);
     const long long capacity = static_cast<long long>(ctx->sm_count) * knn_ctas_per_sm(ctx, p.threads, variant);
     const long long want = std::max<long long>(1, capacity / qblocks); // workers per query block
     long long rows = (n2 + want - 1) / want;
@@ -292,7 +300,8 @@ KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2) {
 int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threads) {
     long long total = 0;
     for (int i = 0; i < n_tasks; ++i) {
-        const long long c = static_cast<long long>((tp.t[i].n1 + threads - 1) / threads) * tp.t[i].n_workers + tp.t[i].extra_qb;
+        const int qpb = tp.t[i].threads > 0 ? tp.t[i].threads : threads; // queries per CTA of this task
+        const long long c = static_cast<long long>((tp.t[i].n1 + qpb - 1) / qpb) * tp.t[i].n_workers + tp.t[i].extra_qb;
         if (i == 0) tp.cta_split = static_cast<int>(c);
         total += c;
     }
@@ -302,7 +311,8 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
     const dim3 grid(static_cast<unsigned>(total), 1, 1);
     int min_rows = INT_MAX;
     for (int i = 0; i < n_tasks; ++i) min_rows = std::min<long long>(min_rows, std::min<long long>(tp.t[i].n2, INT_MAX));
-    const int variant = knn_variant_for(min_rows >= 65536 ? 4096 : 64);
+    int variant = knn_variant_for(min_rows >= 65536 ? 4096 : 64);
+    if (n_tasks == 1 && tp.t[0].threads == 2 * threads) variant = 6; // planned with two queries per thread
     if (variant >= 2 && g_knn_fill) {
         // the shared second-best bounds live behind each task's partial results (build_knn_task reserved the room)
         for (int i = 0; i < n_tasks; ++i) {
@@ -325,7 +335,8 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
     }
 #define PLM_KNN_LAUNCH(T, V) plm::knn2_slice_kernel<T, V><<<grid, T, 0, ctx->stream>>>(tp)
     if (threads == 128) {
-        if (variant == 5) PLM_KNN_LAUNCH(128, 5);
+        if (variant == 6) PLM_KNN_LAUNCH(128, 6);
+        else if (variant == 5) PLM_KNN_LAUNCH(128, 5);
         else if (variant == 4) PLM_KNN_LAUNCH(128, 4);
         else if (variant == 3) PLM_KNN_LAUNCH(128, 3);
         else if (variant == 2) PLM_KNN_LAUNCH(128, 2);
@@ -390,6 +401,10 @@ PLM_API int plm_set_option(const char *key, int value) {
     }
     if (std::strcmp(key, "peer_spin_ms") == 0) {
         g_peer_spin_ticks = static_cast<long long>(std::max(1, value)) * 2000000ll; // ~2 GHz SM clock
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "knn_qpt") == 0) {
+        g_knn_qpt = value == 2 ? 2 : 1;
         return PLM_OK;
     }
     if (std::strcmp(key, "knn_fill") == 0) {
@@ -577,8 +592,8 @@ struct KnnScratch {
 };
 
 int build_knn_task(plm_ctx *ctx, Layout &L, plm::KnnTask &t, KnnPlan &plan, const uint4 *q, int n1, const uint4 *db,
-                   long long n2, unsigned long long idx_base, size_t &part_off) {
-    plan = plan_knn(ctx, n1, n2);
+                   long long n2, unsigned long long idx_base, size_t &part_off, bool allow_two = false) {
+    plan = plan_knn(ctx, n1, n2, allow_two);
     t.q = q;
     t.db = db;
     t.n1 = n1;
@@ -588,7 +603,7 @@ int build_knn_task(plm_ctx *ctx, Layout &L, plm::KnnTask &t, KnnPlan &plan, cons
     t.n_units = plan.n_units;
     t.n_workers = plan.n_workers;
     t.extra_qb = plan.extra_qb;
-    t.threads = plan.threads;
+    t.threads = plan.qpb;
     t.part = nullptr;
     t.top2 = nullptr;
     t.m = nullptr;
@@ -617,7 +632,7 @@ PLM_API int plm_dev_knn2(plm_ctx *ctx, const void *d1_dev, int n1, const void *d
     KnnPlan plan;
     size_t part_off = 0;
     build_knn_task(ctx, L, tp.t[0], plan, static_cast<const uint4 *>(d1_dev), n1, static_cast<const uint4 *>(d2_dev), n2,
-                   idx_base, part_off);
+                   idx_base, part_off, true);
     if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
     tp.t[0].part = reinterpret_cast<ulonglong2 *>(ctx->d_buf + part_off);
     tp.t[0].top2 = reinterpret_cast<ulonglong2 *>(top2_dev);
@@ -685,7 +700,7 @@ PLM_API int plm_knn2(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, cons
     std::memset(&tp, 0, sizeof(tp));
     KnnPlan plan;
     size_t part_off = 0;
-    build_knn_task(ctx, L, tp.t[0], plan, nullptr, n1, nullptr, n2, idx_base, part_off);
+    build_knn_task(ctx, L, tp.t[0], plan, nullptr, n1, nullptr, n2, idx_base, part_off, true);
     if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
     if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
     pack_rows(ctx->h_buf + o_d1, d1, n1, step1);
@@ -740,7 +755,7 @@ static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, con
     std::memset(&tp, 0, sizeof(tp));
     KnnPlan plan[2];
     size_t part_off[2] = {0, 0};
-    build_knn_task(ctx, L, tp.t[0], plan[0], nullptr, n1, nullptr, n2, 0, part_off[0]);
+    build_knn_task(ctx, L, tp.t[0], plan[0], nullptr, n1, nullptr, n2, 0, part_off[0], !best_lr);
     if (best_lr) build_knn_task(ctx, L, tp.t[1], plan[1], nullptr, n2, nullptr, n1, 0, part_off[1]);
     (void)staged;
     if (phase == EXEC_SIZE) {
@@ -2290,7 +2305,7 @@ PLM_API int plm_db_knn2(plm_db *db, const uint8_t *q, int nq, size_t step, uint6
     std::memset(&tp, 0, sizeof(tp));
     KnnPlan plan;
     size_t part_off = 0;
-    build_knn_task(ctx, L, tp.t[0], plan, nullptr, nq, db->rows, db->size, idx_base, part_off);
+    build_knn_task(ctx, L, tp.t[0], plan, nullptr, nq, db->rows, db->size, idx_base, part_off, true);
     if ((st = ctx->ensure_pinned(staged)) != PLM_OK) return st;
     if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
     pack_rows(ctx->h_buf + o_q, q, nq, step);
