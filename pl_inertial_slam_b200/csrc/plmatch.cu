@@ -216,7 +216,7 @@ int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame 
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 2; // single matchGrid calls: 2 = row-parallel kernel on one cluster, 1 = chunk kernel on an 8-CTA cluster, 0 = one CTA
 long long g_peer_spin_ticks = 4000000000ll; // bounded spin of the peer-memory kernels (~2 s of SM clock); option "peer_spin_ms"
-int g_knn_qpt = 1;      // 2: long scans with >= 8192 queries keep two queries per thread (variant 6); option "knn_qpt"
+int g_knn_qpt = 1;      // 2: long scans with >= 4096 queries keep two queries per thread (variant 6); option "knn_qpt"
 int g_knn_fill = 1;     // long brute-force scans: uneven workers fill every CTA slot + shared second-best bound (0: off, measurement)
 int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
 
@@ -278,7 +278,7 @@ KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2, bool allow_two = false) {
     p.threads = (n1 >= 4096) ? 128 : 64;
     int variant = knn_variant_for(n2 >= 65536 ? 4096 : 64);
     // long scans with many queries: two queries per thread (variant 6), single-direction launches only
-    if (allow_two && variant == 3 && g_knn_qpt == 2 && p.threads == 128 && n1 >= 8192) variant = 6;
+    if (allow_two && variant == 3 && g_knn_qpt == 2 && p.threads == 128) variant = 6;
     p.qpb = (variant == 6) ? 2 * p.threads : p.threads;
     const long long qblocks = std::max<long long>(1, (n1 + p.qpb - 1) / p.qpb);
     const long long capacity = static_cast<long long>(ctx->sm_count) * knn_ctas_per_sm(ctx, p.threads, variant);

@@ -63,6 +63,24 @@ def test_knn2_every_variant(M, plm_lib, variant, n1, n2):
     assert (got == want).all()
 
 
+@pytest.mark.parametrize("n1,n2,tie", [(4100, 70003, False), (4096, 65536, True), (9001, 66001, False), (4097, 131072, True)])
+def test_knn2_two_queries_per_thread(M, plm_lib, n1, n2, tie):
+    """Option knn_qpt = 2: knn2_slice_kernel<128, 6> (a CTA owns 256 queries, thread t the queries t and t + 128);
+    ragged query blocks (n1 % 256 in {4, 0, 41, 1}) and ragged train tails."""
+    d1, d2 = _case(555 + n1, n1, n2, tie)
+    want = port.knn2_packed(d1, d2, idx_base=3)
+    assert plm_lib.plm_set_option(b"knn_qpt", 2) == 0
+    try:
+        got = M.knn2(d1, d2, idx_base=3)
+        m_g = np.full(n1, -1, np.int32)
+        n_g = M.matchNNR(d1, d2, 0.8, m_g)
+    finally:
+        plm_lib.plm_set_option(b"knn_qpt", 1)
+    assert (got == want).all(), np.flatnonzero((got != want).any(1))[:10]
+    n_o, m_o = port.match_nnr(d1, d2, 0.8)
+    assert n_g == n_o and (m_g == m_o).all()
+
+
 @pytest.mark.parametrize("n1,n2", [(300, 70000), (4100, 70000)])
 @pytest.mark.parametrize("nnr", [0.75, 0.9])
 def test_match_nnr_large_vs_reference(M, n1, n2, nnr):
