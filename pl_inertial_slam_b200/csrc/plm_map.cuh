@@ -68,10 +68,33 @@ __device__ __forceinline__ double med_dir_component(const double *__restrict__ d
     return __ddiv_rn(s, static_cast<double>(n));
 }
 
+// Batcher's odd-even merge sort as a comparator network over a register array (19 / 63 / 191 comparators for 8 / 16 /
+// 32 inputs; explicit lists generated and 0-1-verified by tools/gen_sort_networks.py).  Only d[G / 2] is read afterwards,
+// so the compiler drops the comparators (and the min or max halves) that output does not depend on.
+#include "plm_sort_networks.inc"
+#define PLM_CE(A, B)                  \
+    {                                 \
+        const int x = d[A], y = d[B]; \
+        d[A] = min(x, y);             \
+        d[B] = max(x, y);             \
+    }
+__device__ __forceinline__ void med_sort_network(int (&d)[8]) { PLM_SORT_NET_8(PLM_CE) }
+__device__ __forceinline__ void med_sort_network(int (&d)[16]) { PLM_SORT_NET_16(PLM_CE) }
+__device__ __forceinline__ void med_sort_network(int (&d)[32]) { PLM_SORT_NET_32(PLM_CE) }
+#undef PLM_CE
+
 // One pass of a warp over 32 / G landmarks, G lanes each (G = 8, 16 or 32): sub-lane i of a group owns observation i
-// and keeps the G distances of its row in REGISTERS (every loop below is unrolled over compile-time indices).
+// and keeps the distances of its row in REGISTERS (every loop below is unrolled over compile-time indices).
 // `n` / `lo` are this lane's group values (n = 0 for a group without a landmark in this pass; lists longer than G
 // never get here); `nmax` is the warp-uniform maximum of n over the groups of the pass.
+//
+// Every pair once: lane i computes d(i, i + k mod n) for k = 1 .. n / 2 and receives d(i - k mod n, i) from lane
+// i - k by shuffle (k = 1 .. (n - 1) / 2), so a row of n entries costs n / 2 Hamming distances instead of n.  The row
+// (self distance 0 included, mapFeatures.cpp:66-76) is a multiset -- its order does not matter to the sort.
+//
+// Selection instead of a full sort: the wanted element sits at sorted position r = int(1 + 0.5 * (n - 1)) of the n
+// real entries (mapFeatures.cpp:79).  The G - n unused slots are filled with G / 2 - r pads below every distance (-1)
+// and the rest above (0x7FFF), which puts the wanted element at the FIXED position G / 2 of the sorted array.
 template <int G>
 __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, long long lm, long long lo, int n, int nmax,
                                               bool valid) {
@@ -89,41 +112,31 @@ __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, lo
     }
     int best = n > 0 ? 0 : -1;
     if (nmax >= 2) {
-        // distances of row `sl` to every row j of its own landmark (L1-resident re-read of row j; the 4-POPC
-        // carry-save form keeps the POPC pipe, 16 lanes/clk/SM, from binding); 0xFFFF pads the row to G entries
         int d[G];
+        d[0] = 0; // self distance
+        const int h = (n - 1) >> 1;           // offsets +-1 .. +-h are seen from both sides
+        const int pads_lo = G / 2 - (1 + h);  // med_rank(n) == 1 + h
+        const int gbase = lane - sl;
+        auto pad = [&](int s) { return (s - n < pads_lo) ? -1 : 0x7FFF; };
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            d[j] = 0xFFFF;
-            if (j < nmax) { // warp-uniform
-                if (j < n) {
-                    const Desc t = load_desc(a.desc, lo + j);
-                    d[j] = hamming256_csa4(q, t.lo, t.hi);
+        for (int k = 1; k <= G / 2; ++k) {
+            int own = 0, recv = 0;
+            if (2 * k <= nmax) { // warp-uniform
+                if (sl < n && 2 * k <= n) {
+                    int j = sl + k;
+                    j -= (j >= n) ? n : 0;
+                    const Desc t = load_desc(a.desc, lo + j); // L1-resident: the owner lane fetched this row above
+                    own = hamming256_csa4(q, t.lo, t.hi);
                 }
+                int src = sl - k;
+                src += (src < 0) ? n : 0;
+                recv = __shfl_sync(0xFFFFFFFFu, own, gbase + (src & (G - 1)));
             }
+            d[2 * k - 1] = (2 * k - 1 < n) ? own : pad(2 * k - 1);
+            if (2 * k < G) d[2 * k] = (2 * k < n) ? recv : pad(2 * k);
         }
-        // bitonic sorting network over the register row (ascending; the pads sink to the end)
-#pragma unroll
-        for (int k = 2; k <= G; k <<= 1) {
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-                for (int i = 0; i < G; ++i) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const int x = d[i], y = d[l];
-                        const bool up = (i & k) == 0;
-                        d[i] = up ? min(x, y) : max(x, y);
-                        d[l] = up ? max(x, y) : min(x, y);
-                    }
-                }
-            }
-        }
-        // the element at sorted position int(1 + 0.5*(n-1)) (mapFeatures.cpp:79)
-        const int rank = med_rank(n);
-        int med = d[0];
-#pragma unroll
-        for (int j = 1; j < G; ++j) med = (j == rank) ? d[j] : med;
+        med_sort_network(d);
+        const int med = d[G / 2];
         uint32_t key = (sl < n && n >= 2) ? (static_cast<uint32_t>(med) << 5) | sl : KEY32_ABSENT;
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
@@ -157,60 +170,97 @@ __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, lo
     }
 }
 
-// A warp takes 4 consecutive landmarks and packs them by the longest list among them: 4 x 8 lanes, 2 x 16 lanes
-// (two passes) or 1 x 32 lanes (four passes).
+// The g-th (0-based) set bit of `m`, or -1.
+__device__ __forceinline__ int med_nth_bit(unsigned m, int g) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+        if (t < g) m &= m - 1;
+    return m ? __ffs(m) - 1 : -1;
+}
+
+// A warp takes a chunk of 32 consecutive landmarks (lane l reads the offsets of landmark 32 * chunk + l -- one coalesced
+// request), sorts them into three classes by list length and works each class off at its own packing: 4 landmarks x 8
+// lanes for lists of <= 8 observations, 2 x 16 for <= 16, 1 x 32 for <= 32.  (Packing by the longest list of 4
+// NEIGHBOURS put 86 % of a Poisson(8) map into the 16-lane form.)  Longer lists go to the work list of
+// med_desc_cta_kernel.
 __global__ void __launch_bounds__(32 * MED_WARPS) med_desc_warp_kernel(MedArgs a) {
     __shared__ double sdir_all[MED_WARPS][32 * 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *sdir = sdir_all[warp];
-    const long long n_blocks = (static_cast<long long>(a.n_lm) + 3) / 4;
+    const long long n_chunks = (static_cast<long long>(a.n_lm) + 31) / 32;
     const long long stride = static_cast<long long>(gridDim.x) * MED_WARPS;
-    // lanes read the offsets of the block's 4 landmarks; the next block's are fetched one iteration ahead
-    auto fetch = [&](long long blk, long long &lo, long long &n) {
-        const long long my_lm = blk * 4 + (lane & 3);
+    auto fetch = [&](long long chunk, long long &lo, int &n) {
+        const long long my_lm = chunk * 32 + lane;
         lo = 0;
         n = -2; // past the end
-        if (blk < n_blocks && my_lm < a.n_lm) {
+        if (chunk < n_chunks && my_lm < a.n_lm) {
             lo = __ldg(a.obs_start + my_lm);
-            n = static_cast<long long>(__ldg(a.obs_start + my_lm + 1)) - lo;
+            const long long len = static_cast<long long>(__ldg(a.obs_start + my_lm + 1)) - lo;
+            n = (lo < 0 || len < 0 || lo + len > a.n_obs) ? 0 : static_cast<int>(min(len, 1LL << 30)); // malformed: empty
         }
     };
-    long long blk = static_cast<long long>(blockIdx.x) * MED_WARPS + warp;
-    long long nx_lo, nx_n;
-    fetch(blk, nx_lo, nx_n);
-    for (; blk < n_blocks; blk += stride) {
-        long long my_lo = nx_lo, my_n = nx_n;
-        fetch(blk + stride, nx_lo, nx_n);
-        if (my_n > -2) {
-            if (my_lo < 0 || my_n < 0 || my_lo + my_n > a.n_obs) my_n = 0; // malformed range: treated as empty
-            if (my_n > 32) {
-                if (lane < 4) a.work[1 + atomicAdd(a.work, 1)] = static_cast<int32_t>(blk * 4 + lane);
-                my_n = -1; // handled by med_desc_cta_kernel
+    long long chunk = static_cast<long long>(blockIdx.x) * MED_WARPS + warp;
+    long long nx_lo;
+    int nx_n;
+    fetch(chunk, nx_lo, nx_n);
+    for (; chunk < n_chunks; chunk += stride) {
+        const long long my_lo = nx_lo;
+        const int my_n = nx_n;
+        // the chunk's observations are one contiguous range of the arenas: ask L2 for all of it now, the passes below
+        // then wait on L2, not on HBM
+        {
+            const long long first = __shfl_sync(0xFFFFFFFFu, my_lo, 0);
+            const unsigned live = __ballot_sync(0xFFFFFFFFu, my_n >= 0);
+            const int last_lane = 31 - __clz(live | 1u);
+            const long long end = __shfl_sync(0xFFFFFFFFu, my_lo + max(my_n, 0), last_lane);
+            const char *p0 = reinterpret_cast<const char *>(a.desc) + first * 32;
+            const long long bytes = min((end - first) * 32, 64LL * 1024);
+            for (long long o = static_cast<long long>(lane) * 128; o < bytes; o += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+            if (a.dirs && a.med_dir) {
+                const char *p1 = reinterpret_cast<const char *>(a.dirs) + first * 24;
+                const long long b1 = min((end - first) * 24, 64LL * 1024);
+                for (long long o = static_cast<long long>(lane) * 128; o < b1; o += 32 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + o));
             }
         }
-        int nmax = static_cast<int>(my_n);
-        nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, 1));
-        nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, 2));
-        nmax = __shfl_sync(0xFFFFFFFFu, nmax, 0);
-        if (nmax <= 8) {
-            const int g = lane >> 3;
-            const int n = static_cast<int>(__shfl_sync(0xFFFFFFFFu, my_n, g));
-            const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, g);
-            med_desc_pass<8>(a, sdir, blk * 4 + g, lo, max(n, 0), nmax, n >= 0);
-        } else if (nmax <= 16) {
-            for (int pass = 0; pass < 2; ++pass) {
-                const int g = 2 * pass + (lane >> 4);
-                const int n = static_cast<int>(__shfl_sync(0xFFFFFFFFu, my_n, g));
-                const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, g);
-                const int pmax = max(n, __shfl_xor_sync(0xFFFFFFFFu, n, 16));
-                med_desc_pass<16>(a, sdir, blk * 4 + g, lo, max(n, 0), pmax, n >= 0);
-            }
-        } else {
-            for (int pass = 0; pass < 4; ++pass) {
-                const int n = static_cast<int>(__shfl_sync(0xFFFFFFFFu, my_n, pass));
-                const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, pass);
-                if (n >= 0) med_desc_pass<32>(a, sdir, blk * 4 + pass, lo, n, n, true);
-            }
+        fetch(chunk + stride, nx_lo, nx_n);
+        const unsigned m_long = __ballot_sync(0xFFFFFFFFu, my_n > 32);
+        if (m_long) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(a.work, __popc(m_long));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (my_n > 32) a.work[1 + base + __popc(m_long & ((1u << lane) - 1))] = static_cast<int32_t>(chunk * 32 + lane);
+        }
+        unsigned m8 = __ballot_sync(0xFFFFFFFFu, my_n >= 0 && my_n <= 8);
+        unsigned m16 = __ballot_sync(0xFFFFFFFFu, my_n > 8 && my_n <= 16);
+        unsigned m32 = __ballot_sync(0xFFFFFFFFu, my_n > 16 && my_n <= 32);
+        while (m8) {
+            const int src = med_nth_bit(m8, lane >> 3);
+            const int n_src = __shfl_sync(0xFFFFFFFFu, my_n, src & 31);
+            const int n = src >= 0 ? n_src : 0;
+            const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, src & 31);
+            const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+            med_desc_pass<8>(a, sdir, chunk * 32 + src, lo, n, nmax, src >= 0);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) m8 &= m8 - 1;
+        }
+        while (m16) {
+            const int src = med_nth_bit(m16, lane >> 4);
+            const int n_src = __shfl_sync(0xFFFFFFFFu, my_n, src & 31);
+            const int n = src >= 0 ? n_src : 0;
+            const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, src & 31);
+            const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+            med_desc_pass<16>(a, sdir, chunk * 32 + src, lo, n, nmax, src >= 0);
+            m16 &= m16 - 1;
+            m16 &= m16 - 1;
+        }
+        while (m32) {
+            const int src = __ffs(m32) - 1;
+            const int n = __shfl_sync(0xFFFFFFFFu, my_n, src);
+            const long long lo = __shfl_sync(0xFFFFFFFFu, my_lo, src);
+            med_desc_pass<32>(a, sdir, chunk * 32 + src, lo, n, n, true);
+            m32 &= m32 - 1;
         }
     }
 }

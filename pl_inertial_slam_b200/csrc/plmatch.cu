@@ -1533,7 +1533,7 @@ namespace {
 // Both launches of a batch; `work` (1 + n_lm int32) is scratch for the list of long observation lists.
 int launch_med_desc(plm_ctx *ctx, plm::MedArgs a) {
     CU_TRY(cudaMemsetAsync(a.work, 0, 4, ctx->stream));
-    const int per_cta = 4 * plm::MED_WARPS; // a warp takes 4 landmarks at a time
+    const int per_cta = 32 * plm::MED_WARPS; // a warp takes a chunk of 32 landmarks at a time
     const int ctas = std::min((a.n_lm + per_cta - 1) / per_cta, ctx->sm_count * 32);
     plm::med_desc_warp_kernel<<<ctas, 32 * plm::MED_WARPS, 0, ctx->stream>>>(a);
     ctx->launches++;
