@@ -93,8 +93,9 @@ __device__ __forceinline__ void med_sort_network(int (&d)[32]) { PLM_SORT_NET_32
 // (self distance 0 included, mapFeatures.cpp:66-76) is a multiset -- its order does not matter to the sort.
 //
 // Selection instead of a full sort: the wanted element sits at sorted position r = int(1 + 0.5 * (n - 1)) of the n
-// real entries (mapFeatures.cpp:79).  The G - n unused slots are filled with G / 2 - r pads below every distance (-1)
-// and the rest above (0x7FFF), which puts the wanted element at the FIXED position G / 2 of the sorted array.
+// real entries (mapFeatures.cpp:79); the G - n unused slots hold 0x7FFF and sink to the end.  The classes are cut so
+// that r is one of G / 4 positions (lists of a 16- or 32-lane pass have n > G / 2), and only those outputs of the
+// network are read -- the compiler prunes the comparators that none of them depends on.
 template <int G>
 __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, long long lm, long long lo, int n, int nmax,
                                               bool valid) {
@@ -113,30 +114,38 @@ __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, lo
     int best = n > 0 ? 0 : -1;
     if (nmax >= 2) {
         int d[G];
-        d[0] = 0; // self distance
-        const int h = (n - 1) >> 1;           // offsets +-1 .. +-h are seen from both sides
-        const int pads_lo = G / 2 - (1 + h);  // med_rank(n) == 1 + h
+        d[0] = (sl < n) ? 0 : 0x7FFF; // self distance
         const int gbase = lane - sl;
-        auto pad = [&](int s) { return (s - n < pads_lo) ? -1 : 0x7FFF; };
+        const uint4 *rows = a.desc + 2 * lo;
 #pragma unroll
         for (int k = 1; k <= G / 2; ++k) {
-            int own = 0, recv = 0;
+            int own = 0x7FFF, recv = 0x7FFF;
             if (2 * k <= nmax) { // warp-uniform
-                if (sl < n && 2 * k <= n) {
-                    int j = sl + k;
-                    j -= (j >= n) ? n : 0;
-                    const Desc t = load_desc(a.desc, lo + j); // L1-resident: the owner lane fetched this row above
-                    own = hamming256_csa4(q, t.lo, t.hi);
+                const bool act = sl < n && 2 * k <= n;
+                int j = sl + k;
+                j -= (j >= n) ? n : 0;
+                Desc t = q;
+                if (act) { // L1-resident: the owner lane fetched this row above
+                    t.lo = __ldg(rows + 2 * j);
+                    t.hi = __ldg(rows + 2 * j + 1);
                 }
+                const int dist = hamming256_csa4(q, t.lo, t.hi);
+                own = act ? dist : 0x7FFF;
                 int src = sl - k;
                 src += (src < 0) ? n : 0;
                 recv = __shfl_sync(0xFFFFFFFFu, own, gbase + (src & (G - 1)));
+                recv = (2 * k < n) ? recv : 0x7FFF;
             }
-            d[2 * k - 1] = (2 * k - 1 < n) ? own : pad(2 * k - 1);
-            if (2 * k < G) d[2 * k] = (2 * k < n) ? recv : pad(2 * k);
+            d[2 * k - 1] = own;
+            if (2 * k < G) d[2 * k] = recv;
         }
+        // unused slots hold 0x7FFF and sink to the end: the wanted element is at sorted position med_rank(n), one of
+        // G / 4 + 1 .. G / 2 for the lists of this class (n > G / 2) -- and of 1 .. 4 in the 8-lane class
         med_sort_network(d);
-        const int med = d[G / 2];
+        const int rank = med_rank(n);
+        int med = d[G / 2];
+#pragma unroll
+        for (int pos = (G == 8) ? 1 : G / 4 + 1; pos < G / 2; ++pos) med = (rank == pos) ? d[pos] : med;
         uint32_t key = (sl < n && n >= 2) ? (static_cast<uint32_t>(med) << 5) | sl : KEY32_ABSENT;
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
@@ -161,7 +170,9 @@ __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, lo
                 r = g[0]; // a single observation keeps its direction (constructor, :38)
             } else if (n >= 2) {
                 double acc = 0.0;
-                for (int j = 0; j < n; ++j) acc = __dadd_rn(acc, g[3 * j]);
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (j < n) acc = __dadd_rn(acc, g[3 * j]);
                 r = __ddiv_rn(acc, static_cast<double>(n));
             }
             a.med_dir[3 * lm + sl] = r;
@@ -265,11 +276,16 @@ __global__ void __launch_bounds__(32 * MED_WARPS) med_desc_warp_kernel(MedArgs a
     }
 }
 
-constexpr int MED_CTA_CACHE_N = 128; // lists up to this length keep their distance matrix in shared memory
+constexpr int MED_CTA_CACHE_N = 128; // lists up to this length keep their rows and their distance matrix in shared memory
 
+// Lists of more than 32 observations (the work list of the warp kernel), one per CTA at a time.  Up to 128 observations
+// the rows are staged in shared memory, every pair is computed once into a uint16 matrix, and a row's rank search
+// (smallest v with #{d <= v} >= rank + 1, bisection over 0 .. 256) is shared by 2 or 4 lanes that each count a
+// strided part of the row and add up by shuffle; longer lists fall back to one thread per row recomputing distances.
 __global__ void __launch_bounds__(MED_CTA_THREADS) med_desc_cta_kernel(MedArgs a) {
     __shared__ unsigned long long s_best;
     __shared__ uint16_t s_dist[MED_CTA_CACHE_N * MED_CTA_CACHE_N];
+    __shared__ uint4 s_rows[MED_CTA_CACHE_N * 2];
     const int n_work = a.work[0];
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const long long lm = a.work[1 + w];
@@ -277,29 +293,59 @@ __global__ void __launch_bounds__(MED_CTA_THREADS) med_desc_cta_kernel(MedArgs a
         const int n = static_cast<int>(static_cast<long long>(__ldg(a.obs_start + lm + 1)) - lo);
         if (threadIdx.x == 0) s_best = KEY64_ABSENT;
         const bool cached = n <= MED_CTA_CACHE_N;
-        if (cached) { // every pair once, all threads (row-major n x n)
-            for (int idx = threadIdx.x; idx < n * n; idx += MED_CTA_THREADS) {
-                const int i = idx / n, j = idx - i * n;
-                s_dist[idx] = static_cast<uint16_t>(hamming256(load_desc(a.desc, lo + i), load_desc(a.desc, lo + j)));
-            }
-        }
-        __syncthreads();
         const int need = med_rank(n) + 1;
-        for (int i = threadIdx.x; i < n; i += MED_CTA_THREADS) {
-            const Desc q = load_desc(a.desc, lo + i);
-            int v_lo = 0, v_hi = 256;
-            while (v_lo < v_hi) {
-                const int mid = (v_lo + v_hi) >> 1;
-                int c = 0;
-                if (cached) {
-                    for (int j = 0; j < n; ++j) c += (s_dist[i * n + j] <= mid);
-                } else {
-                    for (int j = 0; j < n; ++j) c += (hamming256(q, load_desc(a.desc, lo + j)) <= mid);
-                }
-                if (c >= need) v_hi = mid;
-                else v_lo = mid + 1;
+        if (cached) {
+            for (int i = threadIdx.x; i < 2 * n; i += MED_CTA_THREADS) s_rows[i] = __ldg(a.desc + 2 * lo + i);
+            __syncthreads();
+            // every pair once, mirrored: item (i, k) is the pair (i, i + k mod n), k = 1 .. n / 2; for even n the offset
+            // n / 2 reaches each pair from both ends, so only its first half is taken
+            const int half = n >> 1;
+            for (int idx = threadIdx.x; idx < n * half; idx += MED_CTA_THREADS) {
+                const int k = idx / n + 1, i = idx - (k - 1) * n;
+                if (2 * k == n && i >= half) continue;
+                int j = i + k;
+                j -= (j >= n) ? n : 0;
+                const Desc qa{s_rows[2 * i], s_rows[2 * i + 1]};
+                const uint16_t dist = static_cast<uint16_t>(hamming256(qa, s_rows[2 * j], s_rows[2 * j + 1]));
+                s_dist[i * n + j] = dist;
+                s_dist[j * n + i] = dist;
             }
-            atomicMin(&s_best, make_key64(static_cast<uint32_t>(v_lo), static_cast<uint32_t>(i)));
+            for (int i = threadIdx.x; i < n; i += MED_CTA_THREADS) s_dist[i * n + i] = 0;
+            __syncthreads();
+            const int T = (n <= MED_CTA_THREADS / 4) ? 4 : 2; // lanes per row
+            const int part = threadIdx.x & (T - 1);
+            for (int base = 0; base < n; base += MED_CTA_THREADS / T) { // uniform trip count: the shuffles need whole warps
+                const int i = base + threadIdx.x / T;
+                const uint16_t *row = s_dist + min(i, n - 1) * n;
+                int v_lo = 0, v_hi = 256;
+#pragma unroll 1
+                for (int step = 0; step < 8; ++step) { // 256 -> 1 in exactly 8 halvings; v_lo == v_hi earlier is harmless
+                    const int mid = (v_lo + v_hi) >> 1;
+                    int c = 0;
+                    for (int j = part; j < n; j += T) c += (row[j] <= mid);
+                    c += __shfl_xor_sync(0xFFFFFFFFu, c, 1);
+                    if (T == 4) c += __shfl_xor_sync(0xFFFFFFFFu, c, 2);
+                    if (v_lo < v_hi) {
+                        if (c >= need) v_hi = mid;
+                        else v_lo = mid + 1;
+                    }
+                }
+                if (i < n && part == 0) atomicMin(&s_best, make_key64(static_cast<uint32_t>(v_lo), static_cast<uint32_t>(i)));
+            }
+        } else {
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += MED_CTA_THREADS) {
+                const Desc q = load_desc(a.desc, lo + i);
+                int v_lo = 0, v_hi = 256;
+                while (v_lo < v_hi) {
+                    const int mid = (v_lo + v_hi) >> 1;
+                    int c = 0;
+                    for (int j = 0; j < n; ++j) c += (hamming256(q, load_desc(a.desc, lo + j)) <= mid);
+                    if (c >= need) v_hi = mid;
+                    else v_lo = mid + 1;
+                }
+                atomicMin(&s_best, make_key64(static_cast<uint32_t>(v_lo), static_cast<uint32_t>(i)));
+            }
         }
         __syncthreads();
         const int best = static_cast<int>(s_best & 0xFFFFFFFFull);

@@ -205,3 +205,27 @@ def test_gpu_med_desc_group_boundaries():
     assert np.array_equal(med_g, med_p)
     assert np.array_equal(d_g.view(np.uint64), d_p.view(np.uint64))
     assert (i_p[same] == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tie", [False, True])
+def test_gpu_med_desc_every_length(tie):
+    """One landmark of every list length 0 .. 140, shuffled (classes of the warp kernel: <= 8, <= 16, <= 32 lanes;
+    CTA kernel: 2 / 4 lanes per row up to 128, one thread per row above), noisy copies and the tie-stress set
+    (few distinct rows -> many equal medians, first row wins, mapFeatures.cpp:80-84)."""
+    from pl_inertial_slam_b200 import mapfeatures as MF
+    rng = np.random.default_rng(77 + tie)
+    counts = rng.permutation(np.concatenate([np.arange(0, 141), np.arange(2, 34), np.arange(2, 34)])).astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    n_obs = int(start[-1])
+    owner = np.repeat(np.arange(len(counts)), counts)
+    if tie:
+        desc = synth.tie_stress_desc(rng, n_obs)
+    else:
+        desc = synth.flip_bits(rng, synth.rand_desc(rng, len(counts))[owner], 0.07)
+    dirs = rng.normal(size=(n_obs, 3))
+    i_p, med_p, d_p = port.med_desc(desc, dirs, start)
+    i_g, med_g, d_g = MF.med_desc_batch(desc, start, dirs)
+    assert np.array_equal(i_g, i_p), np.flatnonzero(i_g != i_p)[:10]
+    assert np.array_equal(med_g, med_p)
+    assert np.array_equal(d_g.view(np.uint64), d_p.view(np.uint64))
