@@ -116,7 +116,7 @@ __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, lo
         int d[G];
         d[0] = (sl < n) ? 0 : 0x7FFF; // self distance
         const int gbase = lane - sl;
-        const uint4 *rows = a.desc + 2 * lo;
+        const uint4 *rows = a.desc + 2 * (n > 0 ? lo : 0); // a group without a landmark reads row 0 (nmax >= 2: it exists)
 #pragma unroll
         for (int k = 1; k <= G / 2; ++k) {
             int own = 0x7FFF, recv = 0x7FFF;
@@ -124,12 +124,9 @@ __device__ __forceinline__ void med_desc_pass(const MedArgs &a, double *sdir, lo
                 const bool act = sl < n && 2 * k <= n;
                 int j = sl + k;
                 j -= (j >= n) ? n : 0;
-                Desc t = q;
-                if (act) { // L1-resident: the owner lane fetched this row above
-                    t.lo = __ldg(rows + 2 * j);
-                    t.hi = __ldg(rows + 2 * j + 1);
-                }
-                const int dist = hamming256_csa4(q, t.lo, t.hi);
+                const int jc = act ? j : 0; // idle lanes re-read the list's first row (one broadcast request)
+                const uint4 tlo = __ldg(rows + 2 * jc), thi = __ldg(rows + 2 * jc + 1); // L1-resident: the owner lane fetched it above
+                const int dist = hamming256_csa4(q, tlo, thi);
                 own = act ? dist : 0x7FFF;
                 int src = sl - k;
                 src += (src < 0) ? n : 0;
@@ -286,6 +283,7 @@ __global__ void __launch_bounds__(MED_CTA_THREADS) med_desc_cta_kernel(MedArgs a
     __shared__ unsigned long long s_best;
     __shared__ uint16_t s_dist[MED_CTA_CACHE_N * MED_CTA_CACHE_N];
     __shared__ uint4 s_rows[MED_CTA_CACHE_N * 2];
+    __shared__ double s_dirs[MED_CTA_CACHE_N * 3];
     const int n_work = a.work[0];
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const long long lm = a.work[1 + w];
@@ -296,6 +294,8 @@ __global__ void __launch_bounds__(MED_CTA_THREADS) med_desc_cta_kernel(MedArgs a
         const int need = med_rank(n) + 1;
         if (cached) {
             for (int i = threadIdx.x; i < 2 * n; i += MED_CTA_THREADS) s_rows[i] = __ldg(a.desc + 2 * lo + i);
+            if (a.med_dir && a.dirs)
+                for (int i = threadIdx.x; i < 3 * n; i += MED_CTA_THREADS) s_dirs[i] = __ldg(a.dirs + 3 * lo + i);
             __syncthreads();
             // every pair once, mirrored: item (i, k) is the pair (i, i + k mod n), k = 1 .. n / 2; for even n the offset
             // n / 2 reaches each pair from both ends, so only its first half is taken
@@ -354,8 +354,16 @@ __global__ void __launch_bounds__(MED_CTA_THREADS) med_desc_cta_kernel(MedArgs a
             const long long row = a.dst_rows ? __ldg(a.dst_rows + lm) : lm;
             if (row >= 0) a.med_desc[2 * row + threadIdx.x] = __ldg(a.desc + 2 * (lo + best) + threadIdx.x);
         }
-        if (a.med_dir && a.dirs && threadIdx.x >= 32 && threadIdx.x < 35)
-            a.med_dir[3 * lm + (threadIdx.x - 32)] = med_dir_component(a.dirs, lo, n, threadIdx.x - 32);
+        if (a.med_dir && a.dirs && threadIdx.x >= 32 && threadIdx.x < 35) {
+            const int c = threadIdx.x - 32;
+            if (cached) { // same sequential sum as med_dir_component, from the staged copy (60 dependent L2 reads otherwise)
+                double acc = 0.0;
+                for (int i = 0; i < n; ++i) acc = __dadd_rn(acc, s_dirs[3 * i + c]);
+                a.med_dir[3 * lm + c] = __ddiv_rn(acc, static_cast<double>(n));
+            } else {
+                a.med_dir[3 * lm + c] = med_dir_component(a.dirs, lo, n, c);
+            }
+        }
         __syncthreads();
     }
 }
