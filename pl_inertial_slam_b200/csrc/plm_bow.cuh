@@ -173,27 +173,124 @@ struct BowScoreArgs {
     double *scores;   // n_q x n_db: scores[q * n_db + j] = score(query q, db j)
 };
 
+constexpr int BOW_SCORE_MAX_WARPS = 16;
+
+// query values | hash table | bitmap + its sentinel word | pending-candidate lists of the CTA's warps (32 x int64 each)
 inline size_t bow_score_smem(int q_cap, int table_slots, int bitmap_words) {
-    return size_t(q_cap) * 8 + size_t(table_slots) * 8 + size_t(bitmap_words) * 4 + 16;
+    return size_t(q_cap) * 8 + size_t(table_slots) * 8 + ((size_t(bitmap_words + 1) * 4 + 7) & ~size_t(7)) +
+           size_t(BOW_SCORE_MAX_WARPS) * 32 * 8;
 }
 
 __device__ __forceinline__ uint32_t bow_hash(uint32_t id, int slots) { return (id * 2654435761u) & static_cast<uint32_t>(slots - 1); }
 
-// grid = (CTAs over the database, queries); a warp per database vector, 128 coalesced entries in flight.  Two
-// keyframes share only a handful of the vocabulary's 10^5 - 10^6 words, so membership of a database entry in the
-// query is first tested against a BITMAP of the query's word ids in shared memory (one LDS); the rare candidates
-// find the query value through a shared-memory hash table (1-2 probes) and only then load the database value.
-// The kernel is then a coalesced stream over the database ids.  The hit lanes' terms are accumulated in lane
-// order = ascending word id = the reference's summation order.
-__global__ void __launch_bounds__(1024) bow_score_kernel(BowScoreArgs a) {
+// Membership pre-test: bit `id` of the query's word bitmap; ids beyond the bitmap read the all-ones sentinel word that
+// follows it ("maybe": the hash table decides).
+__device__ __forceinline__ uint32_t bow_maybe(const uint32_t *bitmap, uint32_t bitmap_words, uint32_t id) {
+    return (bitmap[min(id >> 5, bitmap_words)] >> (id & 31u)) & 1u;
+}
+
+// Position of word `id` in the staged query, or -1.  0xFFFFFFFF marks an empty slot of the table; no word has this id.
+__device__ __forceinline__ int bow_find(const uint2 *table, int slots, uint32_t id) {
+    if (id == 0xFFFFFFFFu) return -1;
+    uint32_t h = bow_hash(id, slots);
+    uint2 t = table[h];
+    while (t.x != id && t.x != 0xFFFFFFFFu) {
+        h = (h + 1) & static_cast<uint32_t>(slots - 1);
+        t = table[h];
+    }
+    return t.x == id ? static_cast<int>(t.y) : -1;
+}
+
+// The first n pending candidates of the warp (entry indices, in entry order), all lanes at once: re-read the word id
+// (cache hit), look it up in the query's hash table, fetch the database value -- ONE round trip to memory for up to 32
+// candidates -- and form the L1 term |vi - wi| - |vi| - |wi| (ScoringObject.cpp:46-52, every operation rounded).  The
+// hit terms are then added in lane order == entry order == ascending word id, the reference's summation order.
+__device__ __noinline__ double bow_flush(const BowScoreArgs &a, const double *qv, const uint2 *table, const long long *pend, int n,
+                                         double score) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    double term = 0.0;
+    bool hit = false;
+    if (lane < n) {
+        const long long e = pend[lane];
+        const int pos = bow_find(table, a.table_slots, __ldg(a.db_ids + e));
+        if (pos >= 0) {
+            const double vi = qv[pos], wi = __ldg(a.db_vals + e);
+            term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+            hit = true;
+        }
+    }
+    unsigned lanes = __ballot_sync(0xFFFFFFFFu, hit);
+    while (lanes) {
+        const int src = __ffs(lanes) - 1;
+        score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, term, src));
+        lanes &= lanes - 1;
+    }
+    __syncwarp();
+    return score;
+}
+
+// A chunk with more than 32 candidates (a database vector that shares most of its words with the query: the keyframe's
+// neighbours in the map, or the keyframe itself).  Flushing 32 at a time would cost one memory round trip and one
+// 32-step serial sum per flush; instead every lane resolves ITS candidates (up to 32, eight value loads in flight at a
+// time) into a thread-local array of terms, and the running score is then handed from lane to lane, each lane adding
+// its terms in order: the serial chain is one DADD per common word, nothing else.
+__device__ __noinline__ double bow_dense_chunk(const BowScoreArgs &a, const double *qv, const uint2 *table, uint32_t mb, long long b,
+                                               double score) {
+    const int lane = threadIdx.x & 31;
+    double t[32];
+    int cnt = 0;
+    while (mb) {
+        int pos[8];
+        double w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            pos[u] = -1;
+            w[u] = 0.0;
+            if (mb) {
+                const long long e = b + (__ffs(mb) - 1);
+                mb &= mb - 1;
+                pos[u] = bow_find(table, a.table_slots, __ldg(a.db_ids + e));
+                if (pos[u] >= 0) w[u] = __ldg(a.db_vals + e);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (pos[u] >= 0) {
+                const double vi = qv[pos[u]];
+                t[cnt++] = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, w[u])), fabs(vi)), fabs(w[u]));
+            }
+        }
+    }
+    unsigned lanes = __ballot_sync(0xFFFFFFFFu, cnt > 0);
+    while (lanes) {
+        const int src = __ffs(lanes) - 1;
+        if (lane == src)
+            for (int c = 0; c < cnt; ++c) score = __dadd_rn(score, t[c]);
+        score = __shfl_sync(0xFFFFFFFFu, score, src);
+        lanes &= lanes - 1;
+    }
+    return score;
+}
+
+// grid = (CTAs over the database, queries); a warp per database vector.  Two keyframes share only a handful of the
+// vocabulary's 10^5 - 10^6 words, so the kernel is a stream over the database word ids.  A lane owns 32 CONSECUTIVE ids
+// of the vector (eight 16-byte loads, all issued before the first is looked at: one memory round trip per 1024 ids),
+// tests each against a BITMAP of the query's word ids in shared memory (one LDS) and collects the outcome in one 32-bit
+// mask.  Because lanes own consecutive ranges, a candidate's position in entry order is a warp prefix sum of the mask
+// popcounts; candidates are written at that position into the warp's pending list and resolved 32 at a time by
+// bow_flush; a chunk with more than 32 of them takes bow_dense_chunk.
+__global__ void __launch_bounds__(512) bow_score_kernel(BowScoreArgs a) {
     extern __shared__ __align__(16) unsigned char bow_smem[];
     double *qv = reinterpret_cast<double *>(bow_smem);
     uint2 *table = reinterpret_cast<uint2 *>(bow_smem + size_t(a.q_cap) * 8);
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(table + a.table_slots);
+    long long *pend_all = reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(bitmap) + ((size_t(a.bitmap_words + 1) * 4 + 7) & ~size_t(7)));
     const int q = blockIdx.y;
     const long long qs = __ldg(a.q_start + q);
     const int qn = min(__ldg(a.q_len + q), a.q_cap);
     for (int i = threadIdx.x; i < a.bitmap_words; i += blockDim.x) bitmap[i] = 0u;
+    if (threadIdx.x == 0) bitmap[a.bitmap_words] = 0xFFFFFFFFu;
     for (int i = threadIdx.x; i < a.table_slots; i += blockDim.x) table[i] = make_uint2(0xFFFFFFFFu, 0u);
     __syncthreads();
     const uint32_t bitmap_bits = static_cast<uint32_t>(a.bitmap_words) * 32u;
@@ -208,45 +305,98 @@ __global__ void __launch_bounds__(1024) bow_score_kernel(BowScoreArgs a) {
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
-    for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < a.n_db; j += gridDim.x * warps) {
-        const long long ds = __ldg(a.db_start + j);
-        const int dn = __ldg(a.db_len + j);
+    long long *pend = pend_all + 32 * (threadIdx.x >> 5);
+    const bool vec = (reinterpret_cast<uintptr_t>(a.db_ids) & 15) == 0;
+    const uint32_t bwords = static_cast<uint32_t>(a.bitmap_words);
+    const int stride = gridDim.x * warps;
+    int j = blockIdx.x * warps + (threadIdx.x >> 5);
+    long long nx_ds = 0;
+    int nx_dn = 0;
+    if (j < a.n_db) {
+        nx_ds = __ldg(a.db_start + j);
+        nx_dn = __ldg(a.db_len + j);
+    }
+    for (; j < a.n_db; j += stride) {
+        const long long ds = nx_ds;
+        const long long end = ds + max(nx_dn, 0);
+        if (j + stride < a.n_db) {
+            nx_ds = __ldg(a.db_start + j + stride);
+            nx_dn = __ldg(a.db_len + j + stride);
+        }
         double score = 0.0;
-        for (int base = 0; base < dn; base += 128) {
-            uint32_t id[4];
+        int n_pend = 0; // warp-uniform
+        // 16-byte groups start at a multiple of 4 entries; the group holding `ds` may begin up to 3 entries early and
+        // the one holding `end - 1` may reach up to 3 entries further -- inside the same 16 aligned bytes as a valid
+        // entry, hence mapped; the validity mask drops them
+        const long long A = vec ? (ds & ~3LL) : ds;
+        for (long long c0 = A; c0 < end; c0 += 1024) {
+            const long long b = c0 + 32 * lane; // this lane's 32 entries
+            uint4 r[8];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int e = base + 32 * c + lane;
-                id[c] = e < dn ? __ldg(a.db_ids + ds + e) : 0xFFFFFFFFu; // no word has this id
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int e = base + 32 * c + lane;
-                bool maybe = id[c] != 0xFFFFFFFFu;
-                if (maybe && id[c] < bitmap_bits) maybe = (bitmap[id[c] >> 5] >> (id[c] & 31u)) & 1u;
-                double term = 0.0;
-                bool hit = false;
-                if (maybe) {
-                    uint32_t h = bow_hash(id[c], a.table_slots);
-                    uint2 t = table[h];
-                    while (t.x != id[c] && t.x != 0xFFFFFFFFu) {
-                        h = (h + 1) & static_cast<uint32_t>(a.table_slots - 1);
-                        t = table[h];
-                    }
-                    if (t.x == id[c]) {
-                        const double vi = qv[t.y], wi = __ldg(a.db_vals + ds + e);
-                        term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
-                        hit = true;
+            for (int i = 0; i < 8; ++i) {
+                r[i] = make_uint4(0, 0, 0, 0);
+                const long long e = b + 4 * i;
+                if (e < end) {
+                    if (vec) {
+                        r[i] = __ldg(reinterpret_cast<const uint4 *>(a.db_ids + e));
+                    } else { // arena not 16-byte aligned: one id at a time
+                        r[i].x = __ldg(a.db_ids + e);
+                        if (e + 1 < end) r[i].y = __ldg(a.db_ids + e + 1);
+                        if (e + 2 < end) r[i].z = __ldg(a.db_ids + e + 2);
+                        if (e + 3 < end) r[i].w = __ldg(a.db_ids + e + 3);
                     }
                 }
-                unsigned mask = __ballot_sync(0xFFFFFFFFu, hit);
-                while (mask) { // common words in ascending id: the reference's summation order
-                    const int src = __ffs(mask) - 1;
-                    score = __dadd_rn(score, __shfl_sync(0xFFFFFFFFu, term, src));
-                    mask &= mask - 1;
+            }
+            // bits [lo, hi) of the lane's mask are entries of the vector
+            const int lo = static_cast<int>(max(ds - b, 0LL)), hi = static_cast<int>(min(max(end - b, 0LL), 32LL));
+            uint32_t vm = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u));
+            vm &= ~((1u << min(lo, 31)) - 1u);
+            if (hi <= lo) vm = 0u;
+            uint32_t mb = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                mb |= bow_maybe(bitmap, bwords, r[i].x) << (4 * i);
+                mb |= bow_maybe(bitmap, bwords, r[i].y) << (4 * i + 1);
+                mb |= bow_maybe(bitmap, bwords, r[i].z) << (4 * i + 2);
+                mb |= bow_maybe(bitmap, bwords, r[i].w) << (4 * i + 3);
+            }
+            mb &= vm;
+            if (!__ballot_sync(0xFFFFFFFFu, mb != 0)) continue;
+            // rank of this lane's first candidate among the chunk's candidates (entry order == lane order)
+            const int cnt = __popc(mb);
+            int incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            int rank = incl - cnt; // exclusive
+            if (total > 32) {
+                if (n_pend) score = bow_flush(a, qv, table, pend, n_pend, score);
+                n_pend = 0;
+                score = bow_dense_chunk(a, qv, table, mb, b, score);
+                continue;
+            }
+            for (int done = 0; done < total;) {
+                // the pending list takes candidates of rank [done, done + room)
+                const int room = 32 - n_pend;
+                const int upto = min(total, done + room);
+                while (mb && rank < upto) {
+                    const int k = __ffs(mb) - 1;
+                    pend[n_pend + rank - done] = b + k;
+                    mb &= mb - 1;
+                    ++rank;
+                }
+                n_pend += upto - done;
+                done = upto;
+                if (n_pend == 32) {
+                    score = bow_flush(a, qv, table, pend, 32, score);
+                    n_pend = 0;
                 }
             }
         }
+        if (n_pend) score = bow_flush(a, qv, table, pend, n_pend, score);
         if (lane == 0) a.scores[static_cast<size_t>(q) * a.n_db + j] = __ddiv_rn(-score, 2.0);
     }
 }

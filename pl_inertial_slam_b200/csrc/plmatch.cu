@@ -1911,9 +1911,12 @@ int launch_bow_score(plm_ctx *ctx, plm::BowScoreArgs a, int max_q_len, int64_t n
     if (smem > budget) return fail(PLM_E_UNSUPPORTED, "query vector too long for shared memory");
     CU_TRY(cudaFuncSetAttribute(plm::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
     // a large bitmap leaves room for few CTAs per SM: make them wide so that enough warps stream the database
-    const int threads = smem > 64 * 1024 ? 1024 : (smem > 24 * 1024 ? 512 : plm::BOW_THREADS);
+    const int threads = smem > 24 * 1024 ? 512 : plm::BOW_THREADS;
     const int warps = threads / 32;
-    const int ctas = std::max(1, std::min((a.n_db + warps - 1) / warps, ctx->sm_count * (threads == 1024 ? 2 : 8)));
+    // one resident wave: every CTA builds the query's bitmap and hash table once, its warps then loop over the database
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plm::bow_score_kernel, threads, smem));
+    const int ctas = std::max(1, std::min((a.n_db + warps - 1) / warps, ctx->sm_count * std::max(per_sm, 1)));
     plm::bow_score_kernel<<<dim3(ctas, a.n_q), threads, smem, ctx->stream>>>(a);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
