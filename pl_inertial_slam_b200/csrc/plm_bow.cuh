@@ -230,27 +230,29 @@ __device__ __noinline__ double bow_flush(const BowScoreArgs &a, const double *qv
     return score;
 }
 
-// A chunk with more than 32 candidates (a database vector that shares most of its words with the query: the keyframe's
-// neighbours in the map, or the keyframe itself).  Flushing 32 at a time would cost one memory round trip and one
-// 32-step serial sum per flush; instead every lane resolves ITS candidates (up to 32, eight value loads in flight at a
-// time) into a thread-local array of terms, and the running score is then handed from lane to lane, each lane adding
-// its terms in order: the serial chain is one DADD per common word, nothing else.
-__device__ __noinline__ double bow_dense_chunk(const BowScoreArgs &a, const double *qv, const uint2 *table, uint32_t mb, long long b,
-                                               double score) {
+// A chunk (1024 ids) with more than 32 candidates: a database vector that shares most of its words with the query --
+// the keyframe's neighbours in the map, or the keyframe itself.  Flushing 32 at a time would cost one memory round
+// trip and one 32-step serial sum per flush.  Instead the chunk is re-read (cache hits) with every lane owning 32
+// CONSECUTIVE ids, every lane resolves its candidates (eight value loads in flight at a time) into a thread-local array
+// of terms, and the running score is handed from lane to lane, each adding its terms in order: the serial chain is one
+// DADD per common word and 32 hand-overs.
+__device__ __noinline__ double bow_dense_chunk(const BowScoreArgs &a, const double *qv, const uint2 *table, const uint32_t *bitmap,
+                                               long long c0, long long ds, long long end, double score) {
     const int lane = threadIdx.x & 31;
+    const long long b = c0 + 32 * lane;
     double t[32];
     int cnt = 0;
-    while (mb) {
+    for (int k0 = 0; k0 < 32; k0 += 8) {
         int pos[8];
         double w[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
+            const long long e = b + k0 + u;
             pos[u] = -1;
             w[u] = 0.0;
-            if (mb) {
-                const long long e = b + (__ffs(mb) - 1);
-                mb &= mb - 1;
-                pos[u] = bow_find(table, a.table_slots, __ldg(a.db_ids + e));
+            if (e >= ds && e < end) {
+                const uint32_t id = __ldg(a.db_ids + e);
+                if (bow_maybe(bitmap, static_cast<uint32_t>(a.bitmap_words), id)) pos[u] = bow_find(table, a.table_slots, id);
                 if (pos[u] >= 0) w[u] = __ldg(a.db_vals + e);
             }
         }
@@ -273,13 +275,20 @@ __device__ __noinline__ double bow_dense_chunk(const BowScoreArgs &a, const doub
     return score;
 }
 
+// Four nibbles -> four bytes.
+__device__ __forceinline__ uint32_t bow_spread4(uint32_t v) {
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    return (v | (v << 4)) & 0x0F0F0F0Fu;
+}
+
 // grid = (CTAs over the database, queries); a warp per database vector.  Two keyframes share only a handful of the
-// vocabulary's 10^5 - 10^6 words, so the kernel is a stream over the database word ids.  A lane owns 32 CONSECUTIVE ids
-// of the vector (eight 16-byte loads, all issued before the first is looked at: one memory round trip per 1024 ids),
-// tests each against a BITMAP of the query's word ids in shared memory (one LDS) and collects the outcome in one 32-bit
-// mask.  Because lanes own consecutive ranges, a candidate's position in entry order is a warp prefix sum of the mask
-// popcounts; candidates are written at that position into the warp's pending list and resolved 32 at a time by
-// bow_flush; a chunk with more than 32 of them takes bow_dense_chunk.
+// vocabulary's 10^5 - 10^6 words, so the kernel is a stream over the database word ids: chunks of 1024 ids, eight
+// coalesced 16-byte loads per lane, all issued before the first is looked at (one memory round trip per chunk); each id
+// is tested against a BITMAP of the query's word ids in shared memory (one LDS) and the outcomes are collected in one
+// 32-bit mask per lane (bit 4 i + c: component c of load i).  Entry order is (load, lane, component), so a candidate's
+// position among the chunk's candidates comes from one packed warp prefix sum of the eight per-load counts; candidates
+// are written at that position into the warp's pending list and resolved together by bow_flush at the end of the
+// vector (or when 32 are pending).  A chunk with more than 32 candidates takes bow_dense_chunk.
 __global__ void __launch_bounds__(512) bow_score_kernel(BowScoreArgs a) {
     extern __shared__ __align__(16) unsigned char bow_smem[];
     double *qv = reinterpret_cast<double *>(bow_smem);
@@ -330,12 +339,12 @@ __global__ void __launch_bounds__(512) bow_score_kernel(BowScoreArgs a) {
         // entry, hence mapped; the validity mask drops them
         const long long A = vec ? (ds & ~3LL) : ds;
         for (long long c0 = A; c0 < end; c0 += 1024) {
-            const long long b = c0 + 32 * lane; // this lane's 32 entries
+            const long long e0 = c0 + 4 * lane; // entry of component 0 of this lane's first load; load i is 128 entries on
             uint4 r[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 r[i] = make_uint4(0, 0, 0, 0);
-                const long long e = b + 4 * i;
+                const long long e = e0 + 128 * i;
                 if (e < end) {
                     if (vec) {
                         r[i] = __ldg(reinterpret_cast<const uint4 *>(a.db_ids + e));
@@ -347,54 +356,57 @@ __global__ void __launch_bounds__(512) bow_score_kernel(BowScoreArgs a) {
                     }
                 }
             }
-            // bits [lo, hi) of the lane's mask are entries of the vector
-            const int lo = static_cast<int>(max(ds - b, 0LL)), hi = static_cast<int>(min(max(end - b, 0LL), 32LL));
-            uint32_t vm = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u));
-            vm &= ~((1u << min(lo, 31)) - 1u);
-            if (hi <= lo) vm = 0u;
+            const int left = static_cast<int>(min(end - e0, 4096LL));   // entries from e0 to the end of the vector
+            const int skip = static_cast<int>(min(max(ds - e0, 0LL), 4LL)); // > 0 only in the very first load of the vector
             uint32_t mb = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                mb |= bow_maybe(bitmap, bwords, r[i].x) << (4 * i);
-                mb |= bow_maybe(bitmap, bwords, r[i].y) << (4 * i + 1);
-                mb |= bow_maybe(bitmap, bwords, r[i].z) << (4 * i + 2);
-                mb |= bow_maybe(bitmap, bwords, r[i].w) << (4 * i + 3);
+                uint32_t nib = bow_maybe(bitmap, bwords, r[i].x) | (bow_maybe(bitmap, bwords, r[i].y) << 1) |
+                               (bow_maybe(bitmap, bwords, r[i].z) << 2) | (bow_maybe(bitmap, bwords, r[i].w) << 3);
+                const int n_valid = min(max(left - 128 * i, 0), 4);
+                nib &= (1u << n_valid) - 1u;
+                if (i == 0) nib &= ~((1u << skip) - 1u);
+                mb |= nib << (4 * i);
             }
-            mb &= vm;
             if (!__ballot_sync(0xFFFFFFFFu, mb != 0)) continue;
-            // rank of this lane's first candidate among the chunk's candidates (entry order == lane order)
-            const int cnt = __popc(mb);
-            int incl = cnt;
+            // per-load candidate counts of this lane, packed one byte each, and their inclusive prefix over the lanes
+            uint32_t x = mb - ((mb >> 1) & 0x55555555u);
+            x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u); // a popcount per nibble
+            const uint32_t own0 = bow_spread4(x & 0xFFFFu), own1 = bow_spread4(x >> 16);
+            uint32_t in0 = own0, in1 = own1;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-                if (lane >= off) incl += t;
+                const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, in0, off), t1 = __shfl_up_sync(0xFFFFFFFFu, in1, off);
+                if (lane >= off) {
+                    in0 += t0; // a byte never exceeds 128 (32 lanes x 4)
+                    in1 += t1;
+                }
             }
-            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            int rank = incl - cnt; // exclusive
+            const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, in0, 31), tot1 = __shfl_sync(0xFFFFFFFFu, in1, 31);
+            const int sum0 = static_cast<int>(__vsadu4(tot0, 0u)), total = sum0 + static_cast<int>(__vsadu4(tot1, 0u));
             if (total > 32) {
                 if (n_pend) score = bow_flush(a, qv, table, pend, n_pend, score);
                 n_pend = 0;
-                score = bow_dense_chunk(a, qv, table, mb, b, score);
+                score = bow_dense_chunk(a, qv, table, bitmap, c0, ds, end, score);
                 continue;
             }
-            for (int done = 0; done < total;) {
-                // the pending list takes candidates of rank [done, done + room)
-                const int room = 32 - n_pend;
-                const int upto = min(total, done + room);
-                while (mb && rank < upto) {
-                    const int k = __ffs(mb) - 1;
-                    pend[n_pend + rank - done] = b + k;
-                    mb &= mb - 1;
-                    ++rank;
-                }
-                n_pend += upto - done;
-                done = upto;
-                if (n_pend == 32) {
-                    score = bow_flush(a, qv, table, pend, 32, score);
-                    n_pend = 0;
-                }
+            if (n_pend + total > 32) {
+                score = bow_flush(a, qv, table, pend, n_pend, score);
+                n_pend = 0;
             }
+            // rank of the first candidate of load i of this lane = candidates of the loads before i (all lanes) +
+            // candidates of load i in the lanes below; every byte stays <= 32 here
+            const uint32_t rk0 = tot0 * 0x01010100u + (in0 - own0);
+            const uint32_t rk1 = tot1 * 0x01010100u + static_cast<uint32_t>(sum0) * 0x01010101u + (in1 - own1);
+            uint32_t m = mb;
+            while (m) {
+                const int k = __ffs(m) - 1, i = k >> 2;
+                const uint32_t rk = ((i < 4 ? rk0 : rk1) >> (8 * (i & 3))) & 0xFFu;
+                const uint32_t before = __popc((mb >> (4 * i)) & ((1u << (k & 3)) - 1u));
+                pend[n_pend + rk + before] = e0 + 128 * i + (k & 3);
+                m &= m - 1;
+            }
+            n_pend += total;
         }
         if (n_pend) score = bow_flush(a, qv, table, pend, n_pend, score);
         if (lane == 0) a.scores[static_cast<size_t>(q) * a.n_db + j] = __ddiv_rn(-score, 2.0);

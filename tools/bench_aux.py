@@ -67,6 +67,16 @@ def events(ctx):
         db_len[::n_kf] = 0
         out["bow_score_without_self_copies"] = timed(score)
         db_len = db_len_full
+        n_db_full = n_db
+        n_db = 64
+        out["bow_score_64_vectors"] = timed(score)
+        db_len = db_len_full.clone()
+        db_len[::n_kf] = 0
+        out["bow_score_64_vectors_without_self"] = timed(score)
+        n_db = 4736
+        out["bow_score_4736_vectors_without_self"] = timed(score)
+        db_len = db_len_full
+        n_db = n_db_full
         common = [int(np.isin(ids[:int(lens[0])].cpu().numpy(), ids[k * per:k * per + int(lens[k])].cpu().numpy()).sum()) for k in (0, 1, 2, 3)]
         out["bow_score"]["common_words_with_kf_0_1_2_3"] = common
         desc, dirs, start = synth.make_landmark_observations(synth.SEED0 + 21, 250_000, mean_obs=8, long_lists=50, long_len=60)
