@@ -828,7 +828,7 @@ __device__ __forceinline__ void row_walk(const GridJob &job, const GridParams &g
 //         thread-block cluster: pass 0, cluster barrier, thresholds = minima of the lower-ranked CTAs read through
 //         distributed shared memory, pass 1, cluster barrier, mutual check from the global m21 keys.
 template <int STAGED, int MODE>
-__device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
+__device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, const int cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_warp_tot[GRID_ROW_THREADS / 32];
     __shared__ int s_seg_end;
@@ -853,7 +853,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
     const int32_t *s_items = reinterpret_cast<const int32_t *>(smem_raw + o_ci);
     bool items_staged = false;
     // pass 1 in its replay form (every pair of this CTA was handed over by pass 0) never touches the frame side
-    const bool replay_only = MODE == 1 && gp.best_lr && gp.ent_g && gp.seg_cnt[blockIdx.x] >= 0;
+    const bool replay_only = MODE == 1 && gp.best_lr && gp.ent_g && gp.seg_cnt[cta] >= 0;
     if (STAGED && !replay_only) {
         const int n_items = job.cell_start[n_cells];
         stage_bytes(smem_raw + o_cs, job.cell_start, static_cast<size_t>(n_cells + 1) * 4);
@@ -867,11 +867,14 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
         if (job.is_lines) job.dirs2 = reinterpret_cast<const double *>(dirp);
         if (items_staged) job.cell_items = s_items;
     }
-    const long long cta_row0 = static_cast<long long>(blockIdx.x) * gp.rows_per_cta;
+    const long long cta_row0 = static_cast<long long>(cta) * gp.rows_per_cta;
     const int row_end = static_cast<int>(min(static_cast<long long>(n1), cta_row0 + gp.rows_per_cta));
-    uint16_t *cta_min = MODE == 2 ? nullptr : gp.cta_min + static_cast<size_t>(blockIdx.x) * n2;
+    uint16_t *cta_min = MODE == 2 ? nullptr : gp.cta_min + static_cast<size_t>(cta) * n2;
     uint16_t *cmin16 = reinterpret_cast<uint16_t *>(smem_raw + L.cmin);
 
+    // MODE 2 with a single block of rows per CTA: the pair list pass 0 evaluated stays in shared memory (entries
+    // re-encoded as i2 | row | D) and pass 1 only streams it against its thresholds; -1 = not available
+    int smem_rec_total = -1;
     // one pass over this CTA's rows; P = std::integral_constant<int, 0 / 1>
     auto run_pass = [&](auto P, uint16_t *cmin_out, const uint16_t *thr_in) {
     constexpr int PASS = decltype(P)::value;
@@ -934,27 +937,36 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
     };
     int accepted = 0;
     // pass 0 records its pairs for pass 1 (MODE 0 / 1 only; the one-launch cluster form keeps everything on chip)
-    const bool recording = PASS == 0 && MODE == 0 && gp.ent_g != nullptr;
-    uint32_t *rec_base = recording || (PASS == 1 && MODE == 1 && gp.ent_g) ? gp.ent_g + static_cast<size_t>(blockIdx.x) * gp.ent_per_cta : nullptr;
-    int4 *rec_tab = gp.seg_tab ? gp.seg_tab + static_cast<size_t>(blockIdx.x) * GRID_SEG_TAB : nullptr;
+    const bool rec_smem = PASS == 0 && MODE == 2 && row_end - cta_row0 <= NT;
+    const bool recording = (PASS == 0 && MODE == 0 && gp.ent_g != nullptr) || rec_smem;
+    const bool replay_smem = PASS == 1 && MODE == 2 && thresholds && smem_rec_total >= 0;
+    uint32_t *rec_base = (recording && !rec_smem) || (PASS == 1 && MODE == 1 && gp.ent_g) ? gp.ent_g + static_cast<size_t>(cta) * gp.ent_per_cta : nullptr;
+    int4 *rec_tab = gp.seg_tab ? gp.seg_tab + static_cast<size_t>(cta) * GRID_SEG_TAB : nullptr;
     bool rec_ok = true;   // uniform
     int rec_n = 0, rec_used = 0;
-    const int n_rec = (PASS == 1 && MODE == 1 && thresholds && gp.ent_g) ? gp.seg_cnt[blockIdx.x] : -1;
+    const int n_rec = (PASS == 1 && MODE == 1 && thresholds && gp.ent_g) ? gp.seg_cnt[cta] : -1;
     int rec_i = 0;
     for (long long base = cta_row0; base < row_end; base += NT) { // uniform over the CTA
         const long long i1 = base + tid;
         const bool has_row = i1 < row_end;
         const int blk = static_cast<int>((base - cta_row0) / NT);
-        if (n_rec >= 0) {
+        if (n_rec >= 0 || replay_smem) {
             // ---- pass 1, replay form: stream the pairs pass 0 left behind against the thresholds ----
             rb0[tid] = KEY32_ABSENT;
             rb1[tid] = KEY32_ABSENT;
             __syncthreads();
-            while (rec_i < n_rec && rec_tab[rec_i].z == blk) {
-                const int4 rec = rec_tab[rec_i];
-                ++rec_i;
-                const uint32_t *src = rec_base + rec.x;
-                const int seg_total = rec.y;
+            bool smem_pending = replay_smem;
+            while (smem_pending || (rec_i < n_rec && rec_tab[rec_i].z == blk)) {
+                const uint32_t *src = ent;
+                int seg_total = smem_rec_total;
+                if (smem_pending) {
+                    smem_pending = false;
+                } else {
+                    const int4 rec = rec_tab[rec_i];
+                    ++rec_i;
+                    src = rec_base + rec.x;
+                    seg_total = rec.y;
+                }
                 for (int e = tid; e < seg_total; e += NT) {
                     uint32_t v = src[e];
                     if (v != PAIR_INVALID) {
@@ -1110,7 +1122,12 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
                 if (n_seg > 1) seg_total = s_seg_end;
                 // pass 0: room for this segment's pairs in the CTA's hand-over region (uniform decision)
                 uint32_t *rec_dst = nullptr;
-                if (recording && rec_ok) {
+                if (rec_smem) {
+                    if (n_seg == 1) { // in place: every thread rewrites the entries it has just read
+                        rec_dst = ent;
+                        smem_rec_total = seg_total;
+                    }
+                } else if (recording && rec_ok) {
                     if (rec_n < GRID_SEG_TAB && rec_used + seg_total <= gp.ent_per_cta) {
                         rec_dst = rec_base + rec_used;
                         if (tid == 0) rec_tab[rec_n] = make_int4(rec_used, seg_total, blk, 0);
@@ -1205,7 +1222,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
     if (PASS == 0) {
         __syncthreads();
         for (int i = tid; i < n2; i += NT) cmin_out[i] = static_cast<uint16_t>(min(K[i], 0xFFFFu));
-        if (recording && tid == 0) gp.seg_cnt[blockIdx.x] = rec_ok ? rec_n : -1;
+        if (recording && !rec_smem && tid == 0) gp.seg_cnt[cta] = rec_ok ? rec_n : -1;
         return;
     }
     if (accepted) atomicAdd(job.count, accepted);
@@ -1253,12 +1270,12 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp) {
 
 template <int PASS, int STAGED>
 __global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
-grid_rows_kernel(GridJob job, GridParams gp) { grid_rows_device<STAGED, PASS>(job, gp); }
+grid_rows_kernel(GridJob job, GridParams gp) { grid_rows_device<STAGED, PASS>(job, gp, static_cast<int>(blockIdx.x)); }
 
 // One launch, one cluster of gridDim.x <= 8 CTAs (MODE 2 above): the single-call path for frame-sized jobs.
 template <int STAGED>
 __global__ void __launch_bounds__(GRID_ROW_THREADS, 3)
-grid_rows_cluster_kernel(GridJob job, GridParams gp) { grid_rows_device<STAGED, 2>(job, gp); }
+grid_rows_cluster_kernel(GridJob job, GridParams gp) { grid_rows_device<STAGED, 2>(job, gp, static_cast<int>(blockIdx.x)); }
 
 // cta_min[c][i2] <- min(seed[i2], min over c' < c of cta_min[c'][i2]) when CTA c's own minimum beats it, else 0;
 // col_min[i2] = overall minimum.

@@ -21,6 +21,7 @@
 #include "plm_bow.cuh"
 #include "plm_common.cuh"
 #include "plm_frames.cuh"
+#include "plm_frame_fused.cuh"
 #include "plm_grid.cuh"
 #include "plm_knn2.cuh"
 #include "plm_map.cuh"
@@ -81,6 +82,7 @@ struct plm_ctx {
     int knn_occ[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
     size_t chunked_attr[2] = {0, 0};
     bool rows_attr_set = false;
+    bool frame_fused_attr_set = false;
     // frame session: the calls recorded between plm_frame_begin and plm_frame_end
     struct FrameCall {
         int kind = 0; // 0 match / matchNNR, 1 matchGrid
@@ -218,6 +220,7 @@ int g_grid_cluster = 2; // single matchGrid calls: 2 = row-parallel kernel on on
 long long g_peer_spin_ticks = 4000000000ll; // bounded spin of the peer-memory kernels (~2 s of SM clock); option "peer_spin_ms"
 int g_knn_qpt = 1;      // 2: long scans with >= 4096 queries keep two queries per thread (variant 6); option "knn_qpt"
 int g_knn_fill = 1;     // long brute-force scans: uneven workers fill every CTA slot + shared second-best bound (0: off, measurement)
+int g_frame_fused = 1;  // frame sessions run as ONE launch (frame_fused_kernel) when every recorded call fits (0: one lane per call)
 int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
 
 // -1 = automatic (variant 3 for long slices, 1 otherwise); 0..3 force a variant (measurement only)
@@ -413,6 +416,10 @@ PLM_API int plm_set_option(const char *key, int value) {
     }
     if (std::strcmp(key, "grid_rows") == 0) {
         g_grid_rows = value ? 1 : 0;
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "frame_fused") == 0) {
+        g_frame_fused = value ? 1 : 0;
         return PLM_OK;
     }
     if (std::strcmp(key, "grid_cluster") == 0) {
@@ -942,23 +949,30 @@ int launch_grid_cluster(plm_ctx *ctx, const plm::GridJob *jobs_dev, int n_jobs, 
 // per-column work arrays fit shared memory, else the warp-per-chunk kernels.  warps == 0 selects the row-parallel
 // form; n_cta is sized so that the whole launch is one wave of co-resident CTAs.
 
+// Shared-memory plan of the row-parallel kernels (grid_rows_device): per-column work arrays + block arrays are fixed;
+// the frame side is staged when everything stays under ~72 KB (3 CTAs per SM); the pair list takes what is left, at
+// least 2048 entries.  false = the work arrays do not fit (the warp-per-chunk kernels take the job).
+bool plan_grid_rows_smem(plm_ctx *ctx, int n2c, int n_cells, bool is_lines, plm::GridParams &gp, size_t &smem) {
+    const size_t optin = ctx->smem_optin - 2048;
+    const size_t fixed = plm::grid_rows_layout(n2c, is_lines, 0, n_cells, 0, 0).total;
+    if (!(g_grid_rows && n2c <= 0xFFFF && fixed + 2048 * 4 <= std::min<size_t>(optin, 160 * 1024))) return false;
+    const size_t target = 72 * 1024;
+    const size_t frame = plm::grid_rows_layout(n2c, is_lines, 0, n_cells, 0, 1).total - fixed;
+    gp.staged = (fixed + frame + 3072 * 4 <= target) ? 1 : 0;
+    size_t room = std::max<size_t>(target, fixed + 2048 * 4 + 64) - fixed - (gp.staged ? frame : 0);
+    gp.cap_items = gp.staged ? static_cast<int>(std::min<size_t>(room / 4 / 4, 8192)) : 0; // <= a quarter of the room
+    room -= plm::grid_align16(size_t(gp.cap_items) * 4);
+    gp.cap_pairs = static_cast<int>(std::min<size_t>(room / 4 - 8, 16384));
+    smem = plm::grid_rows_layout(n2c, is_lines, gp.cap_pairs, n_cells, gp.cap_items, gp.staged).total;
+    return true;
+}
+
 int plan_map_grid(plm_ctx *ctx, long long n1, int n2, int n_cells, bool is_lines, plm::GridParams &gp, int &warps, int &n_cta,
                   size_t &smem) {
     const size_t optin = ctx->smem_optin - 2048;
     const int n2c = std::max(n2, 1);
-    // shared memory: per-column work arrays + block arrays are fixed; the frame side is staged when everything stays
-    // under ~72 KB (3 CTAs per SM); the pair list takes what is left, at least 2048 entries
-    const size_t fixed = plm::grid_rows_layout(n2c, is_lines, 0, n_cells, 0, 0).total;
-    if (g_grid_rows && n2c <= 0xFFFF && fixed + 2048 * 4 <= std::min<size_t>(optin, 160 * 1024)) {
+    if (plan_grid_rows_smem(ctx, n2c, n_cells, is_lines, gp, smem)) {
         warps = 0;
-        const size_t target = 72 * 1024;
-        const size_t frame = plm::grid_rows_layout(n2c, is_lines, 0, n_cells, 0, 1).total - fixed;
-        gp.staged = (fixed + frame + 3072 * 4 <= target) ? 1 : 0;
-        size_t room = std::max<size_t>(target, fixed + 2048 * 4 + 64) - fixed - (gp.staged ? frame : 0);
-        gp.cap_items = gp.staged ? static_cast<int>(std::min<size_t>(room / 4 / 4, 8192)) : 0; // <= a quarter of the room
-        room -= plm::grid_align16(size_t(gp.cap_items) * 4);
-        gp.cap_pairs = static_cast<int>(std::min<size_t>(room / 4 - 8, 16384));
-        smem = plm::grid_rows_layout(n2c, is_lines, gp.cap_pairs, n_cells, gp.cap_items, gp.staged).total;
         if (!ctx->rows_attr_set) {
             CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
             CU_TRY(cudaFuncSetAttribute(plm::grid_rows_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
@@ -2793,6 +2807,171 @@ int frame_run(plm_ctx *ctx, const plm_ctx::FrameCall &c, Exec *ex) {
                            c.step2, c.dirs2, c.line_sim_th, c.win, c.ratio, c.best_lr, c.m12, c.n_matches, ex);
 }
 
+// The whole session as ONE launch (csrc/plm_frame_fused.cuh): job table + in/out vectors + inputs of every call in one
+// pinned block -> one copy in, frame_fused_kernel (one 8-CTA cluster per call), one copy out of the in/out vectors.
+// *done stays false when a call does not fit the fused kernel (the caller then runs one lane per call).
+int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, bool *done) {
+    *done = false;
+    const int n = static_cast<int>(calls.size());
+    if (!g_frame_fused || g_grid_cluster < 2 || n > 64) return PLM_OK;
+    struct Plan {
+        size_t o_io = 0, o_d1 = 0, o_d2 = 0, o_xy = 0, o_cs = 0, o_ci = 0, o_dir = 0, o_scr = 0;
+        int n_items = 0, n_cta = plm::FRAME_CLUSTER, c12 = 0;
+        plm::GridParams gp;
+    };
+    std::vector<Plan> plan(n);
+    Layout L;
+    L.add(size_t(n + 1) * sizeof(plm::FrameJobRec)); // + the sentinel record
+    const size_t io_begin = L.total;
+    for (int k = 0; k < n; ++k) plan[k].o_io = L.add(size_t(calls[k].n1) * 4 + 8); // m12, the counter, the arrival counter of a match job
+    const size_t io_end = L.total;
+    size_t smem = 0;
+    for (int k = 0; k < n; ++k) {
+        const plm_ctx::FrameCall &c = calls[k];
+        Plan &p = plan[k];
+        std::memset(&p.gp, 0, sizeof(p.gp));
+        p.o_d1 = L.add(size_t(c.n1) * 32);
+        p.o_d2 = L.add(size_t(std::max(c.n2, 1)) * 32);
+        if (c.kind == 0) {
+            if (c.n1 > plm::FRAME_MATCH_MAX_ROWS || c.n2 > plm::FRAME_MATCH_MAX_ROWS) return PLM_OK;
+            smem = std::max(smem, plm::match_cta_smem(c.n1, c.n2, c.best_lr));
+            // ~24 query rows per CTA (both directions count), whole clusters, at most 64 CTAs per job
+            const int q_rows = c.n1 + (c.best_lr ? c.n2 : 0);
+            p.n_cta = std::min(64, (q_rows + 24 * plm::FRAME_CLUSTER - 1) / (24 * plm::FRAME_CLUSTER) * plm::FRAME_CLUSTER);
+            p.c12 = p.n_cta;
+            if (c.best_lr) p.c12 = std::max(1, std::min(p.n_cta - 1, static_cast<int>((static_cast<long long>(p.n_cta) * c.n1 + q_rows / 2) / std::max(q_rows, 1))));
+            continue;
+        }
+        if (c.n1 > plm::FRAME_CLUSTER * plm::GRID_ROW_THREADS || c.n1 >= (1 << plm::GRID_KEY_BITS)) return PLM_OK;
+        const int n_cells = c.grid_rows * c.grid_cols;
+        p.n_items = c.cell_start[n_cells];
+        size_t job_smem = 0;
+        if (!plan_grid_rows_smem(ctx, std::max(c.n2, 1), n_cells, c.is_lines != 0, p.gp, job_smem)) return PLM_OK;
+        smem = std::max(smem, job_smem);
+        // the rows are spread over the 8 CTAs of the cluster in multiples of a warp
+        int rpc = ((c.n1 + plm::FRAME_CLUSTER - 1) / plm::FRAME_CLUSTER + 31) / 32 * 32;
+        p.gp.rows_per_cta = std::min(rpc, plm::GRID_ROW_THREADS);
+        p.gp.grid_rows = c.grid_rows;
+        p.gp.grid_cols = c.grid_cols;
+        p.gp.best_lr = c.best_lr ? 1 : 0;
+        p.gp.ratio = c.ratio;
+        p.gp.line_sim_th = c.line_sim_th;
+        p.o_xy = L.add(size_t(c.n1) * (c.is_lines ? 4 : 2) * 4);
+        p.o_cs = L.add(size_t(n_cells + 1) * 4);
+        p.o_ci = L.add(size_t(std::max(p.n_items, 1)) * 4);
+        p.o_dir = L.add(c.is_lines ? size_t(std::max(c.n2, 1)) * 16 : 0);
+    }
+    const size_t in_end = L.total;
+    for (int k = 0; k < n; ++k) // device-only scratch: matches_21 (match) / per-column keys (matchGrid)
+        plan[k].o_scr = L.add(size_t(std::max(calls[k].n2, 1)) * (calls[k].kind == 0 ? 4 : 8));
+    if (smem > ctx->smem_optin - 2048) return PLM_OK;
+    int st;
+    if ((st = ctx->ensure_pinned(in_end)) != PLM_OK) return st;
+    if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
+    if (!ctx->frame_fused_attr_set) {
+        CU_TRY(cudaFuncSetAttribute(plm::frame_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin - 2048)));
+        ctx->frame_fused_attr_set = true;
+    }
+    static const bool trace = std::getenv("PLM_FRAME_TRACE") != nullptr;
+    static double t_acc[5] = {0, 0, 0, 0, 0};
+    static int t_n = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    char *HB = ctx->h_buf, *DB = ctx->d_buf;
+    plm::FrameJobRec *tab = reinterpret_cast<plm::FrameJobRec *>(HB);
+    int n_cta_total = 0;
+    for (int k = 0; k < n; ++k) {
+        const plm_ctx::FrameCall &c = calls[k];
+        const Plan &p = plan[k];
+        plm::FrameJobRec &r = tab[k];
+        std::memset(&r, 0, sizeof(r));
+        r.kind = c.kind;
+        pack_rows(HB + p.o_d1, c.d1, c.n1, c.step1);
+        pack_rows(HB + p.o_d2, c.d2, c.n2, c.step2);
+        std::memcpy(HB + p.o_io, c.m12, size_t(c.n1) * 4);
+        std::memset(HB + p.o_io + size_t(c.n1) * 4, 0, 8);
+        int32_t *dm12 = reinterpret_cast<int32_t *>(DB + p.o_io);
+        r.cta_begin = n_cta_total;
+        n_cta_total += p.n_cta;
+        if (c.kind == 0) {
+            r.mj.done = dm12 + c.n1 + 1;
+            r.mj.n_cta = p.n_cta;
+            r.mj.c12 = p.c12;
+            r.mj.d1 = reinterpret_cast<const uint4 *>(DB + p.o_d1);
+            r.mj.d2 = reinterpret_cast<const uint4 *>(DB + p.o_d2);
+            r.mj.m12 = dm12;
+            r.mj.count = dm12 + c.n1;
+            r.mj.m21 = reinterpret_cast<int32_t *>(DB + p.o_scr);
+            r.mj.n1 = c.n1;
+            r.mj.n2 = c.n2;
+            r.mj.best_lr = c.best_lr ? 1 : 0;
+            r.mj.nnr = c.nnr;
+            continue;
+        }
+        const int n_cells = c.grid_rows * c.grid_cols;
+        std::memcpy(HB + p.o_xy, c.coords, size_t(c.n1) * (c.is_lines ? 4 : 2) * 4);
+        std::memcpy(HB + p.o_cs, c.cell_start, size_t(n_cells + 1) * 4);
+        if (p.n_items > 0) std::memcpy(HB + p.o_ci, c.cell_items, size_t(p.n_items) * 4);
+        if (c.is_lines && c.n2 > 0) std::memcpy(HB + p.o_dir, c.dirs2, size_t(c.n2) * 16);
+        r.gj.coords = reinterpret_cast<const int32_t *>(DB + p.o_xy);
+        r.gj.d1 = reinterpret_cast<const uint4 *>(DB + p.o_d1);
+        r.gj.cell_start = reinterpret_cast<const int32_t *>(DB + p.o_cs);
+        r.gj.cell_items = reinterpret_cast<const int32_t *>(DB + p.o_ci);
+        r.gj.d2 = reinterpret_cast<const uint4 *>(DB + p.o_d2);
+        r.gj.dirs2 = reinterpret_cast<const double *>(DB + p.o_dir);
+        r.gj.m12 = dm12;
+        r.gj.count = dm12 + c.n1;
+        r.gj.n1 = c.n1;
+        r.gj.n2 = c.n2;
+        r.gj.is_lines = c.is_lines;
+        for (int i = 0; i < 4; ++i) r.gj.win[i] = c.win[i];
+        r.gp = p.gp;
+        r.gp.m21key = reinterpret_cast<unsigned long long *>(DB + p.o_scr);
+    }
+    std::memset(&tab[n], 0, sizeof(plm::FrameJobRec));
+    tab[n].cta_begin = n_cta_total;
+    const auto t1 = std::chrono::steady_clock::now();
+    CU_TRY(cudaMemcpyAsync(DB, HB, in_end, cudaMemcpyHostToDevice, ctx->stream));
+    const auto t2 = std::chrono::steady_clock::now();
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_cta_total, 1, 1);
+    cfg.blockDim = dim3(plm::GRID_ROW_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plm::FRAME_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU_TRY(cudaLaunchKernelEx(&cfg, plm::frame_fused_kernel, reinterpret_cast<const plm::FrameJobRec *>(DB), n));
+    ctx->launches++;
+    const auto t3 = std::chrono::steady_clock::now();
+    CU_TRY(cudaMemcpyAsync(HB + io_begin, DB + io_begin, io_end - io_begin, cudaMemcpyDeviceToHost, ctx->stream));
+    const auto t4 = std::chrono::steady_clock::now();
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (trace) {
+        const auto t5 = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        t_acc[0] += us(t0, t1); t_acc[1] += us(t1, t2); t_acc[2] += us(t2, t3); t_acc[3] += us(t3, t4); t_acc[4] += us(t4, t5);
+        if (++t_n % 200 == 0) {
+            std::fprintf(stderr, "[frame_fused] pack %.1f  h2d-issue %.1f  launch %.1f  d2h-issue %.1f  sync %.1f us  (in %zu B, smem %zu)\n",
+                         t_acc[0] / 200, t_acc[1] / 200, t_acc[2] / 200, t_acc[3] / 200, t_acc[4] / 200, in_end, smem);
+            for (double &v : t_acc) v = 0;
+        }
+    }
+    for (int k = 0; k < n; ++k) {
+        const plm_ctx::FrameCall &c = calls[k];
+        std::memcpy(c.m12, HB + plan[k].o_io, size_t(c.n1) * 4);
+        int32_t cnt;
+        std::memcpy(&cnt, HB + plan[k].o_io + size_t(c.n1) * 4, 4);
+        *c.n_matches = cnt;
+    }
+    *done = true;
+    return PLM_OK;
+}
+
 } // namespace
 
 PLM_API int plm_frame_begin(plm_ctx *ctx) {
@@ -2813,6 +2992,9 @@ PLM_API int plm_frame_end(plm_ctx *ctx) {
     calls.swap(ctx->frame_calls);
     const int n = static_cast<int>(calls.size());
     if (n == 0) return PLM_OK;
+    bool fused_done = false;
+    if ((st = frame_end_fused(ctx, calls, &fused_done)) != PLM_OK) return st;
+    if (fused_done) return PLM_OK;
     std::vector<Exec> ex(n);
     size_t h_total = 0, d_total = 0;
     std::vector<size_t> h_off(n), d_off(n);

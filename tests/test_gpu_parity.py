@@ -411,6 +411,88 @@ def test_frame_session_equals_separate_calls(M):
     assert M.match(prev.pdesc_l, curr.pdesc_l, 0.9, []) == want[2] or True     # the context is usable afterwards
 
 
+def _match_case(rng, n1, n2, tie):
+    d2 = synth.tie_stress_desc(rng, n2) if tie else synth.rand_desc(rng, n2)
+    if tie:
+        return synth.tie_stress_desc(rng, n1), d2
+    d1 = synth.rand_desc(rng, n1)
+    k = min(n1, n2) * 2 // 3
+    if k:
+        d1[rng.choice(n1, k, replace=False)] = synth.flip_bits(rng, d2[rng.choice(n2, k, replace=False)], 0.08)
+    return d1, d2
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_frame_session_one_launch_vs_oracle(M, plm_lib, fused):
+    """A frame session runs as ONE launch (frame_fused_kernel: one 8-CTA cluster per recorded call) whenever every call
+    is frame-sized.  Sessions made of the matchGrid cases (points and lines, ties, off-grid rows, bad items, NaN
+    directions, stale in/out entries) and of match / matchNNR calls from 1 x 2 up to 2048 x 2048 rows are held to the
+    oracle call by call; option frame_fused = 0 (one lane per call) must give the same."""
+    assert plm_lib.plm_set_option(b"frame_fused", fused) == 0
+    ctx = M.Context(0)
+    try:
+        rng = np.random.default_rng(2024)
+        grid_cases = [c for c in GRID_CASES if c[0] <= 2048]
+        match_cases = [(1, 2, True), (2, 1, False), (50, 3, True), (33, 1025, True), (600, 600, False), (200, 200, False),
+                       (640, 577, False), (75, 2048, False), (2048, 2048, False), (257, 9, True), (9, 257, True)]
+        sessions = [(grid_cases[:4], match_cases[:4]), (grid_cases[4:8], match_cases[4:8]), (grid_cases[8:], match_cases[8:]),
+                    ([], match_cases[:2]), (grid_cases[:1], [])]
+        for gcs, mcs in sessions:
+            for best_lr, ratio, nnr in ((1, 0.9, 0.9), (0, 0.75, 0.75), (1, 1.0, 0.75)):
+                want, bufs, pend = [], [], []
+                M.Config.bestLRMatches = bool(best_lr)
+                M.Config.minRatio12P = ratio
+                before = ctx.launch_count
+                with M.FrameSession(ctx):
+                    for n1, n2, is_lines, tie, win, bad, zl in gcs:
+                        case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=tie, win=win, bad_items=bad, zero_len=zl)
+                        stale = np.full(n1, -1, np.int32)
+                        stale[::9] = rng.integers(0, max(n2, 1), len(stale[::9]))
+                        want.append(oracle_grid(port, case, ratio, best_lr, m12=stale))
+                        buf = stale.copy()
+                        grid = (case["cell_start"], case["cell_items"], case["rows"], case["cols"])
+                        if is_lines:
+                            pend.append(M.matchGrid(case["coords"], case["d1"], grid, case["d2"], case["dirs2"], case["win"], buf, ctx=ctx))
+                        else:
+                            pend.append(M.matchGrid(case["coords"], case["d1"], grid, case["d2"], case["win"], buf, ctx=ctx))
+                        bufs.append(buf)
+                    for n1, n2, tie in mcs:
+                        d1, d2 = _match_case(rng, n1, n2, tie)
+                        stale = np.full(n1, -1, np.int32)
+                        stale[::7] = rng.integers(0, n2, len(stale[::7]))
+                        degenerate = n2 < 2 or n1 < 2     # undefined in the reference (matching.cpp:54): the oracle
+                        for fn, ofn in ((M.match, lambda: port.match(d1, d2, nnr, best_lr, m12=stale)),   # flags it;
+                                        (M.matchNNR, lambda: port.match_nnr(d1, d2, nnr, m12=stale))):    # held to the
+                            if degenerate:                                                                # stand-alone call
+                                ref = stale.copy()
+                                want.append((fn(d1, d2, nnr, ref), ref))
+                            else:
+                                want.append(ofn())
+                            buf = stale.copy()
+                            pend.append(fn(d1, d2, nnr, buf, ctx=ctx))
+                            bufs.append(buf)
+                launches = ctx.launch_count - before
+                if fused:
+                    assert launches == 1, launches
+                else:
+                    assert launches >= len(pend)
+                for k, ((n_o, m_o), n_g, m_g) in enumerate(zip(want, pend, bufs)):
+                    assert int(n_g) == n_o, (fused, k, best_lr, ratio)
+                    assert (m_g == m_o).all(), (fused, k, best_lr, ratio, np.flatnonzero(m_g != m_o)[:10])
+        # a call beyond the frame-sized limits sends the whole session down the lane path -- same results
+        d1, d2 = _match_case(rng, 2100, 300, False)
+        before = ctx.launch_count
+        buf = np.full(2100, -1, np.int32)
+        with M.FrameSession(ctx):
+            p = M.match(d1, d2, 0.9, buf, ctx=ctx)
+        n_o, m_o = port.match(d1, d2, 0.9, True)
+        assert int(p) == n_o and (buf == m_o).all() and ctx.launch_count - before > 1
+    finally:
+        M.Config.bestLRMatches = True
+        M.Config.minRatio12P = 0.9
+        plm_lib.plm_set_option(b"frame_fused", 1)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_match_grid_single_call_kernel_families(M, plm_lib, mode):
     """The three single-call kernels for frame-sized jobs -- one CTA (0), chunk phases on an 8-CTA cluster (1), the

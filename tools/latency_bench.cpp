@@ -110,7 +110,26 @@ static void frame_mode(int reps) {
         plm_match(nullptr, Ln.d1.data(), Ln.n, 32, Ln.d2.data(), Ln.n, 32, 0.9f, 1, t_l.data(), &c4[3]);
         plm_frame_end(nullptr);
     };
+    plm_set_option("frame_fused", 0);
+    const double session_lanes = median_us(session_frame, reps);
+    plm_set_option("frame_fused", 1);
     const double session = median_us(session_frame, reps);
+    // the same session through a window of +-3 cells (the keyframe matchers' window): ~6x the candidates per row
+    const int32_t win_kf[4] = {3, 3, 3, 3};
+    auto session_kf = [&] {
+        static std::vector<int32_t> a, b, t_p, t_l;
+        a.assign(P.n, -1); b.assign(Ln.n, -1); t_p.assign(P.n, -1); t_l.assign(Ln.n, -1);
+        int c[4];
+        plm_frame_begin(nullptr);
+        plm_match_grid_points(nullptr, P.coords.data(), P.d1.data(), P.n, 32, P.cell_start.data(), P.cell_items.data(), 48, 64, P.d2.data(), P.n, 32,
+                              win_kf, 0.9, 1, a.data(), &c[0]);
+        plm_match_grid_lines(nullptr, Ln.coords.data(), Ln.d1.data(), Ln.n, 32, Ln.cell_start.data(), Ln.cell_items.data(), 48, 64, Ln.d2.data(), Ln.n,
+                             32, Ln.dirs2.data(), 0.75, win_kf, 0.9, 1, b.data(), &c[1]);
+        plm_match(nullptr, P.d1.data(), P.n, 32, P.d2.data(), P.n, 32, 0.9f, 1, t_p.data(), &c[2]);
+        plm_match(nullptr, Ln.d1.data(), Ln.n, 32, Ln.d2.data(), Ln.n, 32, 0.9f, 1, t_l.data(), &c[3]);
+        plm_frame_end(nullptr);
+    };
+    const double session_w3 = median_us(session_kf, reps);
     // two threads, as the reference: a generation counter starts a stage, a done counter joins it
     std::atomic<int> go{0}, done{0};
     std::atomic<bool> quit{false};
@@ -139,8 +158,9 @@ static void frame_mode(int reps) {
     tp.join();
     tl.join();
     printf("frame (600 pts + 200 lines): stereo matchGrid + temporal match, 4 calls serial %7.1f us; points || lines on two host threads "
-           "(the reference's std::async structure) %7.1f us; one frame session (plm_frame_begin/end, one round trip) %7.1f us "
-           "[matches %d %d %d %d]\n", serial, threaded, session, c4[0], c4[1], c4[2], c4[3]);
+           "(the reference's std::async structure) %7.1f us; one frame session (plm_frame_begin/end): one lane per call %7.1f us, ONE launch "
+           "(frame_fused_kernel) %7.1f us, one launch with +-3 windows %7.1f us [matches %d %d %d %d]\n", serial, threaded, session_lanes, session,
+           session_w3, c4[0], c4[1], c4[2], c4[3]);
 }
 
 int main(int argc, char **argv) {
