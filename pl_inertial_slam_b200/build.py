@@ -49,7 +49,8 @@ def cuda_sources():
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     if force or _stale(LIB, cuda_sources()):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        extra = os.environ.get("PLM_BUILD_DEFINES", "").split()  # e.g. -DPLM_TIMELINE (debug phase stamps)
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
               ["-o", LIB, os.path.join(CSRC, "plmatch.cu")]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:
@@ -67,7 +68,7 @@ def build_tools(force: bool = False):
     if not os.path.exists(src) or not (force or _stale(out, [src, LIB])):
         return
     cmd = ["g++", "-O2", "-std=c++17", src, "-I", os.path.join(HERE, "..", "include"), "-L", LIBDIR, "-lplmatch",
-           "-Wl,-rpath,$ORIGIN/../pl_inertial_slam_b200/lib", "-o", out]
+           "-Wl,-rpath,$ORIGIN/../pl_inertial_slam_b200/lib", "-ldl", "-lpthread", "-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         print(res.stdout, res.stderr, file=sys.stderr)

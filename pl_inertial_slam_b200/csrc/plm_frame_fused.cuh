@@ -11,8 +11,9 @@
 //                    threads (column slices) whose packed top-2 keys meet in shared memory; direction 21 writes
 //                    matches_21 to global scratch; the last CTA of the job to finish runs the mutual check.
 //
-// The job table travels in the same host -> device copy as the descriptors, so a frame is: one copy in, one launch,
-// one copy out (plm_frame_end in plmatch.cu).
+// The job table travels in the same host -> device copy as the descriptors and the kernel stores the final match
+// vectors and counts straight into the pinned host block, so a frame is: one copy in, one launch, one synchronisation
+// (plm_frame_end in plmatch.cu).
 #pragma once
 #include "plm_grid.cuh"
 
@@ -35,11 +36,19 @@ struct MatchJob {
 struct alignas(16) FrameJobRec {
     int32_t kind;      // 0 = match / matchNNR, 1 = matchGrid
     int32_t cta_begin; // first CTA of the job in the grid (a multiple of FRAME_CLUSTER)
-    int32_t pad_[2];
+    int32_t *h_io;     // the job's [m12 | count] in the PINNED HOST block: the kernel stores the results there itself
     GridJob gj;
     GridParams gp;
     MatchJob mj;
 };
+
+// The job table is a kernel PARAMETER (constant bank): no dependent global loads before a CTA knows its job.
+constexpr int FRAME_MAX_JOBS = 12;
+struct FrameTable {
+    int32_t n_jobs, n_cta, pad_[2];
+    FrameJobRec job[FRAME_MAX_JOBS];
+};
+static_assert(sizeof(FrameTable) <= 4000, "the job table must fit the kernel parameter space");
 
 __host__ __device__ inline size_t match_cta_smem(int n1, int n2, int best_lr) {
     const int nt = best_lr ? (n1 > n2 ? n1 : n2) : n2;
@@ -109,7 +118,7 @@ __device__ __forceinline__ void match_rows_direction(const uint4 *__restrict__ q
 // StVO::match (matching.cpp:63-91) of one frame-sized job.  The job's CTAs are independent: CTA c takes a block of
 // query rows of one direction (the train side of that direction staged in shared memory).  The LAST CTA of the job to
 // finish (a counter in global memory, no waiting) runs the mutual check over all rows.
-__device__ __forceinline__ void match_job_device(const MatchJob &j, unsigned char *smem, int c) {
+__device__ __forceinline__ void match_job_device(const MatchJob &j, unsigned char *smem, int c, int32_t *h_io) {
     __shared__ int s_last;
     const int tid = threadIdx.x, NT = GRID_ROW_THREADS;
     const bool fwd = c < j.c12;
@@ -121,46 +130,72 @@ __device__ __forceinline__ void match_job_device(const MatchJob &j, unsigned cha
     uint32_t *part0 = reinterpret_cast<uint32_t *>(smem + static_cast<size_t>(nt) * 32);
     uint32_t *part1 = part0 + NT;
     if (nr > 0) {
-        stage_bytes(reinterpret_cast<unsigned char *>(st), fwd ? j.d2 : j.d1, static_cast<size_t>(nt) * 32);
+        stage_bytes_async(reinterpret_cast<unsigned char *>(st), fwd ? j.d2 : j.d1, static_cast<size_t>(nt) * 32);
+        prefetch_l2((fwd ? j.d1 : j.d2) + 2 * (row0 + tid % nr)); // the query row this thread loads next
+        stage_wait();
         __syncthreads();
     }
     if (fwd) match_rows_direction<true>(j.d1, row0, nr, st, nt, j.nnr, j.m12, j.count, part0, part1);
     else match_rows_direction<false>(j.d2, row0, nr, st, nt, j.nnr, j.m21, nullptr, part0, part1);
-    if (!j.best_lr) return;
     __threadfence(); // this CTA's slice of matches_12 / matches_21 and its count before the arrival
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(j.done, 1) == j.n_cta - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // mutual check (matching.cpp:80-86): every entry >= 0, stale ones included
-    int culled = 0;
-    for (int i1 = tid; i1 < j.n1; i1 += NT) {
-        const int32_t i2 = __ldcg(j.m12 + i1);
-        if (i2 >= 0 && (i2 >= j.n2 || __ldcg(j.m21 + i2) != i1)) {
-            j.m12[i1] = -1;
-            ++culled;
+    if (j.best_lr) {
+        // mutual check (matching.cpp:80-86): every entry >= 0, stale ones included
+        int culled = 0;
+        for (int i1 = tid; i1 < j.n1; i1 += NT) {
+            const int32_t i2 = __ldcg(j.m12 + i1);
+            if (i2 >= 0 && (i2 >= j.n2 || __ldcg(j.m21 + i2) != i1)) {
+                j.m12[i1] = -1;
+                ++culled;
+            }
         }
+        if (culled) atomicSub(j.count, culled);
+        __syncthreads();
     }
-    if (culled) atomicSub(j.count, culled);
+    // results straight into the pinned host block (no device -> host copy after the kernel)
+    for (int i1 = tid; i1 < j.n1; i1 += NT) h_io[i1] = __ldcg(j.m12 + i1);
+    if (tid == 0) h_io[j.n1] = atomicAdd(j.count, 0);
 }
 
-// Cluster dimension FRAME_CLUSTER; job k owns the CTAs [tab[k].cta_begin, tab[k + 1].cta_begin): exactly one cluster
-// for a matchGrid job, one or more for a match job (tab[n_jobs] is a sentinel record that carries the grid size).
+// Cluster dimension FRAME_CLUSTER; job k owns the CTAs [job[k].cta_begin, job[k + 1].cta_begin): exactly one cluster
+// for a matchGrid job, one or more for a match job.
 __global__ void __launch_bounds__(GRID_ROW_THREADS, 1)
-frame_fused_kernel(const FrameJobRec *__restrict__ tab, int n_jobs) {
+frame_fused_kernel(const __grid_constant__ FrameTable tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    PLM_TL(0);
     const int cta = static_cast<int>(blockIdx.x);
     int job = 0;
-    while (job + 1 < n_jobs && cta >= tab[job + 1].cta_begin) ++job; // uniform over the CTA (and its cluster)
-    const FrameJobRec *r = tab + job;
+    while (job + 1 < tab.n_jobs && cta >= tab.job[job + 1].cta_begin) ++job; // uniform over the CTA (and its cluster)
+    const FrameJobRec *r = &tab.job[job];
     const int c = cta - r->cta_begin;
+    int32_t *h_io = r->h_io;
     if (r->kind == 1) {
         if (r->gp.staged) grid_rows_device<1, 2>(r->gj, r->gp, c);
         else grid_rows_device<0, 2>(r->gj, r->gp, c);
+        // Results straight into the pinned host block: every CTA its own rows (their culls are its own), the count by
+        // the last CTA of the cluster to arrive (the word after the count is the job's arrival counter, zeroed by the host).
+        const int n1 = r->gj.n1, rpc = r->gp.rows_per_cta;
+        const int32_t *m12 = r->gj.m12;
+        __threadfence(); // this CTA's count updates before its arrival
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int32_t *arrive = r->gj.count + 1;
+            if (atomicAdd(arrive, 1) == FRAME_CLUSTER - 1) {
+                __threadfence();
+                h_io[n1] = atomicAdd(r->gj.count, 0);
+            }
+        }
+        const int i1 = c * rpc + static_cast<int>(threadIdx.x);
+        if (static_cast<int>(threadIdx.x) < rpc && i1 < n1) h_io[i1] = m12[i1];
+        PLM_TL(14);
     } else {
         const MatchJob mj = r->mj;
-        match_job_device(mj, smem_raw, c);
+        match_job_device(mj, smem_raw, c, h_io);
+        PLM_TL(15);
     }
 }
 

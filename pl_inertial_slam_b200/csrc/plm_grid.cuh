@@ -27,6 +27,15 @@ namespace plm {
 
 namespace cg = cooperative_groups;
 
+// Phase timeline of the one-launch frame kernel (debug builds only: PLM_BUILD_DEFINES=-DPLM_TIMELINE): thread 0 of a
+// CTA stamps clock64() at phase boundaries, tools/latency_bench prints the deltas.
+#ifdef PLM_TIMELINE
+__device__ long long g_timeline[128][24];
+#define PLM_TL(k) do { if (threadIdx.x == 0) g_timeline[blockIdx.x & 127][k] = clock64(); } while (0)
+#else
+#define PLM_TL(k) do { } while (0)
+#endif
+
 struct GridJob {
     const int32_t *coords;     // n1 x 2 (points) or n1 x 4 (lines), grid-cell coordinates
     const uint4 *d1;           // n1 query descriptors
@@ -58,7 +67,8 @@ struct GridParams {
     // fused kernel: when staged != 0 every input of the job is first copied into shared memory with
     // coalesced 128-bit loads (capacities below, in elements), so the per-row dependent accesses
     // (coords -> cell_start -> cell_items -> descriptor / threshold) cost shared-memory latency
-    int staged, cap_n1, cap_items, cap_pad_;
+    int staged, cap_n1, cap_items;
+    int n_items_p1; // row-parallel kernels: number of grid items + 1 when the host knows it (0: read cell_start[n_cells])
     double ratio, line_sim_th;
     // chunked (multi-CTA) launch only:
     uint16_t *cta_min;          // [n_cta][n2] per-CTA column minima, turned into thresholds in place
@@ -269,6 +279,24 @@ __device__ __forceinline__ void stage_bytes(unsigned char *dst, const void *src,
         for (size_t i = threadIdx.x; i < (n_bytes >> 2); i += blockDim.x) d1[i] = __ldg(s1 + i);
     }
 }
+
+// Same copy issued as 16-byte cp.async (LDGSTS): every region of a staging block is in flight before the first one
+// lands; stage_wait() + a CTA barrier make the data visible.  Falls back to the synchronous copy for a source that is
+// not 16-byte aligned.
+__device__ __forceinline__ void stage_bytes_async(unsigned char *dst, const void *src, size_t n_bytes) {
+    if ((reinterpret_cast<size_t>(src) & 15) != 0) {
+        stage_bytes(dst, src, n_bytes);
+        return;
+    }
+    const size_t n16 = n_bytes >> 4;
+    const unsigned char *sb = static_cast<const unsigned char *>(src);
+    const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + static_cast<uint32_t>(i << 4)), "l"(sb + (i << 4)) : "memory");
+    for (size_t i = (n16 << 4) + threadIdx.x; i < n_bytes; i += blockDim.x) dst[i] = sb[i];
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __host__ __device__ inline size_t grid_align16(size_t v) { return (v + 15) & ~size_t(15); }
 
@@ -777,6 +805,7 @@ grid_match_chunked_kernel(GridJob job, GridParams gp) {
 // thread re-walking its own row instead (slower, same result).
 constexpr int GRID_ROW_THREADS = 256;
 constexpr int GRID_SEG_TAB = 32;          // list segments a CTA can hand from pass 0 to pass 1
+constexpr int GRID_CLUSTER_MAX_CTAS = 8;   // CTAs of the one-launch cluster form (MODE 2)
 constexpr int GRID_ENT_PER_ROW = 64;      // hand-over capacity per row (slots; ~10 are used for points, ~50 for lines)
 
 struct GridRowsSmem { // layout of the work area, in bytes from the start of dynamic shared memory
@@ -854,19 +883,28 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
     bool items_staged = false;
     // pass 1 in its replay form (every pair of this CTA was handed over by pass 0) never touches the frame side
     const bool replay_only = MODE == 1 && gp.best_lr && gp.ent_g && gp.seg_cnt[cta] >= 0;
+    if (MODE == 2) { // the rows this thread will load in phase A: on their way into L2 while the frame side is staged
+        const long long i1 = static_cast<long long>(cta) * gp.rows_per_cta + tid;
+        if (tid < gp.rows_per_cta && i1 < n1) {
+            prefetch_l2(job.d1 + 2 * (i1 - job.q_row_base));
+            prefetch_l2(job.coords + (job.is_lines ? 4 : 2) * (i1 - job.q_row_base));
+        }
+    }
     if (STAGED && !replay_only) {
-        const int n_items = job.cell_start[n_cells];
-        stage_bytes(smem_raw + o_cs, job.cell_start, static_cast<size_t>(n_cells + 1) * 4);
-        stage_bytes(smem_raw + o_d2, job.d2, static_cast<size_t>(n2) * 32);
-        if (job.is_lines) stage_bytes(smem_raw + o_dir, job.dirs2, static_cast<size_t>(n2) * 16);
+        stage_bytes_async(smem_raw + o_cs, job.cell_start, static_cast<size_t>(n_cells + 1) * 4);
+        stage_bytes_async(smem_raw + o_d2, job.d2, static_cast<size_t>(n2) * 32);
+        if (job.is_lines) stage_bytes_async(smem_raw + o_dir, job.dirs2, static_cast<size_t>(n2) * 16);
+        const int n_items = gp.n_items_p1 > 0 ? gp.n_items_p1 - 1 : job.cell_start[n_cells];
         items_staged = n_items <= gp.cap_items;
-        if (items_staged) stage_bytes(smem_raw + o_ci, job.cell_items, static_cast<size_t>(max(n_items, 0)) * 4);
+        if (items_staged) stage_bytes_async(smem_raw + o_ci, job.cell_items, static_cast<size_t>(max(n_items, 0)) * 4);
+        stage_wait(); // visible to the CTA after the barrier that opens the first pass
         // the re-walk form (list overflow) goes through the job's pointers
         job.cell_start = cs;
         job.d2 = d2p;
         if (job.is_lines) job.dirs2 = reinterpret_cast<const double *>(dirp);
         if (items_staged) job.cell_items = s_items;
     }
+    PLM_TL(1);
     const long long cta_row0 = static_cast<long long>(cta) * gp.rows_per_cta;
     const int row_end = static_cast<int>(min(static_cast<long long>(n1), cta_row0 + gp.rows_per_cta));
     uint16_t *cta_min = MODE == 2 ? nullptr : gp.cta_min + static_cast<size_t>(cta) * n2;
@@ -977,7 +1015,9 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
                     ent[e] = v;
                 }
                 __syncthreads();
+                PLM_TL(8);
                 list_rounds(seg_total, base);
+                PLM_TL(9);
                 for (int i2 = tid; i2 < n2; i2 += NT) { // thresholds for the rows that follow
                     T[i2] = Tnew[i2];
                     B[i2] = D_INF;
@@ -1021,6 +1061,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
             rb1[tid] = KEY32_ABSENT;
         }
         __syncthreads();
+        if (PASS == 0) PLM_TL(2);
         int off = incl - S, total = 0;
 #pragma unroll
         for (int w = 0; w < GRID_ROW_THREADS / 32; ++w) {
@@ -1119,6 +1160,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
                     else emit(job.cell_items);
                 }
                 __syncthreads();
+                if (PASS == 0) PLM_TL(3);
                 if (n_seg > 1) seg_total = s_seg_end;
                 // pass 0: room for this segment's pairs in the CTA's hand-over region (uniform decision)
                 uint32_t *rec_dst = nullptr;
@@ -1154,6 +1196,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
                     }
                 }
                 __syncthreads();
+                if (PASS == 0) PLM_TL(4);
                 if (!thresholds) continue;
                 list_rounds(seg_total, base);
                 if (seg + 1 < n_seg || base + NT < row_end) next_thresholds(); // for the rows that follow
@@ -1239,17 +1282,30 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
             if (rank == 0)
                 for (int i = tid; i < n2; i += NT) gp.m21key[i] = KEY64_ABSENT;
             run_pass(std::integral_constant<int, 0>{}, cmin16, nullptr);
+            PLM_TL(5);
             cluster.sync();
+            PLM_TL(6);
+            // exclusive prefix-min over the lower-ranked CTAs: all remote loads of a column in flight together
+            const uint16_t *rem[GRID_CLUSTER_MAX_CTAS];
+#pragma unroll
+            for (int r = 0; r < GRID_CLUSTER_MAX_CTAS; ++r) rem[r] = cluster.map_shared_rank(cmin16, min(r, max(rank - 1, 0)));
             for (int i = tid; i < n2; i += NT) {
+                uint16_t v[GRID_CLUSTER_MAX_CTAS];
+#pragma unroll
+                for (int r = 0; r < GRID_CLUSTER_MAX_CTAS - 1; ++r) v[r] = (r < rank) ? rem[r][i] : D_INF;
                 uint16_t t = D_INF;
-                for (int r = 0; r < rank; ++r) t = min(t, cluster.map_shared_rank(cmin16, r)[i]);
+#pragma unroll
+                for (int r = 0; r < GRID_CLUSTER_MAX_CTAS - 1; ++r) t = min(t, v[r]);
                 Tnew[i] = t;
             }
             __syncthreads();
+            PLM_TL(7);
         }
         run_pass(std::integral_constant<int, 1>{}, nullptr, Tnew);
+        PLM_TL(10);
         if (gp.best_lr) {
             cluster.sync(); // every CTA's m21 keys are in; nobody's cmin16 is read any more
+            PLM_TL(11);
             // mutual check (matching.cpp:166-174) over this CTA's rows, stale entries included
             int culled = 0;
             for (long long i1 = cta_row0 + tid; i1 < row_end; i1 += NT) {
@@ -1264,6 +1320,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
                 }
             }
             if (culled) atomicSub(job.count, culled);
+            PLM_TL(12);
         }
     }
 }

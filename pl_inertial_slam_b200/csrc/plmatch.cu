@@ -152,6 +152,10 @@ struct Exec {
     size_t h_bytes = 0, d_bytes = 0;            // reported by phase SIZE
 };
 
+namespace {
+int frame_end_fused(plm_ctx *ctx, const plm_ctx::FrameCall *calls, int n, bool *done);
+}
+
 struct plm_db {
     plm_ctx *ctx = nullptr;
     uint4 *rows = nullptr;
@@ -743,12 +747,16 @@ static int match_impl(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, con
     if (n1 == 0) return PLM_OK;
     if (n2 == 0) return fail(PLM_E_TRAIN, "matchNNR: empty train set");
     if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
-    if (ctx->in_frame && !ex) { // frame session: record, run at plm_frame_end
+    if (!ex) { // frame session: record, run at plm_frame_end; a stand-alone frame-sized call is a session of one call
         plm_ctx::FrameCall c;
         c.kind = 0; c.d1 = d1; c.n1 = n1; c.step1 = step1; c.d2 = d2; c.n2 = n2; c.step2 = step2; c.nnr = nnr; c.best_lr = best_lr;
         c.m12 = m12_inout; c.n_matches = n_matches;
-        ctx->frame_calls.push_back(c);
-        return PLM_OK;
+        if (ctx->in_frame) {
+            ctx->frame_calls.push_back(c);
+            return PLM_OK;
+        }
+        bool done = false;
+        if ((st = frame_end_fused(ctx, &c, 1, &done)) != PLM_OK || done) return st;
     }
     const int phase = ex ? ex->phase : EXEC_ALL;
 
@@ -1112,14 +1120,18 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     if (n2 > GRID_N2_MAX) return fail(PLM_E_UNSUPPORTED, "matchGrid supports at most 32768 train features");
     if (n1 == 0) return PLM_OK;
     if ((st = resolve_ctx(ctx)) != PLM_OK) return st;
-    if (ctx->in_frame && !ex) { // frame session: record, run at plm_frame_end
+    if (!ex) { // frame session: record, run at plm_frame_end; a stand-alone frame-sized call is a session of one call
         plm_ctx::FrameCall c;
         c.kind = 1; c.is_lines = is_lines; c.coords = coords; c.d1 = d1; c.n1 = n1; c.step1 = step1; c.cell_start = cell_start;
         c.cell_items = cell_items; c.grid_rows = grid_rows; c.grid_cols = grid_cols; c.d2 = d2; c.n2 = n2; c.step2 = step2; c.dirs2 = dirs2;
         c.line_sim_th = line_sim_th; c.ratio = ratio; c.best_lr = best_lr; c.m12 = m12_inout; c.n_matches = n_matches;
         for (int i = 0; i < 4; ++i) c.win[i] = win[i];
-        ctx->frame_calls.push_back(c);
-        return PLM_OK;
+        if (ctx->in_frame) {
+            ctx->frame_calls.push_back(c);
+            return PLM_OK;
+        }
+        bool done = false;
+        if ((st = frame_end_fused(ctx, &c, 1, &done)) != PLM_OK || done) return st;
     }
     const int phase = ex ? ex->phase : EXEC_ALL;
 
@@ -2808,12 +2820,12 @@ int frame_run(plm_ctx *ctx, const plm_ctx::FrameCall &c, Exec *ex) {
 }
 
 // The whole session as ONE launch (csrc/plm_frame_fused.cuh): job table + in/out vectors + inputs of every call in one
-// pinned block -> one copy in, frame_fused_kernel (one 8-CTA cluster per call), one copy out of the in/out vectors.
+// pinned block -> one copy in, frame_fused_kernel (clusters of 8 CTAs per call), which stores the final in/out vectors and
+// counts straight into the pinned block (zero-copy), one synchronisation.
 // *done stays false when a call does not fit the fused kernel (the caller then runs one lane per call).
-int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, bool *done) {
+int frame_end_fused(plm_ctx *ctx, const plm_ctx::FrameCall *calls, int n, bool *done) {
     *done = false;
-    const int n = static_cast<int>(calls.size());
-    if (!g_frame_fused || g_grid_cluster < 2 || n > 64) return PLM_OK;
+    if (!g_frame_fused || g_grid_cluster < 2 || n > plm::FRAME_MAX_JOBS) return PLM_OK;
     struct Plan {
         size_t o_io = 0, o_d1 = 0, o_d2 = 0, o_xy = 0, o_cs = 0, o_ci = 0, o_dir = 0, o_scr = 0;
         int n_items = 0, n_cta = plm::FRAME_CLUSTER, c12 = 0;
@@ -2821,10 +2833,7 @@ int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, 
     };
     std::vector<Plan> plan(n);
     Layout L;
-    L.add(size_t(n + 1) * sizeof(plm::FrameJobRec)); // + the sentinel record
-    const size_t io_begin = L.total;
     for (int k = 0; k < n; ++k) plan[k].o_io = L.add(size_t(calls[k].n1) * 4 + 8); // m12, the counter, the arrival counter of a match job
-    const size_t io_end = L.total;
     size_t smem = 0;
     for (int k = 0; k < n; ++k) {
         const plm_ctx::FrameCall &c = calls[k];
@@ -2877,7 +2886,9 @@ int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, 
     static int t_n = 0;
     const auto t0 = std::chrono::steady_clock::now();
     char *HB = ctx->h_buf, *DB = ctx->d_buf;
-    plm::FrameJobRec *tab = reinterpret_cast<plm::FrameJobRec *>(HB);
+    plm::FrameTable table; // travels as the kernel parameter
+    std::memset(&table, 0, sizeof(table));
+    plm::FrameJobRec *tab = table.job;
     int n_cta_total = 0;
     for (int k = 0; k < n; ++k) {
         const plm_ctx::FrameCall &c = calls[k];
@@ -2891,6 +2902,7 @@ int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, 
         std::memset(HB + p.o_io + size_t(c.n1) * 4, 0, 8);
         int32_t *dm12 = reinterpret_cast<int32_t *>(DB + p.o_io);
         r.cta_begin = n_cta_total;
+        r.h_io = reinterpret_cast<int32_t *>(HB + p.o_io); // pinned + unified addressing: the same pointer on the device
         n_cta_total += p.n_cta;
         if (c.kind == 0) {
             r.mj.done = dm12 + c.n1 + 1;
@@ -2925,10 +2937,11 @@ int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, 
         r.gj.is_lines = c.is_lines;
         for (int i = 0; i < 4; ++i) r.gj.win[i] = c.win[i];
         r.gp = p.gp;
+        r.gp.n_items_p1 = p.n_items + 1;
         r.gp.m21key = reinterpret_cast<unsigned long long *>(DB + p.o_scr);
     }
-    std::memset(&tab[n], 0, sizeof(plm::FrameJobRec));
-    tab[n].cta_begin = n_cta_total;
+    table.n_jobs = n;
+    table.n_cta = n_cta_total;
     const auto t1 = std::chrono::steady_clock::now();
     CU_TRY(cudaMemcpyAsync(DB, HB, in_end, cudaMemcpyHostToDevice, ctx->stream));
     const auto t2 = std::chrono::steady_clock::now();
@@ -2945,11 +2958,10 @@ int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CU_TRY(cudaLaunchKernelEx(&cfg, plm::frame_fused_kernel, reinterpret_cast<const plm::FrameJobRec *>(DB), n));
+    CU_TRY(cudaLaunchKernelEx(&cfg, plm::frame_fused_kernel, table));
     ctx->launches++;
     const auto t3 = std::chrono::steady_clock::now();
-    CU_TRY(cudaMemcpyAsync(HB + io_begin, DB + io_begin, io_end - io_begin, cudaMemcpyDeviceToHost, ctx->stream));
-    const auto t4 = std::chrono::steady_clock::now();
+    const auto t4 = t3; // no copy out: the kernel stores the results into the pinned block itself
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     if (trace) {
         const auto t5 = std::chrono::steady_clock::now();
@@ -2974,6 +2986,14 @@ int frame_end_fused(plm_ctx *ctx, const std::vector<plm_ctx::FrameCall> &calls, 
 
 } // namespace
 
+#ifdef PLM_TIMELINE
+// debug builds: the phase stamps of the last frame_fused_kernel launch, [128 CTAs][24] SM clock values
+extern "C" __attribute__((visibility("default"))) int plm_debug_timeline(long long *out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, plm::g_timeline, sizeof(long long) * 128 * 24) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 PLM_API int plm_frame_begin(plm_ctx *ctx) {
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
@@ -2993,7 +3013,7 @@ PLM_API int plm_frame_end(plm_ctx *ctx) {
     const int n = static_cast<int>(calls.size());
     if (n == 0) return PLM_OK;
     bool fused_done = false;
-    if ((st = frame_end_fused(ctx, calls, &fused_done)) != PLM_OK) return st;
+    if ((st = frame_end_fused(ctx, calls.data(), n, &fused_done)) != PLM_OK) return st;
     if (fused_done) return PLM_OK;
     std::vector<Exec> ex(n);
     size_t h_total = 0, d_total = 0;

@@ -1,6 +1,7 @@
 // C-level latency of the host-buffer entry points (no Python in the loop).
 //   g++ -O2 -std=c++17 tools/latency_bench.cpp -Iinclude -Lpl_inertial_slam_b200/lib -lplmatch -Wl,-rpath,$PWD/pl_inertial_slam_b200/lib -o /tmp/latency_bench
 #include <algorithm>
+#include <dlfcn.h>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -130,6 +131,53 @@ static void frame_mode(int reps) {
         plm_frame_end(nullptr);
     };
     const double session_w3 = median_us(session_kf, reps);
+    if (std::getenv("PLM_LATENCY_TIMELINE")) { // debug builds (PLM_BUILD_DEFINES=-DPLM_TIMELINE): phase stamps of the frame kernel
+        typedef int (*tl_fn)(long long *);
+        tl_fn tl = reinterpret_cast<tl_fn>(dlsym(RTLD_DEFAULT, "plm_debug_timeline"));
+        if (!tl) {
+            printf("  no plm_debug_timeline in this build\n");
+        } else {
+            std::vector<long long> buf(128 * 24);
+            std::vector<double> acc(128 * 24, 0.0);
+            const int runs = 200;
+            for (int r = 0; r < runs + 20; ++r) {
+                session_frame();
+                if (r < 20) continue;
+                tl(buf.data());
+                for (int c = 0; c < 128; ++c)
+                    for (int k = 0; k < 24; ++k) acc[c * 24 + k] += double(buf[c * 24 + k] - buf[c * 24]) / runs;
+            }
+            printf("  phase stamps, SM cycles since kernel entry (mean of %d frames); columns = stamps 1..15\n", runs);
+            for (int c = 0; c < 96; ++c) {
+                if (c >= 16 && c % 8) continue;
+                printf("  cta %3d:", c);
+                for (int k = 1; k < 16; ++k) printf(" %7.0f", acc[c * 24 + k]);
+                printf("\n");
+            }
+        }
+    }
+    if (std::getenv("PLM_LATENCY_PARTS")) { // each call of the frame as a session of its own (kernel time per job under ncu)
+        static std::vector<int32_t> a, b, t_p, t_l;
+        int c;
+        auto one = [&](int which) {
+            a.assign(P.n, -1); b.assign(Ln.n, -1); t_p.assign(P.n, -1); t_l.assign(Ln.n, -1);
+            plm_frame_begin(nullptr);
+            if (which == 0)
+                plm_match_grid_points(nullptr, P.coords.data(), P.d1.data(), P.n, 32, P.cell_start.data(), P.cell_items.data(), 48, 64, P.d2.data(), P.n, 32,
+                                      win_st, 0.9, 1, a.data(), &c);
+            if (which == 1)
+                plm_match_grid_lines(nullptr, Ln.coords.data(), Ln.d1.data(), Ln.n, 32, Ln.cell_start.data(), Ln.cell_items.data(), 48, 64, Ln.d2.data(),
+                                     Ln.n, 32, Ln.dirs2.data(), 0.75, win_st, 0.9, 1, b.data(), &c);
+            if (which == 2) plm_match(nullptr, P.d1.data(), P.n, 32, P.d2.data(), P.n, 32, 0.9f, 1, t_p.data(), &c);
+            if (which == 3) plm_match(nullptr, Ln.d1.data(), Ln.n, 32, Ln.d2.data(), Ln.n, 32, 0.9f, 1, t_l.data(), &c);
+            if (which == 4)
+                plm_match_grid_points(nullptr, P.coords.data(), P.d1.data(), P.n, 32, P.cell_start.data(), P.cell_items.data(), 48, 64, P.d2.data(), P.n, 32,
+                                      win_kf, 0.9, 1, a.data(), &c);
+            plm_frame_end(nullptr);
+        };
+        const char *names[5] = {"grid points (10,0,0,0)", "grid lines", "match points", "match lines", "grid points +-3"};
+        for (int w = 0; w < 5; ++w) printf("  session of one call, %-24s %7.1f us\n", names[w], median_us([&] { one(w); }, reps));
+    }
     // two threads, as the reference: a generation counter starts a stage, a done counter joins it
     std::atomic<int> go{0}, done{0};
     std::atomic<bool> quit{false};
