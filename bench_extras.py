@@ -339,6 +339,7 @@ def map_to_frame(ctx, world: int = 1, rank: int = 0, host_call: bool = True) -> 
                 dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(3_000_000)   # ~1.5 ms of GPU spin: the host enqueues ahead, the events see device time only
             e0.record()
             for _ in range(reps):
                 r = fn()

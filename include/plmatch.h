@@ -363,6 +363,11 @@ typedef struct plm_dev_grid_args {
 int plm_dev_grid_colmin(plm_ctx *ctx, const plm_dev_grid_args *a, uint16_t *col_min_dev);
 int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const uint16_t *seed_dev, uint64_t *m21key_dev);
 int plm_dev_m21_from_keys(plm_ctx *ctx, const uint64_t *m21key_dev, int n2, int32_t *m21_dev);
+/* The complete matchGrid (StVO::matchGrid, matching.cpp:111-258) of device-resident rows against one frame on ONE device
+ * as a single call: minima pass, scan, match pass, mutual check -- four launches back to back.  fresh != 0: m12_inout
+ * is first filled with -1 and *count zeroed inside the first pass (a new matches_12 vector, as matchMap2KFPoints / Lines
+ * build it, mapHandler.cpp:583-803); fresh == 0: both are in/out like the host-buffer entry points. */
+int plm_dev_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a, int fresh);
 
 /* ---- top-2 exchange over NVLink peer memory (multi-GPU merge without a gather collective) ------ */
 /* The per-query top-2 merge of a row-sharded database (config 5) / local map (config 4) as ONE kernel: every

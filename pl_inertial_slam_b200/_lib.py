@@ -144,6 +144,7 @@ SIGNATURES = {
     "plm_dev_grid_colmin": (C.c_int, [vp, C.POINTER(DevGridArgs), vp]),
     "plm_dev_grid_match": (C.c_int, [vp, C.POINTER(DevGridArgs), vp, vp]),
     "plm_dev_m21_from_keys": (C.c_int, [vp, vp, C.c_int, vp]),
+    "plm_dev_match_grid": (C.c_int, [vp, C.POINTER(DevGridArgs), C.c_int]),
     "plm_peer_buffer_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "plm_peer_alloc": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), u8p]),
     "plm_peer_open": (C.c_int, [vp, u8p, C.POINTER(vp)]),

@@ -31,7 +31,7 @@ namespace cg = cooperative_groups;
 // CTA stamps clock64() at phase boundaries, tools/latency_bench prints the deltas.
 #ifdef PLM_TIMELINE
 __device__ long long g_timeline[128][24];
-#define PLM_TL(k) do { if (threadIdx.x == 0) g_timeline[blockIdx.x & 127][k] = clock64(); } while (0)
+#define PLM_TL(k) do { if (threadIdx.x == 0) g_timeline[blockIdx.x < 127 ? blockIdx.x : 127][k] = clock64(); } while (0)
 #else
 #define PLM_TL(k) do { } while (0)
 #endif
@@ -56,6 +56,10 @@ struct GridParams {
     int best_lr;
     int rows_per_warp;          // chunked launch only; the fused kernel derives it from n1
     int rows_per_cta, cap_pairs; // row-parallel launch (grid_rows_kernel): rows per CTA, pair-list capacity
+    // The rows at the START of the map have no thresholds yet (every pair survives into pass 1 and the record chains of
+    // a column are longest there), so the first head_ctas CTAs only take head_rows rows each: the spare CTA slots of
+    // the one-wave launch shorten the tail of pass 1.  0 = uniform.
+    int head_ctas, head_rows;
     // pass 0 -> pass 1 hand-over of the row-parallel launch: pass 0 leaves every pair it evaluated (i2 | row | D) in
     // ent_g (a fixed region of ent_per_cta entries per CTA) with one seg_tab record per list segment, so that pass 1
     // only streams them against its thresholds instead of walking the windows and computing the distances again.
@@ -63,7 +67,8 @@ struct GridParams {
     uint32_t *ent_g;
     int4 *seg_tab;      // [n_cta][GRID_SEG_TAB]: (offset in ent_g, entries, block of rows, 0)
     int32_t *seg_cnt;   // [n_cta]
-    int ent_per_cta, pad4_;
+    int ent_per_cta;
+    int init_flags; // pass 0 of the multi-launch form also initialises: bit 0 m12 = -1 for its rows, bit 1 *count = 0, bit 2 m21key = absent
     // fused kernel: when staged != 0 every input of the job is first copied into shared memory with
     // coalesced 128-bit loads (capacities below, in elements), so the per-row dependent accesses
     // (coords -> cell_start -> cell_items -> descriptor / threshold) cost shared-memory latency
@@ -862,6 +867,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
     __shared__ int s_warp_tot[GRID_ROW_THREADS / 32];
     __shared__ int s_seg_end;
     const int tid = threadIdx.x, NT = GRID_ROW_THREADS, lane = tid & 31, warp = tid >> 5;
+    if (MODE != 2) PLM_TL(MODE == 1 ? 15 : 0);
     const int n1 = job.n1, n2 = job.n2;
     const int n_cells = gp.grid_rows * gp.grid_cols;
     const GridRowsSmem L = grid_rows_layout(n2, job.is_lines != 0, gp.cap_pairs, n_cells, gp.cap_items, STAGED);
@@ -883,6 +889,13 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
     bool items_staged = false;
     // pass 1 in its replay form (every pair of this CTA was handed over by pass 0) never touches the frame side
     const bool replay_only = MODE == 1 && gp.best_lr && gp.ent_g && gp.seg_cnt[cta] >= 0;
+    if (MODE == 0 && gp.init_flags) { // plm_dev_match_grid: no separate memsets in front of the pass
+        if (cta == 0) {
+            if ((gp.init_flags & 4) && gp.m21key)
+                for (int i = tid; i < n2; i += NT) gp.m21key[i] = KEY64_ABSENT;
+            if ((gp.init_flags & 2) && tid == 0) *job.count = 0;
+        }
+    }
     if (MODE == 2) { // the rows this thread will load in phase A: on their way into L2 while the frame side is staged
         const long long i1 = static_cast<long long>(cta) * gp.rows_per_cta + tid;
         if (tid < gp.rows_per_cta && i1 < n1) {
@@ -904,9 +917,14 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
         if (job.is_lines) job.dirs2 = reinterpret_cast<const double *>(dirp);
         if (items_staged) job.cell_items = s_items;
     }
-    PLM_TL(1);
-    const long long cta_row0 = static_cast<long long>(cta) * gp.rows_per_cta;
-    const int row_end = static_cast<int>(min(static_cast<long long>(n1), cta_row0 + gp.rows_per_cta));
+    PLM_TL(MODE == 1 ? 16 : 1);
+    // the first head_ctas CTAs take head_rows rows each (short blocks at the start of the map, see GridParams)
+    const long long cta_row0 = cta < gp.head_ctas ? static_cast<long long>(cta) * gp.head_rows
+                                                  : static_cast<long long>(gp.head_ctas) * gp.head_rows +
+                                                        static_cast<long long>(cta - gp.head_ctas) * gp.rows_per_cta;
+    const int row_end = static_cast<int>(min(static_cast<long long>(n1), cta_row0 + (cta < gp.head_ctas ? gp.head_rows : gp.rows_per_cta)));
+    if (MODE == 0 && (gp.init_flags & 1))
+        for (long long i = cta_row0 + tid; i < row_end; i += NT) job.m12[i] = -1;
     uint16_t *cta_min = MODE == 2 ? nullptr : gp.cta_min + static_cast<size_t>(cta) * n2;
     uint16_t *cmin16 = reinterpret_cast<uint16_t *>(smem_raw + L.cmin);
 
@@ -931,6 +949,7 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
         }
     }
     __syncthreads();
+    if (PASS == 1) PLM_TL(7);
     const uint32_t utid = static_cast<uint32_t>(tid);
     // Rounds over the survivors in ent[0, seg_total) (entry = i2 << 17 | row << 9 | D; the proposals of round 0 are
     // already in K).  Per round ONE pass over the list: the entry that owns the column's minimum key is live, later
@@ -1005,14 +1024,22 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
                     src = rec_base + rec.x;
                     seg_total = rec.y;
                 }
-                for (int e = tid; e < seg_total; e += NT) {
-                    uint32_t v = src[e];
-                    if (v != PAIR_INVALID) {
-                        const uint32_t i2 = v >> 17, d = v & 0x1FFu;
-                        if (d < T[i2]) atomicMin(&K[i2], (d << 16) | ((v >> 9) & 0xFFu));
-                        else v = PAIR_INVALID;
+                // four entries per trip, loaded before any of them is processed: the list comes from global memory (L2)
+                // and the stores below would otherwise serialise the loads behind them
+                for (int e0 = tid; e0 < seg_total; e0 += 4 * NT) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = (e0 + u * NT < seg_total) ? src[e0 + u * NT] : PAIR_INVALID;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (e0 + u * NT >= seg_total) break;
+                        if (v[u] != PAIR_INVALID) {
+                            const uint32_t i2 = v[u] >> 17, d = v[u] & 0x1FFu;
+                            if (d < T[i2]) atomicMin(&K[i2], (d << 16) | ((v[u] >> 9) & 0xFFu));
+                            else v[u] = PAIR_INVALID;
+                        }
+                        ent[e0 + u * NT] = v[u];
                     }
-                    ent[e] = v;
                 }
                 __syncthreads();
                 PLM_TL(8);
@@ -1273,8 +1300,10 @@ __device__ __forceinline__ void grid_rows_device(GridJob job, GridParams gp, con
 
     if (MODE == 0) {
         run_pass(std::integral_constant<int, 0>{}, cta_min, nullptr);
+        PLM_TL(5);
     } else if (MODE == 1) {
         run_pass(std::integral_constant<int, 1>{}, nullptr, cta_min);
+        PLM_TL(10);
     } else {
         cg::cluster_group cluster = cg::this_cluster();
         const int rank = static_cast<int>(cluster.block_rank());

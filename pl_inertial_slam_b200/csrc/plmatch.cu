@@ -225,6 +225,7 @@ long long g_peer_spin_ticks = 4000000000ll; // bounded spin of the peer-memory k
 int g_knn_qpt = 1;      // 2: long scans with >= 4096 queries keep two queries per thread (variant 6); option "knn_qpt"
 int g_knn_fill = 1;     // long brute-force scans: uneven workers fill every CTA slot + shared second-best bound (0: off, measurement)
 int g_frame_fused = 1;  // frame sessions run as ONE launch (frame_fused_kernel) when every recorded call fits (0: one lane per call)
+int g_grid_head = 1;    // map-sized matchGrid: short CTAs at the start of the map (0: uniform rows per CTA, measurement / tests)
 int g_grid_rows = 1;    // map-sized matchGrid uses the row-parallel kernels (0: warp-per-chunk kernels, measurement / tests)
 
 // -1 = automatic (variant 3 for long slices, 1 otherwise); 0..3 force a variant (measurement only)
@@ -416,6 +417,10 @@ PLM_API int plm_set_option(const char *key, int value) {
     }
     if (std::strcmp(key, "knn_fill") == 0) {
         g_knn_fill = value ? 1 : 0;
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "grid_head") == 0) {
+        g_grid_head = value ? 1 : 0;
         return PLM_OK;
     }
     if (std::strcmp(key, "grid_rows") == 0) {
@@ -998,6 +1003,21 @@ int plan_map_grid(plm_ctx *ctx, long long n1, int n2, int n_cells, bool is_lines
         const long long per_cta = std::max<long long>(1, (blocks + resident - 1) / resident); // blocks of rows per CTA
         gp.rows_per_cta = static_cast<int>(per_cta * plm::GRID_ROW_THREADS);
         n_cta = static_cast<int>((n1 + gp.rows_per_cta - 1) / gp.rows_per_cta);
+        // spare slots of the wave go to short CTAs at the start of the map (GridParams::head_ctas)
+        gp.head_ctas = 0;
+        gp.head_rows = 0;
+        const int head_rows = 64;
+        for (long long h = g_grid_head ? std::min<long long>(64, resident - n_cta) : 0; h >= 8; --h) {
+            const long long covered = h * head_rows;
+            if (covered >= n1) continue;
+            const long long rest = (n1 - covered + gp.rows_per_cta - 1) / gp.rows_per_cta;
+            if (h + rest <= resident) {
+                gp.head_ctas = static_cast<int>(h);
+                gp.head_rows = head_rows;
+                n_cta = static_cast<int>(h + rest);
+                break;
+            }
+        }
         return PLM_OK;
     }
     const size_t budget = std::min<size_t>(optin, 200 * 1024);
@@ -1165,6 +1185,8 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
             int rpc = ((n1 + GRID_ROWS_CLUSTER_MAX - 1) / GRID_ROWS_CLUSTER_MAX + 31) / 32 * 32;
             rpc = std::min(rpc, plm::GRID_ROW_THREADS);
             gp.rows_per_cta = rpc;
+            gp.head_ctas = 0; // uniform rows: the CTA index is the cluster rank
+            gp.head_rows = 0;
             n_cta = (n1 + rpc - 1) / rpc;
             o_m21key = L.add(size_t(std::max(n2, 1)) * 8);
         }
@@ -1358,6 +1380,50 @@ PLM_API int plm_dev_grid_match(plm_ctx *ctx, const plm_dev_grid_args *a, const u
         CU_TRY(cudaGetLastError());
     }
     return launch_map_grid(ctx, 1, job, gp, warps, n_cta, smem);
+}
+
+// The complete matchGrid of device-resident rows against one frame on ONE device, as one call: pass 0 (which also
+// initialises the fresh match vector, the count and the per-column keys), scan, pass 1, mutual check from the keys --
+// four launches back to back, nothing else on the stream.
+PLM_API int plm_dev_match_grid(plm_ctx *ctx, const plm_dev_grid_args *a, int fresh) {
+    plm::GridJob job;
+    plm::GridParams gp;
+    int warps = 0, n_cta = 0;
+    size_t smem = 0;
+    char *X = nullptr;
+    int st = dev_grid_setup(ctx, a, job, gp, warps, n_cta, smem, align_up(size_t(std::max(a ? a->n2 : 0, 1)) * 8), &X);
+    if (st != PLM_OK) return st;
+    if (a->n1 == 0) {
+        if (fresh && a->count) CU_TRY(cudaMemsetAsync(a->count, 0, 4, ctx->stream));
+        return PLM_OK;
+    }
+    gp.m21key = reinterpret_cast<unsigned long long *>(X);
+    const bool two_pass = gp.best_lr && a->n2 > 0 && n_cta > 0;
+    if (two_pass && warps == 0) {
+        gp.init_flags = 4 | (fresh ? 3 : 0);
+    } else {
+        if (fresh) {
+            CU_TRY(cudaMemsetAsync(a->m12_inout, 0xFF, size_t(a->n1) * 4, ctx->stream));
+            CU_TRY(cudaMemsetAsync(a->count, 0, 4, ctx->stream));
+        }
+        if (two_pass) CU_TRY(cudaMemsetAsync(gp.m21key, 0xFF, size_t(a->n2) * 8, ctx->stream));
+    }
+    if (n_cta == 0) return PLM_OK;
+    if (a->n2 > 0) {
+        if (two_pass) {
+            if ((st = launch_map_grid(ctx, 0, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
+            plm::grid_scan_kernel<<<(a->n2 + 3) / 4, 128, 0, ctx->stream>>>(gp.cta_min, n_cta, a->n2, nullptr, nullptr);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+        if ((st = launch_map_grid(ctx, 1, job, gp, warps, n_cta, smem)) != PLM_OK) return st;
+    }
+    if (gp.best_lr) { // mutual check (matching.cpp:166-174), stale entries included
+        plm::cross_check_keys_kernel<<<(a->n1 + 127) / 128, 128, 0, ctx->stream>>>(a->m12_inout, a->n1, a->i1_base, gp.m21key, a->n2, a->count);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    return PLM_OK;
 }
 
 namespace {

@@ -628,6 +628,16 @@ class ShardedMap:
                    m12_inout: Optional[torch.Tensor] = None):
         dev = frame.d2.device
         n2 = frame.d2.shape[0]
+        if self.world == 1:
+            # one device: the whole matchGrid is one C call (four launches back to back, the fresh vector and the count
+            # are initialised inside the first pass)
+            fresh = m12_inout is None
+            m12 = torch.empty(self.n_rows, dtype=torch.int32, device=dev) if fresh else m12_inout.clone()
+            count = torch.empty(1, dtype=torch.int32, device=dev) if fresh else torch.zeros(1, dtype=torch.int32, device=dev)
+            a = self.ops._grid_args(self.coords, self.d1, 0, frame, win, ratio, line_sim_th, best_lr, m12, count)
+            self.ops._bind_stream()
+            L.check(self.ops.lib.plm_dev_match_grid(self.ops.ctx.handle, C.byref(a), int(fresh)), "plm_dev_match_grid")
+            return count, m12
         m12 = self._local_m12(m12_inout, dev)
         count = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.peer is not None and self.gatherer is not None and (n2 == 0 or self.peer.fits(8 * n2)):

@@ -319,13 +319,15 @@ def test_match_grid_map_scale_both_kernel_families(M, plm_lib, is_lines):
     stale = np.full(n1, -1, np.int32)
     stale[rng.choice(n1, 500, replace=False)] = rng.integers(0, n2, 500)
     n_o, m_o = oracle_grid(port, case, 0.9, 1, m12=stale)
-    for rows_mode in (1, 0):
+    for rows_mode, head in ((1, 1), (1, 0), (0, 1)):   # head = 0: uniform rows per CTA (no short CTAs at the start of the map)
         assert plm_lib.plm_set_option(b"grid_rows", rows_mode) == 0
+        assert plm_lib.plm_set_option(b"grid_head", head) == 0
         try:
             n_g, m_g = gpu_grid(case, 0.9, 1, m12=stale)
         finally:
             plm_lib.plm_set_option(b"grid_rows", 1)
-        assert n_g == n_o and (m_g == m_o).all(), rows_mode
+            plm_lib.plm_set_option(b"grid_head", 1)
+        assert n_g == n_o and (m_g == m_o).all(), (rows_mode, head)
 
 
 def test_match_grid_map_scale_wide_frame(M):

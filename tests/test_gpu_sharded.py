@@ -100,6 +100,37 @@ def test_sharded_classes_world1(ops):
     assert int(count2.item()) == n_o2 and (m12b.cpu().numpy() == m_o2).all()
 
 
+@pytest.mark.parametrize("is_lines", [False, True])
+def test_dev_match_grid_one_call(ops, is_lines):
+    """plm_dev_match_grid (ShardedMap.match_grid at world 1): the whole device-resident matchGrid as one C call --
+    fresh vector initialised inside the first pass, or an in/out vector with stale entries; both ratio modes; map-sized,
+    frame-sized and chunk-kernel (wide frame) shapes; an empty frame."""
+    from pl_inertial_slam_b200.database import GridFrame, ShardedMap
+    shapes = [(30000, 600), (700, 90), (3, 5), (5000, 20000)] if not is_lines else [(12000, 200), (650, 70)]
+    for n1, n2 in shapes:
+        rng = np.random.default_rng(n1 + n2 + int(is_lines))
+        case = random_grid_case(rng, n1, n2, is_lines=is_lines, win=(3, 3, 3, 3) if n2 < 10000 else (1, 1, 1, 1), zero_len=3 if is_lines else 0)
+        frame = GridFrame(torch.from_numpy(case["d2"]).cuda(), torch.from_numpy(case["cell_start"]).cuda(),
+                          torch.from_numpy(case["cell_items"]).cuda(), case["rows"], case["cols"],
+                          torch.from_numpy(case["dirs2"]).cuda() if is_lines else None)
+        smap = ShardedMap(n1, torch.from_numpy(case["d1"]).cuda(), torch.from_numpy(case["coords"]).cuda(), ops=ops)
+        stale = np.full(n1, -1, np.int32)
+        stale[::11] = rng.integers(0, n2, len(stale[::11]))
+        for best_lr in (True, False):
+            for m_in in (None, stale):
+                count, m12 = smap.match_grid(frame, case["win"], 0.9, 0.75, best_lr,
+                                             m12_inout=None if m_in is None else torch.from_numpy(m_in).cuda())
+                n_o, m_o = oracle_grid(port, case, 0.9, best_lr, m12=m_in)
+                assert int(count.item()) == n_o and (m12.cpu().numpy() == m_o).all(), (is_lines, n1, n2, best_lr, m_in is None)
+    if not is_lines:  # a frame without features: nothing matches, a fresh vector is all -1
+        case = random_grid_case(np.random.default_rng(1), 400, 0, win=(3, 3, 3, 3))
+        frame = GridFrame(torch.zeros((0, 32), dtype=torch.uint8).cuda(), torch.from_numpy(case["cell_start"]).cuda(),
+                          torch.zeros(1, dtype=torch.int32).cuda(), case["rows"], case["cols"])
+        smap = ShardedMap(400, torch.from_numpy(case["d1"]).cuda(), torch.from_numpy(case["coords"]).cuda(), ops=ops)
+        count, m12 = smap.match_grid(frame, case["win"], 0.9)
+        assert int(count.item()) == 0 and (m12.cpu().numpy() == -1).all()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_nccl_two_ranks():
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_gpu_check.py")
