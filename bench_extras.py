@@ -68,6 +68,26 @@ def frame_latency(ctx) -> dict:
     out["note"] = ("wall clock per host-buffer call incl. ctypes, pinned staging, H2D, kernels, D2H and the "
                    "stream sync; includes the Python binding overhead on both sides")
     out["gpu_launches"] = ctx.launch_count - launches0
+    # the four calls of the frame as ONE frame session (plm_frame_begin / plm_frame_end -> frame_fused_kernel: one copy
+    # in, one launch, results stored straight into the pinned host block): through the Python binding, and at C level
+    # by tools/latency_bench (no Python in the loop)
+    def session():
+        with M.FrameSession(ctx):
+            for fn in gpu.values():
+                fn()
+    l0 = ctx.launch_count
+    session()
+    out["frame_session"] = {"launches_per_frame": ctx.launch_count - l0, "python_ms": _median_ms(session)}
+    try:
+        import json as _json
+        import subprocess
+        tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "latency_bench")
+        res = subprocess.run([tool, "300"], capture_output=True, text=True, timeout=120)
+        for line in res.stdout.splitlines():
+            if line.startswith("JSON "):
+                out["frame_session"]["c_level"] = _json.loads(line[5:])
+    except Exception as e:  # noqa: BLE001
+        out["frame_session"]["c_level"] = {"error": repr(e)[:200]}
     # the same four calls at the reference's C++ signature level (StVO::matchGrid / match with cv::Mat, GridStructure,
     # std::vector<int>&): the GPU drop-in (libstvo_gpu.so: GridStructure -> CSR flattening, staging, copies and sync
     # inside the number) next to the reference's own matching.cpp, timed by the same C++ harness, no Python in the loop
@@ -86,6 +106,12 @@ def frame_latency(ctx) -> dict:
                     "temporal_match_lines_200": eng.time_match(prev.ldesc_l, curr.ldesc_l, 0.9, reps=reps),
                 }
                 sig[tag]["per_frame_total"] = sum(sig[tag].values())
+            # ... and the whole frame as ONE launch through StVO::GpuFrame (same types; GridStructure flattening, staging,
+            # copy in, launch and synchronisation inside the number)
+            _, _, med = dropin.gpu_frame((a["xy"], a["d1"], a["cell_start"], a["cell_items"], a["d2"], a["win"]),
+                                         (b["xyxy"], b["d1"], b["cell_start"], b["cell_items"], b["d2"], b["dirs2"], b["win"]),
+                                         (prev.pdesc_l, curr.pdesc_l), (prev.ldesc_l, curr.ldesc_l), a["rows"], a["cols"], 0.9, reps=200)
+            sig["gpu_dropin_us"]["one_launch_frame_StVO_GpuFrame"] = med
             out["stvo_signature_level"] = sig
     except Exception as e:  # noqa: BLE001
         out["stvo_signature_level"] = {"error": repr(e)[:200]}

@@ -477,6 +477,39 @@ class _Ref:
         return float(self.lib.plref_time_match_grid(int(is_lines), cop, p1, n1, s1, csp, cip, int(rows), int(cols), p2, n2, s2,
                                                     None if dr is None else dr.ctypes.data_as(_f64p), wp, int(reps)))
 
+    def gpu_frame(self, pts, lines, t_pts, t_lines, rows, cols, nnr, stale=None, reps=0):
+        """libstvo_gpu.so only: ONE frame through StVO::GpuFrame (the product's one-launch frame behind the StVO:: types).
+        pts = (xy, d1, cell_start, cell_items, d2, win); lines = (xyxy, d1, cell_start, cell_items, d2, dirs2, win);
+        t_pts / t_lines = (desc_prev, desc_curr).  stale: optional four in/out vectors.  Returns (counts[4], [m_sp, m_sl,
+        m_tp, m_tl], median microseconds or None)."""
+        c32 = lambda a: np.ascontiguousarray(a, np.int32).reshape(-1)  # noqa: E731
+        d8 = lambda a: np.ascontiguousarray(a, np.uint8).reshape(-1, 32)  # noqa: E731
+        xy, pd1, pcs, pci, pd2, pwin = pts
+        xyxy, ld1, lcs, lci, ld2, dirs2, lwin = lines
+        arrs = dict(xy=c32(xy), pd1=d8(pd1), pcs=c32(pcs), pci=c32(pci if len(pci) else np.zeros(1, np.int32)), pd2=d8(pd2), pwin=c32(pwin),
+                    xyxy=c32(xyxy), ld1=d8(ld1), lcs=c32(lcs), lci=c32(lci if len(lci) else np.zeros(1, np.int32)), ld2=d8(ld2),
+                    dirs=np.ascontiguousarray(dirs2, np.float64).reshape(-1), lwin=c32(lwin),
+                    tp1=d8(t_pts[0]), tp2=d8(t_pts[1]), tl1=d8(t_lines[0]), tl2=d8(t_lines[1]))
+        sizes = [len(arrs["pd1"]), len(arrs["ld1"]), len(arrs["tp1"]), len(arrs["tl1"])]
+        m = [np.full(n, -1, np.int32) if stale is None else np.array(stale[k], np.int32) for k, n in enumerate(sizes)]
+        counts = np.zeros(4, np.int32)
+        med = C.c_double(0.0)
+        u8 = lambda a: a.ctypes.data_as(_u8p)  # noqa: E731
+        i32 = lambda a: a.ctypes.data_as(_i32p)  # noqa: E731
+        fn = self.lib.plref_gpu_frame
+        fn.restype = C.c_int
+        fn.argtypes = [_i32p, _u8p, C.c_int, _i32p, _i32p, _u8p, C.c_int, _i32p, _i32p, _u8p, C.c_int, _i32p, _i32p, _u8p, C.c_int, _f64p,
+                       _i32p, C.c_int, C.c_int, _u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_float, _i32p, _i32p,
+                       _i32p, _i32p, _i32p, C.c_int, C.POINTER(C.c_double)]
+        st = fn(i32(arrs["xy"]), u8(arrs["pd1"]), sizes[0], i32(arrs["pcs"]), i32(arrs["pci"]), u8(arrs["pd2"]), len(arrs["pd2"]),
+                i32(arrs["pwin"]), i32(arrs["xyxy"]), u8(arrs["ld1"]), sizes[1], i32(arrs["lcs"]), i32(arrs["lci"]), u8(arrs["ld2"]),
+                len(arrs["ld2"]), arrs["dirs"].ctypes.data_as(_f64p), i32(arrs["lwin"]), int(rows), int(cols), u8(arrs["tp1"]), sizes[2],
+                u8(arrs["tp2"]), len(arrs["tp2"]), u8(arrs["tl1"]), sizes[3], u8(arrs["tl2"]), len(arrs["tl2"]), C.c_float(nnr),
+                i32(m[0]), i32(m[1]), i32(m[2]), i32(m[3]), i32(counts), int(reps), C.byref(med))
+        if st != 0:
+            raise RuntimeError("plref_gpu_frame failed")
+        return counts, m, (float(med.value) if reps > 0 else None)
+
     def set_threads(self, n: int):
         self.lib.plref_set_threads(int(n))
 

@@ -194,3 +194,62 @@ PLREF_API void plref_normalize(double *v) {
     v[0] = p.first;
     v[1] = p.second;
 }
+
+#ifdef PLM_STVO_GPU
+// The product's one-launch frame (StVO::GpuFrame, pl_inertial_slam_b200/csrc/stvo_gpu_frame.h) behind the same harness:
+// stereo matchGrid for points and lines + temporal match for points and lines of ONE frame, recorded with the
+// reference's own argument types (GridStructure, GridWindow, cv::Mat, std::vector) and executed by run().  Descriptor
+// rows are 32 bytes apart.  reps > 0 also returns the median wall time of the whole frame -- GridStructure
+// flattening, staging, the copy in, the launch and the synchronisation inside the number.
+#include "stvo_gpu_frame.h"
+PLREF_API int plref_gpu_frame(const int32_t *xy, const uint8_t *pd1, int np1, const int32_t *p_cs, const int32_t *p_ci, const uint8_t *pd2,
+                              int np2, const int32_t *p_win, const int32_t *xyxy, const uint8_t *ld1, int nl1, const int32_t *l_cs,
+                              const int32_t *l_ci, const uint8_t *ld2, int nl2, const double *dirs2, const int32_t *l_win, int rows,
+                              int cols, const uint8_t *tp1, int ntp1, const uint8_t *tp2, int ntp2, const uint8_t *tl1, int ntl1,
+                              const uint8_t *tl2, int ntl2, float nnr, int32_t *m_sp, int32_t *m_sl, int32_t *m_tp, int32_t *m_tl,
+                              int32_t *counts, int reps, double *median_out) {
+    StVO::GridStructure grid_p(rows, cols), grid_l(rows, cols);
+    fill_grid(grid_p, p_cs, p_ci);
+    fill_grid(grid_l, l_cs, l_ci);
+    StVO::GridWindow wp, wl;
+    wp.width = std::make_pair(p_win[0], p_win[1]);
+    wp.height = std::make_pair(p_win[2], p_win[3]);
+    wl.width = std::make_pair(l_win[0], l_win[1]);
+    wl.height = std::make_pair(l_win[2], l_win[3]);
+    const cv::Mat a_p = wrap(pd1, np1, 32), b_p = wrap(pd2, np2, 32), a_l = wrap(ld1, nl1, 32), b_l = wrap(ld2, nl2, 32);
+    const cv::Mat t_p1 = wrap(tp1, ntp1, 32), t_p2 = wrap(tp2, ntp2, 32), t_l1 = wrap(tl1, ntl1, 32), t_l2 = wrap(tl2, ntl2, 32);
+    std::vector<StVO::point_2d> pts(np1);
+    for (int i = 0; i < np1; i++) pts[i] = std::make_pair(xy[2 * i], xy[2 * i + 1]);
+    std::vector<StVO::line_2d> lines(nl1);
+    for (int i = 0; i < nl1; i++)
+        lines[i] = std::make_pair(std::make_pair(xyxy[4 * i], xyxy[4 * i + 1]), std::make_pair(xyxy[4 * i + 2], xyxy[4 * i + 3]));
+    std::vector<std::pair<double, double>> dirs(nl2);
+    for (int i = 0; i < nl2; i++) dirs[i] = std::make_pair(dirs2[2 * i], dirs2[2 * i + 1]);
+    std::vector<int> v_sp, v_sl, v_tp, v_tl;
+    int n_sp = 0, n_sl = 0, n_tp = 0, n_tl = 0;
+    auto frame = [&] {
+        v_sp.assign(m_sp, m_sp + np1); // in/out vectors as the caller handed them over
+        v_sl.assign(m_sl, m_sl + nl1);
+        v_tp.assign(m_tp, m_tp + ntp1);
+        v_tl.assign(m_tl, m_tl + ntl1);
+        StVO::GpuFrame f;
+        f.matchGrid(pts, a_p, grid_p, b_p, wp, v_sp, n_sp);
+        f.matchGrid(lines, a_l, grid_l, b_l, dirs, wl, v_sl, n_sl);
+        f.match(t_p1, t_p2, nnr, v_tp, n_tp);
+        f.match(t_l1, t_l2, nnr, v_tl, n_tl);
+        f.run();
+    };
+    try {
+        if (reps > 0 && median_out) *median_out = median_us(frame, reps);
+        frame();
+    } catch (const std::exception &) {
+        return -1;
+    }
+    std::copy(v_sp.begin(), v_sp.end(), m_sp);
+    std::copy(v_sl.begin(), v_sl.end(), m_sl);
+    std::copy(v_tp.begin(), v_tp.end(), m_tp);
+    std::copy(v_tl.begin(), v_tl.end(), m_tl);
+    counts[0] = n_sp; counts[1] = n_sl; counts[2] = n_tp; counts[3] = n_tl;
+    return 0;
+}
+#endif

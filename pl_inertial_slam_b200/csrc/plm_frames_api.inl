@@ -54,10 +54,11 @@ struct plm_frames {
         h_cap = align_up(bytes, 1 << 16);
         return PLM_OK;
     }
+    bool timing_events = false; // PLM_FRAMES_TRACE: per-chunk device timeline
     int event(size_t i, cudaEvent_t *out) {
         while (events.size() <= i) {
             cudaEvent_t e;
-            CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&e, timing_events ? cudaEventDefault : cudaEventDisableTiming));
             events.push_back(e);
         }
         *out = events[i];
@@ -563,6 +564,12 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;
     const bool trace = std::getenv("PLM_FRAMES_TRACE") != nullptr;
+    if (trace && !fr->timing_events) { // events created so far carry no time stamps: start over with timing ones
+        for (cudaEvent_t e : fr->events) cudaEventDestroy(e);
+        fr->events.clear();
+        fr->timing_events = true;
+    }
+    std::vector<cudaEvent_t> trace_out;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     if ((st = frames_layout(fr, desc_arena, n_rows, kp_arena, n_kp, ln_arena, n_ln, frames, n_frames, c)) != PLM_OK) return st;
@@ -614,7 +621,13 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
             break;
         }
         if ((st = frames_copy_out(fr, out, f0, f1, fr->s_out)) != PLM_OK) break;
-        if (trace) std::fprintf(stderr, "[plm_frames_process] chunk %d issued %.3f ms\n", k, since());
+        if (trace) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, fr->s_out);
+            trace_out.push_back(e);
+            std::fprintf(stderr, "[plm_frames_process] chunk %d issued %.3f ms\n", k, since());
+        }
     }
     next_chunk.store(n_chunks); // after a failure: helpers stop picking up chunks
     for (std::thread &t : helpers) t.join();
@@ -625,7 +638,18 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
     if (fr->s_lines) cudaStreamSynchronize(fr->s_lines);
     if (trace) std::fprintf(stderr, "[plm_frames_process] compute streams drained %.3f ms\n", since());
     cudaStreamSynchronize(fr->s_out);
-    if (trace) std::fprintf(stderr, "[plm_frames_process] copy-out stream drained %.3f ms\n", since());
+    if (trace) {
+        std::fprintf(stderr, "[plm_frames_process] copy-out stream drained %.3f ms\n", since());
+        for (size_t k = 0; k < trace_out.size(); ++k) { // device timeline of every chunk, relative to the start event
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, fr->events[0], fr->events[4 * k + 1]);
+            cudaEventElapsedTime(&b, fr->events[0], fr->events[4 * k + 2]);
+            cudaEventElapsedTime(&c, fr->events[0], trace_out[k]);
+            std::fprintf(stderr, "[plm_frames_process] chunk %zu frames %d..%d: copied in %.3f ms, computed %.3f ms, copied out %.3f ms\n", k,
+                         bounds[k], bounds[k + 1], a, b, c);
+            cudaEventDestroy(trace_out[k]);
+        }
+    }
     if (st != PLM_OK) return st;
     CU_TRY(cudaGetLastError());
     fr->ready = true;

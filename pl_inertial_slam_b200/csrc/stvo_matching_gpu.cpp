@@ -15,6 +15,7 @@
 //    `friend struct PlmGridAccess;` to GridStructure to skip the per-cell set round trip.
 #include "matching.h"
 
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <unordered_set>
@@ -25,6 +26,7 @@
 #include "config.h"
 #include "gridStructure.h"
 #include "plmatch.h"
+#include "stvo_gpu_frame.h"
 
 #ifdef PLM_GRIDSTRUCTURE_FRIEND
 namespace StVO {
@@ -116,62 +118,154 @@ int distance(const cv::Mat &a, const cv::Mat &b) {
     return dist;
 }
 
-int matchGrid(const std::vector<point_2d> &points1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
-              const GridWindow &w, std::vector<int> &matches_12) {
+} // namespace StVO
+
+namespace {
+
+// Flat arguments of one matchGrid call (coordinates, CSR grid, directions, window) built from the reference's types.
+struct GridArgs {
+    std::vector<int32_t> coords;
+    std::vector<double> dirs;
+    GridCsr csr;
+    int32_t win[4];
+};
+
+void grid_args_points(const std::vector<StVO::point_2d> &points1, const cv::Mat &desc1, const StVO::GridStructure &grid,
+                      const cv::Mat &desc2, const StVO::GridWindow &w, std::vector<int> &matches_12, GridArgs &a) {
     if (points1.size() != static_cast<size_t>(desc1.rows))
         throw std::runtime_error("[matchGrid] Each point needs a corresponding descriptor!");
     check_desc(desc1);
     check_desc(desc2);
     matches_12.resize(desc1.rows, -1);
-
-    std::vector<int32_t> xy(points1.size() * 2);
+    a.coords.resize(points1.size() * 2);
     for (size_t i = 0; i < points1.size(); ++i) {
-        xy[2 * i] = points1[i].first;
-        xy[2 * i + 1] = points1[i].second;
+        a.coords[2 * i] = points1[i].first;
+        a.coords[2 * i + 1] = points1[i].second;
     }
-    GridCsr csr;
-    flatten(grid, csr);
-    const int32_t win[4] = {w.width.first, w.width.second, w.height.first, w.height.second};
-    int matches = 0;
-    const int st = plm_match_grid_points(nullptr, xy.data(), rows_of(desc1), desc1.rows, static_cast<size_t>(desc1.step),
-                                         csr.cell_start.data(), csr.cell_items.data(), grid.rows, grid.cols, rows_of(desc2),
-                                         desc2.rows, static_cast<size_t>(desc2.step), win, Config::minRatio12P(),
-                                         Config::bestLRMatches() ? 1 : 0, matches_12.data(), &matches);
-    throw_status(st, "matchGrid");
-    return matches;
+    flatten(grid, a.csr);
+    a.win[0] = w.width.first; a.win[1] = w.width.second; a.win[2] = w.height.first; a.win[3] = w.height.second;
 }
 
-int matchGrid(const std::vector<line_2d> &lines1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
-              const std::vector<std::pair<double, double>> &directions2, const GridWindow &w, std::vector<int> &matches_12) {
+void grid_args_lines(const std::vector<StVO::line_2d> &lines1, const cv::Mat &desc1, const StVO::GridStructure &grid,
+                     const cv::Mat &desc2, const std::vector<std::pair<double, double>> &directions2, const StVO::GridWindow &w,
+                     std::vector<int> &matches_12, GridArgs &a) {
     if (lines1.size() != static_cast<size_t>(desc1.rows))
         throw std::runtime_error("[matchGrid] Each line needs a corresponding descriptor!");
     check_desc(desc1);
     check_desc(desc2);
     matches_12.resize(desc1.rows, -1);
-
-    std::vector<int32_t> xyxy(lines1.size() * 4);
+    a.coords.resize(lines1.size() * 4);
     for (size_t i = 0; i < lines1.size(); ++i) {
-        xyxy[4 * i] = lines1[i].first.first;
-        xyxy[4 * i + 1] = lines1[i].first.second;
-        xyxy[4 * i + 2] = lines1[i].second.first;
-        xyxy[4 * i + 3] = lines1[i].second.second;
+        a.coords[4 * i] = lines1[i].first.first;
+        a.coords[4 * i + 1] = lines1[i].first.second;
+        a.coords[4 * i + 2] = lines1[i].second.first;
+        a.coords[4 * i + 3] = lines1[i].second.second;
     }
     // the reference indexes directions2[i2] for every candidate i2 < desc2.rows (:221)
-    std::vector<double> dirs(static_cast<size_t>(desc2.rows) * 2, 0.0);
+    a.dirs.assign(static_cast<size_t>(desc2.rows) * 2, 0.0);
     for (size_t i = 0; i < directions2.size() && i < static_cast<size_t>(desc2.rows); ++i) {
-        dirs[2 * i] = directions2[i].first;
-        dirs[2 * i + 1] = directions2[i].second;
+        a.dirs[2 * i] = directions2[i].first;
+        a.dirs[2 * i + 1] = directions2[i].second;
     }
-    GridCsr csr;
-    flatten(grid, csr);
-    const int32_t win[4] = {w.width.first, w.width.second, w.height.first, w.height.second};
+    flatten(grid, a.csr);
+    a.win[0] = w.width.first; a.win[1] = w.width.second; a.win[2] = w.height.first; a.win[3] = w.height.second;
+}
+
+int call_grid_points(const GridArgs &a, const cv::Mat &desc1, const StVO::GridStructure &grid, const cv::Mat &desc2,
+                     std::vector<int> &matches_12, int *n_matches) {
+    return plm_match_grid_points(nullptr, a.coords.data(), rows_of(desc1), desc1.rows, static_cast<size_t>(desc1.step),
+                                 a.csr.cell_start.data(), a.csr.cell_items.data(), grid.rows, grid.cols, rows_of(desc2), desc2.rows,
+                                 static_cast<size_t>(desc2.step), a.win, Config::minRatio12P(),
+                                 Config::bestLRMatches() ? 1 : 0, matches_12.data(), n_matches);
+}
+
+int call_grid_lines(const GridArgs &a, const cv::Mat &desc1, const StVO::GridStructure &grid, const cv::Mat &desc2,
+                    std::vector<int> &matches_12, int *n_matches) {
+    return plm_match_grid_lines(nullptr, a.coords.data(), rows_of(desc1), desc1.rows, static_cast<size_t>(desc1.step),
+                                a.csr.cell_start.data(), a.csr.cell_items.data(), grid.rows, grid.cols, rows_of(desc2), desc2.rows,
+                                static_cast<size_t>(desc2.step), a.dirs.data(), Config::lineSimTh(), a.win,
+                                Config::minRatio12P(), Config::bestLRMatches() ? 1 : 0, matches_12.data(), n_matches);
+}
+
+} // namespace
+
+namespace StVO {
+
+int matchGrid(const std::vector<point_2d> &points1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
+              const GridWindow &w, std::vector<int> &matches_12) {
+    GridArgs a;
+    grid_args_points(points1, desc1, grid, desc2, w, matches_12, a);
     int matches = 0;
-    const int st = plm_match_grid_lines(nullptr, xyxy.data(), rows_of(desc1), desc1.rows, static_cast<size_t>(desc1.step),
-                                        csr.cell_start.data(), csr.cell_items.data(), grid.rows, grid.cols, rows_of(desc2),
-                                        desc2.rows, static_cast<size_t>(desc2.step), dirs.data(), Config::lineSimTh(), win,
-                                        Config::minRatio12P(), Config::bestLRMatches() ? 1 : 0, matches_12.data(), &matches);
-    throw_status(st, "matchGrid");
+    throw_status(call_grid_points(a, desc1, grid, desc2, matches_12, &matches), "matchGrid");
     return matches;
+}
+
+int matchGrid(const std::vector<line_2d> &lines1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
+              const std::vector<std::pair<double, double>> &directions2, const GridWindow &w, std::vector<int> &matches_12) {
+    GridArgs a;
+    grid_args_lines(lines1, desc1, grid, desc2, directions2, w, matches_12, a);
+    int matches = 0;
+    throw_status(call_grid_lines(a, desc1, grid, desc2, matches_12, &matches), "matchGrid");
+    return matches;
+}
+
+// ---- StVO::GpuFrame (stvo_gpu_frame.h): the calls of one frame as one launch -----------------------------------------
+struct GpuFrame::Scratch {
+    GridArgs a;
+};
+
+GpuFrame::GpuFrame() : open_(false) {
+    throw_status(plm_frame_begin(nullptr), "GpuFrame");
+    open_ = true;
+}
+
+GpuFrame::~GpuFrame() {
+    if (open_) plm_frame_end(nullptr);
+}
+
+void GpuFrame::matchNNR(const cv::Mat &desc1, const cv::Mat &desc2, float nnr, std::vector<int> &matches_12, int &n_matches) {
+    check_desc(desc1);
+    check_desc(desc2);
+    matches_12.resize(desc1.rows, -1);
+    n_matches = 0;
+    throw_status(plm_match_nnr(nullptr, rows_of(desc1), desc1.rows, static_cast<size_t>(desc1.step), rows_of(desc2), desc2.rows,
+                               static_cast<size_t>(desc2.step), nnr, matches_12.data(), &n_matches), "matchNNR");
+}
+
+void GpuFrame::match(const cv::Mat &desc1, const cv::Mat &desc2, float nnr, std::vector<int> &matches_12, int &n_matches) {
+    check_desc(desc1);
+    check_desc(desc2);
+    matches_12.resize(desc1.rows, -1);
+    n_matches = 0;
+    throw_status(plm_match(nullptr, rows_of(desc1), desc1.rows, static_cast<size_t>(desc1.step), rows_of(desc2), desc2.rows,
+                           static_cast<size_t>(desc2.step), nnr, Config::bestLRMatches() ? 1 : 0, matches_12.data(), &n_matches), "match");
+}
+
+void GpuFrame::matchGrid(const std::vector<point_2d> &points1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
+                         const GridWindow &w, std::vector<int> &matches_12, int &n_matches) {
+    keep_.push_back(std::unique_ptr<Scratch>(new Scratch));
+    GridArgs &a = keep_.back()->a;
+    grid_args_points(points1, desc1, grid, desc2, w, matches_12, a);
+    n_matches = 0;
+    throw_status(call_grid_points(a, desc1, grid, desc2, matches_12, &n_matches), "matchGrid");
+}
+
+void GpuFrame::matchGrid(const std::vector<line_2d> &lines1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
+                         const std::vector<std::pair<double, double>> &directions2, const GridWindow &w, std::vector<int> &matches_12,
+                         int &n_matches) {
+    keep_.push_back(std::unique_ptr<Scratch>(new Scratch));
+    GridArgs &a = keep_.back()->a;
+    grid_args_lines(lines1, desc1, grid, desc2, directions2, w, matches_12, a);
+    n_matches = 0;
+    throw_status(call_grid_lines(a, desc1, grid, desc2, matches_12, &n_matches), "matchGrid");
+}
+
+void GpuFrame::run() {
+    if (!open_) throw std::runtime_error("[plmatch] GpuFrame::run: the frame has already run");
+    open_ = false;
+    const int st = plm_frame_end(nullptr);
+    keep_.clear();
+    throw_status(st, "GpuFrame::run");
 }
 
 } // namespace StVO

@@ -93,6 +93,34 @@ def test_stvo_match_grid(plm_lib, is_lines):
                 assert n_g == n_o and (m_g == m_o).all()
 
 
+@needs_lib
+def test_stvo_gpu_frame_one_launch(plm_lib):
+    """StVO::GpuFrame (csrc/stvo_gpu_frame.h): the four matcher calls of one frame recorded with the reference's own
+    argument types and executed as one launch -- results equal the oracle call by call, stale in/out entries included."""
+    from pl_inertial_slam_b200 import synth as S
+    gpu = oracle.stvo_gpu
+    for seed, n_pts, n_lines in ((0, 600, 200), (1, 150, 40), (2, 5, 3)):
+        prev, curr = S.make_temporal_pair(S.SEED0 + 60 + seed, n_pts=n_pts, n_lines=n_lines)
+        a, b = S.stereo_points_grid_args(curr), S.stereo_lines_grid_args(curr)
+        rng = np.random.default_rng(seed)
+        stale = [np.full(n, -1, np.int32) for n in (n_pts, n_lines, len(prev.pdesc_l), len(prev.ldesc_l))]
+        for k, n2 in enumerate((n_pts, n_lines, len(curr.pdesc_l), len(curr.ldesc_l))):
+            stale[k][::6] = rng.integers(0, n2, len(stale[k][::6]))
+        for blr, ratio in ((1, 0.9), (0, 0.75)):
+            gpu.set_config(bool(blr), True, ratio, 0.75)
+            counts, m, _ = gpu.gpu_frame((a["xy"], a["d1"], a["cell_start"], a["cell_items"], a["d2"], a["win"]),
+                                         (b["xyxy"], b["d1"], b["cell_start"], b["cell_items"], b["d2"], b["dirs2"], b["win"]),
+                                         (prev.pdesc_l, curr.pdesc_l), (prev.ldesc_l, curr.ldesc_l), a["rows"], a["cols"], 0.9, stale=stale)
+            want = [port.match_grid_points(a["xy"], a["d1"], a["cell_start"], a["cell_items"], a["rows"], a["cols"], a["d2"], a["win"], ratio, blr, stale[0]),
+                    port.match_grid_lines(b["xyxy"], b["d1"], b["cell_start"], b["cell_items"], b["rows"], b["cols"], b["d2"], b["dirs2"], 0.75,
+                                          b["win"], ratio, blr, stale[1]),
+                    port.match(prev.pdesc_l, curr.pdesc_l, 0.9, blr, m12=stale[2]),
+                    port.match(prev.ldesc_l, curr.ldesc_l, 0.9, blr, m12=stale[3])]
+            for k, (n_o, m_o) in enumerate(want):
+                assert int(counts[k]) == n_o and (m[k] == m_o).all(), (seed, blr, k)
+    gpu.set_config(True, True, 0.9, 0.75)
+
+
 needs_map_lib = pytest.mark.skipif(not oracle.map_gpu.available(),
                                    reason="oracle/_ref/libmapfeatures_gpu.so not built (needs the reference headers)")
 

@@ -209,6 +209,9 @@ static void frame_mode(int reps) {
            "(the reference's std::async structure) %7.1f us; one frame session (plm_frame_begin/end): one lane per call %7.1f us, ONE launch "
            "(frame_fused_kernel) %7.1f us, one launch with +-3 windows %7.1f us [matches %d %d %d %d]\n", serial, threaded, session_lanes, session,
            session_w3, c4[0], c4[1], c4[2], c4[3]);
+    printf("JSON {\"frame_us\": {\"four_calls_serial\": %.1f, \"two_host_threads\": %.1f, \"session_one_lane_per_call\": %.1f, "
+           "\"session_one_launch\": %.1f, \"session_one_launch_pm3_windows\": %.1f}, \"features\": \"600 points + 200 lines per side\", "
+           "\"reps\": %d}\n", serial, threaded, session_lanes, session, session_w3, reps);
 }
 
 int main(int argc, char **argv) {

@@ -38,6 +38,37 @@ M.matchNNR(prev.ldesc_l, curr.ldesc_l, 0.9, [], ctx=ctx)
 M.stereo_filter_points(prev.kp_l, prev.kp_r, m_p, ctx=ctx)
 M.stereo_filter_lines(prev.ln_l, prev.ln_r, m_l, ctx=ctx)
 M.distances(prev.pdesc_l, prev.pdesc_r, ctx=ctx)
+M.line_pair_filter(prev.ln_l, prev.ln_r, m_l, ctx=ctx)
+# the same four matcher calls as ONE frame session: frame_fused_kernel with four jobs (one launch per frame)
+with M.FrameSession(ctx):
+    M.matchGrid(a["xy"], a["d1"], ga, a["d2"], a["win"], [], ctx=ctx)
+    M.matchGrid(b["xyxy"], b["d1"], gb, b["d2"], b["dirs2"], b["win"], [], ctx=ctx)
+    M.match(prev.pdesc_l, curr.pdesc_l, 0.9, [], ctx=ctx)
+    M.match(prev.ldesc_l, curr.ldesc_l, 0.9, [], ctx=ctx)
+# ... and with the one-launch form switched off: the per-call kernels (cluster matchGrid, brute-force slices + merge +
+# mutual check) that frames beyond the frame-sized limits still take
+from pl_inertial_slam_b200 import _lib as _L  # noqa: E402
+_L.load().plm_set_option(b"frame_fused", 0)
+M.matchGrid(a["xy"], a["d1"], ga, a["d2"], a["win"], [], ctx=ctx)
+M.matchGrid(b["xyxy"], b["d1"], gb, b["d2"], b["dirs2"], b["win"], [], ctx=ctx)
+M.match(prev.pdesc_l, curr.pdesc_l, 0.9, [], ctx=ctx)
+M.matchNNR(prev.ldesc_l, curr.ldesc_l, 0.9, [], ctx=ctx)
+_L.load().plm_set_option(b"frame_fused", 1)
+# local-map selection + reprojection gates of matchMap2KF* (map_select_kernel, gather_rows_kernel, map_gate_kernel)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+try:
+    from test_reproj import CAM, H, INV_H, INV_W, W, make_scene  # noqa: E402
+    from pl_inertial_slam_b200 import drivers as D  # noqa: E402
+    rngm = np.random.default_rng(7)
+    for lines_ in (False, True):
+        T_, X_, act_ = make_scene(5, 20_000 if quick else 70_000, lines_)
+        view_ = D.map_view(T_, CAM, INV_W, INV_H, W, H)
+        sel_, coords_, pf_ = D.mapSelect(X_, act_, view_)
+        m12_ = rngm.integers(-1, 300, len(sel_)).astype(np.int32)
+        feat_ = rngm.uniform(0, 700, (300, 2)) if not lines_ else rngm.normal(0, 1, (300, 3))
+        D.mapGate(pf_, m12_, feat_, 1.0, int((m12_ >= 0).sum()))
+except Exception as e:  # noqa: BLE001 -- the capture of the other kernels does not depend on this block
+    print("reprojection kernels skipped:", repr(e)[:200])
 
 # replay batch: fused matchGrid kernel (one CTA per job), list kernels of the brute-force path
 rp = synth.make_replay(synth.SEED0 + 3, 100 if quick else 300)
