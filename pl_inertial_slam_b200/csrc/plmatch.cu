@@ -73,6 +73,7 @@ struct plm_ctx {
     char *d_buf = nullptr;
     size_t d_cap = 0;
     char *h_buf = nullptr; // pinned
+    char *h_buf_dev = nullptr; // the same block as the device addresses it (zero-copy result stores of the frame kernel)
     size_t h_cap = 0;
     char *d_aux = nullptr; // second device scratch: survives the ensure_device of nested entry points
     size_t aux_cap = 0;
@@ -137,6 +138,10 @@ struct plm_ctx {
         const size_t cap = align_up(bytes + bytes / 4, 1 << 16);
         CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_buf), cap, cudaHostAllocDefault));
         h_cap = cap;
+        // the address kernels use for zero-copy stores into this block (equal to h_buf under unified addressing)
+        void *dp = nullptr;
+        h_buf_dev = (cudaHostGetDevicePointer(&dp, h_buf, 0) == cudaSuccess && dp) ? static_cast<char *>(dp) : nullptr;
+        if (!h_buf_dev) (void)cudaGetLastError();
         return PLM_OK;
     }
 };
@@ -2942,6 +2947,7 @@ int frame_end_fused(plm_ctx *ctx, const plm_ctx::FrameCall *calls, int n, bool *
     if (smem > ctx->smem_optin - 2048) return PLM_OK;
     int st;
     if ((st = ctx->ensure_pinned(in_end)) != PLM_OK) return st;
+    if (!ctx->h_buf_dev) return PLM_OK; // no device mapping of the pinned block: one lane per call
     if ((st = ctx->ensure_device(L.total)) != PLM_OK) return st;
     if (!ctx->frame_fused_attr_set) {
         CU_TRY(cudaFuncSetAttribute(plm::frame_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin - 2048)));
@@ -2968,7 +2974,7 @@ int frame_end_fused(plm_ctx *ctx, const plm_ctx::FrameCall *calls, int n, bool *
         std::memset(HB + p.o_io + size_t(c.n1) * 4, 0, 8);
         int32_t *dm12 = reinterpret_cast<int32_t *>(DB + p.o_io);
         r.cta_begin = n_cta_total;
-        r.h_io = reinterpret_cast<int32_t *>(HB + p.o_io); // pinned + unified addressing: the same pointer on the device
+        r.h_io = reinterpret_cast<int32_t *>(ctx->h_buf_dev + p.o_io); // the pinned block as the device addresses it
         n_cta_total += p.n_cta;
         if (c.kind == 0) {
             r.mj.done = dm12 + c.n1 + 1;

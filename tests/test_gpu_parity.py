@@ -495,6 +495,50 @@ def test_frame_session_one_launch_vs_oracle(M, plm_lib, fused):
         plm_lib.plm_set_option(b"frame_fused", 1)
 
 
+def test_frame_session_two_host_threads(M):
+    """Two host threads, each with its own context, run one-launch frame sessions at the same time (the reference's
+    points || lines std::async structure): the kernels of the two contexts overlap on the device, results stay exact."""
+    import threading
+    prev, curr = synth.make_temporal_pair(synth.SEED0 + 9)
+    a, b = synth.stereo_points_grid_args(curr), synth.stereo_lines_grid_args(curr)
+    ga = (a["cell_start"], a["cell_items"], a["rows"], a["cols"])
+    gb = (b["cell_start"], b["cell_items"], b["rows"], b["cols"])
+    M.Config.minRatio12P = 0.9
+    want_p = (port.match_grid_points(a["xy"], a["d1"], a["cell_start"], a["cell_items"], a["rows"], a["cols"], a["d2"], a["win"], 0.9, True),
+              port.match(prev.pdesc_l, curr.pdesc_l, 0.9, True))
+    want_l = (port.match_grid_lines(b["xyxy"], b["d1"], b["cell_start"], b["cell_items"], b["rows"], b["cols"], b["d2"], b["dirs2"], 0.75,
+                                    b["win"], 0.9, True),
+              port.match(prev.ldesc_l, curr.ldesc_l, 0.9, True))
+    errors = []
+
+    def worker(lines):
+        try:
+            ctx = M.Context(0)
+            for _ in range(200):
+                m_s = np.full(len(b["d1"]) if lines else len(a["d1"]), -1, np.int32)
+                m_t = np.full(len(prev.ldesc_l) if lines else len(prev.pdesc_l), -1, np.int32)
+                with M.FrameSession(ctx):
+                    if lines:
+                        r_s = M.matchGrid(b["xyxy"], b["d1"], gb, b["d2"], b["dirs2"], b["win"], m_s, ctx=ctx)
+                        r_t = M.match(prev.ldesc_l, curr.ldesc_l, 0.9, m_t, ctx=ctx)
+                    else:
+                        r_s = M.matchGrid(a["xy"], a["d1"], ga, a["d2"], a["win"], m_s, ctx=ctx)
+                        r_t = M.match(prev.pdesc_l, curr.pdesc_l, 0.9, m_t, ctx=ctx)
+                want = want_l if lines else want_p
+                if int(r_s) != want[0][0] or not (m_s == want[0][1]).all() or int(r_t) != want[1][0] or not (m_t == want[1][1]).all():
+                    errors.append(("mismatch", lines))
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in (False, True)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_match_grid_single_call_kernel_families(M, plm_lib, mode):
     """The three single-call kernels for frame-sized jobs -- one CTA (0), chunk phases on an 8-CTA cluster (1), the
