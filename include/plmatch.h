@@ -132,6 +132,8 @@ int plm_match(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8
  * StereoFrameHandler::f2fTracking (stereoFrame.cpp:75-76, stereoFrameHandler.cpp:142-143) without host threads. */
 int plm_frame_begin(plm_ctx *ctx);
 int plm_frame_end(plm_ctx *ctx);
+/* 1 while a frame session is open on the context (NULL = the calling thread's default context), else 0. */
+int plm_frame_active(plm_ctx *ctx);
 
 /* StVO::matchGrid, points.  xy = n1 x (x, y) grid-cell coordinates of the queries.
  * Grid = CSR of GridStructure over the train features: cell (x, y) has id x * grid_rows + y,

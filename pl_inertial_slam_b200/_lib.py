@@ -106,6 +106,7 @@ SIGNATURES = {
     "plm_match_nnr": (C.c_int, [vp] + _DESC + _DESC + [C.c_float, i32p, intp]),
     "plm_match": (C.c_int, [vp] + _DESC + _DESC + [C.c_float, C.c_int, i32p, intp]),
     "plm_frame_begin": (C.c_int, [vp]),
+    "plm_frame_active": (C.c_int, [vp]),
     "plm_frame_end": (C.c_int, [vp]),
     "plm_match_grid_points": (C.c_int, [vp, i32p] + _DESC + [i32p, i32p, C.c_int, C.c_int] + _DESC +
                               [i32p, C.c_double, C.c_int, i32p, intp]),

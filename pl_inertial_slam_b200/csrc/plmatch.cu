@@ -3075,6 +3075,11 @@ PLM_API int plm_frame_begin(plm_ctx *ctx) {
     return PLM_OK;
 }
 
+PLM_API int plm_frame_active(plm_ctx *ctx) {
+    if (!ctx) ctx = g_tls.ctx;
+    return ctx && ctx->in_frame ? 1 : 0;
+}
+
 PLM_API int plm_frame_end(plm_ctx *ctx) {
     int st = resolve_ctx(ctx);
     if (st != PLM_OK) return st;

@@ -44,6 +44,13 @@ void check_desc(const cv::Mat &m) {
     if (m.rows > 0 && m.cols != 32) throw std::runtime_error("[plmatch] descriptors must be 32 bytes (256 bit) wide");
 }
 
+// The free functions return their count by value: inside an open frame session the library would record the address of
+// a local -- use StVO::GpuFrame (stvo_gpu_frame.h) there.
+void no_open_frame(const char *where) {
+    if (plm_frame_active(nullptr))
+        throw std::logic_error(std::string("[plmatch] StVO::") + where + " called inside an open frame session; record the call with StVO::GpuFrame");
+}
+
 void throw_status(int st, const char *where) {
     if (st == PLM_OK) return;
     if (st == PLM_E_TRAIN) throw std::runtime_error("[matchNNR] Different size for matches and descriptors!");
@@ -86,6 +93,7 @@ void flatten(const StVO::GridStructure &grid, GridCsr &csr) {
 namespace StVO {
 
 int matchNNR(const cv::Mat &desc1, const cv::Mat &desc2, float nnr, std::vector<int> &matches_12) {
+    no_open_frame("matchNNR");
     check_desc(desc1);
     check_desc(desc2);
     matches_12.resize(desc1.rows, -1);
@@ -97,6 +105,7 @@ int matchNNR(const cv::Mat &desc1, const cv::Mat &desc2, float nnr, std::vector<
 }
 
 int match(const cv::Mat &desc1, const cv::Mat &desc2, float nnr, std::vector<int> &matches_12) {
+    no_open_frame("match");
     check_desc(desc1);
     check_desc(desc2);
     matches_12.resize(desc1.rows, -1);
@@ -193,6 +202,7 @@ namespace StVO {
 
 int matchGrid(const std::vector<point_2d> &points1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
               const GridWindow &w, std::vector<int> &matches_12) {
+    no_open_frame("matchGrid");
     GridArgs a;
     grid_args_points(points1, desc1, grid, desc2, w, matches_12, a);
     int matches = 0;
@@ -202,6 +212,7 @@ int matchGrid(const std::vector<point_2d> &points1, const cv::Mat &desc1, const 
 
 int matchGrid(const std::vector<line_2d> &lines1, const cv::Mat &desc1, const GridStructure &grid, const cv::Mat &desc2,
               const std::vector<std::pair<double, double>> &directions2, const GridWindow &w, std::vector<int> &matches_12) {
+    no_open_frame("matchGrid");
     GridArgs a;
     grid_args_lines(lines1, desc1, grid, desc2, directions2, w, matches_12, a);
     int matches = 0;
