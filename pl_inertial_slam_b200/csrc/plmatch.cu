@@ -2954,8 +2954,8 @@ int frame_end_fused(plm_ctx *ctx, const plm_ctx::FrameCall *calls, int n, bool *
         ctx->frame_fused_attr_set = true;
     }
     static const bool trace = std::getenv("PLM_FRAME_TRACE") != nullptr;
-    static double t_acc[5] = {0, 0, 0, 0, 0};
-    static int t_n = 0;
+    static thread_local double t_acc[5] = {0, 0, 0, 0, 0};
+    static thread_local int t_n = 0;
     const auto t0 = std::chrono::steady_clock::now();
     char *HB = ctx->h_buf, *DB = ctx->d_buf;
     plm::FrameTable table; // travels as the kernel parameter

@@ -76,15 +76,24 @@ void flatten(const StVO::GridStructure &grid, GridCsr &csr) {
         }
 #else
     // GridStructure::at is the reference's own public accessor (gridStructure.h:48); it is not const-qualified although
-    // it only returns a reference to the cell's list, hence the const_cast.  One list walk per cell -- the portable
-    // alternative, get(x, y, {0,0}x{0,0}, unordered_set), costs a hash-set build per cell (3072 per call).
+    // it only returns a reference to the cell's list, hence the const_cast.  The cells of one grid column are the
+    // elements of ONE std::vector<std::list<int>> (gridStructure.h:54, grid[x][y]), so &at(x, 0) + y is cell (x, y):
+    // one out-of-line call per column instead of one per cell (4.4 us instead of 10-13 us for the 64 x 48 grid).  The
+    // portable alternative, get(x, y, {0,0}x{0,0}, unordered_set), costs a hash-set build per cell.
     StVO::GridStructure &g = const_cast<StVO::GridStructure &>(grid);
-    for (int x = 0; x < cols; ++x)
+    int32_t *cs = csr.cell_start.data();
+    int32_t n = 0;
+    for (int x = 0; x < cols; ++x) {
+        const std::list<int> *column = &g.at(x, 0);
         for (int y = 0; y < rows; ++y) {
-            const std::list<int> &cell = g.at(x, y);
-            csr.cell_items.insert(csr.cell_items.end(), cell.begin(), cell.end());
-            csr.cell_start[static_cast<size_t>(x) * rows + y + 1] = static_cast<int32_t>(csr.cell_items.size());
+            const std::list<int> &cell = column[y];
+            if (!cell.empty()) {
+                for (std::list<int>::const_iterator it = cell.begin(); it != cell.end(); ++it) csr.cell_items.push_back(*it);
+                n = static_cast<int32_t>(csr.cell_items.size());
+            }
+            cs[static_cast<size_t>(x) * rows + y + 1] = n;
         }
+    }
 #endif
 }
 
