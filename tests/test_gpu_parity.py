@@ -495,6 +495,60 @@ def test_frame_session_one_launch_vs_oracle(M, plm_lib, fused):
         plm_lib.plm_set_option(b"frame_fused", 1)
 
 
+def test_frame_session_random_shapes(M):
+    """Randomised differential test of the one-launch frame kernel: 40 sessions of 1-4 matchGrid and 0-4 match / matchNNR
+    calls with log-uniform sizes (1 ... 2048 rows per side), random windows, ratios, tie-heavy or planted-match
+    descriptors and stale in/out entries, every call against the oracle."""
+    ctx = M.Context(0)
+    rng = np.random.default_rng(77)
+    size = lambda lo=1: int(np.clip(np.exp(rng.uniform(np.log(lo), np.log(2048))), lo, 2048))  # noqa: E731
+    try:
+        for sess in range(40):
+            best_lr = bool(rng.integers(0, 2))
+            ratio = float(rng.choice([0.75, 0.9, 1.0]))
+            nnr = float(rng.choice([0.75, 0.9]))
+            M.Config.bestLRMatches = best_lr
+            M.Config.minRatio12P = ratio
+            want, pend, bufs = [], [], []
+            before = ctx.launch_count
+            with M.FrameSession(ctx):
+                for _ in range(int(rng.integers(1, 5))):
+                    is_lines = bool(rng.integers(0, 2))
+                    n1, n2 = size(), size()
+                    win = tuple(int(v) for v in rng.integers(0, 12, 4))
+                    case = random_grid_case(rng, n1, n2, is_lines=is_lines, tie=bool(rng.integers(0, 2)), win=win,
+                                            bad_items=int(rng.integers(0, 3)) if not is_lines else 0, zero_len=2 if is_lines else 0)
+                    stale = np.full(n1, -1, np.int32)
+                    stale[::5] = rng.integers(0, n2, len(stale[::5]))
+                    want.append(oracle_grid(port, case, ratio, best_lr, m12=stale))
+                    buf = stale.copy()
+                    grid = (case["cell_start"], case["cell_items"], case["rows"], case["cols"])
+                    if is_lines:
+                        pend.append(M.matchGrid(case["coords"], case["d1"], grid, case["d2"], case["dirs2"], case["win"], buf, ctx=ctx))
+                    else:
+                        pend.append(M.matchGrid(case["coords"], case["d1"], grid, case["d2"], case["win"], buf, ctx=ctx))
+                    bufs.append(buf)
+                for _ in range(int(rng.integers(0, 5))):
+                    n1, n2 = size(2), size(2)
+                    d1, d2 = _match_case(rng, n1, n2, bool(rng.integers(0, 2)))
+                    stale = np.full(n1, -1, np.int32)
+                    stale[::4] = rng.integers(0, n2, len(stale[::4]))
+                    buf = stale.copy()
+                    if rng.integers(0, 2):
+                        want.append(port.match(d1, d2, nnr, best_lr, m12=stale))
+                        pend.append(M.match(d1, d2, nnr, buf, ctx=ctx))
+                    else:
+                        want.append(port.match_nnr(d1, d2, nnr, m12=stale))
+                        pend.append(M.matchNNR(d1, d2, nnr, buf, ctx=ctx))
+                    bufs.append(buf)
+            assert ctx.launch_count - before == 1
+            for k, ((n_o, m_o), n_g, m_g) in enumerate(zip(want, pend, bufs)):
+                assert int(n_g) == n_o and (m_g == m_o).all(), (sess, k, best_lr, ratio, len(m_o), np.flatnonzero(m_g != m_o)[:8])
+    finally:
+        M.Config.bestLRMatches = True
+        M.Config.minRatio12P = 0.9
+
+
 def test_frame_session_two_host_threads(M):
     """Two host threads, each with its own context, run one-launch frame sessions at the same time (the reference's
     points || lines std::async structure): the kernels of the two contexts overlap on the device, results stay exact."""
