@@ -1005,8 +1005,16 @@ int plan_map_grid(plm_ctx *ctx, long long n1, int n2, int n_cells, bool is_lines
             per_sm = 1;
         const long long resident = static_cast<long long>(ctx->sm_count) * per_sm;
         const long long blocks = (n1 + plm::GRID_ROW_THREADS - 1) / plm::GRID_ROW_THREADS;
-        const long long per_cta = std::max<long long>(1, (blocks + resident - 1) / resident); // blocks of rows per CTA
-        gp.rows_per_cta = static_cast<int>(per_cta * plm::GRID_ROW_THREADS);
+        if (blocks >= resident) {
+            const long long per_cta = (blocks + resident - 1) / resident; // whole blocks of rows per CTA
+            gp.rows_per_cta = static_cast<int>(per_cta * plm::GRID_ROW_THREADS);
+        } else {
+            // fewer rows than one wave of full blocks: spread them over every resident slot (>= 64 rows per CTA, whole
+            // warps) -- the pair-list phases use all 256 threads of a CTA whatever its row count, and dense windows
+            // (lines: ~50 slots per row) make those phases the bulk of the work
+            const long long per = (n1 + resident - 1) / resident;
+            gp.rows_per_cta = static_cast<int>(std::min<long long>(plm::GRID_ROW_THREADS, std::max<long long>(64, (per + 31) / 32 * 32)));
+        }
         n_cta = static_cast<int>((n1 + gp.rows_per_cta - 1) / gp.rows_per_cta);
         // spare slots of the wave go to short CTAs at the start of the map (GridParams::head_ctas)
         gp.head_ctas = 0;
