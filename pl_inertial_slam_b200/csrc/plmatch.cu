@@ -325,6 +325,14 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
     int min_rows = INT_MAX;
     for (int i = 0; i < n_tasks; ++i) min_rows = std::min<long long>(min_rows, std::min<long long>(tp.t[i].n2, INT_MAX));
     int variant = knn_variant_for(min_rows >= 65536 ? 4096 : 64);
+    if (variant == 1 && g_knn_variant < 0 && min_rows >= 64) {
+        // a short train side but a lot of work (the match fallback of the local map, 200 000 x 600 in both directions):
+        // the 13-LOP3 distance with the per-pair update (variant 5) -- a few per cent there (0.369 -> 0.358 ms; 0.335 ms when the plan is made for it too); frame-sized calls keep
+        // variant 1, whose stages need no in-place transform
+        long long pairs = 0;
+        for (int i = 0; i < n_tasks; ++i) pairs = std::max(pairs, static_cast<long long>(tp.t[i].n1) * tp.t[i].n2);
+        if (pairs >= (1ll << 26)) variant = 5;
+    }
     if (n_tasks == 1 && tp.t[0].threads == 2 * threads) variant = 6; // planned with two queries per thread
     if (variant >= 2 && g_knn_fill) {
         // the shared second-best bounds live behind each task's partial results (build_knn_task reserved the room)
@@ -630,8 +638,9 @@ int build_knn_task(plm_ctx *ctx, Layout &L, plm::KnnTask &t, KnnPlan &plan, cons
     t.m = nullptr;
     t.count = nullptr;
     t.gthr = nullptr;
+    // behind the partial results: room for the per-query bound the workers of a launch share (launch_knn_slices)
     part_off = L.add(size_t(plan.n_workers + (plan.extra_qb ? 1 : 0)) * size_t(std::max(n1, 1)) * sizeof(ulonglong2) +
-                     (plan.share_thr ? align_up(size_t(std::max(n1, 1)) * 4) : 0));
+                     align_up(size_t(std::max(n1, 1)) * 4));
     return PLM_OK;
 }
 
