@@ -1189,7 +1189,10 @@ int match_grid_impl(plm_ctx *ctx, int is_lines, const int32_t *coords, const uin
     const size_t in_bytes = L.total;
     const size_t staged = L.total;
 
-    const bool fused = n1 <= GRID_FUSED_MAX_ROWS && n1 < (1 << plm::GRID_KEY_BITS);
+    // single-launch kernels: the per-column arrays of at least one chunk (8 bytes per train feature) must fit shared memory;
+    // wider train sides take the multi-launch kernels whatever the number of rows
+    const bool fused = n1 <= GRID_FUSED_MAX_ROWS && n1 < (1 << plm::GRID_KEY_BITS) &&
+                       size_t(8) * size_t(std::max(n2, 1)) + 1024 <= ctx->smem_optin - 2048;
     int warps = 0, n_cta = 0;
     size_t map_smem = 0;
     size_t o_cta_min = 0, o_m21key = 0, o_m21 = 0, o_handover = 0;

@@ -549,6 +549,19 @@ def test_frame_session_random_shapes(M):
         M.Config.minRatio12P = 0.9
 
 
+@pytest.mark.parametrize("n1,n2", [(400, 9000), (1500, 6000), (2048, 2048), (64, 32000)])
+def test_frame_kernel_wide_train_sides(M, n1, n2):
+    """Frame-sized query sides against wide train sides: the per-column work arrays of the cluster matchGrid grow to
+    ~150 KB of shared memory per CTA (n2 = 9000); beyond that (n2 = 32 000) the call leaves the one-launch path."""
+    rng = np.random.default_rng(n1 + n2)
+    ctx = M.Context(0)
+    case = random_grid_case(rng, n1, n2, tie=False, win=(2, 2, 2, 2))
+    for best_lr in (1, 0):
+        n_o, m_o = oracle_grid(port, case, 0.9, best_lr)
+        n_g, m_g = gpu_grid(case, 0.9, best_lr, ctx=ctx)
+        assert n_g == n_o and (m_g == m_o).all(), best_lr
+
+
 def test_frame_session_two_host_threads(M):
     """Two host threads, each with its own context, run one-launch frame sessions at the same time (the reference's
     points || lines std::async structure): the kernels of the two contexts overlap on the device, results stay exact."""
