@@ -124,12 +124,18 @@ int plm_match(plm_ctx *ctx, const uint8_t *d1, int n1, size_t step1, const uint8
 
 /* Frame session: the matcher calls of ONE frame as one host <-> device round trip.  Between plm_frame_begin and
  * plm_frame_end the plm_match_nnr / plm_match / plm_match_grid_points / plm_match_grid_lines calls made on this context
- * (NULL = the calling thread's default context) validate their arguments and are RECORDED; plm_frame_end then packs
- * all inputs into one pinned block, issues the copies and kernels of the independent calls on three streams so that
- * they overlap, synchronises once and writes every m12_inout / n_matches.  The recorded pointers (descriptors, grids,
- * m12_inout, n_matches) must stay valid until plm_frame_end returns; results are only defined after it.  This is the
- * stereo (points || lines) + temporal (points || lines) structure of StereoFrame::extractStereoFeatures /
- * StereoFrameHandler::f2fTracking (stereoFrame.cpp:75-76, stereoFrameHandler.cpp:142-143) without host threads. */
+ * (NULL = the calling thread's default context) validate their arguments and are RECORDED; plm_frame_end executes them.
+ * When every recorded call is frame-sized (matchGrid: n1 <= 2048 and a train side whose work arrays fit shared memory;
+ * match: n1, n2 <= 2048; at most 12 calls) the whole session is ONE kernel (frame_fused_kernel, csrc/plm_frame_fused.cuh):
+ * all inputs packed into one pinned block, one host -> device copy, one launch -- a cluster of 8 CTAs per matchGrid call,
+ * independent CTAs per match call, the job table in the kernel parameters -- and the kernel stores every m12_inout /
+ * n_matches straight into the pinned block (no device -> host copy), one synchronisation.  Otherwise each call runs its
+ * own copy-in / kernels / copy-out on one of four streams, one synchronisation at the end (option "frame_fused" = 0
+ * forces this form).  The recorded pointers (descriptors, grids, m12_inout, n_matches) must stay valid until
+ * plm_frame_end returns; results are only defined after it.  This is the stereo (points || lines) + temporal
+ * (points || lines) structure of StereoFrame::extractStereoFeatures / StereoFrameHandler::f2fTracking
+ * (stereoFrame.cpp:75-76, stereoFrameHandler.cpp:142-143) without host threads.  A stand-alone frame-sized call takes
+ * the same kernel as a session of one call.  C++ hosts: StVO::GpuFrame (csrc/stvo_gpu_frame.h). */
 int plm_frame_begin(plm_ctx *ctx);
 int plm_frame_end(plm_ctx *ctx);
 /* 1 while a frame session is open on the context (NULL = the calling thread's default context), else 0. */
