@@ -100,12 +100,13 @@ __device__ __forceinline__ void back_projection(const FrameCfg &c, double u, dou
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-stereo_frame_kernel(const StereoJob *__restrict__ jobs, const FrameCfg cfg, const StereoCaps caps) {
+stereo_frame_kernel(const StereoJob *__restrict__ jobs, const size_t job_stride, const FrameCfg cfg, const StereoCaps caps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int32_t s_part[THREADS / 32 + 1];
     __shared__ int s_count, s_run;
     constexpr int W = THREADS / 32;
-    const StereoJob sj = jobs[blockIdx.x];
+    // the jobs of a frame sit in one record (plm_frames_api.inl FrameJobs): job_stride bytes from one frame to the next
+    const StereoJob sj = *reinterpret_cast<const StereoJob *>(reinterpret_cast<const char *>(jobs) + blockIdx.x * job_stride);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_l = sj.n_l, n_r = sj.n_r;
     const bool lines = sj.is_lines != 0;
@@ -381,10 +382,10 @@ __device__ __forceinline__ bool nnr_accept_f32(uint32_t k0, uint32_t k1, float n
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-f2f_match_kernel(const F2FJob *__restrict__ jobs, int best_lr) {
+f2f_match_kernel(const F2FJob *__restrict__ jobs, const size_t job_stride, int best_lr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_count;
-    const F2FJob job = jobs[blockIdx.x];
+    const F2FJob job = *reinterpret_cast<const F2FJob *>(reinterpret_cast<const char *>(jobs) + blockIdx.x * job_stride);
     const int tid = threadIdx.x, lane = tid & 31;
     const int n1 = min(*job.n1_ptr, job.cap1), n2 = min(*job.n2_ptr, job.cap2);
     // matchF2FPoints / Lines return early when either frame has no stereo features

@@ -26,7 +26,7 @@ struct plm_frames {
     std::vector<int64_t> lp_off, ll_off;
     std::vector<plm_frames_chunk> chunks;
     size_t o_desc = 0, o_kp = 0, o_ln = 0, o_cdesc_p = 0, o_cdesc_l = 0;
-    size_t o_sjobs_p = 0, o_sjobs_l = 0, o_fjobs_p = 0, o_fjobs_l = 0;
+    size_t o_jobs = 0; // [n_frames] FrameJobs
     size_t o_m12_p = 0, o_m12_l = 0, o_kept_p = 0, o_kept_l = 0, o_pt_disp = 0, o_pt_P = 0, o_ls_disp = 0, o_ls_sP = 0,
            o_ls_eP = 0, o_ls_le = 0, o_f2f_p = 0, o_f2f_l = 0, o_counts = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr, s_lines = nullptr;
@@ -85,13 +85,19 @@ inline long long line_walk_cells(double x1, double y1, double x2, double y2) {
     return n > 0 ? n : 0;
 }
 
+// The four jobs of one frame as one record: a chunk of consecutive frames is ONE host -> device copy of the job tables.
+struct FrameJobs {
+    plm::StereoJob sp, sl; // stereo stage: points, lines
+    plm::F2FJob fp, fl;    // temporal stage against the previous frame: points, lines
+};
+
 template <int THREADS>
 int launch_stereo(plm_ctx *ctx, cudaStream_t stream, const plm::StereoJob *jobs, int n_jobs, const plm::FrameCfg &cfg,
                   const plm::StereoCaps &caps, size_t smem) {
     if (n_jobs == 0) return PLM_OK;
     CU_TRY(cudaFuncSetAttribute(plm::stereo_frame_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-    plm::stereo_frame_kernel<THREADS><<<n_jobs, THREADS, smem, stream>>>(jobs, cfg, caps);
+    plm::stereo_frame_kernel<THREADS><<<n_jobs, THREADS, smem, stream>>>(jobs, sizeof(FrameJobs), cfg, caps);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;
@@ -102,7 +108,7 @@ int launch_f2f(plm_ctx *ctx, cudaStream_t stream, const plm::F2FJob *jobs, int n
     if (n_jobs == 0) return PLM_OK;
     CU_TRY(cudaFuncSetAttribute(plm::f2f_match_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-    plm::f2f_match_kernel<THREADS><<<n_jobs, THREADS, smem, stream>>>(jobs, best_lr);
+    plm::f2f_match_kernel<THREADS><<<n_jobs, THREADS, smem, stream>>>(jobs, sizeof(FrameJobs), best_lr);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return PLM_OK;
@@ -156,13 +162,10 @@ int frames_layout(plm_frames *fr, const uint8_t *desc_arena, int64_t n_rows, con
     fr->o_f2f_p = L.add(size_t(NP) * 4);
     fr->o_f2f_l = L.add(size_t(NL) * 4);
     fr->o_counts = L.add(F * 6 * 4);
-    fr->o_sjobs_p = L.add(F * sizeof(plm::StereoJob));
-    fr->o_sjobs_l = L.add(F * sizeof(plm::StereoJob));
-    fr->o_fjobs_p = L.add(F * sizeof(plm::F2FJob));
-    fr->o_fjobs_l = L.add(F * sizeof(plm::F2FJob));
+    fr->o_jobs = L.add(F * sizeof(FrameJobs));
     int st = fr->ensure(L.total);
     if (st != PLM_OK) return st;
-    if ((st = fr->ensure_tab(2 * F * (sizeof(plm::StereoJob) + sizeof(plm::F2FJob)))) != PLM_OK) return st;
+    if ((st = fr->ensure_tab(F * sizeof(FrameJobs))) != PLM_OK) return st;
     fr->n_frames = n_frames;
     fr->NP = NP;
     fr->NL = NL;
@@ -280,10 +283,7 @@ FrameChunkPrep frames_chunk_prep(const plm_frames *fr, const float *ln_arena, co
     // ---- job tables of the chunk ---------------------------------------------------------------------------
     char *D = fr->d_buf;
     const size_t F = size_t(std::max(fr->n_frames, 1));
-    plm::StereoJob *sp = reinterpret_cast<plm::StereoJob *>(fr->h_tab);
-    plm::StereoJob *sl = sp + F;
-    plm::F2FJob *fp = reinterpret_cast<plm::F2FJob *>(sl + F);
-    plm::F2FJob *fl = fp + F;
+    FrameJobs *tab = reinterpret_cast<FrameJobs *>(fr->h_tab);
     const uint4 *d_desc = reinterpret_cast<const uint4 *>(D + fr->o_desc);
     const float *d_kp = reinterpret_cast<const float *>(D + fr->o_kp);
     const float *d_ln = reinterpret_cast<const float *>(D + fr->o_ln);
@@ -292,7 +292,7 @@ FrameChunkPrep frames_chunk_prep(const plm_frames *fr, const float *ln_arena, co
     const std::vector<int64_t> &lp_off = fr->lp_off, &ll_off = fr->ll_off;
     for (int f = f0; f < f1; ++f) {
         const plm_frame_rec &r = frames[f];
-        plm::StereoJob &a = sp[f];
+        plm::StereoJob &a = tab[f].sp;
         std::memset(&a, 0, sizeof(a));
         a.geo_l = d_kp + 2 * r.kp_l;
         a.geo_r = d_kp + 2 * r.kp_r;
@@ -307,7 +307,7 @@ FrameChunkPrep frames_chunk_prep(const plm_frames *fr, const float *ln_arena, co
         a.n_l = r.n_pl;
         a.n_r = r.n_pr;
         a.is_lines = 0;
-        plm::StereoJob &b = sl[f];
+        plm::StereoJob &b = tab[f].sl;
         std::memset(&b, 0, sizeof(b));
         b.geo_l = d_ln + 4 * r.ln_l;
         b.geo_r = d_ln + 4 * r.ln_r;
@@ -325,8 +325,8 @@ FrameChunkPrep frames_chunk_prep(const plm_frames *fr, const float *ln_arena, co
         b.n_r = r.n_lr;
         b.is_lines = 1;
         // temporal job of (frame f - 1, frame f); row 0 of the tables stays unused
-        plm::F2FJob &p = fp[f];
-        plm::F2FJob &q = fl[f];
+        plm::F2FJob &p = tab[f].fp;
+        plm::F2FJob &q = tab[f].fl;
         std::memset(&p, 0, sizeof(p));
         std::memset(&q, 0, sizeof(q));
         if (f >= 1) {
@@ -361,17 +361,11 @@ int frames_chunk_copy(plm_frames *fr, FrameChunkPrep &pr, const uint8_t *desc_ar
     char *D = fr->d_buf;
     const int f0 = pr.ch.f0, f1 = pr.ch.f1;
     const size_t F = size_t(std::max(fr->n_frames, 1));
-    const plm::StereoJob *sp = reinterpret_cast<const plm::StereoJob *>(fr->h_tab);
-    const plm::StereoJob *sl = sp + F;
-    const plm::F2FJob *fp = reinterpret_cast<const plm::F2FJob *>(sl + F);
-    const plm::F2FJob *fl = fp + F;
+    const FrameJobs *tab = reinterpret_cast<const FrameJobs *>(fr->h_tab);
     const size_t nf = size_t(f1 - f0);
     if (nf) {
-        CU_TRY(cudaMemcpyAsync(D + fr->o_sjobs_p + f0 * sizeof(plm::StereoJob), sp + f0, nf * sizeof(plm::StereoJob), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(D + fr->o_sjobs_l + f0 * sizeof(plm::StereoJob), sl + f0, nf * sizeof(plm::StereoJob), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(D + fr->o_fjobs_p + f0 * sizeof(plm::F2FJob), fp + f0, nf * sizeof(plm::F2FJob), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(D + fr->o_fjobs_l + f0 * sizeof(plm::F2FJob), fl + f0, nf * sizeof(plm::F2FJob), cudaMemcpyHostToDevice, s));
-        fr->h2d += static_cast<int64_t>(2 * nf * (sizeof(plm::StereoJob) + sizeof(plm::F2FJob)));
+        CU_TRY(cudaMemcpyAsync(D + fr->o_jobs + f0 * sizeof(FrameJobs), tab + f0, nf * sizeof(FrameJobs), cudaMemcpyHostToDevice, s));
+        fr->h2d += static_cast<int64_t>(nf * sizeof(FrameJobs));
     }
     auto copy_spans = [&](FrameSpan *sp_, int n_sp, size_t dev_off, const void *host, size_t elem) -> cudaError_t {
         std::sort(sp_, sp_ + n_sp, [](const FrameSpan &x, const FrameSpan &y) { return x.lo < y.lo; });
@@ -422,23 +416,23 @@ int frames_chunk_run(plm_frames *fr, const plm_frames_chunk &ch, size_t k) {
     CU_TRY(cudaStreamWaitEvent(fr->s_lines, e_fork, 0));
     const int t0 = std::max(ch.f0, 1); // frame 0 has no predecessor
     const bool wide_p = ch.caps_p.warps * 32 == 512;
-    if ((st = wide_p ? launch_stereo<512>(ctx, s, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n, fr->cfg,
+    if ((st = wide_p ? launch_stereo<512>(ctx, s, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[ch.f0].sp, n, fr->cfg,
                                           ch.caps_p, ch.smem_p)
-                     : launch_stereo<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_p) + ch.f0, n,
+                     : launch_stereo<FRAMES_THREADS_P>(ctx, s, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[ch.f0].sp, n,
                                                        fr->cfg, ch.caps_p, ch.smem_p)) != PLM_OK) return st;
     const bool wide_l = ch.caps_l.warps * 32 == FRAMES_THREADS_P;
-    if ((st = wide_l ? launch_stereo<FRAMES_THREADS_P>(ctx, fr->s_lines, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0,
+    if ((st = wide_l ? launch_stereo<FRAMES_THREADS_P>(ctx, fr->s_lines, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[ch.f0].sl,
                                                        n, fr->cfg, ch.caps_l, ch.smem_l)
-                     : launch_stereo<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::StereoJob *>(D + fr->o_sjobs_l) + ch.f0,
+                     : launch_stereo<FRAMES_THREADS_L>(ctx, fr->s_lines, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[ch.f0].sl,
                                                        n, fr->cfg, ch.caps_l, ch.smem_l)) != PLM_OK) return st;
     if (ch.f1 > t0) {
-        if ((st = wide_p ? launch_f2f<512>(ctx, s, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
+        if ((st = wide_p ? launch_f2f<512>(ctx, s, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[t0].fp, ch.f1 - t0,
                                            fr->cfg.best_lr, ch.smem_fp)
-                         : launch_f2f<FRAMES_THREADS_P>(ctx, s, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_p) + t0, ch.f1 - t0,
+                         : launch_f2f<FRAMES_THREADS_P>(ctx, s, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[t0].fp, ch.f1 - t0,
                                                         fr->cfg.best_lr, ch.smem_fp)) != PLM_OK) return st;
-        if ((st = wide_l ? launch_f2f<FRAMES_THREADS_P>(ctx, fr->s_lines, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0,
+        if ((st = wide_l ? launch_f2f<FRAMES_THREADS_P>(ctx, fr->s_lines, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[t0].fl,
                                                         ch.f1 - t0, fr->cfg.best_lr, ch.smem_fl)
-                         : launch_f2f<FRAMES_THREADS_L>(ctx, fr->s_lines, reinterpret_cast<const plm::F2FJob *>(D + fr->o_fjobs_l) + t0,
+                         : launch_f2f<FRAMES_THREADS_L>(ctx, fr->s_lines, &reinterpret_cast<const FrameJobs *>(D + fr->o_jobs)[t0].fl,
                                                         ch.f1 - t0, fr->cfg.best_lr, ch.smem_fl)) != PLM_OK) return st;
     }
     CU_TRY(cudaEventRecord(e_join, fr->s_lines));

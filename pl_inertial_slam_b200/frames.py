@@ -166,18 +166,30 @@ class FramePipeline:
 
 
 def replay_frame_records(rp) -> tuple:
-    """(kp_arena, ln_arena, frame records) for a synth.Replay: keypoint arena = [all left | all right],
-    line arena likewise; descriptor rows as laid out by the generator."""
+    """(kp_arena, ln_arena, frame records) for a synth.Replay.  Keypoints and segments are laid out frame by frame
+    ([left of frame f | right of frame f]), like the descriptor arena of the generator, so that the rows a chunk of
+    consecutive frames needs are ONE contiguous slice of each arena (one host -> device copy per arena and chunk)."""
     F = rp.n_frames
     n_p, n_l = rp.n_pts.astype(np.int64), rp.n_lines.astype(np.int64)
     pbase = np.concatenate([[0], np.cumsum(n_p)])
     lbase = np.concatenate([[0], np.cumsum(n_l)])
-    kp_arena = np.ascontiguousarray(np.concatenate([rp.kp_l, rp.kp_r]), np.float32)
-    ln_arena = np.ascontiguousarray(np.concatenate([rp.ln_l, rp.ln_r]), np.float32)
+    kp_arena = np.empty((2 * int(pbase[-1]), 2), np.float32)
+    ln_arena = np.empty((2 * int(lbase[-1]), 4), np.float32)
     rec = np.zeros(F, L.FRAME_REC_DTYPE)
     rec["desc_pl"], rec["desc_pr"], rec["desc_ll"], rec["desc_lr"] = rp.off_pl, rp.off_pr, rp.off_ll, rp.off_lr
-    rec["kp_l"], rec["kp_r"] = pbase[:-1], pbase[-1] + pbase[:-1]
-    rec["ln_l"], rec["ln_r"] = lbase[:-1], lbase[-1] + lbase[:-1]
+    rec["kp_l"], rec["kp_r"] = 2 * pbase[:-1], 2 * pbase[:-1] + n_p
+    rec["ln_l"], rec["ln_r"] = 2 * lbase[:-1], 2 * lbase[:-1] + n_l
+    # scatter [all left | all right] into the per-frame layout
+    idx_p = np.repeat(pbase[:-1], n_p) if F else np.zeros(0, np.int64)            # first left row of every row's frame
+    within_p = np.arange(int(pbase[-1])) - idx_p
+    dst_p = 2 * idx_p + within_p
+    kp_arena[dst_p] = np.asarray(rp.kp_l, np.float32).reshape(-1, 2)
+    kp_arena[dst_p + np.repeat(n_p, n_p)] = np.asarray(rp.kp_r, np.float32).reshape(-1, 2)
+    idx_l = np.repeat(lbase[:-1], n_l) if F else np.zeros(0, np.int64)
+    within_l = np.arange(int(lbase[-1])) - idx_l
+    dst_l = 2 * idx_l + within_l
+    ln_arena[dst_l] = np.asarray(rp.ln_l, np.float32).reshape(-1, 4)
+    ln_arena[dst_l + np.repeat(n_l, n_l)] = np.asarray(rp.ln_r, np.float32).reshape(-1, 4)
     rec["n_pl"] = rec["n_pr"] = n_p
     rec["n_ll"] = rec["n_lr"] = n_l
     return kp_arena, ln_arena, rec
