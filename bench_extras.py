@@ -175,7 +175,7 @@ def replay_throughput(ctx, n_frames: int, rp=None) -> dict:
     }
 
 
-def replay_pipeline(ctx, n_frames: int, rp=None, chunk: int = 250) -> dict:
+def replay_pipeline(ctx, n_frames: int, rp=None, chunk: int = 320) -> dict:
     """Config 3 through the device-resident frame pipeline (plm_frames_*): raw keypoints / segments /
     descriptors in, per frame the stereo drivers (grid build, matchGrid, gates, compaction, back-projection)
     and the frame-to-frame match on the compacted descriptors; two launches per feature type for the replay."""

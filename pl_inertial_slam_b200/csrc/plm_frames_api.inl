@@ -570,7 +570,7 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
     if (trace) std::fprintf(stderr, "[plm_frames_process] layout done %.3f ms\n", since());
     if (!fr->s_in) CU_TRY(cudaStreamCreateWithFlags(&fr->s_in, cudaStreamNonBlocking));
     if (!fr->s_out) CU_TRY(cudaStreamCreateWithFlags(&fr->s_out, cudaStreamNonBlocking));
-    if (chunk_frames <= 0) chunk_frames = 256;
+    if (chunk_frames <= 0) chunk_frames = 320;
     // everything enqueued earlier on the compute stream (a previous run on the same buffers) comes first
     cudaEvent_t e_start;
     if ((st = fr->event(0, &e_start)) != PLM_OK) return st;
@@ -598,6 +598,8 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
     std::vector<std::thread> helpers;
     for (int i = 0; i < n_helpers; ++i) helpers.emplace_back(worker);
     if (n_helpers == 0) worker();
+    const int out_group = std::max(1, g_frames_out_group);
+    int out_first = 0;
     for (int k = 0; k < n_chunks; ++k) {
         const int f0 = bounds[k], f1 = bounds[k + 1];
         cudaEvent_t e_in, e_run;
@@ -614,7 +616,14 @@ PLM_API int plm_frames_process(plm_frames *fr, const uint8_t *desc_arena, int64_
             st = fail(PLM_E_CUDA, "event record / wait failed");
             break;
         }
-        if ((st = frames_copy_out(fr, out, f0, f1, fr->s_out)) != PLM_OK) break;
+        // copy-out in groups of chunks: every output array is one copy per group (13 fixed copy costs per group); the
+        // last chunks go out one by one so that the tail after the last kernel stays short
+        (void)f0;
+        const int group = (k + 3 >= n_chunks) ? 1 : out_group;
+        if (k + 1 - out_first >= group || k + 1 == n_chunks) {
+            if ((st = frames_copy_out(fr, out, bounds[out_first], f1, fr->s_out)) != PLM_OK) break;
+            out_first = k + 1;
+        }
         if (trace) {
             cudaEvent_t e;
             cudaEventCreate(&e);

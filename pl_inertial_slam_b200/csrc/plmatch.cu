@@ -223,6 +223,7 @@ struct KnnPlan {
 // sits in ~8 cells, so a row holds ~20 slots for ~6 distinct candidates, the slot arrays push the CTA to one
 // per SM and the measured stereo-lines stage is 6x slower than with the chunk phases (profiles/r1_frames.md).
 int g_frames_pairs_per_row[2] = {8, 0};
+int g_frames_out_group = 2;  // plm_frames_process: chunks per device -> host copy group (option "frames_out_group")
 int g_frames_threads_l = 256; // threads per CTA of the line chain of the frame pipeline (128 or 256; measurement knob)
 int g_frames_threads_p = 512; // ... of the point chain (256 or 512)
 int g_grid_cluster = 2; // single matchGrid calls: 2 = row-parallel kernel on one cluster, 1 = chunk kernel on an 8-CTA cluster, 0 = one CTA
@@ -446,6 +447,10 @@ PLM_API int plm_set_option(const char *key, int value) {
     }
     if (std::strcmp(key, "grid_cluster") == 0) {
         g_grid_cluster = std::max(0, std::min(value, 2));
+        return PLM_OK;
+    }
+    if (std::strcmp(key, "frames_out_group") == 0) {
+        g_frames_out_group = std::max(1, std::min(value, 64));
         return PLM_OK;
     }
     if (std::strcmp(key, "frames_threads_l") == 0) {

@@ -109,7 +109,7 @@ class FramePipeline:
         self.NP, self.NL = int(self.off_p[-1]), int(self.off_l[-1])
 
     def process(self, desc_arena, kp_arena, ln_arena, frames: np.ndarray, cfg: FrameConfig,
-                out: Optional[Dict[str, np.ndarray]] = None, chunk_frames: int = 256) -> Dict[str, np.ndarray]:
+                out: Optional[Dict[str, np.ndarray]] = None, chunk_frames: int = 320) -> Dict[str, np.ndarray]:
         """upload + run + fetch as one chunk-pipelined call (plm_frames_process)."""
         assert frames.dtype == L.FRAME_REC_DTYPE
         frames = np.ascontiguousarray(frames)
