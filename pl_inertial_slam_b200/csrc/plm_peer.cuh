@@ -185,8 +185,11 @@ template <int OP> __global__ void __launch_bounds__(PEER_THREADS) peer_reduce_ke
 //        [parity][my rank];
 // signal the LAST block of the grid to finish pushing (device-scope counter) raises flag [parity][my rank] = epoch on
 //        every rank;
-// wait   every block waits for the G flags of the own buffer (bounded spin) -- they depend only on the other ranks'
-//        own pushes, never on this grid, so there is no circular wait;
+// wait   every block waits for the G flags of the own buffer (bounded spin).  G - 1 of them depend only on the other
+//        ranks' pushes; the flag of the OWN rank is raised by the last block of THIS grid, so every block of the grid
+//        must be resident at the same time: the host launches at most one block per SM (plm_dev_peer_allgather_i32),
+//        which holds as long as nothing else occupies whole SMs for longer than the spin limit (then: PLM_E_PEER, never
+//        a silent result);
 // copy   grid-stride copy of the assembled vector into the caller's output, block 0 sums the G counts.
 struct PeerGatherArgs {
     unsigned char *peer[PEER_MAX_RANKS];
