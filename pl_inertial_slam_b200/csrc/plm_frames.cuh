@@ -412,6 +412,10 @@ f2f_match_kernel(const F2FJob *__restrict__ jobs, const size_t job_stride, int b
     }
     if (tid == 0) s_count = 0;
     __syncthreads();
+    // 13-LOP3 distance (plm_common.cuh): the staged train rows and every query go through the same GF(2)-linear
+    // transform once; the xor of two transformed descriptors already holds the first carry-save level
+    for (int r = tid; r < n2; r += THREADS) desc_transform13(sd2[2 * r], sd2[2 * r + 1]);
+    __syncthreads();
 
     int accepted = 0;
     for (int rb = 0; rb < n1; rb += THREADS) {
@@ -425,6 +429,7 @@ f2f_match_kernel(const F2FJob *__restrict__ jobs, const size_t job_stride, int b
             a.lo = make_uint4(0, 0, 0, 0);
             a.hi = a.lo;
         }
+        desc_transform13(a.lo, a.hi);
         const uint32_t ck_add = valid ? static_cast<uint32_t>(i1) : (F2F_INVALID | static_cast<uint32_t>(i1));
         uint32_t b0 = KEY32_ABSENT, b1 = KEY32_ABSENT; // row top-2: (d << 22 | i2)
         int j = 0;
@@ -432,7 +437,7 @@ f2f_match_kernel(const F2FJob *__restrict__ jobs, const size_t job_stride, int b
             uint32_t ck[4], m0[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const uint32_t dk = static_cast<uint32_t>(hamming256_csa(a, sd2[2 * (j + v)], sd2[2 * (j + v) + 1])) << F2F_KEY_BITS;
+                const uint32_t dk = static_cast<uint32_t>(hamming256_t13(a, sd2[2 * (j + v)], sd2[2 * (j + v) + 1])) << F2F_KEY_BITS;
                 top2_insert(b0, b1, dk + static_cast<uint32_t>(j + v));
                 ck[v] = dk + ck_add;
             }
@@ -457,7 +462,7 @@ f2f_match_kernel(const F2FJob *__restrict__ jobs, const size_t job_stride, int b
             }
         }
         for (; j < n2; ++j) {
-            const uint32_t dk = static_cast<uint32_t>(hamming256_csa(a, sd2[2 * j], sd2[2 * j + 1])) << F2F_KEY_BITS;
+            const uint32_t dk = static_cast<uint32_t>(hamming256_t13(a, sd2[2 * j], sd2[2 * j + 1])) << F2F_KEY_BITS;
             top2_insert(b0, b1, dk + static_cast<uint32_t>(j));
             if (best_lr) {
                 const uint32_t ck = dk + ck_add;
