@@ -600,15 +600,25 @@ int plm_dev_bow_score(plm_ctx *ctx, const uint32_t *q_ids_dev, const double *q_v
                       const double *db_vals_dev, const int64_t *db_start_dev, const int32_t *db_len_dev, int n_db,
                       double *scores_dev);
 
-/* Tuning knobs (measurement only; results never depend on them):
- *   "knn_variant"  -1 = automatic (default), 0 = plain 8-POPC Hamming, 1 = carry-save 5-POPC,
- *                  2 = carry-save 4-POPC with blocked top-2 update.
- *   "grid_cluster" 1 = single matchGrid calls run on an 8-CTA thread-block cluster (default),
- *                  0 = on one CTA.
+/* Tuning knobs (measurement / A-B tests only; results never depend on them):
+ *   "knn_variant"  -1 = automatic (default: 3 for train sets >= 65 536 rows, 5 for short train sides with >= 2^26 pairs,
+ *                  else 1), 0 = plain 8-POPC Hamming, 1 = carry-save 5-POPC, 2 = carry-save 4-POPC with blocked top-2
+ *                  update, 3 = 13-LOP3 / 4-POPC in the transformed domain (blocked update), 4 = 3 with three lower-bound
+ *                  rows per block, 5 = 13-LOP3 with the per-pair update.
+ *   "knn_qpt"      2 = long scans with >= 4096 queries keep two queries per thread (default 1).
+ *   "knn_fill"     0 = do not fill the last resident CTA slots / share the second-best bound (default 1).
+ *   "frame_fused"  1 = frame sessions and stand-alone frame-sized calls run as ONE launch (frame_fused_kernel, default),
+ *                  0 = one lane of copies + kernels per call.
+ *   "grid_cluster" single matchGrid calls outside the one-launch path: 2 = row-parallel kernel on one 8-CTA thread-block
+ *                  cluster (default), 1 = chunk phases on a cluster, 0 = one CTA.
+ *   "grid_rows"    1 = map-sized matchGrid uses the row-parallel kernels (default), 0 = warp-per-chunk kernels.
+ *   "grid_head"    1 = short CTAs at the start of the map (default), 0 = uniform rows per CTA.
+ *   "frames_out_group"  chunks per device -> host copy group of plm_frames_process (default 2).
  *   "frames_threads_p" / "frames_threads_l"  CTA width of the frame pipeline's point chain (256 or 512, default 512)
  *                  and line chain (128 or 256, default 256).
  *   "frames_pairs_p" / "frames_pairs_l"  candidate slots per query row the frame pipeline's pair-list
- *                  matcher is sized for (default 8 / 0; 0 = always use the chunk phases). */
+ *                  matcher is sized for (default 8 / 0; 0 = always use the chunk phases).
+ *   "peer_spin_ms" bounded spin of the peer-memory kernels in milliseconds (default ~2000). */
 int plm_set_option(const char *key, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
