@@ -291,6 +291,8 @@ KnnPlan plan_knn(plm_ctx *ctx, int n1, long long n2, bool allow_two = false) {
     KnnPlan p;
     p.threads = (n1 >= 4096) ? 128 : 64;
     int variant = knn_variant_for(n2 >= 65536 ? 4096 : 64);
+    // a short train side with a lot of work is launched with variant 5 (launch_knn_slices): plan the workers for it
+    if (variant == 1 && g_knn_variant < 0 && n2 >= 64 && static_cast<long long>(n1) * n2 >= (1ll << 26)) variant = 5;
     // long scans with many queries: two queries per thread (variant 6), single-direction launches only
     if (allow_two && variant == 3 && g_knn_qpt == 2 && p.threads == 128) variant = 6;
     p.qpb = (variant == 6) ? 2 * p.threads : p.threads;
