@@ -330,7 +330,7 @@ int launch_knn_slices(plm_ctx *ctx, plm::KnnTaskPair &tp, int n_tasks, int threa
     int variant = knn_variant_for(min_rows >= 65536 ? 4096 : 64);
     if (variant == 1 && g_knn_variant < 0 && min_rows >= 64) {
         // a short train side but a lot of work (the match fallback of the local map, 200 000 x 600 in both directions):
-        // the 13-LOP3 distance with the per-pair update (variant 5) -- a few per cent there (0.369 -> 0.358 ms; 0.335 ms when the plan is made for it too); frame-sized calls keep
+        // the 13-LOP3 distance with the per-pair update (variant 5) -- a few per cent there (0.369 -> 0.356 ms, plan_knn sizes the workers for it); frame-sized calls keep
         // variant 1, whose stages need no in-place transform
         long long pairs = 0;
         for (int i = 0; i < n_tasks; ++i) pairs = std::max(pairs, static_cast<long long>(tp.t[i].n1) * tp.t[i].n2);
